@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the SLR hot path on B200 next to the reference's CPU path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+
+One "step" = one pass of the hot path over one batch of synthetic input. Prints ONE JSON line
+(rank 0). See DESIGN.md "Measurement" for the definition of every field.
+
+Workloads
+  intersect   incoherent-ray closest-hit microbench (BASELINE.json configs[4] at a single-GPU size):
+              heightfield triangle mesh -> host SBVH -> QBVH, random rays; metric Mrays/s.
+  (the path-tracing workloads are added by slr_b200/render_bench.py when the renderer is built)
+
+Timing: CUDA events on the launching stream, W >= 3 warm-up steps, barrier + synchronize on both
+sides, max over ranks. The ray batch (>= 512 MB of SoA inputs+outputs per step at the default size)
+is larger than L2 (126 MB), so no explicit L2 flush is needed between steps; config says so.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (B200_PROFILING.md "clocks line")
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------------------
+# intersect workload
+# --------------------------------------------------------------------------------------------------
+def intersect_inputs(args, rank):
+    from slr_b200 import synth
+    pos, idx = synth.heightfield(args.grid)
+    rays = synth.random_rays(args.rays, pos.min(0), pos.max(0), seed=12345 + 1000 * rank)
+    return pos, idx, rays
+
+
+def workload_name(args):
+    return (f"intersect: {args.rays} incoherent rays vs {2 * args.grid * args.grid}-triangle heightfield "
+            f"(host SBVH->QBVH), closest hit")
+
+
+def run_intersect_gpu(args, rank, world, dist):
+    import torch
+    from slr_b200 import capi
+    import oracle_util as ou
+
+    dev = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(dev)
+    pos, idx, rays = intersect_inputs(args, rank)
+    hs = ou.build_host_scene([(pos, idx)], [(0, 0, None)])
+    gs = capi.GpuScene(hs, device=dev)
+    n = args.rays
+    keys = ("ox", "oy", "oz", "dx", "dy", "dz", "tmin", "tmax")
+
+    # ---- device-resident inputs (the `value` leg)
+    host_pinned = {k: torch.from_numpy(np.ascontiguousarray(rays[k])).pin_memory() for k in keys}
+    d_in = {k: host_pinned[k].cuda(non_blocking=True) for k in keys}
+    d_prim = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_inst = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_t = torch.empty(n, dtype=torch.float32, device="cuda")
+    d_nodes = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_tris = torch.empty(n, dtype=torch.int32, device="cuda")
+    rb = capi.RayBatch(*[C.cast(d_in[k].data_ptr(), capi.PF) for k in keys])
+    hb = capi.HitBatch(C.cast(d_prim.data_ptr(), capi.PU32), C.cast(d_inst.data_ptr(), capi.PU32),
+                       C.cast(d_t.data_ptr(), capi.PF), None, None, None, None)
+    hb_cnt = capi.HitBatch(C.cast(d_prim.data_ptr(), capi.PU32), C.cast(d_inst.data_ptr(), capi.PU32),
+                           C.cast(d_t.data_ptr(), capi.PF), None, None,
+                           C.cast(d_nodes.data_ptr(), capi.PU32), C.cast(d_tris.data_ptr(), capi.PU32))
+    stream = torch.cuda.current_stream()
+
+    def launch(h):
+        rc = capi.gpu.slrgpu_intersect_batch_device(gs.handle, C.byref(rb), n, C.byref(h), C.c_void_p(stream.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(capi.gpu.slrgpu_last_error().decode())
+
+    # algorithmic bytes per ray, counted by the oracle-order traversal (one counting launch, untimed)
+    launch(hb_cnt)
+    torch.cuda.synchronize()
+    tot_nodes = int(d_nodes.to(torch.int64).sum().item())
+    tot_tris = int(d_tris.to(torch.int64).sum().item())
+    hit_rate = float((d_prim != -1).float().mean().item())
+    algo_bytes = 32 * n + 128 * tot_nodes + 48 * tot_tris + 16 * n
+
+    for _ in range(args.warmup):
+        launch(hb)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev) as clocks:
+        e0.record(stream)
+        for _ in range(args.steps):
+            launch(hb)
+        e1.record(stream)
+        torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+
+    # ---- end to end through the host-buffer C-ABI call (H2D + kernel + D2H inside the timed region)
+    comps = [np.ascontiguousarray(rays[k], np.float32) for k in keys]
+    rb_h = capi.RayBatch(*[c.ctypes.data_as(capi.PF) for c in comps])
+    o_prim, o_inst, o_t = np.empty(n, np.uint32), np.empty(n, np.uint32), np.empty(n, np.float32)
+    hb_h = capi.HitBatch(o_prim.ctypes.data_as(capi.PU32), o_inst.ctypes.data_as(capi.PU32), o_t.ctypes.data_as(capi.PF),
+                         None, None, None, None)
+    e2e_steps = max(1, min(args.steps, 3))
+    capi.gpu.slrgpu_intersect_batch(gs.handle, C.byref(rb_h), n, C.byref(hb_h), None)   # warm
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rc = capi.gpu.slrgpu_intersect_batch(gs.handle, C.byref(rb_h), n, C.byref(hb_h), None)
+        assert rc == 0, capi.gpu.slrgpu_last_error()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+
+    return {"ms_total": ms, "units": n * args.steps, "algo_bytes_per_launch": algo_bytes, "launches": args.steps,
+            "nodes_per_ray": tot_nodes / n, "tris_per_ray": tot_tris / n, "hit_rate": hit_rate,
+            "clocks": clocks.summary(), "e2e_units_per_s": n / e2e_s, "h2d": 32 * n, "d2h": 12 * n,
+            "scene_bytes": gs.device_bytes, "host_scene": hs, "rays": rays, "build_s": hs.build_seconds}
+
+
+def cpu_baseline_intersect(args, sample_rays, kind_pref="reference"):
+    """The reference's own QBVH::intersect on the box's host cores (oracle/_ref/ref_intersect) on a
+    bounded sample of the same workload; falls back to the scalar restatement (1 core)."""
+    import oracle_util as ou
+    from slr_b200 import synth
+    pos, idx = synth.heightfield(args.grid)
+    rays = synth.random_rays(sample_rays, pos.min(0), pos.max(0), seed=12345)
+    if kind_pref == "reference" and ou.have_ref():
+        _, _, info = ou.run_ref_intersect([(pos, idx)], [(0, 0, None)], rays, want_trees=False)
+        best = min(info["qbvh_1t_s"], info["qbvh_nt_s"])
+        cores = 1 if info["qbvh_1t_s"] <= info["qbvh_nt_s"] else info["threads"]
+        return {"value": sample_rays / best / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference",
+                "sample": f"{sample_rays} rays of the same batch through QBVH::intersect; best of 1 thread "
+                          f"({sample_rays / info['qbvh_1t_s'] / 1e6:.3f}) and {info['threads']} threads "
+                          f"({sample_rays / info['qbvh_nt_s'] / 1e6:.3f} Mrays/s)",
+                "threads_available": info["threads"]}
+    hs = ou.build_host_scene([(pos, idx)], [(0, 0, None)])
+    t0 = time.perf_counter()
+    ou.restate_intersect(hs, rays)
+    dt = time.perf_counter() - t0
+    return {"value": sample_rays / dt / 1e6, "unit": "Mrays/s", "cores": 1, "kind": "port",
+            "sample": f"{sample_rays} rays of the same batch through the scalar C restatement"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--grid", type=int, default=500, help="heightfield resolution (2*grid^2 triangles)")
+    ap.add_argument("--rays", type=int, default=16 * 1024 * 1024)
+    ap.add_argument("--cpu-sample", type=int, default=2_000_000)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+
+    try:
+        from slr_b200 import render_bench      # present once the renderer is built
+    except ImportError:
+        render_bench = None
+    if args.workload is None:
+        args.workload = "cornell_spheres" if render_bench is not None else "intersect"
+    if args.workload != "intersect":
+        if render_bench is None:
+            raise SystemExit(f"workload {args.workload} needs the renderer")
+        return render_bench.main(args, rank, world)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        t0 = time.perf_counter()
+        vals = []
+        for _ in range(max(1, args.steps)):
+            vals.append(cpu_baseline_intersect(args, args.cpu_sample))
+        best = max(vals, key=lambda v: v["value"])
+        wall = time.perf_counter() - t0
+        line = {"impl": "reference", "metric": "Mrays/s (closest-hit, incoherent rays)", "value": best["value"],
+                "unit": "Mrays/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(args)}, "cpu_baseline": best,
+                "e2e": {"value": best["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl")
+    r = run_intersect_gpu(args, rank, world, dist)
+    ms = r["ms_total"]
+    e2e = r["e2e_units_per_s"]
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms, 1.0 / e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e = float(t[0]), 1.0 / float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    value = r["units"] * world / (ms * 1e-3) / 1e6
+    ach = r["algo_bytes_per_launch"] / (ms * 1e-3 / r["launches"]) / 1e9
+    cpu = cpu_baseline_intersect(args, args.cpu_sample)
+    line = {"metric": "Mrays/s (closest-hit, incoherent rays)", "value": value, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "rays_per_gpu_per_step": args.rays,
+                       "triangles": 2 * args.grid * args.grid, "hit_rate": round(r["hit_rate"], 4),
+                       "nodes_per_ray": round(r["nodes_per_ray"], 3), "tris_per_ray": round(r["tris_per_ray"], 3),
+                       "l2_policy": "inputs larger than L2 (ray SoA + results >= 44 B/ray x rays)",
+                       "scene_bytes": int(r["scene_bytes"]), "host_bvh_build_s": round(r["build_s"], 2)},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "kernel": "intersectBatchKernel", "peak_source": peak_src,
+                         "algorithmic_bytes_per_ray": r["algo_bytes_per_launch"] / args.rays},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e * world / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+            "gpu_launches": args.steps, "clocks": r["clocks"]}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

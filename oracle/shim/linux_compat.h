@@ -1,0 +1,22 @@
+// Force-included (-include) when compiling the untouched reference on Linux.
+// libSLR/defines.h:105-108 leaves SLR_memalign / SLR_freealign undefined on Linux; this repairs
+// them through posix_memalign without editing the reference. Test infrastructure only.
+#pragma once
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <cfloat>
+#include <libSLR/defines.h>
+#undef SLR_memalign
+#undef SLR_freealign
+static inline void* slr_oracle_memalign(size_t size, size_t alignment) {
+    void* p = nullptr;
+    if (alignment < sizeof(void*)) alignment = sizeof(void*);
+    if (posix_memalign(&p, alignment, size)) p = nullptr;
+    return p;
+}
+#define SLR_memalign(size, alignment) slr_oracle_memalign(size, alignment)
+#define SLR_freealign(ptr) ::free(ptr)
+#ifndef SLR_alignof
+#define SLR_alignof(T) alignof(T)
+#endif

@@ -1,0 +1,367 @@
+"""ctypes bindings of include/slrgpu.h and include/slrhost.h.
+
+Mirrors the C structs field for field; ``check_abi()`` compares every ``ctypes.sizeof`` with the
+library's ``slrgpu_struct_size`` so a drifted mirror fails loudly instead of corrupting memory.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
+INVALID_ID = 0xFFFFFFFF
+
+c_f = C.c_float
+c_u32 = C.c_uint32
+c_u64 = C.c_uint64
+PF = C.POINTER(c_f)
+PU32 = C.POINTER(c_u32)
+PU8 = C.POINTER(C.c_uint8)
+
+
+class BvhNode(C.Structure):
+    _fields_ = [("lo_x", c_f * 4), ("lo_y", c_f * 4), ("lo_z", c_f * 4),
+                ("hi_x", c_f * 4), ("hi_y", c_f * 4), ("hi_z", c_f * 4),
+                ("child", c_u32 * 4), ("top_axis", C.c_uint8), ("left_axis", C.c_uint8),
+                ("right_axis", C.c_uint8), ("pad0", C.c_uint8), ("pad", c_u32 * 3)]
+
+
+class LeafRecord(C.Structure):
+    _fields_ = [("a", c_f * 4), ("b", c_f * 4), ("c", c_f * 4)]
+
+
+class Instance(C.Structure):
+    _fields_ = [("mat", c_f * 16), ("mat_inv", c_f * 16), ("root_node", c_u32),
+                ("light_base", c_u32), ("num_lights", c_u32), ("pad", c_u32)]
+
+
+class Triangle(C.Structure):
+    _fields_ = [("v", c_u32 * 3), ("material", c_u32), ("normal_map", c_u32), ("alpha_map", c_u32),
+                ("light_index", c_u32), ("pad", c_u32)]
+
+
+class Vertex(C.Structure):
+    _fields_ = [("position", c_f * 3), ("u", c_f), ("normal", c_f * 3), ("v", c_f),
+                ("tangent", c_f * 3), ("pad", c_f)]
+
+
+class Spectrum(C.Structure):
+    _fields_ = [("kind", c_u32), ("data_offset", c_u32), ("num_samples", c_u32),
+                ("p0", c_f), ("p1", c_f), ("p2", c_f), ("pad", c_u32 * 2)]
+
+
+class Texture(C.Structure):
+    _fields_ = [("kind", c_u32), ("mapping", c_u32), ("i0", c_u32), ("i1", c_u32),
+                ("f0", c_f), ("f1", c_f), ("f2", c_f), ("f3", c_f),
+                ("map_offset", c_f * 2), ("map_scale", c_f * 2)]
+
+
+class Image(C.Structure):
+    _fields_ = [("format", c_u32), ("width", c_u32), ("height", c_u32), ("pad", c_u32),
+                ("data_offset", c_u64), ("spectrum_type", c_u32), ("pad1", c_u32)]
+
+
+class Material(C.Structure):
+    _fields_ = [("kind", c_u32), ("tex", c_u32 * 4), ("sub", c_u32 * 2), ("f0", c_f)]
+
+
+class Light(C.Structure):
+    _fields_ = [("object", c_u32), ("importance", c_f)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("mat", c_f * 16), ("mat_inv", c_f * 16), ("sensitivity", c_f), ("aspect", c_f),
+                ("fov_y", c_f), ("lens_radius", c_f), ("img_plane_dist", c_f), ("obj_plane_dist", c_f),
+                ("pad", c_f * 2)]
+
+
+class Environment(C.Structure):
+    _fields_ = [("present", c_u32), ("material", c_u32), ("map_width", c_u32), ("map_height", c_u32),
+                ("row_pdf", PF), ("row_cdf", PF), ("row_integral", PF), ("marginal_pdf", PF),
+                ("marginal_cdf", PF), ("marginal_integral", c_f), ("pad", c_f)]
+
+
+class SpectralTables(C.Structure):
+    _fields_ = [("upsample_grid", PF), ("upsample_grid_floats", c_u32),
+                ("upsample_points", PF), ("upsample_points_floats", c_u32),
+                ("xbar_16", PF), ("ybar_16", PF), ("zbar_16", PF), ("integral_cmf", c_f), ("pad", c_f)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("struct_size", c_u32), ("rgb_mode", c_u32),
+                ("bvh_nodes", C.POINTER(BvhNode)), ("num_bvh_nodes", c_u32),
+                ("leaf_records", C.POINTER(LeafRecord)), ("num_leaf_records", c_u32),
+                ("instances", C.POINTER(Instance)), ("num_instances", c_u32),
+                ("triangles", C.POINTER(Triangle)), ("num_triangles", c_u32),
+                ("vertices", C.POINTER(Vertex)), ("num_vertices", c_u32),
+                ("materials", C.POINTER(Material)), ("num_materials", c_u32),
+                ("textures", C.POINTER(Texture)), ("num_textures", c_u32),
+                ("spectra", C.POINTER(Spectrum)), ("num_spectra", c_u32),
+                ("spectrum_data", PF), ("num_spectrum_floats", c_u32),
+                ("images", C.POINTER(Image)), ("num_images", c_u32),
+                ("image_data", PU8), ("image_data_bytes", c_u64),
+                ("lights", C.POINTER(Light)), ("num_lights", c_u32),
+                ("num_top_lights", c_u32), ("pad0", c_u32),
+                ("world_center", c_f * 3), ("world_radius", c_f),
+                ("camera", Camera), ("environment", Environment), ("spectral", SpectralTables)]
+
+
+class RayBatch(C.Structure):
+    _fields_ = [(n, PF) for n in ("org_x", "org_y", "org_z", "dir_x", "dir_y", "dir_z", "tmin", "tmax")]
+
+
+class HitBatch(C.Structure):
+    _fields_ = [("prim", PU32), ("inst", PU32), ("t", PF), ("u", PF), ("v", PF),
+                ("nodes_visited", PU32), ("tris_tested", PU32)]
+
+
+class RenderParams(C.Structure):
+    _fields_ = [("struct_size", c_u32), ("width", c_u32), ("height", c_u32),
+                ("spp_begin", c_u32), ("spp_end", c_u32), ("time_start", c_f), ("time_end", c_f),
+                ("rng_seed", C.c_int32), ("max_path_length", c_u32), ("pool_size", c_u32), ("flags", c_u32)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("paths", c_u64), ("rays", c_u64), ("extend_rays", c_u64), ("shadow_rays", c_u64),
+                ("kernel_launches", c_u64), ("device_ms", c_f), ("extend_ms", c_f), ("shade_ms", c_f),
+                ("shadow_ms", c_f), ("other_ms", c_f)]
+
+
+_ABI_STRUCTS = [SceneDesc, BvhNode, LeafRecord, Instance, Triangle, Vertex, Spectrum, Texture, Image,
+                Material, Light, Camera, Environment, SpectralTables, RayBatch, HitBatch, RenderParams,
+                RenderStats]
+
+RENDER_PROFILE_STAGES = 0x1
+
+
+def _load(name):
+    path = os.path.join(_LIBDIR, name)
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} is missing: build the native libraries first (python -c 'import __graft_entry__ as g; g.build()'). "
+            "There is no Python/CPU fallback for the SLR hot path.")
+    return C.CDLL(path, mode=C.RTLD_GLOBAL)
+
+
+gpu = _load("libslrgpu.so")
+host = _load("libslrhost.so")
+
+# ---- slrgpu.h prototypes
+gpu.slrgpu_device_count.restype = C.c_int
+gpu.slrgpu_abi_version.restype = c_u32
+gpu.slrgpu_last_error.restype = C.c_char_p
+gpu.slrgpu_struct_size.restype = c_u32
+gpu.slrgpu_struct_size.argtypes = [C.c_int]
+gpu.slrgpu_scene_create.restype = C.c_int
+gpu.slrgpu_scene_create.argtypes = [C.POINTER(SceneDesc), C.c_int, C.POINTER(C.c_void_p)]
+gpu.slrgpu_scene_destroy.restype = None
+gpu.slrgpu_scene_destroy.argtypes = [C.c_void_p]
+gpu.slrgpu_scene_device_bytes.restype = c_u64
+gpu.slrgpu_scene_device_bytes.argtypes = [C.c_void_p]
+gpu.slrgpu_scene_channels.restype = c_u32
+gpu.slrgpu_scene_channels.argtypes = [C.c_void_p]
+gpu.slrgpu_intersect_batch.restype = C.c_int
+gpu.slrgpu_intersect_batch.argtypes = [C.c_void_p, C.POINTER(RayBatch), c_u64, C.POINTER(HitBatch), PF]
+gpu.slrgpu_intersect_batch_device.restype = C.c_int
+gpu.slrgpu_intersect_batch_device.argtypes = [C.c_void_p, C.POINTER(RayBatch), c_u64, C.POINTER(HitBatch), C.c_void_p]
+gpu.slrgpu_intersect_launch_config.restype = C.c_int
+gpu.slrgpu_intersect_launch_config.argtypes = [C.c_void_p, c_u64, PU32, PU32]
+gpu.slrgpu_occluded_batch.restype = C.c_int
+gpu.slrgpu_occluded_batch.argtypes = [C.c_void_p, C.POINTER(RayBatch), c_u64, PU8, PF]
+
+# ---- slrhost.h prototypes
+host.slrhost_last_error.restype = C.c_char_p
+host.slrhost_builder_create.restype = C.c_void_p
+host.slrhost_builder_destroy.argtypes = [C.c_void_p]
+host.slrhost_builder_destroy.restype = None
+host.slrhost_builder_add_mesh.restype = C.c_int
+host.slrhost_builder_add_mesh.argtypes = [C.c_void_p, PF, PF, PF, PF, c_u32, PU32, c_u32]
+host.slrhost_builder_place_mesh.restype = C.c_int
+host.slrhost_builder_place_mesh.argtypes = [C.c_void_p, C.c_int, PF]
+host.slrhost_builder_instance_mesh.restype = C.c_int
+host.slrhost_builder_instance_mesh.argtypes = [C.c_void_p, C.c_int, PF]
+host.slrhost_builder_finish.restype = C.c_int
+host.slrhost_builder_finish.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+host.slrhost_scene_destroy.restype = None
+host.slrhost_scene_destroy.argtypes = [C.c_void_p]
+host.slrhost_scene_describe.restype = C.c_int
+host.slrhost_scene_describe.argtypes = [C.c_void_p, C.POINTER(SceneDesc)]
+host.slrhost_scene_stats.restype = C.c_int
+host.slrhost_scene_stats.argtypes = [C.c_void_p, c_u32, C.POINTER(C.c_double)]
+host.slrhost_scene_build_seconds.restype = C.c_double
+host.slrhost_scene_build_seconds.argtypes = [C.c_void_p]
+
+
+class SlrError(RuntimeError):
+    pass
+
+
+def check_abi():
+    """Every ctypes mirror must have the size the library was compiled with."""
+    for i, s in enumerate(_ABI_STRUCTS):
+        want = gpu.slrgpu_struct_size(i)
+        if want != C.sizeof(s):
+            raise SlrError(f"ABI mismatch: {s.__name__} is {C.sizeof(s)} bytes in ctypes, {want} in libslrgpu.so")
+    return True
+
+
+def _gpu_check(rc, what):
+    if rc != 0:
+        raise SlrError(f"{what} failed ({rc}): {gpu.slrgpu_last_error().decode()}")
+
+
+def _host_check(rc, what):
+    if rc < 0:
+        raise SlrError(f"{what} failed: {host.slrhost_last_error().decode()}")
+    return rc
+
+
+def _pf(a):
+    return a.ctypes.data_as(PF) if a is not None else None
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class HostScene:
+    """A flattened scene owned by libslrhost (SoA buffers + build statistics)."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+        self.desc = SceneDesc()
+        _host_check(host.slrhost_scene_describe(self._h, C.byref(self.desc)), "slrhost_scene_describe")
+
+    def close(self):
+        if self._h:
+            host.slrhost_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def stats(self):
+        out = []
+        buf = (C.c_double * 10)()
+        n = _host_check(host.slrhost_scene_stats(self._h, 0, buf), "slrhost_scene_stats")
+        keys = ["numObjects", "sbvhNodes", "sbvhRefs", "sbvhDepth", "qbvhNodes", "qbvhDepth", "nodeBase", "leafBase",
+                "sbvhCost", "qbvhCost"]
+        for a in range(n):
+            host.slrhost_scene_stats(self._h, a, buf)
+            out.append({k: (buf[i] if i >= 8 else int(buf[i])) for i, k in enumerate(keys)})
+        return out
+
+    @property
+    def build_seconds(self):
+        return host.slrhost_scene_build_seconds(self._h)
+
+    def nodes_array(self):
+        """numpy view (copy) of the flattened QBVH nodes as a structured (n, 32) uint32 array."""
+        n = self.desc.num_bvh_nodes
+        return np.ctypeslib.as_array(C.cast(self.desc.bvh_nodes, PU32), shape=(n, 32)).copy()
+
+    def leaves_array(self):
+        n = self.desc.num_leaf_records
+        return np.ctypeslib.as_array(C.cast(self.desc.leaf_records, PU32), shape=(n, 12)).copy()
+
+
+class SceneBuilder:
+    """Programmatic scene graph (the subset of the scene language's builtins needed for geometry)."""
+
+    def __init__(self):
+        self._b = C.c_void_p(host.slrhost_builder_create())
+        if not self._b:
+            raise SlrError("slrhost_builder_create failed")
+
+    def close(self):
+        if self._b:
+            host.slrhost_builder_destroy(self._b)
+            self._b = None
+
+    def __del__(self):
+        self.close()
+
+    def add_mesh(self, positions, indices, normals=None, tangents=None, uvs=None):
+        pos = _f32(positions).reshape(-1, 3)
+        idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
+        nrm = _f32(normals).reshape(-1, 3) if normals is not None else None
+        tng = _f32(tangents).reshape(-1, 3) if tangents is not None else None
+        uv = _f32(uvs).reshape(-1, 2) if uvs is not None else None
+        return _host_check(host.slrhost_builder_add_mesh(self._b, _pf(pos), _pf(nrm), _pf(tng), _pf(uv), pos.shape[0],
+                                                          idx.ctypes.data_as(PU32), idx.shape[0]), "slrhost_builder_add_mesh")
+
+    @staticmethod
+    def _mat(m):
+        if m is None:
+            return None, None
+        a = _f32(np.asarray(m, dtype=np.float32).T.reshape(16))  # numpy row-major 4x4 -> column-major floats
+        return a, _pf(a)
+
+    def place_mesh(self, mesh, matrix=None):
+        keep, p = self._mat(matrix)
+        _host_check(host.slrhost_builder_place_mesh(self._b, mesh, p), "slrhost_builder_place_mesh")
+
+    def instance_mesh(self, mesh, matrix=None):
+        keep, p = self._mat(matrix)
+        _host_check(host.slrhost_builder_instance_mesh(self._b, mesh, p), "slrhost_builder_instance_mesh")
+
+    def finish(self, rgb_mode=False):
+        out = C.c_void_p()
+        _host_check(host.slrhost_builder_finish(self._b, 1 if rgb_mode else 0, C.byref(out)), "slrhost_builder_finish")
+        return HostScene(out.value)
+
+
+class GpuScene:
+    """A scene resident in HBM (slrgpu_scene_create)."""
+
+    def __init__(self, host_scene, device=0):
+        self._host = host_scene            # keeps the SoA buffers alive
+        self._s = C.c_void_p()
+        _gpu_check(gpu.slrgpu_scene_create(C.byref(host_scene.desc), device, C.byref(self._s)), "slrgpu_scene_create")
+
+    def close(self):
+        if self._s:
+            gpu.slrgpu_scene_destroy(self._s)
+            self._s = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._s
+
+    @property
+    def device_bytes(self):
+        return gpu.slrgpu_scene_device_bytes(self._s)
+
+    def intersect(self, rays, counters=False):
+        """rays: dict of 8 float32 arrays (ox oy oz dx dy dz tmin tmax). Returns dict of result arrays."""
+        comps = [_f32(rays[k]) for k in ("ox", "oy", "oz", "dx", "dy", "dz", "tmin", "tmax")]
+        n = comps[0].shape[0]
+        rb = RayBatch(*[_pf(c) for c in comps])
+        out = {"prim": np.empty(n, np.uint32), "inst": np.empty(n, np.uint32), "t": np.empty(n, np.float32),
+               "u": np.empty(n, np.float32), "v": np.empty(n, np.float32)}
+        hb = HitBatch(out["prim"].ctypes.data_as(PU32), out["inst"].ctypes.data_as(PU32), _pf(out["t"]), _pf(out["u"]),
+                      _pf(out["v"]), None, None)
+        if counters:
+            out["nodes"] = np.empty(n, np.uint32)
+            out["tris"] = np.empty(n, np.uint32)
+            hb.nodes_visited = out["nodes"].ctypes.data_as(PU32)
+            hb.tris_tested = out["tris"].ctypes.data_as(PU32)
+        ms = c_f(0)
+        _gpu_check(gpu.slrgpu_intersect_batch(self._s, C.byref(rb), n, C.byref(hb), C.byref(ms)), "slrgpu_intersect_batch")
+        out["kernel_ms"] = ms.value
+        return out
+
+    def occluded(self, rays):
+        comps = [_f32(rays[k]) for k in ("ox", "oy", "oz", "dx", "dy", "dz", "tmin", "tmax")]
+        n = comps[0].shape[0]
+        rb = RayBatch(*[_pf(c) for c in comps])
+        occ = np.empty(n, np.uint8)
+        ms = c_f(0)
+        _gpu_check(gpu.slrgpu_occluded_batch(self._s, C.byref(rb), n, occ.ctypes.data_as(PU8), C.byref(ms)), "slrgpu_occluded_batch")
+        return occ, ms.value

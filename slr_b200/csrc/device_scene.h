@@ -1,0 +1,64 @@
+// Device-side view of an uploaded scene (pointers into HBM) shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/slrgpu.h"
+
+namespace slrgpu {
+
+// Layout in HBM (all arrays 256-byte aligned by cudaMalloc):
+//   nodes    : float4[8 * num_nodes]   one 128 B QBVH node = 8 consecutive float4 (see SlrGpuBvhNode)
+//   leaves   : float4[3 * num_leaves]  one 48 B leaf record = 3 consecutive float4 (see SlrGpuLeafRecord)
+//   instances: SlrGpuInstance[num_instances]
+struct DeviceScene {
+    const float4* nodes;
+    const float4* leaves;
+    const SlrGpuInstance* instances;
+    const SlrGpuTriangle* triangles;
+    const float4* vertices;          // 3 float4 per vertex (SlrGpuVertex)
+    const SlrGpuMaterial* materials;
+    const SlrGpuTexture* textures;
+    const SlrGpuSpectrum* spectra;
+    const float* spectrumData;
+    const SlrGpuImage* images;
+    const uint8_t* imageData;
+    const SlrGpuLight* lights;
+    // environment importance map
+    const float* envRowPdf;
+    const float* envRowCdf;
+    const float* envRowIntegral;
+    const float* envMarginalPdf;
+    const float* envMarginalCdf;
+    // spectral tables
+    const float* upsampleGrid;
+    const float* upsamplePoints;
+    uint32_t numNodes, numLeaves, numInstances, numTriangles, numVertices;
+    uint32_t numMaterials, numTextures, numSpectra, numImages, numLights, numTopLights;
+    uint32_t envPresent, envMaterial, envMapWidth, envMapHeight;
+    float envMarginalIntegral;
+    uint32_t rgbMode;
+    float worldCenter[3];
+    float worldRadius;
+    SlrGpuCamera camera;
+    float xbar16[16], ybar16[16], zbar16[16];
+    float integralCMF;
+};
+
+}  // namespace slrgpu
+
+struct SlrGpuScene {
+    int device = 0;
+    slrgpu::DeviceScene dev;          // host copy of the device view (passed to kernels by value / constant)
+    void* allocations[32] = {};
+    int numAllocations = 0;
+    uint64_t deviceBytes = 0;
+    bool hasInstances = false;
+    bool hasShading = false;
+    uint32_t channels = 16;
+};
+
+namespace slrgpu {
+void setError(const char* fmt, ...);
+int cudaFail(cudaError_t e, const char* what);
+#define SLRGPU_CUDA_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return slrgpu::cudaFail(_e, #expr); } while (0)
+}

@@ -1,0 +1,209 @@
+// Ray-batch entry points: closest hit (Accelerator::intersect, libSLR/Core/Accelerator.h:17-34 /
+// QBVH::intersect, QBVH.h:295-337) and occlusion (Scene::testVisibility, SurfaceObject.cpp:418-430).
+// MUST be compiled with -fmad=false (see traverse.cuh).
+#include "traverse.cuh"
+
+namespace slrgpu {
+
+constexpr int kIntersectBlock = 128;
+
+template <bool INSTANCES, bool COUNT>
+__global__ void __launch_bounds__(kIntersectBlock)
+intersectBatchKernel(const DeviceScene s, SlrGpuRayBatch rays, uint64_t n, SlrGpuHitBatch hits, int* status) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray r;
+    r.ox = rays.org_x[i]; r.oy = rays.org_y[i]; r.oz = rays.org_z[i];
+    r.dx = rays.dir_x[i]; r.dy = rays.dir_y[i]; r.dz = rays.dir_z[i];
+    r.tmin = rays.tmin[i]; r.tmax = rays.tmax[i];
+    Hit h;
+    h.prim = SLRGPU_INVALID_ID; h.inst = SLRGPU_INVALID_ID; h.t = INFINITY; h.u = 0.0f; h.v = 0.0f;
+    uint32_t stack[kStackSize];
+    TraversalCounters cnt = {0, 0};
+    bool overflow = false;
+    traverse<INSTANCES ? 0 : 1, false, COUNT>(s, 0, r, h, stack, 0, cnt, overflow);
+    hits.prim[i] = h.prim;
+    hits.inst[i] = h.inst;
+    hits.t[i] = h.t;
+    if (hits.u) hits.u[i] = h.u;
+    if (hits.v) hits.v[i] = h.v;
+    if (COUNT) {
+        if (hits.nodes_visited) hits.nodes_visited[i] = cnt.nodes;
+        if (hits.tris_tested) hits.tris_tested[i] = cnt.tris;
+    }
+    if (overflow) atomicExch(status, 1);
+}
+
+template <bool INSTANCES>
+__global__ void __launch_bounds__(kIntersectBlock)
+occludedBatchKernel(const DeviceScene s, SlrGpuRayBatch rays, uint64_t n, uint8_t* occluded, int* status) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray r;
+    r.ox = rays.org_x[i]; r.oy = rays.org_y[i]; r.oz = rays.org_z[i];
+    r.dx = rays.dir_x[i]; r.dy = rays.dir_y[i]; r.dz = rays.dir_z[i];
+    r.tmin = rays.tmin[i]; r.tmax = rays.tmax[i];
+    Hit h;
+    h.prim = SLRGPU_INVALID_ID; h.inst = SLRGPU_INVALID_ID; h.t = INFINITY; h.u = h.v = 0.0f;
+    uint32_t stack[kStackSize];
+    TraversalCounters cnt = {0, 0};
+    bool overflow = false;
+    const bool any = traverse<INSTANCES ? 0 : 1, true, false>(s, 0, r, h, stack, 0, cnt, overflow);
+    occluded[i] = any ? 1 : 0;
+    if (overflow) atomicExch(status, 1);
+}
+
+static int launchIntersect(SlrGpuScene* sc, const SlrGpuRayBatch& rays, uint64_t n, const SlrGpuHitBatch& hits,
+                           int* dStatus, cudaStream_t stream) {
+    if (n == 0) return SLRGPU_OK;
+    const uint64_t blocks = (n + kIntersectBlock - 1) / kIntersectBlock;
+    if (blocks > 0x7FFFFFFFull) { setError("ray batch too large"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    const bool count = hits.nodes_visited || hits.tris_tested;
+    const dim3 grid((unsigned)blocks), block(kIntersectBlock);
+    if (sc->hasInstances) {
+        if (count) intersectBatchKernel<true, true><<<grid, block, 0, stream>>>(sc->dev, rays, n, hits, dStatus);
+        else       intersectBatchKernel<true, false><<<grid, block, 0, stream>>>(sc->dev, rays, n, hits, dStatus);
+    } else {
+        if (count) intersectBatchKernel<false, true><<<grid, block, 0, stream>>>(sc->dev, rays, n, hits, dStatus);
+        else       intersectBatchKernel<false, false><<<grid, block, 0, stream>>>(sc->dev, rays, n, hits, dStatus);
+    }
+    SLRGPU_CUDA_TRY(cudaGetLastError());
+    return SLRGPU_OK;
+}
+
+struct DeviceBuffers {
+    void* ptrs[24] = {};
+    int n = 0;
+    ~DeviceBuffers() { for (int i = 0; i < n; ++i) cudaFree(ptrs[i]); }
+    template <typename T> int alloc(T** p, uint64_t count) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 4);
+        if (e != cudaSuccess) return cudaFail(e, "cudaMalloc(batch buffer)");
+        ptrs[n++] = q; *p = reinterpret_cast<T*>(q);
+        return SLRGPU_OK;
+    }
+};
+
+static int uploadRays(DeviceBuffers& bufs, const SlrGpuRayBatch* rays, uint64_t n, SlrGpuRayBatch* d) {
+    const float* src[8] = {rays->org_x, rays->org_y, rays->org_z, rays->dir_x, rays->dir_y, rays->dir_z, rays->tmin, rays->tmax};
+    float* dst[8];
+    for (int k = 0; k < 8; ++k) {
+        if (!src[k]) { setError("ray batch: null component array"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+        int rc = bufs.alloc(&dst[k], n);
+        if (rc != SLRGPU_OK) return rc;
+        SLRGPU_CUDA_TRY(cudaMemcpy(dst[k], src[k], n * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    d->org_x = dst[0]; d->org_y = dst[1]; d->org_z = dst[2];
+    d->dir_x = dst[3]; d->dir_y = dst[4]; d->dir_z = dst[5];
+    d->tmin = dst[6]; d->tmax = dst[7];
+    return SLRGPU_OK;
+}
+
+}  // namespace slrgpu
+
+using namespace slrgpu;
+
+extern "C" {
+
+SLRGPU_API int slrgpu_intersect_launch_config(SlrGpuScene* scene, uint64_t num_rays, uint32_t* grid, uint32_t* block) {
+    if (!scene) { setError("null scene"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    if (grid) *grid = (uint32_t)((num_rays + kIntersectBlock - 1) / kIntersectBlock);
+    if (block) *block = kIntersectBlock;
+    return SLRGPU_OK;
+}
+
+SLRGPU_API int slrgpu_intersect_batch_device(SlrGpuScene* scene, const SlrGpuRayBatch* rays, uint64_t num_rays,
+                                             const SlrGpuHitBatch* hits, void* stream) {
+    if (!scene || !rays || !hits || !hits->prim || !hits->inst || !hits->t) {
+        setError("slrgpu_intersect_batch_device: null argument"); return SLRGPU_ERR_INVALID_ARGUMENT;
+    }
+    SLRGPU_CUDA_TRY(cudaSetDevice(scene->device));
+    static thread_local int* dStatus = nullptr;
+    if (!dStatus) { SLRGPU_CUDA_TRY(cudaMalloc(&dStatus, sizeof(int))); SLRGPU_CUDA_TRY(cudaMemset(dStatus, 0, sizeof(int))); }
+    return launchIntersect(scene, *rays, num_rays, *hits, dStatus, (cudaStream_t)stream);
+}
+
+SLRGPU_API int slrgpu_intersect_batch(SlrGpuScene* scene, const SlrGpuRayBatch* rays, uint64_t n,
+                                      const SlrGpuHitBatch* hits, float* kernel_ms) {
+    if (!scene || !rays || !hits || !hits->prim || !hits->inst || !hits->t) {
+        setError("slrgpu_intersect_batch: null argument"); return SLRGPU_ERR_INVALID_ARGUMENT;
+    }
+    if (kernel_ms) *kernel_ms = 0.0f;
+    if (n == 0) return SLRGPU_OK;
+    SLRGPU_CUDA_TRY(cudaSetDevice(scene->device));
+    DeviceBuffers bufs;
+    SlrGpuRayBatch dr;
+    int rc = uploadRays(bufs, rays, n, &dr);
+    if (rc != SLRGPU_OK) return rc;
+    SlrGpuHitBatch dh = {};
+    int* dStatus = nullptr;
+    if ((rc = bufs.alloc(&dh.prim, n)) || (rc = bufs.alloc(&dh.inst, n)) || (rc = bufs.alloc(&dh.t, n)) ||
+        (rc = bufs.alloc(&dStatus, 1))) return rc;
+    if (hits->u && (rc = bufs.alloc(&dh.u, n))) return rc;
+    if (hits->v && (rc = bufs.alloc(&dh.v, n))) return rc;
+    if (hits->nodes_visited && (rc = bufs.alloc(&dh.nodes_visited, n))) return rc;
+    if (hits->tris_tested && (rc = bufs.alloc(&dh.tris_tested, n))) return rc;
+    SLRGPU_CUDA_TRY(cudaMemset(dStatus, 0, sizeof(int)));
+    cudaEvent_t e0, e1;
+    SLRGPU_CUDA_TRY(cudaEventCreate(&e0));
+    SLRGPU_CUDA_TRY(cudaEventCreate(&e1));
+    SLRGPU_CUDA_TRY(cudaEventRecord(e0, 0));
+    rc = launchIntersect(scene, dr, n, dh, dStatus, 0);
+    cudaEventRecord(e1, 0);
+    cudaError_t se = cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc != SLRGPU_OK) return rc;
+    SLRGPU_CUDA_TRY(se);
+    if (kernel_ms) *kernel_ms = ms;
+    SLRGPU_CUDA_TRY(cudaMemcpy(hits->prim, dh.prim, n * 4, cudaMemcpyDeviceToHost));
+    SLRGPU_CUDA_TRY(cudaMemcpy(hits->inst, dh.inst, n * 4, cudaMemcpyDeviceToHost));
+    SLRGPU_CUDA_TRY(cudaMemcpy(hits->t, dh.t, n * 4, cudaMemcpyDeviceToHost));
+    if (hits->u) SLRGPU_CUDA_TRY(cudaMemcpy(hits->u, dh.u, n * 4, cudaMemcpyDeviceToHost));
+    if (hits->v) SLRGPU_CUDA_TRY(cudaMemcpy(hits->v, dh.v, n * 4, cudaMemcpyDeviceToHost));
+    if (hits->nodes_visited) SLRGPU_CUDA_TRY(cudaMemcpy(hits->nodes_visited, dh.nodes_visited, n * 4, cudaMemcpyDeviceToHost));
+    if (hits->tris_tested) SLRGPU_CUDA_TRY(cudaMemcpy(hits->tris_tested, dh.tris_tested, n * 4, cudaMemcpyDeviceToHost));
+    int status = 0;
+    SLRGPU_CUDA_TRY(cudaMemcpy(&status, dStatus, sizeof(int), cudaMemcpyDeviceToHost));
+    if (status) { setError("traversal stack overflow (more than %d pending nodes)", kStackSize); return SLRGPU_ERR_STACK_OVERFLOW; }
+    return SLRGPU_OK;
+}
+
+SLRGPU_API int slrgpu_occluded_batch(SlrGpuScene* scene, const SlrGpuRayBatch* rays, uint64_t n,
+                                     uint8_t* occluded, float* kernel_ms) {
+    if (!scene || !rays || !occluded) { setError("slrgpu_occluded_batch: null argument"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    if (kernel_ms) *kernel_ms = 0.0f;
+    if (n == 0) return SLRGPU_OK;
+    SLRGPU_CUDA_TRY(cudaSetDevice(scene->device));
+    DeviceBuffers bufs;
+    SlrGpuRayBatch dr;
+    int rc = uploadRays(bufs, rays, n, &dr);
+    if (rc != SLRGPU_OK) return rc;
+    uint8_t* dOcc = nullptr; int* dStatus = nullptr;
+    if ((rc = bufs.alloc(&dOcc, n)) || (rc = bufs.alloc(&dStatus, 1))) return rc;
+    SLRGPU_CUDA_TRY(cudaMemset(dStatus, 0, sizeof(int)));
+    const uint64_t blocks = (n + kIntersectBlock - 1) / kIntersectBlock;
+    cudaEvent_t e0, e1;
+    SLRGPU_CUDA_TRY(cudaEventCreate(&e0));
+    SLRGPU_CUDA_TRY(cudaEventCreate(&e1));
+    cudaEventRecord(e0, 0);
+    if (scene->hasInstances) occludedBatchKernel<true><<<(unsigned)blocks, kIntersectBlock>>>(scene->dev, dr, n, dOcc, dStatus);
+    else                     occludedBatchKernel<false><<<(unsigned)blocks, kIntersectBlock>>>(scene->dev, dr, n, dOcc, dStatus);
+    cudaError_t le = cudaGetLastError();
+    cudaEventRecord(e1, 0);
+    cudaError_t se = cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    SLRGPU_CUDA_TRY(le);
+    SLRGPU_CUDA_TRY(se);
+    if (kernel_ms) *kernel_ms = ms;
+    SLRGPU_CUDA_TRY(cudaMemcpy(occluded, dOcc, n, cudaMemcpyDeviceToHost));
+    int status = 0;
+    SLRGPU_CUDA_TRY(cudaMemcpy(&status, dStatus, sizeof(int), cudaMemcpyDeviceToHost));
+    if (status) { setError("traversal stack overflow"); return SLRGPU_ERR_STACK_OVERFLOW; }
+    return SLRGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+// Scene upload: copies the caller's SoA host buffers into HBM once and keeps a device view.
+// Replaces, on the GPU side, the object graph a reference renderer receives from
+// SLRSceneGraph::Scene::build (libSLRSceneGraph/Scene.cpp:28-44).
+#include "device_scene.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+namespace slrgpu {
+
+static thread_local char g_error[512] = "";
+
+void setError(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int cudaFail(cudaError_t e, const char* what) {
+    setError("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    if (e == cudaErrorMemoryAllocation) return SLRGPU_ERR_OUT_OF_MEMORY;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return SLRGPU_ERR_NO_DEVICE;
+    return SLRGPU_ERR_CUDA;
+}
+
+template <typename T>
+static int upload(SlrGpuScene* sc, const T* src, uint64_t count, const T** dst) {
+    *dst = nullptr;
+    if (count == 0 || src == nullptr) return SLRGPU_OK;
+    if (sc->numAllocations >= 32) { setError("too many scene buffers"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    void* p = nullptr;
+    const uint64_t bytes = count * sizeof(T);
+    SLRGPU_CUDA_TRY(cudaMalloc(&p, bytes));
+    sc->allocations[sc->numAllocations++] = p;
+    sc->deviceBytes += bytes;
+    SLRGPU_CUDA_TRY(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+    *dst = reinterpret_cast<const T*>(p);
+    return SLRGPU_OK;
+}
+
+}  // namespace slrgpu
+
+using namespace slrgpu;
+
+extern "C" {
+
+SLRGPU_API int slrgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+SLRGPU_API uint32_t slrgpu_abi_version(void) { return (1u << 16) | 0u; }
+
+SLRGPU_API const char* slrgpu_last_error(void) { return g_error; }
+
+SLRGPU_API uint32_t slrgpu_struct_size(int which) {
+    static const uint32_t sizes[] = {
+        sizeof(SlrGpuSceneDesc), sizeof(SlrGpuBvhNode), sizeof(SlrGpuLeafRecord), sizeof(SlrGpuInstance),
+        sizeof(SlrGpuTriangle), sizeof(SlrGpuVertex), sizeof(SlrGpuSpectrum), sizeof(SlrGpuTexture),
+        sizeof(SlrGpuImage), sizeof(SlrGpuMaterial), sizeof(SlrGpuLight), sizeof(SlrGpuCamera),
+        sizeof(SlrGpuEnvironment), sizeof(SlrGpuSpectralTables), sizeof(SlrGpuRayBatch), sizeof(SlrGpuHitBatch),
+        sizeof(SlrGpuRenderParams), sizeof(SlrGpuRenderStats)};
+    if (which < 0 || which >= (int)(sizeof(sizes) / sizeof(sizes[0]))) return 0;
+    return sizes[which];
+}
+
+SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuScene** out) {
+    if (!d || !out) { setError("slrgpu_scene_create: null argument"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    *out = nullptr;
+    if (d->struct_size != sizeof(SlrGpuSceneDesc)) {
+        setError("slrgpu_scene_create: struct_size %u != %zu (ABI mismatch)", d->struct_size, sizeof(SlrGpuSceneDesc));
+        return SLRGPU_ERR_INVALID_ARGUMENT;
+    }
+    if (!d->bvh_nodes || d->num_bvh_nodes == 0 || !d->leaf_records || d->num_leaf_records == 0) {
+        setError("slrgpu_scene_create: a scene needs at least one BVH node and one leaf record");
+        return SLRGPU_ERR_INVALID_ARGUMENT;
+    }
+    if (d->num_bvh_nodes > 0x07FFFFFFu || d->num_leaf_records > 0x07FFFFFFu) {
+        setError("slrgpu_scene_create: node / leaf-record count exceeds the 27-bit child index");
+        return SLRGPU_ERR_UNSUPPORTED;
+    }
+    int n = slrgpu_device_count();
+    if (n == 0) { setError("no CUDA device available (this library has no CPU fallback)"); return SLRGPU_ERR_NO_DEVICE; }
+    if (device < 0 || device >= n) { setError("device %d out of range [0,%d)", device, n); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    SLRGPU_CUDA_TRY(cudaSetDevice(device));
+
+    SlrGpuScene* sc = new (std::nothrow) SlrGpuScene();
+    if (!sc) { setError("host allocation failed"); return SLRGPU_ERR_OUT_OF_MEMORY; }
+    sc->device = device;
+    DeviceScene& v = sc->dev;
+    memset(&v, 0, sizeof(v));
+    int rc = SLRGPU_OK;
+#define UP(src, count, dst) if (rc == SLRGPU_OK) rc = upload(sc, src, (uint64_t)(count), dst)
+    UP(reinterpret_cast<const float4*>(d->bvh_nodes), (uint64_t)d->num_bvh_nodes * 8, &v.nodes);
+    UP(reinterpret_cast<const float4*>(d->leaf_records), (uint64_t)d->num_leaf_records * 3, &v.leaves);
+    UP(d->instances, d->num_instances, &v.instances);
+    UP(d->triangles, d->num_triangles, &v.triangles);
+    UP(reinterpret_cast<const float4*>(d->vertices), (uint64_t)d->num_vertices * 3, &v.vertices);
+    UP(d->materials, d->num_materials, &v.materials);
+    UP(d->textures, d->num_textures, &v.textures);
+    UP(d->spectra, d->num_spectra, &v.spectra);
+    UP(d->spectrum_data, d->num_spectrum_floats, &v.spectrumData);
+    UP(d->images, d->num_images, &v.images);
+    UP(d->image_data, d->image_data_bytes, &v.imageData);
+    UP(d->lights, d->num_lights, &v.lights);
+    const SlrGpuEnvironment& e = d->environment;
+    if (e.present) {
+        const uint64_t w = e.map_width, h = e.map_height;
+        UP(e.row_pdf, w * h, &v.envRowPdf);
+        UP(e.row_cdf, (w + 1) * h, &v.envRowCdf);
+        UP(e.row_integral, h, &v.envRowIntegral);
+        UP(e.marginal_pdf, h, &v.envMarginalPdf);
+        UP(e.marginal_cdf, h + 1, &v.envMarginalCdf);
+    }
+    UP(d->spectral.upsample_grid, d->spectral.upsample_grid_floats, &v.upsampleGrid);
+    UP(d->spectral.upsample_points, d->spectral.upsample_points_floats, &v.upsamplePoints);
+#undef UP
+    if (rc != SLRGPU_OK) { slrgpu_scene_destroy(sc); return rc; }
+
+    v.numNodes = d->num_bvh_nodes; v.numLeaves = d->num_leaf_records; v.numInstances = d->num_instances;
+    v.numTriangles = d->num_triangles; v.numVertices = d->num_vertices; v.numMaterials = d->num_materials;
+    v.numTextures = d->num_textures; v.numSpectra = d->num_spectra; v.numImages = d->num_images;
+    v.numLights = d->num_lights; v.numTopLights = d->num_top_lights;
+    v.envPresent = e.present; v.envMaterial = e.material; v.envMapWidth = e.map_width; v.envMapHeight = e.map_height;
+    v.envMarginalIntegral = e.marginal_integral;
+    v.rgbMode = d->rgb_mode;
+    for (int i = 0; i < 3; ++i) v.worldCenter[i] = d->world_center[i];
+    v.worldRadius = d->world_radius;
+    v.camera = d->camera;
+    if (d->spectral.xbar_16 && d->spectral.ybar_16 && d->spectral.zbar_16) {
+        for (int i = 0; i < 16; ++i) { v.xbar16[i] = d->spectral.xbar_16[i]; v.ybar16[i] = d->spectral.ybar_16[i]; v.zbar16[i] = d->spectral.zbar_16[i]; }
+    }
+    v.integralCMF = d->spectral.integral_cmf;
+    sc->hasInstances = d->num_instances > 0;
+    sc->hasShading = d->num_materials > 0 && d->num_triangles > 0;
+    sc->channels = d->rgb_mode ? 3 : 16;
+    *out = sc;
+    return SLRGPU_OK;
+}
+
+SLRGPU_API void slrgpu_scene_destroy(SlrGpuScene* sc) {
+    if (!sc) return;
+    cudaSetDevice(sc->device);
+    for (int i = 0; i < sc->numAllocations; ++i) cudaFree(sc->allocations[i]);
+    delete sc;
+}
+
+SLRGPU_API uint64_t slrgpu_scene_device_bytes(const SlrGpuScene* sc) { return sc ? sc->deviceBytes : 0; }
+
+SLRGPU_API uint32_t slrgpu_scene_channels(const SlrGpuScene* sc) { return sc ? sc->channels : 0; }
+
+}  // extern "C"

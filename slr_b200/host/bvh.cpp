@@ -1,0 +1,432 @@
+#include "bvh.h"
+#include <algorithm>
+#include <stdexcept>
+
+namespace slr {
+
+void PrimitiveSet::addTriangle(const Vec3& a, const Vec3& b, const Vec3& c) {
+    Prim pr;
+    pr.bounds = BBox(a).grow(b).grow(c);
+    pr.cost = 1.0f;
+    pr.isTriangle = true;
+    pr.p[0] = a; pr.p[1] = b; pr.p[2] = c;
+    prims.push_back(pr);
+}
+
+void PrimitiveSet::addBox(const BBox& b, float cost) {
+    Prim pr;
+    pr.bounds = b;
+    pr.cost = cost;
+    pr.isTriangle = false;
+    prims.push_back(pr);
+}
+
+namespace {
+
+inline Vec3 lerpPoint(const Vec3& a, const Vec3& b, float t) { return (1 - t) * a + t * b; }
+
+// Bounds of the part of a primitive that lies in the slab [lo, hi) along `axis`.
+BBox choppedBounds(const PrimitiveSet::Prim& pr, Axis axis, float lo, float hi) {
+    if (!pr.isTriangle) {
+        const BBox& base = pr.bounds;
+        if (hi < base.lo[axis] || lo > base.hi[axis]) return BBox();
+        if (lo < base.lo[axis] && hi > base.hi[axis]) return base;
+        BBox r = base;
+        r.lo[axis] = std::max(lo, r.lo[axis]);
+        r.hi[axis] = std::min(hi, r.hi[axis]);
+        return r;
+    }
+    const float planes[2] = {lo, hi};
+    Vec3 p[3] = {pr.p[0], pr.p[1], pr.p[2]};
+    std::sort(p, p + 3, [axis](const Vec3& a, const Vec3& b) { return a[axis] < b[axis]; });
+    const float pmin = p[0][axis], pmax = p[2][axis];
+    if (pmin >= hi || pmax <= lo) return BBox();
+    if (pmin >= lo && pmax <= hi) return pr.bounds;
+
+    uint32_t n = 0;
+    Vec3 cuts[4];
+    for (int from = 0; from < 2; ++from) {
+        const Vec3& a = p[from];
+        for (int to = from + 1; to < 3; ++to) {
+            const Vec3& b = p[to];
+            float dAB = b[axis] - a[axis];
+            for (int k = 0; k < 2; ++k) {
+                float dAP = planes[k] - a[axis];
+                float dPB = planes[k] - b[axis];
+                float t = dAP / dAB;
+                if (dAP > 0 && dPB <= 0) cuts[n++] = lerpPoint(a, b, t);
+            }
+        }
+    }
+    BBox r;
+    if (p[1][axis] >= lo && p[1][axis] < hi) r.grow(p[1]);
+    for (uint32_t i = 0; i < n; ++i) r.grow(cuts[i]);
+    if (n == 2) r.grow(pmax < hi ? p[2] : p[0]);
+    return r;
+}
+
+// Bounds of the two halves of a primitive cut by the plane `axis = pos`.
+void splitBounds(const PrimitiveSet::Prim& pr, Axis axis, float pos, BBox* left, BBox* right) {
+    if (!pr.isTriangle) {
+        const BBox& base = pr.bounds;
+        if (pos < base.lo[axis]) { *left = BBox(); *right = base; return; }
+        if (pos > base.hi[axis]) { *left = base; *right = BBox(); return; }
+        *left = base;  left->hi[axis] = std::min(left->hi[axis], pos);
+        *right = base; right->lo[axis] = std::max(right->lo[axis], pos);
+        return;
+    }
+    Vec3 p[3] = {pr.p[0], pr.p[1], pr.p[2]};
+    std::sort(p, p + 3, [axis](const Vec3& a, const Vec3& b) { return a[axis] < b[axis]; });
+    const float pmin = p[0][axis], pmax = p[2][axis];
+    if (pos <= pmin) { *left = BBox(); *right = pr.bounds; return; }
+    if (pos >= pmax) { *left = pr.bounds; *right = BBox(); return; }
+
+    uint32_t n = 0;
+    Vec3 cuts[2];
+    for (int from = 0; from < 2; ++from) {
+        const Vec3& a = p[from];
+        for (int to = from + 1; to < 3; ++to) {
+            const Vec3& b = p[to];
+            float dAB = b[axis] - a[axis];
+            float dAP = pos - a[axis];
+            float dPB = pos - b[axis];
+            float t = dAP / dAB;
+            if (dAP > 0 && dPB <= 0 && n < 2) cuts[n++] = lerpPoint(a, b, t);
+        }
+    }
+    *left = BBox(p[0]);
+    *right = BBox(p[2]);
+    if (p[1][axis] < pos) left->grow(p[1]); else right->grow(p[1]);
+    for (uint32_t i = 0; i < n; ++i) { left->grow(cuts[i]); right->grow(cuts[i]); }
+}
+
+struct Fragment {
+    uint32_t prim;
+    BBox bbox;
+    float cost;
+};
+
+constexpr uint32_t kObjectBins = 32;
+constexpr uint32_t kSpatialBins = 16;
+constexpr float kTraversalCost = 1.2f;
+constexpr uint32_t kFragmentBudget = 5;
+
+struct Builder {
+    const PrimitiveSet& ps;
+    SBVH& out;
+    std::vector<Fragment> frags;   // grows in place when spatial splits duplicate references
+    uint32_t live = 0;             // number of fragments currently in use
+
+    Builder(const PrimitiveSet& p, SBVH& o) : ps(p), out(o) {}
+
+    static uint32_t binOf(uint32_t numBins, float v, float lo, float hi) {
+        uint32_t b = (uint32_t)(numBins * ((v - lo) / (hi - lo)));
+        return std::min(b, numBins - 1);
+    }
+
+    // Opens a gap of `count` fragments after position `end` (the fragments of later, not yet
+    // processed subtrees shift right), mirroring the in-place array the reference grows.
+    void shiftTail(uint32_t end, uint32_t count) {
+        if (count == 0) return;
+        if (live + count > frags.size()) frags.resize(std::max<size_t>(live + count, frags.size() * 2));
+        std::copy_backward(frags.begin() + end, frags.begin() + live, frags.begin() + live + count);
+    }
+
+    // returns node index; *added = number of fragments this subtree added to the array
+    uint32_t recurse(uint32_t start, uint32_t end, uint32_t depth, uint32_t* added) {
+        *added = 0;
+        const uint32_t nodeIdx = (uint32_t)out.nodes.size();
+        out.nodes.emplace_back();
+        if (++depth > out.depth) out.depth = depth;
+
+        BBox box, centroidBox;
+        float leafCost = 0.0f;
+        for (uint32_t i = start; i < end; ++i) {
+            box.grow(frags[i].bbox);
+            centroidBox.grow(frags[i].bbox.centroid());
+            leafCost += frags[i].cost;
+        }
+        const Axis axisO = centroidBox.widestAxis();
+        const Axis axisS = box.widestAxis();
+        const float areaParent = box.surfaceArea();
+        const float cLo = centroidBox.lo[axisO], cHi = centroidBox.hi[axisO];
+        const float bLo = box.lo[axisS], bHi = box.hi[axisS];
+        const uint32_t count = end - start;
+
+        auto makeLeaf = [&](uint32_t n) {
+            SBVHNode& nd = out.nodes[nodeIdx];
+            nd.bbox = box;
+            nd.c0 = nd.c1 = 0;
+            nd.firstRef = (uint32_t)out.refs.size();
+            nd.numRefs = n;
+            for (uint32_t i = start; i < start + n; ++i) out.refs.push_back(frags[i].prim);
+        };
+        if (count == 1) { makeLeaf(1); return nodeIdx; }
+
+        // ---- object binning over centroids
+        struct ObjBin { BBox box; uint32_t n = 0; float cost = 0.0f; } objBins[kObjectBins];
+        uint32_t planeO = 0;
+        float bestO = INFINITY;
+        if ((cHi - cLo) > 0) {
+            for (uint32_t i = start; i < end; ++i) {
+                const Fragment& f = frags[i];
+                uint32_t b = binOf(kObjectBins, f.bbox.centerOf(axisO), cLo, cHi);
+                ++objBins[b].n;
+                objBins[b].cost += f.cost;
+                objBins[b].box.grow(f.bbox);
+            }
+            for (uint32_t i = 0; i < kObjectBins - 1; ++i) {
+                BBox l, r;
+                float cl = 0.0f, cr = 0.0f;
+                for (uint32_t j = 0; j <= i; ++j) { l.grow(objBins[j].box); cl += objBins[j].cost; }
+                for (uint32_t j = i + 1; j < kObjectBins; ++j) { r.grow(objBins[j].box); cr += objBins[j].cost; }
+                float c = kTraversalCost + (l.surfaceArea() * cl + r.surfaceArea() * cr) / areaParent;
+                if (c < bestO) { bestO = c; planeO = i; }
+            }
+        }
+
+        // ---- how much do the two object-split children overlap? decides whether to try spatial splits
+        BBox lO, rO;
+        for (uint32_t j = 0; j <= planeO; ++j) lO.grow(objBins[j].box);
+        for (uint32_t j = planeO + 1; j < kObjectBins; ++j) rO.grow(objBins[j].box);
+        BBox overlap = intersection(lO, rO);
+        float overlapArea = 0;
+        if (overlap.isValid()) overlapArea = overlap.surfaceArea();
+
+        struct SpBin { BBox box; uint32_t in = 0, outN = 0; float costIn = 0.0f, costOut = 0.0f; } spBins[kSpatialBins];
+        const float binWidth = box.width(axisS) / kSpatialBins;
+        uint32_t planeS = 0;
+        float bestS = INFINITY;
+        const float alpha = 1e-5;
+        if (overlapArea / out.bounds.surfaceArea() > alpha) {
+            for (uint32_t i = start; i < end; ++i) {
+                const Fragment& f = frags[i];
+                uint32_t bIn = binOf(kSpatialBins, f.bbox.lo[axisS], bLo, bHi);
+                uint32_t bOut = binOf(kSpatialBins, f.bbox.hi[axisS], bLo, bHi);
+                ++spBins[bIn].in;
+                ++spBins[bOut].outN;
+                spBins[bIn].costIn += f.cost;
+                spBins[bOut].costOut += f.cost;
+                for (int b = (int)bIn; b <= (int)bOut; ++b) {
+                    float lo = b * binWidth + bLo;
+                    BBox chopped = choppedBounds(ps.prims[f.prim], axisS, lo, lo + binWidth);
+                    spBins[b].box.grow(intersection(chopped, f.bbox));
+                }
+            }
+            for (uint32_t i = 0; i < kSpatialBins - 1; ++i) {
+                BBox l, r;
+                float cl = 0.0f, cr = 0.0f;
+                for (uint32_t j = 0; j <= i; ++j) { l.grow(spBins[j].box); cl += spBins[j].costIn; }
+                for (uint32_t j = i + 1; j < kSpatialBins; ++j) { r.grow(spBins[j].box); cr += spBins[j].costOut; }
+                float c = kTraversalCost + (l.surfaceArea() * cl + r.surfaceArea() * cr) / areaParent;
+                if (c < bestS) { bestS = c; planeS = i; }
+            }
+        }
+
+        if (leafCost < bestO && leafCost < bestS) { makeLeaf(count); return nodeIdx; }
+
+        if (bestO < bestS) {
+            // ---- object partition about the chosen centroid plane
+            float pivot = cLo + (cHi - cLo) / kObjectBins * (planeO + 1);
+            Fragment* first = frags.data() + start;
+            Fragment* mid = std::partition(first, frags.data() + end,
+                                           [axisO, pivot](const Fragment& f) { return f.bbox.centerOf(axisO) < pivot; });
+            uint32_t split = std::max((uint32_t)(mid - first), 1u) + start;
+            uint32_t addL, addR;
+            uint32_t c0 = recurse(start, split, depth, &addL);
+            uint32_t c1 = recurse(split + addL, end + addL, depth, &addR);
+            SBVHNode& nd = out.nodes[nodeIdx];
+            nd.bbox = box; nd.c0 = c0; nd.c1 = c1; nd.axis = axisO; nd.firstRef = nd.numRefs = 0;
+            *added += addL + addR;
+            return nodeIdx;
+        }
+
+        // ---- spatial partition: references straddling the plane go to both sides with clipped bounds
+        uint32_t maxL = 0, maxR = 0;
+        for (uint32_t j = 0; j <= planeS; ++j) maxL += spBins[j].in;
+        for (uint32_t j = planeS + 1; j < kSpatialBins; ++j) maxR += spBins[j].outN;
+        std::vector<Fragment> lefts(maxL), rights(maxR);
+        uint32_t nL = 0, nR = 0;
+        const float splitPos = (planeS + 1) * binWidth + bLo;
+        for (uint32_t i = start; i < end; ++i) {
+            const Fragment& f = frags[i];
+            uint32_t bIn = binOf(kSpatialBins, f.bbox.lo[axisS], bLo, bHi);
+            uint32_t bOut = binOf(kSpatialBins, f.bbox.hi[axisS], bLo, bHi);
+            if (bOut <= planeS) {
+                lefts[nL++] = f;
+            } else if (bIn > planeS) {
+                rights[nR++] = f;
+            } else {
+                BBox sl, sr;
+                splitBounds(ps.prims[f.prim], axisS, splitPos, &sl, &sr);
+                Fragment& dl = lefts[nL++];
+                Fragment& dr = rights[nR++];
+                dl.prim = dr.prim = f.prim;
+                dl.cost = dr.cost = f.cost;
+                dl.bbox = intersection(sl, f.bbox);
+                dr.bbox = intersection(sr, f.bbox);
+                if (!sl.isValid()) --nL;
+                if (!sr.isValid()) --nR;
+            }
+        }
+        *added = (nL + nR) - count;
+        shiftTail(end, *added);
+        std::copy(lefts.begin(), lefts.begin() + nL, frags.begin() + start);
+        std::copy(rights.begin(), rights.begin() + nR, frags.begin() + start + nL);
+        live += *added;
+        lefts.clear(); lefts.shrink_to_fit();
+        rights.clear(); rights.shrink_to_fit();
+        uint32_t split = start + nL;
+        uint32_t addL, addR;
+        uint32_t c0 = recurse(start, split, depth, &addL);
+        uint32_t c1 = recurse(split + addL, end + *added + addL, depth, &addR);
+        SBVHNode& nd = out.nodes[nodeIdx];
+        nd.bbox = box; nd.c0 = c0; nd.c1 = c1; nd.axis = axisS; nd.firstRef = nd.numRefs = 0;
+        *added += addL + addR;
+        return nodeIdx;
+    }
+};
+
+}  // namespace
+
+void SBVH::build(const PrimitiveSet& ps) {
+    nodes.clear(); refs.clear(); bounds = BBox(); depth = 0;
+    if (ps.prims.empty()) throw std::runtime_error("SBVH::build: empty primitive set");
+    Builder b(ps, *this);
+    const uint32_t n = (uint32_t)ps.prims.size();
+    b.frags.resize((size_t)n + n / 4 + 16);
+    for (uint32_t i = 0; i < n; ++i) {
+        bounds.grow(ps.prims[i].bounds);
+        b.frags[i].prim = i;
+        b.frags[i].bbox = ps.prims[i].bounds;
+        b.frags[i].cost = ps.prims[i].cost;
+    }
+    b.live = n;
+    uint32_t added = 0;
+    b.recurse(0, n, 0, &added);
+    if ((uint64_t)n + added > (uint64_t)kFragmentBudget * n)
+        throw std::runtime_error("SBVH::build: spatial splits exceeded the 5x fragment budget of the reference (SBVH.h:385)");
+    numFragmentsAdded = added;
+
+    // SAH cost (traversal 1.2, leaf overhead 0)
+    float cInt = 0.0f, cLeaf = 0.0f, cObj = 0.0f;
+    for (const SBVHNode& nd : nodes) {
+        float sa = nd.bbox.surfaceArea();
+        if (nd.numRefs == 0) {
+            cInt += sa;
+        } else {
+            cLeaf += sa;
+            float cp = 0.0f;
+            for (uint32_t j = 0; j < nd.numRefs; ++j) cp += ps.prims[refs[nd.firstRef + j]].cost;
+            cObj += sa * cp;
+        }
+    }
+    float rootSA = nodes[0].bbox.surfaceArea();
+    cInt *= 1.2f / rootSA;
+    cLeaf *= 0.0f / rootSA;
+    cObj /= rootSA;
+    cost = cInt + cLeaf + cObj;
+}
+
+namespace {
+
+struct Collapser {
+    const SBVH& src;
+    QBVH& out;
+    Collapser(const SBVH& s, QBVH& o) : src(s), out(o) {}
+
+    static uint32_t pack(uint32_t idx, uint32_t numLeaves, bool leaf) {
+        if (idx > 0x07FFFFFFu) throw std::runtime_error("QBVH: index exceeds 27 bits");
+        return idx | (numLeaves << 27) | (leaf ? 0x80000000u : 0u);
+    }
+
+    void setLane(QBVHNode& n, int lane, const BBox* b) {
+        n.lo_x[lane] = b ? b->lo.x : INFINITY;  n.lo_y[lane] = b ? b->lo.y : INFINITY;  n.lo_z[lane] = b ? b->lo.z : INFINITY;
+        n.hi_x[lane] = b ? b->hi.x : -INFINITY; n.hi_y[lane] = b ? b->hi.y : -INFINITY; n.hi_z[lane] = b ? b->hi.z : -INFINITY;
+    }
+
+    uint32_t collapse(uint32_t subtreeRoot, uint32_t depth) {
+        const SBVHNode& root = src.nodes[subtreeRoot];
+        if (root.numRefs > 0) {
+            if (root.numRefs >= 16)
+                throw std::runtime_error("QBVH: a leaf holds >= 16 references; the reference's 4-bit numLeaves field cannot represent it");
+            uint32_t base = (uint32_t)out.refs.size();
+            for (uint32_t i = 0; i < root.numRefs; ++i) out.refs.push_back(src.refs[root.firstRef + i]);
+            return pack(base, root.numRefs, true);
+        }
+        if (++depth > out.depth) out.depth = depth;
+
+        // lanes 0,1 come from the left child (its two children, or itself if it is a leaf -> lane 0),
+        // lanes 2,3 from the right child likewise
+        const uint32_t kid[2] = {root.c0, root.c1};
+        uint32_t laneSrc[4] = {UINT32_MAX, UINT32_MAX, UINT32_MAX, UINT32_MAX};
+        uint8_t sideAxis[2] = {Axis_X, Axis_X};
+        for (int s = 0; s < 2; ++s) {
+            const SBVHNode& k = src.nodes[kid[s]];
+            if (k.numRefs == 0) { laneSrc[2 * s] = k.c0; laneSrc[2 * s + 1] = k.c1; sideAxis[s] = k.axis; }
+            else                { laneSrc[2 * s] = kid[s]; }
+        }
+        const uint32_t nodeIdx = (uint32_t)out.nodes.size();
+        out.nodes.emplace_back();
+        {
+            QBVHNode& n = out.nodes.back();
+            for (int l = 0; l < 4; ++l) setLane(n, l, laneSrc[l] == UINT32_MAX ? nullptr : &src.nodes[laneSrc[l]].bbox);
+            n.topAxis = root.axis; n.leftAxis = sideAxis[0]; n.rightAxis = sideAxis[1]; n.pad0 = 0;
+            n.pad[0] = n.pad[1] = n.pad[2] = 0;
+            for (int l = 0; l < 4; ++l) n.child[l] = kQBVHEmptyChild;
+        }
+        uint32_t kids[4] = {kQBVHEmptyChild, kQBVHEmptyChild, kQBVHEmptyChild, kQBVHEmptyChild};
+        for (int l = 0; l < 4; ++l)
+            if (laneSrc[l] != UINT32_MAX) kids[l] = collapse(laneSrc[l], depth);
+        for (int l = 0; l < 4; ++l) out.nodes[nodeIdx].child[l] = kids[l];   // vector may have grown: index, not reference
+        return pack(nodeIdx, 0, false);
+    }
+};
+
+}  // namespace
+
+void QBVH::build(const SBVH& sbvh, const PrimitiveSet& ps) {
+    nodes.clear(); refs.clear(); depth = 0;
+    bounds = sbvh.bounds;
+    Collapser c(sbvh, *this);
+    uint32_t rootChild = c.collapse(0, 0);
+    if (qbvhChildIsLeaf(rootChild)) {
+        // single-leaf tree: wrap it in one node whose lane 0 is the whole scene
+        nodes.emplace_back();
+        QBVHNode& n = nodes.back();
+        c.setLane(n, 0, &sbvh.nodes[0].bbox);
+        for (int l = 1; l < 4; ++l) c.setLane(n, l, nullptr);
+        n.child[0] = rootChild;
+        n.child[1] = n.child[2] = n.child[3] = kQBVHEmptyChild;
+        n.topAxis = n.leftAxis = n.rightAxis = Axis_X; n.pad0 = 0;
+        n.pad[0] = n.pad[1] = n.pad[2] = 0;
+    }
+
+    // SAH cost of the collapsed tree
+    float cInt = 0.0f, cObj = 0.0f;
+    for (const QBVHNode& n : nodes) {
+        BBox nodeBox, kid[4];
+        for (int l = 0; l < 4; ++l) {
+            if (n.child[l] == kQBVHEmptyChild) continue;
+            kid[l] = BBox(Vec3(n.lo_x[l], n.lo_y[l], n.lo_z[l]), Vec3(n.hi_x[l], n.hi_y[l], n.hi_z[l]));
+            nodeBox.grow(kid[l]);
+        }
+        cInt += nodeBox.surfaceArea();
+        for (int l = 0; l < 4; ++l) {
+            uint32_t ch = n.child[l];
+            if (ch == kQBVHEmptyChild) continue;
+            float sa = kid[l].surfaceArea();
+            if (qbvhChildIsLeaf(ch)) {
+                float cp = 0.0f;
+                for (uint32_t j = 0; j < qbvhChildNumLeaves(ch); ++j) cp += ps.prims[refs[qbvhChildIdx(ch) + j]].cost;
+                cObj += sa * cp;
+            }
+        }
+    }
+    float rootSA = bounds.surfaceArea();
+    cInt *= 1.2f / rootSA;
+    cObj /= rootSA;
+    cost = cInt + cObj;
+}
+
+}  // namespace slr

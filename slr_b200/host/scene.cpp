@@ -1,0 +1,285 @@
+#include "scene.h"
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <stdexcept>
+
+namespace slr {
+
+// ---------------------------------------------------------------------------------------------
+// nodes
+// ---------------------------------------------------------------------------------------------
+
+static bool containsNode(const InternalNode* self, const Node* target) {
+    for (const NodeRef& c : self->children()) {
+        if (c.get() == target) return true;
+        if (const InternalNode* in = dynamic_cast<const InternalNode*>(c.get()))
+            if (containsNode(in, target)) return true;
+    }
+    return false;
+}
+
+bool InternalNode::addChildNode(const NodeRef& n) {
+    if (n.get() == this) return false;
+    if (const InternalNode* in = dynamic_cast<const InternalNode*>(n.get()))
+        if (containsNode(in, this)) return false;                 // would create a cycle
+    if (n->isInstanced()) {
+        if (std::find(m_children.begin(), m_children.end(), n) != m_children.end()) return false;
+    } else if (containsNode(this, n.get())) {
+        return false;
+    }
+    m_children.push_back(n);
+    return true;
+}
+
+void InternalNode::getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) {
+    // parent * local, with the inverse recomputed from the product as StaticTransform's ctor does
+    StaticTransform reduced = subTF ? (*subTF * m_localToWorld) : m_localToWorld;
+    for (const NodeRef& c : m_children) c->getRenderingData(b, &reduced, data);
+}
+
+void TriangleMeshNode::addTriangles(const SurfaceMaterialRef& mat, const Normal3DTextureRef& normalMap,
+                                    const FloatTextureRef& alphaMap, std::vector<uint32_t>&& indices) {
+    if (indices.size() % 3 != 0) throw std::runtime_error("TriangleMeshNode::addTriangles: index count is not a multiple of 3");
+    for (uint32_t i : indices)
+        if (i >= m_vertices.size()) throw std::runtime_error("TriangleMeshNode::addTriangles: vertex index out of range");
+    m_groups.emplace_back();
+    MaterialGroup& g = m_groups.back();
+    g.material = mat; g.normalMap = normalMap; g.alphaMap = alphaMap;
+    g.indices = std::move(indices);
+}
+
+void TriangleMeshNode::getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) {
+    if (m_flattened)
+        throw std::runtime_error("a TriangleMeshNode is reachable twice in one flattening pass; wrap it in a ReferenceNode to instance it");
+    m_flattened = true;
+    StaticTransform tf = subTF ? *subTF : StaticTransform();
+    FlatScene& f = b.flat;
+    const uint32_t vBase = (uint32_t)f.vertices.size();
+    f.vertices.reserve(f.vertices.size() + m_vertices.size());
+    for (const Vertex& v : m_vertices) {
+        // baked exactly as applyTransformForRendering does (TriangleMeshNode.cpp:68-78)
+        Vec3 p = tf.point(v.position);
+        Vec3 n = normalize(tf.normal(v.normal));
+        Vec3 t = normalize(tf.vector(v.tangent));
+        SlrGpuVertex o;
+        o.position[0] = p.x; o.position[1] = p.y; o.position[2] = p.z; o.u = v.texCoord.u;
+        o.normal[0] = n.x; o.normal[1] = n.y; o.normal[2] = n.z; o.v = v.texCoord.v;
+        o.tangent[0] = t.x; o.tangent[1] = t.y; o.tangent[2] = t.z; o.pad = 0.0f;
+        f.vertices.push_back(o);
+    }
+    for (const MaterialGroup& g : m_groups) {
+        const uint32_t mat = g.material ? b.exportMaterial(g.material.get()) : SLRGPU_INVALID_ID;
+        const uint32_t nmap = g.normalMap ? b.exportNormalTexture(g.normalMap.get()) : SLRGPU_INVALID_ID;
+        const uint32_t amap = g.alphaMap ? b.exportFloatTexture(g.alphaMap.get()) : SLRGPU_INVALID_ID;
+        const bool emits = g.material && b.materialEmits(g.material.get());
+        for (size_t i = 0; i + 2 < g.indices.size(); i += 3) {
+            SlrGpuTriangle t;
+            t.v[0] = vBase + g.indices[i]; t.v[1] = vBase + g.indices[i + 1]; t.v[2] = vBase + g.indices[i + 2];
+            t.material = mat; t.normal_map = nmap; t.alpha_map = amap;
+            t.light_index = SLRGPU_INVALID_ID; t.pad = 0;
+            const uint32_t id = (uint32_t)f.triangles.size();
+            if (id >= 0x80000000u) throw std::runtime_error("more than 2^31 triangles");
+            f.triangles.push_back(t);
+            b.triangleEmits.push_back(emits ? 1 : 0);
+            data->objects.push_back(ObjectRef{false, id});
+        }
+    }
+}
+
+void ReferenceNode::getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) {
+    if (!m_ready) {
+        RenderingData sub;
+        m_node->getRenderingData(b, nullptr, &sub);
+        if (sub.objects.empty()) throw std::runtime_error("ReferenceNode refers to a subtree without surfaces");
+        m_aggregate = b.createAggregate(std::move(sub.objects));
+        m_ready = true;
+    }
+    StaticTransform tf = subTF ? *subTF : StaticTransform();
+    data->objects.push_back(ObjectRef{true, b.addInstance(m_aggregate, tf)});
+}
+
+void CameraNode::getRenderingData(GpuSceneBuilder&, const StaticTransform* subTF, RenderingData* data) {
+    data->camera = m_camera;
+    data->cameraTransform = subTF ? *subTF : StaticTransform();
+    data->hasCameraTransform = subTF != nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// aggregates
+// ---------------------------------------------------------------------------------------------
+
+static Vec3 vpos(const SlrGpuVertex& v) { return Vec3(v.position[0], v.position[1], v.position[2]); }
+
+uint32_t GpuSceneBuilder::createAggregate(std::vector<ObjectRef>&& objects) {
+    aggregates.emplace_back();
+    const uint32_t id = (uint32_t)aggregates.size() - 1;
+    Aggregate& ag = aggregates.back();
+    ag.objects = std::move(objects);
+
+    PrimitiveSet ps;
+    ps.prims.reserve(ag.objects.size());
+    for (const ObjectRef& o : ag.objects) {
+        if (!o.isInstance) {
+            const SlrGpuTriangle& t = flat.triangles[o.id];
+            ps.addTriangle(vpos(flat.vertices[t.v[0]]), vpos(flat.vertices[t.v[1]]), vpos(flat.vertices[t.v[2]]));
+        } else {
+            ag.containsInstances = true;
+            const Aggregate& nested = aggregates[instanceAggregate[o.id]];
+            if (nested.containsInstances)
+                throw std::runtime_error("instancing nested deeper than one level is not supported by the GPU traversal yet");
+            Mat4 m;
+            std::memcpy(static_cast<void*>(&m), flat.instances[o.id].mat, sizeof(float) * 16);
+            // TransformedSurfaceObject::bounds / costForIntersect (SurfaceObject.cpp:303-305, SurfaceObject.h:206)
+            float cost = nested.objects.size() == 1 ? 1.0f : nested.sbvh.cost;
+            ps.addBox(transformBounds(m, nested.sbvh.bounds), cost);
+        }
+    }
+    ag.sbvh.build(ps);
+    ag.qbvh.build(ag.sbvh, ps);
+
+    // light list: emitting objects in object order (SurfaceObject.cpp:232-252)
+    for (const ObjectRef& o : ag.objects) {
+        if (!o.isInstance) {
+            if (triangleEmits[o.id]) {
+                flat.triangles[o.id].light_index = (uint32_t)ag.lights.size();
+                ag.lights.push_back(SlrGpuLight{o.id, 1.0f});
+            }
+        } else {
+            const Aggregate& nested = aggregates[instanceAggregate[o.id]];
+            if (!nested.lights.empty()) {
+                // importance of an aggregate = integral of its light distribution (compensated sum of importances)
+                float sum = 0.0f, comp = 0.0f;
+                for (const SlrGpuLight& l : nested.lights) { float y = l.importance - comp; float t = sum + y; comp = (t - sum) - y; sum = t; }
+                ag.lights.push_back(SlrGpuLight{0x80000000u | o.id, sum});
+            }
+        }
+    }
+    return id;
+}
+
+uint32_t GpuSceneBuilder::addInstance(uint32_t aggregate, const StaticTransform& tf) {
+    SlrGpuInstance inst;
+    std::memset(&inst, 0, sizeof(inst));
+    std::memcpy(inst.mat, &tf.mat, sizeof(float) * 16);
+    std::memcpy(inst.mat_inv, &tf.matInv, sizeof(float) * 16);
+    inst.root_node = 0;           // patched in finalize()
+    inst.light_base = SLRGPU_INVALID_ID;
+    inst.num_lights = 0;
+    flat.instances.push_back(inst);
+    instanceAggregate.push_back(aggregate);
+    return (uint32_t)flat.instances.size() - 1;
+}
+
+void GpuSceneBuilder::finalize(uint32_t top) {
+    std::vector<uint32_t> order;
+    order.push_back(top);
+    for (uint32_t i = 0; i < aggregates.size(); ++i) if (i != top) order.push_back(i);
+
+    std::vector<uint32_t> nodeBase(aggregates.size()), leafBase(aggregates.size()), lightBase(aggregates.size());
+    uint64_t nNodes = 0, nLeaves = 0, nLights = 0;
+    for (uint32_t a : order) {
+        nodeBase[a] = (uint32_t)nNodes; leafBase[a] = (uint32_t)nLeaves; lightBase[a] = (uint32_t)nLights;
+        nNodes += aggregates[a].qbvh.nodes.size();
+        nLeaves += aggregates[a].qbvh.refs.size();
+        nLights += aggregates[a].lights.size();
+    }
+    if (nNodes > 0x07FFFFFFull || nLeaves > 0x07FFFFFFull)
+        throw std::runtime_error("scene exceeds the 27-bit node / leaf index of the QBVH child word");
+    flat.nodes.resize(nNodes);
+    flat.leaves.resize(nLeaves);
+    flat.lights.resize(nLights);
+    flat.numTopLights = (uint32_t)aggregates[top].lights.size();
+    flat.stats.clear();
+
+    for (uint32_t a : order) {
+        const Aggregate& ag = aggregates[a];
+        for (size_t i = 0; i < ag.qbvh.nodes.size(); ++i) {
+            const QBVHNode& s = ag.qbvh.nodes[i];
+            SlrGpuBvhNode& d = flat.nodes[nodeBase[a] + i];
+            static_assert(sizeof(QBVHNode) == sizeof(SlrGpuBvhNode), "node layouts must match");
+            std::memcpy(&d, &s, sizeof(d));
+            for (int l = 0; l < 4; ++l) {
+                uint32_t c = s.child[l];
+                if (c == kQBVHEmptyChild) continue;
+                uint32_t idx = qbvhChildIdx(c) + (qbvhChildIsLeaf(c) ? leafBase[a] : nodeBase[a]);
+                d.child[l] = (c & 0xF8000000u) | idx;
+            }
+        }
+        for (size_t i = 0; i < ag.qbvh.refs.size(); ++i) {
+            const ObjectRef& o = ag.objects[ag.qbvh.refs[i]];
+            SlrGpuLeafRecord& r = flat.leaves[leafBase[a] + i];
+            std::memset(&r, 0, sizeof(r));
+            uint32_t idBits;
+            if (!o.isInstance) {
+                const SlrGpuTriangle& t = flat.triangles[o.id];
+                Vec3 p0 = vpos(flat.vertices[t.v[0]]), p1 = vpos(flat.vertices[t.v[1]]), p2 = vpos(flat.vertices[t.v[2]]);
+                Vec3 e1 = p1 - p0, e2 = p2 - p0;
+                r.a[0] = p0.x; r.a[1] = p0.y; r.a[2] = p0.z;
+                r.b[0] = e1.x; r.b[1] = e1.y; r.b[2] = e1.z;
+                r.c[0] = e2.x; r.c[1] = e2.y; r.c[2] = e2.z;
+                uint32_t flags = t.alpha_map != SLRGPU_INVALID_ID ? SLRGPU_LEAF_FLAG_ALPHA_TEST : 0u;
+                std::memcpy(&r.b[3], &flags, 4);
+                idBits = o.id;
+            } else {
+                idBits = 0x80000000u | o.id;
+            }
+            std::memcpy(&r.a[3], &idBits, 4);
+        }
+        for (size_t i = 0; i < ag.lights.size(); ++i) flat.lights[lightBase[a] + i] = ag.lights[i];
+        FlatScene::AggregateStats st;
+        st.numObjects = (uint32_t)ag.objects.size();
+        st.sbvhNodes = (uint32_t)ag.sbvh.nodes.size(); st.sbvhRefs = (uint32_t)ag.sbvh.refs.size(); st.sbvhDepth = ag.sbvh.depth;
+        st.qbvhNodes = (uint32_t)ag.qbvh.nodes.size(); st.qbvhDepth = ag.qbvh.depth;
+        st.nodeBase = nodeBase[a]; st.leafBase = leafBase[a];
+        st.sbvhCost = ag.sbvh.cost; st.qbvhCost = ag.qbvh.cost;
+        flat.stats.push_back(st);
+    }
+    for (size_t i = 0; i < flat.instances.size(); ++i) {
+        const uint32_t a = instanceAggregate[i];
+        flat.instances[i].root_node = nodeBase[a];
+        flat.instances[i].light_base = aggregates[a].lights.empty() ? SLRGPU_INVALID_ID : lightBase[a];
+        flat.instances[i].num_lights = (uint32_t)aggregates[a].lights.size();
+    }
+    const BBox& wb = aggregates[top].sbvh.bounds;
+    Vec3 c = wb.centroid();
+    flat.worldCenter[0] = c.x; flat.worldCenter[1] = c.y; flat.worldCenter[2] = c.z;
+    flat.worldRadius = (wb.hi - c).length();
+}
+
+// ---------------------------------------------------------------------------------------------
+// scene
+// ---------------------------------------------------------------------------------------------
+
+Scene::Scene() : m_root(std::make_shared<InternalNode>()) { m_root->name = "root"; }
+
+void FlatScene::describe(SlrGpuSceneDesc* d) const {
+    std::memset(d, 0, sizeof(*d));
+    d->struct_size = sizeof(SlrGpuSceneDesc);
+    d->rgb_mode = rgbMode ? 1 : 0;
+    d->bvh_nodes = nodes.data();       d->num_bvh_nodes = (uint32_t)nodes.size();
+    d->leaf_records = leaves.data();   d->num_leaf_records = (uint32_t)leaves.size();
+    d->instances = instances.data();   d->num_instances = (uint32_t)instances.size();
+    d->triangles = triangles.data();   d->num_triangles = (uint32_t)triangles.size();
+    d->vertices = vertices.data();     d->num_vertices = (uint32_t)vertices.size();
+    d->materials = materials.data();   d->num_materials = (uint32_t)materials.size();
+    d->textures = textures.data();     d->num_textures = (uint32_t)textures.size();
+    d->spectra = spectra.data();       d->num_spectra = (uint32_t)spectra.size();
+    d->spectrum_data = spectrumData.data(); d->num_spectrum_floats = (uint32_t)spectrumData.size();
+    d->images = images.data();         d->num_images = (uint32_t)images.size();
+    d->image_data = imageData.data();  d->image_data_bytes = imageData.size();
+    d->lights = lights.data();         d->num_lights = (uint32_t)lights.size();
+    d->num_top_lights = numTopLights;
+    for (int i = 0; i < 3; ++i) d->world_center[i] = worldCenter[i];
+    d->world_radius = worldRadius;
+    d->camera = camera;
+    d->environment.present = envPresent ? 1 : 0;
+    d->environment.material = envMaterial;
+    d->environment.map_width = envMapWidth; d->environment.map_height = envMapHeight;
+    d->environment.row_pdf = envRowPdf.data(); d->environment.row_cdf = envRowCdf.data();
+    d->environment.row_integral = envRowIntegral.data();
+    d->environment.marginal_pdf = envMarginalPdf.data(); d->environment.marginal_cdf = envMarginalCdf.data();
+    d->environment.marginal_integral = envMarginalIntegral;
+}
+
+}  // namespace slr

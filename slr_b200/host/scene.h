@@ -1,0 +1,198 @@
+// Host-side scene graph and its flattening into the SoA buffers the GPU consumes.
+//
+// Mirrors the part of libSLRSceneGraph / libSLR that feeds the renderer, with the same names where a
+// user of the reference would look for them:
+//   InternalNode / TriangleMeshNode / ReferenceNode / CameraNode / InfiniteSphereNode
+//       libSLRSceneGraph/nodes.h, nodes.cpp:110-212, TriangleMeshNode.cpp:58-112, InfiniteSphereNode.cpp
+//   Scene::build            libSLRSceneGraph/Scene.cpp:28-44  +  SLR::Scene::build SurfaceObject.cpp:396-406
+//   SurfaceObjectAggregate  libSLR/Core/SurfaceObject.cpp:226-253 (accelerator + light list)
+// Instead of allocating one heap object per triangle (SingleSurfaceObject + Triangle + 3 Vertex*),
+// flattening appends to flat arrays: SlrGpuVertex / SlrGpuTriangle records, per-aggregate object
+// lists, and per-aggregate SBVH -> QBVH trees that are concatenated into one node array and one
+// leaf-record array for upload (include/slrgpu.h).
+#pragma once
+#include "../../include/slrgpu.h"
+#include "bvh.h"
+#include "geom.h"
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace slr {
+
+class SurfaceMaterial;
+class Normal3DTexture;
+class FloatTexture;
+class IBLEmission;
+class SpectrumTexture;
+class GpuSceneBuilder;
+typedef std::shared_ptr<SurfaceMaterial> SurfaceMaterialRef;
+typedef std::shared_ptr<Normal3DTexture> Normal3DTextureRef;
+typedef std::shared_ptr<FloatTexture> FloatTextureRef;
+typedef std::shared_ptr<SpectrumTexture> SpectrumTextureRef;
+
+class PerspectiveCamera {
+public:
+    float sensitivity, aspect, fovY, lensRadius, imgPlaneDistance, objPlaneDistance;
+    PerspectiveCamera(float sens, float asp, float fov, float lensR, float imgDist, float objDist)
+        : sensitivity(sens), aspect(asp), fovY(fov), lensRadius(lensR), imgPlaneDistance(imgDist), objPlaneDistance(objDist) {}
+};
+
+// One object of an aggregate, in the order the reference's surfObjs vector would hold them.
+struct ObjectRef {
+    bool isInstance;
+    uint32_t id;            // triangle prim_id, or instance id
+};
+
+struct RenderingData {
+    std::vector<ObjectRef> objects;
+    std::shared_ptr<PerspectiveCamera> camera;
+    StaticTransform cameraTransform;
+    bool hasCameraTransform = false;
+};
+
+class Node {
+public:
+    std::string name;
+    virtual ~Node() {}
+    virtual bool isInstanced() const { return false; }
+    // `subTF` is the accumulated parent transform or null (nodes.cpp:110-141).
+    virtual void getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) = 0;
+};
+typedef std::shared_ptr<Node> NodeRef;
+
+class InternalNode : public Node {
+    std::vector<NodeRef> m_children;
+    StaticTransform m_localToWorld;
+public:
+    bool addChildNode(const NodeRef& n);
+    void setTransform(const StaticTransform& t) { m_localToWorld = t; }
+    const StaticTransform& getTransform() const { return m_localToWorld; }
+    const std::vector<NodeRef>& children() const { return m_children; }
+    void getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) override;
+};
+typedef std::shared_ptr<InternalNode> InternalNodeRef;
+
+class TriangleMeshNode : public Node {
+public:
+    struct MaterialGroup {
+        SurfaceMaterialRef material;
+        Normal3DTextureRef normalMap;
+        FloatTextureRef alphaMap;
+        std::vector<uint32_t> indices;     // 3 per triangle
+    };
+private:
+    std::vector<Vertex> m_vertices;
+    std::vector<MaterialGroup> m_groups;
+    bool m_flattened = false;
+public:
+    uint64_t addVertex(const Vertex& v) { m_vertices.push_back(v); return m_vertices.size() - 1; }
+    void addTriangles(const SurfaceMaterialRef& mat, const Normal3DTextureRef& normalMap, const FloatTextureRef& alphaMap,
+                      std::vector<uint32_t>&& indices);
+    const std::vector<Vertex>& vertices() const { return m_vertices; }
+    const std::vector<MaterialGroup>& groups() const { return m_groups; }
+    void getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) override;
+};
+typedef std::shared_ptr<TriangleMeshNode> TriangleMeshNodeRef;
+
+class ReferenceNode : public Node {
+    NodeRef m_node;
+    bool m_ready = false;
+    uint32_t m_aggregate = 0;
+public:
+    explicit ReferenceNode(const NodeRef& n) : m_node(n) {}
+    bool isInstanced() const override { return true; }
+    void getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) override;
+};
+
+class CameraNode : public Node {
+    std::shared_ptr<PerspectiveCamera> m_camera;
+public:
+    explicit CameraNode(const std::shared_ptr<PerspectiveCamera>& c) : m_camera(c) {}
+    void getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) override;
+};
+
+// Environment light: InfiniteSphereNode (libSLRSceneGraph/InfiniteSphereNode.cpp) holding an
+// IBLEmission over an image spectrum texture.
+class InfiniteSphereNode {
+public:
+    std::shared_ptr<IBLEmission> emission;
+    explicit InfiniteSphereNode(const std::shared_ptr<IBLEmission>& e) : emission(e) {}
+};
+
+// The flattened scene: owns every buffer SlrGpuSceneDesc points into.
+struct FlatScene {
+    std::vector<SlrGpuBvhNode> nodes;
+    std::vector<SlrGpuLeafRecord> leaves;
+    std::vector<SlrGpuInstance> instances;
+    std::vector<SlrGpuTriangle> triangles;
+    std::vector<SlrGpuVertex> vertices;
+    std::vector<SlrGpuMaterial> materials;
+    std::vector<SlrGpuTexture> textures;
+    std::vector<SlrGpuSpectrum> spectra;
+    std::vector<float> spectrumData;
+    std::vector<SlrGpuImage> images;
+    std::vector<uint8_t> imageData;
+    std::vector<SlrGpuLight> lights;
+    uint32_t numTopLights = 0;
+    // environment
+    bool envPresent = false;
+    uint32_t envMaterial = SLRGPU_INVALID_ID, envMapWidth = 0, envMapHeight = 0;
+    std::vector<float> envRowPdf, envRowCdf, envRowIntegral, envMarginalPdf, envMarginalCdf;
+    float envMarginalIntegral = 0.0f;
+    SlrGpuCamera camera = {};
+    bool hasCamera = false;
+    float worldCenter[3] = {0, 0, 0};
+    float worldRadius = 0.0f;
+    bool rgbMode = false;
+    // build statistics (per aggregate: 0 = top level)
+    struct AggregateStats { uint32_t numObjects, sbvhNodes, sbvhRefs, sbvhDepth, qbvhNodes, qbvhDepth, nodeBase, leafBase; float sbvhCost, qbvhCost; };
+    std::vector<AggregateStats> stats;
+    double buildSeconds = 0.0;
+
+    // Fills a descriptor whose pointers alias this object's vectors (valid while *this is alive and unchanged).
+    void describe(SlrGpuSceneDesc* desc) const;
+};
+
+class Scene {
+    InternalNodeRef m_root;
+    std::shared_ptr<InfiniteSphereNode> m_env;
+public:
+    Scene();
+    const InternalNodeRef& rootNode() const { return m_root; }
+    void setEnvNode(const std::shared_ptr<InfiniteSphereNode>& e) { m_env = e; }
+    const std::shared_ptr<InfiniteSphereNode>& envNode() const { return m_env; }
+    // Flattens the graph, builds every aggregate's SBVH -> QBVH and the shading tables.
+    // Throws std::runtime_error on unsupported input (e.g. instancing nested deeper than one level).
+    void build(FlatScene* out, bool rgbMode = false);
+};
+
+// Working state of one flattening pass.
+class GpuSceneBuilder {
+public:
+    struct Aggregate {
+        std::vector<ObjectRef> objects;
+        SBVH sbvh;
+        QBVH qbvh;
+        std::vector<SlrGpuLight> lights;     // emitting objects in object order
+        bool containsInstances = false;
+    };
+    FlatScene& flat;
+    std::vector<Aggregate> aggregates;       // nested ones first as they are discovered; index = aggregate id
+    std::vector<uint32_t> instanceAggregate; // instance id -> aggregate id
+    std::vector<uint8_t> triangleEmits;      // prim_id -> is emitting
+
+    explicit GpuSceneBuilder(FlatScene& f) : flat(f) {}
+    // Builds trees + light list for `objects`; returns the aggregate id.
+    uint32_t createAggregate(std::vector<ObjectRef>&& objects);
+    uint32_t addInstance(uint32_t aggregate, const StaticTransform& tf);
+    // Concatenates all aggregates (top level = `top` first) into flat.nodes / flat.leaves.
+    void finalize(uint32_t top);
+    // shading tables (materials.cpp)
+    uint32_t exportMaterial(const SurfaceMaterial* m);
+    uint32_t exportNormalTexture(const Normal3DTexture* t);
+    uint32_t exportFloatTexture(const FloatTexture* t);
+    bool materialEmits(const SurfaceMaterial* m) const;
+};
+
+}  // namespace slr

@@ -1,0 +1,116 @@
+"""GPU parity: the CUDA traversal, called through the C ABI, must report the reference's hit
+primitive/instance ids bit-exactly (and t, u, v bit-exactly too -- stricter than the 1e-5 relative
+tolerance north_star allows), on the golden batches and against the CPU restatement at larger sizes."""
+import numpy as np
+import pytest
+
+import oracle_util as ou
+from slr_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert capi.gpu.slrgpu_device_count() > 0, "these tests need a CUDA device"
+
+
+def assert_same_hits(got, want_prim, want_inst, want_t_bits, want_u_bits=None, want_v_bits=None):
+    assert np.array_equal(got["prim"], want_prim), f"{(got['prim'] != want_prim).sum()} hit-id mismatches"
+    assert np.array_equal(got["inst"], want_inst)
+    hit = want_prim != 0xFFFFFFFF
+    assert np.array_equal(got["t"].view(np.uint32)[hit], want_t_bits[hit])
+    if want_u_bits is not None:
+        assert np.array_equal(got["u"].view(np.uint32)[hit], want_u_bits[hit])
+        assert np.array_equal(got["v"].view(np.uint32)[hit], want_v_bits[hit])
+    assert np.all(np.isinf(got["t"][~hit]))
+
+
+@pytest.mark.parametrize("name", list(ou.CASES))
+def test_golden_hits_bit_exact(name):
+    meshes, placements, rays = ou.CASES[name]()
+    hs = ou.build_host_scene(meshes, placements)
+    gs = capi.GpuScene(hs)
+    g = np.load(f"{ou.GOLDEN}/intersect_{name}.npz")
+    got = gs.intersect(rays)
+    assert_same_hits(got, g["prim"], g["inst"], g["t_bits"], g["u_bits"], g["v_bits"])
+
+
+@pytest.mark.parametrize("name", list(ou.CASES))
+def test_counters_match_oracle_order_traversal(name):
+    """Nodes popped / leaf records tested per ray are a property of (tree, ray, visiting order):
+    equal counts mean the GPU walks the tree exactly as the reference does."""
+    meshes, placements, rays = ou.CASES[name]()
+    hs = ou.build_host_scene(meshes, placements)
+    gs = capi.GpuScene(hs)
+    got = gs.intersect(rays, counters=True)
+    want = ou.restate_intersect(hs, rays)
+    assert np.array_equal(got["nodes"], want["nodes"])
+    assert np.array_equal(got["tris"], want["tris"])
+
+
+def test_large_scene_against_restatement():
+    """500k triangles (spatial splits), 1M incoherent + coherent rays, vs the CPU restatement."""
+    pos, idx = synth.heightfield(500)
+    hs = ou.build_host_scene([(pos, idx)], [(0, 0, None)])
+    gs = capi.GpuScene(hs)
+    rays = synth.concat_rays(synth.random_rays(500000, pos.min(0), pos.max(0), seed=12345),
+                             synth.aimed_rays(500000, pos.min(0), pos.max(0), seed=777))
+    got = gs.intersect(rays)
+    want = ou.restate_intersect(hs, rays)
+    assert want["overflow"] == 0
+    assert_same_hits(got, want["prim"], want["inst"], want["t"].view(np.uint32), want["u"].view(np.uint32), want["v"].view(np.uint32))
+
+
+def test_occlusion_equals_closest_hit_boolean():
+    """Scene::testVisibility is a closest-hit query reduced to a boolean; the early-exit kernel must agree."""
+    meshes, placements, rays = ou.case_instanced()
+    rays = dict(rays)
+    rays["tmin"] = np.full_like(rays["tmin"], 1e-4)
+    rays["tmax"] = np.full_like(rays["tmax"], 1.75)
+    hs = ou.build_host_scene(meshes, placements)
+    gs = capi.GpuScene(hs)
+    occ, _ = gs.occluded(rays)
+    want = ou.restate_intersect(hs, rays)
+    assert np.array_equal(occ.astype(bool), want["prim"] != 0xFFFFFFFF)
+
+
+def test_properties_at_scale():
+    """Size-independent properties on a batch too big for the CPU oracle: (1) shrinking tmax to just
+    below the reported t turns a hit into a miss or a strictly closer... never a farther hit;
+    (2) re-tracing with tmax = t (ties accepted) reproduces the same primitive; (3) determinism."""
+    pos, idx = synth.heightfield(300)
+    hs = ou.build_host_scene([(pos, idx)], [(0, 0, None)])
+    gs = capi.GpuScene(hs)
+    rays = synth.random_rays(4_000_000, pos.min(0), pos.max(0), seed=2024)
+    a = gs.intersect(rays)
+    b = gs.intersect(rays)
+    assert np.array_equal(a["prim"], b["prim"]) and np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
+    hit = a["prim"] != 0xFFFFFFFF
+    assert 0.05 < hit.mean() < 0.95
+    again = dict(rays)
+    again["tmax"] = np.where(hit, a["t"], rays["tmax"]).astype(np.float32)
+    c = gs.intersect(again)
+    assert np.array_equal(c["prim"], a["prim"])
+    below = dict(rays)
+    below["tmax"] = np.where(hit, np.nextafter(a["t"], np.float32(0)), rays["tmax"]).astype(np.float32)
+    d = gs.intersect(below)
+    still = d["prim"] != 0xFFFFFFFF
+    assert not np.any(still & ~hit)
+    assert np.all(d["t"][still] < a["t"][still])
+
+
+def test_edge_cases_through_abi():
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 0, 1]], np.float32)
+    idx = np.array([[0, 2, 1]], np.uint32)
+    hs = ou.build_host_scene([(pos, idx)], [(0, 0, None)])
+    gs = capi.GpuScene(hs)
+    empty = {k: np.zeros(0, np.float32) for k in ("ox", "oy", "oz", "dx", "dy", "dz", "tmin", "tmax")}
+    assert gs.intersect(empty)["prim"].shape == (0,)
+    rays = {"ox": np.array([0.25, 5.0, 0.25], np.float32), "oy": np.array([1.0, 1.0, 1.0], np.float32),
+            "oz": np.array([0.25, 5.0, 0.25], np.float32), "dx": np.zeros(3, np.float32),
+            "dy": -np.ones(3, np.float32), "dz": np.zeros(3, np.float32),
+            "tmin": np.zeros(3, np.float32), "tmax": np.array([np.inf, np.inf, 0.5], np.float32)}
+    r = gs.intersect(rays)
+    assert list(r["prim"]) == [0, 0xFFFFFFFF, 0xFFFFFFFF] and r["t"][0] == 1.0
+    assert gs.device_bytes >= 128 + 48
