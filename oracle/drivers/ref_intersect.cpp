@@ -31,7 +31,7 @@ int main(int argc, char** argv) {
     initSpectrum();
     GeomSpec spec = readGeomSpec(argv[1]);
     RayFile rays = readRays(argv[2]);
-    const char* treesOut = argc > 4 ? argv[4] : nullptr;
+    const char* treesOut = (argc > 4 && argv[4][0] && strcmp(argv[4], "-") != 0) ? argv[4] : nullptr;
     unsigned threads = argc > 5 ? (unsigned)atoi(argv[5]) : std::thread::hardware_concurrency();
     if (threads == 0) threads = 1;
 

@@ -60,7 +60,7 @@ def run_ref_intersect(meshes, placements, rays, want_trees=True, threads=None):
         spec, rf, hf, tf = (os.path.join(d, n) for n in ("spec.bin", "rays.bin", "hits.bin", "trees.bin"))
         synth.write_geom_spec(spec, meshes, placements)
         synth.write_rays(rf, rays)
-        cmd = [os.path.join(REF_DIR, "ref_intersect"), spec, rf, hf, tf if want_trees else ""]
+        cmd = [os.path.join(REF_DIR, "ref_intersect"), spec, rf, hf, tf if want_trees else "-"]
         if threads is not None:
             cmd.append(str(threads))
         r = subprocess.run(cmd, capture_output=True, text=True, check=True)
