@@ -93,7 +93,9 @@ typedef struct SlrGpuInstance {
     uint32_t root_node;     /* global node index of the nested BVH's root */
     uint32_t light_base;    /* first entry of the nested aggregate's light list in `lights`, or INVALID */
     uint32_t num_lights;
-    uint32_t pad;
+    uint32_t light_index;   /* position of this instance in ITS parent's light list, or INVALID */
+    float light_importance; /* integral of the nested light distribution (importance of the instance) */
+    uint32_t pad[3];
 } SlrGpuInstance;
 
 /* 32-byte per-triangle shading record (indexed by prim_id). */
@@ -204,10 +206,15 @@ typedef struct SlrGpuMaterial {
 } SlrGpuMaterial;
 
 /* One entry of an aggregate's light list (SurfaceObjectAggregate ctor, SurfaceObject.cpp:232-252):
- * object = prim_id of an emitting triangle, or 0x80000000|instance_id of an emitting instance. */
+ * object = prim_id of an emitting triangle, or 0x80000000|instance_id of an emitting instance.
+ * pmf / cdf_lo / cdf_hi are this entry's slice of the aggregate's RegularConstantDiscrete1D
+ * (distributions.cpp:81-119), built on the host with the reference's compensated sums:
+ * pmf = importance / integral, cdf_lo = CDF[i], cdf_hi = CDF[i+1]. */
 typedef struct SlrGpuLight {
     uint32_t object;
     float importance;
+    float pmf, cdf_lo, cdf_hi;
+    uint32_t pad[3];
 } SlrGpuLight;
 
 /* PerspectiveCamera (Cameras/PerspectiveCamera.cpp:15-74) with its static transform. */
@@ -271,7 +278,7 @@ typedef struct SlrGpuSceneDesc {
      * aggregates' lists follow (SlrGpuInstance::light_base). */
     const SlrGpuLight* lights;             uint32_t num_lights;
     uint32_t num_top_lights;
-    uint32_t pad0;
+    float top_light_importance;      /* SurfaceObjectAggregate::importance() of the top-level aggregate */
 
     float world_center[3];           /* Scene::build, SurfaceObject.cpp:396-406 */
     float world_radius;

@@ -37,6 +37,32 @@ SLRGPU_API int slrhost_builder_instance_mesh(SlrHostBuilder* b, int mesh, const 
 /* Flattens and builds (SBVH -> QBVH). rgb_mode: 0 spectral, 1 RGB. */
 SLRGPU_API int slrhost_builder_finish(SlrHostBuilder* b, int rgb_mode, SlrHostScene** out);
 
+/* --- scene description language (libSLRSceneGraph/API.hpp:20 readScene + Scene::build) --- */
+/* Parses and executes a scene file, flattens it and builds the acceleration structures.
+ * rgb_mode: 0 = 16-wavelength spectral, 1 = RGB. */
+SLRGPU_API int slrhost_read_scene(const char* path, int rgb_mode, SlrHostScene** out);
+/* Rendering context read from the file (setRenderer / setRenderSettings):
+ * ctx8 = {width, height, samples, rngSeed, timeStart, timeEnd, brightness, 1 if a renderer was set}. */
+SLRGPU_API int slrhost_scene_context(const SlrHostScene* s, double* ctx8);
+/* Renderer::render through GPUPathTracingRenderer on `device`: width/height/spp <= 0 take the
+ * scene file's values. On return accum (if non-NULL, width*height*channels floats) holds the
+ * sensor's un-normalised sums; stats6 = {paths, rays, deviceSeconds, wallSeconds, uploadSeconds, channels}.
+ * bmp_dir: directory for the progressive NNN.bmp files, or NULL to skip image export. */
+SLRGPU_API int slrhost_render(SlrHostScene* s, int device, int width, int height, int spp, int seed,
+                              const char* bmp_dir, float* accum, double* stats6);
+/* Tone-maps a frame buffer exactly like ImageSensor::saveImage (ImageSensor.cpp:138-186). */
+SLRGPU_API int slrhost_save_bmp(const char* path, const float* accum, int width, int height, int channels,
+                                float scale, float sensitivity);
+/* linear sRGB (3 floats per pixel) of a frame buffer, before tone mapping */
+SLRGPU_API int slrhost_accum_to_rgb(const float* accum, int width, int height, int channels, float scale, float* rgb);
+
+/* --- synthetic asset writers (tests / bench build their own models and environment maps) --- */
+SLRGPU_API int slrhost_write_assbin(const char* path, const float* positions, const float* normals,
+                                    const float* tangents, const float* uvs, uint32_t num_vertices,
+                                    const uint32_t* indices, uint32_t num_triangles, const char* material_name,
+                                    const float* diffuse_rgb);
+SLRGPU_API int slrhost_write_exr(const char* path, uint32_t width, uint32_t height, const float* rgba);
+
 SLRGPU_API void slrhost_scene_destroy(SlrHostScene* s);
 /* Fills `desc` with pointers into the scene's buffers (valid until slrhost_scene_destroy). */
 SLRGPU_API int slrhost_scene_describe(const SlrHostScene* s, SlrGpuSceneDesc* desc);

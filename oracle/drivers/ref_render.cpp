@@ -1,0 +1,96 @@
+// Reference renderer driver (test infrastructure + CPU baseline): the reference's own HostProgram
+// flow (HostProgram/main.cpp:20-62) -- initSpectrum, readScene, Scene::build, Renderer::render --
+// with the renderer/size/seed overridable from the command line, the sensor dumped as raw floats and
+// a timing JSON on stderr.
+//   ref_render scene.txt out.bin [spp] [width] [height] [seed] [qbvh=0|1]
+// out.bin: u32 width, height, channels(16), then width*height*16 f32 (row-major, un-normalised sums,
+// i.e. ImageSensor::pixel(x, y) after PathTracingRenderer::render). spp/width/height/seed <= 0 keep the
+// scene file's values. The renderer is always the unidirectional PathTracingRenderer. With qbvh=1 every
+// aggregate's accelerator is swapped for QBVH(SBVH) after construction.
+#include <libSLR/Core/SurfaceObject.h>
+#include <libSLR/Core/RenderSettings.h>
+#include <libSLR/Core/ImageSensor.h>
+#include <libSLR/Core/cameras.h>
+#include <libSLR/Accelerator/SBVH.h>
+#include <libSLR/Accelerator/QBVH.h>
+#include <libSLR/Memory/ArenaAllocator.h>
+#include <libSLR/Renderers/PathTracingRenderer.h>
+#include <libSLR/BasicTypes/Spectrum.h>
+#include <libSLR/BasicTypes/SpectrumTypes.h>
+#include <libSLRSceneGraph/Scene.h>
+#include <libSLRSceneGraph/API.hpp>
+#include <chrono>
+#include <set>
+#include <thread>
+#include <unistd.h>
+
+using namespace SLR;
+
+static void swapToQBVH(const SurfaceObjectAggregate* aggr, std::set<const SurfaceObjectAggregate*>& seen) {
+    if (!aggr || seen.count(aggr)) return;
+    seen.insert(aggr);
+    SBVH* sbvh = dynamic_cast<SBVH*>(aggr->m_accelerator);
+    if (!sbvh) return;
+    for (const SurfaceObject* o : sbvh->m_objLists)
+        if (const TransformedSurfaceObject* t = dynamic_cast<const TransformedSurfaceObject*>(o))
+            swapToQBVH(dynamic_cast<const SurfaceObjectAggregate*>(t->m_surfObj), seen);
+    const_cast<SurfaceObjectAggregate*>(aggr)->m_accelerator = new QBVH(*sbvh);
+}
+
+int main(int argc, char** argv) {
+    if (argc < 3) { fprintf(stderr, "usage: ref_render scene.txt out.bin [spp] [width] [height] [seed] [qbvh]\n"); return 2; }
+    const int spp = argc > 3 ? atoi(argv[3]) : 0, w = argc > 4 ? atoi(argv[4]) : 0, h = argc > 5 ? atoi(argv[5]) : 0;
+    const int seed = argc > 6 ? atoi(argv[6]) : 0, qbvh = argc > 7 ? atoi(argv[7]) : 0;
+    initSpectrum();
+    auto t0 = std::chrono::steady_clock::now();
+    SLRSceneGraph::SceneRef scene = createShared<SLRSceneGraph::Scene>();
+    SLRSceneGraph::RenderingContext context;
+    context.width = 1024; context.height = 1024; context.timeStart = 0; context.timeEnd = 0; context.brightness = 1.0f; context.rngSeed = 1509761209;
+    if (!SLRSceneGraph::readScene(argv[1], scene, &context)) { fprintf(stderr, "Failed to read a scene file.\n"); return 1; }
+    auto t1 = std::chrono::steady_clock::now();
+    const Scene* rawScene;
+    ArenaAllocator mem;
+    scene->build(&rawScene, mem);
+    if (qbvh) { std::set<const SurfaceObjectAggregate*> seen; swapToQBVH(rawScene->m_aggregate, seen); }
+    auto t2 = std::chrono::steady_clock::now();
+
+    uint32_t useSpp = spp > 0 ? (uint32_t)spp : 8;
+    if (spp <= 0) if (PathTracingRenderer* pt = dynamic_cast<PathTracingRenderer*>(context.renderer.get())) useSpp = pt->m_samplesPerPixel;
+    RenderSettings settings;
+    settings.addItem(RenderSettingItem::ImageWidth, (int32_t)(w > 0 ? w : context.width));
+    settings.addItem(RenderSettingItem::ImageHeight, (int32_t)(h > 0 ? h : context.height));
+    settings.addItem(RenderSettingItem::TimeStart, context.timeStart);
+    settings.addItem(RenderSettingItem::TimeEnd, context.timeEnd);
+    settings.addItem(RenderSettingItem::Brightness, context.brightness);
+    settings.addItem(RenderSettingItem::RNGSeed, (int32_t)(seed != 0 ? seed : context.rngSeed));
+
+    // the renderer writes NNN.bmp into the working directory: run inside the output file's directory
+    std::string out = argv[2];
+    if (out[0] != '/') { char cwd[4096]; out = std::string(getcwd(cwd, sizeof(cwd))) + "/" + out; }
+    std::string outDir = out.substr(0, out.find_last_of('/'));
+    if (chdir(outDir.c_str()) != 0) perror("chdir");
+
+    PathTracingRenderer renderer(useSpp);
+    auto t3 = std::chrono::steady_clock::now();
+    renderer.render(*rawScene, settings);
+    auto t4 = std::chrono::steady_clock::now();
+
+    ImageSensor* sensor = rawScene->getCamera()->getSensor();
+    uint32_t W = sensor->width(), H = sensor->height(), C = 16;
+    FILE* f = fopen(out.c_str(), "wb");
+    if (!f) { perror(out.c_str()); return 1; }
+    fwrite(&W, 4, 1, f); fwrite(&H, 4, 1, f); fwrite(&C, 4, 1, f);
+    for (uint32_t y = 0; y < H; ++y)
+        for (uint32_t x = 0; x < W; ++x) {
+            DiscretizedSpectrum px = ((const ImageSensor*)sensor)->pixel(x, y);
+            fwrite(px.values, 4, 16, f);
+        }
+    fclose(f);
+    auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    double paths = (double)W * H * useSpp;
+    fprintf(stderr, "{\"width\": %u, \"height\": %u, \"spp\": %u, \"threads\": %u, \"read_s\": %.3f, \"build_s\": %.3f, \"render_s\": %.4f, "
+                    "\"mpaths_per_s\": %.5f, \"accelerator\": \"%s\", \"sensitivity\": %.9g}\n",
+            W, H, useSpp, std::thread::hardware_concurrency(), sec(t0, t1), sec(t1, t2), sec(t3, t4), paths / sec(t3, t4) / 1e6,
+            qbvh ? "QBVH" : "SBVH", (double)sensor->m_sensitivity);
+    return 0;
+}

@@ -31,7 +31,8 @@ class LeafRecord(C.Structure):
 
 class Instance(C.Structure):
     _fields_ = [("mat", c_f * 16), ("mat_inv", c_f * 16), ("root_node", c_u32),
-                ("light_base", c_u32), ("num_lights", c_u32), ("pad", c_u32)]
+                ("light_base", c_u32), ("num_lights", c_u32), ("light_index", c_u32),
+                ("light_importance", c_f), ("pad", c_u32 * 3)]
 
 
 class Triangle(C.Structure):
@@ -65,7 +66,7 @@ class Material(C.Structure):
 
 
 class Light(C.Structure):
-    _fields_ = [("object", c_u32), ("importance", c_f)]
+    _fields_ = [("object", c_u32), ("importance", c_f), ("pmf", c_f), ("cdf_lo", c_f), ("cdf_hi", c_f), ("pad", c_u32 * 3)]
 
 
 class Camera(C.Structure):
@@ -100,7 +101,7 @@ class SceneDesc(C.Structure):
                 ("images", C.POINTER(Image)), ("num_images", c_u32),
                 ("image_data", PU8), ("image_data_bytes", c_u64),
                 ("lights", C.POINTER(Light)), ("num_lights", c_u32),
-                ("num_top_lights", c_u32), ("pad0", c_u32),
+                ("num_top_lights", c_u32), ("top_light_importance", c_f),
                 ("world_center", c_f * 3), ("world_radius", c_f),
                 ("camera", Camera), ("environment", Environment), ("spectral", SpectralTables)]
 
@@ -365,3 +366,93 @@ class GpuScene:
         ms = c_f(0)
         _gpu_check(gpu.slrgpu_occluded_batch(self._s, C.byref(rb), n, occ.ctypes.data_as(PU8), C.byref(ms)), "slrgpu_occluded_batch")
         return occ, ms.value
+
+
+# ---- scene files, rendering front end, asset writers (slrhost.h)
+host.slrhost_read_scene.restype = C.c_int
+host.slrhost_read_scene.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+host.slrhost_scene_context.restype = C.c_int
+host.slrhost_scene_context.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+host.slrhost_render.restype = C.c_int
+host.slrhost_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, PF, C.POINTER(C.c_double)]
+host.slrhost_save_bmp.restype = C.c_int
+host.slrhost_save_bmp.argtypes = [C.c_char_p, PF, C.c_int, C.c_int, C.c_int, c_f, c_f]
+host.slrhost_accum_to_rgb.restype = C.c_int
+host.slrhost_accum_to_rgb.argtypes = [PF, C.c_int, C.c_int, C.c_int, c_f, PF]
+host.slrhost_write_assbin.restype = C.c_int
+host.slrhost_write_assbin.argtypes = [C.c_char_p, PF, PF, PF, PF, c_u32, PU32, c_u32, C.c_char_p, PF]
+host.slrhost_write_exr.restype = C.c_int
+host.slrhost_write_exr.argtypes = [C.c_char_p, c_u32, c_u32, PF]
+gpu.slrgpu_render.restype = C.c_int
+gpu.slrgpu_render.argtypes = [C.c_void_p, C.POINTER(RenderParams), PF, C.POINTER(RenderStats)]
+gpu.slrgpu_render_device.restype = C.c_int
+gpu.slrgpu_render_device.argtypes = [C.c_void_p, C.POINTER(RenderParams), C.c_void_p, C.c_void_p, C.POINTER(RenderStats)]
+
+
+def read_scene(path, rgb_mode=False):
+    """readScene + Scene::build: parse a scene-description file and flatten it."""
+    out = C.c_void_p()
+    _host_check(host.slrhost_read_scene(os.fsencode(path), 1 if rgb_mode else 0, C.byref(out)), "slrhost_read_scene")
+    hs = HostScene(out.value)
+    buf = (C.c_double * 8)()
+    host.slrhost_scene_context(hs.handle, buf)
+    hs.context = {"width": int(buf[0]), "height": int(buf[1]), "samples": int(buf[2]), "rngSeed": int(buf[3]),
+                  "timeStart": buf[4], "timeEnd": buf[5], "brightness": buf[6], "hasRenderer": bool(buf[7])}
+    return hs
+
+
+def host_render(host_scene, width=0, height=0, spp=0, seed=0, device=0, bmp_dir=None):
+    """Renderer::render through the host's GPUPathTracingRenderer. Returns (accum[h, w, c], stats)."""
+    ctx = getattr(host_scene, "context", {"width": 0, "height": 0})
+    w = width or ctx["width"]
+    h = height or ctx["height"]
+    chan = 3 if host_scene.desc.rgb_mode else 16
+    accum = np.zeros((h, w, chan), np.float32)
+    st = (C.c_double * 6)()
+    _host_check(host.slrhost_render(host_scene.handle, device, width, height, spp, seed,
+                                    os.fsencode(bmp_dir) if bmp_dir else None, _pf(accum), st), "slrhost_render")
+    return accum, {"paths": int(st[0]), "rays": int(st[1]), "device_s": st[2], "wall_s": st[3], "upload_s": st[4], "channels": int(st[5])}
+
+
+def gpu_render(gpu_scene, width, height, spp_begin, spp_end, seed=1509761209, time_start=0.0, time_end=0.0, flags=0,
+               pool_size=0, max_path_length=0):
+    """slrgpu_render with host buffers. Returns (accum[h, w, c], RenderStats as dict)."""
+    chan = gpu.slrgpu_scene_channels(gpu_scene.handle)
+    accum = np.zeros((height, width, chan), np.float32)
+    p = RenderParams(C.sizeof(RenderParams), width, height, spp_begin, spp_end, time_start, time_end, seed, max_path_length,
+                     pool_size, flags)
+    st = RenderStats()
+    _gpu_check(gpu.slrgpu_render(gpu_scene.handle, C.byref(p), _pf(accum), C.byref(st)), "slrgpu_render")
+    return accum, {k: getattr(st, k) for k, _ in RenderStats._fields_}
+
+
+def accum_to_rgb(accum, scale):
+    h, w, c = accum.shape
+    rgb = np.empty((h, w, 3), np.float32)
+    a = np.ascontiguousarray(accum, np.float32)
+    _host_check(host.slrhost_accum_to_rgb(_pf(a), w, h, c, scale, _pf(rgb)), "slrhost_accum_to_rgb")
+    return rgb
+
+
+def save_bmp(path, accum, scale, sensitivity=1.0):
+    h, w, c = accum.shape
+    a = np.ascontiguousarray(accum, np.float32)
+    _host_check(host.slrhost_save_bmp(os.fsencode(path), _pf(a), w, h, c, scale, sensitivity), "slrhost_save_bmp")
+
+
+def write_assbin(path, positions, indices, normals=None, tangents=None, uvs=None, material_name="material", diffuse=None):
+    pos = _f32(positions).reshape(-1, 3)
+    idx = np.ascontiguousarray(indices, np.uint32).reshape(-1, 3)
+    nrm = _f32(normals).reshape(-1, 3) if normals is not None else None
+    tng = _f32(tangents).reshape(-1, 3) if tangents is not None else None
+    uv = _f32(uvs).reshape(-1, 2) if uvs is not None else None
+    dif = _f32(diffuse) if diffuse is not None else None
+    _host_check(host.slrhost_write_assbin(os.fsencode(path), _pf(pos), _pf(nrm), _pf(tng), _pf(uv), pos.shape[0],
+                                          idx.ctypes.data_as(PU32), idx.shape[0], material_name.encode(), _pf(dif)),
+                "slrhost_write_assbin")
+
+
+def write_exr(path, rgba):
+    a = _f32(rgba)
+    h, w, _ = a.shape
+    _host_check(host.slrhost_write_exr(os.fsencode(path), w, h, _pf(a)), "slrhost_write_exr")

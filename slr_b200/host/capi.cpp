@@ -1,6 +1,10 @@
 // C entry points of the host library (include/slrhost.h).
 #include "../../include/slrhost.h"
 #include "scene.h"
+#include "renderer.h"
+#include "assets/assbin.h"
+#include "assets/exr.h"
+#include "parser/scene_parser.h"
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -21,7 +25,10 @@ struct SlrHostBuilder {
     std::vector<NodeRef> references;     // one shared ReferenceNode per instanced mesh
 };
 struct SlrHostScene {
-    FlatScene flat;
+    RenderScene render;
+    FlatScene& flat = render.flat;
+    RenderingContext context;
+    bool hasRenderer = false;
 };
 
 static StaticTransform toTransform(const float* m) {
@@ -91,10 +98,127 @@ SLRGPU_API int slrhost_builder_finish(SlrHostBuilder* b, int rgb_mode, SlrHostSc
     *out = nullptr;
     try {
         SlrHostScene* s = new SlrHostScene();
-        try { b->scene.build(&s->flat, rgb_mode != 0); } catch (...) { delete s; throw; }
+        try { b->scene.build(&s->render.flat, rgb_mode != 0); } catch (...) { delete s; throw; }
         *out = s;
         return 0;
     } catch (const std::exception& e) { return fail("%s", e.what()); }
+}
+
+SLRGPU_API int slrhost_read_scene(const char* path, int rgb_mode, SlrHostScene** out) {
+    if (!path || !out) return fail("slrhost_read_scene: null argument");
+    *out = nullptr;
+    try {
+        std::unique_ptr<SlrHostScene> s(new SlrHostScene());
+        Scene graph;
+        std::string err;
+        if (!readScene(path, &graph, &s->context, &err, rgb_mode != 0)) return fail("%s", err.c_str());
+        s->hasRenderer = s->context.renderer != nullptr;
+        graph.build(&s->flat, rgb_mode != 0);
+        *out = s.release();
+        return 0;
+    } catch (const std::exception& e) { return fail("%s", e.what()); }
+}
+
+SLRGPU_API int slrhost_scene_context(const SlrHostScene* s, double* c) {
+    if (!s || !c) return fail("slrhost_scene_context: null argument");
+    c[0] = s->context.width; c[1] = s->context.height; c[2] = s->context.samples; c[3] = s->context.rngSeed;
+    c[4] = s->context.timeStart; c[5] = s->context.timeEnd; c[6] = s->context.brightness; c[7] = s->hasRenderer ? 1 : 0;
+    return 0;
+}
+
+SLRGPU_API int slrhost_render(SlrHostScene* s, int device, int width, int height, int spp, int seed,
+                              const char* bmp_dir, float* accum, double* stats) {
+    if (!s) return fail("slrhost_render: null scene");
+    try {
+        if (!s->flat.hasCamera) return fail("the scene has no camera");
+        if (!s->render.sensor) {
+            float sens = s->flat.camera.sensitivity;
+            float r = s->flat.camera.lens_radius;
+            s->render.sensor = std::make_shared<ImageSensor>(sens > 0 ? sens : (float)(1.0f / (M_PI * r * r)));
+        }
+        RenderSettings settings;
+        settings.addItem(RenderSettingItem::ImageWidth, (int32_t)(width > 0 ? width : s->context.width));
+        settings.addItem(RenderSettingItem::ImageHeight, (int32_t)(height > 0 ? height : s->context.height));
+        settings.addItem(RenderSettingItem::TimeStart, s->context.timeStart);
+        settings.addItem(RenderSettingItem::TimeEnd, s->context.timeEnd);
+        settings.addItem(RenderSettingItem::Brightness, s->context.brightness);
+        settings.addItem(RenderSettingItem::RNGSeed, (int32_t)(seed != 0 ? seed : s->context.rngSeed));
+        GPUPathTracingRenderer renderer(spp > 0 ? (uint32_t)spp : s->context.samples);
+        renderer.device = device;
+        renderer.exportProgressiveImages = bmp_dir != nullptr;
+        if (bmp_dir) renderer.outputDirectory = bmp_dir;
+        renderer.render(s->render, settings);
+        const ImageSensor& sensor = *s->render.sensor;
+        if (accum) std::memcpy(accum, sensor.data(), sizeof(float) * (size_t)sensor.width() * sensor.height() * sensor.channels());
+        if (stats) {
+            const RenderStatistics& st = renderer.lastStatistics;
+            stats[0] = (double)st.paths; stats[1] = (double)st.rays; stats[2] = st.deviceSeconds; stats[3] = st.wallSeconds;
+            stats[4] = st.uploadSeconds; stats[5] = sensor.channels();
+        }
+        return 0;
+    } catch (const std::exception& e) { return fail("%s", e.what()); }
+}
+
+SLRGPU_API int slrhost_save_bmp(const char* path, const float* accum, int width, int height, int channels, float scale, float sensitivity) {
+    if (!path || !accum || width <= 0 || height <= 0) return fail("slrhost_save_bmp: invalid argument");
+    try {
+        ImageSensor sensor(sensitivity);
+        sensor.init(width, height, channels);
+        std::memcpy(sensor.data(), accum, sizeof(float) * (size_t)width * height * channels);
+        sensor.saveImage(path, scale);
+        return 0;
+    } catch (const std::exception& e) { return fail("%s", e.what()); }
+}
+
+SLRGPU_API int slrhost_accum_to_rgb(const float* accum, int width, int height, int channels, float scale, float* rgb) {
+    if (!accum || !rgb || width <= 0 || height <= 0) return fail("slrhost_accum_to_rgb: invalid argument");
+    try {
+        ImageSensor sensor(1.0f);
+        sensor.init(width, height, channels);
+        std::memcpy(sensor.data(), accum, sizeof(float) * (size_t)width * height * channels);
+        for (int y = 0; y < height; ++y)
+            for (int x = 0; x < width; ++x) sensor.pixelRGB(x, y, scale, rgb + 3 * ((size_t)y * width + x));
+        return 0;
+    } catch (const std::exception& e) { return fail("%s", e.what()); }
+}
+
+SLRGPU_API int slrhost_write_assbin(const char* path, const float* positions, const float* normals, const float* tangents,
+                                    const float* uvs, uint32_t nv, const uint32_t* indices, uint32_t nt,
+                                    const char* material_name, const float* diffuse_rgb) {
+    if (!path || !positions || !indices || nv == 0 || nt == 0) return fail("slrhost_write_assbin: invalid argument");
+    assbin::Scene sc;
+    assbin::Mesh m;
+    m.name = "mesh";
+    m.positions.assign(positions, positions + 3ull * nv);
+    if (normals) m.normals.assign(normals, normals + 3ull * nv);
+    if (tangents) {
+        m.tangents.assign(tangents, tangents + 3ull * nv);
+        m.bitangents.resize(3ull * nv, 0.0f);
+        if (normals)
+            for (uint32_t i = 0; i < nv; ++i) {
+                Vec3 b = cross(Vec3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]), Vec3(tangents[3 * i], tangents[3 * i + 1], tangents[3 * i + 2]));
+                m.bitangents[3 * i] = b.x; m.bitangents[3 * i + 1] = b.y; m.bitangents[3 * i + 2] = b.z;
+            }
+    }
+    if (uvs) {
+        m.numUVComponents = 2;
+        m.texCoords.resize(3ull * nv, 0.0f);
+        for (uint32_t i = 0; i < nv; ++i) { m.texCoords[3 * i] = uvs[2 * i]; m.texCoords[3 * i + 1] = uvs[2 * i + 1]; }
+    }
+    m.indices.assign(indices, indices + 3ull * nt);
+    sc.meshes.push_back(m);
+    assbin::Material mat;
+    mat.setString("?mat.name", material_name ? material_name : "material");
+    if (diffuse_rgb) mat.setColor("$clr.diffuse", diffuse_rgb[0], diffuse_rgb[1], diffuse_rgb[2]);
+    sc.materials.push_back(mat);
+    sc.root.name = "root";
+    sc.root.meshes.push_back(0);
+    return assbin::save(path, sc) ? 0 : fail("cannot write %s", path);
+}
+
+SLRGPU_API int slrhost_write_exr(const char* path, uint32_t width, uint32_t height, const float* rgba) {
+    if (!path || !rgba || !width || !height) return fail("slrhost_write_exr: invalid argument");
+    return exr::save(path, width, height, rgba) ? 0 : fail("cannot write %s", path);
 }
 
 SLRGPU_API void slrhost_scene_destroy(SlrHostScene* s) { delete s; }

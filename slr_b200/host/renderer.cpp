@@ -1,0 +1,130 @@
+#include "renderer.h"
+#include "spectrum.h"
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+namespace slr {
+
+void ImageSensor::init(uint32_t width, uint32_t height, uint32_t channels) {
+    m_width = width; m_height = height; m_channels = channels;
+    m_data.assign((size_t)width * height * channels, 0.0f);
+}
+void ImageSensor::clear() { std::fill(m_data.begin(), m_data.end(), 0.0f); }
+
+void ImageSensor::pixelRGB(uint32_t x, uint32_t y, float scale, float rgb[3]) const {
+    const float* p = pixel(x, y);
+    if (m_channels == 3) { for (int i = 0; i < 3; ++i) rgb[i] = p[i] * scale; return; }
+    const SpectralTables& T = SpectralTables::instance();
+    float XYZ[3] = {0, 0, 0};
+    for (int i = 0; i < 16; ++i) {
+        float v = p[i] * scale;
+        XYZ[0] += T.xbar16[i] * v; XYZ[1] += T.ybar16[i] * v; XYZ[2] += T.zbar16[i] * v;
+    }
+    for (int i = 0; i < 3; ++i) XYZ[i] /= T.integralCMF;
+    rgb[0] = (float)(3.2404542 * XYZ[0] - 1.5371385 * XYZ[1] - 0.4985314 * XYZ[2]);
+    rgb[1] = (float)(-0.9692660 * XYZ[0] + 1.8760108 * XYZ[1] + 0.0415560 * XYZ[2]);
+    rgb[2] = (float)(0.0556434 * XYZ[0] - 0.2040259 * XYZ[1] + 1.0572252 * XYZ[2]);
+}
+
+void saveBMP(const std::string& path, const uint8_t* pixels, uint32_t width, uint32_t height) {
+    const uint32_t rowBytes = 3 * width + width % 4;       // the reference's (non-standard) row padding
+    const uint32_t headerSize = 54, dataSize = rowBytes * height, fileSize = dataSize + headerSize;
+    uint8_t h[54];
+    std::memset(h, 0, sizeof(h));
+    h[0] = 'B'; h[1] = 'M';
+    auto put32 = [&h](int at, uint32_t v) { std::memcpy(h + at, &v, 4); };
+    auto put16 = [&h](int at, uint16_t v) { std::memcpy(h + at, &v, 2); };
+    put32(2, fileSize); put32(10, headerSize); put32(14, 40); put32(18, width); put32(22, height);
+    put16(26, 1); put16(28, 24); put32(30, 0); put32(34, dataSize); put32(38, 1); put32(42, 1);
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) return;
+    std::fwrite(h, 1, headerSize, f);
+    std::fwrite(pixels, 1, dataSize, f);
+    std::fclose(f);
+}
+
+void ImageSensor::saveImage(const std::string& path, float scale) const {
+    float sens = std::isinf(m_sensitivity) ? 1.0f : m_sensitivity;
+    scale *= sens;
+    const uint32_t rowBytes = 3 * m_width + m_width % 4;
+    std::vector<uint8_t> bmp((size_t)rowBytes * m_height, 0);
+    for (uint32_t y = 0; y < m_height; ++y) {
+        for (uint32_t x = 0; x < m_width; ++x) {
+            float rgb[3];
+            pixelRGB(x, y, scale, rgb);
+            for (int c = 0; c < 3; ++c) rgb[c] = rgb[c] < 0.0f ? 0.0f : rgb[c];
+            float Y = (float)(0.222485 * rgb[0] + 0.716905 * rgb[1] + 0.060610 * rgb[2]);
+            float sy = Y != 0 ? (1.0f - std::exp(-Y)) / Y : 0.0f;
+            uint8_t* dst = &bmp[(size_t)(m_height - y - 1) * rowBytes + 3 * x];
+            for (int c = 0; c < 3; ++c) {
+                float v = std::min(sy * rgb[c], 1.0f);
+                dst[2 - c] = (uint8_t)(256 * std::min(sRGB_gamma(v), 0.999f));
+            }
+        }
+    }
+    saveBMP(path, bmp.data(), m_width, m_height);
+}
+
+void GPUPathTracingRenderer::render(const RenderScene& scene, const RenderSettings& settings) const {
+    auto wall0 = std::chrono::steady_clock::now();
+    ImageSensor* sensor = scene.getSensor();
+    if (!sensor) throw std::runtime_error("GPUPathTracingRenderer: the scene has no camera/sensor");
+    const uint32_t W = (uint32_t)settings.getInt(RenderSettingItem::ImageWidth);
+    const uint32_t H = (uint32_t)settings.getInt(RenderSettingItem::ImageHeight);
+
+    SlrGpuSceneDesc desc;
+    scene.flat.describe(&desc);
+    SlrGpuScene* gpu = nullptr;
+    auto up0 = std::chrono::steady_clock::now();
+    if (slrgpu_scene_create(&desc, device, &gpu) != SLRGPU_OK)
+        throw std::runtime_error(std::string("slrgpu_scene_create failed: ") + slrgpu_last_error());
+    lastStatistics.uploadSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - up0).count();
+    const uint32_t channels = slrgpu_scene_channels(gpu);
+    sensor->init(W, H, channels);
+
+    SlrGpuRenderParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.struct_size = sizeof(p);
+    p.width = W; p.height = H;
+    p.time_start = settings.getFloat(RenderSettingItem::TimeStart);
+    p.time_end = settings.getFloat(RenderSettingItem::TimeEnd);
+    p.rng_seed = settings.getInt(RenderSettingItem::RNGSeed);
+    const float brightness = settings.getFloat(RenderSettingItem::Brightness);
+
+    lastStatistics = RenderStatistics();
+    std::vector<float> pass((size_t)W * H * channels);
+    // Progressive export cadence of the reference: an image after 1, 2, 4, ... samples (at most 16
+    // images, PathTracingRenderer.cpp:63-65,83-94). Each segment [begin, end) is one GPU render call.
+    uint32_t begin = 0, exportAt = 1, imgIdx = 0;
+    while (begin < m_samplesPerPixel) {
+        uint32_t end = exportProgressiveImages ? std::min(exportAt, m_samplesPerPixel) : m_samplesPerPixel;
+        p.spp_begin = begin; p.spp_end = end;
+        SlrGpuRenderStats st;
+        if (slrgpu_render(gpu, &p, pass.data(), &st) != SLRGPU_OK) {
+            std::string msg = std::string("slrgpu_render failed: ") + slrgpu_last_error();
+            slrgpu_scene_destroy(gpu);
+            throw std::runtime_error(msg);
+        }
+        float* dst = sensor->data();
+        for (size_t i = 0; i < pass.size(); ++i) dst[i] += pass[i];
+        lastStatistics.paths += st.paths; lastStatistics.rays += st.rays;
+        lastStatistics.deviceSeconds += st.device_ms * 1e-3;
+        if (exportProgressiveImages && end == exportAt) {
+            char name[64];
+            std::snprintf(name, sizeof(name), "%03u.bmp", imgIdx);
+            sensor->saveImage(outputDirectory + "/" + name, brightness / end);
+            double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+            std::printf("%u samples: %s, %g[s]\n", end, name, el);
+            if (++imgIdx == 16) { begin = end; break; }
+            exportAt += exportAt;
+        }
+        begin = end;
+    }
+    slrgpu_scene_destroy(gpu);
+    lastStatistics.wallSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+}
+
+}  // namespace slr

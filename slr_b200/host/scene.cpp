@@ -1,4 +1,5 @@
 #include "scene.h"
+#include "spectrum.h"
 #include <algorithm>
 #include <chrono>
 #include <cstring>
@@ -140,20 +141,39 @@ uint32_t GpuSceneBuilder::createAggregate(std::vector<ObjectRef>&& objects) {
 
     // light list: emitting objects in object order (SurfaceObject.cpp:232-252)
     for (const ObjectRef& o : ag.objects) {
+        SlrGpuLight l;
+        std::memset(&l, 0, sizeof(l));
         if (!o.isInstance) {
-            if (triangleEmits[o.id]) {
-                flat.triangles[o.id].light_index = (uint32_t)ag.lights.size();
-                ag.lights.push_back(SlrGpuLight{o.id, 1.0f});
-            }
+            if (!triangleEmits[o.id]) continue;
+            flat.triangles[o.id].light_index = (uint32_t)ag.lights.size();
+            l.object = o.id; l.importance = 1.0f;                       // SingleSurfaceObject::importance
         } else {
             const Aggregate& nested = aggregates[instanceAggregate[o.id]];
-            if (!nested.lights.empty()) {
-                // importance of an aggregate = integral of its light distribution (compensated sum of importances)
-                float sum = 0.0f, comp = 0.0f;
-                for (const SlrGpuLight& l : nested.lights) { float y = l.importance - comp; float t = sum + y; comp = (t - sum) - y; sum = t; }
-                ag.lights.push_back(SlrGpuLight{0x80000000u | o.id, sum});
-            }
+            if (nested.lights.empty()) continue;
+            flat.instances[o.id].light_index = (uint32_t)ag.lights.size();
+            flat.instances[o.id].light_importance = nested.lightImportance;
+            l.object = 0x80000000u | o.id; l.importance = nested.lightImportance;
         }
+        ag.lights.push_back(l);
+    }
+    // RegularConstantDiscrete1D over the importances: compensated running sum, then normalise
+    if (!ag.lights.empty()) {
+        const size_t n = ag.lights.size();
+        std::vector<float> cdf(n + 1, 0.0f);
+        float sum = 0.0f, comp = 0.0f;
+        for (size_t i = 0; i < n; ++i) {
+            float y = ag.lights[i].importance - comp;
+            float t = sum + y;
+            comp = (t - sum) - y;
+            sum = t;
+            cdf[i + 1] = sum;
+        }
+        ag.lightImportance = sum;
+        for (size_t i = 0; i < n; ++i) {
+            ag.lights[i].pmf = ag.lights[i].importance / sum;
+            cdf[i + 1] /= sum;
+        }
+        for (size_t i = 0; i < n; ++i) { ag.lights[i].cdf_lo = cdf[i]; ag.lights[i].cdf_hi = cdf[i + 1]; }
     }
     return id;
 }
@@ -166,6 +186,7 @@ uint32_t GpuSceneBuilder::addInstance(uint32_t aggregate, const StaticTransform&
     inst.root_node = 0;           // patched in finalize()
     inst.light_base = SLRGPU_INVALID_ID;
     inst.num_lights = 0;
+    inst.light_index = SLRGPU_INVALID_ID;
     flat.instances.push_back(inst);
     instanceAggregate.push_back(aggregate);
     return (uint32_t)flat.instances.size() - 1;
@@ -190,6 +211,7 @@ void GpuSceneBuilder::finalize(uint32_t top) {
     flat.leaves.resize(nLeaves);
     flat.lights.resize(nLights);
     flat.numTopLights = (uint32_t)aggregates[top].lights.size();
+    flat.topLightImportance = aggregates[top].lightImportance;
     flat.stats.clear();
 
     for (uint32_t a : order) {
@@ -270,6 +292,7 @@ void FlatScene::describe(SlrGpuSceneDesc* d) const {
     d->image_data = imageData.data();  d->image_data_bytes = imageData.size();
     d->lights = lights.data();         d->num_lights = (uint32_t)lights.size();
     d->num_top_lights = numTopLights;
+    d->top_light_importance = topLightImportance;
     for (int i = 0; i < 3; ++i) d->world_center[i] = worldCenter[i];
     d->world_radius = worldRadius;
     d->camera = camera;
@@ -280,6 +303,17 @@ void FlatScene::describe(SlrGpuSceneDesc* d) const {
     d->environment.row_integral = envRowIntegral.data();
     d->environment.marginal_pdf = envMarginalPdf.data(); d->environment.marginal_cdf = envMarginalCdf.data();
     d->environment.marginal_integral = envMarginalIntegral;
+    if (!materials.empty()) {
+        // shading needs the spectral constant tables (loaded once per process)
+        const SpectralTables& T = SpectralTables::instance();
+        const std::vector<float>& pts = T.floats("upsampling/points");
+        d->spectral.upsample_grid = T.upsampleGridWords.data();
+        d->spectral.upsample_grid_floats = (uint32_t)T.upsampleGridWords.size();
+        d->spectral.upsample_points = pts.data();
+        d->spectral.upsample_points_floats = (uint32_t)pts.size();
+        d->spectral.xbar_16 = T.xbar16; d->spectral.ybar_16 = T.ybar16; d->spectral.zbar_16 = T.zbar16;
+        d->spectral.integral_cmf = T.integralCMF;
+    }
 }
 
 }  // namespace slr

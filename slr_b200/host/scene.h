@@ -135,6 +135,7 @@ struct FlatScene {
     std::vector<uint8_t> imageData;
     std::vector<SlrGpuLight> lights;
     uint32_t numTopLights = 0;
+    float topLightImportance = 0.0f;
     // environment
     bool envPresent = false;
     uint32_t envMaterial = SLRGPU_INVALID_ID, envMapWidth = 0, envMapHeight = 0;
@@ -176,6 +177,7 @@ public:
         QBVH qbvh;
         std::vector<SlrGpuLight> lights;     // emitting objects in object order
         bool containsInstances = false;
+        float lightImportance = 0.0f;        // integral of the light distribution
     };
     FlatScene& flat;
     std::vector<Aggregate> aggregates;       // nested ones first as they are discovered; index = aggregate id

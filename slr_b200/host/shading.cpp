@@ -1,14 +1,239 @@
 #include "shading.h"
+#include <cstring>
+#include <map>
 #include <stdexcept>
 
 namespace slr {
 
-// Phase-1 placeholders: geometry-only scenes carry no materials yet.
-uint32_t GpuSceneBuilder::exportMaterial(const SurfaceMaterial*) { throw std::runtime_error("materials not implemented yet"); }
-uint32_t GpuSceneBuilder::exportNormalTexture(const Normal3DTexture*) { throw std::runtime_error("textures not implemented yet"); }
-uint32_t GpuSceneBuilder::exportFloatTexture(const FloatTexture*) { throw std::runtime_error("textures not implemented yet"); }
-bool GpuSceneBuilder::materialEmits(const SurfaceMaterial*) const { return false; }
-void exportEnvironment(GpuSceneBuilder&, const InfiniteSphereNode&) { throw std::runtime_error("environment not implemented yet"); }
-void finishShadingTables(GpuSceneBuilder&) {}
+size_t Image2D::texelSize(SlrGpuImageFormat f) {
+    switch (f) {
+        case SLRGPU_IMG_RGB8x3: return 3;
+        case SLRGPU_IMG_RGB_8x4: case SLRGPU_IMG_RGBA8x4: return 4;
+        case SLRGPU_IMG_RGBA16Fx4: case SLRGPU_IMG_UVSA16Fx4: return 8;
+        case SLRGPU_IMG_GRAY8: return 1;
+        case SLRGPU_IMG_UVS16Fx3: return 6;
+        case SLRGPU_IMG_FLOAT32: return 4;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// factories
+// ---------------------------------------------------------------------------------------------
+
+static TextureMappingRef orDefault(const TextureMappingRef& m) { return m ? m : std::make_shared<TextureMapping>(); }
+
+SpectrumTextureRef SpectrumTexture::constant(const InputSpectrumRef& s) {
+    auto t = std::make_shared<SpectrumTexture>(); t->kind = SLRGPU_TEX_CONSTANT_SPECTRUM; t->spectrum[0] = s; return t;
+}
+SpectrumTextureRef SpectrumTexture::checkerBoard(const TextureMappingRef& m, const InputSpectrumRef& v0, const InputSpectrumRef& v1) {
+    auto t = std::make_shared<SpectrumTexture>(); t->kind = SLRGPU_TEX_CHECKER_SPECTRUM; t->mapping = orDefault(m);
+    t->spectrum[0] = v0; t->spectrum[1] = v1; return t;
+}
+SpectrumTextureRef SpectrumTexture::voronoi(const TextureMappingRef& m, float scale, float brightness) {
+    auto t = std::make_shared<SpectrumTexture>(); t->kind = SLRGPU_TEX_VORONOI_SPECTRUM; t->mapping = orDefault(m);
+    t->f0 = scale; t->f1 = brightness; return t;
+}
+SpectrumTextureRef SpectrumTexture::imageTexture(const TextureMappingRef& m, const Image2DRef& img) {
+    auto t = std::make_shared<SpectrumTexture>(); t->kind = SLRGPU_TEX_IMAGE_SPECTRUM; t->mapping = orDefault(m); t->image = img; return t;
+}
+Normal3DTextureRef Normal3DTexture::checkerBoard(const TextureMappingRef& m, float stepWidth, bool reverse) {
+    auto t = std::make_shared<Normal3DTexture>(); t->kind = SLRGPU_TEX_CHECKER_NORMAL; t->mapping = orDefault(m);
+    t->f0 = stepWidth; t->i0 = reverse ? 1 : 0; return t;
+}
+Normal3DTextureRef Normal3DTexture::voronoi(const TextureMappingRef& m, float scale, float thetaMax) {
+    auto t = std::make_shared<Normal3DTexture>(); t->kind = SLRGPU_TEX_VORONOI_NORMAL; t->mapping = orDefault(m);
+    t->f0 = scale; t->f1 = std::cos(thetaMax); return t;     // stores cos(thetaMax), voronoi_textures.h:37
+}
+Normal3DTextureRef Normal3DTexture::imageTexture(const TextureMappingRef& m, const Image2DRef& img) {
+    auto t = std::make_shared<Normal3DTexture>(); t->kind = SLRGPU_TEX_IMAGE_NORMAL; t->mapping = orDefault(m); t->image = img; return t;
+}
+FloatTextureRef FloatTexture::constant(float v) {
+    auto t = std::make_shared<FloatTexture>(); t->kind = SLRGPU_TEX_CONSTANT_FLOAT; t->f0 = v; return t;
+}
+FloatTextureRef FloatTexture::checkerBoard(const TextureMappingRef& m, float v0, float v1) {
+    auto t = std::make_shared<FloatTexture>(); t->kind = SLRGPU_TEX_CHECKER_FLOAT; t->mapping = orDefault(m); t->f0 = v0; t->f1 = v1; return t;
+}
+FloatTextureRef FloatTexture::voronoi(const TextureMappingRef& m, float scale, float valueScale, bool flat) {
+    auto t = std::make_shared<FloatTexture>(); t->kind = SLRGPU_TEX_VORONOI_FLOAT; t->mapping = orDefault(m);
+    t->f0 = scale; t->f1 = valueScale; t->i0 = flat ? 1 : 0; return t;
+}
+FloatTextureRef FloatTexture::imageTexture(const TextureMappingRef& m, const Image2DRef& img) {
+    auto t = std::make_shared<FloatTexture>(); t->kind = SLRGPU_TEX_IMAGE_FLOAT; t->mapping = orDefault(m); t->image = img; return t;
+}
+
+static SurfaceMaterialRef mk(SlrGpuMaterialKind k) { auto m = std::make_shared<SurfaceMaterial>(); m->kind = k; return m; }
+
+SurfaceMaterialRef SurfaceMaterial::createMatte(const SpectrumTextureRef& R, const FloatTextureRef& sigma) {
+    auto m = mk(SLRGPU_MAT_DIFFUSE); m->stex[0] = R; m->ftex[1] = sigma; return m;
+}
+SurfaceMaterialRef SurfaceMaterial::createMetal(const SpectrumTextureRef& c, const SpectrumTextureRef& eta, const SpectrumTextureRef& k) {
+    auto m = mk(SLRGPU_MAT_SPECULAR_REFLECTION); m->stex[0] = c; m->stex[1] = eta; m->stex[2] = k; return m;
+}
+SurfaceMaterialRef SurfaceMaterial::createGlass(const SpectrumTextureRef& c, const SpectrumTextureRef& e, const SpectrumTextureRef& i) {
+    auto m = mk(SLRGPU_MAT_SPECULAR_SCATTERING); m->stex[0] = c; m->stex[1] = e; m->stex[2] = i; return m;
+}
+SurfaceMaterialRef SurfaceMaterial::createModifiedWardDur(const SpectrumTextureRef& R, const FloatTextureRef& ax, const FloatTextureRef& ay) {
+    auto m = mk(SLRGPU_MAT_WARD_DUR); m->stex[0] = R; m->ftex[1] = ax; m->ftex[2] = ay; return m;
+}
+SurfaceMaterialRef SurfaceMaterial::createAshikhminShirley(const SpectrumTextureRef& Rd, const SpectrumTextureRef& Rs,
+                                                           const FloatTextureRef& nu, const FloatTextureRef& nv) {
+    auto m = mk(SLRGPU_MAT_ASHIKHMIN_SHIRLEY); m->stex[0] = Rs; m->stex[1] = Rd; m->ftex[2] = nu; m->ftex[3] = nv; return m;
+}
+SurfaceMaterialRef SurfaceMaterial::createMicrofacetMetal(const SpectrumTextureRef& eta, const SpectrumTextureRef& k, const FloatTextureRef& a) {
+    auto m = mk(SLRGPU_MAT_MICROFACET_REFLECTION); m->stex[0] = eta; m->stex[1] = k; m->ftex[2] = a; return m;
+}
+SurfaceMaterialRef SurfaceMaterial::createMicrofacetGlass(const SpectrumTextureRef& e, const SpectrumTextureRef& i, const FloatTextureRef& a) {
+    auto m = mk(SLRGPU_MAT_MICROFACET_SCATTERING); m->stex[0] = e; m->stex[1] = i; m->ftex[2] = a; return m;
+}
+SurfaceMaterialRef SurfaceMaterial::createInverseMaterial(const SurfaceMaterialRef& base) {
+    auto m = mk(SLRGPU_MAT_INVERSE); m->sub[0] = base; return m;
+}
+SurfaceMaterialRef SurfaceMaterial::createSummedMaterial(const SurfaceMaterialRef& m0, const SurfaceMaterialRef& m1) {
+    auto m = mk(SLRGPU_MAT_SUMMED); m->sub[0] = m0; m->sub[1] = m1; return m;
+}
+SurfaceMaterialRef SurfaceMaterial::createMixedMaterial(const SurfaceMaterialRef& m0, const SurfaceMaterialRef& m1, const FloatTextureRef& f) {
+    auto m = mk(SLRGPU_MAT_MIXED); m->sub[0] = m0; m->sub[1] = m1; m->ftex[0] = f; return m;
+}
+EmitterSurfacePropertyRef SurfaceMaterial::createDiffuseEmitter(const SpectrumTextureRef& emittance) {
+    auto e = std::make_shared<EmitterSurfaceProperty>(); e->kind = SLRGPU_MAT_DIFFUSE_EMISSION; e->emittance = emittance; return e;
+}
+SurfaceMaterialRef SurfaceMaterial::createEmitterSurfaceMaterial(const SurfaceMaterialRef& mat, const EmitterSurfacePropertyRef& emit) {
+    if (mat && mat->isEmitting()) throw std::runtime_error("EmitterSurfaceMaterial cannot wrap an emitting material");
+    auto m = mk(SLRGPU_MAT_EMITTER); m->sub[0] = mat; m->emitter = emit; return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// export (deduplicated by object identity)
+// ---------------------------------------------------------------------------------------------
+
+namespace {
+struct ExportCache {
+    std::map<const void*, uint32_t> spectra, textures, materials, images, emitters;
+};
+std::map<const GpuSceneBuilder*, ExportCache>& caches() { static std::map<const GpuSceneBuilder*, ExportCache> c; return c; }
+
+uint32_t exportSpectrum(GpuSceneBuilder& b, const InputSpectrum* s) {
+    if (!s) throw std::runtime_error("texture refers to a null spectrum");
+    ExportCache& c = caches()[&b];
+    auto it = c.spectra.find(s);
+    if (it != c.spectra.end()) return it->second;
+    uint32_t id = s->exportTo(b.flat.spectra, b.flat.spectrumData);
+    c.spectra[s] = id;
+    return id;
+}
+
+uint32_t exportImage(GpuSceneBuilder& b, const Image2D* img) {
+    if (!img) throw std::runtime_error("image texture without an image");
+    ExportCache& c = caches()[&b];
+    auto it = c.images.find(img);
+    if (it != c.images.end()) return it->second;
+    SlrGpuImage g = {};
+    g.format = img->format; g.width = img->width; g.height = img->height;
+    while (b.flat.imageData.size() % 16) b.flat.imageData.push_back(0);
+    g.data_offset = b.flat.imageData.size();
+    g.spectrum_type = (uint32_t)img->spectrumType;
+    b.flat.imageData.insert(b.flat.imageData.end(), img->data.begin(), img->data.end());
+    b.flat.images.push_back(g);
+    return c.images[img] = (uint32_t)b.flat.images.size() - 1;
+}
+
+void fillMapping(SlrGpuTexture& t, const TextureMappingRef& m) {
+    t.mapping = m ? m->kind : SLRGPU_MAP_TEXCOORD;
+    t.map_offset[0] = m ? m->offset[0] : 0; t.map_offset[1] = m ? m->offset[1] : 0;
+    t.map_scale[0] = m ? m->scale[0] : 1;   t.map_scale[1] = m ? m->scale[1] : 1;
+}
+
+uint32_t exportSpectrumTexture(GpuSceneBuilder& b, const SpectrumTexture* t) {
+    ExportCache& c = caches()[&b];
+    auto it = c.textures.find(t);
+    if (it != c.textures.end()) return it->second;
+    SlrGpuTexture g = {};
+    g.kind = t->kind;
+    fillMapping(g, t->mapping);
+    g.i0 = g.i1 = SLRGPU_INVALID_ID;
+    g.f0 = t->f0; g.f1 = t->f1;
+    switch (t->kind) {
+        case SLRGPU_TEX_CONSTANT_SPECTRUM: g.i0 = exportSpectrum(b, t->spectrum[0].get()); break;
+        case SLRGPU_TEX_CHECKER_SPECTRUM:
+            g.i0 = exportSpectrum(b, t->spectrum[0].get()); g.i1 = exportSpectrum(b, t->spectrum[1].get()); break;
+        case SLRGPU_TEX_VORONOI_SPECTRUM: break;
+        case SLRGPU_TEX_IMAGE_SPECTRUM: g.i0 = exportImage(b, t->image.get()); break;
+        default: throw std::runtime_error("not a spectrum texture kind");
+    }
+    b.flat.textures.push_back(g);
+    return c.textures[t] = (uint32_t)b.flat.textures.size() - 1;
+}
+
+uint32_t exportEmitter(GpuSceneBuilder& b, const EmitterSurfaceProperty* e) {
+    ExportCache& c = caches()[&b];
+    auto it = c.emitters.find(e);
+    if (it != c.emitters.end()) return it->second;
+    SlrGpuMaterial g = {};
+    g.kind = e->kind;
+    for (int i = 0; i < 4; ++i) g.tex[i] = SLRGPU_INVALID_ID;
+    g.sub[0] = g.sub[1] = SLRGPU_INVALID_ID;
+    g.tex[0] = exportSpectrumTexture(b, e->emittance.get());
+    g.f0 = e->scale;
+    b.flat.materials.push_back(g);
+    return c.emitters[e] = (uint32_t)b.flat.materials.size() - 1;
+}
+}  // namespace
+
+uint32_t GpuSceneBuilder::exportFloatTexture(const FloatTexture* t) {
+    ExportCache& c = caches()[this];
+    auto it = c.textures.find(t);
+    if (it != c.textures.end()) return it->second;
+    SlrGpuTexture g = {};
+    g.kind = t->kind;
+    fillMapping(g, t->mapping);
+    g.i0 = t->i0; g.i1 = SLRGPU_INVALID_ID;
+    g.f0 = t->f0; g.f1 = t->f1;
+    if (t->kind == SLRGPU_TEX_IMAGE_FLOAT) g.i0 = exportImage(*this, t->image.get());
+    flat.textures.push_back(g);
+    return c.textures[t] = (uint32_t)flat.textures.size() - 1;
+}
+
+uint32_t GpuSceneBuilder::exportNormalTexture(const Normal3DTexture* t) {
+    ExportCache& c = caches()[this];
+    auto it = c.textures.find(t);
+    if (it != c.textures.end()) return it->second;
+    SlrGpuTexture g = {};
+    g.kind = t->kind;
+    fillMapping(g, t->mapping);
+    g.i0 = t->i0; g.i1 = SLRGPU_INVALID_ID;
+    g.f0 = t->f0; g.f1 = t->f1;
+    if (t->kind == SLRGPU_TEX_IMAGE_NORMAL) g.i0 = exportImage(*this, t->image.get());
+    flat.textures.push_back(g);
+    return c.textures[t] = (uint32_t)flat.textures.size() - 1;
+}
+
+uint32_t GpuSceneBuilder::exportMaterial(const SurfaceMaterial* m) {
+    ExportCache& c = caches()[this];
+    auto it = c.materials.find(m);
+    if (it != c.materials.end()) return it->second;
+    SlrGpuMaterial g = {};
+    g.kind = m->kind;
+    for (int i = 0; i < 4; ++i) {
+        g.tex[i] = SLRGPU_INVALID_ID;
+        if (m->stex[i]) g.tex[i] = exportSpectrumTexture(*this, m->stex[i].get());
+        else if (m->ftex[i]) g.tex[i] = exportFloatTexture(m->ftex[i].get());
+    }
+    for (int i = 0; i < 2; ++i) g.sub[i] = m->sub[i] ? exportMaterial(m->sub[i].get()) : SLRGPU_INVALID_ID;
+    if (m->kind == SLRGPU_MAT_EMITTER) {
+        if (!m->emitter) throw std::runtime_error("emitter material without an emitter property");
+        g.sub[1] = exportEmitter(*this, m->emitter.get());
+    }
+    flat.materials.push_back(g);
+    return c.materials[m] = (uint32_t)flat.materials.size() - 1;
+}
+
+bool GpuSceneBuilder::materialEmits(const SurfaceMaterial* m) const { return m && m->isEmitting(); }
+
+void exportEnvironment(GpuSceneBuilder&, const InfiniteSphereNode&) {
+    throw std::runtime_error("environment lights are not implemented yet");
+}
+
+void finishShadingTables(GpuSceneBuilder& b) { caches().erase(&b); }
 
 }  // namespace slr

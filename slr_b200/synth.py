@@ -85,9 +85,9 @@ def uv_sphere(segments_u=64, segments_v=32, radius=1.0):
         for i in range(segments_u):
             a, b, c, d = j * w + i, j * w + i + 1, (j + 1) * w + i, (j + 1) * w + i + 1
             if j != 0:
-                idx.append([a, c, b])
+                idx.append([a, b, c])
             if j != segments_v - 1:
-                idx.append([b, c, d])
+                idx.append([b, d, c])
     return (np.asarray(pos, np.float32), np.asarray(idx, np.uint32), np.asarray(nrm, np.float32),
             np.asarray(tng, np.float32), np.asarray(uv, np.float32))
 
