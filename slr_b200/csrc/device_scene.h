@@ -36,6 +36,7 @@ struct DeviceScene {
     uint32_t numMaterials, numTextures, numSpectra, numImages, numLights, numTopLights;
     uint32_t envPresent, envMaterial, envMapWidth, envMapHeight;
     float envMarginalIntegral;
+    float topLightImportance;     // SurfaceObjectAggregate::importance() of the top-level aggregate
     uint32_t rgbMode;
     float worldCenter[3];
     float worldRadius;
@@ -55,6 +56,7 @@ struct SlrGpuScene {
     bool hasInstances = false;
     bool hasShading = false;
     uint32_t channels = 16;
+    uint32_t maxLobes = 1;            // 1 unless a material is a sum / mix (MultiBSDF): picks the shade kernel variant
 };
 
 namespace slrgpu {

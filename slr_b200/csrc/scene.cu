@@ -126,6 +126,7 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
     v.numLights = d->num_lights; v.numTopLights = d->num_top_lights;
     v.envPresent = e.present; v.envMaterial = e.material; v.envMapWidth = e.map_width; v.envMapHeight = e.map_height;
     v.envMarginalIntegral = e.marginal_integral;
+    v.topLightImportance = d->top_light_importance;
     v.rgbMode = d->rgb_mode;
     for (int i = 0; i < 3; ++i) v.worldCenter[i] = d->world_center[i];
     v.worldRadius = d->world_radius;
@@ -137,6 +138,9 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
     sc->hasInstances = d->num_instances > 0;
     sc->hasShading = d->num_materials > 0 && d->num_triangles > 0;
     sc->channels = d->rgb_mode ? 3 : 16;
+    sc->maxLobes = 1;
+    for (uint32_t i = 0; i < d->num_materials; ++i)
+        if (d->materials[i].kind == SLRGPU_MAT_SUMMED || d->materials[i].kind == SLRGPU_MAT_MIXED) sc->maxLobes = 4;
     *out = sc;
     return SLRGPU_OK;
 }

@@ -37,9 +37,9 @@ template <int NC> __device__ __forceinline__ float specLuminance(const Spec<NC>&
     for (int i = 0; i < NC; ++i) sum += s.v[i];
     return sum / NC;                                                                       // SpectrumTypes.h:504-509
 }
-// importance(): 0.9 on the selected (hero) wavelength, the rest spread uniformly; RGB: plain weights
+// importance(): 0.9 on the selected (hero) component, the rest spread uniformly
+// (SpectrumTypes.h:512-526, RGBTypes.h:103-108)
 template <int NC> __device__ __forceinline__ float specImportance(const Spec<NC>& s, uint32_t hero) {
-    if (NC == 3) return 0.222485f * s.v[0] + 0.716905f * s.v[1] + 0.060610f * s.v[2];
     float sum = 0, sel = 0;
 #pragma unroll
     for (int i = 0; i < NC; ++i) { sum += s.v[i]; sel = (i == (int)hero) ? s.v[i] : sel; }
@@ -47,6 +47,31 @@ template <int NC> __device__ __forceinline__ float specImportance(const Spec<NC>
     const float marginal = (1 - primary) / (NC - 1);
     return sum * marginal + sel * (primary - marginal);
 }
+template <int NC> __device__ __forceinline__ float specAt(const Spec<NC>& s, uint32_t idx) {
+    float sel = 0;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) sel = (i == (int)idx) ? s.v[i] : sel;
+    return sel;
+}
+template <int NC> __device__ __forceinline__ Spec<NC> operator*(const Spec<NC>& a, const Spec<NC>& b) {
+    Spec<NC> r;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) r.v[i] = a.v[i] * b.v[i];
+    return r;
+}
+template <int NC> __device__ __forceinline__ Spec<NC> operator+(const Spec<NC>& a, const Spec<NC>& b) {
+    Spec<NC> r;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) r.v[i] = a.v[i] + b.v[i];
+    return r;
+}
+template <int NC> __device__ __forceinline__ Spec<NC> operator*(const Spec<NC>& a, float s) {
+    Spec<NC> r;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) r.v[i] = a.v[i] * s;
+    return r;
+}
+template <int NC> __device__ __forceinline__ Spec<NC> operator*(float s, const Spec<NC>& a) { return a * s; }
 
 // wavelength i of a path with stratification offset `off`
 __device__ __forceinline__ float wavelengthOf(int i, float off) { return kWlLow + (kWlHigh - kWlLow) * (i + off) / 16; }
@@ -87,7 +112,7 @@ struct UpsampleWeights {
 
 constexpr int kUpGridW = 12, kUpGridH = 14, kUpNumWl = 95, kUpPointStride = 99;   // xystar[2] uv[2] spectrum[95]
 
-__device__ inline UpsampleWeights upsampleWeights(const DeviceScene& s, float u, float v) {
+__device__ __noinline__ UpsampleWeights upsampleWeights(const DeviceScene& s, float u, float v) {
     UpsampleWeights r;
     r.n = 0;
     if (u < 0.0f || u >= kUpGridW || v < 0.0f || v >= kUpGridH) return r;
@@ -145,7 +170,7 @@ __device__ __forceinline__ float evalUpsampled(const DeviceScene& s, const Upsam
 
 // Evaluates input spectrum `id` at the path's wavelengths (or returns the RGB triple in RGB mode).
 template <int NC>
-__device__ inline Spec<NC> evalInputSpectrum(const DeviceScene& s, uint32_t id, float wlOffset) {
+__device__ __noinline__ Spec<NC> evalInputSpectrum(const DeviceScene& s, uint32_t id, float wlOffset) {
     const SlrGpuSpectrum sp = s.spectra[id];
     Spec<NC> out;
     if (NC == 3) {
@@ -172,7 +197,7 @@ __device__ inline Spec<NC> evalInputSpectrum(const DeviceScene& s, uint32_t id, 
 
 // UpsampledContinuousSpectrum built per texel / per Voronoi cell from (u, v, scale)
 template <int NC>
-__device__ inline Spec<NC> evalUVS(const DeviceScene& s, float u, float v, float scale, float wlOffset) {
+__device__ __noinline__ Spec<NC> evalUVS(const DeviceScene& s, float u, float v, float scale, float wlOffset) {
     Spec<NC> out;
     const UpsampleWeights w = upsampleWeights(s, u, v);
 #pragma unroll

@@ -1,0 +1,89 @@
+// Wavefront ray stages: `extend` (closest hit for every path in the queue) and `shadow` (occlusion
+// of the next-event-estimation rays, splatting the unoccluded contributions to the sensor).
+//   Scene::intersect        libSLR/Core/SurfaceObject.cpp:408-416  -> QBVH traversal of traverse.cuh
+//   Scene::testVisibility   libSLR/Core/SurfaceObject.cpp:418-430  (the reference runs a full closest-hit
+//                           query and keeps only the boolean; any-hit with early exit gives the same boolean)
+// MUST be compiled with -fmad=false like intersect.cu: the renderer's rays use the bit-exact traversal.
+#include "traverse.cuh"
+#include "wavefront.cuh"
+
+namespace slrgpu {
+
+constexpr int kTraceBlock = 128;
+
+template <bool INSTANCES>
+__global__ void __launch_bounds__(kTraceBlock)
+extendKernel(const DeviceScene s, PathQueue q, uint32_t n, HitBuffer hits, WavefrontCounters* counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 o = q.org[i], d = q.dir[i];
+    Ray r;
+    r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = o.w;
+    r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = INFINITY;
+    Hit h;
+    h.prim = SLRGPU_INVALID_ID; h.inst = SLRGPU_INVALID_ID; h.t = INFINITY; h.u = 0.0f; h.v = 0.0f;
+    uint32_t stack[kStackSize];
+    TraversalCounters cnt = {0, 0};
+    bool overflow = false;
+    traverse<INSTANCES ? 0 : 1, false, false>(s, 0, r, h, stack, 0, cnt, overflow);
+    hits.id[i] = make_uint2(h.prim, h.inst);
+    hits.tuv[i] = make_float4(h.t, h.u, h.v, 0.0f);
+    if (overflow) atomicExch(&counters->stackOverflow, 1u);
+}
+
+template <bool INSTANCES, int NC>
+__global__ void __launch_bounds__(kTraceBlock)
+shadowKernel(const DeviceScene s, ShadowQueue q, uint32_t n, float* __restrict__ accum, WavefrontCounters* counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 o = q.org[i], d = q.dir[i];
+    Ray r;
+    r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = o.w;
+    r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = d.w;
+    Hit h;
+    h.prim = SLRGPU_INVALID_ID; h.inst = SLRGPU_INVALID_ID; h.t = INFINITY; h.u = h.v = 0.0f;
+    uint32_t stack[kStackSize];
+    TraversalCounters cnt = {0, 0};
+    bool overflow = false;
+    const bool occluded = traverse<INSTANCES ? 0 : 1, true, false>(s, 0, r, h, stack, 0, cnt, overflow);
+    if (overflow) atomicExch(&counters->stackOverflow, 1u);
+    if (occluded) return;
+    const uint2 pw = q.pixelWl[i];
+    float v[NC == 3 ? 4 : NC];
+    constexpr int Q = (NC + 3) / 4;
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+        const float4 c = q.contrib[(size_t)k * q.capacity + i];
+        v[4 * k] = c.x;
+        if (4 * k + 1 < (NC == 3 ? 4 : NC)) v[4 * k + 1] = c.y;
+        if (4 * k + 2 < (NC == 3 ? 4 : NC)) v[4 * k + 2] = c.z;
+        if (4 * k + 3 < (NC == 3 ? 4 : NC)) v[4 * k + 3] = c.w;
+    }
+    splat<NC>(accum, pw.x & 0x7FFFFFFFu, __uint_as_float(pw.y), (pw.x >> 31) != 0, v);
+}
+
+int launchExtend(const SlrGpuScene* sc, const PathQueue& q, uint32_t n, const HitBuffer& hits, WavefrontCounters* counters, cudaStream_t stream) {
+    if (n == 0) return SLRGPU_OK;
+    const dim3 grid((n + kTraceBlock - 1) / kTraceBlock), block(kTraceBlock);
+    if (sc->hasInstances) extendKernel<true><<<grid, block, 0, stream>>>(sc->dev, q, n, hits, counters);
+    else extendKernel<false><<<grid, block, 0, stream>>>(sc->dev, q, n, hits, counters);
+    SLRGPU_CUDA_TRY(cudaGetLastError());
+    return SLRGPU_OK;
+}
+
+int launchShadow(const SlrGpuScene* sc, const ShadowQueue& q, uint32_t n, float* accum, WavefrontCounters* counters, cudaStream_t stream) {
+    if (n == 0) return SLRGPU_OK;
+    const dim3 grid((n + kTraceBlock - 1) / kTraceBlock), block(kTraceBlock);
+    const bool rgb = sc->channels == 3;
+    if (sc->hasInstances) {
+        if (rgb) shadowKernel<true, 3><<<grid, block, 0, stream>>>(sc->dev, q, n, accum, counters);
+        else shadowKernel<true, 16><<<grid, block, 0, stream>>>(sc->dev, q, n, accum, counters);
+    } else {
+        if (rgb) shadowKernel<false, 3><<<grid, block, 0, stream>>>(sc->dev, q, n, accum, counters);
+        else shadowKernel<false, 16><<<grid, block, 0, stream>>>(sc->dev, q, n, accum, counters);
+    }
+    SLRGPU_CUDA_TRY(cudaGetLastError());
+    return SLRGPU_OK;
+}
+
+}  // namespace slrgpu

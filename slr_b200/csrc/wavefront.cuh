@@ -1,0 +1,107 @@
+// Wavefront path-tracing state: the buffers that link the ray-generation, extend, shade and shadow
+// kernels. Every stage reads a compacted queue front to back (fully coalesced) and appends its
+// survivors to the next queue with one warp-aggregated atomic per warp, so the path state itself is
+// what moves through the queues (no slot indirection).
+//
+// HBM layout, all SoA over the queue position i (capacity P):
+//   PathQueue   org[i]   = (ray origin xyz, distMin)                         16 B
+//               dir[i]   = (ray direction xyz, pdf the direction was sampled with)   16 B
+//               meta[i]  = (pixel, global sample index, hero | flags<<8 | pathLength<<16, bits(wavelength offset))  16 B
+//               weight[i]= camera-sample weight (Job::kernel, PathTracingRenderer.cpp:126)  4 B
+//               alpha[q*P + i], q < NC/4 = path throughput, four components per 16 B load   64 B (16 B in RGB mode)
+//   HitBuffer   id[i] = (prim, inst), tuv[i] = (t, b0, b1, -)                 24 B
+//   ShadowQueue org/dir (distMin / distMax in .w), pixel+wavelength offset, contribution[q*P + i]   108 B
+// S_state = 116 B per path per stage transition in spectral mode.
+#pragma once
+#include "device_scene.h"
+
+namespace slrgpu {
+
+constexpr uint32_t kFlagLambdaSelected = 1u, kFlagPrevDelta = 2u, kFlagCameraRay = 4u, kFlagStrataInPlace = 8u;
+
+struct PathQueue {
+    float4* org;
+    float4* dir;
+    uint4* meta;
+    float* weight;
+    float4* alpha;
+    uint32_t capacity;     // stride of the alpha quarters
+};
+
+struct HitBuffer {
+    uint2* id;
+    float4* tuv;
+};
+
+struct ShadowQueue {
+    float4* org;
+    float4* dir;
+    uint2* pixelWl;        // pixel | strataInPlace << 31, bits(wavelength offset)
+    float4* contrib;
+    uint32_t capacity;     // stride of the contribution quarters
+};
+
+struct WavefrontCounters {
+    uint32_t numNext;          // entries appended to the next path queue
+    uint32_t numShadow;        // entries appended to the shadow queue
+    uint32_t stackOverflow;
+    uint32_t pad;
+    unsigned long long extendRays, shadowRays, pathsStarted, pathsFinished;
+};
+
+struct RenderConstants {
+    uint32_t width, height, numPixels;
+    uint32_t sppBegin;
+    uint32_t capacity;          // P
+    uint32_t maxPathLength;     // 100 (PathTracingRenderer.cpp:162)
+    uint32_t seed;
+    float timeStart, timeEnd;
+    // camera constants derived once on the host (PerspectiveCamera ctor, PerspectiveCamera.cpp:15-24)
+    float opWidth, opHeight, imgPlaneArea, lensAreaPDF;
+    float selectWLPDF;          // 16/470 spectral, 1 RGB
+    float recBinWidth;          // 16/470 spectral (SpectrumStorage::add), 1 RGB
+};
+
+// launch helpers implemented in trace.cu (compiled with -fmad=false: same arithmetic as the batch API)
+int launchExtend(const SlrGpuScene* sc, const PathQueue& q, uint32_t n, const HitBuffer& hits, WavefrontCounters* counters, cudaStream_t stream);
+int launchShadow(const SlrGpuScene* sc, const ShadowQueue& q, uint32_t n, float* accum, WavefrontCounters* counters, cudaStream_t stream);
+
+// Stratum of wavelength i for a path with stratification offset `wlOffset`: min(uint((lambda_i - 360)
+// / 470 * 16), 15) (SpectrumTypes.h:826-835) in uncontracted fp32 as the x86-64 reference computes it
+// (the index is a rounding decision). It equals i except at rounding boundaries.
+__device__ __forceinline__ uint32_t stratumOf(int i, float wlOffset) {
+    const float lambda = __fadd_rn(360.0f, __fdiv_rn(__fmul_rn(470.0f, __fadd_rn((float)i, wlOffset)), 16.0f));
+    return min((uint32_t)__fmul_rn(__fdiv_rn(__fsub_rn(lambda, 360.0f), 470.0f), 16.0f), 15u);
+}
+__device__ __forceinline__ bool strataInPlace(float wlOffset) {
+    bool inPlace = true;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) inPlace = inPlace && (stratumOf(i, wlOffset) == (uint32_t)i);
+    return inPlace;
+}
+
+// accum[pixel * NC + stratum(i)] += v[i]: the sensor splat of ImageSensor::add / SpectrumStorage::add
+// (ImageSensor.cpp:124-129). `inPlace` (decided once per path at ray generation) says every
+// wavelength falls into its own stratum: the splat is then four 16-byte vector reductions
+// (RED.E.ADD.F32x4.FTZ.RN), else sixteen scalar ones at the computed strata.
+template <int NC>
+__device__ __forceinline__ void splat(float* __restrict__ accum, uint32_t pixel, float wlOffset, bool inPlace, const float* v) {
+    float* px = accum + (size_t)pixel * NC;
+    if (NC == 16) {
+        if (inPlace) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(px + 4 * q), "f"(v[4 * q]), "f"(v[4 * q + 1]),
+                             "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
+                             : "memory");
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(px + stratumOf(i, wlOffset), v[i]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) atomicAdd(px + i, v[i]);
+    }
+}
+
+}  // namespace slrgpu
