@@ -101,3 +101,9 @@ def write_cornell_diffuse(directory, width=128, height=128, spp=16):
     with open(path, "w") as f:
         f.write(t)
     return path
+
+
+SCENES = {
+    "diffuse": write_cornell_diffuse,
+    "spheres": write_cornell_spheres,
+}
