@@ -7,9 +7,11 @@ One "step" = one pass of the hot path over one batch of synthetic input. Prints 
 (rank 0). See DESIGN.md "Measurement" for the definition of every field.
 
 Workloads
+  cornell_spheres (default)  the path tracer on BASELINE.json configs[0], Cornell_Box_Spheres 512x512 64 spp
+              spectral -- the configuration north_star's >= 100x target is quoted on; metric Mpaths/s
+              (slr_b200/render_bench.py).
   intersect   incoherent-ray closest-hit microbench (BASELINE.json configs[4] at a single-GPU size):
               heightfield triangle mesh -> host SBVH -> QBVH, random rays; metric Mrays/s.
-  (the path-tracing workloads are added by slr_b200/render_bench.py when the renderer is built)
 
 Timing: CUDA events on the launching stream, W >= 3 warm-up steps, barrier + synchronize on both
 sides, max over ranks. The ray batch (>= 512 MB of SoA inputs+outputs per step at the default size)
@@ -210,6 +212,9 @@ def main():
     ap.add_argument("--grid", type=int, default=500, help="heightfield resolution (2*grid^2 triangles)")
     ap.add_argument("--rays", type=int, default=16 * 1024 * 1024)
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
+    ap.add_argument("--size", type=int, default=0, help="render workloads: override the image size")
+    ap.add_argument("--spp", type=int, default=0, help="render workloads: override the samples per pixel (per GPU)")
+    ap.add_argument("--pool", type=int, default=0, help="render workloads: paths in flight (0 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

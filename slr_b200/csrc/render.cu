@@ -14,6 +14,7 @@
 #include <chrono>
 #include <cstring>
 #include <new>
+#include <vector>
 
 namespace slrgpu {
 
@@ -364,6 +365,7 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accum
     if ((rcode = bufs.alloc(&sq.contrib, (uint64_t)P * quarters))) return rcode;
     sq.capacity = P;
     if ((rcode = bufs.alloc(&dCounters, 1))) return rcode;
+    SLRGPU_CUDA_TRY(cudaMemsetAsync(dCounters, 0, sizeof(WavefrontCounters), stream));
     WavefrontCounters* hCounters = nullptr;
     SLRGPU_CUDA_TRY(cudaMallocHost(&hCounters, sizeof(WavefrontCounters)));
     struct PinnedFree { void* p; ~PinnedFree() { cudaFreeHost(p); } } pinnedFree{hCounters};
@@ -374,7 +376,23 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accum
     struct EventFree { cudaEvent_t a, b; ~EventFree() { cudaEventDestroy(a); cudaEventDestroy(b); } } eventFree{ev0, ev1};
     SLRGPU_CUDA_TRY(cudaEventRecord(ev0, stream));
 
-    unsigned long long generated = 0, extendRays = 0, shadowRays = 0, launches = 0;
+    // per-stage device time (SLRGPU_RENDER_PROFILE_STAGES): one event pair per launch, summed at the end
+    const bool profile = (p->flags & SLRGPU_RENDER_PROFILE_STAGES) != 0;
+    struct StageTimer {
+        std::vector<cudaEvent_t> ev[4];      // 0 raygen, 1 extend, 2 shade, 3 shadow: begin/end pairs
+        bool on;
+        cudaStream_t st;
+        void mark(int stage) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev[stage].push_back(e); }
+        float total(int stage) {
+            float sum = 0.0f;
+            for (size_t i = 0; i + 1 < ev[stage].size(); i += 2) { float ms = 0.0f; cudaEventElapsedTime(&ms, ev[stage][i], ev[stage][i + 1]); sum += ms; }
+            return sum;
+        }
+        ~StageTimer() { for (auto& v : ev) for (cudaEvent_t e : v) cudaEventDestroy(e); }
+    } timer;
+    timer.on = profile; timer.st = stream;
+
+    unsigned long long generated = 0, extendRays = 0, shadowRays = 0, launches = 0, waves = 0;
     int cur = 0;
     uint32_t nCur = 0;
     bool overflow = false;
@@ -384,17 +402,24 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accum
         const uint32_t room = P - nCur;
         const uint32_t fresh = (uint32_t)(remaining < room ? remaining : room);
         if (fresh) {
+            timer.mark(0);
             if (rgb) launchRaygen<3>(sc, rc, generated, fresh, q[cur], nCur, stream);
             else launchRaygen<16>(sc, rc, generated, fresh, q[cur], nCur, stream);
+            timer.mark(0);
             ++launches;
             generated += fresh;
             nCur += fresh;
         }
         if (nCur == 0) break;
         SLRGPU_CUDA_TRY(cudaMemsetAsync(dCounters, 0, 16, stream));
-        if ((rcode = launchExtend(sc, q[cur], nCur, hits, dCounters, stream))) return rcode;
+        ++waves;
+        timer.mark(1);
+        if ((rcode = launchExtend(sc, q[cur], nCur, hits, dCounters, profile, stream))) return rcode;
+        timer.mark(1);
+        timer.mark(2);
         if (rgb) launchShade<3>(sc, rc, q[cur], nCur, hits, q[cur ^ 1], sq, accumDev, dCounters, stream);
         else launchShade<16>(sc, rc, q[cur], nCur, hits, q[cur ^ 1], sq, accumDev, dCounters, stream);
+        timer.mark(2);
         SLRGPU_CUDA_TRY(cudaGetLastError());
         launches += 2;
         extendRays += nCur;
@@ -403,7 +428,9 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accum
         const uint32_t nShadow = hCounters->numShadow;
         if (hCounters->stackOverflow) overflow = true;
         if (nShadow) {
-            if ((rcode = launchShadow(sc, sq, nShadow, accumDev, dCounters, stream))) return rcode;
+            timer.mark(3);
+            if ((rcode = launchShadow(sc, sq, nShadow, accumDev, dCounters, profile, stream))) return rcode;
+            timer.mark(3);
             ++launches;
             shadowRays += nShadow;
         }
@@ -412,7 +439,7 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accum
     }
     SLRGPU_CUDA_TRY(cudaEventRecord(ev1, stream));
     SLRGPU_CUDA_TRY(cudaEventSynchronize(ev1));
-    SLRGPU_CUDA_TRY(cudaMemcpy(hCounters, dCounters, 16, cudaMemcpyDeviceToHost));
+    SLRGPU_CUDA_TRY(cudaMemcpy(hCounters, dCounters, sizeof(WavefrontCounters), cudaMemcpyDeviceToHost));
     if (hCounters->stackOverflow) overflow = true;
     if (stats) {
         memset(stats, 0, sizeof(*stats));
@@ -420,7 +447,15 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accum
         stats->extend_rays = extendRays; stats->shadow_rays = shadowRays;
         stats->rays = extendRays + shadowRays;
         stats->kernel_launches = launches;
+        stats->waves = waves;
         cudaEventElapsedTime(&stats->device_ms, ev0, ev1);
+        if (profile) {
+            stats->raygen_ms = timer.total(0); stats->extend_ms = timer.total(1);
+            stats->shade_ms = timer.total(2); stats->shadow_ms = timer.total(3);
+            stats->other_ms = stats->device_ms - stats->raygen_ms - stats->extend_ms - stats->shade_ms - stats->shadow_ms;
+            stats->extend_nodes = hCounters->extendNodes; stats->extend_leaf_records = hCounters->extendLeafRecords;
+            stats->shadow_nodes = hCounters->shadowNodes; stats->shadow_leaf_records = hCounters->shadowLeafRecords;
+        }
     }
     if (overflow) { setError("traversal stack overflow (more than %d entries)", 64); return SLRGPU_ERR_STACK_OVERFLOW; }
     return SLRGPU_OK;

@@ -11,42 +11,55 @@ namespace slrgpu {
 
 constexpr int kTraceBlock = 128;
 
-template <bool INSTANCES>
+// per-warp totals of the traversal counters -> one atomic pair per warp
+__device__ __forceinline__ void addTraversalCounts(const TraversalCounters& cnt, unsigned long long* nodes, unsigned long long* leafRecords) {
+    uint32_t n = cnt.nodes, t = cnt.tris;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { n += __shfl_xor_sync(0xFFFFFFFFu, n, o); t += __shfl_xor_sync(0xFFFFFFFFu, t, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(nodes, (unsigned long long)n); atomicAdd(leafRecords, (unsigned long long)t); }
+}
+
+template <bool INSTANCES, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock)
 extendKernel(const DeviceScene s, PathQueue q, uint32_t n, HitBuffer hits, WavefrontCounters* counters) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 o = q.org[i], d = q.dir[i];
-    Ray r;
-    r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = o.w;
-    r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = INFINITY;
-    Hit h;
-    h.prim = SLRGPU_INVALID_ID; h.inst = SLRGPU_INVALID_ID; h.t = INFINITY; h.u = 0.0f; h.v = 0.0f;
-    uint32_t stack[kStackSize];
     TraversalCounters cnt = {0, 0};
-    bool overflow = false;
-    traverse<INSTANCES ? 0 : 1, false, false>(s, 0, r, h, stack, 0, cnt, overflow);
-    hits.id[i] = make_uint2(h.prim, h.inst);
-    hits.tuv[i] = make_float4(h.t, h.u, h.v, 0.0f);
-    if (overflow) atomicExch(&counters->stackOverflow, 1u);
+    if (i < n) {
+        const float4 o = q.org[i], d = q.dir[i];
+        Ray r;
+        r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = o.w;
+        r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = INFINITY;
+        Hit h;
+        h.prim = SLRGPU_INVALID_ID; h.inst = SLRGPU_INVALID_ID; h.t = INFINITY; h.u = 0.0f; h.v = 0.0f;
+        uint32_t stack[kStackSize];
+        bool overflow = false;
+        traverse<INSTANCES ? 0 : 1, false, COUNT>(s, 0, r, h, stack, 0, cnt, overflow);
+        hits.id[i] = make_uint2(h.prim, h.inst);
+        hits.tuv[i] = make_float4(h.t, h.u, h.v, 0.0f);
+        if (overflow) atomicExch(&counters->stackOverflow, 1u);
+    }
+    if (COUNT) addTraversalCounts(cnt, &counters->extendNodes, &counters->extendLeafRecords);
 }
 
-template <bool INSTANCES, int NC>
+template <bool INSTANCES, int NC, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock)
 shadowKernel(const DeviceScene s, ShadowQueue q, uint32_t n, float* __restrict__ accum, WavefrontCounters* counters) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 o = q.org[i], d = q.dir[i];
-    Ray r;
-    r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = o.w;
-    r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = d.w;
-    Hit h;
-    h.prim = SLRGPU_INVALID_ID; h.inst = SLRGPU_INVALID_ID; h.t = INFINITY; h.u = h.v = 0.0f;
-    uint32_t stack[kStackSize];
     TraversalCounters cnt = {0, 0};
-    bool overflow = false;
-    const bool occluded = traverse<INSTANCES ? 0 : 1, true, false>(s, 0, r, h, stack, 0, cnt, overflow);
-    if (overflow) atomicExch(&counters->stackOverflow, 1u);
+    bool occluded = true;
+    if (i < n) {
+        const float4 o = q.org[i], d = q.dir[i];
+        Ray r;
+        r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = o.w;
+        r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = d.w;
+        Hit h;
+        h.prim = SLRGPU_INVALID_ID; h.inst = SLRGPU_INVALID_ID; h.t = INFINITY; h.u = h.v = 0.0f;
+        uint32_t stack[kStackSize];
+        bool overflow = false;
+        occluded = traverse<INSTANCES ? 0 : 1, true, COUNT>(s, 0, r, h, stack, 0, cnt, overflow);
+        if (overflow) atomicExch(&counters->stackOverflow, 1u);
+    }
+    if (COUNT) addTraversalCounts(cnt, &counters->shadowNodes, &counters->shadowLeafRecords);
     if (occluded) return;
     const uint2 pw = q.pixelWl[i];
     float v[NC == 3 ? 4 : NC];
@@ -62,26 +75,29 @@ shadowKernel(const DeviceScene s, ShadowQueue q, uint32_t n, float* __restrict__
     splat<NC>(accum, pw.x & 0x7FFFFFFFu, __uint_as_float(pw.y), (pw.x >> 31) != 0, v);
 }
 
-int launchExtend(const SlrGpuScene* sc, const PathQueue& q, uint32_t n, const HitBuffer& hits, WavefrontCounters* counters, cudaStream_t stream) {
-    if (n == 0) return SLRGPU_OK;
+template <bool INSTANCES, bool COUNT>
+static void launchExtendT(const SlrGpuScene* sc, const PathQueue& q, uint32_t n, const HitBuffer& hits, WavefrontCounters* counters, cudaStream_t stream) {
+    extendKernel<INSTANCES, COUNT><<<(n + kTraceBlock - 1) / kTraceBlock, kTraceBlock, 0, stream>>>(sc->dev, q, n, hits, counters);
+}
+template <bool INSTANCES, bool COUNT>
+static void launchShadowT(const SlrGpuScene* sc, const ShadowQueue& q, uint32_t n, float* accum, WavefrontCounters* counters, cudaStream_t stream) {
     const dim3 grid((n + kTraceBlock - 1) / kTraceBlock), block(kTraceBlock);
-    if (sc->hasInstances) extendKernel<true><<<grid, block, 0, stream>>>(sc->dev, q, n, hits, counters);
-    else extendKernel<false><<<grid, block, 0, stream>>>(sc->dev, q, n, hits, counters);
+    if (sc->channels == 3) shadowKernel<INSTANCES, 3, COUNT><<<grid, block, 0, stream>>>(sc->dev, q, n, accum, counters);
+    else shadowKernel<INSTANCES, 16, COUNT><<<grid, block, 0, stream>>>(sc->dev, q, n, accum, counters);
+}
+
+int launchExtend(const SlrGpuScene* sc, const PathQueue& q, uint32_t n, const HitBuffer& hits, WavefrontCounters* counters, bool count, cudaStream_t stream) {
+    if (n == 0) return SLRGPU_OK;
+    if (sc->hasInstances) { if (count) launchExtendT<true, true>(sc, q, n, hits, counters, stream); else launchExtendT<true, false>(sc, q, n, hits, counters, stream); }
+    else { if (count) launchExtendT<false, true>(sc, q, n, hits, counters, stream); else launchExtendT<false, false>(sc, q, n, hits, counters, stream); }
     SLRGPU_CUDA_TRY(cudaGetLastError());
     return SLRGPU_OK;
 }
 
-int launchShadow(const SlrGpuScene* sc, const ShadowQueue& q, uint32_t n, float* accum, WavefrontCounters* counters, cudaStream_t stream) {
+int launchShadow(const SlrGpuScene* sc, const ShadowQueue& q, uint32_t n, float* accum, WavefrontCounters* counters, bool count, cudaStream_t stream) {
     if (n == 0) return SLRGPU_OK;
-    const dim3 grid((n + kTraceBlock - 1) / kTraceBlock), block(kTraceBlock);
-    const bool rgb = sc->channels == 3;
-    if (sc->hasInstances) {
-        if (rgb) shadowKernel<true, 3><<<grid, block, 0, stream>>>(sc->dev, q, n, accum, counters);
-        else shadowKernel<true, 16><<<grid, block, 0, stream>>>(sc->dev, q, n, accum, counters);
-    } else {
-        if (rgb) shadowKernel<false, 3><<<grid, block, 0, stream>>>(sc->dev, q, n, accum, counters);
-        else shadowKernel<false, 16><<<grid, block, 0, stream>>>(sc->dev, q, n, accum, counters);
-    }
+    if (sc->hasInstances) { if (count) launchShadowT<true, true>(sc, q, n, accum, counters, stream); else launchShadowT<true, false>(sc, q, n, accum, counters, stream); }
+    else { if (count) launchShadowT<false, true>(sc, q, n, accum, counters, stream); else launchShadowT<false, false>(sc, q, n, accum, counters, stream); }
     SLRGPU_CUDA_TRY(cudaGetLastError());
     return SLRGPU_OK;
 }

@@ -46,7 +46,7 @@ struct WavefrontCounters {
     uint32_t numShadow;        // entries appended to the shadow queue
     uint32_t stackOverflow;
     uint32_t pad;
-    unsigned long long extendRays, shadowRays, pathsStarted, pathsFinished;
+    unsigned long long extendNodes, extendLeafRecords, shadowNodes, shadowLeafRecords;   // only counted by the profiling variants of extend / shadow
 };
 
 struct RenderConstants {
@@ -63,8 +63,9 @@ struct RenderConstants {
 };
 
 // launch helpers implemented in trace.cu (compiled with -fmad=false: same arithmetic as the batch API)
-int launchExtend(const SlrGpuScene* sc, const PathQueue& q, uint32_t n, const HitBuffer& hits, WavefrontCounters* counters, cudaStream_t stream);
-int launchShadow(const SlrGpuScene* sc, const ShadowQueue& q, uint32_t n, float* accum, WavefrontCounters* counters, cudaStream_t stream);
+// `count` selects the variants that also total QBVH nodes popped / leaf records tested (the algorithmic-bytes model)
+int launchExtend(const SlrGpuScene* sc, const PathQueue& q, uint32_t n, const HitBuffer& hits, WavefrontCounters* counters, bool count, cudaStream_t stream);
+int launchShadow(const SlrGpuScene* sc, const ShadowQueue& q, uint32_t n, float* accum, WavefrontCounters* counters, bool count, cudaStream_t stream);
 
 // Stratum of wavelength i for a path with stratification offset `wlOffset`: min(uint((lambda_i - 360)
 // / 470 * 16), 15) (SpectrumTypes.h:826-835) in uncontracted fp32 as the x86-64 reference computes it

@@ -1,4 +1,7 @@
 #include "shading.h"
+#include "assets/exr.h"
+#include "assets/images.h"
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -230,8 +233,84 @@ uint32_t GpuSceneBuilder::exportMaterial(const SurfaceMaterial* m) {
 
 bool GpuSceneBuilder::materialEmits(const SurfaceMaterial* m) const { return m && m->isEmitting(); }
 
-void exportEnvironment(GpuSceneBuilder&, const InfiniteSphereNode&) {
-    throw std::runtime_error("environment lights are not implemented yet");
+// InfiniteSphereSurfaceObject + IBLEmission: the environment's emitter material and the importance map
+// of ImageSpectrumTexture::createIBLImportanceMap (image_textures.cpp:81-134) -- one cell per 4x4 texel
+// block, weight = sin(theta) * luminance of the block's area average (Image2D::areaAverage,
+// Image.cpp:19-330, whose summation order and half-float round trips are kept) -- as the
+// RegularConstantContinuous2D the reference builds from it (distributions.cpp:126-206).
+namespace {
+struct KahanSum {
+    float result = 0.0f, comp = 0.0f;
+    void add(float v) { float c = v - comp; float t = result + c; comp = (t - result) - c; result = t; }
+};
+float halfRound(float f) { return exr::halfToFloat(exr::floatToHalf(f)); }
+
+// luminance of the area average of the 4x4 block (bx, by)
+float blockLuminance(const Image2D& img, uint32_t bx, uint32_t by, uint32_t dx, uint32_t dy) {
+    const uint16_t* tex = reinterpret_cast<const uint16_t*>(img.data.data());
+    const bool uvs = img.format == SLRGPU_IMG_UVSA16Fx4;
+    KahanSum sr, sg, sb;
+    auto addTexel = [&](uint32_t x, uint32_t y) {
+        const uint16_t* t = tex + 4 * ((size_t)y * img.width + x);
+        float v[3] = {exr::halfToFloat(t[0]), exr::halfToFloat(t[1]), exr::halfToFloat(t[2])};
+        if (uvs) { float rgb[3]; uvs_to_sRGB(img.spectrumType, v, rgb); sr.add(rgb[0]); sg.add(rgb[1]); sb.add(rgb[2]); }
+        else { sr.add(v[0]); sg.add(v[1]); sb.add(v[2]); }
+    };
+    const uint32_t x0 = bx * dx, x1 = x0 + dx - 1, y0 = by * dy, y1 = y0 + dy - 1;
+    addTexel(x0, y0); addTexel(x1, y0); addTexel(x0, y1); addTexel(x1, y1);                    // corners
+    for (uint32_t x = x0 + 1; x < x1; ++x) { addTexel(x, y0); addTexel(x, y1); }              // top / bottom edges
+    for (uint32_t y = y0 + 1; y < y1; ++y) { addTexel(x0, y); addTexel(x1, y); }              // left / right edges
+    for (uint32_t y = y0 + 1; y < y1; ++y) for (uint32_t x = x0 + 1; x < x1; ++x) addTexel(x, y);
+    const float area = (float)dy * (float)dx;
+    float rgb[3] = {sr.result / area, sg.result / area, sb.result / area};
+    if (uvs) {
+        float q[3];
+        sRGB_to_uvs(img.spectrumType, rgb, q);
+        for (int i = 0; i < 3; ++i) q[i] = halfRound(q[i]);
+        uvs_to_sRGB(img.spectrumType, q, rgb);
+    } else {
+        for (int i = 0; i < 3; ++i) rgb[i] = halfRound(rgb[i]);
+    }
+    return 0.222485f * rgb[0] + 0.716905f * rgb[1] + 0.060610f * rgb[2];
+}
+
+// RegularConstantContinuous1D ctor on pdf[0..n) in place; cdf gets n + 1 entries; returns the integral
+float buildContinuous1D(float* pdf, float* cdf, uint32_t n) {
+    KahanSum sum;
+    cdf[0] = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) { sum.add(pdf[i] / n); cdf[i + 1] = sum.result; }
+    const float integral = sum.result;
+    for (uint32_t i = 0; i < n; ++i) { pdf[i] /= integral; cdf[i + 1] /= integral; }
+    return integral;
+}
+}  // namespace
+
+void exportEnvironment(GpuSceneBuilder& b, const InfiniteSphereNode& env) {
+    if (!env.emission || !env.emission->emittance || !env.emission->emittance->image)
+        throw std::runtime_error("the environment needs an image texture");
+    const Image2D& img = *env.emission->emittance->image;
+    if (img.format != SLRGPU_IMG_UVSA16Fx4 && img.format != SLRGPU_IMG_RGBA16Fx4)
+        throw std::runtime_error("the environment image must be a half-float RGBA image");
+    FlatScene& f = b.flat;
+    const uint32_t W = img.width / 4, H = img.height / 4;
+    if (W == 0 || H == 0) throw std::runtime_error("the environment image is too small");
+    const uint32_t dx = img.width / W, dy = img.height / H;
+    f.envPresent = true;
+    f.envMaterial = exportEmitter(b, env.emission.get());
+    f.envMapWidth = W; f.envMapHeight = H;
+    f.envRowPdf.assign((size_t)W * H, 0.0f);
+    f.envRowCdf.assign((size_t)(W + 1) * H, 0.0f);
+    f.envRowIntegral.assign(H, 0.0f);
+    f.envMarginalPdf.assign(H, 0.0f);
+    f.envMarginalCdf.assign(H + 1, 0.0f);
+    for (uint32_t y = 0; y < H; ++y) {
+        const double sinTheta = std::sin(M_PI * (y + 0.5f) / H);
+        float* pdf = &f.envRowPdf[(size_t)y * W];
+        for (uint32_t x = 0; x < W; ++x) pdf[x] = (float)(sinTheta * blockLuminance(img, x, y, dx, dy));
+        f.envRowIntegral[y] = buildContinuous1D(pdf, &f.envRowCdf[(size_t)y * (W + 1)], W);
+        f.envMarginalPdf[y] = f.envRowIntegral[y];
+    }
+    f.envMarginalIntegral = buildContinuous1D(f.envMarginalPdf.data(), f.envMarginalCdf.data(), H);
 }
 
 void finishShadingTables(GpuSceneBuilder& b) { caches().erase(&b); }

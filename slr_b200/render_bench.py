@@ -1,0 +1,244 @@
+"""Path-tracing workloads of bench.py (see bench.py's docstring for the command line contract).
+
+Workload `cornell_spheres` = BASELINE.json configs[0] (the configuration north_star's target is quoted
+on): Cornell_Box_Spheres, 512x512, 64 spp, unidirectional PT, spectral. One step = one frame.
+
+  value   frame throughput with the scene resident in HBM: per step every rank clears its device
+          accumulation buffer, renders its samples (slrgpu_render_device) and -- N > 1 -- the buffers are
+          summed onto rank 0 with one NCCL reduce. CUDA events on the launch stream, max over ranks.
+          Weak scaling: every rank renders the full 64 spp of its own sample range [64 r, 64 (r + 1)),
+          i.e. the N-GPU frame has 64 N spp (BASELINE.json configs[3] splits 1024 spp as 128 per GPU).
+  e2e     the same frame through the renderer front end with HOST buffers: scene upload
+          (slrgpu_scene_create from the host SoA buffers), render, download of the accumulation buffer
+          into host memory. At N = 1 this is literally slrhost_render (= GPUPathTracingRenderer::render,
+          the drop-in for PathTracingRenderer::render); at N > 1 each rank does upload + render, the
+          device buffers are NCCL-reduced and rank 0 downloads.
+"""
+import ctypes as C
+import json
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+METRIC = "Mpaths/s (unidirectional path tracing, camera samples per second)"
+
+WORKLOADS = {
+    # name: (scene key of slr_b200.scenes.SCENES, width, height, spp, description)
+    "cornell_spheres": ("spheres", 512, 512, 64,
+                        "Cornell_Box_Spheres 512x512 64spp unidirectional PT spectral (BASELINE configs[0])"),
+    "cornell_diffuse": ("diffuse", 512, 512, 64, "empty Cornell box 512x512 64spp unidirectional PT spectral"),
+}
+
+
+def _scene(args):
+    from . import scenes
+    key, w, h, spp, desc = WORKLOADS[args.workload]
+    if getattr(args, "size", 0):
+        w = h = args.size
+    if getattr(args, "spp", 0):
+        spp = args.spp
+    d = tempfile.mkdtemp(prefix="slr_bench_")
+    path = scenes.SCENES[key](d, width=w, height=h, spp=spp)
+    return path, w, h, spp, desc
+
+
+def _ref_step(path, w, h, spp):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import render_util as ru
+    t0 = time.perf_counter()
+    _, j = ru.run_ref_render(path, spp, w, h)
+    wall = time.perf_counter() - t0
+    return j, wall
+
+
+def cpu_baseline(path, w, h, spp):
+    """The reference's own PathTracingRenderer (oracle/_ref/ref_render, built from /root/reference) on
+    this box's host cores: std::thread::hardware_concurrency() workers, shipped default accelerator (SBVH)."""
+    j, wall = _ref_step(path, w, h, spp)
+    return {"value": j["mpaths_per_s"], "unit": "Mpaths/s", "cores": j["threads"], "kind": "reference",
+            "sample": f"the same scene at {w}x{h}, {spp} spp ({w * h * spp} paths) through the reference's "
+                      f"PathTracingRenderer::render, {j['threads']} threads, {j['accelerator']}; render {j['render_s']:.2f} s "
+                      f"(scene read+build {j['read_s'] + j['build_s']:.2f} s not counted)"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    path, w, h, spp, desc = _scene(args)
+    total = args.steps + args.warmup
+    step_spp = spp if total <= 20 else max(8, spp // 4)     # keep the whole run within a few minutes
+    vals = []
+    t0 = time.perf_counter()
+    for i in range(total):
+        j, wall = _ref_step(path, w, h, step_spp)
+        if i >= args.warmup:
+            vals.append(j)
+    wall = time.perf_counter() - t0
+    mp = float(np.mean([j["mpaths_per_s"] for j in vals]))
+    render_s = float(np.mean([j["render_s"] for j in vals]))
+    cb = {"value": mp, "unit": "Mpaths/s", "cores": vals[0]["threads"], "kind": "reference",
+          "sample": f"{w}x{h}, {step_spp} spp per step through the reference's PathTracingRenderer::render "
+                    f"({vals[0]['threads']} threads, {vals[0]['accelerator']}); mean of {len(vals)} steps"}
+    line = {"impl": "reference", "metric": METRIC, "value": mp, "unit": "Mpaths/s", "n_gpus": 0, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * render_s, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "width": w, "height": h, "spp": spp, "spp_per_step": step_spp},
+            "cpu_baseline": cb,
+            "e2e": {"value": mp, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main(args, rank, world):
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    import torch
+    import bench
+    from . import capi
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl")
+    dev = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(dev)
+    path, w, h, spp, desc = _scene(args)
+    hs = capi.read_scene(path)
+    gs = capi.GpuScene(hs, device=dev)
+    chan = capi.gpu.slrgpu_scene_channels(gs.handle)
+    accum = torch.zeros((h, w, chan), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream()
+    seed = 1509761209
+    params = capi.RenderParams(C.sizeof(capi.RenderParams), w, h, spp * rank, spp * (rank + 1), 0.0, 0.0, seed, 0,
+                               getattr(args, "pool", 0) or 0, 0)
+
+    def frame(flags=0):
+        params.flags = flags
+        st = capi.RenderStats()
+        accum.zero_()
+        rc = capi.gpu.slrgpu_render_device(gs.handle, C.byref(params), C.c_void_p(accum.data_ptr()),
+                                           C.c_void_p(stream.cuda_stream), C.byref(st))
+        if rc != 0:
+            raise RuntimeError(capi.gpu.slrgpu_last_error().decode())
+        if dist is not None:
+            dist.reduce(accum, dst=0)
+        return st
+
+    # one profiled, untimed frame: stage times and the traversal counts of the algorithmic-bytes model
+    prof = frame(capi.RENDER_PROFILE_STAGES)
+    torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        frame()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    rays = 0
+    with bench.ClockSampler(dev) as clocks:
+        e0.record(stream)
+        for _ in range(args.steps):
+            st = frame()
+            launches += st.kernel_launches + (1 if dist is not None else 0) + 1     # + reduce, + clear
+            rays += st.rays
+        e1.record(stream)
+        torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    paths_per_step = w * h * spp
+
+    # ---- end to end with host buffers
+    e2e_steps = max(1, min(args.steps, 3))
+    scene_bytes = int(gs.device_bytes)
+    accum_bytes = w * h * chan * 4
+    if world == 1:
+        capi.host_render(hs, w, h, spp, seed, dev)        # warm
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            img, hst = capi.host_render(hs, w, h, spp, seed, dev)
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+    else:
+        pinned = torch.empty((h, w, chan), dtype=torch.float32).pin_memory()
+
+        def e2e_frame():
+            g2 = capi.GpuScene(hs, device=dev)
+            st2 = capi.RenderStats()
+            accum.zero_()
+            rc = capi.gpu.slrgpu_render_device(g2.handle, C.byref(params), C.c_void_p(accum.data_ptr()),
+                                               C.c_void_p(stream.cuda_stream), C.byref(st2))
+            if rc != 0:
+                raise RuntimeError(capi.gpu.slrgpu_last_error().decode())
+            dist.reduce(accum, dst=0)
+            if rank == 0:
+                pinned.copy_(accum, non_blocking=False)
+            torch.cuda.synchronize()
+            g2.close()
+        e2e_frame()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_frame()
+        dist.barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+
+    if dist is not None:
+        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+        tr = torch.tensor([float(rays)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tr)
+        rays = float(tr[0])
+    else:
+        rays = float(rays)
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+
+    peak, peak_src = bench.measured_peaks()
+    value = paths_per_step * world * args.steps / (ms * 1e-3) / 1e6
+    # dominant kernel by the profiled frame's stage times
+    stages = {"extendKernel": prof.extend_ms, "shadeKernel": prof.shade_ms, "shadowKernel": prof.shadow_ms, "raygenKernel": prof.raygen_ms}
+    dom = max(stages, key=stages.get)
+    S_PATH, S_HIT, S_SHADOW = (116, 24, 108) if chan == 16 else (68, 24, 60)
+    n_ext, n_sh = prof.extend_rays, prof.shadow_rays
+    algo = {
+        # 32 B ray in + 128 B per node popped + 48 B per leaf record tested + 24 B hit record out
+        "extendKernel": 32 * n_ext + 128 * prof.extend_nodes + 48 * prof.extend_leaf_records + S_HIT * n_ext,
+        # shadow entry in + nodes + leaf records (+ the splat, counted as 64 B read-modify-write of unoccluded entries; upper bound: all)
+        "shadowKernel": S_SHADOW * n_sh + 128 * prof.shadow_nodes + 48 * prof.shadow_leaf_records,
+        # path state + hit in, surviving path state + shadow entry out, 3 vertices (144 B) + triangle record (32 B) per hit
+        "shadeKernel": (S_PATH + S_HIT + 176) * n_ext + S_PATH * (n_ext - paths_per_step) + S_SHADOW * n_sh,
+        "raygenKernel": S_PATH * paths_per_step,
+    }
+    # share of the step the dominant kernel takes in the profiled frame, applied to the timed steps
+    share = stages[dom] / max(prof.device_ms, 1e-9)
+    dom_ms_per_step = share * ms / args.steps
+    ach = algo[dom] / (dom_ms_per_step * 1e-3) / 1e9
+    cpu = cpu_baseline(path, w, h, spp)
+    line = {"metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "width": w, "height": h, "spp_per_gpu": spp, "frame_spp": spp * world,
+                       "paths_per_gpu_per_step": paths_per_step, "rays_per_path": rays / (paths_per_step * world * args.steps),
+                       "mrays_per_s": rays / (ms * 1e-3) / 1e6, "waves_per_frame": int(prof.waves),
+                       "triangles": int(hs.desc.num_triangles), "qbvh_nodes": int(hs.desc.num_bvh_nodes),
+                       "scene_bytes": scene_bytes, "host_scene_build_s": round(hs.build_seconds, 3),
+                       "l2_policy": "per-step working set (wavefront queues + accumulation buffer, > 500 MB) is larger than L2; "
+                                    "the scene itself (QBVH + leaf records) is L2-resident by design",
+                       "stage_ms_profiled_frame": {k: round(v, 3) for k, v in stages.items()} | {"other": round(prof.other_ms, 3), "frame": round(prof.device_ms, 3)}},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "kernel": dom, "peak_source": peak_src, "kernel_share_of_step": share,
+                         "algorithmic_bytes_per_launch_set": algo[dom],
+                         "note": "algorithmic bytes of all launches of the kernel in one frame / its summed device time"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": paths_per_step * world / e2e_s / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": scene_bytes,
+                    "d2h_bytes_per_step": accum_bytes},
+            "gpu_launches": int(launches), "clocks": clocks.summary()}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()

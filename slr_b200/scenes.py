@@ -103,7 +103,297 @@ def write_cornell_diffuse(directory, width=128, height=128, spp=16):
     return path
 
 
+
+def write_cornell_box_rb_asset(directory):
+    """models/Cornell_box_RB.assbin: the [-1, 1]^3 box of Cornell_Box_ColorChecker.txt, open towards +z,
+    white floor / ceiling / back wall, red left and blue right wall (one mesh + material per colour)."""
+    os.makedirs(os.path.join(directory, "models"), exist_ok=True)
+    q = synth.quad_mesh
+    white = [q([(-1, -1, 1), (1, -1, 1), (1, -1, -1), (-1, -1, -1)], (0, 1, 0), (1, 0, 0)),
+             q([(-1, 1, -1), (1, 1, -1), (1, 1, 1), (-1, 1, 1)], (0, -1, 0), (1, 0, 0)),
+             q([(-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1)], (0, 0, 1), (1, 0, 0))]
+    pos = np.concatenate([m["positions"] for m in white])
+    idx = np.concatenate([m["indices"] + 4 * k for k, m in enumerate(white)])
+    wmesh = {"name": "white", "positions": pos, "indices": idx, "normals": np.concatenate([m["normals"] for m in white]),
+             "tangents": np.concatenate([m["tangents"] for m in white]), "uvs": np.concatenate([m["uvs"] for m in white]), "material": 0}
+    red = q([(-1, -1, 1), (-1, -1, -1), (-1, 1, -1), (-1, 1, 1)], (1, 0, 0), (0, 0, -1))
+    red.update(name="red", material=1)
+    blue = q([(1, -1, -1), (1, -1, 1), (1, 1, 1), (1, 1, -1)], (-1, 0, 0), (0, 0, 1))
+    blue.update(name="blue", material=2)
+    path = os.path.join(directory, "models", "Cornell_box_RB.assbin")
+    synth.write_assbin_scene(path, [wmesh, red, blue],
+                             [{"name": "white", "diffuse": (0.75, 0.75, 0.75)}, {"name": "red", "diffuse": (0.75, 0.25, 0.25)},
+                              {"name": "blue", "diffuse": (0.25, 0.25, 0.75)}])
+    return path
+
+
+_RB_LIGHT = """    lightNode = createNode();
+    setTransform(lightNode, translate(0.0, 0.999, 0.0));
+        diffuseCol = Spectrum(0.9, 0.9, 0.9);
+        diffuseTex = SpectrumTexture(diffuseCol);
+        scatterMat = createSurfaceMaterial("matte", (diffuseTex,));
+        difLightCol = Spectrum("ID": "D65");
+        difLightTex = SpectrumTexture(difLightCol);
+        emitterMat = createEmitterSurfaceProperty("diffuse", (difLightTex,));
+        surfMat = createSurfaceMaterial("emitter", (scatterMat, emitterMat));
+
+        lightMesh = createMesh(
+            (
+            ((-0.25, 0, -0.25), (0, -1, 0), (1, 0, 0), (0, 0)),
+            (( 0.25, 0, -0.25), (0, -1, 0), (1, 0, 0), (1, 0)),
+            (( 0.25, 0,  0.25), (0, -1, 0), (1, 0, 0), (1, 1)),
+            ((-0.25, 0,  0.25), (0, -1, 0), (1, 0, 0), (0, 1))
+            ),
+            (
+            (surfMat, ((0, 1, 2), (0, 2, 3))),
+            )
+            );
+        addChild(lightNode, lightMesh);
+    addChild(CBNode, lightNode);
+addChild(root, CBNode);
+"""
+
+_COLOR_CHECKER = """// Color Checker Materials
+mats = (,);
+for (i = 0; i < 24; ++i) {
+    sp = Spectrum("ID": "ColorChecker", i);
+    difTex = SpectrumTexture(sp);
+    scatterMat = createSurfaceMaterial("matte", (difTex,));
+    addItem(mats, scatterMat);
+}
+
+// Create Color Checker
+vertices = (,);
+matGroups = (,);
+for (i = 0; i < 24; ++i) {
+    transform = %s;
+
+    addItem(vertices, transform * createVertex((0.0, 0.0, 0.0), %s, (1, 0, 0), (0, 0)));
+    addItem(vertices, transform * createVertex((1.0, 0.0, 0.0), %s, (1, 0, 0), (1, 0)));
+    addItem(vertices, transform * createVertex(%s, %s, (1, 0, 0), (1, 1)));
+    addItem(vertices, transform * createVertex(%s, %s, (1, 0, 0), (0, 1)));
+
+    idxBase = 4 * i;
+    addItem(matGroups, (mats[i], ((idxBase + 0, idxBase + 1, idxBase + 2), (idxBase + 0, idxBase + 2, idxBase + 3))));
+}
+colorCheckerMesh = createMesh(vertices, matGroups);
+"""
+
+
+def write_cornell_materials(directory, width=1024, height=1024, spp=256):
+    """Config C2: the Cornell_Box_ColorChecker.txt layout (Cornell_box_RB model, D65 light quad, colour
+    checker on the back wall) with the material override script of SURVEY.md section 8d: GGX conductor
+    with a checker roughness texture, Ward, Oren-Nayar with checker / Voronoi colour and normal textures,
+    Ashikhmin-Shirley, a mixed material and rough glass."""
+    write_cornell_box_rb_asset(directory)
+    write_sphere_asset(directory)
+    t = f'setRenderer("method": "PT", ("samples": {spp},));\nsetRenderSettings("width": {width}, "height": {height}, "brightness": 4.0);\n\n'
+    t += """function CornellBoxMaterial(name, attrs) {
+    difCol = attrs["diffuse color"];
+    if (name == "white") {
+        c0 = Spectrum(difCol[0], difCol[1], difCol[2]);
+        c1 = Spectrum(0.35, 0.45, 0.35);
+        difTex = SpectrumTexture("checker board", (c0, c1));
+        sigma = FloatTexture(0.6);
+        normalTex = NormalTexture("checker board", (0.05, false));
+        return (createSurfaceMaterial("matte", (difTex, sigma)), normalTex);
+    }
+    if (name == "red") {
+        difTex = SpectrumTexture("voronoi", (0.35, 0.8));
+        return createSurfaceMaterial("matte", (difTex, FloatTexture(0.3)));
+    }
+    difTex = SpectrumTexture(Spectrum(difCol[0], difCol[1], difCol[2]));
+    ax = FloatTexture(0.1);
+    ay = FloatTexture(0.3);
+    return createSurfaceMaterial("Ward", (difTex, ax, ay));
+}
+
+CBNode = load3DModel("models/Cornell_box_RB.assbin", CornellBoxMaterial);
+""" + _RB_LIGHT + "\n" + (_COLOR_CHECKER % (
+        "translate(0, 0, -0.999) * scale(0.9 / 3.0) *\n                translate(-3.0 + (i % 6), 1.0 - (i / 6), 0.0)",
+        "(0, 0, 1)", "(0, 0, 1)", "(1.0, 1.0, 0.0)", "(0, 0, 1)", "(0.0, 1.0, 0.0)", "(0, 0, 1)")) + """addChild(CBNode, colorCheckerMesh);
+
+function ggxMetal(name, attrs) {
+    eta = SpectrumTexture(Spectrum("ID": "Gold", 0));
+    k = SpectrumTexture(Spectrum("ID": "Gold", 1));
+    alpha = FloatTexture("checker board", (0.05, 0.3));
+    return createSurfaceMaterial("microfacet metal", (eta, k, alpha));
+}
+s0 = load3DModel("models/sphere.assbin", ggxMetal);
+setTransform(s0, translate(-0.55, -0.65, -0.3) * scale(0.35));
+addChild(CBNode, s0);
+
+function ashikhmin(name, attrs) {
+    Rd = SpectrumTexture(Spectrum(0.1, 0.5, 0.7));
+    Rs = SpectrumTexture(Spectrum(0.1, 0.1, 0.1));
+    return (createSurfaceMaterial("Ashikhmin", (Rd, Rs, FloatTexture(1000), FloatTexture(100))), NormalTexture("voronoi", (0.08, 0.4)));
+}
+s1 = load3DModel("models/sphere.assbin", ashikhmin);
+setTransform(s1, translate(0.45, -0.7, 0.1) * scale(0.3));
+addChild(CBNode, s1);
+
+function mixedMat(name, attrs) {
+    m0 = createSurfaceMaterial("matte", (SpectrumTexture(Spectrum(0.7, 0.6, 0.2)),));
+    eta = SpectrumTexture(Spectrum("ID": "Copper", 0));
+    k = SpectrumTexture(Spectrum("ID": "Copper", 1));
+    m1 = createSurfaceMaterial("metal", (SpectrumTexture(Spectrum("Reflectance", 0.95)), eta, k));
+    return createSurfaceMaterial("mix", (m0, m1, FloatTexture("voronoi", (0.15, 1.0, true))));
+}
+s2 = load3DModel("models/sphere.assbin", mixedMat);
+setTransform(s2, translate(-0.1, -0.75, 0.55) * scale(0.25));
+addChild(CBNode, s2);
+
+function roughGlass(name, attrs) {
+    etaExt = SpectrumTexture(Spectrum("ID": "Air", 0));
+    etaInt = SpectrumTexture(Spectrum("ID": "Glass_BK7", 0));
+    return createSurfaceMaterial("microfacet glass", (etaExt, etaInt, FloatTexture(0.15)));
+}
+s3 = load3DModel("models/sphere.assbin", roughGlass);
+setTransform(s3, translate(0.55, 0.2, -0.4) * scale(0.28));
+addChild(CBNode, s3);
+
+cameraNode = createNode();
+    camera = createPerspectiveCamera("aspect": 1.0, "fovY": 0.5235987756, "radius": 0.025,
+                                     "imgDist": 1.0, "objDist": 5);
+    addChild(cameraNode, camera);
+setTransform(cameraNode, translate(0, 0, 5) * rotateY(-3.1415926536));
+
+addChild(root, cameraNode);
+"""
+    path = os.path.join(directory, "Cornell_Box_ColorChecker.txt")
+    with open(path, "w") as f:
+        f.write(t)
+    return path
+
+
+def write_ibl_test(directory, width=1024, height=1024, spp=256, env_size=(2048, 1024)):
+    """Config C3: the IBL_Test.txt layout -- HDR environment with importance sampling, colour checker on
+    the ground, aluminium sphere, an Ashikhmin-Shirley object (a synthetic bumpy ball stands in for the
+    Kirby model), thin-lens camera, whole scene rotated."""
+    write_sphere_asset(directory)
+    os.makedirs(os.path.join(directory, "images"), exist_ok=True)
+    os.makedirs(os.path.join(directory, "models", "Kirby_Pikachu_Hat"), exist_ok=True)
+    capi.write_exr(os.path.join(directory, "images", "Malibu_Overlook_3k_corrected.exr"), synth.sky_environment(*env_size))
+    pos, idx, nrm, tng, uv = synth.displaced_sphere(96, 48)
+    capi.write_assbin(os.path.join(directory, "models", "Kirby_Pikachu_Hat", "pikachu_hat_corrected.assbin"),
+                      pos * 0.8 + np.array([1.2, 0.8, 0.6], np.float32), idx, nrm, tng, uv, material_name="hat", diffuse=(0.8, 0.7, 0.1))
+    t = f'setRenderer("method": "PT", ("samples": {spp},));\nsetRenderSettings("width": {width}, "height": {height}, "brightness": 4.0);\n\n'
+    t += 'setEnvironment("images/Malibu_Overlook_3k_corrected.exr");\n\n'
+    t += _COLOR_CHECKER % ("translate(0, -1, 0) * scale(0.9 / 3.0) *\n                translate(-3.0 + (i % 6), 0.0, (i / 6) - 1.0)",
+                           "(0, 1, 0)", "(0, 1, 0)", "(1.0, 0.0, -1.0)", "(0, 1, 0)", "(0.0, 0.0, -1.0)", "(0, 1, 0)")
+    t += """addChild(root, colorCheckerMesh);
+
+function sphereMaterial(name, attrs) {
+    coeffR = SpectrumTexture(Spectrum("type": "Reflectance", 0.99));
+    eta = SpectrumTexture(Spectrum("ID": "Aluminium", 0));
+    k = SpectrumTexture(Spectrum("ID": "Aluminium", 1));
+    return createSurfaceMaterial("metal", (coeffR, eta, k));
+}
+
+sphereNode = load3DModel("models/sphere.assbin", sphereMaterial);
+setTransform(sphereNode, translate(0, 0.5, 0) * scale(0.4));
+addChild(root, sphereNode);
+
+function PikachuMaterial(name, attrs) {
+    difTex = 0;
+    if (numElements(attrs["diffuse textures"])) {
+        difTexPaths = attrs["diffuse textures"];
+        image = Image2D(difTexPaths[0]);
+        difTex = SpectrumTexture(image);
+    }
+    else {
+        difCol = attrs["diffuse color"];
+        difTex = SpectrumTexture(Spectrum(difCol[0], difCol[1], difCol[2]));
+    }
+    speTex = SpectrumTexture(Spectrum(0.1, 0.1, 0.1));
+    nxTex = nyTex = FloatTexture(1000);
+    return createSurfaceMaterial("Ashikhmin", (difTex, speTex, nxTex, nyTex));
+}
+
+kirbyNode = load3DModel("models/Kirby_Pikachu_Hat/pikachu_hat_corrected.assbin", PikachuMaterial);
+setTransform(kirbyNode, translate(0, -1, 0) * scale(0.5));
+addChild(root, kirbyNode);
+
+cameraNode = createNode();
+    camera = createPerspectiveCamera("aspect": 1.0, "fovY": 0.5235987756, "radius": 0.025,
+                                     "imgDist": 1.0, "objDist": 4.75);
+    addChild(cameraNode, camera);
+setTransform(cameraNode, translate(0, 0, 5) * rotateY(3.1415926536));
+
+addChild(root, cameraNode);
+setTransform(root, rotateY(1.2));
+"""
+    path = os.path.join(directory, "IBL_Test.txt")
+    with open(path, "w") as f:
+        f.write(t)
+    return path
+
+
+def write_instanced(directory, width=1920, height=1080, spp=1024, base_segments=(224, 112), grid=10, env=False):
+    """Config C4 shape: one procedural base mesh (a bumpy ball, 2 * su * (sv - 1) triangles) instanced
+    grid x grid times through createReferenceNode on a jittered grid (LCG seed 12345) over a ground quad,
+    one D65 area light. The default base mesh has 49,728 triangles; base_segments=(318, 159) gives
+    100,488 (x 100 instances = 10 M). Two-level BVH: top-level over the instances, one shared nested BVH."""
+    os.makedirs(os.path.join(directory, "models"), exist_ok=True)
+    pos, idx, nrm, tng, uv = synth.displaced_sphere(*base_segments)
+    capi.write_assbin(os.path.join(directory, "models", "bumpy_ball.assbin"), pos, idx, nrm, tng, uv, material_name="ball", diffuse=(0.7, 0.7, 0.7))
+    t = f'setRenderer("method": "PT", ("samples": {spp},));\nsetRenderSettings("width": {width}, "height": {height});\n\n'
+    ext = 1.6 * grid
+    t += "groundNode = createNode();\nsetTransform(groundNode, translate(0, 0, 0));\n"
+    t += _quad("ground", [(-ext, 0, ext), (ext, 0, ext), (ext, 0, -ext), (-ext, 0, -ext)], (0, 1, 0), (1, 0, 0),
+               ['diffuseTex = SpectrumTexture("checker board", (Spectrum(0.7, 0.7, 0.7), Spectrum(0.3, 0.3, 0.35)));',
+                'surfMat = createSurfaceMaterial("matte", (diffuseTex,));']).replace("CBNode", "groundNode")
+    light = ['scatterMat = createSurfaceMaterial("matte", (SpectrumTexture(Spectrum(0.9, 0.9, 0.9)),));',
+             'emitterMat = createEmitterSurfaceProperty("diffuse", (SpectrumTexture(Spectrum("ID": "D65") * 6),));',
+             'surfMat = createSurfaceMaterial("emitter", (scatterMat, emitterMat));']
+    h = 9.0
+    t += _quad("lightMesh", [(-ext / 2, h, -ext / 2), (ext / 2, h, -ext / 2), (ext / 2, h, ext / 2), (-ext / 2, h, ext / 2)], (0, -1, 0), (1, 0, 0), light).replace("CBNode", "groundNode")
+    t += "addChild(root, groundNode);\n\n"
+    t += """function ballMat(name, attrs) {
+    difTex = SpectrumTexture(Spectrum(0.75, 0.55, 0.3));
+    speTex = SpectrumTexture(Spectrum(0.08, 0.08, 0.08));
+    return createSurfaceMaterial("Ashikhmin", (difTex, speTex, FloatTexture(200), FloatTexture(200)));
+}
+ballNode = load3DModel("models/bumpy_ball.assbin", ballMat);
+ballRef = createReferenceNode(ballNode);
+"""
+    state = 12345
+    def lcg():
+        nonlocal state
+        state = (state * 1103515245 + 12345) & 0x7FFFFFFF
+        return state / float(0x80000000)
+    for j in range(grid):
+        for i in range(grid):
+            x = (i - (grid - 1) / 2) * 2.6 + (lcg() - 0.5) * 0.6
+            z = (j - (grid - 1) / 2) * 2.6 + (lcg() - 0.5) * 0.6
+            sc = 0.8 + 0.4 * lcg()
+            rot = 6.2831853 * lcg()
+            t += (f"inst = createNode();\naddChild(inst, ballRef);\n"
+                  f"setTransform(inst, translate({x:.5f}, {1.08 * sc:.5f}, {z:.5f}) * rotateY({rot:.5f}) * scale({sc:.5f}));\naddChild(root, inst);\n")
+    dist = 1.9 * grid
+    t += f"""
+cameraNode = createNode();
+camera = createPerspectiveCamera("aspect": {width / height:.6f}, "fovY": 0.7, "radius": 0.02, "imgDist": 1.0, "objDist": {dist:.3f});
+addChild(cameraNode, camera);
+setTransform(cameraNode, translate(0.0, {0.55 * dist:.3f}, {0.85 * dist:.3f}) * rotateY(3.1415926536) * rotateX(0.55));
+addChild(root, cameraNode);
+"""
+    path = os.path.join(directory, "Instanced_Balls.txt")
+    with open(path, "w") as f:
+        f.write(t)
+    return path
+
+
+def _small_instanced(directory, width=128, height=128, spp=64):
+    return write_instanced(directory, width, height, spp, base_segments=(48, 24), grid=4)
+
+
 SCENES = {
     "diffuse": write_cornell_diffuse,
     "spheres": write_cornell_spheres,
+    "materials": write_cornell_materials,
+    "ibl": lambda d, width=1024, height=1024, spp=256: write_ibl_test(d, width, height, spp, env_size=(512, 256)),
+    "ibl_full": write_ibl_test,
+    "instanced": _small_instanced,
+    "instanced_full": write_instanced,
 }

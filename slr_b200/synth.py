@@ -213,3 +213,114 @@ def read_trees(path):
             costs = np.frombuffer(f.read(8), np.float32)
             out.append({"nodes": nodes, "refs": refs, "sbvh_cost": float(costs[0]), "qbvh_cost": float(costs[1])})
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# .assbin writer (Assimp binary dump, the subset slr_b200/host/assets/assbin.h documents): several
+# meshes and materials in one file, one child node per mesh under the root.
+# --------------------------------------------------------------------------------------------------
+def _chunk(magic, payload):
+    return struct.pack("<II", magic, len(payload)) + payload
+
+
+def _aistring(s):
+    b = s.encode()
+    return struct.pack("<I", len(b)) + b
+
+
+def write_assbin_scene(path, meshes, materials):
+    """meshes: list of dicts {name, positions[n,3], indices[m,3], normals, tangents, uvs[n,2] (optional), material}
+    materials: list of dicts {name, diffuse (r,g,b) optional}."""
+    header = bytearray(512)
+    sig = ("ASSIMP.binary-dump.%-25s" % "slr_b200 synthetic asset").encode()[:44]
+    header[:len(sig)] = sig
+    header[44:60] = struct.pack("<IIII", 3, 1, 0, 0)
+    for i in range(44 + 20 + 256 + 128, 512):
+        header[i] = 0xCD
+    ident = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]
+    children = b""
+    for i, m in enumerate(meshes):
+        children += _chunk(0x123C, _aistring(m.get("name", f"mesh{i}")) + struct.pack("<16f", *ident) + struct.pack("<II", 0, 1) + struct.pack("<I", i))
+    root = _chunk(0x123C, _aistring("root") + struct.pack("<16f", *ident) + struct.pack("<II", len(meshes), 0) + children)
+    body = struct.pack("<7I", 0, len(meshes), len(materials), 0, 0, 0, 0) + root
+    for m in meshes:
+        pos = np.ascontiguousarray(m["positions"], np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(m["indices"], np.uint32).reshape(-1, 3)
+        nv = pos.shape[0]
+        comps = 0x1
+        payload = b""
+        arrays = [pos.tobytes()]
+        nrm = m.get("normals")
+        tng = m.get("tangents")
+        uv = m.get("uvs")
+        if nrm is not None:
+            comps |= 0x2
+            nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1, 3)
+            arrays.append(nrm.tobytes())
+        if tng is not None and nrm is not None:
+            comps |= 0x4
+            tng = np.ascontiguousarray(tng, np.float32).reshape(-1, 3)
+            arrays.append(tng.tobytes())
+            arrays.append(np.cross(nrm, tng).astype(np.float32).tobytes())
+        if uv is not None:
+            comps |= 0x100
+            uv3 = np.zeros((nv, 3), np.float32)
+            uv3[:, :2] = np.asarray(uv, np.float32).reshape(-1, 2)
+            arrays.append(struct.pack("<I", 2) + uv3.tobytes())
+        payload = struct.pack("<6I", 0x4, nv, idx.shape[0], 0, int(m.get("material", 0)), comps) + b"".join(arrays)
+        if nv < 65536:
+            faces = np.empty((idx.shape[0], 4), np.uint16)
+            faces[:, 0] = 3
+            faces[:, 1:] = idx
+        else:
+            faces = np.empty(idx.shape[0], np.dtype([("n", "<u2"), ("i", "<u4", 3)]))
+            faces["n"] = 3
+            faces["i"] = idx
+        payload += faces.tobytes()
+        body += _chunk(0x1237, payload)
+    for mat in materials:
+        props = [_chunk(0x123E, _aistring("?mat.name") + struct.pack("<IIII", 0, 0, 4 + len(mat["name"]) + 1, 3)
+                        + struct.pack("<I", len(mat["name"])) + mat["name"].encode() + b"\0")]
+        if mat.get("diffuse") is not None:
+            props.append(_chunk(0x123E, _aistring("$clr.diffuse") + struct.pack("<IIII", 0, 0, 12, 1) + struct.pack("<3f", *mat["diffuse"])))
+        body += _chunk(0x123D, struct.pack("<I", len(props)) + b"".join(props))
+    with open(path, "wb") as f:
+        f.write(bytes(header) + _chunk(0x1239, body))
+
+
+def quad_mesh(corners, normal, tangent):
+    """Two triangles (0,1,2), (0,2,3) over four corners with a constant frame and unit uvs."""
+    pos = np.asarray(corners, np.float32)
+    return {"positions": pos, "indices": np.array([[0, 1, 2], [0, 2, 3]], np.uint32),
+            "normals": np.tile(np.asarray(normal, np.float32), (4, 1)), "tangents": np.tile(np.asarray(tangent, np.float32), (4, 1)),
+            "uvs": np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32)}
+
+
+def displaced_sphere(segments_u=128, segments_v=64, amplitude=0.08, freq=6.0):
+    """UV sphere with a smooth radial displacement (bumpy ball): the instanced base mesh of config C4."""
+    pos, idx, nrm, tng, uv = uv_sphere(segments_u, segments_v)
+    r = 1.0 + amplitude * np.sin(freq * pos[:, 0]) * np.cos(freq * pos[:, 1] + 0.5) * np.sin(freq * pos[:, 2] + 1.0)
+    return (pos * r[:, None]).astype(np.float32), idx, nrm, tng, uv
+
+
+def sky_environment(width=2048, height=1024):
+    """Synthetic HDR lat-long environment (RGBA float32): analytic sky gradient, a small bright sun and two
+    coloured lobes -- a fixed formula, no random numbers."""
+    v, u = np.meshgrid((np.arange(height) + 0.5) / height, (np.arange(width) + 0.5) / width, indexing="ij")
+    theta, phi = v * np.pi, u * 2 * np.pi
+    d = np.stack([-np.sin(phi) * np.sin(theta), np.cos(theta), np.cos(phi) * np.sin(theta)], -1)
+    up = np.clip(d[..., 1], 0, 1)
+    sky = np.stack([0.25 + 0.35 * (1 - up), 0.35 + 0.35 * (1 - up), 0.55 + 0.35 * up], -1)
+    ground = np.array([0.18, 0.15, 0.12])
+    img = np.where(d[..., 1:2] > 0, sky, ground * (0.4 + 0.6 * np.clip(-d[..., 1:2], 0, 1)))
+
+    def lobe(direction, sharp, rgb):
+        dd = np.asarray(direction, np.float64)
+        dd = dd / np.linalg.norm(dd)
+        return np.exp(sharp * (d @ dd - 1.0))[..., None] * np.asarray(rgb)
+    img = img + lobe((0.5, 0.6, 0.4), 600.0, (900.0, 800.0, 600.0))     # sun, ~5 degrees
+    img = img + lobe((-0.7, 0.3, -0.5), 20.0, (1.5, 0.4, 0.2))
+    img = img + lobe((0.1, 0.2, -0.9), 30.0, (0.2, 0.6, 1.8))
+    rgba = np.ones((height, width, 4), np.float32)
+    rgba[..., :3] = img
+    return rgba

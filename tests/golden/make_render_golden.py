@@ -1,0 +1,48 @@
+"""Generates tests/golden/render_<scene>.npz from the REFERENCE renderer (oracle/_ref/ref_render, built by
+oracle/Makefile from /root/reference): block means of the converged image and their standard error.
+
+    python tests/golden/make_render_golden.py [scene ...]
+
+For every scene of slr_b200.scenes.SCENES used by tests/test_gpu_render.py the reference's
+PathTracingRenderer renders SEEDS independent images at SIZE x SIZE, SPP_EACH spp; the golden is the
+per-block (BLOCK x BLOCK pixels, linear sRGB) mean over the seeds, `block_sigma` the standard error of
+that mean estimated from the spread between seeds, `ref_spp` = SEEDS * SPP_EACH. Runs only where the
+reference is available (this container); the .npz files are committed and travel to the GPU box.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import render_util as ru  # noqa: E402
+from slr_b200 import capi  # noqa: E402
+
+SIZE, BLOCK, SEEDS, SPP_EACH, GPU_SPP = 64, 8, 4, 512, 2048
+SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced"]
+
+
+def main():
+    names = sys.argv[1:] or SCENES
+    work = tempfile.mkdtemp(prefix="slr_golden_")
+    for name in names:
+        path = ru.scene_file(name, work, SIZE, SIZE, SPP_EACH)
+        means = []
+        for k in range(SEEDS):
+            accum, timing = ru.run_ref_render(path, SPP_EACH, SIZE, SIZE, seed=1000 + 7919 * k)
+            means.append(ru.block_means(capi.accum_to_rgb(accum, 1.0 / SPP_EACH), BLOCK))
+        means = np.stack(means)
+        out = os.path.join(ru.GOLDEN, f"render_{name}.npz")
+        np.savez_compressed(out, block_mean=means.mean(0).astype(np.float32),
+                            block_sigma=(means.std(0, ddof=1) / np.sqrt(SEEDS)).astype(np.float32),
+                            size=SIZE, block=BLOCK, ref_spp=SEEDS * SPP_EACH, gpu_spp=GPU_SPP,
+                            reference_threads=timing.get("threads", 0))
+        rel = (means.std(0, ddof=1) / np.sqrt(SEEDS) / means.mean(0)).mean()
+        print(f"{name}: wrote {out}; mean relative standard error of a block mean {rel:.4f}")
+
+
+if __name__ == "__main__":
+    main()

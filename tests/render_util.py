@@ -27,7 +27,7 @@ def run_ref_render(scene_path, spp, width, height, seed=0, qbvh=0, timeout=3600)
     timing = {}
     for line in p.stderr.splitlines():
         if line.startswith("{"):
-            timing = json.loads(line)
+            timing = json.loads(line.replace(': inf', ': Infinity').replace(': nan', ': NaN'))
     with open(out, "rb") as f:
         w, h, c = np.frombuffer(f.read(12), np.uint32)
         accum = np.frombuffer(f.read(), np.float32).reshape(h, w, c).copy()
@@ -42,11 +42,18 @@ def scene_file(name, directory, width, height, spp):
     return scenes.SCENES[name](directory, width=width, height=height, spp=spp)
 
 
-def rel_rmse(img, ref):
-    """sqrt(mean((img - ref)^2)) / mean(ref) over all pixels and channels (linear sRGB floats)."""
+def rel_rmse(img, ref, trim=0.0):
+    """sqrt(mean((img - ref)^2)) / mean(ref) over all pixels and channels (linear sRGB floats). With
+    trim > 0 the largest `trim` fraction of the squared errors is left out: a few pixels that see a
+    tiny very bright feature (a mirrored sun, caustic fireflies) have a heavy-tailed error that would
+    otherwise decide the whole statistic -- both for the image under test and for the noise floor."""
     img = np.asarray(img, np.float64)
     ref = np.asarray(ref, np.float64)
-    return float(np.sqrt(np.mean((img - ref) ** 2)) / np.mean(ref))
+    err = ((img - ref) ** 2).ravel()
+    if trim > 0.0:
+        keep = err.size - int(np.ceil(trim * err.size))
+        err = np.partition(err, keep - 1)[:keep]
+    return float(np.sqrt(np.mean(err)) / np.mean(ref))
 
 
 def block_means(img, block):

@@ -1,0 +1,130 @@
+"""GPU image parity: the wavefront path tracer behind slrgpu_render / GPUPathTracingRenderer against the
+reference's PathTracingRenderer (libSLR/Renderers/PathTracingRenderer.cpp:27-261).
+
+The reference's image depends on thread scheduling (per-thread xorshift streams), so only statistical
+parity is defined (hard part 5). Tolerances, all on linear sRGB before tone mapping:
+  * rel_rmse(gpu, ref1) <= 1.25 * rel_rmse(ref2, ref1)   -- ref1/ref2 = the reference with two seeds: the
+    Monte-Carlo noise floor at that spp (both images are independent and equally noisy); the largest
+    0.5 % of the squared errors are trimmed from both sides of the comparison (render_util.rel_rmse);
+  * image means per channel within 1 % (bias check; the noise of the mean is ~0.1 % at these sizes);
+  * against the committed golden block means (tests/golden/render_*.npz, made by make_render_golden.py
+    from the reference at high spp): every 8x8 block mean within 6 sigma of the golden's own two-seed
+    spread plus 2 %.
+Size-independent properties at larger sizes: sample-range additivity (the multi-GPU partition),
+independence of the in-flight pool size, determinism.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import render_util as ru
+from slr_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert capi.gpu.slrgpu_device_count() > 0, "these tests need a CUDA device"
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory):
+    return str(tmp_path_factory.mktemp("scenes"))
+
+
+def _gpu_rgb(path, size, spp, **kw):
+    hs = capi.read_scene(path, **kw)
+    accum, st = capi.host_render(hs, size, size, spp)
+    assert np.isfinite(accum).all()
+    assert st["paths"] == size * size * spp
+    return capi.accum_to_rgb(accum, 1.0 / spp), st
+
+
+@pytest.mark.parametrize("name,size,spp", [("diffuse", 96, 256), ("spheres", 128, 256), ("materials", 128, 256), ("ibl", 128, 256),
+                                           ("instanced", 128, 128)])
+def test_image_matches_reference_within_noise_floor(name, size, spp, workdir):
+    if not ru.have_ref_render():
+        pytest.skip("oracle/_ref/ref_render not built")
+    path = ru.scene_file(name, workdir, size, size, spp)
+    gpu, _ = _gpu_rgb(path, size, spp)
+    ref1 = capi.accum_to_rgb(ru.run_ref_render(path, spp, size, size, seed=1509761209)[0], 1.0 / spp)
+    ref2 = capi.accum_to_rgb(ru.run_ref_render(path, spp, size, size, seed=20240229)[0], 1.0 / spp)
+    floor = ru.rel_rmse(ref2, ref1, trim=0.005)
+    got = ru.rel_rmse(gpu, ref1, trim=0.005)
+    assert got <= 1.25 * floor, f"relRMSE {got:.4f} vs noise floor {floor:.4f}"
+    ratio = gpu.reshape(-1, 3).mean(0) / ref1.reshape(-1, 3).mean(0)
+    assert np.all(np.abs(ratio - 1.0) < 0.01), f"image mean ratio {ratio}"
+    bfloor = ru.block_rel_rmse(ref2, ref1, 16)
+    bgot = ru.block_rel_rmse(gpu, ref1, 16)
+    assert bgot <= 1.5 * bfloor + 0.002, f"16x16-block relRMSE {bgot:.4f} vs floor {bfloor:.4f}"
+
+
+@pytest.mark.parametrize("name", ["diffuse", "spheres", "materials", "ibl", "instanced"])
+def test_image_matches_golden_block_means(name, workdir):
+    f = os.path.join(ru.GOLDEN, f"render_{name}.npz")
+    g = np.load(f)
+    size, spp, block = int(g["size"]), int(g["gpu_spp"]), int(g["block"])
+    path = ru.scene_file(name, workdir, size, size, spp)
+    gpu, _ = _gpu_rgb(path, size, spp)
+    got = ru.block_means(gpu, block)
+    want, sigma = g["block_mean"], g["block_sigma"]
+    # the GPU image has gpu_spp samples, the golden ref_spp: scale the golden's per-block sigma
+    sig = sigma * np.sqrt(float(g["ref_spp"]) / spp + 1.0)
+    err = np.abs(got - want)
+    tol = 6.0 * sig + 0.02 * want + 1e-6
+    bad = err > tol
+    assert bad.mean() <= 0.01, f"{bad.sum()} of {bad.size} block means outside 6 sigma + 2 %: worst {np.max(err / tol):.2f}x"
+    ratio = got.mean((0, 1)) / want.mean((0, 1))
+    assert np.all(np.abs(ratio - 1.0) < 0.01), f"image mean ratio {ratio}"
+
+
+def test_sample_ranges_add_up(workdir):
+    """Rendering [0, 32) and [32, 64) separately and summing equals rendering [0, 64): the counter-based
+    RNG is keyed by (pixel, global sample index), which is what lets N GPUs split a frame by samples."""
+    path = ru.scene_file("spheres", workdir, 192, 192, 64)
+    hs = capi.read_scene(path)
+    gs = capi.GpuScene(hs)
+    whole, st = capi.gpu_render(gs, 192, 192, 0, 64)
+    a, _ = capi.gpu_render(gs, 192, 192, 0, 32)
+    b, _ = capi.gpu_render(gs, 192, 192, 32, 64)
+    # identical sample sets; only the fp32 atomic summation order differs
+    np.testing.assert_allclose(a + b, whole, rtol=2e-4, atol=1e-5 * float(whole.mean()))
+    assert not np.array_equal(a, b)
+
+
+def test_pool_size_and_rerun_do_not_change_the_image(workdir):
+    path = ru.scene_file("spheres", workdir, 160, 160, 16)
+    hs = capi.read_scene(path)
+    gs = capi.GpuScene(hs)
+    big, st_big = capi.gpu_render(gs, 160, 160, 0, 16)
+    small, st_small = capi.gpu_render(gs, 160, 160, 0, 16, pool_size=32768)
+    again, _ = capi.gpu_render(gs, 160, 160, 0, 16)
+    assert st_big["rays"] == st_small["rays"] and st_big["paths"] == st_small["paths"]
+    tol = dict(rtol=2e-4, atol=1e-5 * float(big.mean()))
+    np.testing.assert_allclose(small, big, **tol)
+    np.testing.assert_allclose(again, big, **tol)
+    other, _ = capi.gpu_render(gs, 160, 160, 0, 16, seed=4242)
+    assert ru.rel_rmse(other, big) > 0.05
+
+
+def test_rgb_mode_is_close_to_spectral(workdir):
+    """RGB mode (references.h:45-60 without Use_Spectral_Representation) on the diffuse box: same light
+    transport with 3 channels; colours differ slightly from the spectral render (no metamerism), means agree."""
+    path = ru.scene_file("diffuse", workdir, 96, 96, 256)
+    spec, _ = _gpu_rgb(path, 96, 256)
+    rgb, st = _gpu_rgb(path, 96, 256, rgb_mode=True)
+    assert st["channels"] == 3
+    ratio = rgb.reshape(-1, 3).mean(0) / spec.reshape(-1, 3).mean(0)
+    assert np.all(np.abs(ratio - 1.0) < 0.15), ratio
+
+
+def test_render_argument_errors(workdir):
+    path = ru.scene_file("diffuse", workdir, 32, 32, 1)
+    hs = capi.read_scene(path)
+    gs = capi.GpuScene(hs)
+    with pytest.raises(capi.SlrError):
+        capi.gpu_render(gs, 0, 32, 0, 1)
+    with pytest.raises(capi.SlrError):
+        capi.gpu_render(gs, 32, 32, 4, 4)

@@ -26,7 +26,7 @@ import render_util as ru  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("scenes", nargs="*", default=["diffuse", "spheres"])
+    ap.add_argument("scenes", nargs="*", default=["diffuse", "spheres", "materials", "ibl", "instanced"])
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--spp", type=int, default=64)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "render_check"))
