@@ -235,9 +235,12 @@ __device__ __noinline__ Spec<NC> mfTransmissionEval(const Lobe<NC>& L, const Bsd
     return ret;
 }
 
-template <int NC>
-__device__ __noinline__ Spec<NC> baseSample(const Lobe<NC>& L, const BsdfQuery& q, float uComp, float u0, float u1, BsdfSampleResult* res) {
-    switch (L.type) {
+// The four base functions are templates over LT: LT >= 0 fixes the lobe type at compile time (the
+// per-material-class shade kernels; everything inlines and the other cases are pruned), LT = -1
+// dispatches on L.type at run time (the generic kernel; kept out of line).
+template <int NC, int LT>
+__device__ __forceinline__ Spec<NC> baseSampleT(const Lobe<NC>& L, const BsdfQuery& q, float uComp, float u0, float u1, BsdfSampleResult* res) {
+    switch (LT >= 0 ? (uint32_t)LT : L.type) {
     case LOBE_LAMBERT: {
         res->dir = cosineSampleHemisphere(u0, u1);
         res->pdf = res->dir.z / kPi;
@@ -420,8 +423,13 @@ __device__ __noinline__ Spec<NC> baseSample(const Lobe<NC>& L, const BsdfQuery& 
 }
 
 template <int NC>
-__device__ __noinline__ Spec<NC> baseEvaluate(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir) {
-    switch (L.type) {
+__device__ __noinline__ Spec<NC> baseSample(const Lobe<NC>& L, const BsdfQuery& q, float uComp, float u0, float u1, BsdfSampleResult* res) {
+    return baseSampleT<NC, -1>(L, q, uComp, u0, u1, res);
+}
+
+template <int NC, int LT>
+__device__ __forceinline__ Spec<NC> baseEvaluateT(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir) {
+    switch (LT >= 0 ? (uint32_t)LT : L.type) {
     case LOBE_LAMBERT:
         if (q.dir.z * dir.z <= 0.0f) return specZero<NC>();
         return L.s0 * (1.0f / kPi);
@@ -488,8 +496,11 @@ __device__ __noinline__ Spec<NC> baseEvaluate(const Lobe<NC>& L, const BsdfQuery
 }
 
 template <int NC>
-__device__ __noinline__ float basePdf(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir) {
-    switch (L.type) {
+__device__ __noinline__ Spec<NC> baseEvaluate(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir) { return baseEvaluateT<NC, -1>(L, q, dir); }
+
+template <int NC, int LT>
+__device__ __forceinline__ float basePdfT(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir) {
+    switch (LT >= 0 ? (uint32_t)LT : L.type) {
     case LOBE_LAMBERT:
     case LOBE_OREN_NAYAR:
         if (q.dir.z * dir.z <= 0.0f) return 0.0f;
@@ -557,6 +568,9 @@ __device__ __noinline__ float basePdf(const Lobe<NC>& L, const BsdfQuery& q, con
     }
     return 0.0f;
 }
+
+template <int NC>
+__device__ __noinline__ float basePdf(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir) { return basePdfT<NC, -1>(L, q, dir); }
 
 template <int NC>
 __device__ __noinline__ float baseWeight(const Lobe<NC>& L, const BsdfQuery& q) {
@@ -722,6 +736,30 @@ __device__ inline Spec<NC> bsdfSample(const Bsdf<NC, ML>& b, const BsdfQuery& q,
     }
     const float snCorrection = fabsf(res->dir.z / dot(res->dir, q.gn));
     return value * snCorrection;
+}
+
+// ---- a hit whose BSDF is ONE base lobe of compile-time type LT (no InverseBSDF, no MultiBSDF) ----
+template <int NC, int LT>
+__device__ __forceinline__ Spec<NC> lobeSample(const Lobe<NC>& L, const BsdfQuery& q, float uComp, float u0, float u1, BsdfSampleResult* res) {
+    res->pdf = 0.0f; res->type = 0; res->dir = V3(0, 0, 1);
+    if (!dtMatches(L.baseDirType, q.flags)) return specZero<NC>();
+    const Spec<NC> value = baseSampleT<NC, LT>(L, q, uComp, u0, u1, res);
+    const float snCorrection = fabsf(res->dir.z / dot(res->dir, q.gn));
+    return value * snCorrection;
+}
+template <int NC, int LT>
+__device__ __forceinline__ Spec<NC> lobeEvaluate(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir) {
+    BsdfQuery mq = q;
+    mq.flags &= sideTest(q.gn, q.dir, dir);
+    if (!dtMatches(L.baseDirType, mq.flags)) return specZero<NC>();
+    const Spec<NC> fs = baseEvaluateT<NC, LT>(L, mq, dir);
+    const float snCorrection = fabsf(dir.z / dot(dir, q.gn));
+    return fs * snCorrection;
+}
+template <int NC, int LT>
+__device__ __forceinline__ float lobePdf(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir) {
+    if (!dtMatches(L.baseDirType, q.flags)) return 0.0f;
+    return basePdfT<NC, LT>(L, q, dir);
 }
 
 template <int NC, int ML>

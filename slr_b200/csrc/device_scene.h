@@ -56,7 +56,9 @@ struct SlrGpuScene {
     bool hasInstances = false;
     bool hasShading = false;
     uint32_t channels = 16;
-    uint32_t maxLobes = 1;            // 1 unless a material is a sum / mix (MultiBSDF): picks the shade kernel variant
+    uint32_t classMask = 0;           // material classes (wavefront.cuh: ShadeClass) the scene's materials can produce
+    void* workspace = nullptr;        // render queues, cached between render calls (render.cu)
+    void (*destroyWorkspace)(void*) = nullptr;
 };
 
 namespace slrgpu {

@@ -15,12 +15,13 @@
 namespace slrgpu {
 
 // MicrofacetReflection / MicrofacetScattering ignore `scale` (MicrofacetSurfaceMaterial.cpp:14-29): kept.
-template <int NC>
-__device__ __noinline__ void fillLobe(const DeviceScene& s, const SlrGpuMaterial& m, const SurfPt& sp, float wlOffset, bool lambdaSelected,
-                                float scale, uint32_t inverse, Lobe<NC>* L) {
+// MK >= 0 fixes the material kind at compile time (per-class material kernels), MK = -1 dispatches at run time.
+template <int NC, int MK>
+__device__ __forceinline__ void fillLobeT(const DeviceScene& s, const SlrGpuMaterial& m, const SurfPt& sp, float wlOffset, bool lambdaSelected,
+                                          float scale, uint32_t inverse, Lobe<NC>* L) {
     L->inverse = inverse;
     L->f0 = 0.0f; L->f1 = 0.0f;
-    switch (m.kind) {
+    switch (MK >= 0 ? (uint32_t)MK : m.kind) {
     case SLRGPU_MAT_DIFFUSE:
         L->s0 = scale * evalSpectrumTexture<NC>(s, m.tex[0], sp, wlOffset);
         if (m.tex[1] != SLRGPU_INVALID_ID) {
@@ -84,6 +85,12 @@ __device__ __noinline__ void fillLobe(const DeviceScene& s, const SlrGpuMaterial
     }
 }
 
+template <int NC>
+__device__ __noinline__ void fillLobe(const DeviceScene& s, const SlrGpuMaterial& m, const SurfPt& sp, float wlOffset, bool lambdaSelected,
+                                float scale, uint32_t inverse, Lobe<NC>* L) {
+    fillLobeT<NC, -1>(s, m, sp, wlOffset, lambdaSelected, scale, inverse, L);
+}
+
 // SVGGX evaluates alpha_g with a surface point that only carries the texture coordinate
 // (surface_material.cpp:27-29 -> FloatTexture::evaluate(TexCoord2D), textures.h:84-88): a world-position
 // mapped alpha texture therefore sees an indeterminate position in the reference; here it sees p.
@@ -134,6 +141,38 @@ __device__ __noinline__ void buildBsdf(const DeviceScene& s, uint32_t materialId
             break;
         }
     }
+}
+
+// Material class of a hit (wavefront.cuh: ShadeClass values, numbered like LobeType) and the leaf
+// material the class kernel builds its lobe from. Emitter wrappers are peeled (their BSDF is the
+// scattering material's, surface_material.h); sum / mix / inverse trees go to the generic kernel with
+// the ORIGINAL material id. Returns 0xFF when the hit has no BSDF (an emitter without a scattering part).
+__device__ __forceinline__ uint32_t classifyMaterial(const DeviceScene& s, uint32_t materialId, uint32_t* leaf) {
+    uint32_t id = materialId;
+    SlrGpuMaterial m = s.materials[id];
+    for (int depth = 0; depth < 4 && m.kind == SLRGPU_MAT_EMITTER; ++depth) {
+        if (m.sub[0] == SLRGPU_INVALID_ID) return 0xFFu;
+        id = m.sub[0];
+        m = s.materials[id];
+    }
+    *leaf = id;
+    switch (m.kind) {
+    case SLRGPU_MAT_DIFFUSE: return m.tex[1] == SLRGPU_INVALID_ID ? 0u : 1u;
+    case SLRGPU_MAT_SPECULAR_REFLECTION: return 2u;
+    case SLRGPU_MAT_SPECULAR_SCATTERING: return 3u;
+    case SLRGPU_MAT_WARD_DUR: return 4u;
+    case SLRGPU_MAT_ASHIKHMIN_SHIRLEY: return 5u;
+    case SLRGPU_MAT_MICROFACET_REFLECTION: return 6u;
+    case SLRGPU_MAT_MICROFACET_SCATTERING: return 7u;
+    default: *leaf = materialId; return 8u;
+    }
+}
+// material kind behind a single-lobe class
+__host__ __device__ constexpr int classMaterialKind(int cls) {
+    return cls == 0 || cls == 1 ? (int)SLRGPU_MAT_DIFFUSE : cls == 2 ? (int)SLRGPU_MAT_SPECULAR_REFLECTION
+         : cls == 3 ? (int)SLRGPU_MAT_SPECULAR_SCATTERING : cls == 4 ? (int)SLRGPU_MAT_WARD_DUR
+         : cls == 5 ? (int)SLRGPU_MAT_ASHIKHMIN_SHIRLEY : cls == 6 ? (int)SLRGPU_MAT_MICROFACET_REFLECTION
+         : cls == 7 ? (int)SLRGPU_MAT_MICROFACET_SCATTERING : -1;
 }
 
 __device__ __forceinline__ bool materialIsEmitting(const DeviceScene& s, uint32_t materialId) {

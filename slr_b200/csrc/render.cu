@@ -11,15 +11,18 @@
 #include "rng.cuh"
 #include "shade.cuh"
 #include "wavefront.cuh"
+#include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <vector>
 
 namespace slrgpu {
 
-constexpr int kShadeBlock = 128;
-constexpr int kRaygenBlock = 256;
+constexpr int kSurfaceBlock = 128;
+constexpr int kMaterialBlock = 128;
+constexpr int kRaygenBlock = 128;
 
 // position of `alive` lanes in an output queue: one atomic per warp
 __device__ __forceinline__ uint32_t warpAppend(bool alive, uint32_t* counter) {
@@ -51,252 +54,366 @@ template <int NC> __device__ __forceinline__ Spec<NC> loadAlpha(const PathQueue&
 }
 
 // ---------------------------------------------------------------------------------------------
-// ray generation: camera samples [first, first + count) of this render call, appended to `out`
+// ray generation: fills the free tail of the current queue with fresh camera samples
 // ---------------------------------------------------------------------------------------------
 template <int NC>
 __global__ void __launch_bounds__(kRaygenBlock)
-raygenKernel(const DeviceScene s, const RenderConstants rc, unsigned long long first, uint32_t count, PathQueue out, uint32_t outBase) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= count) return;
-    const unsigned long long g = first + j;
-    const uint32_t pass = (uint32_t)(g / rc.numPixels);
-    const uint32_t r = (uint32_t)(g % rc.numPixels);
-    // pixel order: bands of 8 rows, column-major inside a band, so a warp covers a 4x8 pixel block
-    const uint32_t band = r / (8u * rc.width);
-    const uint32_t local = r - band * 8u * rc.width;
-    const uint32_t rows = min(8u, rc.height - band * 8u);
-    const uint32_t x = local / rows, y = band * 8u + local % rows;
-    const uint32_t pixel = y * rc.width + x;
-    const uint32_t sample = rc.sppBegin + pass;
+raygenKernel(const DeviceScene s, const RenderConstants rc, PathQueue out, const WavefrontCounters* __restrict__ counters) {
+    const uint32_t outBase = counters->numPaths;
+    const unsigned long long first = counters->generated, remaining = counters->total - first;
+    const uint32_t room = rc.capacity - outBase;
+    const uint32_t count = (uint32_t)(remaining < (unsigned long long)room ? remaining : (unsigned long long)room);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
+        const unsigned long long g = first + j;
+        const uint32_t pass = (uint32_t)(g / rc.numPixels);
+        const uint32_t r = (uint32_t)(g % rc.numPixels);
+        // pixel order: bands of 8 rows, column-major inside a band, so a warp covers a 4x8 pixel block
+        const uint32_t band = r / (8u * rc.width);
+        const uint32_t local = r - band * 8u * rc.width;
+        const uint32_t rows = min(8u, rc.height - band * 8u);
+        const uint32_t x = local / rows, y = band * 8u + local % rows;
+        const uint32_t pixel = y * rc.width + x;
+        const uint32_t sample = rc.sppBegin + pass;
 
-    const Rand4 r0 = pathRandom(rc.seed, pixel, sample, 0);    // time, pixel x, pixel y, wavelength offset
-    const Rand4 r1 = pathRandom(rc.seed, pixel, sample, 1);    // wavelength selection, lens u0, lens u1
-    const float px = x + r0.y, py = y + r0.z;
-    const float wlOffset = r0.w;
-    const uint32_t hero = min((uint32_t)(NC * r1.x), (uint32_t)(NC - 1));
+        const Rand4 r0 = pathRandom(rc.seed, pixel, sample, 0);    // time, pixel x, pixel y, wavelength offset
+        const Rand4 r1 = pathRandom(rc.seed, pixel, sample, 1);    // wavelength selection, lens u0, lens u1
+        const float px = x + r0.y, py = y + r0.z;
+        const float wlOffset = r0.w;
+        const uint32_t hero = min((uint32_t)(NC * r1.x), (uint32_t)(NC - 1));
 
-    // PerspectiveCamera::sample
-    float lx, ly;
-    concentricSampleDisk(r1.y, r1.z, &lx, &ly);
-    const SlrGpuCamera& cam = s.camera;
-    const V3 orgLocal(cam.lens_radius * lx, cam.lens_radius * ly, 0.0f);
-    const V3 org = xfmPoint(cam.mat, orgLocal);
-    const V3 lensN = xfmNormal(cam.mat_inv, V3(0, 0, 1));
-    Frame f;
-    f.z = lensN;
-    f.x = xfmVector(cam.mat, V3(1, 0, 0));
-    f.y = cross(f.z, f.x);
-    // PerspectiveIDF::sample with (p.x / W, p.y / H)
-    const V3 pFocus(rc.opWidth * (0.5f - px / rc.width), rc.opHeight * (0.5f - py / rc.height), cam.obj_plane_dist);
-    const V3 dirLocal = normalize(pFocus - orgLocal);
-    const float dirPDF = cam.img_plane_dist * cam.img_plane_dist / ((dirLocal.z * dirLocal.z * dirLocal.z) * rc.imgPlaneArea);
-    const V3 dir = f.fromLocal(dirLocal);
-    const float weight = absDot(dir, lensN) / (rc.lensAreaPDF * dirPDF * rc.selectWLPDF);
+        // PerspectiveCamera::sample
+        float lx, ly;
+        concentricSampleDisk(r1.y, r1.z, &lx, &ly);
+        const SlrGpuCamera& cam = s.camera;
+        const V3 orgLocal(cam.lens_radius * lx, cam.lens_radius * ly, 0.0f);
+        const V3 org = xfmPoint(cam.mat, orgLocal);
+        const V3 lensN = xfmNormal(cam.mat_inv, V3(0, 0, 1));
+        Frame f;
+        f.z = lensN;
+        f.x = xfmVector(cam.mat, V3(1, 0, 0));
+        f.y = cross(f.z, f.x);
+        // PerspectiveIDF::sample with (p.x / W, p.y / H)
+        const V3 pFocus(rc.opWidth * (0.5f - px / rc.width), rc.opHeight * (0.5f - py / rc.height), cam.obj_plane_dist);
+        const V3 dirLocal = normalize(pFocus - orgLocal);
+        const float dirPDF = cam.img_plane_dist * cam.img_plane_dist / ((dirLocal.z * dirLocal.z * dirLocal.z) * rc.imgPlaneArea);
+        const V3 dir = f.fromLocal(dirLocal);
+        const float weight = absDot(dir, lensN) / (rc.lensAreaPDF * dirPDF * rc.selectWLPDF);
 
-    // ImageSensor::add bins by the float pixel position
-    const uint32_t ipx = min((uint32_t)px, rc.width - 1), ipy = min((uint32_t)py, rc.height - 1);
-    uint32_t flags = kFlagCameraRay;
-    if (NC == 16 && strataInPlace(wlOffset)) flags |= kFlagStrataInPlace;
+        // ImageSensor::add bins by the float pixel position
+        const uint32_t ipx = min((uint32_t)px, rc.width - 1), ipy = min((uint32_t)py, rc.height - 1);
+        uint32_t flags = kFlagCameraRay;
+        if (NC == 16 && strataInPlace(wlOffset)) flags |= kFlagStrataInPlace;
 
-    const uint32_t pos = outBase + j;
-    out.org[pos] = make_float4(org.x, org.y, org.z, 0.0f);
-    out.dir[pos] = make_float4(dir.x, dir.y, dir.z, 0.0f);
-    out.meta[pos] = make_uint4(ipy * rc.width + ipx, sample, hero | (flags << 8), __float_as_uint(wlOffset));
-    out.weight[pos] = weight * rc.recBinWidth;
-    storeAlpha<NC>(out, pos, specConst<NC>(1.0f));
+        const uint32_t pos = outBase + j;
+        out.org[pos] = make_float4(org.x, org.y, org.z, 0.0f);
+        out.dir[pos] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+        out.meta[pos] = make_uint4(ipy * rc.width + ipx, sample, hero | (flags << 8), __float_as_uint(wlOffset));
+        out.weight[pos] = weight * rc.recBinWidth;
+        storeAlpha<NC>(out, pos, specConst<NC>(1.0f));
+    }
+}
+
+// after raygen: account for the fresh samples (single thread)
+__global__ void beginWaveKernel(const RenderConstants rc, WavefrontCounters* counters) {
+    const uint32_t n = counters->numPaths;
+    const unsigned long long remaining = counters->total - counters->generated;
+    const uint32_t room = rc.capacity - n;
+    const uint32_t fresh = (uint32_t)(remaining < (unsigned long long)room ? remaining : (unsigned long long)room);
+    counters->numPaths = n + fresh;
+    counters->generated += fresh;
+    counters->extendRays += n + fresh;
+}
+
+// after shadow: the next queue becomes the current one (single thread)
+__global__ void endWaveKernel(WavefrontCounters* counters) {
+    counters->shadowRays += counters->numShadow;
+    counters->numPaths = counters->numNext;
+    counters->numNext = 0;
+    counters->numShadow = 0;
+    for (int c = 0; c < 16; ++c) counters->classCount[c] = 0;
+    counters->waves += 1;
+    counters->done = (counters->numPaths == 0 && counters->generated == counters->total) ? 1u : 0u;
 }
 
 // ---------------------------------------------------------------------------------------------
-// shade: one bounce of Job::contribution for every path of the queue
+// surface: what Job::contribution does between a hit and the BSDF of that hit -- emission seen by the
+// ray that arrived (implicit light sampling with MIS), the environment for rays that left the scene,
+// Russian roulette and the path-length cap (PathTracingRenderer.cpp:147-163, 225-258). Survivors are
+// sorted into one queue per material class.
 // ---------------------------------------------------------------------------------------------
-template <int NC, int ML>
-__global__ void __launch_bounds__(kShadeBlock)
-shadeKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, uint32_t n, HitBuffer hits, PathQueue out, ShadowQueue sq,
-            float* __restrict__ accum, WavefrontCounters* counters) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool alive = false, shadow = false;
-    // outputs of the bounce
-    V3 nOrg(0, 0, 0), nDir(0, 0, 1);
-    float nPdf = 0.0f;
-    uint4 meta = make_uint4(0, 0, 0, 0);
-    float weight = 0.0f;
-    Spec<NC> alpha = specConst<NC>(0.0f);
-    V3 sOrg(0, 0, 0), sDir(0, 0, 1);
-    float sTmax = 0.0f;
-    Spec<NC> sContrib = specConst<NC>(0.0f);
-
-    if (i < n) {
-        const float4 o4 = in.org[i], d4 = in.dir[i];
-        meta = in.meta[i];
-        weight = in.weight[i];
-        alpha = loadAlpha<NC>(in, i);
-        const uint2 hid = hits.id[i];
-        const float4 htuv = hits.tuv[i];
-        const V3 org(o4.x, o4.y, o4.z), dir(d4.x, d4.y, d4.z);
-        const float prevPdf = d4.w;
-        const uint32_t hero = meta.z & 0xFFu;
-        uint32_t flags = (meta.z >> 8) & 0xFFu;
-        uint32_t pathLength = meta.z >> 16;
-        const float wlOffset = __uint_as_float(meta.w);
-        const bool cameraRay = flags & kFlagCameraRay;
-        const bool inPlace = flags & kFlagStrataInPlace;
-
-        SurfPt sp;
-        bool hit = true, emitting = false;
-        uint32_t material = SLRGPU_INVALID_ID;
-        SlrGpuTriangle tri = {};
-        float localArea = 1.0f;
-        if (hid.x != SLRGPU_INVALID_ID) {
-            tri = hitSurfacePoint(s, hid.x, hid.y, htuv.x, htuv.y, htuv.z, org, dir, &sp, &localArea);
-            material = tri.material;
-            emitting = materialIsEmitting(s, material);
-        } else if (s.envPresent) {
-            envSurfacePoint(dir, &sp);
-            material = s.envMaterial;
-            emitting = true;
-        } else {
-            hit = false;
-        }
-
-        if (hit) {
-            V3 dirOut = sp.sf.toLocal(-dir);
-            bool cont = true;
-            if (emitting) {
-                // DiffuseEDF: 1/pi on the front side; IBLEDF: 1/pi
-                const float edf = (sp.atInfinity || dirOut.z > 0.0f) ? 1.0f / kPi : 0.0f;
-                float mis = 1.0f;
-                if (!cameraRay && !(flags & kFlagPrevDelta)) {
-                    const float lightProb = lightSelectionProb(s, tri, hid.y, sp.atInfinity);
-                    float areaPDF, dist2;
-                    if (sp.atInfinity) { areaPDF = envEvaluateUVPDF(s, sp.u / (2 * kPi), sp.v / kPi) / (2 * kPi * kPi * sinf(sp.v)); dist2 = 1.0f; }
-                    else { areaPDF = 1.0f / localArea; dist2 = sqLength(sp.p - org); }
-                    const float lightPDF = lightProb * areaPDF * dist2 / absDot(dir, sp.gn);
-                    mis = (prevPdf * prevPdf) / (lightPDF * lightPDF + prevPdf * prevPdf);
+template <int NC>
+__global__ void __launch_bounds__(kSurfaceBlock)
+surfaceKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitBuffer hits, ClassQueue cq,
+              float* __restrict__ accum, WavefrontCounters* counters) {
+    const uint32_t n = counters->numPaths;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const uint32_t i = base + lane;
+        uint32_t cls = SC_NONE, leaf = SLRGPU_INVALID_ID;
+        if (i < n) {
+            const uint2 hid = hits.id[i];
+            uint4 meta = in.meta[i];
+            const uint32_t hero = meta.z & 0xFFu;
+            const uint32_t flags = (meta.z >> 8) & 0xFFu;
+            uint32_t pathLength = meta.z >> 16;
+            const bool cameraRay = flags & kFlagCameraRay;
+            const bool isEnv = hid.x == SLRGPU_INVALID_ID;
+            if (!isEnv || s.envPresent) {
+                uint32_t material = s.envMaterial;
+                SlrGpuTriangle tri = {};
+                bool emitting = true;
+                if (!isEnv) {
+                    tri = s.triangles[hid.x];
+                    material = tri.material;
+                    emitting = materialIsEmitting(s, material);
                 }
-                if (edf > 0.0f) {
-                    const Spec<NC> Le = materialEmittance<NC>(s, material, sp, wlOffset);
-                    float v[NC == 3 ? 4 : NC];
-                    const float k = edf * mis * weight;
-#pragma unroll
-                    for (int c = 0; c < NC; ++c) v[c] = alpha.v[c] * Le.v[c] * k;
-                    splat<NC>(accum, meta.x, wlOffset, inPlace, v);
-                }
-            }
-            if (sp.atInfinity) cont = false;
-            if (cont && !cameraRay) {
-                // Russian roulette; initY = importance of a unit spectrum = 1
-                const float continueProb = fminf(specImportance(alpha, hero) / 1.0f, 1.0f);
-                const Rand4 rr = pathRandom(rc.seed, meta.x, meta.y, 2 * pathLength + 1);   // .z of the previous bounce's second block
-                if (rr.z < continueProb) alpha = alpha * (1.0f / continueProb);
-                else cont = false;
-            }
-            if (cont) {
-                ++pathLength;
-                if (pathLength >= rc.maxPathLength) cont = false;
-            }
-            if (cont) {
-                const V3 gNorm = sp.sf.toLocal(sp.gn);
-                Bsdf<NC, ML> bsdf;
-                buildBsdf<NC, ML>(s, material, sp, wlOffset, (flags & kFlagLambdaSelected) != 0, &bsdf);
-                BsdfQuery q;
-                q.dir = dirOut; q.gn = gNorm; q.hero = hero; q.flags = DT_All;
-                const Rand4 ra = pathRandom(rc.seed, meta.x, meta.y, 2 * pathLength);       // light select, light u0, u1, bsdf component
-                const Rand4 rb = pathRandom(rc.seed, meta.x, meta.y, 2 * pathLength + 1);   // bsdf u0, u1
-
-                // next event estimation
-                if (bsdfHasNonDelta(bsdf) && (s.numTopLights > 0 || s.envPresent)) {
-                    LightSample ls;
-                    sampleLight(s, ra.x, ra.y, ra.z, &ls);
-                    float dist2;
-                    V3 shadowDir;
-                    if (ls.sp.atInfinity) { dist2 = 1.0f; shadowDir = normalize(ls.sp.p); }
-                    else { const V3 d = ls.sp.p - sp.p; dist2 = sqLength(d); shadowDir = d / sqrtf(dist2); }
-                    const V3 shadowDir_l = ls.sp.sf.toLocal(-shadowDir);
-                    const V3 shadowDir_sn = sp.sf.toLocal(shadowDir);
-                    const float edf = (ls.isEnv || shadowDir_l.z > 0.0f) ? 1.0f / kPi : 0.0f;
-                    if (edf > 0.0f && ls.areaPDF > 0.0f) {
-                        const Spec<NC> fs = bsdfEvaluate(bsdf, q, shadowDir_sn);
-                        if (!specIsZero(fs)) {
-                            const Spec<NC> M = materialEmittance<NC>(s, ls.material, ls.sp, wlOffset);
-                            const float cosLight = absDot(-shadowDir, ls.sp.gn);
-                            const float bsdfPDF = bsdfPdf(bsdf, q, shadowDir_sn) * cosLight / dist2;
-                            float mis = 1.0f;
-                            if (!isinf(ls.areaPDF)) mis = (ls.lightPDF * ls.lightPDF) / (ls.lightPDF * ls.lightPDF + bsdfPDF * bsdfPDF);
-                            const float G = absDot(shadowDir_sn, gNorm) * cosLight / dist2;
-                            const float k = edf * (G * mis / ls.lightPDF) * weight;
-#pragma unroll
-                            for (int c = 0; c < NC; ++c) sContrib.v[c] = alpha.v[c] * M.v[c] * fs.v[c] * k;
-                            // Scene::testVisibility
-                            sOrg = sp.p;
-                            if (ls.sp.atInfinity) { sDir = shadowDir; sTmax = 3.402823466e+38f; }
-                            else { const float dist = length(ls.sp.p - sp.p); sDir = (ls.sp.p - sp.p) / dist; sTmax = dist * (1.0f - 0.0001f); }
-                            shadow = true;
+                Spec<NC> alpha;
+                const bool needAlpha = emitting || !cameraRay;
+                if (needAlpha) alpha = loadAlpha<NC>(in, i);
+                if (emitting) {
+                    const float4 o4 = in.org[i], d4 = in.dir[i];
+                    const V3 org(o4.x, o4.y, o4.z), dir(d4.x, d4.y, d4.z);
+                    const float prevPdf = d4.w;
+                    const float wlOffset = __uint_as_float(meta.w);
+                    SurfPt sp;
+                    float localArea = 1.0f;
+                    if (isEnv) envSurfacePoint(dir, &sp);
+                    else { const float4 htuv = hits.tuv[i]; hitSurfacePoint(s, hid.x, hid.y, htuv.x, htuv.y, htuv.z, org, dir, &sp, &localArea); }
+                    const V3 dirOut = sp.sf.toLocal(-dir);
+                    // DiffuseEDF: 1/pi on the front side; IBLEDF: 1/pi
+                    const float edf = (sp.atInfinity || dirOut.z > 0.0f) ? 1.0f / kPi : 0.0f;
+                    if (edf > 0.0f) {
+                        float mis = 1.0f;
+                        if (!cameraRay && !(flags & kFlagPrevDelta)) {
+                            const float lightProb = lightSelectionProb(s, tri, hid.y, sp.atInfinity);
+                            float areaPDF, dist2;
+                            if (sp.atInfinity) { areaPDF = envEvaluateUVPDF(s, sp.u / (2 * kPi), sp.v / kPi) / (2 * kPi * kPi * sinf(sp.v)); dist2 = 1.0f; }
+                            else { areaPDF = 1.0f / localArea; dist2 = sqLength(sp.p - org); }
+                            const float lightPDF = lightProb * areaPDF * dist2 / absDot(dir, sp.gn);
+                            mis = (prevPdf * prevPdf) / (lightPDF * lightPDF + prevPdf * prevPdf);
                         }
+                        const Spec<NC> Le = materialEmittance<NC>(s, material, sp, wlOffset);
+                        float v[NC == 3 ? 4 : NC];
+                        const float k = edf * mis * in.weight[i];
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) v[c] = alpha.v[c] * Le.v[c] * k;
+                        splat<NC>(accum, meta.x, wlOffset, (flags & kFlagStrataInPlace) != 0, v);
                     }
                 }
-
-                // sample the BSDF for the next direction
-                BsdfSampleResult res;
-                const Spec<NC> fs = bsdfSample(bsdf, q, ra.w, rb.x, rb.y, &res);
-                if (!specIsZero(fs) && res.pdf != 0.0f) {
-                    float dirPDF = res.pdf;
-                    if (res.type & DT_Dispersive) { dirPDF /= NC; flags |= kFlagLambdaSelected; }
-                    const float k = absDot(res.dir, gNorm) / dirPDF;
-                    alpha = alpha * (fs * k);
-                    nOrg = sp.p;
-                    nDir = sp.sf.fromLocal(res.dir);
-                    nPdf = dirPDF;
-                    flags &= ~(kFlagCameraRay | kFlagPrevDelta);
-                    if (dtIsDelta(res.type)) flags |= kFlagPrevDelta;
-                    meta.z = hero | (flags << 8) | (pathLength << 16);
-                    alive = true;
+                bool cont = !isEnv;
+                if (cont && !cameraRay) {
+                    // Russian roulette; initY = importance of a unit spectrum = 1
+                    const float continueProb = fminf(specImportance(alpha, hero), 1.0f);
+                    const Rand4 rr = pathRandom(rc.seed, meta.x, meta.y, 2 * pathLength + 1);   // .z of the previous bounce's second block
+                    if (rr.z < continueProb) { alpha = alpha * (1.0f / continueProb); storeAlpha<NC>(in, i, alpha); }
+                    else cont = false;
+                }
+                if (cont) {
+                    ++pathLength;
+                    if (pathLength >= rc.maxPathLength) cont = false;
+                }
+                if (cont) {
+                    cls = classifyMaterial(s, material, &leaf);
+                    if (cls != SC_NONE) in.meta[i].z = hero | (flags << 8) | (pathLength << 16);
                 }
             }
         }
-    }
-
-    const uint32_t spos = warpAppend(shadow, &counters->numShadow);
-    if (shadow) {
-        sq.org[spos] = make_float4(sOrg.x, sOrg.y, sOrg.z, 0.0001f);
-        sq.dir[spos] = make_float4(sDir.x, sDir.y, sDir.z, sTmax);
-        const bool inPlace = ((meta.z >> 8) & kFlagStrataInPlace) != 0;
-        sq.pixelWl[spos] = make_uint2(meta.x | (inPlace ? 0x80000000u : 0u), meta.w);
-        if (NC == 3) sq.contrib[spos] = make_float4(sContrib.v[0], sContrib.v[1], sContrib.v[2], 0.0f);
-        else {
-#pragma unroll
-            for (int k = 0; k < NC / 4; ++k)
-                sq.contrib[(size_t)k * sq.capacity + spos] =
-                    make_float4(sContrib.v[4 * k], sContrib.v[(4 * k + 1) % NC], sContrib.v[(4 * k + 2) % NC], sContrib.v[(4 * k + 3) % NC]);
+        // append to the class queues: one atomic per (warp, class)
+        const unsigned active = __ballot_sync(0xFFFFFFFFu, cls != SC_NONE);
+        if (cls != SC_NONE) {
+            const unsigned grp = __match_any_sync(active, cls);
+            const int leader = __ffs(grp) - 1;
+            uint32_t pos = 0;
+            if ((int)lane == leader) pos = atomicAdd(&counters->classCount[cls], (uint32_t)__popc(grp));
+            pos = __shfl_sync(grp, pos, leader) + __popc(grp & ((1u << lane) - 1u));
+            cq.entries[(size_t)cls * cq.capacity + pos] = make_uint2(i, leaf);
         }
     }
-    const uint32_t npos = warpAppend(alive, &counters->numNext);
-    if (alive) {
-        out.org[npos] = make_float4(nOrg.x, nOrg.y, nOrg.z, 0.0001f);      // Ray::Epsilon
-        out.dir[npos] = make_float4(nDir.x, nDir.y, nDir.z, nPdf);
-        out.meta[npos] = meta;
-        out.weight[npos] = weight;
-        storeAlpha<NC>(out, npos, alpha);
+}
+
+// ---------------------------------------------------------------------------------------------
+// material: for every survivor of one class -- BSDF at the hit, next event estimation (the shadow ray
+// goes to the shadow queue with its MIS-weighted contribution), BSDF sampling of the next direction
+// (PathTracingRenderer.cpp:164-222). CLASS < SC_GENERIC: one lobe of compile-time type; SC_GENERIC:
+// the tagged multi-lobe BSDF.
+// ---------------------------------------------------------------------------------------------
+template <int NC, int CLASS> struct HitBsdf {
+    Lobe<NC> lobe;
+    __device__ __forceinline__ void build(const DeviceScene& s, uint32_t leaf, const SurfPt& sp, float wlOffset, bool lambdaSelected) {
+        fillLobeT<NC, classMaterialKind(CLASS)>(s, s.materials[leaf], sp, wlOffset, lambdaSelected, 1.0f, 0u, &lobe);
+    }
+    __device__ __forceinline__ bool hasNonDelta() const { return dtMatches(lobe.baseDirType, DT_WholeSphere | DT_NonDelta); }
+    __device__ __forceinline__ Spec<NC> evaluate(const BsdfQuery& q, const V3& d) const { return lobeEvaluate<NC, CLASS>(lobe, q, d); }
+    __device__ __forceinline__ float pdf(const BsdfQuery& q, const V3& d) const { return lobePdf<NC, CLASS>(lobe, q, d); }
+    __device__ __forceinline__ Spec<NC> sample(const BsdfQuery& q, float uc, float u0, float u1, BsdfSampleResult* r) const { return lobeSample<NC, CLASS>(lobe, q, uc, u0, u1, r); }
+};
+template <int NC> struct HitBsdf<NC, SC_GENERIC> {
+    Bsdf<NC, 4> bsdf;
+    __device__ __forceinline__ void build(const DeviceScene& s, uint32_t leaf, const SurfPt& sp, float wlOffset, bool lambdaSelected) {
+        buildBsdf<NC, 4>(s, leaf, sp, wlOffset, lambdaSelected, &bsdf);
+    }
+    __device__ __forceinline__ bool hasNonDelta() const { return bsdfHasNonDelta(bsdf); }
+    __device__ __forceinline__ Spec<NC> evaluate(const BsdfQuery& q, const V3& d) const { return bsdfEvaluate(bsdf, q, d); }
+    __device__ __forceinline__ float pdf(const BsdfQuery& q, const V3& d) const { return bsdfPdf(bsdf, q, d); }
+    __device__ __forceinline__ Spec<NC> sample(const BsdfQuery& q, float uc, float u0, float u1, BsdfSampleResult* r) const { return bsdfSample(bsdf, q, uc, u0, u1, r); }
+};
+
+template <int NC, int CLASS>
+__global__ void __launch_bounds__(kMaterialBlock)
+materialKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitBuffer hits, ClassQueue cq, PathQueue out, ShadowQueue sq,
+               WavefrontCounters* counters) {
+    const uint32_t n = counters->classCount[CLASS];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint2* __restrict__ entries = cq.entries + (size_t)CLASS * cq.capacity;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const uint32_t k = base + lane;
+        bool alive = false, shadow = false;
+        V3 nOrg(0, 0, 0), nDir(0, 0, 1);
+        float nPdf = 0.0f;
+        uint4 meta = make_uint4(0, 0, 0, 0);
+        float weight = 0.0f;
+        Spec<NC> alpha = specConst<NC>(0.0f);
+        V3 sOrg(0, 0, 0), sDir(0, 0, 1);
+        float sTmax = 0.0f;
+        Spec<NC> sContrib = specConst<NC>(0.0f);
+
+        if (k < n) {
+            const uint2 e = entries[k];
+            const uint32_t i = e.x;
+            const float4 o4 = in.org[i], d4 = in.dir[i];
+            meta = in.meta[i];
+            weight = in.weight[i];
+            alpha = loadAlpha<NC>(in, i);
+            const uint2 hid = hits.id[i];
+            const float4 htuv = hits.tuv[i];
+            const V3 org(o4.x, o4.y, o4.z), dir(d4.x, d4.y, d4.z);
+            const uint32_t hero = meta.z & 0xFFu;
+            uint32_t flags = (meta.z >> 8) & 0xFFu;
+            const uint32_t pathLength = meta.z >> 16;
+            const float wlOffset = __uint_as_float(meta.w);
+
+            SurfPt sp;
+            float localArea;
+            hitSurfacePoint(s, hid.x, hid.y, htuv.x, htuv.y, htuv.z, org, dir, &sp, &localArea);
+            const V3 dirOut = sp.sf.toLocal(-dir);
+            const V3 gNorm = sp.sf.toLocal(sp.gn);
+            HitBsdf<NC, CLASS> bsdf;
+            bsdf.build(s, e.y, sp, wlOffset, (flags & kFlagLambdaSelected) != 0);
+            BsdfQuery q;
+            q.dir = dirOut; q.gn = gNorm; q.hero = hero; q.flags = DT_All;
+            const Rand4 ra = pathRandom(rc.seed, meta.x, meta.y, 2 * pathLength);       // light select, light u0, u1, bsdf component
+            const Rand4 rb = pathRandom(rc.seed, meta.x, meta.y, 2 * pathLength + 1);   // bsdf u0, u1
+
+            // next event estimation
+            if (bsdf.hasNonDelta() && (s.numTopLights > 0 || s.envPresent)) {
+                LightSample ls;
+                sampleLight(s, ra.x, ra.y, ra.z, &ls);
+                float dist2;
+                V3 shadowDir;
+                if (ls.sp.atInfinity) { dist2 = 1.0f; shadowDir = normalize(ls.sp.p); }
+                else { const V3 d = ls.sp.p - sp.p; dist2 = sqLength(d); shadowDir = d / sqrtf(dist2); }
+                const V3 shadowDir_l = ls.sp.sf.toLocal(-shadowDir);
+                const V3 shadowDir_sn = sp.sf.toLocal(shadowDir);
+                const float edf = (ls.isEnv || shadowDir_l.z > 0.0f) ? 1.0f / kPi : 0.0f;
+                if (edf > 0.0f && ls.areaPDF > 0.0f) {
+                    const Spec<NC> fs = bsdf.evaluate(q, shadowDir_sn);
+                    if (!specIsZero(fs)) {
+                        const Spec<NC> M = materialEmittance<NC>(s, ls.material, ls.sp, wlOffset);
+                        const float cosLight = absDot(-shadowDir, ls.sp.gn);
+                        const float bsdfPDF = bsdf.pdf(q, shadowDir_sn) * cosLight / dist2;
+                        float mis = 1.0f;
+                        if (!isinf(ls.areaPDF)) mis = (ls.lightPDF * ls.lightPDF) / (ls.lightPDF * ls.lightPDF + bsdfPDF * bsdfPDF);
+                        const float G = absDot(shadowDir_sn, gNorm) * cosLight / dist2;
+                        const float kk = edf * (G * mis / ls.lightPDF) * weight;
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) sContrib.v[c] = alpha.v[c] * M.v[c] * fs.v[c] * kk;
+                        // Scene::testVisibility
+                        sOrg = sp.p;
+                        if (ls.sp.atInfinity) { sDir = shadowDir; sTmax = 3.402823466e+38f; }
+                        else { const float dist = length(ls.sp.p - sp.p); sDir = (ls.sp.p - sp.p) / dist; sTmax = dist * (1.0f - 0.0001f); }
+                        shadow = true;
+                    }
+                }
+            }
+
+            // sample the BSDF for the next direction
+            BsdfSampleResult res;
+            const Spec<NC> fs = bsdf.sample(q, ra.w, rb.x, rb.y, &res);
+            if (!specIsZero(fs) && res.pdf != 0.0f) {
+                float dirPDF = res.pdf;
+                if (res.type & DT_Dispersive) { dirPDF /= NC; flags |= kFlagLambdaSelected; }
+                const float kk = absDot(res.dir, gNorm) / dirPDF;
+                alpha = alpha * (fs * kk);
+                nOrg = sp.p;
+                nDir = sp.sf.fromLocal(res.dir);
+                nPdf = dirPDF;
+                flags &= ~(kFlagCameraRay | kFlagPrevDelta);
+                if (dtIsDelta(res.type)) flags |= kFlagPrevDelta;
+                meta.z = hero | (flags << 8) | (pathLength << 16);
+                alive = true;
+            }
+        }
+
+        const uint32_t spos = warpAppend(shadow, &counters->numShadow);
+        if (shadow) {
+            sq.org[spos] = make_float4(sOrg.x, sOrg.y, sOrg.z, 0.0001f);
+            sq.dir[spos] = make_float4(sDir.x, sDir.y, sDir.z, sTmax);
+            const bool inPlace = ((meta.z >> 8) & kFlagStrataInPlace) != 0;
+            sq.pixelWl[spos] = make_uint2(meta.x | (inPlace ? 0x80000000u : 0u), meta.w);
+            if (NC == 3) sq.contrib[spos] = make_float4(sContrib.v[0], sContrib.v[1], sContrib.v[2], 0.0f);
+            else {
+#pragma unroll
+                for (int c = 0; c < NC / 4; ++c)
+                    sq.contrib[(size_t)c * sq.capacity + spos] =
+                        make_float4(sContrib.v[4 * c], sContrib.v[(4 * c + 1) % NC], sContrib.v[(4 * c + 2) % NC], sContrib.v[(4 * c + 3) % NC]);
+            }
+        }
+        const uint32_t npos = warpAppend(alive, &counters->numNext);
+        if (alive) {
+            out.org[npos] = make_float4(nOrg.x, nOrg.y, nOrg.z, 0.0001f);      // Ray::Epsilon
+            out.dir[npos] = make_float4(nDir.x, nDir.y, nDir.z, nPdf);
+            out.meta[npos] = meta;
+            out.weight[npos] = weight;
+            storeAlpha<NC>(out, npos, alpha);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-struct RenderBuffers {
-    void* ptrs[40] = {};
+struct RenderWorkspace {
+    void* ptrs[48] = {};
     int n = 0;
-    ~RenderBuffers() { for (int i = 0; i < n; ++i) cudaFree(ptrs[i]); }
+    uint32_t capacity = 0, channels = 0;
+    PathQueue q[2];
+    HitBuffer hits;
+    ShadowQueue sq;
+    ClassQueue cq;
+    WavefrontCounters* dCounters = nullptr;
+    WavefrontCounters* hCounters = nullptr;      // pinned ring of kRing snapshots
+    cudaEvent_t ringEvents[8] = {};
+    ~RenderWorkspace() {
+        for (int i = 0; i < n; ++i) cudaFree(ptrs[i]);
+        if (hCounters) cudaFreeHost(hCounters);
+        for (cudaEvent_t e : ringEvents) if (e) cudaEventDestroy(e);
+    }
     template <typename T> int alloc(T** p, uint64_t count) {
         void* q = nullptr;
         cudaError_t e = cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
-        if (e != cudaSuccess) return cudaFail(e, "cudaMalloc(render buffers)");
+        if (e != cudaSuccess) return cudaFail(e, "cudaMalloc(render workspace)");
         ptrs[n++] = q;
         *p = reinterpret_cast<T*>(q);
         return SLRGPU_OK;
     }
 };
+constexpr int kRing = 8;
 
-static int allocPathQueue(RenderBuffers& b, PathQueue* q, uint32_t P, int quarters) {
+static void destroyWorkspace(void* w) { delete static_cast<RenderWorkspace*>(w); }
+
+static int allocPathQueue(RenderWorkspace& b, PathQueue* q, uint32_t P, int quarters) {
     int rc;
     if ((rc = b.alloc(&q->org, P))) return rc;
     if ((rc = b.alloc(&q->dir, P))) return rc;
@@ -307,20 +424,54 @@ static int allocPathQueue(RenderBuffers& b, PathQueue* q, uint32_t P, int quarte
     return SLRGPU_OK;
 }
 
-template <int NC>
-static void launchRaygen(const SlrGpuScene* sc, const RenderConstants& rc, unsigned long long first, uint32_t count, const PathQueue& out,
-                         uint32_t outBase, cudaStream_t stream) {
-    if (count == 0) return;
-    raygenKernel<NC><<<(count + kRaygenBlock - 1) / kRaygenBlock, kRaygenBlock, 0, stream>>>(sc->dev, rc, first, count, out, outBase);
+// The queues of a render call live with the scene and are reused by later calls of the same size.
+static int getWorkspace(SlrGpuScene* sc, uint32_t P, RenderWorkspace** out) {
+    RenderWorkspace* w = static_cast<RenderWorkspace*>(sc->workspace);
+    if (w && w->capacity == P && w->channels == sc->channels) { *out = w; return SLRGPU_OK; }
+    if (w) { delete w; sc->workspace = nullptr; }
+    w = new (std::nothrow) RenderWorkspace();
+    if (!w) { setError("host allocation failed"); return SLRGPU_ERR_OUT_OF_MEMORY; }
+    const int quarters = sc->channels == 3 ? 1 : 4;
+    int rc = SLRGPU_OK;
+    for (int k = 0; k < 2 && !rc; ++k) rc = allocPathQueue(*w, &w->q[k], P, quarters);
+    if (!rc) rc = w->alloc(&w->hits.id, P);
+    if (!rc) rc = w->alloc(&w->hits.tuv, P);
+    if (!rc) rc = w->alloc(&w->sq.org, P);
+    if (!rc) rc = w->alloc(&w->sq.dir, P);
+    if (!rc) rc = w->alloc(&w->sq.pixelWl, P);
+    if (!rc) rc = w->alloc(&w->sq.contrib, (uint64_t)P * quarters);
+    if (!rc) rc = w->alloc(&w->cq.entries, (uint64_t)P * SC_COUNT);
+    if (!rc) rc = w->alloc(&w->dCounters, 1);
+    if (!rc) { cudaError_t e = cudaMallocHost(&w->hCounters, sizeof(WavefrontCounters) * kRing); if (e != cudaSuccess) rc = cudaFail(e, "cudaMallocHost"); }
+    for (int k = 0; k < kRing && !rc; ++k) { cudaError_t e = cudaEventCreateWithFlags(&w->ringEvents[k], cudaEventDisableTiming); if (e != cudaSuccess) rc = cudaFail(e, "cudaEventCreate"); }
+    if (rc) { delete w; return rc; }
+    w->sq.capacity = P; w->cq.capacity = P;
+    w->capacity = P; w->channels = sc->channels;
+    sc->workspace = w; sc->destroyWorkspace = destroyWorkspace;
+    *out = w;
+    return SLRGPU_OK;
 }
 
+template <int NC, int CLASS>
+static void launchMaterial(const SlrGpuScene* sc, const RenderConstants& rc, const RenderWorkspace& w, int cur, uint32_t grid, cudaStream_t stream) {
+    materialKernel<NC, CLASS><<<grid, kMaterialBlock, 0, stream>>>(sc->dev, rc, w.q[cur], w.hits, w.cq, w.q[cur ^ 1], w.sq, w.dCounters);
+}
+
+// the shade stage of one wave: surface + one material launch per class the scene contains
 template <int NC>
-static void launchShade(const SlrGpuScene* sc, const RenderConstants& rc, const PathQueue& in, uint32_t n, const HitBuffer& hits,
-                        const PathQueue& out, const ShadowQueue& sq, float* accum, WavefrontCounters* counters, cudaStream_t stream) {
-    if (n == 0) return;
-    const dim3 grid((n + kShadeBlock - 1) / kShadeBlock), block(kShadeBlock);
-    if (sc->maxLobes <= 1) shadeKernel<NC, 1><<<grid, block, 0, stream>>>(sc->dev, rc, in, n, hits, out, sq, accum, counters);
-    else shadeKernel<NC, 4><<<grid, block, 0, stream>>>(sc->dev, rc, in, n, hits, out, sq, accum, counters);
+static void launchShadeStage(const SlrGpuScene* sc, const RenderConstants& rc, const RenderWorkspace& w, int cur, float* accum, uint32_t grid,
+                             cudaStream_t stream) {
+    surfaceKernel<NC><<<grid, kSurfaceBlock, 0, stream>>>(sc->dev, rc, w.q[cur], w.hits, w.cq, accum, w.dCounters);
+    const uint32_t m = sc->classMask;
+    if (m & (1u << SC_LAMBERT)) launchMaterial<NC, SC_LAMBERT>(sc, rc, w, cur, grid, stream);
+    if (m & (1u << SC_OREN_NAYAR)) launchMaterial<NC, SC_OREN_NAYAR>(sc, rc, w, cur, grid, stream);
+    if (m & (1u << SC_SPECULAR_BRDF)) launchMaterial<NC, SC_SPECULAR_BRDF>(sc, rc, w, cur, grid, stream);
+    if (m & (1u << SC_SPECULAR_BSDF)) launchMaterial<NC, SC_SPECULAR_BSDF>(sc, rc, w, cur, grid, stream);
+    if (m & (1u << SC_WARD)) launchMaterial<NC, SC_WARD>(sc, rc, w, cur, grid, stream);
+    if (m & (1u << SC_ASHIKHMIN)) launchMaterial<NC, SC_ASHIKHMIN>(sc, rc, w, cur, grid, stream);
+    if (m & (1u << SC_MF_BRDF)) launchMaterial<NC, SC_MF_BRDF>(sc, rc, w, cur, grid, stream);
+    if (m & (1u << SC_MF_BSDF)) launchMaterial<NC, SC_MF_BSDF>(sc, rc, w, cur, grid, stream);
+    if (m & (1u << SC_GENERIC)) launchMaterial<NC, SC_GENERIC>(sc, rc, w, cur, grid, stream);
 }
 
 static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accumDev, cudaStream_t stream, SlrGpuRenderStats* stats) {
@@ -349,26 +500,16 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accum
     rc.selectWLPDF = rgb ? 1.0f : 16.0f / (830.0f - 360.0f);
     rc.recBinWidth = rgb ? 1.0f : 16.0f / (830.0f - 360.0f);
 
-    RenderBuffers bufs;
-    PathQueue q[2];
-    HitBuffer hits;
-    ShadowQueue sq;
-    WavefrontCounters* dCounters = nullptr;
-    const int quarters = rgb ? 1 : 4;
-    int rcode;
-    for (int k = 0; k < 2; ++k) if ((rcode = allocPathQueue(bufs, &q[k], P, quarters))) return rcode;
-    if ((rcode = bufs.alloc(&hits.id, P))) return rcode;
-    if ((rcode = bufs.alloc(&hits.tuv, P))) return rcode;
-    if ((rcode = bufs.alloc(&sq.org, P))) return rcode;
-    if ((rcode = bufs.alloc(&sq.dir, P))) return rcode;
-    if ((rcode = bufs.alloc(&sq.pixelWl, P))) return rcode;
-    if ((rcode = bufs.alloc(&sq.contrib, (uint64_t)P * quarters))) return rcode;
-    sq.capacity = P;
-    if ((rcode = bufs.alloc(&dCounters, 1))) return rcode;
-    SLRGPU_CUDA_TRY(cudaMemsetAsync(dCounters, 0, sizeof(WavefrontCounters), stream));
-    WavefrontCounters* hCounters = nullptr;
-    SLRGPU_CUDA_TRY(cudaMallocHost(&hCounters, sizeof(WavefrontCounters)));
-    struct PinnedFree { void* p; ~PinnedFree() { cudaFreeHost(p); } } pinnedFree{hCounters};
+    RenderWorkspace* wp = nullptr;
+    int rcode = getWorkspace(sc, P, &wp);
+    if (rcode) return rcode;
+    RenderWorkspace& w = *wp;
+
+    // grid-stride launches: enough blocks to fill the machine, never more than the queue needs
+    int numSMs = 148;
+    cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, sc->device);
+    const uint32_t fullGrid = (uint32_t)numSMs * 16u;
+    const uint32_t grid = std::min(fullGrid, (P + 127u) / 128u);
 
     cudaEvent_t ev0, ev1;
     SLRGPU_CUDA_TRY(cudaEventCreate(&ev0));
@@ -376,10 +517,10 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accum
     struct EventFree { cudaEvent_t a, b; ~EventFree() { cudaEventDestroy(a); cudaEventDestroy(b); } } eventFree{ev0, ev1};
     SLRGPU_CUDA_TRY(cudaEventRecord(ev0, stream));
 
-    // per-stage device time (SLRGPU_RENDER_PROFILE_STAGES): one event pair per launch, summed at the end
+    // per-stage device time (SLRGPU_RENDER_PROFILE_STAGES): one event pair per launch group, summed at the end
     const bool profile = (p->flags & SLRGPU_RENDER_PROFILE_STAGES) != 0;
     struct StageTimer {
-        std::vector<cudaEvent_t> ev[4];      // 0 raygen, 1 extend, 2 shade, 3 shadow: begin/end pairs
+        std::vector<cudaEvent_t> ev[4];      // 0 raygen, 1 extend, 2 shade (surface + material), 3 shadow: begin/end pairs
         bool on;
         cudaStream_t st;
         void mark(int stage) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev[stage].push_back(e); }
@@ -392,72 +533,73 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accum
     } timer;
     timer.on = profile; timer.st = stream;
 
-    unsigned long long generated = 0, extendRays = 0, shadowRays = 0, launches = 0, waves = 0;
+    WavefrontCounters init;
+    memset(&init, 0, sizeof(init));
+    init.total = totalSamples;
+    // the pinned slot 0 doubles as the staging buffer of the initial state (copied before any wave is enqueued)
+    w.hCounters[0] = init;
+    SLRGPU_CUDA_TRY(cudaMemcpyAsync(w.dCounters, &w.hCounters[0], sizeof(WavefrontCounters), cudaMemcpyHostToDevice, stream));
+    SLRGPU_CUDA_TRY(cudaStreamSynchronize(stream));
+
+    // Waves are enqueued without waiting for their counts; after each wave a snapshot of the counters
+    // goes to a pinned ring, and the host reads the snapshot kLag waves back to learn when the work
+    // ran out (the waves enqueued in between find empty queues and cost a few microseconds each).
+    constexpr int kLag = 3;
+    const uint32_t launchesPerWave = 6u + (uint32_t)__builtin_popcount(sc->classMask);
+    unsigned long long wave = 0, launches = 0;
     int cur = 0;
-    uint32_t nCur = 0;
-    bool overflow = false;
+    WavefrontCounters last = init;
     while (true) {
-        // refill the current queue with fresh camera samples
-        const unsigned long long remaining = totalSamples - generated;
-        const uint32_t room = P - nCur;
-        const uint32_t fresh = (uint32_t)(remaining < room ? remaining : room);
-        if (fresh) {
-            timer.mark(0);
-            if (rgb) launchRaygen<3>(sc, rc, generated, fresh, q[cur], nCur, stream);
-            else launchRaygen<16>(sc, rc, generated, fresh, q[cur], nCur, stream);
-            timer.mark(0);
-            ++launches;
-            generated += fresh;
-            nCur += fresh;
-        }
-        if (nCur == 0) break;
-        SLRGPU_CUDA_TRY(cudaMemsetAsync(dCounters, 0, 16, stream));
-        ++waves;
+        timer.mark(0);
+        if (rgb) raygenKernel<3><<<grid, kRaygenBlock, 0, stream>>>(sc->dev, rc, w.q[cur], w.dCounters);
+        else raygenKernel<16><<<grid, kRaygenBlock, 0, stream>>>(sc->dev, rc, w.q[cur], w.dCounters);
+        beginWaveKernel<<<1, 1, 0, stream>>>(rc, w.dCounters);
+        timer.mark(0);
         timer.mark(1);
-        if ((rcode = launchExtend(sc, q[cur], nCur, hits, dCounters, profile, stream))) return rcode;
+        if ((rcode = launchExtend(sc, w.q[cur], w.hits, w.dCounters, profile, grid, stream))) return rcode;
         timer.mark(1);
         timer.mark(2);
-        if (rgb) launchShade<3>(sc, rc, q[cur], nCur, hits, q[cur ^ 1], sq, accumDev, dCounters, stream);
-        else launchShade<16>(sc, rc, q[cur], nCur, hits, q[cur ^ 1], sq, accumDev, dCounters, stream);
+        if (rgb) launchShadeStage<3>(sc, rc, w, cur, accumDev, grid, stream);
+        else launchShadeStage<16>(sc, rc, w, cur, accumDev, grid, stream);
         timer.mark(2);
+        timer.mark(3);
+        if ((rcode = launchShadow(sc, w.sq, accumDev, w.dCounters, profile, grid, stream))) return rcode;
+        endWaveKernel<<<1, 1, 0, stream>>>(w.dCounters);
+        timer.mark(3);
         SLRGPU_CUDA_TRY(cudaGetLastError());
-        launches += 2;
-        extendRays += nCur;
-        SLRGPU_CUDA_TRY(cudaMemcpyAsync(hCounters, dCounters, 16, cudaMemcpyDeviceToHost, stream));
-        SLRGPU_CUDA_TRY(cudaStreamSynchronize(stream));
-        const uint32_t nShadow = hCounters->numShadow;
-        if (hCounters->stackOverflow) overflow = true;
-        if (nShadow) {
-            timer.mark(3);
-            if ((rcode = launchShadow(sc, sq, nShadow, accumDev, dCounters, profile, stream))) return rcode;
-            timer.mark(3);
-            ++launches;
-            shadowRays += nShadow;
-        }
-        nCur = hCounters->numNext;
+        const int slot = (int)(wave % kRing);
+        SLRGPU_CUDA_TRY(cudaMemcpyAsync(&w.hCounters[slot], w.dCounters, sizeof(WavefrontCounters), cudaMemcpyDeviceToHost, stream));
+        SLRGPU_CUDA_TRY(cudaEventRecord(w.ringEvents[slot], stream));
+        launches += launchesPerWave;
         cur ^= 1;
+        ++wave;
+        if (wave >= (unsigned long long)kLag) {
+            const int back = (int)((wave - kLag) % kRing);
+            SLRGPU_CUDA_TRY(cudaEventSynchronize(w.ringEvents[back]));
+            last = w.hCounters[back];
+            if (last.done) break;
+        }
     }
     SLRGPU_CUDA_TRY(cudaEventRecord(ev1, stream));
     SLRGPU_CUDA_TRY(cudaEventSynchronize(ev1));
-    SLRGPU_CUDA_TRY(cudaMemcpy(hCounters, dCounters, sizeof(WavefrontCounters), cudaMemcpyDeviceToHost));
-    if (hCounters->stackOverflow) overflow = true;
+    last = w.hCounters[(wave - 1) % kRing];
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->paths = totalSamples;
-        stats->extend_rays = extendRays; stats->shadow_rays = shadowRays;
-        stats->rays = extendRays + shadowRays;
+        stats->extend_rays = last.extendRays; stats->shadow_rays = last.shadowRays;
+        stats->rays = last.extendRays + last.shadowRays;
         stats->kernel_launches = launches;
-        stats->waves = waves;
+        stats->waves = wave;
         cudaEventElapsedTime(&stats->device_ms, ev0, ev1);
         if (profile) {
             stats->raygen_ms = timer.total(0); stats->extend_ms = timer.total(1);
             stats->shade_ms = timer.total(2); stats->shadow_ms = timer.total(3);
             stats->other_ms = stats->device_ms - stats->raygen_ms - stats->extend_ms - stats->shade_ms - stats->shadow_ms;
-            stats->extend_nodes = hCounters->extendNodes; stats->extend_leaf_records = hCounters->extendLeafRecords;
-            stats->shadow_nodes = hCounters->shadowNodes; stats->shadow_leaf_records = hCounters->shadowLeafRecords;
+            stats->extend_nodes = last.extendNodes; stats->extend_leaf_records = last.extendLeafRecords;
+            stats->shadow_nodes = last.shadowNodes; stats->shadow_leaf_records = last.shadowLeafRecords;
         }
     }
-    if (overflow) { setError("traversal stack overflow (more than %d entries)", 64); return SLRGPU_ERR_STACK_OVERFLOW; }
+    if (last.stackOverflow) { setError("traversal stack overflow (more than %d entries)", 64); return SLRGPU_ERR_STACK_OVERFLOW; }
     return SLRGPU_OK;
 }
 

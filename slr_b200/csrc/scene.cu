@@ -138,9 +138,22 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
     sc->hasInstances = d->num_instances > 0;
     sc->hasShading = d->num_materials > 0 && d->num_triangles > 0;
     sc->channels = d->rgb_mode ? 3 : 16;
-    sc->maxLobes = 1;
-    for (uint32_t i = 0; i < d->num_materials; ++i)
-        if (d->materials[i].kind == SLRGPU_MAT_SUMMED || d->materials[i].kind == SLRGPU_MAT_MIXED) sc->maxLobes = 4;
+    // which material-class kernels a wave has to launch (same numbering as ShadeClass / LobeType)
+    sc->classMask = 0;
+    for (uint32_t i = 0; i < d->num_materials; ++i) {
+        const SlrGpuMaterial& m = d->materials[i];
+        switch (m.kind) {
+            case SLRGPU_MAT_DIFFUSE: sc->classMask |= m.tex[1] == SLRGPU_INVALID_ID ? 1u << 0 : 1u << 1; break;
+            case SLRGPU_MAT_SPECULAR_REFLECTION: sc->classMask |= 1u << 2; break;
+            case SLRGPU_MAT_SPECULAR_SCATTERING: sc->classMask |= 1u << 3; break;
+            case SLRGPU_MAT_WARD_DUR: sc->classMask |= 1u << 4; break;
+            case SLRGPU_MAT_ASHIKHMIN_SHIRLEY: sc->classMask |= 1u << 5; break;
+            case SLRGPU_MAT_MICROFACET_REFLECTION: sc->classMask |= 1u << 6; break;
+            case SLRGPU_MAT_MICROFACET_SCATTERING: sc->classMask |= 1u << 7; break;
+            case SLRGPU_MAT_INVERSE: case SLRGPU_MAT_SUMMED: case SLRGPU_MAT_MIXED: sc->classMask |= 1u << 8; break;
+            default: break;
+        }
+    }
     *out = sc;
     return SLRGPU_OK;
 }
@@ -148,6 +161,7 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
 SLRGPU_API void slrgpu_scene_destroy(SlrGpuScene* sc) {
     if (!sc) return;
     cudaSetDevice(sc->device);
+    if (sc->workspace && sc->destroyWorkspace) sc->destroyWorkspace(sc->workspace);
     for (int i = 0; i < sc->numAllocations; ++i) cudaFree(sc->allocations[i]);
     delete sc;
 }

@@ -9,7 +9,6 @@
 
 namespace slrgpu {
 
-constexpr int kTraceBlock = 128;
 
 // per-warp totals of the traversal counters -> one atomic pair per warp
 __device__ __forceinline__ void addTraversalCounts(const TraversalCounters& cnt, unsigned long long* nodes, unsigned long long* leafRecords) {
@@ -21,10 +20,10 @@ __device__ __forceinline__ void addTraversalCounts(const TraversalCounters& cnt,
 
 template <bool INSTANCES, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock)
-extendKernel(const DeviceScene s, PathQueue q, uint32_t n, HitBuffer hits, WavefrontCounters* counters) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+extendKernel(const DeviceScene s, PathQueue q, HitBuffer hits, WavefrontCounters* counters) {
+    const uint32_t n = counters->numPaths;
     TraversalCounters cnt = {0, 0};
-    if (i < n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 o = q.org[i], d = q.dir[i];
         Ray r;
         r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = o.w;
@@ -43,11 +42,10 @@ extendKernel(const DeviceScene s, PathQueue q, uint32_t n, HitBuffer hits, Wavef
 
 template <bool INSTANCES, int NC, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock)
-shadowKernel(const DeviceScene s, ShadowQueue q, uint32_t n, float* __restrict__ accum, WavefrontCounters* counters) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+shadowKernel(const DeviceScene s, ShadowQueue q, float* __restrict__ accum, WavefrontCounters* counters) {
+    const uint32_t n = counters->numShadow;
     TraversalCounters cnt = {0, 0};
-    bool occluded = true;
-    if (i < n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 o = q.org[i], d = q.dir[i];
         Ray r;
         r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = o.w;
@@ -56,48 +54,45 @@ shadowKernel(const DeviceScene s, ShadowQueue q, uint32_t n, float* __restrict__
         h.prim = SLRGPU_INVALID_ID; h.inst = SLRGPU_INVALID_ID; h.t = INFINITY; h.u = h.v = 0.0f;
         uint32_t stack[kStackSize];
         bool overflow = false;
-        occluded = traverse<INSTANCES ? 0 : 1, true, COUNT>(s, 0, r, h, stack, 0, cnt, overflow);
+        const bool occluded = traverse<INSTANCES ? 0 : 1, true, COUNT>(s, 0, r, h, stack, 0, cnt, overflow);
         if (overflow) atomicExch(&counters->stackOverflow, 1u);
+        if (occluded) continue;
+        const uint2 pw = q.pixelWl[i];
+        float v[NC == 3 ? 4 : NC];
+        constexpr int Q = (NC + 3) / 4;
+#pragma unroll
+        for (int k = 0; k < Q; ++k) {
+            const float4 c = q.contrib[(size_t)k * q.capacity + i];
+            v[4 * k] = c.x;
+            if (4 * k + 1 < (NC == 3 ? 4 : NC)) v[4 * k + 1] = c.y;
+            if (4 * k + 2 < (NC == 3 ? 4 : NC)) v[4 * k + 2] = c.z;
+            if (4 * k + 3 < (NC == 3 ? 4 : NC)) v[4 * k + 3] = c.w;
+        }
+        splat<NC>(accum, pw.x & 0x7FFFFFFFu, __uint_as_float(pw.y), (pw.x >> 31) != 0, v);
     }
     if (COUNT) addTraversalCounts(cnt, &counters->shadowNodes, &counters->shadowLeafRecords);
-    if (occluded) return;
-    const uint2 pw = q.pixelWl[i];
-    float v[NC == 3 ? 4 : NC];
-    constexpr int Q = (NC + 3) / 4;
-#pragma unroll
-    for (int k = 0; k < Q; ++k) {
-        const float4 c = q.contrib[(size_t)k * q.capacity + i];
-        v[4 * k] = c.x;
-        if (4 * k + 1 < (NC == 3 ? 4 : NC)) v[4 * k + 1] = c.y;
-        if (4 * k + 2 < (NC == 3 ? 4 : NC)) v[4 * k + 2] = c.z;
-        if (4 * k + 3 < (NC == 3 ? 4 : NC)) v[4 * k + 3] = c.w;
-    }
-    splat<NC>(accum, pw.x & 0x7FFFFFFFu, __uint_as_float(pw.y), (pw.x >> 31) != 0, v);
 }
 
 template <bool INSTANCES, bool COUNT>
-static void launchExtendT(const SlrGpuScene* sc, const PathQueue& q, uint32_t n, const HitBuffer& hits, WavefrontCounters* counters, cudaStream_t stream) {
-    extendKernel<INSTANCES, COUNT><<<(n + kTraceBlock - 1) / kTraceBlock, kTraceBlock, 0, stream>>>(sc->dev, q, n, hits, counters);
+static void launchExtendT(const SlrGpuScene* sc, const PathQueue& q, const HitBuffer& hits, WavefrontCounters* counters, uint32_t grid, cudaStream_t stream) {
+    extendKernel<INSTANCES, COUNT><<<grid, kTraceBlock, 0, stream>>>(sc->dev, q, hits, counters);
 }
 template <bool INSTANCES, bool COUNT>
-static void launchShadowT(const SlrGpuScene* sc, const ShadowQueue& q, uint32_t n, float* accum, WavefrontCounters* counters, cudaStream_t stream) {
-    const dim3 grid((n + kTraceBlock - 1) / kTraceBlock), block(kTraceBlock);
-    if (sc->channels == 3) shadowKernel<INSTANCES, 3, COUNT><<<grid, block, 0, stream>>>(sc->dev, q, n, accum, counters);
-    else shadowKernel<INSTANCES, 16, COUNT><<<grid, block, 0, stream>>>(sc->dev, q, n, accum, counters);
+static void launchShadowT(const SlrGpuScene* sc, const ShadowQueue& q, float* accum, WavefrontCounters* counters, uint32_t grid, cudaStream_t stream) {
+    if (sc->channels == 3) shadowKernel<INSTANCES, 3, COUNT><<<grid, kTraceBlock, 0, stream>>>(sc->dev, q, accum, counters);
+    else shadowKernel<INSTANCES, 16, COUNT><<<grid, kTraceBlock, 0, stream>>>(sc->dev, q, accum, counters);
 }
 
-int launchExtend(const SlrGpuScene* sc, const PathQueue& q, uint32_t n, const HitBuffer& hits, WavefrontCounters* counters, bool count, cudaStream_t stream) {
-    if (n == 0) return SLRGPU_OK;
-    if (sc->hasInstances) { if (count) launchExtendT<true, true>(sc, q, n, hits, counters, stream); else launchExtendT<true, false>(sc, q, n, hits, counters, stream); }
-    else { if (count) launchExtendT<false, true>(sc, q, n, hits, counters, stream); else launchExtendT<false, false>(sc, q, n, hits, counters, stream); }
+int launchExtend(const SlrGpuScene* sc, const PathQueue& q, const HitBuffer& hits, WavefrontCounters* counters, bool count, uint32_t grid, cudaStream_t stream) {
+    if (sc->hasInstances) { if (count) launchExtendT<true, true>(sc, q, hits, counters, grid, stream); else launchExtendT<true, false>(sc, q, hits, counters, grid, stream); }
+    else { if (count) launchExtendT<false, true>(sc, q, hits, counters, grid, stream); else launchExtendT<false, false>(sc, q, hits, counters, grid, stream); }
     SLRGPU_CUDA_TRY(cudaGetLastError());
     return SLRGPU_OK;
 }
 
-int launchShadow(const SlrGpuScene* sc, const ShadowQueue& q, uint32_t n, float* accum, WavefrontCounters* counters, bool count, cudaStream_t stream) {
-    if (n == 0) return SLRGPU_OK;
-    if (sc->hasInstances) { if (count) launchShadowT<true, true>(sc, q, n, accum, counters, stream); else launchShadowT<true, false>(sc, q, n, accum, counters, stream); }
-    else { if (count) launchShadowT<false, true>(sc, q, n, accum, counters, stream); else launchShadowT<false, false>(sc, q, n, accum, counters, stream); }
+int launchShadow(const SlrGpuScene* sc, const ShadowQueue& q, float* accum, WavefrontCounters* counters, bool count, uint32_t grid, cudaStream_t stream) {
+    if (sc->hasInstances) { if (count) launchShadowT<true, true>(sc, q, accum, counters, grid, stream); else launchShadowT<true, false>(sc, q, accum, counters, grid, stream); }
+    else { if (count) launchShadowT<false, true>(sc, q, accum, counters, grid, stream); else launchShadowT<false, false>(sc, q, accum, counters, grid, stream); }
     SLRGPU_CUDA_TRY(cudaGetLastError());
     return SLRGPU_OK;
 }

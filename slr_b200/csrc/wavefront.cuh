@@ -41,12 +41,33 @@ struct ShadowQueue {
     uint32_t capacity;     // stride of the contribution quarters
 };
 
+// Material class of a surviving hit: the lobe type of a single-lobe BSDF (numbered like LobeType in
+// bsdf.cuh) or SC_GENERIC for anything wrapped in a MultiBSDF / InverseBSDF. The `surface` kernel
+// sorts survivors into one queue per class so that every `material` kernel launch runs one BSDF
+// model with full warps (the reference dispatches per hit through virtual calls).
+enum ShadeClass : uint32_t {
+    SC_LAMBERT = 0, SC_OREN_NAYAR = 1, SC_SPECULAR_BRDF = 2, SC_SPECULAR_BSDF = 3, SC_WARD = 4, SC_ASHIKHMIN = 5,
+    SC_MF_BRDF = 6, SC_MF_BSDF = 7, SC_GENERIC = 8, SC_COUNT = 9, SC_NONE = 0xFFu
+};
+
+// Device-resident loop state: every kernel of a wave reads its work size from here, so the host
+// never has to wait for a count (it only polls, two waves behind, for termination).
 struct WavefrontCounters {
+    uint32_t numPaths;         // entries of the current path queue
     uint32_t numNext;          // entries appended to the next path queue
     uint32_t numShadow;        // entries appended to the shadow queue
     uint32_t stackOverflow;
-    uint32_t pad;
-    unsigned long long extendNodes, extendLeafRecords, shadowNodes, shadowLeafRecords;   // only counted by the profiling variants of extend / shadow
+    uint32_t classCount[16];   // entries of each material-class queue (SC_COUNT used)
+    unsigned long long generated, total;          // camera samples started / to render in this call
+    unsigned long long extendRays, shadowRays;
+    unsigned long long extendNodes, extendLeafRecords, shadowNodes, shadowLeafRecords;   // only counted by the profiling variants
+    uint32_t waves, done;
+};
+
+// One entry of a material-class queue: position in the current path queue + the leaf material id.
+struct ClassQueue {
+    uint2* entries;        // [SC_COUNT][capacity]
+    uint32_t capacity;
 };
 
 struct RenderConstants {
@@ -63,9 +84,11 @@ struct RenderConstants {
 };
 
 // launch helpers implemented in trace.cu (compiled with -fmad=false: same arithmetic as the batch API)
+// Grid-stride launches over counters->numPaths / counters->numShadow entries (`grid` blocks).
 // `count` selects the variants that also total QBVH nodes popped / leaf records tested (the algorithmic-bytes model)
-int launchExtend(const SlrGpuScene* sc, const PathQueue& q, uint32_t n, const HitBuffer& hits, WavefrontCounters* counters, bool count, cudaStream_t stream);
-int launchShadow(const SlrGpuScene* sc, const ShadowQueue& q, uint32_t n, float* accum, WavefrontCounters* counters, bool count, cudaStream_t stream);
+int launchExtend(const SlrGpuScene* sc, const PathQueue& q, const HitBuffer& hits, WavefrontCounters* counters, bool count, uint32_t grid, cudaStream_t stream);
+int launchShadow(const SlrGpuScene* sc, const ShadowQueue& q, float* accum, WavefrontCounters* counters, bool count, uint32_t grid, cudaStream_t stream);
+constexpr int kTraceBlock = 128;
 
 // Stratum of wavelength i for a path with stratification offset `wlOffset`: min(uint((lambda_i - 360)
 // / 470 * 16), 15) (SpectrumTypes.h:826-835) in uncontracted fp32 as the x86-64 reference computes it
