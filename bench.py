@@ -37,26 +37,62 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 # clocks sampling during the timed region (B200_PROFILING.md "clocks line")
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region through NVML (in-process: no
+    nvidia-smi process start-up contending with the render loop's stream polling); falls back to
+    `nvidia-smi --query-gpu` once per second when the NVML binding is missing."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.1):
         self.index = index
-        self.samples = []
+        self.period = period
+        self.samples = []          # (sm_mhz, max_mhz, [bool x 4])
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self._handle, n.NVML_CLOCK_SM)
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle)
+        bits = [0x8, 0x40, 0x20, 0x4]     # HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap
+        self.samples.append((float(sm), float(mx), [bool(r & b) for b in bits]))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(",")]
+        if len(parts) >= 6:
+            self.samples.append((float(parts[0]), float(parts[1]), [p.lower().startswith("active") for p in parts[2:6]]))
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(self.period if self._nvml is not None else 1.0)
 
     def __enter__(self):
         self._t.start()
@@ -69,11 +105,10 @@ class ClockSampler:
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2][i] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": reasons,
+                "samples": len(self.samples), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def measured_peaks():

@@ -388,6 +388,10 @@ SLRGPU_API int slrgpu_render(SlrGpuScene* scene, const SlrGpuRenderParams* param
 SLRGPU_API int slrgpu_render_device(SlrGpuScene* scene, const SlrGpuRenderParams* params, float* accum_device,
                                     void* stream, SlrGpuRenderStats* stats);
 
+/* Render calls keep their wavefront queues (about 440 bytes per path in flight) in a per-device pool
+ * for reuse by later calls; this frees the pool. */
+SLRGPU_API void slrgpu_release_workspaces(void);
+
 #ifdef __cplusplus
 }
 #endif

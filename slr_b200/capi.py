@@ -3,8 +3,11 @@
 Mirrors the C structs field for field; ``check_abi()`` compares every ``ctypes.sizeof`` with the
 library's ``slrgpu_struct_size`` so a drifted mirror fails loudly instead of corrupting memory.
 """
+import contextlib
 import ctypes as C
 import os
+import sys
+import time
 import numpy as np
 
 _LIBDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
@@ -191,6 +194,21 @@ host.slrhost_scene_stats.restype = C.c_int
 host.slrhost_scene_stats.argtypes = [C.c_void_p, c_u32, C.POINTER(C.c_double)]
 host.slrhost_scene_build_seconds.restype = C.c_double
 host.slrhost_scene_build_seconds.argtypes = [C.c_void_p]
+
+
+@contextlib.contextmanager
+def stdout_to_stderr():
+    """The host library reports model loading on stdout like the reference does ("Reading: ... done.");
+    programs whose stdout is a protocol (bench.py prints ONE JSON line) route it to stderr."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    try:
+        os.dup2(2, 1)
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
 
 
 class SlrError(RuntimeError):
@@ -408,11 +426,14 @@ def host_render(host_scene, width=0, height=0, spp=0, seed=0, device=0, bmp_dir=
     w = width or ctx["width"]
     h = height or ctx["height"]
     chan = 3 if host_scene.desc.rgb_mode else 16
-    accum = np.zeros((h, w, chan), np.float32)
+    accum = np.empty((h, w, chan), np.float32)
     st = (C.c_double * 6)()
+    t0 = time.perf_counter()
     _host_check(host.slrhost_render(host_scene.handle, device, width, height, spp, seed,
                                     os.fsencode(bmp_dir) if bmp_dir else None, _pf(accum), st), "slrhost_render")
-    return accum, {"paths": int(st[0]), "rays": int(st[1]), "device_s": st[2], "wall_s": st[3], "upload_s": st[4], "channels": int(st[5])}
+    call_s = time.perf_counter() - t0
+    return accum, {"paths": int(st[0]), "rays": int(st[1]), "device_s": st[2], "wall_s": st[3], "upload_s": st[4], "channels": int(st[5]),
+                   "call_s": call_s}
 
 
 def gpu_render(gpu_scene, width, height, spp_begin, spp_end, seed=1509761209, time_start=0.0, time_end=0.0, flags=0,

@@ -6,6 +6,10 @@
 
 namespace slrgpu {
 
+// internal spectrum kind produced by scene.cu compileSpectra (never part of the ABI)
+constexpr uint32_t SLRGPU_SPECTRUM_IRREGULAR_LUT = 16;
+constexpr int SLRGPU_SPECTRUM_LUT_BINS = 236;      // 2 nm bins over [360, 830] + 1
+
 // Layout in HBM (all arrays 256-byte aligned by cudaMalloc):
 //   nodes    : float4[8 * num_nodes]   one 128 B QBVH node = 8 consecutive float4 (see SlrGpuBvhNode)
 //   leaves   : float4[3 * num_leaves]  one 48 B leaf record = 3 consecutive float4 (see SlrGpuLeafRecord)
@@ -57,8 +61,6 @@ struct SlrGpuScene {
     bool hasShading = false;
     uint32_t channels = 16;
     uint32_t classMask = 0;           // material classes (wavefront.cuh: ShadeClass) the scene's materials can produce
-    void* workspace = nullptr;        // render queues, cached between render calls (render.cu)
-    void (*destroyWorkspace)(void*) = nullptr;
 };
 
 namespace slrgpu {

@@ -7,65 +7,76 @@ namespace slrgpu {
 
 constexpr int kIntersectBlock = 128;
 
+// Both kernels run the warp-cooperative walk of traverse.cuh (walkQueue): `status` points at two
+// words, [0] = stack-overflow flag, [1] = the chunk cursor (must be 0 at launch).
+struct BatchRaySource {
+    SlrGpuRayBatch rays;
+    __device__ __forceinline__ void load(uint32_t i, Ray& r) const {
+        r.ox = rays.org_x[i]; r.oy = rays.org_y[i]; r.oz = rays.org_z[i];
+        r.dx = rays.dir_x[i]; r.dy = rays.dir_y[i]; r.dz = rays.dir_z[i];
+        r.tmin = rays.tmin[i]; r.tmax = rays.tmax[i];
+    }
+};
+template <bool COUNT> struct BatchHitSink {
+    SlrGpuHitBatch hits;
+    __device__ __forceinline__ void done(uint32_t i, const WalkState& w, const TraversalCounters& cnt) const {
+        hits.prim[i] = w.hit.prim;
+        hits.inst[i] = w.hit.inst;
+        hits.t[i] = w.hit.t;
+        if (hits.u) hits.u[i] = w.hit.u;
+        if (hits.v) hits.v[i] = w.hit.v;
+        if (COUNT) {
+            if (hits.nodes_visited) hits.nodes_visited[i] = cnt.nodes - w.cnt0.nodes;
+            if (hits.tris_tested) hits.tris_tested[i] = cnt.tris - w.cnt0.tris;
+        }
+    }
+};
+struct OccludedSink {
+    uint8_t* occluded;
+    __device__ __forceinline__ void done(uint32_t i, const WalkState& w, const TraversalCounters&) const { occluded[i] = w.found ? 1 : 0; }
+};
+
 template <bool INSTANCES, bool COUNT>
 __global__ void __launch_bounds__(kIntersectBlock)
-intersectBatchKernel(const DeviceScene s, SlrGpuRayBatch rays, uint64_t n, SlrGpuHitBatch hits, int* status) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Ray r;
-    r.ox = rays.org_x[i]; r.oy = rays.org_y[i]; r.oz = rays.org_z[i];
-    r.dx = rays.dir_x[i]; r.dy = rays.dir_y[i]; r.dz = rays.dir_z[i];
-    r.tmin = rays.tmin[i]; r.tmax = rays.tmax[i];
-    Hit h;
-    h.prim = SLRGPU_INVALID_ID; h.inst = SLRGPU_INVALID_ID; h.t = INFINITY; h.u = 0.0f; h.v = 0.0f;
-    uint32_t stack[kStackSize];
+intersectBatchKernel(const DeviceScene s, SlrGpuRayBatch rays, uint32_t n, SlrGpuHitBatch hits, int* status) {
     TraversalCounters cnt = {0, 0};
     bool overflow = false;
-    traverse<INSTANCES ? 0 : 1, false, COUNT>(s, 0, r, h, stack, 0, cnt, overflow);
-    hits.prim[i] = h.prim;
-    hits.inst[i] = h.inst;
-    hits.t[i] = h.t;
-    if (hits.u) hits.u[i] = h.u;
-    if (hits.v) hits.v[i] = h.v;
-    if (COUNT) {
-        if (hits.nodes_visited) hits.nodes_visited[i] = cnt.nodes;
-        if (hits.tris_tested) hits.tris_tested[i] = cnt.tris;
-    }
+    walkQueue<INSTANCES, false, COUNT>(s, n, reinterpret_cast<uint32_t*>(status + 1), BatchRaySource{rays}, BatchHitSink<COUNT>{hits}, cnt, overflow);
     if (overflow) atomicExch(status, 1);
 }
 
 template <bool INSTANCES>
 __global__ void __launch_bounds__(kIntersectBlock)
-occludedBatchKernel(const DeviceScene s, SlrGpuRayBatch rays, uint64_t n, uint8_t* occluded, int* status) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Ray r;
-    r.ox = rays.org_x[i]; r.oy = rays.org_y[i]; r.oz = rays.org_z[i];
-    r.dx = rays.dir_x[i]; r.dy = rays.dir_y[i]; r.dz = rays.dir_z[i];
-    r.tmin = rays.tmin[i]; r.tmax = rays.tmax[i];
-    Hit h;
-    h.prim = SLRGPU_INVALID_ID; h.inst = SLRGPU_INVALID_ID; h.t = INFINITY; h.u = h.v = 0.0f;
-    uint32_t stack[kStackSize];
+occludedBatchKernel(const DeviceScene s, SlrGpuRayBatch rays, uint32_t n, uint8_t* occluded, int* status) {
     TraversalCounters cnt = {0, 0};
     bool overflow = false;
-    const bool any = traverse<INSTANCES ? 0 : 1, true, false>(s, 0, r, h, stack, 0, cnt, overflow);
-    occluded[i] = any ? 1 : 0;
+    walkQueue<INSTANCES, true, false>(s, n, reinterpret_cast<uint32_t*>(status + 1), BatchRaySource{rays}, OccludedSink{occluded}, cnt, overflow);
     if (overflow) atomicExch(status, 1);
+}
+
+// grid of the warp-cooperative kernels: enough resident warps to fill the machine, no more than the batch needs
+static uint32_t batchGrid(const SlrGpuScene* sc, uint64_t n) {
+    int numSMs = 148;
+    cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, sc->device);
+    const uint64_t need = (n + kIntersectBlock - 1) / kIntersectBlock;
+    const uint64_t full = (uint64_t)numSMs * 16u;
+    return (uint32_t)(need < full ? need : full);
 }
 
 static int launchIntersect(SlrGpuScene* sc, const SlrGpuRayBatch& rays, uint64_t n, const SlrGpuHitBatch& hits,
                            int* dStatus, cudaStream_t stream) {
     if (n == 0) return SLRGPU_OK;
-    const uint64_t blocks = (n + kIntersectBlock - 1) / kIntersectBlock;
-    if (blocks > 0x7FFFFFFFull) { setError("ray batch too large"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    if (n >= 0xFFFF0000ull) { setError("ray batch too large (at most 2^32 - 65536 rays per call)"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    SLRGPU_CUDA_TRY(cudaMemsetAsync(dStatus + 1, 0, sizeof(int), stream));
     const bool count = hits.nodes_visited || hits.tris_tested;
-    const dim3 grid((unsigned)blocks), block(kIntersectBlock);
+    const dim3 grid(batchGrid(sc, n)), block(kIntersectBlock);
+    const uint32_t n32 = (uint32_t)n;
     if (sc->hasInstances) {
-        if (count) intersectBatchKernel<true, true><<<grid, block, 0, stream>>>(sc->dev, rays, n, hits, dStatus);
-        else       intersectBatchKernel<true, false><<<grid, block, 0, stream>>>(sc->dev, rays, n, hits, dStatus);
+        if (count) intersectBatchKernel<true, true><<<grid, block, 0, stream>>>(sc->dev, rays, n32, hits, dStatus);
+        else       intersectBatchKernel<true, false><<<grid, block, 0, stream>>>(sc->dev, rays, n32, hits, dStatus);
     } else {
-        if (count) intersectBatchKernel<false, true><<<grid, block, 0, stream>>>(sc->dev, rays, n, hits, dStatus);
-        else       intersectBatchKernel<false, false><<<grid, block, 0, stream>>>(sc->dev, rays, n, hits, dStatus);
+        if (count) intersectBatchKernel<false, true><<<grid, block, 0, stream>>>(sc->dev, rays, n32, hits, dStatus);
+        else       intersectBatchKernel<false, false><<<grid, block, 0, stream>>>(sc->dev, rays, n32, hits, dStatus);
     }
     SLRGPU_CUDA_TRY(cudaGetLastError());
     return SLRGPU_OK;
@@ -107,7 +118,7 @@ extern "C" {
 
 SLRGPU_API int slrgpu_intersect_launch_config(SlrGpuScene* scene, uint64_t num_rays, uint32_t* grid, uint32_t* block) {
     if (!scene) { setError("null scene"); return SLRGPU_ERR_INVALID_ARGUMENT; }
-    if (grid) *grid = (uint32_t)((num_rays + kIntersectBlock - 1) / kIntersectBlock);
+    if (grid) *grid = batchGrid(scene, num_rays);
     if (block) *block = kIntersectBlock;
     return SLRGPU_OK;
 }
@@ -119,7 +130,7 @@ SLRGPU_API int slrgpu_intersect_batch_device(SlrGpuScene* scene, const SlrGpuRay
     }
     SLRGPU_CUDA_TRY(cudaSetDevice(scene->device));
     static thread_local int* dStatus = nullptr;
-    if (!dStatus) { SLRGPU_CUDA_TRY(cudaMalloc(&dStatus, sizeof(int))); SLRGPU_CUDA_TRY(cudaMemset(dStatus, 0, sizeof(int))); }
+    if (!dStatus) { SLRGPU_CUDA_TRY(cudaMalloc(&dStatus, 2 * sizeof(int))); SLRGPU_CUDA_TRY(cudaMemset(dStatus, 0, 2 * sizeof(int))); }
     return launchIntersect(scene, *rays, num_rays, *hits, dStatus, (cudaStream_t)stream);
 }
 
@@ -138,12 +149,12 @@ SLRGPU_API int slrgpu_intersect_batch(SlrGpuScene* scene, const SlrGpuRayBatch* 
     SlrGpuHitBatch dh = {};
     int* dStatus = nullptr;
     if ((rc = bufs.alloc(&dh.prim, n)) || (rc = bufs.alloc(&dh.inst, n)) || (rc = bufs.alloc(&dh.t, n)) ||
-        (rc = bufs.alloc(&dStatus, 1))) return rc;
+        (rc = bufs.alloc(&dStatus, 2))) return rc;
     if (hits->u && (rc = bufs.alloc(&dh.u, n))) return rc;
     if (hits->v && (rc = bufs.alloc(&dh.v, n))) return rc;
     if (hits->nodes_visited && (rc = bufs.alloc(&dh.nodes_visited, n))) return rc;
     if (hits->tris_tested && (rc = bufs.alloc(&dh.tris_tested, n))) return rc;
-    SLRGPU_CUDA_TRY(cudaMemset(dStatus, 0, sizeof(int)));
+    SLRGPU_CUDA_TRY(cudaMemset(dStatus, 0, 2 * sizeof(int)));
     cudaEvent_t e0, e1;
     SLRGPU_CUDA_TRY(cudaEventCreate(&e0));
     SLRGPU_CUDA_TRY(cudaEventCreate(&e1));
@@ -181,15 +192,16 @@ SLRGPU_API int slrgpu_occluded_batch(SlrGpuScene* scene, const SlrGpuRayBatch* r
     int rc = uploadRays(bufs, rays, n, &dr);
     if (rc != SLRGPU_OK) return rc;
     uint8_t* dOcc = nullptr; int* dStatus = nullptr;
-    if ((rc = bufs.alloc(&dOcc, n)) || (rc = bufs.alloc(&dStatus, 1))) return rc;
-    SLRGPU_CUDA_TRY(cudaMemset(dStatus, 0, sizeof(int)));
-    const uint64_t blocks = (n + kIntersectBlock - 1) / kIntersectBlock;
+    if ((rc = bufs.alloc(&dOcc, n)) || (rc = bufs.alloc(&dStatus, 2))) return rc;
+    SLRGPU_CUDA_TRY(cudaMemset(dStatus, 0, 2 * sizeof(int)));
+    if (n >= 0xFFFF0000ull) { setError("ray batch too large (at most 2^32 - 65536 rays per call)"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    const uint32_t blocks = batchGrid(scene, n);
     cudaEvent_t e0, e1;
     SLRGPU_CUDA_TRY(cudaEventCreate(&e0));
     SLRGPU_CUDA_TRY(cudaEventCreate(&e1));
     cudaEventRecord(e0, 0);
-    if (scene->hasInstances) occludedBatchKernel<true><<<(unsigned)blocks, kIntersectBlock>>>(scene->dev, dr, n, dOcc, dStatus);
-    else                     occludedBatchKernel<false><<<(unsigned)blocks, kIntersectBlock>>>(scene->dev, dr, n, dOcc, dStatus);
+    if (scene->hasInstances) occludedBatchKernel<true><<<blocks, kIntersectBlock>>>(scene->dev, dr, (uint32_t)n, dOcc, dStatus);
+    else                     occludedBatchKernel<false><<<blocks, kIntersectBlock>>>(scene->dev, dr, (uint32_t)n, dOcc, dStatus);
     cudaError_t le = cudaGetLastError();
     cudaEventRecord(e1, 0);
     cudaError_t se = cudaEventSynchronize(e1);

@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -60,13 +61,15 @@ template <int NC>
 __global__ void __launch_bounds__(kRaygenBlock)
 raygenKernel(const DeviceScene s, const RenderConstants rc, PathQueue out, const WavefrontCounters* __restrict__ counters) {
     const uint32_t outBase = counters->numPaths;
-    const unsigned long long first = counters->generated, remaining = counters->total - first;
+    const unsigned long long remaining = counters->total - counters->generated;
     const uint32_t room = rc.capacity - outBase;
     const uint32_t count = (uint32_t)(remaining < (unsigned long long)room ? remaining : (unsigned long long)room);
+    // next sample = pixel-order position genOffset of pass genPass (kept by beginWaveKernel: no 64-bit division here)
+    const uint32_t genPass = counters->genPass, genOffset = counters->genOffset;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) {
-        const unsigned long long g = first + j;
-        const uint32_t pass = (uint32_t)(g / rc.numPixels);
-        const uint32_t r = (uint32_t)(g % rc.numPixels);
+        const uint32_t lin = genOffset + j;                       // < numPixels + capacity < 2^32
+        const uint32_t pass = genPass + lin / rc.numPixels;
+        const uint32_t r = lin % rc.numPixels;
         // pixel order: bands of 8 rows, column-major inside a band, so a warp covers a 4x8 pixel block
         const uint32_t band = r / (8u * rc.width);
         const uint32_t local = r - band * 8u * rc.width;
@@ -102,13 +105,16 @@ raygenKernel(const DeviceScene s, const RenderConstants rc, PathQueue out, const
         // ImageSensor::add bins by the float pixel position
         const uint32_t ipx = min((uint32_t)px, rc.width - 1), ipy = min((uint32_t)py, rc.height - 1);
         uint32_t flags = kFlagCameraRay;
-        if (NC == 16 && strataInPlace(wlOffset)) flags |= kFlagStrataInPlace;
+        // wavelength i lands in stratum i unless the offset sits within rounding distance of 0 or 1:
+        // only then is the exact (16 x 2 IEEE divisions) test needed
+        if (NC == 16 && ((wlOffset > 1e-4f && wlOffset < 1.0f - 1e-4f) || strataInPlace(wlOffset))) flags |= kFlagStrataInPlace;
 
         const uint32_t pos = outBase + j;
         out.org[pos] = make_float4(org.x, org.y, org.z, 0.0f);
         out.dir[pos] = make_float4(dir.x, dir.y, dir.z, 0.0f);
         out.meta[pos] = make_uint4(ipy * rc.width + ipx, sample, hero | (flags << 8), __float_as_uint(wlOffset));
         out.weight[pos] = weight * rc.recBinWidth;
+        out.aux[pos] = 1.0f;
         storeAlpha<NC>(out, pos, specConst<NC>(1.0f));
     }
 }
@@ -122,6 +128,9 @@ __global__ void beginWaveKernel(const RenderConstants rc, WavefrontCounters* cou
     counters->numPaths = n + fresh;
     counters->generated += fresh;
     counters->extendRays += n + fresh;
+    const uint32_t lin = counters->genOffset + fresh;
+    counters->genPass += lin / rc.numPixels;
+    counters->genOffset = lin % rc.numPixels;
 }
 
 // after shadow: the next queue becomes the current one (single thread)
@@ -131,6 +140,8 @@ __global__ void endWaveKernel(WavefrontCounters* counters) {
     counters->numNext = 0;
     counters->numShadow = 0;
     for (int c = 0; c < 16; ++c) counters->classCount[c] = 0;
+    counters->extendCursor = 0;
+    counters->shadowCursor = 0;
     counters->waves += 1;
     counters->done = (counters->numPaths == 0 && counters->generated == counters->total) ? 1u : 0u;
 }
@@ -168,10 +179,8 @@ surfaceKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitBu
                     material = tri.material;
                     emitting = materialIsEmitting(s, material);
                 }
-                Spec<NC> alpha;
-                const bool needAlpha = emitting || !cameraRay;
-                if (needAlpha) alpha = loadAlpha<NC>(in, i);
                 if (emitting) {
+                    const Spec<NC> alpha = loadAlpha<NC>(in, i);
                     const float4 o4 = in.org[i], d4 = in.dir[i];
                     const V3 org(o4.x, o4.y, o4.z), dir(d4.x, d4.y, d4.z);
                     const float prevPdf = d4.w;
@@ -203,10 +212,12 @@ surfaceKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitBu
                 }
                 bool cont = !isEnv;
                 if (cont && !cameraRay) {
-                    // Russian roulette; initY = importance of a unit spectrum = 1
-                    const float continueProb = fminf(specImportance(alpha, hero), 1.0f);
+                    // Russian roulette; initY = importance of a unit spectrum = 1. importance(alpha) was left in
+                    // aux by the material kernel that produced this entry; the surviving path's 1/q goes back
+                    // into aux and is applied to alpha by the material kernel of this bounce.
+                    const float continueProb = fminf(in.aux[i], 1.0f);
                     const Rand4 rr = pathRandom(rc.seed, meta.x, meta.y, 2 * pathLength + 1);   // .z of the previous bounce's second block
-                    if (rr.z < continueProb) { alpha = alpha * (1.0f / continueProb); storeAlpha<NC>(in, i, alpha); }
+                    if (rr.z < continueProb) in.aux[i] = 1.0f / continueProb;
                     else cont = false;
                 }
                 if (cont) {
@@ -271,7 +282,7 @@ materialKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitB
         const uint32_t k = base + lane;
         bool alive = false, shadow = false;
         V3 nOrg(0, 0, 0), nDir(0, 0, 1);
-        float nPdf = 0.0f;
+        float nPdf = 0.0f, nImp = 0.0f;
         uint4 meta = make_uint4(0, 0, 0, 0);
         float weight = 0.0f;
         Spec<NC> alpha = specConst<NC>(0.0f);
@@ -285,7 +296,7 @@ materialKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitB
             const float4 o4 = in.org[i], d4 = in.dir[i];
             meta = in.meta[i];
             weight = in.weight[i];
-            alpha = loadAlpha<NC>(in, i);
+            alpha = loadAlpha<NC>(in, i) * in.aux[i];          // Russian-roulette scale decided by `surface`
             const uint2 hid = hits.id[i];
             const float4 htuv = hits.tuv[i];
             const V3 org(o4.x, o4.y, o4.z), dir(d4.x, d4.y, d4.z);
@@ -352,6 +363,7 @@ materialKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitB
                 flags &= ~(kFlagCameraRay | kFlagPrevDelta);
                 if (dtIsDelta(res.type)) flags |= kFlagPrevDelta;
                 meta.z = hero | (flags << 8) | (pathLength << 16);
+                nImp = specImportance(alpha, hero);
                 alive = true;
             }
         }
@@ -376,6 +388,7 @@ materialKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitB
             out.dir[npos] = make_float4(nDir.x, nDir.y, nDir.z, nPdf);
             out.meta[npos] = meta;
             out.weight[npos] = weight;
+            out.aux[npos] = nImp;
             storeAlpha<NC>(out, npos, alpha);
         }
     }
@@ -411,24 +424,39 @@ struct RenderWorkspace {
 };
 constexpr int kRing = 8;
 
-static void destroyWorkspace(void* w) { delete static_cast<RenderWorkspace*>(w); }
-
 static int allocPathQueue(RenderWorkspace& b, PathQueue* q, uint32_t P, int quarters) {
     int rc;
     if ((rc = b.alloc(&q->org, P))) return rc;
     if ((rc = b.alloc(&q->dir, P))) return rc;
     if ((rc = b.alloc(&q->meta, P))) return rc;
     if ((rc = b.alloc(&q->weight, P))) return rc;
+    if ((rc = b.alloc(&q->aux, P))) return rc;
     if ((rc = b.alloc(&q->alpha, (uint64_t)P * quarters))) return rc;
     q->capacity = P;
     return SLRGPU_OK;
 }
 
-// The queues of a render call live with the scene and are reused by later calls of the same size.
-static int getWorkspace(SlrGpuScene* sc, uint32_t P, RenderWorkspace** out) {
-    RenderWorkspace* w = static_cast<RenderWorkspace*>(sc->workspace);
+// The queues of a render call (about 440 B per path in flight: ~0.9 GB at the default pool) are kept
+// in a process-wide pool, one per device, and reused by later calls of the same shape -- a renderer
+// front end that uploads the scene for every render() call does not pay for them again.
+// slrgpu_release_workspaces() frees the pool.
+static std::mutex g_poolMutex;
+static RenderWorkspace* g_pool[64] = {};
+
+static void releaseWorkspace(int device, RenderWorkspace* w) {
+    std::lock_guard<std::mutex> lock(g_poolMutex);
+    if (device >= 0 && device < 64 && !g_pool[device]) g_pool[device] = w;
+    else delete w;
+}
+
+static int acquireWorkspace(SlrGpuScene* sc, uint32_t P, RenderWorkspace** out) {
+    RenderWorkspace* w = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_poolMutex);
+        if (sc->device >= 0 && sc->device < 64) { w = g_pool[sc->device]; g_pool[sc->device] = nullptr; }
+    }
     if (w && w->capacity == P && w->channels == sc->channels) { *out = w; return SLRGPU_OK; }
-    if (w) { delete w; sc->workspace = nullptr; }
+    delete w;
     w = new (std::nothrow) RenderWorkspace();
     if (!w) { setError("host allocation failed"); return SLRGPU_ERR_OUT_OF_MEMORY; }
     const int quarters = sc->channels == 3 ? 1 : 4;
@@ -447,7 +475,6 @@ static int getWorkspace(SlrGpuScene* sc, uint32_t P, RenderWorkspace** out) {
     if (rc) { delete w; return rc; }
     w->sq.capacity = P; w->cq.capacity = P;
     w->capacity = P; w->channels = sc->channels;
-    sc->workspace = w; sc->destroyWorkspace = destroyWorkspace;
     *out = w;
     return SLRGPU_OK;
 }
@@ -501,8 +528,9 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accum
     rc.recBinWidth = rgb ? 1.0f : 16.0f / (830.0f - 360.0f);
 
     RenderWorkspace* wp = nullptr;
-    int rcode = getWorkspace(sc, P, &wp);
+    int rcode = acquireWorkspace(sc, P, &wp);
     if (rcode) return rcode;
+    struct Release { int device; RenderWorkspace* w; ~Release() { releaseWorkspace(device, w); } } release{sc->device, wp};
     RenderWorkspace& w = *wp;
 
     // grid-stride launches: enough blocks to fill the machine, never more than the queue needs
@@ -617,6 +645,12 @@ static int checkRenderArgs(SlrGpuScene* sc, const SlrGpuRenderParams* p) {
 using namespace slrgpu;
 
 extern "C" {
+
+SLRGPU_API void slrgpu_release_workspaces(void) {
+    std::lock_guard<std::mutex> lock(g_poolMutex);
+    for (int d = 0; d < 64; ++d)
+        if (g_pool[d]) { cudaSetDevice(d); delete g_pool[d]; g_pool[d] = nullptr; }
+}
 
 SLRGPU_API int slrgpu_render_device(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accumDev, void* stream, SlrGpuRenderStats* stats) {
     int rc = checkRenderArgs(sc, p);

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 namespace slrgpu {
 
@@ -38,6 +39,103 @@ static int upload(SlrGpuScene* sc, const T* src, uint64_t count, const T** dst) 
     SLRGPU_CUDA_TRY(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
     *dst = reinterpret_cast<const T*>(p);
     return SLRGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Spectrum compilation (host, once per scene): rewrites the caller's spectrum table into the two
+// forms the device evaluates with a couple of independent loads per wavelength.
+//   UPSAMPLED (u, v, scale)  -> REGULAR, 95 samples on [360, 830] nm: the Meng-Simon evaluation
+//       (SpectrumTypes.h:239-339) is linear in the 3-4 data-point spectra it blends, so blending them
+//       once per spectrum and interpolating the blend is the same piecewise-linear function.
+//   IRREGULAR (n knots)      -> the knots that can bracket a wavelength in [360, 830] (the tables of
+//       spectrum_library.cpp run from 200 nm to 12 um) plus a 2 nm bin -> first-knot look-up table, so
+//       the lower_bound of SpectrumTypes.h:141-160 becomes a table read and at most a step or two.
+// Layout of a compiled IRREGULAR spectrum in spectrum_data: lambdas[n], values[n], lut (kLutBins bytes
+// packed in (kLutBins + 3) / 4 words); num_samples = n.
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int kUpGridW = 12, kUpGridH = 14, kUpNumWl = 95, kUpPointStride = 99;
+constexpr float kWlLow = 360.0f, kWlHigh = 830.0f;
+
+// host twin of spectral.cuh upsampleWeights
+int upsampleWeightsHost(const float* grid, const float* points, float u, float v, uint32_t idx[4], float w[4]) {
+    if (u < 0.0f || u >= kUpGridW || v < 0.0f || v >= kUpGridH) return 0;
+    const int ui = (int)u, vi = (int)v;
+    const float* cell = grid + (ui + kUpGridW * vi) * 8;
+    const bool inside = cell[0] != 0.0f;
+    const int numPoints = (int)cell[1];
+    if (inside) {
+        const float sx = u - ui, ty = v - vi;
+        w[0] = (1 - sx) * (1 - ty); w[1] = sx * (1 - ty); w[2] = (1 - sx) * ty; w[3] = sx * ty;
+        for (int i = 0; i < 4; ++i) idx[i] = (uint32_t)cell[2 + i];
+        return 4;
+    }
+    const uint32_t i0 = (uint32_t)cell[2];
+    const float p0u = points[i0 * kUpPointStride + 2], p0v = points[i0 * kUpPointStride + 3];
+    const float ex = u - p0u, ey = v - p0v;
+    const uint32_t i1 = (uint32_t)cell[3];
+    float e0x = points[i1 * kUpPointStride + 2] - p0u, e0y = points[i1 * kUpPointStride + 3] - p0v;
+    float uu = e0x * ey - ex * e0y;
+    for (int i = 1; i < numPoints; ++i) {
+        const uint32_t id = (uint32_t)cell[2 + (i % (numPoints - 1) + 1)];
+        const float e1x = points[id * kUpPointStride + 2] - p0u, e1y = points[id * kUpPointStride + 3] - p0v;
+        const float vv = ex * e1y - e1x * ey;
+        const float area = e0x * e1y - e1x * e0y;
+        const float bu = uu / area, bv = vv / area, bw = 1.0f - bu - bv;
+        if (bu < -1e-6 || bv < -1e-6 || bw < -1e-6) { uu = -vv; e0x = e1x; e0y = e1y; continue; }
+        w[0] = bu; w[1] = bv; w[2] = bw;
+        idx[0] = id; idx[1] = (uint32_t)cell[2 + i]; idx[2] = i0;
+        return 3;
+    }
+    return 0;
+}
+}  // namespace
+
+static void compileSpectra(const SlrGpuSceneDesc* d, std::vector<SlrGpuSpectrum>& spectra, std::vector<float>& data) {
+    spectra.assign(d->spectra, d->spectra + d->num_spectra);
+    data.assign(d->spectrum_data, d->spectrum_data + d->num_spectrum_floats);
+    for (SlrGpuSpectrum& sp : spectra) {
+        if (sp.kind == SLRGPU_SPECTRUM_UPSAMPLED && d->spectral.upsample_grid && d->spectral.upsample_points) {
+            uint32_t idx[4];
+            float w[4];
+            const int n = upsampleWeightsHost(d->spectral.upsample_grid, d->spectral.upsample_points, sp.p0, sp.p1, idx, w);
+            const uint32_t off = (uint32_t)data.size();
+            for (int b = 0; b < kUpNumWl; ++b) {
+                float ret = 0.0f;
+                for (int j = 0; j < n; ++j) ret += w[j] * d->spectral.upsample_points[idx[j] * kUpPointStride + 4 + b];
+                data.push_back(ret * sp.p2);
+            }
+            sp.kind = SLRGPU_SPECTRUM_REGULAR; sp.data_offset = off; sp.num_samples = kUpNumWl; sp.p0 = kWlLow; sp.p1 = kWlHigh; sp.p2 = 0.0f;
+        } else if (sp.kind == SLRGPU_SPECTRUM_IRREGULAR && sp.num_samples >= 2) {
+            const uint32_t n = sp.num_samples;
+            const std::vector<float> lam(data.begin() + sp.data_offset, data.begin() + sp.data_offset + n);
+            const std::vector<float> val(data.begin() + sp.data_offset + n, data.begin() + sp.data_offset + 2 * n);
+            // keep knots [first, last]: first = last knot <= 360 (or 0), last = first knot >= 830 (or n - 1)
+            uint32_t first = 0, last = n - 1;
+            for (uint32_t i = 0; i < n; ++i) if (lam[i] <= kWlLow) first = i;
+            for (uint32_t i = n; i-- > 0;) if (lam[i] >= kWlHigh) last = i;
+            // a clipped table must clamp like the full one outside its range: an end is only clipped when the
+            // visible range is bracketed on that side
+            if (!(lam[first] <= kWlLow)) first = 0;
+            if (!(lam[last] >= kWlHigh)) last = n - 1;
+            const uint32_t m = last - first + 1;
+            const uint32_t off = (uint32_t)data.size();
+            for (uint32_t i = first; i <= last; ++i) data.push_back(lam[i]);
+            for (uint32_t i = first; i <= last; ++i) data.push_back(val[i]);
+            // lut[b] = lower-interval index for wavelengths in bin b = [360 + 2 b, 360 + 2 (b + 1)): the last knot
+            // index i with lambda[i] < binStart (as max(lower_bound - 1, 0) would give at the bin start)
+            std::vector<uint32_t> words((SLRGPU_SPECTRUM_LUT_BINS + 3) / 4, 0u);
+            for (int b = 0; b < SLRGPU_SPECTRUM_LUT_BINS; ++b) {
+                const float binStart = kWlLow + 2.0f * b;
+                uint32_t lo = 0;
+                while (lo < m && data[off + lo] < binStart) ++lo;            // lower_bound
+                const uint32_t lowIdx = lo > 0 ? lo - 1 : 0;
+                words[b >> 2] |= (lowIdx > 255u ? 255u : lowIdx) << (8 * (b & 3));
+            }
+            for (uint32_t wv : words) { float f; memcpy(&f, &wv, 4); data.push_back(f); }
+            sp.data_offset = off; sp.num_samples = m; sp.kind = SLRGPU_SPECTRUM_IRREGULAR_LUT;
+        }
+    }
 }
 
 }  // namespace slrgpu
@@ -101,8 +199,11 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
     UP(reinterpret_cast<const float4*>(d->vertices), (uint64_t)d->num_vertices * 3, &v.vertices);
     UP(d->materials, d->num_materials, &v.materials);
     UP(d->textures, d->num_textures, &v.textures);
-    UP(d->spectra, d->num_spectra, &v.spectra);
-    UP(d->spectrum_data, d->num_spectrum_floats, &v.spectrumData);
+    std::vector<SlrGpuSpectrum> spectra;
+    std::vector<float> spectrumData;
+    if (d->spectra && d->num_spectra) compileSpectra(d, spectra, spectrumData);
+    UP(spectra.data(), spectra.size(), &v.spectra);
+    UP(spectrumData.data(), spectrumData.size(), &v.spectrumData);
     UP(d->images, d->num_images, &v.images);
     UP(d->image_data, d->image_data_bytes, &v.imageData);
     UP(d->lights, d->num_lights, &v.lights);
@@ -161,7 +262,6 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
 SLRGPU_API void slrgpu_scene_destroy(SlrGpuScene* sc) {
     if (!sc) return;
     cudaSetDevice(sc->device);
-    if (sc->workspace && sc->destroyWorkspace) sc->destroyWorkspace(sc->workspace);
     for (int i = 0; i < sc->numAllocations; ++i) cudaFree(sc->allocations[i]);
     delete sc;
 }

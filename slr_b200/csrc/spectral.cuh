@@ -168,7 +168,25 @@ __device__ __forceinline__ float evalUpsampled(const DeviceScene& s, const Upsam
     return ret * scale;
 }
 
+// compiled irregular spectrum (scene.cu compileSpectra): the bin table gives the interval the reference's
+// lower_bound would find at the start of the wavelength's 2 nm bin; walk forward to the wavelength itself
+__device__ __forceinline__ float evalIrregularLut(const float* __restrict__ lambdas, const float* __restrict__ values, uint32_t n,
+                                                  const uint32_t* __restrict__ lut, float wl) {
+    int b = (int)((wl - kWlLow) * 0.5f);
+    b = min(max(b, 0), SLRGPU_SPECTRUM_LUT_BINS - 1);
+    uint32_t lowIdx = (__ldg(lut + (b >> 2)) >> (8 * (b & 3))) & 0xFFu;
+    // lower_bound(wl) - 1 = last knot strictly below wl
+    while (lowIdx + 1 < n && __ldg(lambdas + lowIdx + 1) < wl) ++lowIdx;
+    if (lowIdx >= n - 1) return __ldg(values + n - 1);
+    const float l0 = __ldg(lambdas + lowIdx), l1 = __ldg(lambdas + lowIdx + 1);
+    const float t = (wl - l0) / (l1 - l0);
+    if (t <= 0.0f) return __ldg(values);
+    return (1 - t) * __ldg(values + lowIdx) + t * __ldg(values + lowIdx + 1);
+}
+
 // Evaluates input spectrum `id` at the path's wavelengths (or returns the RGB triple in RGB mode).
+// The table was compiled at scene creation: up-sampled spectra arrive as REGULAR, irregular ones with
+// their look-up table; the other kinds are evaluated as the reference does.
 template <int NC>
 __device__ __noinline__ Spec<NC> evalInputSpectrum(const DeviceScene& s, uint32_t id, float wlOffset) {
     const SlrGpuSpectrum sp = s.spectra[id];
@@ -181,15 +199,21 @@ __device__ __noinline__ Spec<NC> evalInputSpectrum(const DeviceScene& s, uint32_
         const float* vals = s.spectrumData + sp.data_offset;
 #pragma unroll
         for (int i = 0; i < NC; ++i) out.v[i] = evalRegular(vals, sp.num_samples, sp.p0, sp.p1, wavelengthOf(i, wlOffset));
+    } else if (sp.kind == SLRGPU_SPECTRUM_IRREGULAR_LUT) {
+        const float* lam = s.spectrumData + sp.data_offset;
+        const float* vals = lam + sp.num_samples;
+        const uint32_t* lut = reinterpret_cast<const uint32_t*>(vals + sp.num_samples);
+#pragma unroll 4
+        for (int i = 0; i < NC; ++i) out.v[i] = evalIrregularLut(lam, vals, sp.num_samples, lut, wavelengthOf(i, wlOffset));
     } else if (sp.kind == SLRGPU_SPECTRUM_IRREGULAR) {
         const float* lam = s.spectrumData + sp.data_offset;
         const float* vals = lam + sp.num_samples;
         uint32_t base = 0;
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < NC; ++i) out.v[i] = evalIrregular(lam, vals, sp.num_samples, wavelengthOf(i, wlOffset), &base);
     } else {
         const UpsampleWeights w = upsampleWeights(s, sp.p0, sp.p1);
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < NC; ++i) out.v[i] = evalUpsampled(s, w, sp.p2, wavelengthOf(i, wlOffset));
     }
     return out;

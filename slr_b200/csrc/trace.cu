@@ -18,45 +18,45 @@ __device__ __forceinline__ void addTraversalCounts(const TraversalCounters& cnt,
     if ((threadIdx.x & 31) == 0) { atomicAdd(nodes, (unsigned long long)n); atomicAdd(leafRecords, (unsigned long long)t); }
 }
 
+struct PathRaySource {
+    PathQueue q;
+    __device__ __forceinline__ void load(uint32_t i, Ray& r) const {
+        const float4 o = q.org[i], d = q.dir[i];
+        r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = o.w;
+        r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = INFINITY;
+    }
+};
+struct HitSink {
+    HitBuffer hits;
+    __device__ __forceinline__ void done(uint32_t i, const WalkState& w, const TraversalCounters&) const {
+        hits.id[i] = make_uint2(w.hit.prim, w.hit.inst);
+        hits.tuv[i] = make_float4(w.hit.t, w.hit.u, w.hit.v, 0.0f);
+    }
+};
+
 template <bool INSTANCES, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock)
 extendKernel(const DeviceScene s, PathQueue q, HitBuffer hits, WavefrontCounters* counters) {
-    const uint32_t n = counters->numPaths;
     TraversalCounters cnt = {0, 0};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 o = q.org[i], d = q.dir[i];
-        Ray r;
-        r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = o.w;
-        r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = INFINITY;
-        Hit h;
-        h.prim = SLRGPU_INVALID_ID; h.inst = SLRGPU_INVALID_ID; h.t = INFINITY; h.u = 0.0f; h.v = 0.0f;
-        uint32_t stack[kStackSize];
-        bool overflow = false;
-        traverse<INSTANCES ? 0 : 1, false, COUNT>(s, 0, r, h, stack, 0, cnt, overflow);
-        hits.id[i] = make_uint2(h.prim, h.inst);
-        hits.tuv[i] = make_float4(h.t, h.u, h.v, 0.0f);
-        if (overflow) atomicExch(&counters->stackOverflow, 1u);
-    }
+    bool overflow = false;
+    walkQueue<INSTANCES, false, COUNT>(s, counters->numPaths, &counters->extendCursor, PathRaySource{q}, HitSink{hits}, cnt, overflow);
+    if (overflow) atomicExch(&counters->stackOverflow, 1u);
     if (COUNT) addTraversalCounts(cnt, &counters->extendNodes, &counters->extendLeafRecords);
 }
 
-template <bool INSTANCES, int NC, bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock)
-shadowKernel(const DeviceScene s, ShadowQueue q, float* __restrict__ accum, WavefrontCounters* counters) {
-    const uint32_t n = counters->numShadow;
-    TraversalCounters cnt = {0, 0};
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+struct ShadowRaySource {
+    ShadowQueue q;
+    __device__ __forceinline__ void load(uint32_t i, Ray& r) const {
         const float4 o = q.org[i], d = q.dir[i];
-        Ray r;
         r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = o.w;
         r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = d.w;
-        Hit h;
-        h.prim = SLRGPU_INVALID_ID; h.inst = SLRGPU_INVALID_ID; h.t = INFINITY; h.u = h.v = 0.0f;
-        uint32_t stack[kStackSize];
-        bool overflow = false;
-        const bool occluded = traverse<INSTANCES ? 0 : 1, true, COUNT>(s, 0, r, h, stack, 0, cnt, overflow);
-        if (overflow) atomicExch(&counters->stackOverflow, 1u);
-        if (occluded) continue;
+    }
+};
+template <int NC> struct SplatSink {
+    ShadowQueue q;
+    float* accum;
+    __device__ __forceinline__ void done(uint32_t i, const WalkState& w, const TraversalCounters&) const {
+        if (w.found) return;         // occluded
         const uint2 pw = q.pixelWl[i];
         float v[NC == 3 ? 4 : NC];
         constexpr int Q = (NC + 3) / 4;
@@ -70,6 +70,15 @@ shadowKernel(const DeviceScene s, ShadowQueue q, float* __restrict__ accum, Wave
         }
         splat<NC>(accum, pw.x & 0x7FFFFFFFu, __uint_as_float(pw.y), (pw.x >> 31) != 0, v);
     }
+};
+
+template <bool INSTANCES, int NC, bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock)
+shadowKernel(const DeviceScene s, ShadowQueue q, float* __restrict__ accum, WavefrontCounters* counters) {
+    TraversalCounters cnt = {0, 0};
+    bool overflow = false;
+    walkQueue<INSTANCES, true, COUNT>(s, counters->numShadow, &counters->shadowCursor, ShadowRaySource{q}, SplatSink<NC>{q, accum}, cnt, overflow);
+    if (overflow) atomicExch(&counters->stackOverflow, 1u);
     if (COUNT) addTraversalCounts(cnt, &counters->shadowNodes, &counters->shadowLeafRecords);
 }
 

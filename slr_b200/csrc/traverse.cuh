@@ -201,4 +201,180 @@ __device__ bool traverse(const DeviceScene& s, uint32_t root, Ray& r, Hit& hit, 
     return found;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative scheduling of many rays over the traversal above ("persistent threads with
+// dynamic fetch"): a ray's traversal length varies from a handful to dozens of node visits, so with
+// one ray per lane per loop iteration most lanes of a warp wait for its slowest ray (ncu on the
+// first version: 7.5 of 32 threads active per instruction). Here a lane that finishes its ray takes
+// the next one from the warp's chunk while the other lanes keep walking; chunks of 32..256 rays are
+// handed to warps through one global cursor. Per ray the sequence of operations is exactly the
+// reference's (same pops, same box tests, same leaf order): only the interleaving ACROSS rays changes.
+//
+// The top-level walk is a per-lane state machine (one node visit per step); an instance leaf record
+// runs the nested traversal to completion inside the step (traverse<1>), as the reference's recursion does.
+// (A "while-while" split into separate node and leaf phases was measured too -- round 1, profiles/ --
+// and was slower on both benchmarks: rays here are short, the extra state and ballots cost more than
+// the leaf-phase coherence returns.)
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kMaxChunk = 256;
+constexpr int kStepsPerRound = 4;
+
+struct WalkState {
+    Ray r;
+    Hit hit;
+    float ix, iy, iz;
+    uint32_t pos;
+    int sp;
+    bool found;
+    TraversalCounters cnt0;      // the lane's running counters when this ray started (per-ray counts = difference)
+};
+
+__device__ __forceinline__ void walkBegin(WalkState& w, uint32_t* stack) {
+    w.ix = 1.0f / w.r.dx; w.iy = 1.0f / w.r.dy; w.iz = 1.0f / w.r.dz;
+    w.pos = (w.r.dx >= 0.0f ? 1u : 0u) | (w.r.dy >= 0.0f ? 2u : 0u) | (w.r.dz >= 0.0f ? 4u : 0u);
+    w.hit.prim = SLRGPU_INVALID_ID; w.hit.inst = SLRGPU_INVALID_ID; w.hit.t = INFINITY; w.hit.u = 0.0f; w.hit.v = 0.0f;
+    w.found = false;
+    w.sp = 0;
+    stack[w.sp++] = 0;      // the top-level root is node 0
+}
+
+// One node visit of the top-level walk: pop, 4-box test, push the inner children that were hit (far to
+// near), test the leaf children that were hit immediately (near to far). Returns true when the ray is finished.
+template <bool INSTANCES, bool ANY_HIT, bool COUNT>
+__device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, uint32_t* stack, TraversalCounters& cnt, bool& overflow) {
+    Ray& r = w.r;
+    const uint32_t nodeIdx = stack[--w.sp];
+    const float4* n = s.nodes + (size_t)nodeIdx * 8;
+    const float4 lox = ldg4(n + 0), loy = ldg4(n + 1), loz = ldg4(n + 2);
+    const float4 hix = ldg4(n + 3), hiy = ldg4(n + 4), hiz = ldg4(n + 5);
+    if (COUNT) ++cnt.nodes;
+    const uint32_t mask = slab4(lox, loy, loz, hix, hiy, hiz, r, w.ix, w.iy, w.iz);
+    if (mask != 0) {
+        const uint4 kids = __ldg(reinterpret_cast<const uint4*>(n + 6));
+        const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(n + 7));
+        const uint32_t T = (w.pos >> (axes & 0xFF)) & 1u;
+        const uint32_t L = (w.pos >> ((axes >> 8) & 0xFF)) & 1u;
+        const uint32_t R = (w.pos >> ((axes >> 16) & 0xFF)) & 1u;
+        // visiting order (OrderTable, QBVH.h:309-312): near side pair first, near child first inside a pair
+        const uint32_t l0 = L ? 0u : 1u, r0 = R ? 2u : 3u;
+        uint32_t order[4];
+        order[0] = T ? l0 : r0;        order[1] = T ? (l0 ^ 1u) : (r0 ^ 1u);
+        order[2] = T ? r0 : l0;        order[3] = T ? (r0 ^ 1u) : (l0 ^ 1u);
+        uint32_t ch[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t lane = order[i];
+            uint32_t c = lane == 0 ? kids.x : lane == 1 ? kids.y : lane == 2 ? kids.z : kids.w;
+            ch[i] = ((mask >> lane) & 1u) ? c : kEmptyChild;
+        }
+#pragma unroll
+        for (int i = 3; i >= 0; --i) {
+            const uint32_t c = ch[i];
+            if (c == kEmptyChild || (c >> 31)) continue;
+            if (w.sp >= kStackSize) { overflow = true; continue; }
+            stack[w.sp++] = c & 0x07FFFFFFu;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t c = ch[i];
+            if (c == kEmptyChild || !(c >> 31)) continue;
+            const uint32_t first = c & 0x07FFFFFFu;
+            const uint32_t count = (c >> 27) & 0xFu;
+            for (uint32_t j = 0; j < count; ++j) {
+                const float4* rec = s.leaves + (size_t)(first + j) * 3;
+                const float4 a = ldg4(rec);
+                const uint32_t id = __float_as_uint(a.w);
+                if (COUNT) ++cnt.tris;
+                if (id & 0x80000000u) {
+                    if constexpr (INSTANCES) {
+                        const uint32_t instId = id & 0x7FFFFFFFu;
+                        const SlrGpuInstance* inst = s.instances + instId;
+                        Ray lr;
+                        mulPoint(inst->mat_inv, r.ox, r.oy, r.oz, &lr.ox, &lr.oy, &lr.oz);
+                        mulVector(inst->mat_inv, r.dx, r.dy, r.dz, &lr.dx, &lr.dy, &lr.dz);
+                        lr.tmin = r.tmin; lr.tmax = r.tmax;
+                        if (traverse<1, ANY_HIT, COUNT>(s, inst->root_node, lr, w.hit, stack, w.sp, cnt, overflow)) {
+                            r.tmax = lr.tmax;
+                            w.hit.inst = instId;
+                            w.found = true;
+                            if (ANY_HIT) return true;
+                        }
+                    }
+                    continue;
+                }
+                const float4 b = ldg4(rec + 1), cc = ldg4(rec + 2);
+                float t, b0, b1;
+                if (triangleTest(a, b, cc, r, &t, &b0, &b1)) {
+                    r.tmax = t;
+                    w.hit.prim = id; w.hit.inst = SLRGPU_INVALID_ID;
+                    w.hit.t = t; w.hit.u = b0; w.hit.v = b1;
+                    w.found = true;
+                    if (ANY_HIT) return true;
+                }
+            }
+        }
+    }
+    return w.sp == 0;
+}
+
+// Runs `n` rays through the scene with one warp-cooperative loop. Source::load(i, Ray&) fetches ray i,
+// Sink::done(i, state) consumes its result. *cursor must be 0 at launch.
+template <bool INSTANCES, bool ANY_HIT, bool COUNT, typename Source, typename Sink>
+__device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint32_t* cursor, const Source& source, const Sink& sink,
+                                          TraversalCounters& cnt, bool& overflow) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t stack[kStackSize];
+    WalkState w;
+    bool active = false;
+    uint32_t idx = 0;
+    uint32_t chunkNext = 0, chunkEnd = 0;       // warp-uniform
+    bool exhausted = false;                     // warp-uniform
+    // chunk size: about half a warp's fair share of the batch, so that every warp of the grid gets work
+    // (small batches: one ray per lane, like a plain launch) and the tail of the batch stays short
+    const uint32_t totalWarps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t chunk = 32;
+    while (chunk < kMaxChunk && (unsigned long long)chunk * 2ull * totalWarps <= (unsigned long long)n / 2ull) chunk <<= 1;
+    while (true) {
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+        const int numIdle = __popc(idle);
+        // refill when a quarter of the warp is idle (or nothing is running)
+        if (!exhausted && (numIdle >= 8)) {
+            if (chunkNext >= chunkEnd) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(cursor, chunk);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                chunkNext = base;
+                chunkEnd = base < n ? min(base + chunk, n) : base;
+                if (base >= n) exhausted = true;
+            }
+            if (!exhausted) {
+                const uint32_t avail = chunkEnd - chunkNext;
+                const uint32_t rank = __popc(idle & lt);
+                if (!active && rank < avail) {
+                    idx = chunkNext + rank;
+                    source.load(idx, w.r);
+                    walkBegin(w, stack);
+                    w.cnt0 = cnt;
+                    active = true;
+                }
+                chunkNext += min((uint32_t)numIdle, avail);
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) {
+            if (exhausted) break;
+            continue;
+        }
+#pragma unroll 1
+        for (int it = 0; it < kStepsPerRound; ++it) {
+            if (active) {
+                if (walkStep<INSTANCES, ANY_HIT, COUNT>(s, w, stack, cnt, overflow)) {
+                    sink.done(idx, w, cnt);
+                    active = false;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace slrgpu

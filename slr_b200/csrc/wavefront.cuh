@@ -8,10 +8,11 @@
 //               dir[i]   = (ray direction xyz, pdf the direction was sampled with)   16 B
 //               meta[i]  = (pixel, global sample index, hero | flags<<8 | pathLength<<16, bits(wavelength offset))  16 B
 //               weight[i]= camera-sample weight (Job::kernel, PathTracingRenderer.cpp:126)  4 B
+//               aux[i]   = importance(alpha), then the Russian-roulette scale                4 B
 //               alpha[q*P + i], q < NC/4 = path throughput, four components per 16 B load   64 B (16 B in RGB mode)
 //   HitBuffer   id[i] = (prim, inst), tuv[i] = (t, b0, b1, -)                 24 B
 //   ShadowQueue org/dir (distMin / distMax in .w), pixel+wavelength offset, contribution[q*P + i]   108 B
-// S_state = 116 B per path per stage transition in spectral mode.
+// S_state = 120 B per path per stage transition in spectral mode.
 #pragma once
 #include "device_scene.h"
 
@@ -24,6 +25,8 @@ struct PathQueue {
     float4* dir;
     uint4* meta;
     float* weight;
+    float* aux;            // written by the stage that produced the entry: importance(alpha) (the Russian-roulette
+                           // probability of the next hit); overwritten by `surface` with the roulette scale 1/q
     float4* alpha;
     uint32_t capacity;     // stride of the alpha quarters
 };
@@ -62,6 +65,8 @@ struct WavefrontCounters {
     unsigned long long extendRays, shadowRays;
     unsigned long long extendNodes, extendLeafRecords, shadowNodes, shadowLeafRecords;   // only counted by the profiling variants
     uint32_t waves, done;
+    uint32_t genPass, genOffset;                  // pass / pixel-order position of the next camera sample
+    uint32_t extendCursor, shadowCursor;          // chunk cursors of the warp-cooperative ray kernels (zero at launch)
 };
 
 // One entry of a material-class queue: position in the current path queue + the leaf material id.

@@ -75,6 +75,7 @@ void GPUPathTracingRenderer::render(const RenderScene& scene, const RenderSettin
     const uint32_t W = (uint32_t)settings.getInt(RenderSettingItem::ImageWidth);
     const uint32_t H = (uint32_t)settings.getInt(RenderSettingItem::ImageHeight);
 
+    lastStatistics = RenderStatistics();
     SlrGpuSceneDesc desc;
     scene.flat.describe(&desc);
     SlrGpuScene* gpu = nullptr;
@@ -94,7 +95,21 @@ void GPUPathTracingRenderer::render(const RenderScene& scene, const RenderSettin
     p.rng_seed = settings.getInt(RenderSettingItem::RNGSeed);
     const float brightness = settings.getFloat(RenderSettingItem::Brightness);
 
-    lastStatistics = RenderStatistics();
+    if (!exportProgressiveImages) {
+        // one GPU call for the whole sample range, straight into the sensor
+        p.spp_begin = 0; p.spp_end = m_samplesPerPixel;
+        SlrGpuRenderStats st;
+        if (slrgpu_render(gpu, &p, sensor->data(), &st) != SLRGPU_OK) {
+            std::string msg = std::string("slrgpu_render failed: ") + slrgpu_last_error();
+            slrgpu_scene_destroy(gpu);
+            throw std::runtime_error(msg);
+        }
+        lastStatistics.paths = st.paths; lastStatistics.rays = st.rays;
+        lastStatistics.deviceSeconds = st.device_ms * 1e-3;
+        slrgpu_scene_destroy(gpu);
+        lastStatistics.wallSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+        return;
+    }
     std::vector<float> pass((size_t)W * H * channels);
     // Progressive export cadence of the reference: an image after 1, 2, 4, ... samples (at most 16
     // images, PathTracingRenderer.cpp:63-65,83-94). Each segment [begin, end) is one GPU render call.

@@ -98,6 +98,7 @@ def main(args, rank, world):
     import torch
     import bench
     from . import capi
+    from .distributed import reduce_frame, sample_range
 
     dist = None
     if world > 1:
@@ -106,13 +107,15 @@ def main(args, rank, world):
     dev = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(dev)
     path, w, h, spp, desc = _scene(args)
-    hs = capi.read_scene(path)
+    with capi.stdout_to_stderr():
+        hs = capi.read_scene(path)
     gs = capi.GpuScene(hs, device=dev)
     chan = capi.gpu.slrgpu_scene_channels(gs.handle)
     accum = torch.zeros((h, w, chan), dtype=torch.float32, device="cuda")
     stream = torch.cuda.current_stream()
     seed = 1509761209
-    params = capi.RenderParams(C.sizeof(capi.RenderParams), w, h, spp * rank, spp * (rank + 1), 0.0, 0.0, seed, 0,
+    spp_begin, spp_end = sample_range(rank, world, spp, "weak")
+    params = capi.RenderParams(C.sizeof(capi.RenderParams), w, h, spp_begin, spp_end, 0.0, 0.0, seed, 0,
                                getattr(args, "pool", 0) or 0, 0)
 
     def frame(flags=0):
@@ -123,8 +126,7 @@ def main(args, rank, world):
                                            C.c_void_p(stream.cuda_stream), C.byref(st))
         if rc != 0:
             raise RuntimeError(capi.gpu.slrgpu_last_error().decode())
-        if dist is not None:
-            dist.reduce(accum, dst=0)
+        reduce_frame(accum, dist)
         return st
 
     # one profiled, untimed frame: stage times and the traversal counts of the algorithmic-bytes model
@@ -162,8 +164,12 @@ def main(args, rank, world):
         for _ in range(e2e_steps):
             img, hst = capi.host_render(hs, w, h, spp, seed, dev)
         e2e_s = (time.perf_counter() - t0) / e2e_steps
+        e2e_detail = {"wall_ms": round(1e3 * e2e_s, 2), "renderer_wall_ms": round(1e3 * hst["wall_s"], 2),
+                      "scene_upload_ms": round(1e3 * hst["upload_s"], 2), "device_ms": round(1e3 * hst["device_s"], 2),
+                      "c_call_ms": round(1e3 * hst["call_s"], 2)}
     else:
         pinned = torch.empty((h, w, chan), dtype=torch.float32).pin_memory()
+        e2e_detail = None
 
         def e2e_frame():
             g2 = capi.GpuScene(hs, device=dev)
@@ -173,7 +179,7 @@ def main(args, rank, world):
                                                C.c_void_p(stream.cuda_stream), C.byref(st2))
             if rc != 0:
                 raise RuntimeError(capi.gpu.slrgpu_last_error().decode())
-            dist.reduce(accum, dst=0)
+            reduce_frame(accum, dist)
             if rank == 0:
                 pinned.copy_(accum, non_blocking=False)
             torch.cuda.synchronize()
@@ -237,7 +243,7 @@ def main(args, rank, world):
                          "note": "algorithmic bytes of all launches of the kernel in one frame / its summed device time"},
             "cpu_baseline": cpu,
             "e2e": {"value": paths_per_step * world / e2e_s / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": scene_bytes,
-                    "d2h_bytes_per_step": accum_bytes},
+                    "d2h_bytes_per_step": accum_bytes, "breakdown": e2e_detail},
             "gpu_launches": int(launches), "clocks": clocks.summary()}
     print(json.dumps(line))
     if dist is not None:

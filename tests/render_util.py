@@ -62,7 +62,7 @@ def block_means(img, block):
     return np.asarray(img[:hb * block, :wb * block], np.float64).reshape(hb, block, wb, block, c).mean((1, 3))
 
 
-def block_rel_rmse(img, ref, block):
+def block_rel_rmse(img, ref, block, trim=0.0):
     """rel_rmse of block x block averages: Monte-Carlo noise shrinks by `block`, systematic
     differences (a wrong BSDF, a missing light path) do not."""
-    return rel_rmse(block_means(img, block), block_means(ref, block))
+    return rel_rmse(block_means(img, block), block_means(ref, block), trim)
