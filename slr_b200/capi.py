@@ -147,7 +147,7 @@ def _load(name):
     return C.CDLL(path, mode=C.RTLD_GLOBAL)
 
 
-gpu = _load("libslrgpu.so")
+gpu = _load(os.environ.get("SLRGPU_LIB", "libslrgpu.so"))      # SLRGPU_LIB: tuning variants built by csrc/Makefile VARIANT=
 host = _load("libslrhost.so")
 
 # ---- slrgpu.h prototypes

@@ -24,6 +24,13 @@ namespace slrgpu {
 constexpr int kSurfaceBlock = 128;
 constexpr int kMaterialBlock = 128;
 constexpr int kRaygenBlock = 128;
+// resident blocks per SM the register allocation of the shade kernels is bounded for (tuning knobs, see profiles/)
+#ifndef SLR_MATERIAL_MIN_BLOCKS
+#define SLR_MATERIAL_MIN_BLOCKS 1
+#endif
+#ifndef SLR_SURFACE_MIN_BLOCKS
+#define SLR_SURFACE_MIN_BLOCKS 1
+#endif
 
 // position of `alive` lanes in an output queue: one atomic per warp
 __device__ __forceinline__ uint32_t warpAppend(bool alive, uint32_t* counter) {
@@ -134,7 +141,8 @@ __global__ void beginWaveKernel(const RenderConstants rc, WavefrontCounters* cou
 }
 
 // after shadow: the next queue becomes the current one (single thread)
-__global__ void endWaveKernel(WavefrontCounters* counters) {
+// `ring` is pinned host memory (device-visible through UVA): the snapshot the host polls
+__global__ void endWaveKernel(WavefrontCounters* counters, WavefrontCounters* ring, uint32_t ringSize) {
     counters->shadowRays += counters->numShadow;
     counters->numPaths = counters->numNext;
     counters->numNext = 0;
@@ -142,8 +150,11 @@ __global__ void endWaveKernel(WavefrontCounters* counters) {
     for (int c = 0; c < 16; ++c) counters->classCount[c] = 0;
     counters->extendCursor = 0;
     counters->shadowCursor = 0;
-    counters->waves += 1;
     counters->done = (counters->numPaths == 0 && counters->generated == counters->total) ? 1u : 0u;
+    const uint32_t slot = counters->waves % ringSize;
+    counters->waves += 1;
+    ring[slot] = *counters;
+    __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -153,7 +164,7 @@ __global__ void endWaveKernel(WavefrontCounters* counters) {
 // sorted into one queue per material class.
 // ---------------------------------------------------------------------------------------------
 template <int NC>
-__global__ void __launch_bounds__(kSurfaceBlock)
+__global__ void __launch_bounds__(kSurfaceBlock, SLR_SURFACE_MIN_BLOCKS)
 surfaceKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitBuffer hits, ClassQueue cq,
               float* __restrict__ accum, WavefrontCounters* counters) {
     const uint32_t n = counters->numPaths;
@@ -271,7 +282,7 @@ template <int NC> struct HitBsdf<NC, SC_GENERIC> {
 };
 
 template <int NC, int CLASS>
-__global__ void __launch_bounds__(kMaterialBlock)
+__global__ void __launch_bounds__(kMaterialBlock, SLR_MATERIAL_MIN_BLOCKS)
 materialKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitBuffer hits, ClassQueue cq, PathQueue out, ShadowQueue sq,
                WavefrontCounters* counters) {
     const uint32_t n = counters->classCount[CLASS];
@@ -406,10 +417,30 @@ struct RenderWorkspace {
     ShadowQueue sq;
     ClassQueue cq;
     WavefrontCounters* dCounters = nullptr;
-    WavefrontCounters* hCounters = nullptr;      // pinned ring of kRing snapshots
+    WavefrontCounters* hCounters = nullptr;      // pinned ring of kRing snapshots, written by endWaveKernel
     cudaEvent_t ringEvents[8] = {};
+    // frame buffer of the host-buffer entry point (slrgpu_render) and its pinned staging copy
+    float* frame = nullptr;
+    float* frameHost = nullptr;
+    size_t frameBytes = 0;
+    cudaStream_t stream = nullptr;               // non-blocking stream of the host-buffer entry point (graph capture needs one)
+    int ensureFrame(size_t bytes) {
+        if (frame && frameBytes >= bytes) return SLRGPU_OK;
+        if (frame) cudaFree(frame);
+        if (frameHost) cudaFreeHost(frameHost);
+        frame = nullptr; frameHost = nullptr; frameBytes = 0;
+        cudaError_t e = cudaMalloc(&frame, bytes);
+        if (e != cudaSuccess) return cudaFail(e, "cudaMalloc(frame buffer)");
+        e = cudaMallocHost(&frameHost, bytes);
+        if (e != cudaSuccess) { cudaFree(frame); frame = nullptr; return cudaFail(e, "cudaMallocHost(frame staging)"); }
+        frameBytes = bytes;
+        return SLRGPU_OK;
+    }
     ~RenderWorkspace() {
         for (int i = 0; i < n; ++i) cudaFree(ptrs[i]);
+        if (frame) cudaFree(frame);
+        if (frameHost) cudaFreeHost(frameHost);
+        if (stream) cudaStreamDestroy(stream);
         if (hCounters) cudaFreeHost(hCounters);
         for (cudaEvent_t e : ringEvents) if (e) cudaEventDestroy(e);
     }
@@ -472,6 +503,7 @@ static int acquireWorkspace(SlrGpuScene* sc, uint32_t P, RenderWorkspace** out) 
     if (!rc) rc = w->alloc(&w->dCounters, 1);
     if (!rc) { cudaError_t e = cudaMallocHost(&w->hCounters, sizeof(WavefrontCounters) * kRing); if (e != cudaSuccess) rc = cudaFail(e, "cudaMallocHost"); }
     for (int k = 0; k < kRing && !rc; ++k) { cudaError_t e = cudaEventCreateWithFlags(&w->ringEvents[k], cudaEventDisableTiming); if (e != cudaSuccess) rc = cudaFail(e, "cudaEventCreate"); }
+    if (!rc) { cudaError_t e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking); if (e != cudaSuccess) rc = cudaFail(e, "cudaStreamCreate"); }
     if (rc) { delete w; return rc; }
     w->sq.capacity = P; w->cq.capacity = P;
     w->capacity = P; w->channels = sc->channels;
@@ -501,15 +533,20 @@ static void launchShadeStage(const SlrGpuScene* sc, const RenderConstants& rc, c
     if (m & (1u << SC_GENERIC)) launchMaterial<NC, SC_GENERIC>(sc, rc, w, cur, grid, stream);
 }
 
-static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accumDev, cudaStream_t stream, SlrGpuRenderStats* stats) {
+static uint32_t poolCapacity(const SlrGpuRenderParams* p) {
+    const unsigned long long totalSamples = (unsigned long long)p->width * p->height * (p->spp_end - p->spp_begin);
+    uint32_t P = p->pool_size ? p->pool_size : (1u << 21);
+    if ((unsigned long long)P > totalSamples) P = (uint32_t)totalSamples;
+    P = (P + 127u) & ~127u;
+    return P == 0 ? 128u : P;
+}
+
+static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorkspace& w, float* accumDev, cudaStream_t stream, SlrGpuRenderStats* stats) {
     const bool rgb = sc->channels == 3;
     const uint32_t W = p->width, H = p->height;
     const unsigned long long numPixels = (unsigned long long)W * H;
     const unsigned long long totalSamples = numPixels * (p->spp_end - p->spp_begin);
-    uint32_t P = p->pool_size ? p->pool_size : (1u << 21);
-    if ((unsigned long long)P > totalSamples) P = (uint32_t)totalSamples;
-    P = (P + 127u) & ~127u;
-    if (P == 0) P = 128;
+    const uint32_t P = w.capacity;
 
     RenderConstants rc;
     memset(&rc, 0, sizeof(rc));
@@ -527,11 +564,7 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accum
     rc.selectWLPDF = rgb ? 1.0f : 16.0f / (830.0f - 360.0f);
     rc.recBinWidth = rgb ? 1.0f : 16.0f / (830.0f - 360.0f);
 
-    RenderWorkspace* wp = nullptr;
-    int rcode = acquireWorkspace(sc, P, &wp);
-    if (rcode) return rcode;
-    struct Release { int device; RenderWorkspace* w; ~Release() { releaseWorkspace(device, w); } } release{sc->device, wp};
-    RenderWorkspace& w = *wp;
+    int rcode = SLRGPU_OK;
 
     // grid-stride launches: enough blocks to fill the machine, never more than the queue needs
     int numSMs = 148;
@@ -569,48 +602,70 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accum
     SLRGPU_CUDA_TRY(cudaMemcpyAsync(w.dCounters, &w.hCounters[0], sizeof(WavefrontCounters), cudaMemcpyHostToDevice, stream));
     SLRGPU_CUDA_TRY(cudaStreamSynchronize(stream));
 
-    // Waves are enqueued without waiting for their counts; after each wave a snapshot of the counters
-    // goes to a pinned ring, and the host reads the snapshot kLag waves back to learn when the work
-    // ran out (the waves enqueued in between find empty queues and cost a few microseconds each).
-    constexpr int kLag = 3;
+    // Waves are enqueued without waiting for their counts; endWaveKernel leaves a snapshot of the loop
+    // state in a pinned ring and the host reads the snapshot of the wave pair enqueued kLag rounds ago
+    // to learn when the work ran out (waves enqueued in between find empty queues and cost a few
+    // microseconds). Outside profiling two waves (one ping + one pong of the path queues) are captured
+    // into a CUDA graph once per call and replayed: one driver call per ~20 kernel launches.
+    constexpr int kLag = 2;
     const uint32_t launchesPerWave = 6u + (uint32_t)__builtin_popcount(sc->classMask);
-    unsigned long long wave = 0, launches = 0;
-    int cur = 0;
-    WavefrontCounters last = init;
-    while (true) {
+    unsigned long long wave = 0, launches = 0, round = 0;
+    auto enqueueWave = [&](int cur) -> int {
         timer.mark(0);
         if (rgb) raygenKernel<3><<<grid, kRaygenBlock, 0, stream>>>(sc->dev, rc, w.q[cur], w.dCounters);
         else raygenKernel<16><<<grid, kRaygenBlock, 0, stream>>>(sc->dev, rc, w.q[cur], w.dCounters);
         beginWaveKernel<<<1, 1, 0, stream>>>(rc, w.dCounters);
         timer.mark(0);
         timer.mark(1);
-        if ((rcode = launchExtend(sc, w.q[cur], w.hits, w.dCounters, profile, grid, stream))) return rcode;
+        int r = launchExtend(sc, w.q[cur], w.hits, w.dCounters, profile, grid, stream);
+        if (r) return r;
         timer.mark(1);
         timer.mark(2);
         if (rgb) launchShadeStage<3>(sc, rc, w, cur, accumDev, grid, stream);
         else launchShadeStage<16>(sc, rc, w, cur, accumDev, grid, stream);
         timer.mark(2);
         timer.mark(3);
-        if ((rcode = launchShadow(sc, w.sq, accumDev, w.dCounters, profile, grid, stream))) return rcode;
-        endWaveKernel<<<1, 1, 0, stream>>>(w.dCounters);
+        if ((r = launchShadow(sc, w.sq, accumDev, w.dCounters, profile, grid, stream))) return r;
+        endWaveKernel<<<1, 1, 0, stream>>>(w.dCounters, w.hCounters, (uint32_t)kRing);
         timer.mark(3);
-        SLRGPU_CUDA_TRY(cudaGetLastError());
-        const int slot = (int)(wave % kRing);
-        SLRGPU_CUDA_TRY(cudaMemcpyAsync(&w.hCounters[slot], w.dCounters, sizeof(WavefrontCounters), cudaMemcpyDeviceToHost, stream));
-        SLRGPU_CUDA_TRY(cudaEventRecord(w.ringEvents[slot], stream));
-        launches += launchesPerWave;
-        cur ^= 1;
-        ++wave;
-        if (wave >= (unsigned long long)kLag) {
-            const int back = (int)((wave - kLag) % kRing);
-            SLRGPU_CUDA_TRY(cudaEventSynchronize(w.ringEvents[back]));
-            last = w.hCounters[back];
+        return SLRGPU_OK;
+    };
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graphExec = nullptr;
+    struct GraphFree { cudaGraph_t* g; cudaGraphExec_t* e; ~GraphFree() { if (*e) cudaGraphExecDestroy(*e); if (*g) cudaGraphDestroy(*g); } } graphFree{&graph, &graphExec};
+    if (!profile) {
+        if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            int r0 = enqueueWave(0);
+            int r1 = r0 ? r0 : enqueueWave(1);
+            cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+            if (r1) return r1;
+            if (ce == cudaSuccess && graph) { if (cudaGraphInstantiate(&graphExec, graph, 0) != cudaSuccess) graphExec = nullptr; }
+        }
+        cudaGetLastError();     // a failed capture falls back to plain launches
+    }
+    WavefrontCounters last = init;
+    while (true) {
+        if (graphExec) { SLRGPU_CUDA_TRY(cudaGraphLaunch(graphExec, stream)); }
+        else {
+            if ((rcode = enqueueWave(0))) return rcode;
+            if ((rcode = enqueueWave(1))) return rcode;
+            SLRGPU_CUDA_TRY(cudaGetLastError());
+        }
+        wave += 2;
+        launches += 2 * launchesPerWave;
+        SLRGPU_CUDA_TRY(cudaEventRecord(w.ringEvents[round % kRing], stream));
+        ++round;
+        if (round >= (unsigned long long)kLag) {
+            const unsigned long long back = round - kLag;             // round whose two waves are now complete
+            SLRGPU_CUDA_TRY(cudaEventSynchronize(w.ringEvents[back % kRing]));
+            last = w.hCounters[(2 * back + 1) % kRing];              // snapshot of its second wave
             if (last.done) break;
         }
     }
     SLRGPU_CUDA_TRY(cudaEventRecord(ev1, stream));
     SLRGPU_CUDA_TRY(cudaEventSynchronize(ev1));
     last = w.hCounters[(wave - 1) % kRing];
+    wave = last.waves;
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->paths = totalSamples;
@@ -657,7 +712,10 @@ SLRGPU_API int slrgpu_render_device(SlrGpuScene* sc, const SlrGpuRenderParams* p
     if (rc) return rc;
     if (!accumDev) { setError("slrgpu_render_device: null accumulation buffer"); return SLRGPU_ERR_INVALID_ARGUMENT; }
     SLRGPU_CUDA_TRY(cudaSetDevice(sc->device));
-    return renderImpl(sc, p, accumDev, (cudaStream_t)stream, stats);
+    RenderWorkspace* w = nullptr;
+    if ((rc = acquireWorkspace(sc, poolCapacity(p), &w))) return rc;
+    struct Release { int device; RenderWorkspace* w; ~Release() { releaseWorkspace(device, w); } } release{sc->device, w};
+    return renderImpl(sc, p, *w, accumDev, (cudaStream_t)stream, stats);
 }
 
 SLRGPU_API int slrgpu_render(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accum, SlrGpuRenderStats* stats) {
@@ -665,14 +723,18 @@ SLRGPU_API int slrgpu_render(SlrGpuScene* sc, const SlrGpuRenderParams* p, float
     if (rc) return rc;
     if (!accum) { setError("slrgpu_render: null accumulation buffer"); return SLRGPU_ERR_INVALID_ARGUMENT; }
     SLRGPU_CUDA_TRY(cudaSetDevice(sc->device));
+    RenderWorkspace* w = nullptr;
+    if ((rc = acquireWorkspace(sc, poolCapacity(p), &w))) return rc;
+    struct Release { int device; RenderWorkspace* w; ~Release() { releaseWorkspace(device, w); } } release{sc->device, w};
+    // the frame buffer and its pinned staging copy live in the pooled workspace: no allocation per call
     const size_t bytes = (size_t)p->width * p->height * sc->channels * sizeof(float);
-    float* dAccum = nullptr;
-    SLRGPU_CUDA_TRY(cudaMalloc(&dAccum, bytes));
-    struct Free { float* p; ~Free() { cudaFree(p); } } guard{dAccum};
-    SLRGPU_CUDA_TRY(cudaMemset(dAccum, 0, bytes));
-    rc = renderImpl(sc, p, dAccum, 0, stats);
+    if ((rc = w->ensureFrame(bytes))) return rc;
+    SLRGPU_CUDA_TRY(cudaMemsetAsync(w->frame, 0, bytes, w->stream));
+    rc = renderImpl(sc, p, *w, w->frame, w->stream, stats);
     if (rc) return rc;
-    SLRGPU_CUDA_TRY(cudaMemcpy(accum, dAccum, bytes, cudaMemcpyDeviceToHost));
+    SLRGPU_CUDA_TRY(cudaMemcpyAsync(w->frameHost, w->frame, bytes, cudaMemcpyDeviceToHost, w->stream));
+    SLRGPU_CUDA_TRY(cudaStreamSynchronize(w->stream));
+    memcpy(accum, w->frameHost, bytes);
     return SLRGPU_OK;
 }
 

@@ -26,20 +26,37 @@ int cudaFail(cudaError_t e, const char* what) {
     return SLRGPU_ERR_CUDA;
 }
 
-template <typename T>
-static int upload(SlrGpuScene* sc, const T* src, uint64_t count, const T** dst) {
-    *dst = nullptr;
-    if (count == 0 || src == nullptr) return SLRGPU_OK;
-    if (sc->numAllocations >= 32) { setError("too many scene buffers"); return SLRGPU_ERR_INVALID_ARGUMENT; }
-    void* p = nullptr;
-    const uint64_t bytes = count * sizeof(T);
-    SLRGPU_CUDA_TRY(cudaMalloc(&p, bytes));
-    sc->allocations[sc->numAllocations++] = p;
-    sc->deviceBytes += bytes;
-    SLRGPU_CUDA_TRY(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
-    *dst = reinterpret_cast<const T*>(p);
-    return SLRGPU_OK;
-}
+// All scene buffers live in ONE device allocation (256-byte aligned sub-ranges): a scene is created and
+// destroyed with one cudaMalloc / cudaFree, and a small scene goes up in one staged copy.
+struct UploadPlan {
+    struct Item { const void* src; uint64_t bytes; uint64_t offset; const void** dst; };
+    std::vector<Item> items;
+    uint64_t total = 0;
+    template <typename T> void add(const T* src, uint64_t count, const T** dst) {
+        *dst = nullptr;
+        if (count == 0 || src == nullptr) return;
+        const uint64_t bytes = count * sizeof(T);
+        items.push_back(Item{src, bytes, total, reinterpret_cast<const void**>(dst)});
+        total += (bytes + 255u) & ~uint64_t(255);
+    }
+    int commit(SlrGpuScene* sc) {
+        if (total == 0) return SLRGPU_OK;
+        void* base = nullptr;
+        SLRGPU_CUDA_TRY(cudaMalloc(&base, total));
+        sc->allocations[sc->numAllocations++] = base;
+        sc->deviceBytes += total;
+        if (total <= (64u << 20)) {
+            std::vector<uint8_t> stage(total, 0);
+            for (const Item& it : items) memcpy(stage.data() + it.offset, it.src, it.bytes);
+            SLRGPU_CUDA_TRY(cudaMemcpy(base, stage.data(), total, cudaMemcpyHostToDevice));
+        } else {
+            for (const Item& it : items)
+                SLRGPU_CUDA_TRY(cudaMemcpy(static_cast<uint8_t*>(base) + it.offset, it.src, it.bytes, cudaMemcpyHostToDevice));
+        }
+        for (const Item& it : items) *it.dst = static_cast<uint8_t*>(base) + it.offset;
+        return SLRGPU_OK;
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Spectrum compilation (host, once per scene): rewrites the caller's spectrum table into the two
@@ -191,7 +208,8 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
     DeviceScene& v = sc->dev;
     memset(&v, 0, sizeof(v));
     int rc = SLRGPU_OK;
-#define UP(src, count, dst) if (rc == SLRGPU_OK) rc = upload(sc, src, (uint64_t)(count), dst)
+    UploadPlan plan;
+#define UP(src, count, dst) plan.add(src, (uint64_t)(count), dst)
     UP(reinterpret_cast<const float4*>(d->bvh_nodes), (uint64_t)d->num_bvh_nodes * 8, &v.nodes);
     UP(reinterpret_cast<const float4*>(d->leaf_records), (uint64_t)d->num_leaf_records * 3, &v.leaves);
     UP(d->instances, d->num_instances, &v.instances);
@@ -219,6 +237,7 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
     UP(d->spectral.upsample_grid, d->spectral.upsample_grid_floats, &v.upsampleGrid);
     UP(d->spectral.upsample_points, d->spectral.upsample_points_floats, &v.upsamplePoints);
 #undef UP
+    rc = plan.commit(sc);
     if (rc != SLRGPU_OK) { slrgpu_scene_destroy(sc); return rc; }
 
     v.numNodes = d->num_bvh_nodes; v.numLeaves = d->num_leaf_records; v.numInstances = d->num_instances;

@@ -217,7 +217,14 @@ __device__ bool traverse(const DeviceScene& s, uint32_t root, Ray& r, Hit& hit, 
 // the leaf-phase coherence returns.)
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kMaxChunk = 256;
-constexpr int kStepsPerRound = 4;
+#ifndef SLR_WALK_STEPS_PER_ROUND
+#define SLR_WALK_STEPS_PER_ROUND 4
+#endif
+#ifndef SLR_WALK_REFILL_IDLE
+#define SLR_WALK_REFILL_IDLE 8
+#endif
+constexpr int kStepsPerRound = SLR_WALK_STEPS_PER_ROUND;     // node visits between two refill checks
+constexpr int kRefillIdle = SLR_WALK_REFILL_IDLE;            // idle lanes that trigger a refill
 
 struct WalkState {
     Ray r;
@@ -339,7 +346,7 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
         const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
         const int numIdle = __popc(idle);
         // refill when a quarter of the warp is idle (or nothing is running)
-        if (!exhausted && (numIdle >= 8)) {
+        if (!exhausted && (numIdle >= kRefillIdle)) {
             if (chunkNext >= chunkEnd) {
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(cursor, chunk);

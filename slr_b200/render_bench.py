@@ -112,7 +112,9 @@ def main(args, rank, world):
     gs = capi.GpuScene(hs, device=dev)
     chan = capi.gpu.slrgpu_scene_channels(gs.handle)
     accum = torch.zeros((h, w, chan), dtype=torch.float32, device="cuda")
-    stream = torch.cuda.current_stream()
+    # a non-default stream: slrgpu_render_device replays a captured CUDA graph, which the legacy stream cannot do
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     seed = 1509761209
     spp_begin, spp_end = sample_range(rank, world, spp, "weak")
     params = capi.RenderParams(C.sizeof(capi.RenderParams), w, h, spp_begin, spp_end, 0.0, 0.0, seed, 0,
