@@ -50,6 +50,10 @@ SLRGPU_API int slrhost_scene_context(const SlrHostScene* s, double* ctx8);
  * bmp_dir: directory for the progressive NNN.bmp files, or NULL to skip image export. */
 SLRGPU_API int slrhost_render(SlrHostScene* s, int device, int width, int height, int spp, int seed,
                               const char* bmp_dir, float* accum, double* stats6);
+/* Same, for the global sample indices [spp_begin, spp_begin + spp): what process g of an N-process
+ * front end calls before the sensors are summed (one process per GPU). */
+SLRGPU_API int slrhost_render_range(SlrHostScene* s, int device, int width, int height, int spp_begin, int spp, int seed,
+                                    const char* bmp_dir, float* accum, double* stats6);
 /* Tone-maps a frame buffer exactly like ImageSensor::saveImage (ImageSensor.cpp:138-186). */
 SLRGPU_API int slrhost_save_bmp(const char* path, const float* accum, int width, int height, int channels,
                                 float scale, float sensitivity);

@@ -394,6 +394,8 @@ host.slrhost_scene_context.restype = C.c_int
 host.slrhost_scene_context.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
 host.slrhost_render.restype = C.c_int
 host.slrhost_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, PF, C.POINTER(C.c_double)]
+host.slrhost_render_range.restype = C.c_int
+host.slrhost_render_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, PF, C.POINTER(C.c_double)]
 host.slrhost_save_bmp.restype = C.c_int
 host.slrhost_save_bmp.argtypes = [C.c_char_p, PF, C.c_int, C.c_int, C.c_int, c_f, c_f]
 host.slrhost_accum_to_rgb.restype = C.c_int
@@ -420,17 +422,19 @@ def read_scene(path, rgb_mode=False):
     return hs
 
 
-def host_render(host_scene, width=0, height=0, spp=0, seed=0, device=0, bmp_dir=None):
-    """Renderer::render through the host's GPUPathTracingRenderer. Returns (accum[h, w, c], stats)."""
+def host_render(host_scene, width=0, height=0, spp=0, seed=0, device=0, bmp_dir=None, spp_begin=0, out=None):
+    """Renderer::render through the host's GPUPathTracingRenderer (global samples [spp_begin, spp_begin + spp)).
+    Returns (accum[h, w, c], stats); `out` may supply the destination array (e.g. a pinned torch tensor's numpy view)."""
     ctx = getattr(host_scene, "context", {"width": 0, "height": 0})
     w = width or ctx["width"]
     h = height or ctx["height"]
     chan = 3 if host_scene.desc.rgb_mode else 16
-    accum = np.empty((h, w, chan), np.float32)
+    accum = out if out is not None else np.empty((h, w, chan), np.float32)
+    assert accum.shape == (h, w, chan) and accum.dtype == np.float32 and accum.flags["C_CONTIGUOUS"]
     st = (C.c_double * 6)()
     t0 = time.perf_counter()
-    _host_check(host.slrhost_render(host_scene.handle, device, width, height, spp, seed,
-                                    os.fsencode(bmp_dir) if bmp_dir else None, _pf(accum), st), "slrhost_render")
+    _host_check(host.slrhost_render_range(host_scene.handle, device, width, height, spp_begin, spp, seed,
+                                          os.fsencode(bmp_dir) if bmp_dir else None, _pf(accum), st), "slrhost_render_range")
     call_s = time.perf_counter() - t0
     return accum, {"paths": int(st[0]), "rays": int(st[1]), "device_s": st[2], "wall_s": st[3], "upload_s": st[4], "channels": int(st[5]),
                    "call_s": call_s}

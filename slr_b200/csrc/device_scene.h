@@ -57,6 +57,7 @@ struct SlrGpuScene {
     void* allocations[32] = {};
     int numAllocations = 0;
     uint64_t deviceBytes = 0;
+    uint64_t arenaBytes = 0;          // size of allocations[0], the single arena all scene buffers live in
     bool hasInstances = false;
     bool hasShading = false;
     uint32_t channels = 16;
@@ -65,6 +66,7 @@ struct SlrGpuScene {
 
 namespace slrgpu {
 void setError(const char* fmt, ...);
+void releaseSceneArenas();        // scene.cu: drops the per-device arena cache
 int cudaFail(cudaError_t e, const char* what);
 #define SLRGPU_CUDA_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return slrgpu::cudaFail(_e, #expr); } while (0)
 }

@@ -705,6 +705,7 @@ SLRGPU_API void slrgpu_release_workspaces(void) {
     std::lock_guard<std::mutex> lock(g_poolMutex);
     for (int d = 0; d < 64; ++d)
         if (g_pool[d]) { cudaSetDevice(d); delete g_pool[d]; g_pool[d] = nullptr; }
+    releaseSceneArenas();
 }
 
 SLRGPU_API int slrgpu_render_device(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accumDev, void* stream, SlrGpuRenderStats* stats) {

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -26,6 +27,35 @@ int cudaFail(cudaError_t e, const char* what) {
     return SLRGPU_ERR_CUDA;
 }
 
+// A destroyed scene's arena (up to kArenaCacheLimit bytes) is kept, one per device, for the next scene
+// that fits: a renderer front end that uploads the scene on every render() call then runs without any
+// cudaMalloc / cudaFree (both are synchronising driver calls with occasional 100 ms outliers on a busy
+// host). slrgpu_release_workspaces() drops the cache.
+static std::mutex g_arenaMutex;
+static void* g_arena[64] = {};
+static uint64_t g_arenaBytes[64] = {};
+constexpr uint64_t kArenaCacheLimit = 256ull << 20;
+
+static void* takeCachedArena(int device, uint64_t need, uint64_t* got) {
+    std::lock_guard<std::mutex> lock(g_arenaMutex);
+    if (device < 0 || device >= 64 || !g_arena[device] || g_arenaBytes[device] < need) return nullptr;
+    void* p = g_arena[device];
+    *got = g_arenaBytes[device];
+    g_arena[device] = nullptr; g_arenaBytes[device] = 0;
+    return p;
+}
+static bool cacheArena(int device, void* p, uint64_t bytes) {
+    std::lock_guard<std::mutex> lock(g_arenaMutex);
+    if (device < 0 || device >= 64 || bytes > kArenaCacheLimit) return false;
+    if (g_arena[device]) { if (g_arenaBytes[device] >= bytes) return false; cudaFree(g_arena[device]); }
+    g_arena[device] = p; g_arenaBytes[device] = bytes;
+    return true;
+}
+void releaseSceneArenas() {
+    std::lock_guard<std::mutex> lock(g_arenaMutex);
+    for (int d = 0; d < 64; ++d) if (g_arena[d]) { cudaSetDevice(d); cudaFree(g_arena[d]); g_arena[d] = nullptr; g_arenaBytes[d] = 0; }
+}
+
 // All scene buffers live in ONE device allocation (256-byte aligned sub-ranges): a scene is created and
 // destroyed with one cudaMalloc / cudaFree, and a small scene goes up in one staged copy.
 struct UploadPlan {
@@ -41,8 +71,11 @@ struct UploadPlan {
     }
     int commit(SlrGpuScene* sc) {
         if (total == 0) return SLRGPU_OK;
-        void* base = nullptr;
-        SLRGPU_CUDA_TRY(cudaMalloc(&base, total));
+        void* base = takeCachedArena(sc->device, total, &sc->arenaBytes);
+        if (!base) {
+            SLRGPU_CUDA_TRY(cudaMalloc(&base, total));
+            sc->arenaBytes = total;
+        }
         sc->allocations[sc->numAllocations++] = base;
         sc->deviceBytes += total;
         if (total <= (64u << 20)) {
@@ -281,7 +314,10 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
 SLRGPU_API void slrgpu_scene_destroy(SlrGpuScene* sc) {
     if (!sc) return;
     cudaSetDevice(sc->device);
-    for (int i = 0; i < sc->numAllocations; ++i) cudaFree(sc->allocations[i]);
+    for (int i = 0; i < sc->numAllocations; ++i) {
+        if (i == 0 && sc->arenaBytes && cacheArena(sc->device, sc->allocations[0], sc->arenaBytes)) continue;
+        cudaFree(sc->allocations[i]);
+    }
     delete sc;
 }
 

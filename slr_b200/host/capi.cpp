@@ -128,7 +128,13 @@ SLRGPU_API int slrhost_scene_context(const SlrHostScene* s, double* c) {
 
 SLRGPU_API int slrhost_render(SlrHostScene* s, int device, int width, int height, int spp, int seed,
                               const char* bmp_dir, float* accum, double* stats) {
+    return slrhost_render_range(s, device, width, height, 0, spp, seed, bmp_dir, accum, stats);
+}
+
+SLRGPU_API int slrhost_render_range(SlrHostScene* s, int device, int width, int height, int spp_begin, int spp, int seed,
+                                    const char* bmp_dir, float* accum, double* stats) {
     if (!s) return fail("slrhost_render: null scene");
+    if (spp_begin < 0) return fail("slrhost_render_range: negative first sample index");
     try {
         if (!s->flat.hasCamera) return fail("the scene has no camera");
         if (!s->render.sensor) {
@@ -145,6 +151,7 @@ SLRGPU_API int slrhost_render(SlrHostScene* s, int device, int width, int height
         settings.addItem(RenderSettingItem::RNGSeed, (int32_t)(seed != 0 ? seed : s->context.rngSeed));
         GPUPathTracingRenderer renderer(spp > 0 ? (uint32_t)spp : s->context.samples);
         renderer.device = device;
+        renderer.sampleBegin = (uint32_t)spp_begin;
         renderer.exportProgressiveImages = bmp_dir != nullptr;
         if (bmp_dir) renderer.outputDirectory = bmp_dir;
         renderer.render(s->render, settings);

@@ -97,7 +97,7 @@ void GPUPathTracingRenderer::render(const RenderScene& scene, const RenderSettin
 
     if (!exportProgressiveImages) {
         // one GPU call for the whole sample range, straight into the sensor
-        p.spp_begin = 0; p.spp_end = m_samplesPerPixel;
+        p.spp_begin = sampleBegin; p.spp_end = sampleBegin + m_samplesPerPixel;
         SlrGpuRenderStats st;
         if (slrgpu_render(gpu, &p, sensor->data(), &st) != SLRGPU_OK) {
             std::string msg = std::string("slrgpu_render failed: ") + slrgpu_last_error();
@@ -116,7 +116,7 @@ void GPUPathTracingRenderer::render(const RenderScene& scene, const RenderSettin
     uint32_t begin = 0, exportAt = 1, imgIdx = 0;
     while (begin < m_samplesPerPixel) {
         uint32_t end = exportProgressiveImages ? std::min(exportAt, m_samplesPerPixel) : m_samplesPerPixel;
-        p.spp_begin = begin; p.spp_end = end;
+        p.spp_begin = sampleBegin + begin; p.spp_end = sampleBegin + end;
         SlrGpuRenderStats st;
         if (slrgpu_render(gpu, &p, pass.data(), &st) != SLRGPU_OK) {
             std::string msg = std::string("slrgpu_render failed: ") + slrgpu_last_error();

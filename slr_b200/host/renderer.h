@@ -83,6 +83,9 @@ public:
 class GPUPathTracingRenderer : public Renderer {
     uint32_t m_samplesPerPixel;
 public:
+    // Global index of the first sample this renderer instance renders: a multi-process front end gives
+    // process g of N the range [sampleBegin, sampleBegin + spp) and sums the sensors.
+    uint32_t sampleBegin = 0;
     mutable RenderStatistics lastStatistics;
     bool exportProgressiveImages = true;     // NNN.bmp at 1, 2, 4, ... samples like the reference
     std::string outputDirectory = ".";

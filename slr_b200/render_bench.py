@@ -8,11 +8,12 @@ on): Cornell_Box_Spheres, 512x512, 64 spp, unidirectional PT, spectral. One step
           summed onto rank 0 with one NCCL reduce. CUDA events on the launch stream, max over ranks.
           Weak scaling: every rank renders the full 64 spp of its own sample range [64 r, 64 (r + 1)),
           i.e. the N-GPU frame has 64 N spp (BASELINE.json configs[3] splits 1024 spp as 128 per GPU).
-  e2e     the same frame through the renderer front end with HOST buffers: scene upload
-          (slrgpu_scene_create from the host SoA buffers), render, download of the accumulation buffer
-          into host memory. At N = 1 this is literally slrhost_render (= GPUPathTracingRenderer::render,
-          the drop-in for PathTracingRenderer::render); at N > 1 each rank does upload + render, the
-          device buffers are NCCL-reduced and rank 0 downloads.
+  e2e     the same frame through the renderer front end with HOST buffers: every rank calls
+          slrhost_render_range (= GPUPathTracingRenderer::render, the drop-in for
+          PathTracingRenderer::render, on its sample range): scene upload from the host SoA buffers,
+          render, download of the frame buffer into (pinned) host memory. N > 1: the host frame buffers
+          are staged back to the device, summed with one NCCL reduce and downloaded by rank 0. Wall
+          clock between barriers, median over the frames.
 """
 import ctypes as C
 import json
@@ -157,42 +158,40 @@ def main(args, rank, world):
     paths_per_step = w * h * spp
 
     # ---- end to end with host buffers
-    e2e_steps = max(1, min(args.steps, 3))
+    # every rank: Renderer::render of its sample range through the host front end (scene upload + render +
+    # frame-buffer download into pinned host memory); N > 1: the host frame buffers go back to the device,
+    # one NCCL reduce, and rank 0 downloads the sum. Median of the per-frame wall times.
+    e2e_steps = max(3, min(args.steps, 10))
+    pinned = torch.empty((h, w, chan), dtype=torch.float32).pin_memory()
+    staged = torch.empty((h, w, chan), dtype=torch.float32, device="cuda") if dist is not None else None
+    hst = None
+
+    def e2e_frame():
+        nonlocal hst
+        _, hst = capi.host_render(hs, w, h, spp, seed, dev, spp_begin=spp_begin, out=pinned.numpy())
+        if dist is not None:
+            staged.copy_(pinned, non_blocking=True)
+            reduce_frame(staged, dist)
+            if rank == 0:
+                pinned.copy_(staged, non_blocking=True)
+            torch.cuda.synchronize()
+
+    e2e_frame()
+    times = []
+    for _ in range(e2e_steps):
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e2e_frame()
+        if dist is not None:
+            dist.barrier()
+        times.append(time.perf_counter() - t0)
+    e2e_s = float(np.median(times))
+    e2e_detail = {"frames": e2e_steps, "wall_ms_median": round(1e3 * e2e_s, 2), "wall_ms_min": round(1e3 * min(times), 2),
+                  "wall_ms_max": round(1e3 * max(times), 2), "renderer_wall_ms": round(1e3 * hst["wall_s"], 2),
+                  "scene_upload_ms": round(1e3 * hst["upload_s"], 2), "device_ms": round(1e3 * hst["device_s"], 2)}
     scene_bytes = int(gs.device_bytes)
     accum_bytes = w * h * chan * 4
-    if world == 1:
-        capi.host_render(hs, w, h, spp, seed, dev)        # warm
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            img, hst = capi.host_render(hs, w, h, spp, seed, dev)
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-        e2e_detail = {"wall_ms": round(1e3 * e2e_s, 2), "renderer_wall_ms": round(1e3 * hst["wall_s"], 2),
-                      "scene_upload_ms": round(1e3 * hst["upload_s"], 2), "device_ms": round(1e3 * hst["device_s"], 2),
-                      "c_call_ms": round(1e3 * hst["call_s"], 2)}
-    else:
-        pinned = torch.empty((h, w, chan), dtype=torch.float32).pin_memory()
-        e2e_detail = None
-
-        def e2e_frame():
-            g2 = capi.GpuScene(hs, device=dev)
-            st2 = capi.RenderStats()
-            accum.zero_()
-            rc = capi.gpu.slrgpu_render_device(g2.handle, C.byref(params), C.c_void_p(accum.data_ptr()),
-                                               C.c_void_p(stream.cuda_stream), C.byref(st2))
-            if rc != 0:
-                raise RuntimeError(capi.gpu.slrgpu_last_error().decode())
-            reduce_frame(accum, dist)
-            if rank == 0:
-                pinned.copy_(accum, non_blocking=False)
-            torch.cuda.synchronize()
-            g2.close()
-        e2e_frame()
-        dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_frame()
-        dist.barrier()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
 
     if dist is not None:
         t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
@@ -244,8 +243,9 @@ def main(args, rank, world):
                          "algorithmic_bytes_per_launch_set": algo[dom],
                          "note": "algorithmic bytes of all launches of the kernel in one frame / its summed device time"},
             "cpu_baseline": cpu,
-            "e2e": {"value": paths_per_step * world / e2e_s / 1e6, "unit": "Mpaths/s", "h2d_bytes_per_step": scene_bytes,
-                    "d2h_bytes_per_step": accum_bytes, "breakdown": e2e_detail},
+            "e2e": {"value": paths_per_step * world / e2e_s / 1e6, "unit": "Mpaths/s",
+                    "h2d_bytes_per_step": scene_bytes + (accum_bytes if world > 1 else 0),
+                    "d2h_bytes_per_step": accum_bytes * (2 if world > 1 else 1), "breakdown": e2e_detail},
             "gpu_launches": int(launches), "clocks": clocks.summary()}
     print(json.dumps(line))
     if dist is not None:
