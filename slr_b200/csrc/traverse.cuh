@@ -324,6 +324,147 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, uin
     return w.sp == 0;
 }
 
+// ---- instanced scenes: the nested traversal is part of the same state machine -------------------
+// Entering an instance leaf record transforms the ray into the instance's space, pushes a RETURN marker
+// and the nested root; the nested nodes are then ordinary steps of the walk (so they take part in the
+// dynamic fetch like top-level nodes). Popping the marker restores the world-space ray and the leaf
+// records of the top-level node that were still waiting -- exactly where the reference's recursion
+// (TransformedSurfaceObject::intersect, SurfaceObject.cpp:307-318) returns to. One level of instancing.
+constexpr uint32_t kReturnMarker = 0xFFFFFFFEu;
+
+struct LeafQueue {
+    uint32_t first, count;               // current range of leaf records
+    uint32_t pending0, pending1, pending2;   // packed leaf child words still to come, kEmptyChild = none
+    __device__ __forceinline__ void clear() { first = 0; count = 0; pending0 = pending1 = pending2 = kEmptyChild; }
+    __device__ __forceinline__ void next() {
+        count = 0;
+#pragma unroll
+        for (int k = 0; k < 3 && count == 0; ++k) {
+            const uint32_t c = pending0;
+            pending0 = pending1; pending1 = pending2; pending2 = kEmptyChild;
+            if (c == kEmptyChild) return;
+            first = c & 0x07FFFFFFu;
+            count = (c >> 27) & 0xFu;
+        }
+    }
+};
+
+struct InstanceWalkState {
+    LeafQueue leaves;        // of the level the lane is walking
+    LeafQueue saved;         // top-level queue while inside an instance
+    float wox, woy, woz, wdx, wdy, wdz;      // world-space ray while inside an instance
+    uint32_t curInst;        // SLRGPU_INVALID_ID at the top level
+};
+
+__device__ __forceinline__ void walkSetRay(WalkState& w) {
+    w.ix = 1.0f / w.r.dx; w.iy = 1.0f / w.r.dy; w.iz = 1.0f / w.r.dz;
+    w.pos = (w.r.dx >= 0.0f ? 1u : 0u) | (w.r.dy >= 0.0f ? 2u : 0u) | (w.r.dz >= 0.0f ? 4u : 0u);
+}
+
+// One step of the instanced walk: either the leaf records that are due (triangles in a row; an instance
+// record enters the instance), or one stack entry (a node, or the return marker). Returns true when the
+// ray is finished.
+template <bool ANY_HIT, bool COUNT>
+__device__ __forceinline__ bool walkStepInstanced(const DeviceScene& s, WalkState& w, InstanceWalkState& iw, uint32_t* stack,
+                                                  TraversalCounters& cnt, bool& overflow) {
+    Ray& r = w.r;
+    if (iw.leaves.count != 0) {
+        while (iw.leaves.count != 0) {
+            const float4* rec = s.leaves + (size_t)iw.leaves.first * 3;
+            const float4 a = ldg4(rec);
+            ++iw.leaves.first;
+            if (--iw.leaves.count == 0) iw.leaves.next();
+            const uint32_t id = __float_as_uint(a.w);
+            if (COUNT) ++cnt.tris;
+            if (id & 0x80000000u) {
+                if (iw.curInst != SLRGPU_INVALID_ID) continue;          // nested instancing is rejected at scene build
+                if (w.sp + 2 > kStackSize) { overflow = true; continue; }   // no room for marker + root: reported as overflow
+                const uint32_t instId = id & 0x7FFFFFFFu;
+                const SlrGpuInstance* inst = s.instances + instId;
+                iw.wox = r.ox; iw.woy = r.oy; iw.woz = r.oz; iw.wdx = r.dx; iw.wdy = r.dy; iw.wdz = r.dz;
+                iw.saved = iw.leaves;
+                iw.leaves.clear();
+                float lx, ly, lz, mx, my, mz;
+                mulPoint(inst->mat_inv, r.ox, r.oy, r.oz, &lx, &ly, &lz);
+                mulVector(inst->mat_inv, r.dx, r.dy, r.dz, &mx, &my, &mz);
+                r.ox = lx; r.oy = ly; r.oz = lz; r.dx = mx; r.dy = my; r.dz = mz;
+                walkSetRay(w);
+                iw.curInst = instId;
+                stack[w.sp++] = kReturnMarker;
+                stack[w.sp++] = inst->root_node;
+                return false;
+            }
+            const float4 b = ldg4(rec + 1), cc = ldg4(rec + 2);
+            float t, b0, b1;
+            if (triangleTest(a, b, cc, r, &t, &b0, &b1)) {
+                r.tmax = t;
+                w.hit.prim = id; w.hit.inst = iw.curInst;
+                w.hit.t = t; w.hit.u = b0; w.hit.v = b1;
+                w.found = true;
+                if (ANY_HIT) return true;
+            }
+        }
+        return w.sp == 0;
+    }
+    const uint32_t entry = stack[--w.sp];
+    if (entry == kReturnMarker) {
+        r.ox = iw.wox; r.oy = iw.woy; r.oz = iw.woz; r.dx = iw.wdx; r.dy = iw.wdy; r.dz = iw.wdz;   // tmax carries over (SurfaceObject.cpp:314)
+        walkSetRay(w);
+        iw.leaves = iw.saved;
+        iw.curInst = SLRGPU_INVALID_ID;
+        return w.sp == 0 && iw.leaves.count == 0;
+    }
+    const float4* n = s.nodes + (size_t)entry * 8;
+    const float4 lox = ldg4(n + 0), loy = ldg4(n + 1), loz = ldg4(n + 2);
+    const float4 hix = ldg4(n + 3), hiy = ldg4(n + 4), hiz = ldg4(n + 5);
+    if (COUNT) ++cnt.nodes;
+    const uint32_t mask = slab4(lox, loy, loz, hix, hiy, hiz, r, w.ix, w.iy, w.iz);
+    if (mask != 0) {
+        const uint4 kids = __ldg(reinterpret_cast<const uint4*>(n + 6));
+        const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(n + 7));
+        const uint32_t T = (w.pos >> (axes & 0xFF)) & 1u;
+        const uint32_t L = (w.pos >> ((axes >> 8) & 0xFF)) & 1u;
+        const uint32_t R = (w.pos >> ((axes >> 16) & 0xFF)) & 1u;
+        const uint32_t l0 = L ? 0u : 1u, r0 = R ? 2u : 3u;
+        uint32_t order[4];
+        order[0] = T ? l0 : r0;        order[1] = T ? (l0 ^ 1u) : (r0 ^ 1u);
+        order[2] = T ? r0 : l0;        order[3] = T ? (r0 ^ 1u) : (l0 ^ 1u);
+        uint32_t ch[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t lane = order[i];
+            uint32_t c = lane == 0 ? kids.x : lane == 1 ? kids.y : lane == 2 ? kids.z : kids.w;
+            ch[i] = ((mask >> lane) & 1u) ? c : kEmptyChild;
+        }
+#pragma unroll
+        for (int i = 3; i >= 0; --i) {
+            const uint32_t c = ch[i];
+            if (c == kEmptyChild || (c >> 31)) continue;
+            if (w.sp >= kStackSize) { overflow = true; continue; }
+            stack[w.sp++] = c & 0x07FFFFFFu;
+        }
+        // leaf children in visiting order: the first becomes the current range, up to three wait
+        uint32_t q[4] = {kEmptyChild, kEmptyChild, kEmptyChild, kEmptyChild};
+        int nq = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t c = ch[i];
+            if (c != kEmptyChild && (c >> 31)) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (k == nq) q[k] = c;
+                ++nq;
+            }
+        }
+        if (nq > 0) {
+            iw.leaves.first = q[0] & 0x07FFFFFFu;
+            iw.leaves.count = (q[0] >> 27) & 0xFu;
+            iw.leaves.pending0 = q[1]; iw.leaves.pending1 = q[2]; iw.leaves.pending2 = q[3];
+            if (iw.leaves.count == 0) iw.leaves.next();
+        }
+    }
+    return w.sp == 0 && iw.leaves.count == 0;
+}
+
 // Runs `n` rays through the scene with one warp-cooperative loop. Source::load(i, Ray&) fetches ray i,
 // Sink::done(i, state) consumes its result. *cursor must be 0 at launch.
 template <bool INSTANCES, bool ANY_HIT, bool COUNT, typename Source, typename Sink>
@@ -333,6 +474,7 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t stack[kStackSize];
     WalkState w;
+    InstanceWalkState iw;                       // only live in the INSTANCES instantiations
     bool active = false;
     uint32_t idx = 0;
     uint32_t chunkNext = 0, chunkEnd = 0;       // warp-uniform
@@ -362,6 +504,7 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
                     idx = chunkNext + rank;
                     source.load(idx, w.r);
                     walkBegin(w, stack);
+                    if (INSTANCES) { iw.leaves.clear(); iw.saved.clear(); iw.curInst = SLRGPU_INVALID_ID; }
                     w.cnt0 = cnt;
                     active = true;
                 }
@@ -375,7 +518,10 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
 #pragma unroll 1
         for (int it = 0; it < kStepsPerRound; ++it) {
             if (active) {
-                if (walkStep<INSTANCES, ANY_HIT, COUNT>(s, w, stack, cnt, overflow)) {
+                bool finished;
+                if constexpr (INSTANCES) finished = walkStepInstanced<ANY_HIT, COUNT>(s, w, iw, stack, cnt, overflow);
+                else finished = walkStep<false, ANY_HIT, COUNT>(s, w, stack, cnt, overflow);
+                if (finished) {
                     sink.done(idx, w, cnt);
                     active = false;
                 }

@@ -277,12 +277,19 @@ void spectrumToXYZ(SampleFn sample, NextFn nextSampleWL, float XYZ[3]) {
             xv = xb[cmfIdx]; yv = yb[cmfIdx]; zv = zb[cmfIdx];
             ++cmfIdx;
         } else {
-            uint32_t idx = std::min(uint32_t((curWL - kWavelengthLowBound) / cmfBin), kNumCMFSamples - 1);
+            // The reference computes uint32_t((curWL - 360) / bin) also when curWL < 360 (a spectrum whose first
+            // sample lies below 360 nm, e.g. D65 from 300 nm, pulls curWL back: API.cpp:1203-1205), which is
+            // undefined behaviour and in practice indexes one past the CMF tables. That read is replaced by a
+            // clamp to the table: deterministic, and the RGB build is not part of the oracle anyway.
+            float rel = (curWL - kWavelengthLowBound) / cmfBin;
+            uint32_t idx = rel <= 0.0f ? 0u : std::min(uint32_t(rel), kNumCMFSamples - 1);
+            uint32_t idx1 = std::min(idx + 1, kNumCMFSamples - 1);
             float base = kWavelengthLowBound + idx * cmfBin;
             float t = (curWL - base) / cmfBin;
-            xv = (1 - t) * xb[idx] + t * xb[idx + 1];
-            yv = (1 - t) * yb[idx] + t * yb[idx + 1];
-            zv = (1 - t) * zb[idx] + t * zb[idx + 1];
+            t = std::min(std::max(t, 0.0f), 1.0f);
+            xv = (1 - t) * xb[idx] + t * xb[idx1];
+            yv = (1 - t) * yb[idx] + t * yb[idx1];
+            zv = (1 - t) * zb[idx] + t * zb[idx1];
         }
         float value = sample(curWL);
         float avg = (prevValue + value) * 0.5f;
@@ -331,7 +338,7 @@ InputSpectrumRef create(bool rgbMode, SpectrumType type, float minLambda, float 
             if (wl == minLambda + baseIdx * binWidth) return values[baseIdx++];
             uint32_t idx = std::min(uint32_t((wl - minLambda) / binWidth), n - 1);
             float t = (wl - (minLambda + idx * binWidth)) / binWidth;
-            return (1 - t) * values[idx] + t * values[idx + 1];
+            return (1 - t) * values[idx] + t * values[std::min(idx + 1, n - 1)];
         },
         [&]() { return baseIdx < n ? (minLambda + baseIdx * binWidth) : INFINITY; }, XYZ);
     return rgbFromXYZ(type, XYZ);
@@ -348,8 +355,10 @@ InputSpectrumRef create(bool rgbMode, SpectrumType type, const float* lambdas, c
             if (wl == lambdas[baseIdx]) return values[baseIdx++];
             const float* lb = std::lower_bound(lambdas + std::max((int32_t)baseIdx - 1, 0), lambdas + n, wl);
             uint32_t idx = (uint32_t)std::max(int32_t(lb - lambdas) - 1, 0);
-            float t = (wl - lambdas[idx]) / (lambdas[idx + 1] - lambdas[idx]);
-            return (1 - t) * values[idx] + t * values[idx + 1];
+            uint32_t idx1 = std::min(idx + 1, n - 1);
+            if (idx1 == idx) return values[idx];
+            float t = (wl - lambdas[idx]) / (lambdas[idx1] - lambdas[idx]);
+            return (1 - t) * values[idx] + t * values[idx1];
         },
         [&]() { return baseIdx < n ? lambdas[baseIdx] : INFINITY; }, XYZ);
     return rgbFromXYZ(type, XYZ);
