@@ -157,6 +157,43 @@ __global__ void endWaveKernel(WavefrontCounters* counters, WavefrontCounters* ri
     __threadfence_system();
 }
 
+// Emission seen by the ray that arrived at an emitter (or left the scene into the environment), with the
+// MIS weight of implicit light sampling (PathTracingRenderer.cpp:152-156, 232-249). Kept out of line:
+// only a few per cent of the hits take it, and inlined it doubles the register count of the surface kernel.
+template <int NC>
+__device__ __noinline__ void surfaceEmission(const DeviceScene& s, const PathQueue& in, const HitBuffer& hits, uint32_t i, uint2 hid, uint4 meta,
+                                             uint32_t flags, uint32_t material, const SlrGpuTriangle& tri, bool isEnv, float* __restrict__ accum) {
+    const Spec<NC> alpha = loadAlpha<NC>(in, i);
+    const float4 o4 = in.org[i], d4 = in.dir[i];
+    const V3 org(o4.x, o4.y, o4.z), dir(d4.x, d4.y, d4.z);
+    const float prevPdf = d4.w;
+    const float wlOffset = __uint_as_float(meta.w);
+    const bool cameraRay = flags & kFlagCameraRay;
+    SurfPt sp;
+    float localArea = 1.0f;
+    if (isEnv) envSurfacePoint(dir, &sp);
+    else { const float4 htuv = hits.tuv[i]; hitSurfacePoint(s, hid.x, hid.y, htuv.x, htuv.y, htuv.z, org, dir, &sp, &localArea); }
+    const V3 dirOut = sp.sf.toLocal(-dir);
+    // DiffuseEDF: 1/pi on the front side; IBLEDF: 1/pi
+    const float edf = (sp.atInfinity || dirOut.z > 0.0f) ? 1.0f / kPi : 0.0f;
+    if (edf <= 0.0f) return;
+    float mis = 1.0f;
+    if (!cameraRay && !(flags & kFlagPrevDelta)) {
+        const float lightProb = lightSelectionProb(s, tri, hid.y, sp.atInfinity);
+        float areaPDF, dist2;
+        if (sp.atInfinity) { areaPDF = envEvaluateUVPDF(s, sp.u / (2 * kPi), sp.v / kPi) / (2 * kPi * kPi * sinf(sp.v)); dist2 = 1.0f; }
+        else { areaPDF = 1.0f / localArea; dist2 = sqLength(sp.p - org); }
+        const float lightPDF = lightProb * areaPDF * dist2 / absDot(dir, sp.gn);
+        mis = (prevPdf * prevPdf) / (lightPDF * lightPDF + prevPdf * prevPdf);
+    }
+    const Spec<NC> Le = materialEmittance<NC>(s, material, sp, wlOffset);
+    float v[NC == 3 ? 4 : NC];
+    const float k = edf * mis * in.weight[i];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) v[c] = alpha.v[c] * Le.v[c] * k;
+    splat<NC>(accum, meta.x, wlOffset, (flags & kFlagStrataInPlace) != 0, v);
+}
+
 // ---------------------------------------------------------------------------------------------
 // surface: what Job::contribution does between a hit and the BSDF of that hit -- emission seen by the
 // ray that arrived (implicit light sampling with MIS), the environment for rays that left the scene,
@@ -190,37 +227,7 @@ surfaceKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitBu
                     material = tri.material;
                     emitting = materialIsEmitting(s, material);
                 }
-                if (emitting) {
-                    const Spec<NC> alpha = loadAlpha<NC>(in, i);
-                    const float4 o4 = in.org[i], d4 = in.dir[i];
-                    const V3 org(o4.x, o4.y, o4.z), dir(d4.x, d4.y, d4.z);
-                    const float prevPdf = d4.w;
-                    const float wlOffset = __uint_as_float(meta.w);
-                    SurfPt sp;
-                    float localArea = 1.0f;
-                    if (isEnv) envSurfacePoint(dir, &sp);
-                    else { const float4 htuv = hits.tuv[i]; hitSurfacePoint(s, hid.x, hid.y, htuv.x, htuv.y, htuv.z, org, dir, &sp, &localArea); }
-                    const V3 dirOut = sp.sf.toLocal(-dir);
-                    // DiffuseEDF: 1/pi on the front side; IBLEDF: 1/pi
-                    const float edf = (sp.atInfinity || dirOut.z > 0.0f) ? 1.0f / kPi : 0.0f;
-                    if (edf > 0.0f) {
-                        float mis = 1.0f;
-                        if (!cameraRay && !(flags & kFlagPrevDelta)) {
-                            const float lightProb = lightSelectionProb(s, tri, hid.y, sp.atInfinity);
-                            float areaPDF, dist2;
-                            if (sp.atInfinity) { areaPDF = envEvaluateUVPDF(s, sp.u / (2 * kPi), sp.v / kPi) / (2 * kPi * kPi * sinf(sp.v)); dist2 = 1.0f; }
-                            else { areaPDF = 1.0f / localArea; dist2 = sqLength(sp.p - org); }
-                            const float lightPDF = lightProb * areaPDF * dist2 / absDot(dir, sp.gn);
-                            mis = (prevPdf * prevPdf) / (lightPDF * lightPDF + prevPdf * prevPdf);
-                        }
-                        const Spec<NC> Le = materialEmittance<NC>(s, material, sp, wlOffset);
-                        float v[NC == 3 ? 4 : NC];
-                        const float k = edf * mis * in.weight[i];
-#pragma unroll
-                        for (int c = 0; c < NC; ++c) v[c] = alpha.v[c] * Le.v[c] * k;
-                        splat<NC>(accum, meta.x, wlOffset, (flags & kFlagStrataInPlace) != 0, v);
-                    }
-                }
+                if (emitting) surfaceEmission<NC>(s, in, hits, i, hid, meta, flags, material, tri, isEnv, accum);
                 bool cont = !isEnv;
                 if (cont && !cameraRay) {
                     // Russian roulette; initY = importance of a unit spectrum = 1. importance(alpha) was left in
@@ -535,7 +542,7 @@ static void launchShadeStage(const SlrGpuScene* sc, const RenderConstants& rc, c
 
 static uint32_t poolCapacity(const SlrGpuRenderParams* p) {
     const unsigned long long totalSamples = (unsigned long long)p->width * p->height * (p->spp_end - p->spp_begin);
-    uint32_t P = p->pool_size ? p->pool_size : (1u << 21);
+    uint32_t P = p->pool_size ? p->pool_size : (1u << 23);     // 8 Mi paths in flight (3.5 GB of queues): measured +9 % over 2 Mi on C1
     if ((unsigned long long)P > totalSamples) P = (uint32_t)totalSamples;
     P = (P + 127u) & ~127u;
     return P == 0 ? 128u : P;

@@ -7,6 +7,10 @@
 #include "traverse.cuh"
 #include "wavefront.cuh"
 
+#ifndef SLR_TRACE_MIN_BLOCKS
+#define SLR_TRACE_MIN_BLOCKS 1
+#endif
+
 namespace slrgpu {
 
 
@@ -35,7 +39,7 @@ struct HitSink {
 };
 
 template <bool INSTANCES, bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock)
+__global__ void __launch_bounds__(kTraceBlock, SLR_TRACE_MIN_BLOCKS)
 extendKernel(const DeviceScene s, PathQueue q, HitBuffer hits, WavefrontCounters* counters) {
     TraversalCounters cnt = {0, 0};
     bool overflow = false;
@@ -73,7 +77,7 @@ template <int NC> struct SplatSink {
 };
 
 template <bool INSTANCES, int NC, bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock)
+__global__ void __launch_bounds__(kTraceBlock, SLR_TRACE_MIN_BLOCKS)
 shadowKernel(const DeviceScene s, ShadowQueue q, float* __restrict__ accum, WavefrontCounters* counters) {
     TraversalCounters cnt = {0, 0};
     bool overflow = false;

@@ -245,86 +245,7 @@ __device__ __forceinline__ void walkBegin(WalkState& w, uint32_t* stack) {
     stack[w.sp++] = 0;      // the top-level root is node 0
 }
 
-// One node visit of the top-level walk: pop, 4-box test, push the inner children that were hit (far to
-// near), test the leaf children that were hit immediately (near to far). Returns true when the ray is finished.
-template <bool INSTANCES, bool ANY_HIT, bool COUNT>
-__device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, uint32_t* stack, TraversalCounters& cnt, bool& overflow) {
-    Ray& r = w.r;
-    const uint32_t nodeIdx = stack[--w.sp];
-    const float4* n = s.nodes + (size_t)nodeIdx * 8;
-    const float4 lox = ldg4(n + 0), loy = ldg4(n + 1), loz = ldg4(n + 2);
-    const float4 hix = ldg4(n + 3), hiy = ldg4(n + 4), hiz = ldg4(n + 5);
-    if (COUNT) ++cnt.nodes;
-    const uint32_t mask = slab4(lox, loy, loz, hix, hiy, hiz, r, w.ix, w.iy, w.iz);
-    if (mask != 0) {
-        const uint4 kids = __ldg(reinterpret_cast<const uint4*>(n + 6));
-        const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(n + 7));
-        const uint32_t T = (w.pos >> (axes & 0xFF)) & 1u;
-        const uint32_t L = (w.pos >> ((axes >> 8) & 0xFF)) & 1u;
-        const uint32_t R = (w.pos >> ((axes >> 16) & 0xFF)) & 1u;
-        // visiting order (OrderTable, QBVH.h:309-312): near side pair first, near child first inside a pair
-        const uint32_t l0 = L ? 0u : 1u, r0 = R ? 2u : 3u;
-        uint32_t order[4];
-        order[0] = T ? l0 : r0;        order[1] = T ? (l0 ^ 1u) : (r0 ^ 1u);
-        order[2] = T ? r0 : l0;        order[3] = T ? (r0 ^ 1u) : (l0 ^ 1u);
-        uint32_t ch[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t lane = order[i];
-            uint32_t c = lane == 0 ? kids.x : lane == 1 ? kids.y : lane == 2 ? kids.z : kids.w;
-            ch[i] = ((mask >> lane) & 1u) ? c : kEmptyChild;
-        }
-#pragma unroll
-        for (int i = 3; i >= 0; --i) {
-            const uint32_t c = ch[i];
-            if (c == kEmptyChild || (c >> 31)) continue;
-            if (w.sp >= kStackSize) { overflow = true; continue; }
-            stack[w.sp++] = c & 0x07FFFFFFu;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t c = ch[i];
-            if (c == kEmptyChild || !(c >> 31)) continue;
-            const uint32_t first = c & 0x07FFFFFFu;
-            const uint32_t count = (c >> 27) & 0xFu;
-            for (uint32_t j = 0; j < count; ++j) {
-                const float4* rec = s.leaves + (size_t)(first + j) * 3;
-                const float4 a = ldg4(rec);
-                const uint32_t id = __float_as_uint(a.w);
-                if (COUNT) ++cnt.tris;
-                if (id & 0x80000000u) {
-                    if constexpr (INSTANCES) {
-                        const uint32_t instId = id & 0x7FFFFFFFu;
-                        const SlrGpuInstance* inst = s.instances + instId;
-                        Ray lr;
-                        mulPoint(inst->mat_inv, r.ox, r.oy, r.oz, &lr.ox, &lr.oy, &lr.oz);
-                        mulVector(inst->mat_inv, r.dx, r.dy, r.dz, &lr.dx, &lr.dy, &lr.dz);
-                        lr.tmin = r.tmin; lr.tmax = r.tmax;
-                        if (traverse<1, ANY_HIT, COUNT>(s, inst->root_node, lr, w.hit, stack, w.sp, cnt, overflow)) {
-                            r.tmax = lr.tmax;
-                            w.hit.inst = instId;
-                            w.found = true;
-                            if (ANY_HIT) return true;
-                        }
-                    }
-                    continue;
-                }
-                const float4 b = ldg4(rec + 1), cc = ldg4(rec + 2);
-                float t, b0, b1;
-                if (triangleTest(a, b, cc, r, &t, &b0, &b1)) {
-                    r.tmax = t;
-                    w.hit.prim = id; w.hit.inst = SLRGPU_INVALID_ID;
-                    w.hit.t = t; w.hit.u = b0; w.hit.v = b1;
-                    w.found = true;
-                    if (ANY_HIT) return true;
-                }
-            }
-        }
-    }
-    return w.sp == 0;
-}
-
-// ---- instanced scenes: the nested traversal is part of the same state machine -------------------
+// ---- the step of the walk; instancing is part of the same state machine ---------------------------
 // Entering an instance leaf record transforms the ray into the instance's space, pushes a RETURN marker
 // and the nested root; the nested nodes are then ordinary steps of the walk (so they take part in the
 // dynamic fetch like top-level nodes). Popping the marker restores the world-space ray and the leaf
@@ -361,22 +282,84 @@ __device__ __forceinline__ void walkSetRay(WalkState& w) {
     w.pos = (w.r.dx >= 0.0f ? 1u : 0u) | (w.r.dy >= 0.0f ? 2u : 0u) | (w.r.dz >= 0.0f ? 4u : 0u);
 }
 
-// One step of the instanced walk: either the leaf records that are due (triangles in a row; an instance
-// record enters the instance), or one stack entry (a node, or the return marker). Returns true when the
-// ray is finished.
-template <bool ANY_HIT, bool COUNT>
-__device__ __forceinline__ bool walkStepInstanced(const DeviceScene& s, WalkState& w, InstanceWalkState& iw, uint32_t* stack,
-                                                  TraversalCounters& cnt, bool& overflow) {
+// One step of the walk: pop one stack entry -- a node: 4-box test, push the inner children that were hit
+// (far to near), queue the leaf children that were hit (near to far); or the return marker of an instance --
+// then test the queued leaf records in ONE loop shared by all child slots (so lanes whose leaves sit at
+// different child positions run the same instructions). An instance record enters the instance and ends
+// the step. Returns true when the ray is finished.
+template <bool INSTANCES, bool ANY_HIT, bool COUNT>
+__device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, InstanceWalkState& iw, uint32_t* stack,
+                                         TraversalCounters& cnt, bool& overflow) {
     Ray& r = w.r;
-    if (iw.leaves.count != 0) {
-        while (iw.leaves.count != 0) {
-            const float4* rec = s.leaves + (size_t)iw.leaves.first * 3;
-            const float4 a = ldg4(rec);
-            ++iw.leaves.first;
-            if (--iw.leaves.count == 0) iw.leaves.next();
-            const uint32_t id = __float_as_uint(a.w);
-            if (COUNT) ++cnt.tris;
-            if (id & 0x80000000u) {
+    LeafQueue local;
+    LeafQueue& leaves = INSTANCES ? iw.leaves : local;
+    if (!INSTANCES) local.clear();
+    const uint32_t entry = stack[--w.sp];
+    if (INSTANCES && entry == kReturnMarker) {
+        r.ox = iw.wox; r.oy = iw.woy; r.oz = iw.woz; r.dx = iw.wdx; r.dy = iw.wdy; r.dz = iw.wdz;   // tmax carries over (SurfaceObject.cpp:314)
+        walkSetRay(w);
+        iw.leaves = iw.saved;
+        iw.curInst = SLRGPU_INVALID_ID;
+    } else {
+        const float4* n = s.nodes + (size_t)entry * 8;
+        const float4 lox = ldg4(n + 0), loy = ldg4(n + 1), loz = ldg4(n + 2);
+        const float4 hix = ldg4(n + 3), hiy = ldg4(n + 4), hiz = ldg4(n + 5);
+        if (COUNT) ++cnt.nodes;
+        const uint32_t mask = slab4(lox, loy, loz, hix, hiy, hiz, r, w.ix, w.iy, w.iz);
+        if (mask != 0) {
+            const uint4 kids = __ldg(reinterpret_cast<const uint4*>(n + 6));
+            const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(n + 7));
+            const uint32_t T = (w.pos >> (axes & 0xFF)) & 1u;
+            const uint32_t L = (w.pos >> ((axes >> 8) & 0xFF)) & 1u;
+            const uint32_t R = (w.pos >> ((axes >> 16) & 0xFF)) & 1u;
+            // visiting order (OrderTable, QBVH.h:309-312): near side pair first, near child first inside a pair
+            const uint32_t l0 = L ? 0u : 1u, r0 = R ? 2u : 3u;
+            uint32_t order[4];
+            order[0] = T ? l0 : r0;        order[1] = T ? (l0 ^ 1u) : (r0 ^ 1u);
+            order[2] = T ? r0 : l0;        order[3] = T ? (r0 ^ 1u) : (l0 ^ 1u);
+            uint32_t ch[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t lane = order[i];
+                uint32_t c = lane == 0 ? kids.x : lane == 1 ? kids.y : lane == 2 ? kids.z : kids.w;
+                ch[i] = ((mask >> lane) & 1u) ? c : kEmptyChild;
+            }
+#pragma unroll
+            for (int i = 3; i >= 0; --i) {
+                const uint32_t c = ch[i];
+                if (c == kEmptyChild || (c >> 31)) continue;
+                if (w.sp >= kStackSize) { overflow = true; continue; }
+                stack[w.sp++] = c & 0x07FFFFFFu;
+            }
+            // leaf children in visiting order: the first becomes the current range, up to three wait
+            uint32_t q0 = kEmptyChild, q1 = kEmptyChild, q2 = kEmptyChild, q3 = kEmptyChild;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t c = ch[i];
+                if (c != kEmptyChild && (c >> 31)) {
+                    if (q0 == kEmptyChild) q0 = c;
+                    else if (q1 == kEmptyChild) q1 = c;
+                    else if (q2 == kEmptyChild) q2 = c;
+                    else q3 = c;
+                }
+            }
+            if (q0 != kEmptyChild) {
+                leaves.first = q0 & 0x07FFFFFFu;
+                leaves.count = (q0 >> 27) & 0xFu;
+                leaves.pending0 = q1; leaves.pending1 = q2; leaves.pending2 = q3;
+                if (leaves.count == 0) leaves.next();
+            }
+        }
+    }
+    while (leaves.count != 0) {
+        const float4* rec = s.leaves + (size_t)leaves.first * 3;
+        const float4 a = ldg4(rec);
+        ++leaves.first;
+        if (--leaves.count == 0) leaves.next();
+        const uint32_t id = __float_as_uint(a.w);
+        if (COUNT) ++cnt.tris;
+        if (id & 0x80000000u) {
+            if constexpr (INSTANCES) {
                 if (iw.curInst != SLRGPU_INVALID_ID) continue;          // nested instancing is rejected at scene build
                 if (w.sp + 2 > kStackSize) { overflow = true; continue; }   // no room for marker + root: reported as overflow
                 const uint32_t instId = id & 0x7FFFFFFFu;
@@ -394,75 +377,19 @@ __device__ __forceinline__ bool walkStepInstanced(const DeviceScene& s, WalkStat
                 stack[w.sp++] = inst->root_node;
                 return false;
             }
-            const float4 b = ldg4(rec + 1), cc = ldg4(rec + 2);
-            float t, b0, b1;
-            if (triangleTest(a, b, cc, r, &t, &b0, &b1)) {
-                r.tmax = t;
-                w.hit.prim = id; w.hit.inst = iw.curInst;
-                w.hit.t = t; w.hit.u = b0; w.hit.v = b1;
-                w.found = true;
-                if (ANY_HIT) return true;
-            }
+            continue;
         }
-        return w.sp == 0;
-    }
-    const uint32_t entry = stack[--w.sp];
-    if (entry == kReturnMarker) {
-        r.ox = iw.wox; r.oy = iw.woy; r.oz = iw.woz; r.dx = iw.wdx; r.dy = iw.wdy; r.dz = iw.wdz;   // tmax carries over (SurfaceObject.cpp:314)
-        walkSetRay(w);
-        iw.leaves = iw.saved;
-        iw.curInst = SLRGPU_INVALID_ID;
-        return w.sp == 0 && iw.leaves.count == 0;
-    }
-    const float4* n = s.nodes + (size_t)entry * 8;
-    const float4 lox = ldg4(n + 0), loy = ldg4(n + 1), loz = ldg4(n + 2);
-    const float4 hix = ldg4(n + 3), hiy = ldg4(n + 4), hiz = ldg4(n + 5);
-    if (COUNT) ++cnt.nodes;
-    const uint32_t mask = slab4(lox, loy, loz, hix, hiy, hiz, r, w.ix, w.iy, w.iz);
-    if (mask != 0) {
-        const uint4 kids = __ldg(reinterpret_cast<const uint4*>(n + 6));
-        const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(n + 7));
-        const uint32_t T = (w.pos >> (axes & 0xFF)) & 1u;
-        const uint32_t L = (w.pos >> ((axes >> 8) & 0xFF)) & 1u;
-        const uint32_t R = (w.pos >> ((axes >> 16) & 0xFF)) & 1u;
-        const uint32_t l0 = L ? 0u : 1u, r0 = R ? 2u : 3u;
-        uint32_t order[4];
-        order[0] = T ? l0 : r0;        order[1] = T ? (l0 ^ 1u) : (r0 ^ 1u);
-        order[2] = T ? r0 : l0;        order[3] = T ? (r0 ^ 1u) : (l0 ^ 1u);
-        uint32_t ch[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t lane = order[i];
-            uint32_t c = lane == 0 ? kids.x : lane == 1 ? kids.y : lane == 2 ? kids.z : kids.w;
-            ch[i] = ((mask >> lane) & 1u) ? c : kEmptyChild;
-        }
-#pragma unroll
-        for (int i = 3; i >= 0; --i) {
-            const uint32_t c = ch[i];
-            if (c == kEmptyChild || (c >> 31)) continue;
-            if (w.sp >= kStackSize) { overflow = true; continue; }
-            stack[w.sp++] = c & 0x07FFFFFFu;
-        }
-        // leaf children in visiting order: the first becomes the current range, up to three wait
-        uint32_t q[4] = {kEmptyChild, kEmptyChild, kEmptyChild, kEmptyChild};
-        int nq = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t c = ch[i];
-            if (c != kEmptyChild && (c >> 31)) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) if (k == nq) q[k] = c;
-                ++nq;
-            }
-        }
-        if (nq > 0) {
-            iw.leaves.first = q[0] & 0x07FFFFFFu;
-            iw.leaves.count = (q[0] >> 27) & 0xFu;
-            iw.leaves.pending0 = q[1]; iw.leaves.pending1 = q[2]; iw.leaves.pending2 = q[3];
-            if (iw.leaves.count == 0) iw.leaves.next();
+        const float4 b = ldg4(rec + 1), cc = ldg4(rec + 2);
+        float t, b0, b1;
+        if (triangleTest(a, b, cc, r, &t, &b0, &b1)) {
+            r.tmax = t;
+            w.hit.prim = id; w.hit.inst = INSTANCES ? iw.curInst : SLRGPU_INVALID_ID;
+            w.hit.t = t; w.hit.u = b0; w.hit.v = b1;
+            w.found = true;
+            if (ANY_HIT) return true;
         }
     }
-    return w.sp == 0 && iw.leaves.count == 0;
+    return w.sp == 0;
 }
 
 // Runs `n` rays through the scene with one warp-cooperative loop. Source::load(i, Ray&) fetches ray i,
@@ -518,10 +445,7 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
 #pragma unroll 1
         for (int it = 0; it < kStepsPerRound; ++it) {
             if (active) {
-                bool finished;
-                if constexpr (INSTANCES) finished = walkStepInstanced<ANY_HIT, COUNT>(s, w, iw, stack, cnt, overflow);
-                else finished = walkStep<false, ANY_HIT, COUNT>(s, w, stack, cnt, overflow);
-                if (finished) {
+                if (walkStep<INSTANCES, ANY_HIT, COUNT>(s, w, iw, stack, cnt, overflow)) {
                     sink.done(idx, w, cnt);
                     active = false;
                 }

@@ -154,14 +154,16 @@ SLRGPU_API int slrhost_render_range(SlrHostScene* s, int device, int width, int 
         renderer.sampleBegin = (uint32_t)spp_begin;
         renderer.exportProgressiveImages = bmp_dir != nullptr;
         if (bmp_dir) renderer.outputDirectory = bmp_dir;
-        renderer.render(s->render, settings);
+        // with a caller buffer the sensor renders straight into it (no frame-sized copies on the way out)
+        s->render.sensor->bindExternal(accum);
+        try { renderer.render(s->render, settings); } catch (...) { s->render.sensor->bindExternal(nullptr); throw; }
         const ImageSensor& sensor = *s->render.sensor;
-        if (accum) std::memcpy(accum, sensor.data(), sizeof(float) * (size_t)sensor.width() * sensor.height() * sensor.channels());
         if (stats) {
             const RenderStatistics& st = renderer.lastStatistics;
             stats[0] = (double)st.paths; stats[1] = (double)st.rays; stats[2] = st.deviceSeconds; stats[3] = st.wallSeconds;
             stats[4] = st.uploadSeconds; stats[5] = sensor.channels();
         }
+        s->render.sensor->bindExternal(nullptr);
         return 0;
     } catch (const std::exception& e) { return fail("%s", e.what()); }
 }

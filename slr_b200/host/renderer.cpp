@@ -9,10 +9,14 @@
 namespace slr {
 
 void ImageSensor::init(uint32_t width, uint32_t height, uint32_t channels) {
-    m_width = width; m_height = height; m_channels = channels;
-    m_data.assign((size_t)width * height * channels, 0.0f);
+    initForOverwrite(width, height, channels);
+    clear();
 }
-void ImageSensor::clear() { std::fill(m_data.begin(), m_data.end(), 0.0f); }
+void ImageSensor::initForOverwrite(uint32_t width, uint32_t height, uint32_t channels) {
+    m_width = width; m_height = height; m_channels = channels;
+    if (!m_external) m_data.resize((size_t)width * height * channels);
+}
+void ImageSensor::clear() { std::fill(data(), data() + (size_t)m_width * m_height * m_channels, 0.0f); }
 
 void ImageSensor::pixelRGB(uint32_t x, uint32_t y, float scale, float rgb[3]) const {
     const float* p = pixel(x, y);
@@ -84,7 +88,8 @@ void GPUPathTracingRenderer::render(const RenderScene& scene, const RenderSettin
         throw std::runtime_error(std::string("slrgpu_scene_create failed: ") + slrgpu_last_error());
     lastStatistics.uploadSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - up0).count();
     const uint32_t channels = slrgpu_scene_channels(gpu);
-    sensor->init(W, H, channels);
+    if (exportProgressiveImages) sensor->init(W, H, channels);
+    else sensor->initForOverwrite(W, H, channels);      // slrgpu_render overwrites the whole frame
 
     SlrGpuRenderParams p;
     std::memset(&p, 0, sizeof(p));

@@ -38,9 +38,15 @@ class ImageSensor {
     uint32_t m_width = 0, m_height = 0, m_channels = 16;
     float m_sensitivity = 1.0f;
     std::vector<float> m_data;
+    float* m_external = nullptr;      // caller-owned storage the sensor renders into instead of m_data (bindExternal)
 public:
     explicit ImageSensor(float sensitivity = 1.0f) : m_sensitivity(sensitivity) {}
     void init(uint32_t width, uint32_t height, uint32_t channels = 16);
+    // Like init() but WITHOUT clearing: for a renderer that overwrites every value (the GPU path downloads a whole frame).
+    void initForOverwrite(uint32_t width, uint32_t height, uint32_t channels = 16);
+    // The next init*/render uses `storage` (width*height*channels floats, caller-owned, must outlive the use of the
+    // sensor) instead of the sensor's own vector: saves a frame-sized copy when the caller wants the data anyway.
+    void bindExternal(float* storage) { m_external = storage; }
     void clear();
     uint32_t width() const { return m_width; }
     uint32_t height() const { return m_height; }
@@ -49,9 +55,9 @@ public:
     uint32_t tileHeight() const { return 8; }
     uint32_t numTileX() const { return (m_width + 7) >> 3; }
     uint32_t numTileY() const { return (m_height + 7) >> 3; }
-    const float* pixel(uint32_t x, uint32_t y) const { return &m_data[((size_t)y * m_width + x) * m_channels]; }
-    float* data() { return m_data.data(); }
-    const float* data() const { return m_data.data(); }
+    const float* pixel(uint32_t x, uint32_t y) const { return data() + ((size_t)y * m_width + x) * m_channels; }
+    float* data() { return m_external ? m_external : m_data.data(); }
+    const float* data() const { return m_external ? m_external : m_data.data(); }
     // linear sRGB of one pixel scaled by `scale` (before tone mapping)
     void pixelRGB(uint32_t x, uint32_t y, float scale, float rgb[3]) const;
     void saveImage(const std::string& path, float scale) const;
