@@ -26,7 +26,7 @@ constexpr int kMaterialBlock = 128;
 constexpr int kRaygenBlock = 128;
 // resident blocks per SM the register allocation of the shade kernels is bounded for (tuning knobs, see profiles/)
 #ifndef SLR_MATERIAL_MIN_BLOCKS
-#define SLR_MATERIAL_MIN_BLOCKS 1
+#define SLR_MATERIAL_MIN_BLOCKS 3
 #endif
 #ifndef SLR_SURFACE_MIN_BLOCKS
 #define SLR_SURFACE_MIN_BLOCKS 1

@@ -68,6 +68,29 @@ __device__ __forceinline__ uint32_t slab4(const float4 lox, const float4 loy, co
     return mask;
 }
 
+// The same test with the near / far planes already selected by the caller (the selection depends only on the
+// sign of the ray direction, so the walk fetches lo or hi per axis by ADDRESS instead of fetching both and
+// selecting per lane): identical operands, identical operations.
+__device__ __forceinline__ uint32_t slab4NearFar(const float4 nx, const float4 ny, const float4 nz,
+                                                 const float4 fx, const float4 fy, const float4 fz,
+                                                 const Ray& r, float ix, float iy, float iz) {
+    uint32_t mask = 0;
+#define SLAB_LANE(L, bit)                                                   \
+    {                                                                       \
+        float tn = r.tmin, tf = r.tmax;                                     \
+        tn = fmaxf((nx.L - r.ox) * ix, tn);                                 \
+        tn = fmaxf((ny.L - r.oy) * iy, tn);                                 \
+        tn = fmaxf((nz.L - r.oz) * iz, tn);                                 \
+        tf = fminf((fx.L - r.ox) * ix, tf);                                 \
+        tf = fminf((fy.L - r.oy) * iy, tf);                                 \
+        tf = fminf((fz.L - r.oz) * iz, tf);                                 \
+        if (tn <= tf) mask |= bit;                                          \
+    }
+    SLAB_LANE(x, 1u) SLAB_LANE(y, 2u) SLAB_LANE(z, 4u) SLAB_LANE(w, 8u)
+#undef SLAB_LANE
+    return mask;
+}
+
 // Moller-Trumbore, two-sided, exactly the reference's sequence of operations and comparisons
 // (NaNs fall through the range checks the same way because the comparisons are not negated).
 __device__ __forceinline__ bool triangleTest(const float4 a, const float4 b, const float4 c, const Ray& r,
@@ -113,94 +136,6 @@ __device__ __forceinline__ void mulVector(const float* __restrict__ m, float x, 
     *oz = m[2] * x + m[6] * y + m[10] * z;
 }
 
-// Traverses the BVH rooted at `root` for ray `r` (r.tmax shrinks on accepted hits). `sp` is the
-// first free stack slot: a nested (instance) traversal runs on the same stack above its caller's
-// entries and returns when it has popped back down to its own base, which reproduces the
-// reference's recursion (the nested traversal completes before the caller's next leaf record).
-// LEVEL bounds the instancing depth at compile time (0 = top level).
-template <int LEVEL, bool ANY_HIT, bool COUNT>
-__device__ bool traverse(const DeviceScene& s, uint32_t root, Ray& r, Hit& hit, uint32_t* stack, int sp,
-                         TraversalCounters& cnt, bool& overflow) {
-    const float ix = 1.0f / r.dx, iy = 1.0f / r.dy, iz = 1.0f / r.dz;
-    const uint32_t pos = (r.dx >= 0.0f ? 1u : 0u) | (r.dy >= 0.0f ? 2u : 0u) | (r.dz >= 0.0f ? 4u : 0u);
-    bool found = false;
-    const int base = sp;
-    stack[sp++] = root;
-    while (sp > base) {
-        const uint32_t nodeIdx = stack[--sp];
-        const float4* n = s.nodes + (size_t)nodeIdx * 8;
-        const float4 lox = ldg4(n + 0), loy = ldg4(n + 1), loz = ldg4(n + 2);
-        const float4 hix = ldg4(n + 3), hiy = ldg4(n + 4), hiz = ldg4(n + 5);
-        if (COUNT) ++cnt.nodes;
-        const uint32_t mask = slab4(lox, loy, loz, hix, hiy, hiz, r, ix, iy, iz);
-        if (mask == 0) continue;
-        const uint4 kids = __ldg(reinterpret_cast<const uint4*>(n + 6));
-        const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(n + 7));
-        const uint32_t T = (pos >> (axes & 0xFF)) & 1u;
-        const uint32_t L = (pos >> ((axes >> 8) & 0xFF)) & 1u;
-        const uint32_t R = (pos >> ((axes >> 16) & 0xFF)) & 1u;
-        // visiting order (OrderTable, QBVH.h:309-312): near side pair first, near child first inside a pair
-        const uint32_t l0 = L ? 0u : 1u, r0 = R ? 2u : 3u;
-        uint32_t order[4];
-        order[0] = T ? l0 : r0;        order[1] = T ? (l0 ^ 1u) : (r0 ^ 1u);
-        order[2] = T ? r0 : l0;        order[3] = T ? (r0 ^ 1u) : (l0 ^ 1u);
-        uint32_t ch[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t lane = order[i];
-            uint32_t c = lane == 0 ? kids.x : lane == 1 ? kids.y : lane == 2 ? kids.z : kids.w;
-            ch[i] = ((mask >> lane) & 1u) ? c : kEmptyChild;
-        }
-#pragma unroll
-        for (int i = 3; i >= 0; --i) {
-            const uint32_t c = ch[i];
-            if (c == kEmptyChild || (c >> 31)) continue;
-            if (sp >= kStackSize) { overflow = true; continue; }
-            stack[sp++] = c & 0x07FFFFFFu;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t c = ch[i];
-            if (c == kEmptyChild || !(c >> 31)) continue;
-            const uint32_t first = c & 0x07FFFFFFu;
-            const uint32_t count = (c >> 27) & 0xFu;
-            for (uint32_t j = 0; j < count; ++j) {
-                const float4* rec = s.leaves + (size_t)(first + j) * 3;
-                const float4 a = ldg4(rec);
-                const uint32_t id = __float_as_uint(a.w);
-                if (COUNT) ++cnt.tris;
-                if (id & 0x80000000u) {
-                    if constexpr (LEVEL < 1) {
-                        const uint32_t instId = id & 0x7FFFFFFFu;
-                        const SlrGpuInstance* inst = s.instances + instId;
-                        Ray lr;
-                        mulPoint(inst->mat_inv, r.ox, r.oy, r.oz, &lr.ox, &lr.oy, &lr.oz);
-                        mulVector(inst->mat_inv, r.dx, r.dy, r.dz, &lr.dx, &lr.dy, &lr.dz);
-                        lr.tmin = r.tmin; lr.tmax = r.tmax;
-                        if (traverse<LEVEL + 1, ANY_HIT, COUNT>(s, inst->root_node, lr, hit, stack, sp, cnt, overflow)) {
-                            r.tmax = lr.tmax;
-                            hit.inst = instId;
-                            found = true;
-                            if (ANY_HIT) return true;
-                        }
-                    }
-                    continue;
-                }
-                const float4 b = ldg4(rec + 1), cc = ldg4(rec + 2);
-                float t, b0, b1;
-                if (triangleTest(a, b, cc, r, &t, &b0, &b1)) {
-                    r.tmax = t;
-                    hit.prim = id; hit.inst = SLRGPU_INVALID_ID;
-                    hit.t = t; hit.u = b0; hit.v = b1;
-                    found = true;
-                    if (ANY_HIT) return true;
-                }
-            }
-        }
-    }
-    return found;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Warp-cooperative scheduling of many rays over the traversal above ("persistent threads with
 // dynamic fetch"): a ray's traversal length varies from a handful to dozens of node visits, so with
@@ -211,7 +146,7 @@ __device__ bool traverse(const DeviceScene& s, uint32_t root, Ray& r, Hit& hit, 
 // reference's (same pops, same box tests, same leaf order): only the interleaving ACROSS rays changes.
 //
 // The top-level walk is a per-lane state machine (one node visit per step); an instance leaf record
-// runs the nested traversal to completion inside the step (traverse<1>), as the reference's recursion does.
+// is entered by pushing a return marker (see walkStep), as the reference's recursion does.
 // (A "while-while" split into separate node and leaf phases was measured too -- round 1, profiles/ --
 // and was slower on both benchmarks: rays here are short, the extra state and ballots cost more than
 // the leaf-phase coherence returns.)
@@ -236,9 +171,9 @@ struct WalkState {
     TraversalCounters cnt0;      // the lane's running counters when this ray started (per-ray counts = difference)
 };
 
+__device__ __forceinline__ void walkSetRay(WalkState& w);
 __device__ __forceinline__ void walkBegin(WalkState& w, uint32_t* stack) {
-    w.ix = 1.0f / w.r.dx; w.iy = 1.0f / w.r.dy; w.iz = 1.0f / w.r.dz;
-    w.pos = (w.r.dx >= 0.0f ? 1u : 0u) | (w.r.dy >= 0.0f ? 2u : 0u) | (w.r.dz >= 0.0f ? 4u : 0u);
+    walkSetRay(w);
     w.hit.prim = SLRGPU_INVALID_ID; w.hit.inst = SLRGPU_INVALID_ID; w.hit.t = INFINITY; w.hit.u = 0.0f; w.hit.v = 0.0f;
     w.found = false;
     w.sp = 0;
@@ -277,9 +212,12 @@ struct InstanceWalkState {
     uint32_t curInst;        // SLRGPU_INVALID_ID at the top level
 };
 
+// pos bits 0-2: direction component >= 0 (child ordering, QBVH.h:309-312); bits 8-10: invDir > 0 per axis
+// (which plane is the near one, QBVH.h:68-73) -- the two differ for a component of -0.0
 __device__ __forceinline__ void walkSetRay(WalkState& w) {
     w.ix = 1.0f / w.r.dx; w.iy = 1.0f / w.r.dy; w.iz = 1.0f / w.r.dz;
-    w.pos = (w.r.dx >= 0.0f ? 1u : 0u) | (w.r.dy >= 0.0f ? 2u : 0u) | (w.r.dz >= 0.0f ? 4u : 0u);
+    w.pos = (w.r.dx >= 0.0f ? 1u : 0u) | (w.r.dy >= 0.0f ? 2u : 0u) | (w.r.dz >= 0.0f ? 4u : 0u) |
+            (w.ix > 0.0f ? 0x100u : 0u) | (w.iy > 0.0f ? 0x200u : 0u) | (w.iz > 0.0f ? 0x400u : 0u);
 }
 
 // One step of the walk: pop one stack entry -- a node: 4-box test, push the inner children that were hit
@@ -302,10 +240,12 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
         iw.curInst = SLRGPU_INVALID_ID;
     } else {
         const float4* n = s.nodes + (size_t)entry * 8;
-        const float4 lox = ldg4(n + 0), loy = ldg4(n + 1), loz = ldg4(n + 2);
-        const float4 hix = ldg4(n + 3), hiy = ldg4(n + 4), hiz = ldg4(n + 5);
+        // lo planes at n+0..2, hi planes at n+3..5: near = lo where invDir > 0, else hi
+        const uint32_t ox = (w.pos & 0x100u) ? 0u : 3u, oy = (w.pos & 0x200u) ? 0u : 3u, oz = (w.pos & 0x400u) ? 0u : 3u;
+        const float4 nx = ldg4(n + ox), ny = ldg4(n + 1 + oy), nz = ldg4(n + 2 + oz);
+        const float4 fx = ldg4(n + 3 - ox), fy = ldg4(n + 4 - oy), fz = ldg4(n + 5 - oz);
         if (COUNT) ++cnt.nodes;
-        const uint32_t mask = slab4(lox, loy, loz, hix, hiy, hiz, r, w.ix, w.iy, w.iz);
+        const uint32_t mask = slab4NearFar(nx, ny, nz, fx, fy, fz, r, w.ix, w.iy, w.iz);
         if (mask != 0) {
             const uint4 kids = __ldg(reinterpret_cast<const uint4*>(n + 6));
             const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(n + 7));

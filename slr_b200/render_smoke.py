@@ -16,7 +16,7 @@ def run():
     import render_util as ru
     from . import capi
     g = np.load(os.path.join(ru.GOLDEN, "render_spheres.npz"))
-    size, block, spp = int(g["size"]), int(g["block"]), 512
+    size, block, spp = int(g["size"]), int(g["block"]), 2048
     work = tempfile.mkdtemp(prefix="slr_smoke_")
     path = ru.scene_file("spheres", work, size, size, spp)
     hs = capi.read_scene(path)

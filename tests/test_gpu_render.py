@@ -8,8 +8,8 @@ parity is defined (hard part 5). Tolerances, all on linear 
     0.5 % of the squared errors are trimmed from both sides of the comparison (render_util.rel_rmse);
   * image means per channel within 1 % (bias check; values clipped at the reference's 99.8th percentile);
   * against the committed golden block means (tests/golden/render_*.npz, made by make_render_golden.py
-    from the reference at high spp): every 8x8 block mean within 6 sigma of the golden's own two-seed
-    spread plus 2 %.
+    from the reference: 8 seeds x 2048 spp at 64x64): the GPU image at 16384 spp must have >= 99 % of its
+    8x8 block means within 6 standard errors (golden and GPU noise combined) + 1 %, image means within 1 %.
 Size-independent properties at larger sizes: sample-range additivity (the multi-GPU partition),
 independence of the in-flight pool size, determinism.
 """
@@ -82,9 +82,9 @@ def test_image_matches_golden_block_means(name, workdir):
     # the GPU image has gpu_spp samples, the golden ref_spp: scale the golden's per-block sigma
     sig = sigma * np.sqrt(float(g["ref_spp"]) / spp + 1.0)
     err = np.abs(got - want)
-    tol = 6.0 * sig + 0.02 * want + 1e-6
+    tol = 6.0 * sig + 0.01 * want + 1e-7
     bad = err > tol
-    assert bad.mean() <= 0.01, f"{bad.sum()} of {bad.size} block means outside 6 sigma + 2 %: worst {np.max(err / tol):.2f}x"
+    assert bad.mean() <= 0.01, f"{bad.sum()} of {bad.size} block means outside 6 sigma + 1 %: worst {np.max(err / tol):.2f}x"
     ratio = got.mean((0, 1)) / want.mean((0, 1))
     assert np.all(np.abs(ratio - 1.0) < 0.01), f"image mean ratio {ratio}"
 
