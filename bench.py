@@ -10,6 +10,7 @@ Workloads
   cornell_spheres (default)  the path tracer on BASELINE.json configs[0], Cornell_Box_Spheres 512x512 64 spp
               spectral -- the configuration north_star's >= 100x target is quoted on; metric Mpaths/s
               (slr_b200/render_bench.py).
+  materials | ibl | instanced   BASELINE configs[1..3] through the same code (slr_b200/render_bench.py WORKLOADS).
   intersect   incoherent-ray closest-hit microbench (BASELINE.json configs[4] at a single-GPU size):
               heightfield triangle mesh -> host SBVH -> QBVH, random rays; metric Mrays/s.
 

@@ -32,6 +32,13 @@ WORKLOADS = {
     "cornell_spheres": ("spheres", 512, 512, 64,
                         "Cornell_Box_Spheres 512x512 64spp unidirectional PT spectral (BASELINE configs[0])"),
     "cornell_diffuse": ("diffuse", 512, 512, 64, "empty Cornell box 512x512 64spp unidirectional PT spectral"),
+    "materials": ("materials", 1024, 1024, 256,
+                  "Cornell_Box_ColorChecker 1024x1024 256spp, GGX/Ward/Oren-Nayar/Ashikhmin/mix/rough-glass with procedural textures (BASELINE configs[1])"),
+    "ibl": ("ibl_full", 1024, 1024, 256,
+            "IBL_Test 1024x1024 256spp, synthetic 2048x1024 HDR environment, importance sampling + thin lens (BASELINE configs[2])"),
+    "instanced": ("instanced_10m", 1920, 1080, 128,
+                  "100 instances of a 100,488-triangle procedural mesh (10 M instanced triangles, two-level SBVH->QBVH), 1920x1080, "
+                  "128 spp per GPU = 1024 spp on 8 GPUs (BASELINE configs[3])"),
 }
 
 
@@ -56,9 +63,17 @@ def _ref_step(path, w, h, spp):
     return j, wall
 
 
+def bounded_spp(w, h, spp, max_paths=40e6):
+    """Samples per pixel of one reference step: the whole workload when it is at most ~40 M paths (C1: all 64 spp),
+    else the largest count that keeps a step near 10-15 s of host time. Mpaths/s does not depend on it (the
+    reference's per-pass time is constant)."""
+    return int(max(1, min(spp, max_paths // (w * h))))
+
+
 def cpu_baseline(path, w, h, spp):
     """The reference's own PathTracingRenderer (oracle/_ref/ref_render, built from /root/reference) on
     this box's host cores: std::thread::hardware_concurrency() workers, shipped default accelerator (SBVH)."""
+    spp = bounded_spp(w, h, spp)
     j, wall = _ref_step(path, w, h, spp)
     return {"value": j["mpaths_per_s"], "unit": "Mpaths/s", "cores": j["threads"], "kind": "reference",
             "sample": f"the same scene at {w}x{h}, {spp} spp ({w * h * spp} paths) through the reference's "
@@ -71,7 +86,7 @@ def run_reference(args, rank):
         return
     path, w, h, spp, desc = _scene(args)
     total = args.steps + args.warmup
-    step_spp = spp if total <= 20 else max(8, spp // 4)     # keep the whole run within a few minutes
+    step_spp = bounded_spp(w, h, spp, 40e6 if total <= 20 else 10e6)     # keep the whole run within a few minutes
     vals = []
     t0 = time.perf_counter()
     for i in range(total):

@@ -396,4 +396,5 @@ SCENES = {
     "ibl_full": write_ibl_test,
     "instanced": _small_instanced,
     "instanced_full": write_instanced,
+    "instanced_10m": lambda d, width=1920, height=1080, spp=1024: write_instanced(d, width, height, spp, base_segments=(318, 159)),
 }
