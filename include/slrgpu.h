@@ -388,6 +388,23 @@ SLRGPU_API int slrgpu_render(SlrGpuScene* scene, const SlrGpuRenderParams* param
 SLRGPU_API int slrgpu_render_device(SlrGpuScene* scene, const SlrGpuRenderParams* params, float* accum_device,
                                     void* stream, SlrGpuRenderStats* stats);
 
+/* ---------------------------------------------------------------------------------------------
+ * Shading probe (for parity tests): runs, for every probe ray, the same device functions the material
+ * kernels run -- closest hit, surface point (normal map, instance transform), material -> BSDF with its
+ * textures and spectra, BSDF::sample with the given random numbers, BSDF::evaluate / evaluatePDF for a
+ * given world direction, emittance -- and returns the values the reference produces with
+ * Intersection::getSurfacePoint, SurfacePoint::createBSDF, BSDF::sample/evaluate/evaluatePDF
+ * (PathTracingRenderer.cpp:147-210). Spectral scenes only.
+ * probes: n x 14 floats: org[3] dir[3] wlOffset uLambda uComponent uDir0 uDir1 evalDirWorld[3]
+ * out:    n x 64 floats:
+ *   [0] 0 miss / 1 surface hit / 2 environment   [1] t   [2..4] p   [5..7] shading normal   [8..10] shading tangent
+ *   [11] hasNonDelta   [12..27] sampled fs   [28..30] sampled dir_sn   [31] dirPDF   [32] dirType
+ *   [33..48] evaluated fs   [49] evaluated pdf   [50] isEmitting   [51..63] first 13 emittance values
+ * ------------------------------------------------------------------------------------------- */
+#define SLRGPU_PROBE_IN_FLOATS 14
+#define SLRGPU_PROBE_OUT_FLOATS 64
+SLRGPU_API int slrgpu_probe_shading(SlrGpuScene* scene, const float* probes, uint64_t num_probes, float* out);
+
 /* Render calls keep their wavefront queues (about 440 bytes per path in flight) in a per-device pool
  * for reuse by later calls; this frees the pool. */
 SLRGPU_API void slrgpu_release_workspaces(void);

@@ -173,6 +173,10 @@ gpu.slrgpu_intersect_launch_config.argtypes = [C.c_void_p, c_u64, PU32, PU32]
 gpu.slrgpu_occluded_batch.restype = C.c_int
 gpu.slrgpu_occluded_batch.argtypes = [C.c_void_p, C.POINTER(RayBatch), c_u64, PU8, PF]
 
+gpu.slrgpu_probe_shading.restype = C.c_int
+gpu.slrgpu_probe_shading.argtypes = [C.c_void_p, PF, c_u64, PF]
+gpu.slrgpu_release_workspaces.restype = None
+
 # ---- slrhost.h prototypes
 host.slrhost_last_error.restype = C.c_char_p
 host.slrhost_builder_create.restype = C.c_void_p
@@ -450,6 +454,14 @@ def gpu_render(gpu_scene, width, height, spp_begin, spp_end, seed=1509761209, ti
     st = RenderStats()
     _gpu_check(gpu.slrgpu_render(gpu_scene.handle, C.byref(p), _pf(accum), C.byref(st)), "slrgpu_render")
     return accum, {k: getattr(st, k) for k, _ in RenderStats._fields_}
+
+
+def probe_shading(gpu_scene, probes):
+    """slrgpu_probe_shading: probes[n, 14] -> out[n, 64] (layout in include/slrgpu.h)."""
+    p = _f32(probes).reshape(-1, 14)
+    out = np.zeros((p.shape[0], 64), np.float32)
+    _gpu_check(gpu.slrgpu_probe_shading(gpu_scene.handle, _pf(p), p.shape[0], _pf(out)), "slrgpu_probe_shading")
+    return out
 
 
 def accum_to_rgb(accum, scale):

@@ -66,7 +66,9 @@ struct SlrGpuScene {
 
 namespace slrgpu {
 void setError(const char* fmt, ...);
-void releaseSceneArenas();        // scene.cu: drops the per-device arena cache
+void releaseSceneArenas();
+// intersect.cu: closest hits of a device-resident SoA ray batch; dStatus = two zeroed ints (overflow flag, chunk cursor)
+int launchIntersect(SlrGpuScene* sc, const SlrGpuRayBatch& rays, uint64_t n, const SlrGpuHitBatch& hits, int* dStatus, cudaStream_t stream);        // scene.cu: drops the per-device arena cache
 int cudaFail(cudaError_t e, const char* what);
 #define SLRGPU_CUDA_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return slrgpu::cudaFail(_e, #expr); } while (0)
 }

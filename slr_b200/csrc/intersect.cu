@@ -63,7 +63,7 @@ static uint32_t batchGrid(const SlrGpuScene* sc, uint64_t n) {
     return (uint32_t)(need < full ? need : full);
 }
 
-static int launchIntersect(SlrGpuScene* sc, const SlrGpuRayBatch& rays, uint64_t n, const SlrGpuHitBatch& hits,
+int launchIntersect(SlrGpuScene* sc, const SlrGpuRayBatch& rays, uint64_t n, const SlrGpuHitBatch& hits,
                            int* dStatus, cudaStream_t stream) {
     if (n == 0) return SLRGPU_OK;
     if (n >= 0xFFFF0000ull) { setError("ray batch too large (at most 2^32 - 65536 rays per call)"); return SLRGPU_ERR_INVALID_ARGUMENT; }

@@ -693,6 +693,80 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
     return SLRGPU_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// shading probe (slrgpu_probe_shading): the material kernels' device functions on caller-given inputs
+// ---------------------------------------------------------------------------------------------
+__global__ void probeRaysKernel(const float* __restrict__ probes, uint32_t n, SlrGpuRayBatch rays) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = probes + (size_t)i * SLRGPU_PROBE_IN_FLOATS;
+    const_cast<float*>(rays.org_x)[i] = p[0]; const_cast<float*>(rays.org_y)[i] = p[1]; const_cast<float*>(rays.org_z)[i] = p[2];
+    const_cast<float*>(rays.dir_x)[i] = p[3]; const_cast<float*>(rays.dir_y)[i] = p[4]; const_cast<float*>(rays.dir_z)[i] = p[5];
+    const_cast<float*>(rays.tmin)[i] = 0.0f; const_cast<float*>(rays.tmax)[i] = INFINITY;
+}
+
+template <int CLASS>
+__device__ __noinline__ void probeBsdf(const DeviceScene& s, uint32_t leaf, const SurfPt& sp, const V3& dirOut, const V3& gNorm, float wlOffset,
+                                       uint32_t hero, float uComp, float u0, float u1, const V3& evalDir, float* o) {
+    HitBsdf<16, CLASS> bsdf;
+    bsdf.build(s, leaf, sp, wlOffset, false);
+    BsdfQuery q;
+    q.dir = dirOut; q.gn = gNorm; q.hero = hero; q.flags = DT_All;
+    o[11] = bsdf.hasNonDelta() ? 1.0f : 0.0f;
+    BsdfSampleResult res;
+    const Spec<16> fs = bsdf.sample(q, uComp, u0, u1, &res);
+    for (int k = 0; k < 16; ++k) o[12 + k] = fs.v[k];
+    o[28] = res.dir.x; o[29] = res.dir.y; o[30] = res.dir.z;
+    o[31] = res.pdf;
+    o[32] = (float)res.type;
+    const Spec<16> fe = bsdf.evaluate(q, evalDir);
+    for (int k = 0; k < 16; ++k) o[33 + k] = fe.v[k];
+    o[49] = bsdf.pdf(q, evalDir);
+}
+
+__global__ void __launch_bounds__(64)
+probeShadeKernel(const DeviceScene s, const float* __restrict__ probes, uint32_t n, SlrGpuHitBatch hits, float* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = probes + (size_t)i * SLRGPU_PROBE_IN_FLOATS;
+    float* o = out + (size_t)i * SLRGPU_PROBE_OUT_FLOATS;
+    for (int k = 0; k < SLRGPU_PROBE_OUT_FLOATS; ++k) o[k] = 0.0f;
+    const uint32_t prim = hits.prim[i];
+    if (prim == SLRGPU_INVALID_ID) { o[0] = s.envPresent ? 2.0f : 0.0f; return; }
+    const V3 org(p[0], p[1], p[2]), dir(p[3], p[4], p[5]);
+    const float wlOffset = p[6];
+    const uint32_t hero = min((uint32_t)(16 * p[7]), 15u);
+    SurfPt sp;
+    float localArea;
+    const SlrGpuTriangle tri = hitSurfacePoint(s, prim, hits.inst[i], hits.t[i], hits.u[i], hits.v[i], org, dir, &sp, &localArea);
+    o[0] = 1.0f; o[1] = hits.t[i];
+    o[2] = sp.p.x; o[3] = sp.p.y; o[4] = sp.p.z;
+    o[5] = sp.sf.z.x; o[6] = sp.sf.z.y; o[7] = sp.sf.z.z;
+    o[8] = sp.sf.x.x; o[9] = sp.sf.x.y; o[10] = sp.sf.x.z;
+    const V3 dirOut = sp.sf.toLocal(-dir);
+    const V3 gNorm = sp.sf.toLocal(sp.gn);
+    const V3 evalDir = sp.sf.toLocal(V3(p[11], p[12], p[13]));
+    uint32_t leaf = SLRGPU_INVALID_ID;
+    const uint32_t cls = classifyMaterial(s, tri.material, &leaf);
+    switch (cls) {
+    case SC_LAMBERT: probeBsdf<SC_LAMBERT>(s, leaf, sp, dirOut, gNorm, wlOffset, hero, p[8], p[9], p[10], evalDir, o); break;
+    case SC_OREN_NAYAR: probeBsdf<SC_OREN_NAYAR>(s, leaf, sp, dirOut, gNorm, wlOffset, hero, p[8], p[9], p[10], evalDir, o); break;
+    case SC_SPECULAR_BRDF: probeBsdf<SC_SPECULAR_BRDF>(s, leaf, sp, dirOut, gNorm, wlOffset, hero, p[8], p[9], p[10], evalDir, o); break;
+    case SC_SPECULAR_BSDF: probeBsdf<SC_SPECULAR_BSDF>(s, leaf, sp, dirOut, gNorm, wlOffset, hero, p[8], p[9], p[10], evalDir, o); break;
+    case SC_WARD: probeBsdf<SC_WARD>(s, leaf, sp, dirOut, gNorm, wlOffset, hero, p[8], p[9], p[10], evalDir, o); break;
+    case SC_ASHIKHMIN: probeBsdf<SC_ASHIKHMIN>(s, leaf, sp, dirOut, gNorm, wlOffset, hero, p[8], p[9], p[10], evalDir, o); break;
+    case SC_MF_BRDF: probeBsdf<SC_MF_BRDF>(s, leaf, sp, dirOut, gNorm, wlOffset, hero, p[8], p[9], p[10], evalDir, o); break;
+    case SC_MF_BSDF: probeBsdf<SC_MF_BSDF>(s, leaf, sp, dirOut, gNorm, wlOffset, hero, p[8], p[9], p[10], evalDir, o); break;
+    case SC_GENERIC: probeBsdf<SC_GENERIC>(s, leaf, sp, dirOut, gNorm, wlOffset, hero, p[8], p[9], p[10], evalDir, o); break;
+    default: break;
+    }
+    if (materialIsEmitting(s, tri.material)) {
+        o[50] = 1.0f;
+        const Spec<16> Le = materialEmittance<16>(s, tri.material, sp, wlOffset);
+        for (int k = 0; k < 13; ++k) o[51 + k] = Le.v[k];
+    }
+}
+
 static int checkRenderArgs(SlrGpuScene* sc, const SlrGpuRenderParams* p) {
     if (!sc || !p) { setError("slrgpu_render: null argument"); return SLRGPU_ERR_INVALID_ARGUMENT; }
     if (p->struct_size != sizeof(SlrGpuRenderParams)) { setError("slrgpu_render: params struct_size mismatch"); return SLRGPU_ERR_INVALID_ARGUMENT; }
@@ -707,6 +781,37 @@ static int checkRenderArgs(SlrGpuScene* sc, const SlrGpuRenderParams* p) {
 using namespace slrgpu;
 
 extern "C" {
+
+SLRGPU_API int slrgpu_probe_shading(SlrGpuScene* sc, const float* probes, uint64_t n, float* out) {
+    if (!sc || !probes || !out) { setError("slrgpu_probe_shading: null argument"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    if (!sc->hasShading || sc->channels != 16) { setError("slrgpu_probe_shading: needs a spectral scene with materials"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    if (n == 0) return SLRGPU_OK;
+    if (n > (1u << 26)) { setError("slrgpu_probe_shading: too many probes"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    SLRGPU_CUDA_TRY(cudaSetDevice(sc->device));
+    struct Buffers { void* p[16] = {}; int k = 0; ~Buffers() { for (int i = 0; i < k; ++i) cudaFree(p[i]); } } bufs;
+    auto alloc = [&bufs](size_t bytes) -> void* { void* q = nullptr; if (cudaMalloc(&q, bytes) != cudaSuccess) return nullptr; bufs.p[bufs.k++] = q; return q; };
+    float* dProbes = (float*)alloc(n * SLRGPU_PROBE_IN_FLOATS * sizeof(float));
+    float* dOut = (float*)alloc(n * SLRGPU_PROBE_OUT_FLOATS * sizeof(float));
+    float* comp[8];
+    for (int k = 0; k < 8; ++k) comp[k] = (float*)alloc(n * sizeof(float));
+    SlrGpuHitBatch hits = {};
+    hits.prim = (uint32_t*)alloc(n * 4); hits.inst = (uint32_t*)alloc(n * 4);
+    hits.t = (float*)alloc(n * 4); hits.u = (float*)alloc(n * 4); hits.v = (float*)alloc(n * 4);
+    int* dStatus = (int*)alloc(2 * sizeof(int));
+    if (!dProbes || !dOut || !comp[7] || !hits.v || !dStatus) { setError("slrgpu_probe_shading: out of device memory"); return SLRGPU_ERR_OUT_OF_MEMORY; }
+    SLRGPU_CUDA_TRY(cudaMemcpy(dProbes, probes, n * SLRGPU_PROBE_IN_FLOATS * sizeof(float), cudaMemcpyHostToDevice));
+    SLRGPU_CUDA_TRY(cudaMemset(dStatus, 0, 2 * sizeof(int)));
+    SlrGpuRayBatch rays = {comp[0], comp[1], comp[2], comp[3], comp[4], comp[5], comp[6], comp[7]};
+    const uint32_t n32 = (uint32_t)n;
+    probeRaysKernel<<<(n32 + 127) / 128, 128>>>(dProbes, n32, rays);
+    int rc = launchIntersect(sc, rays, n, hits, dStatus, 0);
+    if (rc) return rc;
+    probeShadeKernel<<<(n32 + 63) / 64, 64>>>(sc->dev, dProbes, n32, hits, dOut);
+    SLRGPU_CUDA_TRY(cudaGetLastError());
+    SLRGPU_CUDA_TRY(cudaDeviceSynchronize());
+    SLRGPU_CUDA_TRY(cudaMemcpy(out, dOut, n * SLRGPU_PROBE_OUT_FLOATS * sizeof(float), cudaMemcpyDeviceToHost));
+    return SLRGPU_OK;
+}
 
 SLRGPU_API void slrgpu_release_workspaces(void) {
     std::lock_guard<std::mutex> lock(g_poolMutex);

@@ -82,3 +82,78 @@ def block_rel_rmse(img, ref, block, trim=0.0):
     """rel_rmse of block x block averages: Monte-Carlo noise shrinks by `block`, systematic
     differences (a wrong BSDF, a missing light path) do not."""
     return rel_rmse(block_means(img, block), block_means(ref, block), trim)
+
+
+# --------------------------------------------------------------------------------------------------
+# shading probes (function-level parity of surface points, materials, textures, spectra and BSDFs)
+# --------------------------------------------------------------------------------------------------
+REF_PROBE = os.path.join(ROOT, "oracle", "_ref", "ref_probe")
+
+
+def have_ref_probe():
+    return os.access(REF_PROBE, os.X_OK)
+
+
+def make_probes(center, radius, n, seed):
+    """n probe rays from inside the scene's bounding sphere in random directions, with the random numbers a
+    path would draw (wavelength offset, wavelength selection, BSDF component, BSDF direction) and a random
+    world direction to evaluate the BSDF for. Deterministic in (center, radius, n, seed)."""
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o = rng.normal(size=(n, 3))
+    o *= (0.55 * radius * rng.random((n, 1)) ** (1 / 3)) / np.linalg.norm(o, axis=1, keepdims=True)
+    o += np.asarray(center, np.float64)
+    e = rng.normal(size=(n, 3))
+    e /= np.linalg.norm(e, axis=1, keepdims=True)
+    u = rng.random((n, 5)) * (1.0 - 1e-6)
+    return np.concatenate([o, d, u, e], 1).astype(np.float32)
+
+
+def run_ref_probe(scene_path, probes, timeout=600):
+    scene_path = os.path.abspath(scene_path)
+    pin, pout = scene_path + ".probes.bin", scene_path + ".probes.out"
+    with open(pin, "wb") as f:
+        f.write(np.uint32(probes.shape[0]).tobytes())
+        f.write(np.ascontiguousarray(probes, np.float32).tobytes())
+    p = subprocess.run([REF_PROBE, os.path.basename(scene_path), pin, pout], capture_output=True, text=True, timeout=timeout,
+                       cwd=os.path.dirname(scene_path))
+    if p.returncode != 0:
+        raise RuntimeError(f"ref_probe failed: {p.stderr[-2000:]}")
+    with open(pout, "rb") as f:
+        n, stride = np.frombuffer(f.read(8), np.uint32)
+        out = np.frombuffer(f.read(), np.float32).reshape(n, stride).copy()
+    os.remove(pin)
+    os.remove(pout)
+    return out
+
+
+def compare_probes(got, want, rel=2e-3):
+    """Returns a dict of mismatch fractions / worst errors between two probe result arrays [n, 64]."""
+    res = {}
+    res["status_mismatch"] = float(np.mean(got[:, 0] != want[:, 0]))
+    hit = (got[:, 0] == 1) & (want[:, 0] == 1)
+    g, w = got[hit].astype(np.float64), want[hit].astype(np.float64)
+    res["hits"] = int(hit.sum())
+
+    def relerr(a, b, floor):
+        return np.abs(a - b) / (np.abs(b) + floor)
+    res["t_worst_rel"] = float(relerr(g[:, 1], w[:, 1], 1e-6).max())
+    res["frame_worst_abs"] = float(np.abs(g[:, 2:11] - w[:, 2:11]).max())
+    res["nondelta_mismatch"] = float(np.mean(g[:, 11] != w[:, 11]))
+    same_type = g[:, 32] == w[:, 32]
+    res["sample_type_mismatch"] = float(np.mean(~same_type))
+    gs, ws = g[same_type], w[same_type]
+    scale = np.abs(ws[:, 12:28]).max(1, keepdims=True) + 1e-6
+    bad_fs = (np.abs(gs[:, 12:28] - ws[:, 12:28]) / scale).max(1) > rel
+    bad_dir = np.abs(gs[:, 28:31] - ws[:, 28:31]).max(1) > 2e-3
+    bad_pdf = relerr(gs[:, 31], ws[:, 31], 1e-6) > rel
+    res["sample_value_mismatch"] = float(np.mean(bad_fs | bad_dir | bad_pdf))
+    scale = np.abs(w[:, 33:49]).max(1, keepdims=True) + 1e-6
+    bad_ev = (np.abs(g[:, 33:49] - w[:, 33:49]) / scale).max(1) > rel
+    bad_evpdf = relerr(g[:, 49], w[:, 49], 1e-6) > rel
+    res["eval_mismatch"] = float(np.mean(bad_ev | bad_evpdf))
+    res["emitting_mismatch"] = float(np.mean(g[:, 50] != w[:, 50]))
+    em = w[:, 50] == 1
+    res["emittance_worst_rel"] = float(relerr(g[em, 51:64], w[em, 51:64], 1e-6).max()) if em.any() else 0.0
+    return res
