@@ -369,7 +369,7 @@ typedef struct SlrGpuRenderStats {
     uint64_t kernel_launches;
     float device_ms;                 /* first launch -> accumulators final, CUDA events */
     /* the rest only with SLRGPU_RENDER_PROFILE_STAGES (per-launch CUDA events; slows the run a little) */
-    float raygen_ms, extend_ms, shade_ms, shadow_ms, other_ms;
+    float raygen_ms, extend_ms, surface_ms, material_ms, shadow_ms, other_ms;   /* summed device time per kernel family */
     uint64_t waves;                  /* extend/shade iterations of the wavefront loop (always filled) */
     uint64_t extend_nodes, extend_leaf_records;   /* QBVH nodes popped / leaf records tested by extend rays */
     uint64_t shadow_nodes, shadow_leaf_records;   /* ... and by shadow rays (any-hit: stops at the first hit) */

@@ -126,7 +126,7 @@ class RenderParams(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("paths", c_u64), ("rays", c_u64), ("extend_rays", c_u64), ("shadow_rays", c_u64),
-                ("kernel_launches", c_u64), ("device_ms", c_f), ("raygen_ms", c_f), ("extend_ms", c_f), ("shade_ms", c_f),
+                ("kernel_launches", c_u64), ("device_ms", c_f), ("raygen_ms", c_f), ("extend_ms", c_f), ("surface_ms", c_f), ("material_ms", c_f),
                 ("shadow_ms", c_f), ("other_ms", c_f), ("waves", c_u64), ("extend_nodes", c_u64),
                 ("extend_leaf_records", c_u64), ("shadow_nodes", c_u64), ("shadow_leaf_records", c_u64)]
 

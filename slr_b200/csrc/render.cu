@@ -524,10 +524,13 @@ static void launchMaterial(const SlrGpuScene* sc, const RenderConstants& rc, con
 }
 
 // the shade stage of one wave: surface + one material launch per class the scene contains
-template <int NC>
+template <int NC, typename Mark>
 static void launchShadeStage(const SlrGpuScene* sc, const RenderConstants& rc, const RenderWorkspace& w, int cur, float* accum, uint32_t grid,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, const Mark& mark) {
+    mark(2);
     surfaceKernel<NC><<<grid, kSurfaceBlock, 0, stream>>>(sc->dev, rc, w.q[cur], w.hits, w.cq, accum, w.dCounters);
+    mark(2);
+    mark(3);
     const uint32_t m = sc->classMask;
     if (m & (1u << SC_LAMBERT)) launchMaterial<NC, SC_LAMBERT>(sc, rc, w, cur, grid, stream);
     if (m & (1u << SC_OREN_NAYAR)) launchMaterial<NC, SC_OREN_NAYAR>(sc, rc, w, cur, grid, stream);
@@ -538,6 +541,7 @@ static void launchShadeStage(const SlrGpuScene* sc, const RenderConstants& rc, c
     if (m & (1u << SC_MF_BRDF)) launchMaterial<NC, SC_MF_BRDF>(sc, rc, w, cur, grid, stream);
     if (m & (1u << SC_MF_BSDF)) launchMaterial<NC, SC_MF_BSDF>(sc, rc, w, cur, grid, stream);
     if (m & (1u << SC_GENERIC)) launchMaterial<NC, SC_GENERIC>(sc, rc, w, cur, grid, stream);
+    mark(3);
 }
 
 static uint32_t poolCapacity(const SlrGpuRenderParams* p) {
@@ -588,7 +592,7 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
     // per-stage device time (SLRGPU_RENDER_PROFILE_STAGES): one event pair per launch group, summed at the end
     const bool profile = (p->flags & SLRGPU_RENDER_PROFILE_STAGES) != 0;
     struct StageTimer {
-        std::vector<cudaEvent_t> ev[4];      // 0 raygen, 1 extend, 2 shade (surface + material), 3 shadow: begin/end pairs
+        std::vector<cudaEvent_t> ev[5];      // 0 raygen, 1 extend, 2 surface, 3 material kernels, 4 shadow: begin/end pairs
         bool on;
         cudaStream_t st;
         void mark(int stage) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev[stage].push_back(e); }
@@ -627,14 +631,13 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
         int r = launchExtend(sc, w.q[cur], w.hits, w.dCounters, profile, grid, stream);
         if (r) return r;
         timer.mark(1);
-        timer.mark(2);
-        if (rgb) launchShadeStage<3>(sc, rc, w, cur, accumDev, grid, stream);
-        else launchShadeStage<16>(sc, rc, w, cur, accumDev, grid, stream);
-        timer.mark(2);
-        timer.mark(3);
+        auto mark = [&timer](int stage) { timer.mark(stage); };
+        if (rgb) launchShadeStage<3>(sc, rc, w, cur, accumDev, grid, stream, mark);
+        else launchShadeStage<16>(sc, rc, w, cur, accumDev, grid, stream, mark);
+        timer.mark(4);
         if ((r = launchShadow(sc, w.sq, accumDev, w.dCounters, profile, grid, stream))) return r;
         endWaveKernel<<<1, 1, 0, stream>>>(w.dCounters, w.hCounters, (uint32_t)kRing);
-        timer.mark(3);
+        timer.mark(4);
         return SLRGPU_OK;
     };
     cudaGraph_t graph = nullptr;
@@ -683,8 +686,8 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
         cudaEventElapsedTime(&stats->device_ms, ev0, ev1);
         if (profile) {
             stats->raygen_ms = timer.total(0); stats->extend_ms = timer.total(1);
-            stats->shade_ms = timer.total(2); stats->shadow_ms = timer.total(3);
-            stats->other_ms = stats->device_ms - stats->raygen_ms - stats->extend_ms - stats->shade_ms - stats->shadow_ms;
+            stats->surface_ms = timer.total(2); stats->material_ms = timer.total(3); stats->shadow_ms = timer.total(4);
+            stats->other_ms = stats->device_ms - stats->raygen_ms - stats->extend_ms - stats->surface_ms - stats->material_ms - stats->shadow_ms;
             stats->extend_nodes = last.extendNodes; stats->extend_leaf_records = last.extendLeafRecords;
             stats->shadow_nodes = last.shadowNodes; stats->shadow_leaf_records = last.shadowLeafRecords;
         }

@@ -224,23 +224,36 @@ def main(args, rank, world):
     peak, peak_src = bench.measured_peaks()
     value = paths_per_step * world * args.steps / (ms * 1e-3) / 1e6
     # dominant kernel by the profiled frame's stage times
-    stages = {"extendKernel": prof.extend_ms, "shadeKernel": prof.shade_ms, "shadowKernel": prof.shadow_ms, "raygenKernel": prof.raygen_ms}
+    stages = {"extendKernel": prof.extend_ms, "surfaceKernel": prof.surface_ms, "materialKernel": prof.material_ms,
+              "shadowKernel": prof.shadow_ms, "raygenKernel": prof.raygen_ms}
     dom = max(stages, key=stages.get)
-    S_PATH, S_HIT, S_SHADOW = (116, 24, 108) if chan == 16 else (68, 24, 60)
+    S_PATH, S_HIT, S_SHADOW = (120, 24, 108) if chan == 16 else (72, 24, 60)
     n_ext, n_sh = prof.extend_rays, prof.shadow_rays
     algo = {
         # 32 B ray in + 128 B per node popped + 48 B per leaf record tested + 24 B hit record out
         "extendKernel": 32 * n_ext + 128 * prof.extend_nodes + 48 * prof.extend_leaf_records + S_HIT * n_ext,
         # shadow entry in + nodes + leaf records (+ the splat, counted as 64 B read-modify-write of unoccluded entries; upper bound: all)
         "shadowKernel": S_SHADOW * n_sh + 128 * prof.shadow_nodes + 48 * prof.shadow_leaf_records,
-        # path state + hit in, surviving path state + shadow entry out, 3 vertices (144 B) + triangle record (32 B) per hit
-        "shadeKernel": (S_PATH + S_HIT + 176) * n_ext + S_PATH * (n_ext - paths_per_step) + S_SHADOW * n_sh,
+        # hit id + meta + triangle record + roulette slot in; roulette slot + class-queue entry out (upper bound: every ray survives)
+        "surfaceKernel": (8 + 16 + 32 + 4) * n_ext + (4 + 8) * n_ext,
+        # (all class kernels of a frame) path state + hit + class entry + triangle + 3 vertices in per surviving hit (bounded by
+        # the extend rays), surviving path state out (= the non-camera extend rays), shadow entry out
+        "materialKernel": (S_PATH + S_HIT + 8 + 176) * n_ext + S_PATH * (n_ext - paths_per_step) + S_SHADOW * n_sh,
         "raygenKernel": S_PATH * paths_per_step,
     }
     # share of the step the dominant kernel takes in the profiled frame, applied to the timed steps
     share = stages[dom] / max(prof.device_ms, 1e-9)
     dom_ms_per_step = share * ms / args.steps
     ach = algo[dom] / (dom_ms_per_step * 1e-3) / 1e9
+    # measured DRAM traffic of that kernel family over one frame, from the committed ncu capture of this workload
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(args.workload, {}).get(dom)
+        if t is not None:
+            traffic = t["dram_bytes_per_frame"]
+    except (OSError, ValueError, KeyError):
+        traffic = None
     cpu = cpu_baseline(path, w, h, spp)
     line = {"metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -256,10 +269,11 @@ def main(args, rank, world):
                        "l2_policy": "per-step working set (wavefront queues + accumulation buffer, > 500 MB) is larger than L2; "
                                     "the scene itself (QBVH + leaf records) is L2-resident by design",
                        "stage_ms_profiled_frame": {k: round(v, 3) for k, v in stages.items()} | {"other": round(prof.other_ms, 3), "frame": round(prof.device_ms, 3)}},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                          "kernel": dom, "peak_source": peak_src, "kernel_share_of_step": share,
                          "algorithmic_bytes_per_launch_set": algo[dom],
-                         "note": "algorithmic bytes of all launches of the kernel in one frame / its summed device time"},
+                         "note": "achieved = algorithmic bytes of all launches of the kernel family in one frame / their summed device time; "
+                                 "traffic = ncu dram__bytes_read+write summed over the same launches (profiles/traffic.json), bytes per frame"},
             "cpu_baseline": cpu,
             "e2e": {"value": paths_per_step * world / e2e_s / 1e6, "unit": "Mpaths/s",
                     "h2d_bytes_per_step": scene_bytes + (accum_bytes if world > 1 else 0),

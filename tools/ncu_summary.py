@@ -2,6 +2,7 @@
 
   python tools/ncu_summary.py launches <launches.csv> [title]      per-kernel totals / shares of a launch list
   python tools/ncu_summary.py report <file.ncu-rep> [title]        key metrics of every captured launch
+  python tools/ncu_summary.py traffic <launches.csv> <workload>    DRAM bytes per kernel family (-> profiles/traffic.json)
 """
 import csv
 import io
@@ -45,28 +46,52 @@ def short(name):
     return re.sub(r"\(.*$", "", name)
 
 
-def launches(path, title):
+BYTE_UNITS = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def read_launches(path):
+    """{kernel: [launches, total us, dram bytes]} from an `ncu --csv` launch list (one row per launch and metric)."""
     rows = [r for r in csv.reader(open(path)) if r]
     hdr_i = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     hdr = rows[hdr_i]
-    kn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    kn, mn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     tot = OrderedDict()
     for r in rows[hdr_i + 1:]:
         if len(r) <= mv:
             continue
         v = float(r[mv].replace(",", ""))
         unit = r[mu]
-        us = v / 1e3 if unit in ("ns", "nsecond") else v if unit in ("us", "usecond") else v * 1e3 if unit in ("ms", "msecond") else v
-        k = short(r[kn])
-        t = tot.setdefault(k, [0, 0.0])
-        t[0] += 1
-        t[1] += us
+        t = tot.setdefault(short(r[kn]), [0, 0.0, 0.0])
+        if r[mn] == "gpu__time_duration.sum":
+            t[0] += 1
+            t[1] += v / 1e3 if unit in ("ns", "nsecond") else v if unit in ("us", "usecond") else v * 1e3 if unit in ("ms", "msecond") else v
+        elif r[mn].startswith("dram__bytes"):
+            t[2] += v * BYTE_UNITS.get(unit, 1.0)
+    return tot
+
+
+def launches(path, title):
+    tot = read_launches(path)
     total = sum(t[1] for t in tot.values())
     print(f"## {title}\n\n`{path}`: {sum(t[0] for t in tot.values())} launches, {total / 1e3:.2f} ms of kernel time "
           f"(serialised, cold-cache: compare shares)\n")
-    print("| kernel | launches | total ms | share | mean us |\n|---|---|---|---|---|")
+    print("| kernel | launches | total ms | share | mean us | DRAM read+write MB (all launches) |\n|---|---|---|---|---|---|")
     for k, t in sorted(tot.items(), key=lambda kv: -kv[1][1]):
-        print(f"| `{k}` | {t[0]} | {t[1] / 1e3:.3f} | {100 * t[1] / total:.1f} % | {t[1] / t[0]:.1f} |")
+        print(f"| `{k}` | {t[0]} | {t[1] / 1e3:.3f} | {100 * t[1] / total:.1f} % | {t[1] / max(t[0], 1):.1f} | {t[2] / 1e6:.1f} |")
+
+
+def traffic(path, workload):
+    """Per kernel family DRAM bytes of the listed launches (one frame): the `traffic` of bench.py's roofline object."""
+    fam = {}
+    for k, t in read_launches(path).items():
+        name = re.sub(r"<.*$", "", k)
+        if name.endswith("Kernel") and name[:-6] in ("extend", "shadow", "surface", "material", "raygen"):
+            f = fam.setdefault(name, {"dram_bytes_per_frame": 0.0, "launches": 0, "kernel_ms_per_frame_under_ncu": 0.0})
+            f["dram_bytes_per_frame"] += t[2]
+            f["launches"] += t[0]
+            f["kernel_ms_per_frame_under_ncu"] += t[1] / 1e3
+    import json
+    print(json.dumps({workload: fam}, indent=1))
 
 
 def report(path, title):
@@ -93,4 +118,4 @@ def report(path, title):
 if __name__ == "__main__":
     mode, path = sys.argv[1], sys.argv[2]
     title = sys.argv[3] if len(sys.argv) > 3 else path
-    (launches if mode == "launches" else report)(path, title)
+    {"launches": launches, "report": report, "traffic": traffic}[mode](path, title)
