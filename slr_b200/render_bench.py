@@ -147,7 +147,10 @@ def main(args, rank, world):
         reduce_frame(accum, dist)
         return st
 
-    # one profiled, untimed frame: stage times and the traversal counts of the algorithmic-bytes model
+    # one plain frame (allocates the pooled queues), then one profiled, untimed frame: per-kernel-family device
+    # times and the traversal counts of the algorithmic-bytes model
+    frame()
+    torch.cuda.synchronize()
     prof = frame(capi.RENDER_PROFILE_STAGES)
     torch.cuda.synchronize()
     for _ in range(args.warmup):
