@@ -373,6 +373,9 @@ typedef struct SlrGpuRenderStats {
     uint64_t waves;                  /* extend/shade iterations of the wavefront loop (always filled) */
     uint64_t extend_nodes, extend_leaf_records;   /* QBVH nodes popped / leaf records tested by extend rays */
     uint64_t shadow_nodes, shadow_leaf_records;   /* ... and by shadow rays (any-hit: stops at the first hit) */
+    /* hits shaded per material class (always filled): 0 Lambert, 1 Oren-Nayar, 2 specular reflection, 3 specular
+     * scattering, 4 Ward-Duer, 5 Ashikhmin-Shirley, 6 microfacet reflection, 7 microfacet scattering, 8 sum / mix / inverse */
+    uint64_t class_hits[9];
 } SlrGpuRenderStats;
 
 #define SLRGPU_RENDER_PROFILE_STAGES 0x1u

@@ -128,7 +128,8 @@ class RenderStats(C.Structure):
     _fields_ = [("paths", c_u64), ("rays", c_u64), ("extend_rays", c_u64), ("shadow_rays", c_u64),
                 ("kernel_launches", c_u64), ("device_ms", c_f), ("raygen_ms", c_f), ("extend_ms", c_f), ("surface_ms", c_f), ("material_ms", c_f),
                 ("shadow_ms", c_f), ("other_ms", c_f), ("waves", c_u64), ("extend_nodes", c_u64),
-                ("extend_leaf_records", c_u64), ("shadow_nodes", c_u64), ("shadow_leaf_records", c_u64)]
+                ("extend_leaf_records", c_u64), ("shadow_nodes", c_u64), ("shadow_leaf_records", c_u64),
+                ("class_hits", c_u64 * 9)]
 
 
 _ABI_STRUCTS = [SceneDesc, BvhNode, LeafRecord, Instance, Triangle, Vertex, Spectrum, Texture, Image,
@@ -453,7 +454,7 @@ def gpu_render(gpu_scene, width, height, spp_begin, spp_end, seed=1509761209, ti
                      pool_size, flags)
     st = RenderStats()
     _gpu_check(gpu.slrgpu_render(gpu_scene.handle, C.byref(p), _pf(accum), C.byref(st)), "slrgpu_render")
-    return accum, {k: getattr(st, k) for k, _ in RenderStats._fields_}
+    return accum, {k: (list(getattr(st, k)) if k == "class_hits" else getattr(st, k)) for k, _ in RenderStats._fields_}
 
 
 def probe_shading(gpu_scene, probes):

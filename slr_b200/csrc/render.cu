@@ -147,7 +147,7 @@ __global__ void endWaveKernel(WavefrontCounters* counters, WavefrontCounters* ri
     counters->numPaths = counters->numNext;
     counters->numNext = 0;
     counters->numShadow = 0;
-    for (int c = 0; c < 16; ++c) counters->classCount[c] = 0;
+    for (int c = 0; c < 16; ++c) { counters->classTotal[c] += counters->classCount[c]; counters->classCount[c] = 0; }
     counters->extendCursor = 0;
     counters->shadowCursor = 0;
     counters->done = (counters->numPaths == 0 && counters->generated == counters->total) ? 1u : 0u;
@@ -431,6 +431,10 @@ struct RenderWorkspace {
     float* frameHost = nullptr;
     size_t frameBytes = 0;
     cudaStream_t stream = nullptr;               // non-blocking stream of the host-buffer entry point (graph capture needs one)
+    // the material kernels of a wave are independent of each other: they run on side streams, forked from and
+    // joined to the render stream with events (parallel branches of the captured graph)
+    cudaStream_t side[SC_COUNT] = {};
+    cudaEvent_t forkEvent = nullptr, joinEvent[SC_COUNT] = {};
     int ensureFrame(size_t bytes) {
         if (frame && frameBytes >= bytes) return SLRGPU_OK;
         if (frame) cudaFree(frame);
@@ -448,6 +452,9 @@ struct RenderWorkspace {
         if (frame) cudaFree(frame);
         if (frameHost) cudaFreeHost(frameHost);
         if (stream) cudaStreamDestroy(stream);
+        for (cudaStream_t st : side) if (st) cudaStreamDestroy(st);
+        if (forkEvent) cudaEventDestroy(forkEvent);
+        for (cudaEvent_t e : joinEvent) if (e) cudaEventDestroy(e);
         if (hCounters) cudaFreeHost(hCounters);
         for (cudaEvent_t e : ringEvents) if (e) cudaEventDestroy(e);
     }
@@ -511,6 +518,12 @@ static int acquireWorkspace(SlrGpuScene* sc, uint32_t P, RenderWorkspace** out) 
     if (!rc) { cudaError_t e = cudaMallocHost(&w->hCounters, sizeof(WavefrontCounters) * kRing); if (e != cudaSuccess) rc = cudaFail(e, "cudaMallocHost"); }
     for (int k = 0; k < kRing && !rc; ++k) { cudaError_t e = cudaEventCreateWithFlags(&w->ringEvents[k], cudaEventDisableTiming); if (e != cudaSuccess) rc = cudaFail(e, "cudaEventCreate"); }
     if (!rc) { cudaError_t e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking); if (e != cudaSuccess) rc = cudaFail(e, "cudaStreamCreate"); }
+    for (int k = 0; k < (int)SC_COUNT && !rc; ++k) {
+        cudaError_t e = cudaStreamCreateWithFlags(&w->side[k], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->joinEvent[k], cudaEventDisableTiming);
+        if (e != cudaSuccess) rc = cudaFail(e, "cudaStreamCreate(side)");
+    }
+    if (!rc) { cudaError_t e = cudaEventCreateWithFlags(&w->forkEvent, cudaEventDisableTiming); if (e != cudaSuccess) rc = cudaFail(e, "cudaEventCreate"); }
     if (rc) { delete w; return rc; }
     w->sq.capacity = P; w->cq.capacity = P;
     w->capacity = P; w->channels = sc->channels;
@@ -518,9 +531,14 @@ static int acquireWorkspace(SlrGpuScene* sc, uint32_t P, RenderWorkspace** out) 
     return SLRGPU_OK;
 }
 
+// one class kernel on its side stream, between the fork event (surface done) and its join event
 template <int NC, int CLASS>
 static void launchMaterial(const SlrGpuScene* sc, const RenderConstants& rc, const RenderWorkspace& w, int cur, uint32_t grid, cudaStream_t stream) {
-    materialKernel<NC, CLASS><<<grid, kMaterialBlock, 0, stream>>>(sc->dev, rc, w.q[cur], w.hits, w.cq, w.q[cur ^ 1], w.sq, w.dCounters);
+    cudaStream_t st = w.side[CLASS];
+    cudaStreamWaitEvent(st, w.forkEvent, 0);
+    materialKernel<NC, CLASS><<<grid, kMaterialBlock, 0, st>>>(sc->dev, rc, w.q[cur], w.hits, w.cq, w.q[cur ^ 1], w.sq, w.dCounters);
+    cudaEventRecord(w.joinEvent[CLASS], st);
+    cudaStreamWaitEvent(stream, w.joinEvent[CLASS], 0);
 }
 
 // the shade stage of one wave: surface + one material launch per class the scene contains
@@ -531,6 +549,7 @@ static void launchShadeStage(const SlrGpuScene* sc, const RenderConstants& rc, c
     surfaceKernel<NC><<<grid, kSurfaceBlock, 0, stream>>>(sc->dev, rc, w.q[cur], w.hits, w.cq, accum, w.dCounters);
     mark(2);
     mark(3);
+    cudaEventRecord(w.forkEvent, stream);
     const uint32_t m = sc->classMask;
     if (m & (1u << SC_LAMBERT)) launchMaterial<NC, SC_LAMBERT>(sc, rc, w, cur, grid, stream);
     if (m & (1u << SC_OREN_NAYAR)) launchMaterial<NC, SC_OREN_NAYAR>(sc, rc, w, cur, grid, stream);
@@ -683,6 +702,7 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
         stats->rays = last.extendRays + last.shadowRays;
         stats->kernel_launches = launches;
         stats->waves = wave;
+        for (int c = 0; c < 9; ++c) stats->class_hits[c] = last.classTotal[c];
         cudaEventElapsedTime(&stats->device_ms, ev0, ev1);
         if (profile) {
             stats->raygen_ms = timer.total(0); stats->extend_ms = timer.total(1);

@@ -67,6 +67,7 @@ struct WavefrontCounters {
     uint32_t waves, done;
     uint32_t genPass, genOffset;                  // pass / pixel-order position of the next camera sample
     uint32_t extendCursor, shadowCursor;          // chunk cursors of the warp-cooperative ray kernels (zero at launch)
+    unsigned long long classTotal[16];            // hits shaded per material class over the whole call
 };
 
 // One entry of a material-class queue: position in the current path queue + the leaf material id.
