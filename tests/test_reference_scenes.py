@@ -1,0 +1,57 @@
+"""CPU: the reference's own TestScenes/*.txt are read UNCHANGED by the host scene language (north_star: "TestScenes/*.txt
+render unchanged"). Runs only where /root/reference is mounted (the files are copied to a temp directory at test time and
+never into this repository); the models / environment maps they load are replaced by synthetic assets because the
+reference does not ship them (README.md:69-72)."""
+import os
+import re
+import shutil
+
+import pytest
+
+from slr_b200 import capi, scenes, synth
+
+SRC = "/root/reference/TestScenes"
+# expected (width, height, samples, brightness) as written in the files
+EXPECT = {
+    "Cornell_Box_Spheres.txt": (1024, 768, 16384, 1.0),
+    "Cornell_Box_Boxes.txt": (1024, 1024, 16384, 1.0),
+    "Cornell_Box_ColorChecker.txt": (1024, 1024, 16384, 4.0),
+    "Cornell_Box_ColorChecker_OverrideMaterial.txt": (1024, 1024, 512, 4.0),
+    "IBL_Test.txt": (1024, 1024, 16384, 4.0),
+}
+
+
+@pytest.mark.skipif(not os.path.isdir(SRC), reason="the reference is not mounted on this machine")
+@pytest.mark.parametrize("name", sorted(EXPECT))
+def test_reference_scene_file_reads_unchanged(name, tmp_path):
+    d = str(tmp_path)
+    text = open(os.path.join(SRC, name)).read()
+    shutil.copy(os.path.join(SRC, name), os.path.join(d, name))
+    pos, idx, nrm, tng, uv = synth.uv_sphere(32, 16)
+    for asset in set(re.findall(r'"([^"]*\.(?:assbin|exr))"', text)):
+        p = os.path.join(d, asset)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        if asset.endswith(".exr"):
+            capi.write_exr(p, synth.sky_environment(256, 128))
+        elif "Cornell_box_RB" in asset:
+            scenes.write_cornell_box_rb_asset(d)
+        else:
+            capi.write_assbin(p, pos, idx, nrm, tng, uv, material_name="m", diffuse=(0.7, 0.6, 0.5))
+    with capi.stdout_to_stderr():
+        hs = capi.read_scene(os.path.join(d, name))
+    w, h, spp, brightness = EXPECT[name]
+    c = hs.context
+    assert (c["width"], c["height"], c["samples"]) == (w, h, spp) and c["brightness"] == brightness and c["hasRenderer"]
+    assert hs.desc.num_triangles >= 60 and hs.desc.num_materials >= 8 and hs.desc.num_lights >= (0 if "IBL" in name else 2)
+    assert bool(hs.desc.environment.present) == ("IBL" in name)
+    assert hs.desc.camera.obj_plane_dist > 0
+
+
+@pytest.mark.skipif(not os.path.isdir(SRC), reason="the reference is not mounted on this machine")
+def test_unsupported_builtin_fails_loudly(tmp_path):
+    """RTC3*.txt scatter instances with scanXZFromYPlus (a CPU ray cast during scene construction, API.cpp:926-983),
+    which this host library does not provide: reading them must fail with a message, not build a wrong scene."""
+    shutil.copy(os.path.join(SRC, "RTC3.txt"), str(tmp_path / "RTC3.txt"))
+    with pytest.raises(capi.SlrError, match="scanXZFromYPlus|cannot open|not defined"):
+        with capi.stdout_to_stderr():
+            capi.read_scene(str(tmp_path / "RTC3.txt"))
