@@ -376,6 +376,10 @@ typedef struct SlrGpuRenderStats {
     /* hits shaded per material class (always filled): 0 Lambert, 1 Oren-Nayar, 2 specular reflection, 3 specular
      * scattering, 4 Ward-Duer, 5 Ashikhmin-Shirley, 6 microfacet reflection, 7 microfacet scattering, 8 sum / mix / inverse */
     uint64_t class_hits[9];
+    /* the tail kernel (the persistent kernel that finishes the last long paths of a call): paths it took over and
+     * the longest run of bounces it made (always filled; 0 = it never ran); its device time only with PROFILE_STAGES */
+    uint64_t tail_paths, tail_waves;
+    float tail_ms, reserved0;
 } SlrGpuRenderStats;
 
 #define SLRGPU_RENDER_PROFILE_STAGES 0x1u

@@ -129,7 +129,7 @@ class RenderStats(C.Structure):
                 ("kernel_launches", c_u64), ("device_ms", c_f), ("raygen_ms", c_f), ("extend_ms", c_f), ("surface_ms", c_f), ("material_ms", c_f),
                 ("shadow_ms", c_f), ("other_ms", c_f), ("waves", c_u64), ("extend_nodes", c_u64),
                 ("extend_leaf_records", c_u64), ("shadow_nodes", c_u64), ("shadow_leaf_records", c_u64),
-                ("class_hits", c_u64 * 9)]
+                ("class_hits", c_u64 * 9), ("tail_paths", c_u64), ("tail_waves", c_u64), ("tail_ms", c_f), ("reserved0", c_f)]
 
 
 _ABI_STRUCTS = [SceneDesc, BvhNode, LeafRecord, Instance, Triangle, Vertex, Spectrum, Texture, Image,

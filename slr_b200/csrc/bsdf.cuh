@@ -134,7 +134,7 @@ __device__ __forceinline__ float ggxPdfVisible(float alpha, const V3& v, const V
     return ggxSmithG1(alpha, v, m) * absDot(v, m) * ggxD(alpha, m) / fabsf(v.z);
 }
 // Heitz's visible-normal sampling as the reference implements it (doubles where it uses double literals)
-__device__ __noinline__ float ggxSampleVisible(float alpha, const V3& v, float u0, float u1, V3* m, float* normalPDF) {
+static __device__ __noinline__ float ggxSampleVisible(float alpha, const V3& v, float u0, float u1, V3* m, float* normalPDF) {
     V3 sv = normalize(V3(alpha * v.x, alpha * v.y, v.z));
     float theta_sv = acosf(sv.z);
     float phi_sv = atan2f(sv.y, sv.x);
@@ -182,7 +182,7 @@ __device__ __noinline__ float ggxSampleVisible(float alpha, const V3& v, float u
 template <int NC> __device__ __forceinline__ Spec<NC> specZero() { return specConst<NC>(0.0f); }
 
 template <int NC>
-__device__ __noinline__ Spec<NC> ashikhminEval(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir, const V3& halfv, float* specPDF) {
+static __device__ __noinline__ Spec<NC> ashikhminEval(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir, const V3& halfv, float* specPDF) {
     const float nu = L.f0, nv = L.f1;
     const float dotHV = dot(halfv, q.dir);
     const float ex = (nu * halfv.x * halfv.x + nv * halfv.y * halfv.y) / (1 - halfv.z * halfv.z);
@@ -212,7 +212,7 @@ __device__ __forceinline__ void ashikhminWeights(const Lobe<NC>& L, const BsdfQu
 
 // rough-refraction value for all wavelengths with per-wavelength half vectors (MicrofacetBSDF.cpp:174-188)
 template <int NC>
-__device__ __noinline__ Spec<NC> mfTransmissionEval(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir, bool entering) {
+static __device__ __noinline__ Spec<NC> mfTransmissionEval(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir, bool entering) {
     const float alpha = L.f0;
     Spec<NC> ret;
 #pragma unroll 1
@@ -423,7 +423,7 @@ __device__ __forceinline__ Spec<NC> baseSampleT(const Lobe<NC>& L, const BsdfQue
 }
 
 template <int NC>
-__device__ __noinline__ Spec<NC> baseSample(const Lobe<NC>& L, const BsdfQuery& q, float uComp, float u0, float u1, BsdfSampleResult* res) {
+static __device__ __noinline__ Spec<NC> baseSample(const Lobe<NC>& L, const BsdfQuery& q, float uComp, float u0, float u1, BsdfSampleResult* res) {
     return baseSampleT<NC, -1>(L, q, uComp, u0, u1, res);
 }
 
@@ -496,7 +496,7 @@ __device__ __forceinline__ Spec<NC> baseEvaluateT(const Lobe<NC>& L, const BsdfQ
 }
 
 template <int NC>
-__device__ __noinline__ Spec<NC> baseEvaluate(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir) { return baseEvaluateT<NC, -1>(L, q, dir); }
+static __device__ __noinline__ Spec<NC> baseEvaluate(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir) { return baseEvaluateT<NC, -1>(L, q, dir); }
 
 template <int NC, int LT>
 __device__ __forceinline__ float basePdfT(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir) {
@@ -570,10 +570,10 @@ __device__ __forceinline__ float basePdfT(const Lobe<NC>& L, const BsdfQuery& q,
 }
 
 template <int NC>
-__device__ __noinline__ float basePdf(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir) { return basePdfT<NC, -1>(L, q, dir); }
+static __device__ __noinline__ float basePdf(const Lobe<NC>& L, const BsdfQuery& q, const V3& dir) { return basePdfT<NC, -1>(L, q, dir); }
 
 template <int NC>
-__device__ __noinline__ float baseWeight(const Lobe<NC>& L, const BsdfQuery& q) {
+static __device__ __noinline__ float baseWeight(const Lobe<NC>& L, const BsdfQuery& q) {
     switch (L.type) {
     case LOBE_LAMBERT: return specImportance(L.s0, q.hero);
     case LOBE_OREN_NAYAR: {   // luminance() = plain mean in spectral mode (SpectrumTypes.h:504-509)

@@ -86,7 +86,7 @@ __device__ __forceinline__ void fillLobeT(const DeviceScene& s, const SlrGpuMate
 }
 
 template <int NC>
-__device__ __noinline__ void fillLobe(const DeviceScene& s, const SlrGpuMaterial& m, const SurfPt& sp, float wlOffset, bool lambdaSelected,
+static __device__ __noinline__ void fillLobe(const DeviceScene& s, const SlrGpuMaterial& m, const SurfPt& sp, float wlOffset, bool lambdaSelected,
                                 float scale, uint32_t inverse, Lobe<NC>* L) {
     fillLobeT<NC, -1>(s, m, sp, wlOffset, lambdaSelected, scale, inverse, L);
 }
@@ -96,7 +96,7 @@ __device__ __noinline__ void fillLobe(const DeviceScene& s, const SlrGpuMaterial
 // mapped alpha texture therefore sees an indeterminate position in the reference; here it sees p.
 
 template <int NC, int ML>
-__device__ __noinline__ void buildBsdf(const DeviceScene& s, uint32_t materialId, const SurfPt& sp, float wlOffset, bool lambdaSelected,
+static __device__ __noinline__ void buildBsdf(const DeviceScene& s, uint32_t materialId, const SurfPt& sp, float wlOffset, bool lambdaSelected,
                                  Bsdf<NC, ML>* out) {
     out->numLobes = 0; out->multi = false; out->type = 0;
     // explicit DFS over the material tree

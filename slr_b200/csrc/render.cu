@@ -8,12 +8,12 @@
 // The reference walks one path at a time per CPU thread; here up to `pool_size` paths are in flight
 // and every kernel launch advances all of them by one stage. Finished paths are replaced by new
 // camera samples (path regeneration) until the sample range is exhausted.
-#include "rng.cuh"
-#include "shade.cuh"
-#include "wavefront.cuh"
+#include "stages.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -32,34 +32,6 @@ constexpr int kRaygenBlock = 128;
 #define SLR_SURFACE_MIN_BLOCKS 1
 #endif
 
-// position of `alive` lanes in an output queue: one atomic per warp
-__device__ __forceinline__ uint32_t warpAppend(bool alive, uint32_t* counter) {
-    const unsigned mask = __ballot_sync(0xFFFFFFFFu, alive);
-    if (mask == 0) return 0;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    return base + __popc(mask & ((1u << lane) - 1u));
-}
-
-template <int NC> __device__ __forceinline__ void storeAlpha(const PathQueue& q, uint32_t pos, const Spec<NC>& a) {
-    if (NC == 3) { q.alpha[pos] = make_float4(a.v[0], a.v[1], a.v[2], 0.0f); return; }
-#pragma unroll
-    for (int k = 0; k < NC / 4; ++k)
-        q.alpha[(size_t)k * q.capacity + pos] = make_float4(a.v[4 * k], a.v[(4 * k + 1) % NC], a.v[(4 * k + 2) % NC], a.v[(4 * k + 3) % NC]);
-}
-template <int NC> __device__ __forceinline__ Spec<NC> loadAlpha(const PathQueue& q, uint32_t pos) {
-    Spec<NC> a;
-    if (NC == 3) { const float4 v = q.alpha[pos]; a.v[0] = v.x; a.v[1] = v.y; a.v[2] = v.z; return a; }
-#pragma unroll
-    for (int k = 0; k < NC / 4; ++k) {
-        const float4 v = q.alpha[(size_t)k * q.capacity + pos];
-        a.v[4 * k] = v.x; a.v[(4 * k + 1) % NC] = v.y; a.v[(4 * k + 2) % NC] = v.z; a.v[(4 * k + 3) % NC] = v.w;
-    }
-    return a;
-}
 
 // ---------------------------------------------------------------------------------------------
 // ray generation: fills the free tail of the current queue with fresh camera samples
@@ -142,7 +114,13 @@ __global__ void beginWaveKernel(const RenderConstants rc, WavefrontCounters* cou
 
 // after shadow: the next queue becomes the current one (single thread)
 // `ring` is pinned host memory (device-visible through UVA): the snapshot the host polls
-__global__ void endWaveKernel(WavefrontCounters* counters, WavefrontCounters* ring, uint32_t ringSize) {
+// `log` (SLRGPU_WAVE_LOG runs only, else null): per wave the device clock and the sizes of the queues it leaves
+__global__ void endWaveKernel(WavefrontCounters* counters, WavefrontCounters* ring, uint32_t ringSize, ulonglong2* log, uint32_t logSize) {
+    if (log && counters->waves < logSize) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        log[counters->waves] = make_ulonglong2(t, (unsigned long long)counters->numNext | ((unsigned long long)counters->numShadow << 32));
+    }
     counters->shadowRays += counters->numShadow;
     counters->numPaths = counters->numNext;
     counters->numNext = 0;
@@ -157,259 +135,19 @@ __global__ void endWaveKernel(WavefrontCounters* counters, WavefrontCounters* ri
     __threadfence_system();
 }
 
-// Emission seen by the ray that arrived at an emitter (or left the scene into the environment), with the
-// MIS weight of implicit light sampling (PathTracingRenderer.cpp:152-156, 232-249). Kept out of line:
-// only a few per cent of the hits take it, and inlined it doubles the register count of the surface kernel.
-template <int NC>
-__device__ __noinline__ void surfaceEmission(const DeviceScene& s, const PathQueue& in, const HitBuffer& hits, uint32_t i, uint2 hid, uint4 meta,
-                                             uint32_t flags, uint32_t material, const SlrGpuTriangle& tri, bool isEnv, float* __restrict__ accum) {
-    const Spec<NC> alpha = loadAlpha<NC>(in, i);
-    const float4 o4 = in.org[i], d4 = in.dir[i];
-    const V3 org(o4.x, o4.y, o4.z), dir(d4.x, d4.y, d4.z);
-    const float prevPdf = d4.w;
-    const float wlOffset = __uint_as_float(meta.w);
-    const bool cameraRay = flags & kFlagCameraRay;
-    SurfPt sp;
-    float localArea = 1.0f;
-    if (isEnv) envSurfacePoint(dir, &sp);
-    else { const float4 htuv = hits.tuv[i]; hitSurfacePoint(s, hid.x, hid.y, htuv.x, htuv.y, htuv.z, org, dir, &sp, &localArea); }
-    const V3 dirOut = sp.sf.toLocal(-dir);
-    // DiffuseEDF: 1/pi on the front side; IBLEDF: 1/pi
-    const float edf = (sp.atInfinity || dirOut.z > 0.0f) ? 1.0f / kPi : 0.0f;
-    if (edf <= 0.0f) return;
-    float mis = 1.0f;
-    if (!cameraRay && !(flags & kFlagPrevDelta)) {
-        const float lightProb = lightSelectionProb(s, tri, hid.y, sp.atInfinity);
-        float areaPDF, dist2;
-        if (sp.atInfinity) { areaPDF = envEvaluateUVPDF(s, sp.u / (2 * kPi), sp.v / kPi) / (2 * kPi * kPi * sinf(sp.v)); dist2 = 1.0f; }
-        else { areaPDF = 1.0f / localArea; dist2 = sqLength(sp.p - org); }
-        const float lightPDF = lightProb * areaPDF * dist2 / absDot(dir, sp.gn);
-        mis = (prevPdf * prevPdf) / (lightPDF * lightPDF + prevPdf * prevPdf);
-    }
-    const Spec<NC> Le = materialEmittance<NC>(s, material, sp, wlOffset);
-    float v[NC == 3 ? 4 : NC];
-    const float k = edf * mis * in.weight[i];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) v[c] = alpha.v[c] * Le.v[c] * k;
-    splat<NC>(accum, meta.x, wlOffset, (flags & kFlagStrataInPlace) != 0, v);
-}
-
-// ---------------------------------------------------------------------------------------------
-// surface: what Job::contribution does between a hit and the BSDF of that hit -- emission seen by the
-// ray that arrived (implicit light sampling with MIS), the environment for rays that left the scene,
-// Russian roulette and the path-length cap (PathTracingRenderer.cpp:147-163, 225-258). Survivors are
-// sorted into one queue per material class.
-// ---------------------------------------------------------------------------------------------
+// the shade stages (stages.cuh) as grid-stride kernels over the device-resident counts
 template <int NC>
 __global__ void __launch_bounds__(kSurfaceBlock, SLR_SURFACE_MIN_BLOCKS)
 surfaceKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitBuffer hits, ClassQueue cq,
               float* __restrict__ accum, WavefrontCounters* counters) {
-    const uint32_t n = counters->numPaths;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
-        const uint32_t i = base + lane;
-        uint32_t cls = SC_NONE, leaf = SLRGPU_INVALID_ID;
-        if (i < n) {
-            const uint2 hid = hits.id[i];
-            uint4 meta = in.meta[i];
-            const uint32_t hero = meta.z & 0xFFu;
-            const uint32_t flags = (meta.z >> 8) & 0xFFu;
-            uint32_t pathLength = meta.z >> 16;
-            const bool cameraRay = flags & kFlagCameraRay;
-            const bool isEnv = hid.x == SLRGPU_INVALID_ID;
-            if (!isEnv || s.envPresent) {
-                uint32_t material = s.envMaterial;
-                SlrGpuTriangle tri = {};
-                bool emitting = true;
-                if (!isEnv) {
-                    tri = s.triangles[hid.x];
-                    material = tri.material;
-                    emitting = materialIsEmitting(s, material);
-                }
-                if (emitting) surfaceEmission<NC>(s, in, hits, i, hid, meta, flags, material, tri, isEnv, accum);
-                bool cont = !isEnv;
-                if (cont && !cameraRay) {
-                    // Russian roulette; initY = importance of a unit spectrum = 1. importance(alpha) was left in
-                    // aux by the material kernel that produced this entry; the surviving path's 1/q goes back
-                    // into aux and is applied to alpha by the material kernel of this bounce.
-                    const float continueProb = fminf(in.aux[i], 1.0f);
-                    const Rand4 rr = pathRandom(rc.seed, meta.x, meta.y, 2 * pathLength + 1);   // .z of the previous bounce's second block
-                    if (rr.z < continueProb) in.aux[i] = 1.0f / continueProb;
-                    else cont = false;
-                }
-                if (cont) {
-                    ++pathLength;
-                    if (pathLength >= rc.maxPathLength) cont = false;
-                }
-                if (cont) {
-                    cls = classifyMaterial(s, material, &leaf);
-                    if (cls != SC_NONE) in.meta[i].z = hero | (flags << 8) | (pathLength << 16);
-                }
-            }
-        }
-        // append to the class queues: one atomic per (warp, class)
-        const unsigned active = __ballot_sync(0xFFFFFFFFu, cls != SC_NONE);
-        if (cls != SC_NONE) {
-            const unsigned grp = __match_any_sync(active, cls);
-            const int leader = __ffs(grp) - 1;
-            uint32_t pos = 0;
-            if ((int)lane == leader) pos = atomicAdd(&counters->classCount[cls], (uint32_t)__popc(grp));
-            pos = __shfl_sync(grp, pos, leader) + __popc(grp & ((1u << lane) - 1u));
-            cq.entries[(size_t)cls * cq.capacity + pos] = make_uint2(i, leaf);
-        }
-    }
+    surfaceStage<NC>(s, rc, in, hits, cq, accum, counters, counters->numPaths);
 }
-
-// ---------------------------------------------------------------------------------------------
-// material: for every survivor of one class -- BSDF at the hit, next event estimation (the shadow ray
-// goes to the shadow queue with its MIS-weighted contribution), BSDF sampling of the next direction
-// (PathTracingRenderer.cpp:164-222). CLASS < SC_GENERIC: one lobe of compile-time type; SC_GENERIC:
-// the tagged multi-lobe BSDF.
-// ---------------------------------------------------------------------------------------------
-template <int NC, int CLASS> struct HitBsdf {
-    Lobe<NC> lobe;
-    __device__ __forceinline__ void build(const DeviceScene& s, uint32_t leaf, const SurfPt& sp, float wlOffset, bool lambdaSelected) {
-        fillLobeT<NC, classMaterialKind(CLASS)>(s, s.materials[leaf], sp, wlOffset, lambdaSelected, 1.0f, 0u, &lobe);
-    }
-    __device__ __forceinline__ bool hasNonDelta() const { return dtMatches(lobe.baseDirType, DT_WholeSphere | DT_NonDelta); }
-    __device__ __forceinline__ Spec<NC> evaluate(const BsdfQuery& q, const V3& d) const { return lobeEvaluate<NC, CLASS>(lobe, q, d); }
-    __device__ __forceinline__ float pdf(const BsdfQuery& q, const V3& d) const { return lobePdf<NC, CLASS>(lobe, q, d); }
-    __device__ __forceinline__ Spec<NC> sample(const BsdfQuery& q, float uc, float u0, float u1, BsdfSampleResult* r) const { return lobeSample<NC, CLASS>(lobe, q, uc, u0, u1, r); }
-};
-template <int NC> struct HitBsdf<NC, SC_GENERIC> {
-    Bsdf<NC, 4> bsdf;
-    __device__ __forceinline__ void build(const DeviceScene& s, uint32_t leaf, const SurfPt& sp, float wlOffset, bool lambdaSelected) {
-        buildBsdf<NC, 4>(s, leaf, sp, wlOffset, lambdaSelected, &bsdf);
-    }
-    __device__ __forceinline__ bool hasNonDelta() const { return bsdfHasNonDelta(bsdf); }
-    __device__ __forceinline__ Spec<NC> evaluate(const BsdfQuery& q, const V3& d) const { return bsdfEvaluate(bsdf, q, d); }
-    __device__ __forceinline__ float pdf(const BsdfQuery& q, const V3& d) const { return bsdfPdf(bsdf, q, d); }
-    __device__ __forceinline__ Spec<NC> sample(const BsdfQuery& q, float uc, float u0, float u1, BsdfSampleResult* r) const { return bsdfSample(bsdf, q, uc, u0, u1, r); }
-};
 
 template <int NC, int CLASS>
 __global__ void __launch_bounds__(kMaterialBlock, SLR_MATERIAL_MIN_BLOCKS)
 materialKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitBuffer hits, ClassQueue cq, PathQueue out, ShadowQueue sq,
                WavefrontCounters* counters) {
-    const uint32_t n = counters->classCount[CLASS];
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint2* __restrict__ entries = cq.entries + (size_t)CLASS * cq.capacity;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
-        const uint32_t k = base + lane;
-        bool alive = false, shadow = false;
-        V3 nOrg(0, 0, 0), nDir(0, 0, 1);
-        float nPdf = 0.0f, nImp = 0.0f;
-        uint4 meta = make_uint4(0, 0, 0, 0);
-        float weight = 0.0f;
-        Spec<NC> alpha = specConst<NC>(0.0f);
-        V3 sOrg(0, 0, 0), sDir(0, 0, 1);
-        float sTmax = 0.0f;
-        Spec<NC> sContrib = specConst<NC>(0.0f);
-
-        if (k < n) {
-            const uint2 e = entries[k];
-            const uint32_t i = e.x;
-            const float4 o4 = in.org[i], d4 = in.dir[i];
-            meta = in.meta[i];
-            weight = in.weight[i];
-            alpha = loadAlpha<NC>(in, i) * in.aux[i];          // Russian-roulette scale decided by `surface`
-            const uint2 hid = hits.id[i];
-            const float4 htuv = hits.tuv[i];
-            const V3 org(o4.x, o4.y, o4.z), dir(d4.x, d4.y, d4.z);
-            const uint32_t hero = meta.z & 0xFFu;
-            uint32_t flags = (meta.z >> 8) & 0xFFu;
-            const uint32_t pathLength = meta.z >> 16;
-            const float wlOffset = __uint_as_float(meta.w);
-
-            SurfPt sp;
-            float localArea;
-            hitSurfacePoint(s, hid.x, hid.y, htuv.x, htuv.y, htuv.z, org, dir, &sp, &localArea);
-            const V3 dirOut = sp.sf.toLocal(-dir);
-            const V3 gNorm = sp.sf.toLocal(sp.gn);
-            HitBsdf<NC, CLASS> bsdf;
-            bsdf.build(s, e.y, sp, wlOffset, (flags & kFlagLambdaSelected) != 0);
-            BsdfQuery q;
-            q.dir = dirOut; q.gn = gNorm; q.hero = hero; q.flags = DT_All;
-            const Rand4 ra = pathRandom(rc.seed, meta.x, meta.y, 2 * pathLength);       // light select, light u0, u1, bsdf component
-            const Rand4 rb = pathRandom(rc.seed, meta.x, meta.y, 2 * pathLength + 1);   // bsdf u0, u1
-
-            // next event estimation
-            if (bsdf.hasNonDelta() && (s.numTopLights > 0 || s.envPresent)) {
-                LightSample ls;
-                sampleLight(s, ra.x, ra.y, ra.z, &ls);
-                float dist2;
-                V3 shadowDir;
-                if (ls.sp.atInfinity) { dist2 = 1.0f; shadowDir = normalize(ls.sp.p); }
-                else { const V3 d = ls.sp.p - sp.p; dist2 = sqLength(d); shadowDir = d / sqrtf(dist2); }
-                const V3 shadowDir_l = ls.sp.sf.toLocal(-shadowDir);
-                const V3 shadowDir_sn = sp.sf.toLocal(shadowDir);
-                const float edf = (ls.isEnv || shadowDir_l.z > 0.0f) ? 1.0f / kPi : 0.0f;
-                if (edf > 0.0f && ls.areaPDF > 0.0f) {
-                    const Spec<NC> fs = bsdf.evaluate(q, shadowDir_sn);
-                    if (!specIsZero(fs)) {
-                        const Spec<NC> M = materialEmittance<NC>(s, ls.material, ls.sp, wlOffset);
-                        const float cosLight = absDot(-shadowDir, ls.sp.gn);
-                        const float bsdfPDF = bsdf.pdf(q, shadowDir_sn) * cosLight / dist2;
-                        float mis = 1.0f;
-                        if (!isinf(ls.areaPDF)) mis = (ls.lightPDF * ls.lightPDF) / (ls.lightPDF * ls.lightPDF + bsdfPDF * bsdfPDF);
-                        const float G = absDot(shadowDir_sn, gNorm) * cosLight / dist2;
-                        const float kk = edf * (G * mis / ls.lightPDF) * weight;
-#pragma unroll
-                        for (int c = 0; c < NC; ++c) sContrib.v[c] = alpha.v[c] * M.v[c] * fs.v[c] * kk;
-                        // Scene::testVisibility
-                        sOrg = sp.p;
-                        if (ls.sp.atInfinity) { sDir = shadowDir; sTmax = 3.402823466e+38f; }
-                        else { const float dist = length(ls.sp.p - sp.p); sDir = (ls.sp.p - sp.p) / dist; sTmax = dist * (1.0f - 0.0001f); }
-                        shadow = true;
-                    }
-                }
-            }
-
-            // sample the BSDF for the next direction
-            BsdfSampleResult res;
-            const Spec<NC> fs = bsdf.sample(q, ra.w, rb.x, rb.y, &res);
-            if (!specIsZero(fs) && res.pdf != 0.0f) {
-                float dirPDF = res.pdf;
-                if (res.type & DT_Dispersive) { dirPDF /= NC; flags |= kFlagLambdaSelected; }
-                const float kk = absDot(res.dir, gNorm) / dirPDF;
-                alpha = alpha * (fs * kk);
-                nOrg = sp.p;
-                nDir = sp.sf.fromLocal(res.dir);
-                nPdf = dirPDF;
-                flags &= ~(kFlagCameraRay | kFlagPrevDelta);
-                if (dtIsDelta(res.type)) flags |= kFlagPrevDelta;
-                meta.z = hero | (flags << 8) | (pathLength << 16);
-                nImp = specImportance(alpha, hero);
-                alive = true;
-            }
-        }
-
-        const uint32_t spos = warpAppend(shadow, &counters->numShadow);
-        if (shadow) {
-            sq.org[spos] = make_float4(sOrg.x, sOrg.y, sOrg.z, 0.0001f);
-            sq.dir[spos] = make_float4(sDir.x, sDir.y, sDir.z, sTmax);
-            const bool inPlace = ((meta.z >> 8) & kFlagStrataInPlace) != 0;
-            sq.pixelWl[spos] = make_uint2(meta.x | (inPlace ? 0x80000000u : 0u), meta.w);
-            if (NC == 3) sq.contrib[spos] = make_float4(sContrib.v[0], sContrib.v[1], sContrib.v[2], 0.0f);
-            else {
-#pragma unroll
-                for (int c = 0; c < NC / 4; ++c)
-                    sq.contrib[(size_t)c * sq.capacity + spos] =
-                        make_float4(sContrib.v[4 * c], sContrib.v[(4 * c + 1) % NC], sContrib.v[(4 * c + 2) % NC], sContrib.v[(4 * c + 3) % NC]);
-            }
-        }
-        const uint32_t npos = warpAppend(alive, &counters->numNext);
-        if (alive) {
-            out.org[npos] = make_float4(nOrg.x, nOrg.y, nOrg.z, 0.0001f);      // Ray::Epsilon
-            out.dir[npos] = make_float4(nDir.x, nDir.y, nDir.z, nPdf);
-            out.meta[npos] = meta;
-            out.weight[npos] = weight;
-            out.aux[npos] = nImp;
-            storeAlpha<NC>(out, npos, alpha);
-        }
-    }
+    materialStage<NC, CLASS>(s, rc, in, hits, cq, out, sq, counters, counters->classCount[CLASS]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -423,6 +161,7 @@ struct RenderWorkspace {
     HitBuffer hits;
     ShadowQueue sq;
     ClassQueue cq;
+    ulonglong2* dWaveLog = nullptr;              // kWaveLogSize entries, written only in SLRGPU_WAVE_LOG runs
     WavefrontCounters* dCounters = nullptr;
     WavefrontCounters* hCounters = nullptr;      // pinned ring of kRing snapshots, written by endWaveKernel
     cudaEvent_t ringEvents[8] = {};
@@ -468,6 +207,7 @@ struct RenderWorkspace {
     }
 };
 constexpr int kRing = 8;
+constexpr uint32_t kWaveLogSize = 4096;
 
 static int allocPathQueue(RenderWorkspace& b, PathQueue* q, uint32_t P, int quarters) {
     int rc;
@@ -515,6 +255,7 @@ static int acquireWorkspace(SlrGpuScene* sc, uint32_t P, RenderWorkspace** out) 
     if (!rc) rc = w->alloc(&w->sq.contrib, (uint64_t)P * quarters);
     if (!rc) rc = w->alloc(&w->cq.entries, (uint64_t)P * SC_COUNT);
     if (!rc) rc = w->alloc(&w->dCounters, 1);
+    if (!rc) rc = w->alloc(&w->dWaveLog, kWaveLogSize);
     if (!rc) { cudaError_t e = cudaMallocHost(&w->hCounters, sizeof(WavefrontCounters) * kRing); if (e != cudaSuccess) rc = cudaFail(e, "cudaMallocHost"); }
     for (int k = 0; k < kRing && !rc; ++k) { cudaError_t e = cudaEventCreateWithFlags(&w->ringEvents[k], cudaEventDisableTiming); if (e != cudaSuccess) rc = cudaFail(e, "cudaEventCreate"); }
     if (!rc) { cudaError_t e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking); if (e != cudaSuccess) rc = cudaFail(e, "cudaStreamCreate"); }
@@ -571,6 +312,19 @@ static uint32_t poolCapacity(const SlrGpuRenderParams* p) {
     return P == 0 ? 128u : P;
 }
 
+// SLRGPU_WAVE_LOG=<file>: appends one line per wave of the call -- microseconds since the first wave ended, paths
+// and shadow rays that wave left -- the timeline the ncu launch list cannot give (its kernels run serialised)
+static void dumpWaveLog(const char* path, const ulonglong2* dLog, uint32_t n, const WavefrontCounters& last) {
+    std::vector<ulonglong2> log(n);
+    if (n && cudaMemcpy(log.data(), dLog, n * sizeof(ulonglong2), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return; }
+    FILE* f = fopen(path, "a");
+    if (!f) return;
+    fprintf(f, "# render call: %u waves, tail kernel: %u paths, %u bounces\n", last.waves, last.tailPaths, last.tailWaves);
+    for (uint32_t i = 0; i < n; ++i)
+        fprintf(f, "%u,%.1f,%u,%u\n", i, (double)(log[i].x - log[0].x) * 1e-3, (uint32_t)(log[i].y & 0xFFFFFFFFull), (uint32_t)(log[i].y >> 32));
+    fclose(f);
+}
+
 static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorkspace& w, float* accumDev, cudaStream_t stream, SlrGpuRenderStats* stats) {
     const bool rgb = sc->channels == 3;
     const uint32_t W = p->width, H = p->height;
@@ -611,7 +365,7 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
     // per-stage device time (SLRGPU_RENDER_PROFILE_STAGES): one event pair per launch group, summed at the end
     const bool profile = (p->flags & SLRGPU_RENDER_PROFILE_STAGES) != 0;
     struct StageTimer {
-        std::vector<cudaEvent_t> ev[5];      // 0 raygen, 1 extend, 2 surface, 3 material kernels, 4 shadow: begin/end pairs
+        std::vector<cudaEvent_t> ev[6];      // 0 raygen, 1 extend, 2 surface, 3 material kernels, 4 shadow, 5 tail kernel: begin/end pairs
         bool on;
         cudaStream_t st;
         void mark(int stage) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev[stage].push_back(e); }
@@ -638,6 +392,18 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
     // microseconds). Outside profiling two waves (one ping + one pong of the path queues) are captured
     // into a CUDA graph once per call and replayed: one driver call per ~20 kernel launches.
     constexpr int kLag = 2;
+    // the tail kernel (tail.cu) takes over when at most one path per thread of it is left; SLRGPU_TAIL_PATHS overrides
+    // the limit (0 = no tail kernel: every bounce is a wave) -- a tuning / test knob, the image does not depend on it
+    uint32_t tailCap = tailCapacity(numSMs);
+    if (const char* e = getenv("SLRGPU_TAIL_PATHS")) tailCap = std::min((uint32_t)strtoul(e, nullptr, 10), tailCap);
+    const char* waveLogPath = getenv("SLRGPU_WAVE_LOG");
+    ulonglong2* waveLog = waveLogPath ? w.dWaveLog : nullptr;
+    auto enqueueTail = [&]() -> int {
+        timer.mark(5);
+        int r = launchTail(sc, rc, w.q[0], w.q[1], w.hits, w.sq, accumDev, w.dCounters, w.hCounters, (uint32_t)kRing, tailCap, stream);
+        timer.mark(5);
+        return r;
+    };
     const uint32_t launchesPerWave = 6u + (uint32_t)__builtin_popcount(sc->classMask);
     unsigned long long wave = 0, launches = 0, round = 0;
     auto enqueueWave = [&](int cur) -> int {
@@ -655,7 +421,7 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
         else launchShadeStage<16>(sc, rc, w, cur, accumDev, grid, stream, mark);
         timer.mark(4);
         if ((r = launchShadow(sc, w.sq, accumDev, w.dCounters, profile, grid, stream))) return r;
-        endWaveKernel<<<1, 1, 0, stream>>>(w.dCounters, w.hCounters, (uint32_t)kRing);
+        endWaveKernel<<<1, 1, 0, stream>>>(w.dCounters, w.hCounters, (uint32_t)kRing, waveLog, kWaveLogSize);
         timer.mark(4);
         return SLRGPU_OK;
     };
@@ -666,6 +432,7 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
         if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             int r0 = enqueueWave(0);
             int r1 = r0 ? r0 : enqueueWave(1);
+            if (!r1) r1 = enqueueTail();
             cudaError_t ce = cudaStreamEndCapture(stream, &graph);
             if (r1) return r1;
             if (ce == cudaSuccess && graph) { if (cudaGraphInstantiate(&graphExec, graph, 0) != cudaSuccess) graphExec = nullptr; }
@@ -678,10 +445,11 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
         else {
             if ((rcode = enqueueWave(0))) return rcode;
             if ((rcode = enqueueWave(1))) return rcode;
+            if ((rcode = enqueueTail())) return rcode;
             SLRGPU_CUDA_TRY(cudaGetLastError());
         }
         wave += 2;
-        launches += 2 * launchesPerWave;
+        launches += 2 * launchesPerWave + (tailCap ? 2u : 0u);
         SLRGPU_CUDA_TRY(cudaEventRecord(w.ringEvents[round % kRing], stream));
         ++round;
         if (round >= (unsigned long long)kLag) {
@@ -703,15 +471,18 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
         stats->kernel_launches = launches;
         stats->waves = wave;
         for (int c = 0; c < 9; ++c) stats->class_hits[c] = last.classTotal[c];
+        stats->tail_paths = last.tailPaths; stats->tail_waves = last.tailWaves;
         cudaEventElapsedTime(&stats->device_ms, ev0, ev1);
         if (profile) {
             stats->raygen_ms = timer.total(0); stats->extend_ms = timer.total(1);
             stats->surface_ms = timer.total(2); stats->material_ms = timer.total(3); stats->shadow_ms = timer.total(4);
-            stats->other_ms = stats->device_ms - stats->raygen_ms - stats->extend_ms - stats->surface_ms - stats->material_ms - stats->shadow_ms;
+            stats->tail_ms = timer.total(5);
+            stats->other_ms = stats->device_ms - stats->raygen_ms - stats->extend_ms - stats->surface_ms - stats->material_ms - stats->shadow_ms - stats->tail_ms;
             stats->extend_nodes = last.extendNodes; stats->extend_leaf_records = last.extendLeafRecords;
             stats->shadow_nodes = last.shadowNodes; stats->shadow_leaf_records = last.shadowLeafRecords;
         }
     }
+    if (waveLogPath) dumpWaveLog(waveLogPath, w.dWaveLog, std::min((uint32_t)last.waves, kWaveLogSize), last);
     if (last.stackOverflow) { setError("traversal stack overflow (more than %d entries)", 64); return SLRGPU_ERR_STACK_OVERFLOW; }
     return SLRGPU_OK;
 }

@@ -68,7 +68,7 @@ __device__ __forceinline__ void transformSurfPt(const SlrGpuInstance& inst, Surf
 
 // Intersection -> SurfacePoint for a triangle hit. Returns the hit triangle's record; *localArea is
 // the area evaluateAreaPDF uses (object space, also for instances -- as the reference).
-__device__ __noinline__ SlrGpuTriangle hitSurfacePoint(const DeviceScene& s, uint32_t prim, uint32_t inst, float t, float b0, float b1,
+static __device__ __noinline__ SlrGpuTriangle hitSurfacePoint(const DeviceScene& s, uint32_t prim, uint32_t inst, float t, float b0, float b1,
                                                  const V3& org, const V3& dir, SurfPt* sp, float* localArea) {
     const SlrGpuTriangle tri = s.triangles[prim];
     const TriVerts tv = loadTriangle(s, tri);
@@ -151,7 +151,7 @@ struct LightSample {
 };
 
 // Scene::selectLight + Light::sample (SurfaceObject.cpp:432-452, 82-91, 158-185, 351-364)
-__device__ __noinline__ void sampleLight(const DeviceScene& s, float uSel, float u0, float u1, LightSample* ls) {
+static __device__ __noinline__ void sampleLight(const DeviceScene& s, float uSel, float u0, float u1, LightSample* ls) {
     float prob = 1.0f;
     bool env = false;
     const float aggrImp = s.topLightImportance;

@@ -112,7 +112,7 @@ struct UpsampleWeights {
 
 constexpr int kUpGridW = 12, kUpGridH = 14, kUpNumWl = 95, kUpPointStride = 99;   // xystar[2] uv[2] spectrum[95]
 
-__device__ __noinline__ UpsampleWeights upsampleWeights(const DeviceScene& s, float u, float v) {
+static __device__ __noinline__ UpsampleWeights upsampleWeights(const DeviceScene& s, float u, float v) {
     UpsampleWeights r;
     r.n = 0;
     if (u < 0.0f || u >= kUpGridW || v < 0.0f || v >= kUpGridH) return r;
@@ -188,7 +188,7 @@ __device__ __forceinline__ float evalIrregularLut(const float* __restrict__ lamb
 // The table was compiled at scene creation: up-sampled spectra arrive as REGULAR, irregular ones with
 // their look-up table; the other kinds are evaluated as the reference does.
 template <int NC>
-__device__ __noinline__ Spec<NC> evalInputSpectrum(const DeviceScene& s, uint32_t id, float wlOffset) {
+static __device__ __noinline__ Spec<NC> evalInputSpectrum(const DeviceScene& s, uint32_t id, float wlOffset) {
     const SlrGpuSpectrum sp = s.spectra[id];
     Spec<NC> out;
     if (NC == 3) {
@@ -221,7 +221,7 @@ __device__ __noinline__ Spec<NC> evalInputSpectrum(const DeviceScene& s, uint32_
 
 // UpsampledContinuousSpectrum built per texel / per Voronoi cell from (u, v, scale)
 template <int NC>
-__device__ __noinline__ Spec<NC> evalUVS(const DeviceScene& s, float u, float v, float scale, float wlOffset) {
+static __device__ __noinline__ Spec<NC> evalUVS(const DeviceScene& s, float u, float v, float scale, float wlOffset) {
     Spec<NC> out;
     const UpsampleWeights w = upsampleWeights(s, u, v);
 #pragma unroll

@@ -1,0 +1,324 @@
+// The shade stages of a wave as device functions: `surface` (emission seen by the arriving ray, Russian
+// roulette, sort into material classes) and `material` (BSDF at the hit, next event estimation, BSDF
+// sampling). render.cu wraps them into the grid-stride kernels of the wavefront loop; tail.cu calls the
+// same functions from the persistent kernel that finishes the last long paths of a frame.
+//   Job::contribution                PathTracingRenderer.cpp:137-261
+#pragma once
+#include "rng.cuh"
+#include "shade.cuh"
+#include "wavefront.cuh"
+
+namespace slrgpu {
+
+// position of `alive` lanes in an output queue: one atomic per warp
+__device__ __forceinline__ uint32_t warpAppend(bool alive, uint32_t* counter) {
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, alive);
+    if (mask == 0) return 0;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+template <int NC> __device__ __forceinline__ void storeAlpha(const PathQueue& q, uint32_t pos, const Spec<NC>& a) {
+    if (NC == 3) { q.alpha[pos] = make_float4(a.v[0], a.v[1], a.v[2], 0.0f); return; }
+#pragma unroll
+    for (int k = 0; k < NC / 4; ++k)
+        q.alpha[(size_t)k * q.capacity + pos] = make_float4(a.v[4 * k], a.v[(4 * k + 1) % NC], a.v[(4 * k + 2) % NC], a.v[(4 * k + 3) % NC]);
+}
+template <int NC> __device__ __forceinline__ Spec<NC> loadAlpha(const PathQueue& q, uint32_t pos) {
+    Spec<NC> a;
+    if (NC == 3) { const float4 v = q.alpha[pos]; a.v[0] = v.x; a.v[1] = v.y; a.v[2] = v.z; return a; }
+#pragma unroll
+    for (int k = 0; k < NC / 4; ++k) {
+        const float4 v = q.alpha[(size_t)k * q.capacity + pos];
+        a.v[4 * k] = v.x; a.v[(4 * k + 1) % NC] = v.y; a.v[(4 * k + 2) % NC] = v.z; a.v[(4 * k + 3) % NC] = v.w;
+    }
+    return a;
+}
+
+// Emission seen by the ray that arrived at an emitter (or left the scene into the environment), with the
+// MIS weight of implicit light sampling (PathTracingRenderer.cpp:152-156, 232-249). Kept out of line:
+// only a few per cent of the hits take it, and inlined it doubles the register count of the surface kernel.
+template <int NC>
+static __device__ __noinline__ void surfaceEmission(const DeviceScene& s, const PathQueue& in, const HitBuffer& hits, uint32_t i, uint2 hid, uint4 meta,
+                                             uint32_t flags, uint32_t material, const SlrGpuTriangle& tri, bool isEnv, float* __restrict__ accum) {
+    const Spec<NC> alpha = loadAlpha<NC>(in, i);
+    const float4 o4 = in.org[i], d4 = in.dir[i];
+    const V3 org(o4.x, o4.y, o4.z), dir(d4.x, d4.y, d4.z);
+    const float prevPdf = d4.w;
+    const float wlOffset = __uint_as_float(meta.w);
+    const bool cameraRay = flags & kFlagCameraRay;
+    SurfPt sp;
+    float localArea = 1.0f;
+    if (isEnv) envSurfacePoint(dir, &sp);
+    else { const float4 htuv = hits.tuv[i]; hitSurfacePoint(s, hid.x, hid.y, htuv.x, htuv.y, htuv.z, org, dir, &sp, &localArea); }
+    const V3 dirOut = sp.sf.toLocal(-dir);
+    // DiffuseEDF: 1/pi on the front side; IBLEDF: 1/pi
+    const float edf = (sp.atInfinity || dirOut.z > 0.0f) ? 1.0f / kPi : 0.0f;
+    if (edf <= 0.0f) return;
+    float mis = 1.0f;
+    if (!cameraRay && !(flags & kFlagPrevDelta)) {
+        const float lightProb = lightSelectionProb(s, tri, hid.y, sp.atInfinity);
+        float areaPDF, dist2;
+        if (sp.atInfinity) { areaPDF = envEvaluateUVPDF(s, sp.u / (2 * kPi), sp.v / kPi) / (2 * kPi * kPi * sinf(sp.v)); dist2 = 1.0f; }
+        else { areaPDF = 1.0f / localArea; dist2 = sqLength(sp.p - org); }
+        const float lightPDF = lightProb * areaPDF * dist2 / absDot(dir, sp.gn);
+        mis = (prevPdf * prevPdf) / (lightPDF * lightPDF + prevPdf * prevPdf);
+    }
+    const Spec<NC> Le = materialEmittance<NC>(s, material, sp, wlOffset);
+    float v[NC == 3 ? 4 : NC];
+    const float k = edf * mis * in.weight[i];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) v[c] = alpha.v[c] * Le.v[c] * k;
+    splat<NC>(accum, meta.x, wlOffset, (flags & kFlagStrataInPlace) != 0, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// surface: what Job::contribution does between a hit and the BSDF of that hit -- emission seen by the
+// ray that arrived (implicit light sampling with MIS), the environment for rays that left the scene,
+// Russian roulette and the path-length cap (PathTracingRenderer.cpp:147-163, 225-258). Survivors are
+// sorted into one queue per material class.
+// ---------------------------------------------------------------------------------------------
+// One path-queue entry: *cls = the material class of the surviving hit (SC_NONE: the path ended here), *leaf = its
+// leaf material.
+template <int NC>
+__device__ __forceinline__ void surfaceItem(const DeviceScene& s, const RenderConstants& rc, const PathQueue& in, const HitBuffer& hits,
+                                            float* __restrict__ accum, uint32_t i, uint32_t* clsOut, uint32_t* leafOut) {
+    uint32_t cls = SC_NONE, leaf = SLRGPU_INVALID_ID;
+    const uint2 hid = hits.id[i];
+    uint4 meta = in.meta[i];
+    const uint32_t hero = meta.z & 0xFFu;
+    const uint32_t flags = (meta.z >> 8) & 0xFFu;
+    uint32_t pathLength = meta.z >> 16;
+    const bool cameraRay = flags & kFlagCameraRay;
+    const bool isEnv = hid.x == SLRGPU_INVALID_ID;
+    if (!isEnv || s.envPresent) {
+        uint32_t material = s.envMaterial;
+        SlrGpuTriangle tri = {};
+        bool emitting = true;
+        if (!isEnv) {
+            tri = s.triangles[hid.x];
+            material = tri.material;
+            emitting = materialIsEmitting(s, material);
+        }
+        if (emitting) surfaceEmission<NC>(s, in, hits, i, hid, meta, flags, material, tri, isEnv, accum);
+        bool cont = !isEnv;
+        if (cont && !cameraRay) {
+            // Russian roulette; initY = importance of a unit spectrum = 1. importance(alpha) was left in
+            // aux by the material kernel that produced this entry; the surviving path's 1/q goes back
+            // into aux and is applied to alpha by the material kernel of this bounce.
+            const float continueProb = fminf(in.aux[i], 1.0f);
+            const Rand4 rr = pathRandom(rc.seed, meta.x, meta.y, 2 * pathLength + 1);   // .z of the previous bounce's second block
+            if (rr.z < continueProb) in.aux[i] = 1.0f / continueProb;
+            else cont = false;
+        }
+        if (cont) {
+            ++pathLength;
+            if (pathLength >= rc.maxPathLength) cont = false;
+        }
+        if (cont) {
+            cls = classifyMaterial(s, material, &leaf);
+            if (cls != SC_NONE) in.meta[i].z = hero | (flags << 8) | (pathLength << 16);
+        }
+    }
+    *clsOut = cls; *leafOut = leaf;
+}
+
+// Work items [0, n) are spread over the whole grid, one warp per 32 consecutive entries.
+template <int NC>
+__device__ __forceinline__ void surfaceStage(const DeviceScene& s, const RenderConstants& rc, const PathQueue& in, const HitBuffer& hits,
+                                             const ClassQueue& cq, float* __restrict__ accum, WavefrontCounters* counters, uint32_t n) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const uint32_t i = base + lane;
+        uint32_t cls = SC_NONE, leaf = SLRGPU_INVALID_ID;
+        if (i < n) surfaceItem<NC>(s, rc, in, hits, accum, i, &cls, &leaf);
+        // append to the class queues: one atomic per (warp, class)
+        const unsigned active = __ballot_sync(0xFFFFFFFFu, cls != SC_NONE);
+        if (cls != SC_NONE) {
+            const unsigned grp = __match_any_sync(active, cls);
+            const int leader = __ffs(grp) - 1;
+            uint32_t pos = 0;
+            if ((int)lane == leader) pos = atomicAdd(&counters->classCount[cls], (uint32_t)__popc(grp));
+            pos = __shfl_sync(grp, pos, leader) + __popc(grp & ((1u << lane) - 1u));
+            cq.entries[(size_t)cls * cq.capacity + pos] = make_uint2(i, leaf);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// material: for every survivor of one class -- BSDF at the hit, next event estimation (the shadow ray
+// goes to the shadow queue with its MIS-weighted contribution), BSDF sampling of the next direction
+// (PathTracingRenderer.cpp:164-222). CLASS < SC_GENERIC: one lobe of compile-time type; SC_GENERIC:
+// the tagged multi-lobe BSDF.
+// ---------------------------------------------------------------------------------------------
+template <int NC, int CLASS> struct HitBsdf {
+    Lobe<NC> lobe;
+    __device__ __forceinline__ void build(const DeviceScene& s, uint32_t leaf, const SurfPt& sp, float wlOffset, bool lambdaSelected) {
+        fillLobeT<NC, classMaterialKind(CLASS)>(s, s.materials[leaf], sp, wlOffset, lambdaSelected, 1.0f, 0u, &lobe);
+    }
+    __device__ __forceinline__ bool hasNonDelta() const { return dtMatches(lobe.baseDirType, DT_WholeSphere | DT_NonDelta); }
+    __device__ __forceinline__ Spec<NC> evaluate(const BsdfQuery& q, const V3& d) const { return lobeEvaluate<NC, CLASS>(lobe, q, d); }
+    __device__ __forceinline__ float pdf(const BsdfQuery& q, const V3& d) const { return lobePdf<NC, CLASS>(lobe, q, d); }
+    __device__ __forceinline__ Spec<NC> sample(const BsdfQuery& q, float uc, float u0, float u1, BsdfSampleResult* r) const { return lobeSample<NC, CLASS>(lobe, q, uc, u0, u1, r); }
+};
+template <int NC> struct HitBsdf<NC, SC_GENERIC> {
+    Bsdf<NC, 4> bsdf;
+    __device__ __forceinline__ void build(const DeviceScene& s, uint32_t leaf, const SurfPt& sp, float wlOffset, bool lambdaSelected) {
+        buildBsdf<NC, 4>(s, leaf, sp, wlOffset, lambdaSelected, &bsdf);
+    }
+    __device__ __forceinline__ bool hasNonDelta() const { return bsdfHasNonDelta(bsdf); }
+    __device__ __forceinline__ Spec<NC> evaluate(const BsdfQuery& q, const V3& d) const { return bsdfEvaluate(bsdf, q, d); }
+    __device__ __forceinline__ float pdf(const BsdfQuery& q, const V3& d) const { return bsdfPdf(bsdf, q, d); }
+    __device__ __forceinline__ Spec<NC> sample(const BsdfQuery& q, float uc, float u0, float u1, BsdfSampleResult* r) const { return bsdfSample(bsdf, q, uc, u0, u1, r); }
+};
+
+// What one hit leaves behind: the continued path (if `alive`) and the shadow ray of its light sample (if `shadow`).
+template <int NC> struct MaterialResult {
+    bool alive, shadow;
+    V3 nOrg, nDir;
+    float nPdf, nImp;
+    uint4 meta;
+    float weight;
+    Spec<NC> alpha;
+    V3 sOrg, sDir;
+    float sTmax;
+    Spec<NC> sContrib;
+    __device__ __forceinline__ void clear() {
+        alive = false; shadow = false;
+        nOrg = V3(0, 0, 0); nDir = V3(0, 0, 1); nPdf = 0.0f; nImp = 0.0f;
+        meta = make_uint4(0, 0, 0, 0); weight = 0.0f; alpha = specConst<NC>(0.0f);
+        sOrg = V3(0, 0, 0); sDir = V3(0, 0, 1); sTmax = 0.0f; sContrib = specConst<NC>(0.0f);
+    }
+};
+
+// path-queue entry i, whose hit has the leaf material `leaf` of class CLASS
+template <int NC, int CLASS>
+__device__ __forceinline__ void materialItem(const DeviceScene& s, const RenderConstants& rc, const PathQueue& in, const HitBuffer& hits,
+                                             uint32_t i, uint32_t leaf, MaterialResult<NC>& o) {
+    const float4 o4 = in.org[i], d4 = in.dir[i];
+    o.meta = in.meta[i];
+    o.weight = in.weight[i];
+    o.alpha = loadAlpha<NC>(in, i) * in.aux[i];          // Russian-roulette scale decided by `surface`
+    const uint2 hid = hits.id[i];
+    const float4 htuv = hits.tuv[i];
+    const V3 org(o4.x, o4.y, o4.z), dir(d4.x, d4.y, d4.z);
+    const uint32_t hero = o.meta.z & 0xFFu;
+    uint32_t flags = (o.meta.z >> 8) & 0xFFu;
+    const uint32_t pathLength = o.meta.z >> 16;
+    const float wlOffset = __uint_as_float(o.meta.w);
+
+    SurfPt sp;
+    float localArea;
+    hitSurfacePoint(s, hid.x, hid.y, htuv.x, htuv.y, htuv.z, org, dir, &sp, &localArea);
+    const V3 dirOut = sp.sf.toLocal(-dir);
+    const V3 gNorm = sp.sf.toLocal(sp.gn);
+    HitBsdf<NC, CLASS> bsdf;
+    bsdf.build(s, leaf, sp, wlOffset, (flags & kFlagLambdaSelected) != 0);
+    BsdfQuery q;
+    q.dir = dirOut; q.gn = gNorm; q.hero = hero; q.flags = DT_All;
+    const Rand4 ra = pathRandom(rc.seed, o.meta.x, o.meta.y, 2 * pathLength);       // light select, light u0, u1, bsdf component
+    const Rand4 rb = pathRandom(rc.seed, o.meta.x, o.meta.y, 2 * pathLength + 1);   // bsdf u0, u1
+
+    // next event estimation
+    if (bsdf.hasNonDelta() && (s.numTopLights > 0 || s.envPresent)) {
+        LightSample ls;
+        sampleLight(s, ra.x, ra.y, ra.z, &ls);
+        float dist2;
+        V3 shadowDir;
+        if (ls.sp.atInfinity) { dist2 = 1.0f; shadowDir = normalize(ls.sp.p); }
+        else { const V3 d = ls.sp.p - sp.p; dist2 = sqLength(d); shadowDir = d / sqrtf(dist2); }
+        const V3 shadowDir_l = ls.sp.sf.toLocal(-shadowDir);
+        const V3 shadowDir_sn = sp.sf.toLocal(shadowDir);
+        const float edf = (ls.isEnv || shadowDir_l.z > 0.0f) ? 1.0f / kPi : 0.0f;
+        if (edf > 0.0f && ls.areaPDF > 0.0f) {
+            const Spec<NC> fs = bsdf.evaluate(q, shadowDir_sn);
+            if (!specIsZero(fs)) {
+                const Spec<NC> M = materialEmittance<NC>(s, ls.material, ls.sp, wlOffset);
+                const float cosLight = absDot(-shadowDir, ls.sp.gn);
+                const float bsdfPDF = bsdf.pdf(q, shadowDir_sn) * cosLight / dist2;
+                float mis = 1.0f;
+                if (!isinf(ls.areaPDF)) mis = (ls.lightPDF * ls.lightPDF) / (ls.lightPDF * ls.lightPDF + bsdfPDF * bsdfPDF);
+                const float G = absDot(shadowDir_sn, gNorm) * cosLight / dist2;
+                const float kk = edf * (G * mis / ls.lightPDF) * o.weight;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) o.sContrib.v[c] = o.alpha.v[c] * M.v[c] * fs.v[c] * kk;
+                // Scene::testVisibility
+                o.sOrg = sp.p;
+                if (ls.sp.atInfinity) { o.sDir = shadowDir; o.sTmax = 3.402823466e+38f; }
+                else { const float dist = length(ls.sp.p - sp.p); o.sDir = (ls.sp.p - sp.p) / dist; o.sTmax = dist * (1.0f - 0.0001f); }
+                o.shadow = true;
+            }
+        }
+    }
+
+    // sample the BSDF for the next direction
+    BsdfSampleResult res;
+    const Spec<NC> fs = bsdf.sample(q, ra.w, rb.x, rb.y, &res);
+    if (!specIsZero(fs) && res.pdf != 0.0f) {
+        float dirPDF = res.pdf;
+        if (res.type & DT_Dispersive) { dirPDF /= NC; flags |= kFlagLambdaSelected; }
+        const float kk = absDot(res.dir, gNorm) / dirPDF;
+        o.alpha = o.alpha * (fs * kk);
+        o.nOrg = sp.p;
+        o.nDir = sp.sf.fromLocal(res.dir);
+        o.nPdf = dirPDF;
+        flags &= ~(kFlagCameraRay | kFlagPrevDelta);
+        if (dtIsDelta(res.type)) flags |= kFlagPrevDelta;
+        o.meta.z = hero | (flags << 8) | (pathLength << 16);
+        o.nImp = specImportance(o.alpha, hero);
+        o.alive = true;
+    }
+}
+
+// the continued path goes to position npos of the next path queue, the shadow ray to position spos of the shadow queue
+template <int NC>
+__device__ __forceinline__ void materialWrite(const PathQueue& out, const ShadowQueue& sq, uint32_t npos, uint32_t spos, const MaterialResult<NC>& o) {
+    if (o.shadow) {
+        sq.org[spos] = make_float4(o.sOrg.x, o.sOrg.y, o.sOrg.z, 0.0001f);
+        sq.dir[spos] = make_float4(o.sDir.x, o.sDir.y, o.sDir.z, o.sTmax);
+        const bool inPlace = ((o.meta.z >> 8) & kFlagStrataInPlace) != 0;
+        sq.pixelWl[spos] = make_uint2(o.meta.x | (inPlace ? 0x80000000u : 0u), o.meta.w);
+        if (NC == 3) sq.contrib[spos] = make_float4(o.sContrib.v[0], o.sContrib.v[1], o.sContrib.v[2], 0.0f);
+        else {
+#pragma unroll
+            for (int c = 0; c < NC / 4; ++c)
+                sq.contrib[(size_t)c * sq.capacity + spos] =
+                    make_float4(o.sContrib.v[4 * c], o.sContrib.v[(4 * c + 1) % NC], o.sContrib.v[(4 * c + 2) % NC], o.sContrib.v[(4 * c + 3) % NC]);
+        }
+    }
+    if (o.alive) {
+        out.org[npos] = make_float4(o.nOrg.x, o.nOrg.y, o.nOrg.z, 0.0001f);      // Ray::Epsilon
+        out.dir[npos] = make_float4(o.nDir.x, o.nDir.y, o.nDir.z, o.nPdf);
+        out.meta[npos] = o.meta;
+        out.weight[npos] = o.weight;
+        out.aux[npos] = o.nImp;
+        storeAlpha<NC>(out, npos, o.alpha);
+    }
+}
+
+template <int NC, int CLASS>
+__device__ __forceinline__ void materialStage(const DeviceScene& s, const RenderConstants& rc, const PathQueue& in, const HitBuffer& hits,
+                                              const ClassQueue& cq, const PathQueue& out, const ShadowQueue& sq, WavefrontCounters* counters, uint32_t n) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint2* __restrict__ entries = cq.entries + (size_t)CLASS * cq.capacity;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const uint32_t k = base + lane;
+        MaterialResult<NC> o;
+        o.clear();
+        if (k < n) {
+            const uint2 e = entries[k];
+            materialItem<NC, CLASS>(s, rc, in, hits, e.x, e.y, o);
+        }
+        const uint32_t spos = warpAppend(o.shadow, &counters->numShadow);
+        const uint32_t npos = warpAppend(o.alive, &counters->numNext);
+        materialWrite<NC>(out, sq, npos, spos, o);
+    }
+}
+
+}  // namespace slrgpu

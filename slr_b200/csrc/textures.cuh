@@ -76,7 +76,7 @@ struct VoronoiCell {
     uint32_t hashOfClosest, closestFPIdx;
 };
 
-__device__ __noinline__ VoronoiCell voronoiClosest(const V3& evalp) {
+static __device__ __noinline__ VoronoiCell voronoiClosest(const V3& evalp) {
     int32_t ie[3] = {(int32_t)floorf(evalp.x), (int32_t)floorf(evalp.y), (int32_t)floorf(evalp.z)};
     const int32_t rbx = -1 + (int32_t)roundf(evalp.x - ie[0]);
     const int32_t rby = -1 + (int32_t)roundf(evalp.y - ie[1]);
@@ -130,7 +130,7 @@ __device__ __forceinline__ void imageTexel(const SlrGpuImage& img, const V3& tc,
 __device__ __forceinline__ float halfBitsToFloat(uint16_t h) { return __half2float(__ushort_as_half(h)); }
 
 template <int NC>
-__device__ __noinline__ Spec<NC> imageSpectrum(const DeviceScene& s, const SlrGpuTexture& t, const SurfPt& sp, float wlOffset) {
+static __device__ __noinline__ Spec<NC> imageSpectrum(const DeviceScene& s, const SlrGpuTexture& t, const SurfPt& sp, float wlOffset) {
     const SlrGpuImage img = s.images[t.i0];
     uint32_t px, py;
     imageTexel(img, mapTexture(t, sp), &px, &py);
@@ -169,7 +169,7 @@ __device__ __noinline__ Spec<NC> imageSpectrum(const DeviceScene& s, const SlrGp
 
 // ---- dispatch ----------------------------------------------------------------------------------
 template <int NC>
-__device__ __noinline__ Spec<NC> evalSpectrumTexture(const DeviceScene& s, uint32_t texId, const SurfPt& sp, float wlOffset) {
+static __device__ __noinline__ Spec<NC> evalSpectrumTexture(const DeviceScene& s, uint32_t texId, const SurfPt& sp, float wlOffset) {
     const SlrGpuTexture t = s.textures[texId];
     switch (t.kind) {
     case SLRGPU_TEX_CONSTANT_SPECTRUM: return evalInputSpectrum<NC>(s, t.i0, wlOffset);
@@ -188,7 +188,7 @@ __device__ __noinline__ Spec<NC> evalSpectrumTexture(const DeviceScene& s, uint3
     }
 }
 
-__device__ __noinline__ float evalFloatTexture(const DeviceScene& s, uint32_t texId, const SurfPt& sp) {
+static __device__ __noinline__ float evalFloatTexture(const DeviceScene& s, uint32_t texId, const SurfPt& sp) {
     const SlrGpuTexture t = s.textures[texId];
     switch (t.kind) {
     case SLRGPU_TEX_CONSTANT_FLOAT: return t.f0;
@@ -214,7 +214,7 @@ __device__ __noinline__ float evalFloatTexture(const DeviceScene& s, uint32_t te
     }
 }
 
-__device__ __noinline__ V3 evalNormalTexture(const DeviceScene& s, uint32_t texId, const SurfPt& sp) {
+static __device__ __noinline__ V3 evalNormalTexture(const DeviceScene& s, uint32_t texId, const SurfPt& sp) {
     const SlrGpuTexture t = s.textures[texId];
     switch (t.kind) {
     case SLRGPU_TEX_CHECKER_NORMAL: return checkerNormal(t, sp);

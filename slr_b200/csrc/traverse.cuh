@@ -8,8 +8,9 @@
 //
 // PARITY CONTRACT: hit primitive/instance ids must equal the reference's bit for bit, including
 // which primitive wins when two report the same distance. That pins (1) the arithmetic: plain IEEE
-// fp32, no FMA contraction (this header must be compiled with -fmad=false), division as 1.0f/x then
-// multiply; (2) the visiting order: children ordered by the sign of the ray direction along the
+// fp32, no FMA contraction -- every operation below is an explicit round-to-nearest intrinsic (__fmul_rn,
+// __fadd_rn, __fsub_rn, __fdiv_rn are never fused), so the header gives the same bits in any translation
+// unit whatever its -fmad setting; division as 1.0f/x then multiply; (2) the visiting order: children ordered by the sign of the ray direction along the
 // node's three split axes, inner children pushed in reverse, leaf children tested immediately in
 // order, `t > tmax` rejects so a later primitive at an equal distance replaces an earlier one.
 //
@@ -41,36 +42,11 @@ struct TraversalCounters {
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
-// 4-lane slab test; returns the 4-bit mask of lanes whose [tNear, tFar] is non-empty.
+// 4-lane slab test; returns the 4-bit mask of lanes whose [tNear, tFar] is non-empty. The near / far planes
+// are already selected by the caller (the selection depends only on the sign of the ray direction, so the
+// walk fetches lo or hi per axis by ADDRESS instead of fetching both and selecting per lane).
 // fmaxf/fminf return the non-NaN operand, which coincides with _mm_max_ps/_mm_min_ps here because a
 // NaN can only appear in the freshly computed first operand (0 * inf), never in the running bound.
-__device__ __forceinline__ uint32_t slab4(const float4 lox, const float4 loy, const float4 loz,
-                                          const float4 hix, const float4 hiy, const float4 hiz,
-                                          const Ray& r, float ix, float iy, float iz) {
-    const bool px = ix > 0.0f, py = iy > 0.0f, pz = iz > 0.0f;
-    const float4 nx = px ? lox : hix, fx = px ? hix : lox;
-    const float4 ny = py ? loy : hiy, fy = py ? hiy : loy;
-    const float4 nz = pz ? loz : hiz, fz = pz ? hiz : loz;
-    uint32_t mask = 0;
-#define SLAB_LANE(L, bit)                                                   \
-    {                                                                       \
-        float tn = r.tmin, tf = r.tmax;                                     \
-        tn = fmaxf((nx.L - r.ox) * ix, tn);                                 \
-        tn = fmaxf((ny.L - r.oy) * iy, tn);                                 \
-        tn = fmaxf((nz.L - r.oz) * iz, tn);                                 \
-        tf = fminf((fx.L - r.ox) * ix, tf);                                 \
-        tf = fminf((fy.L - r.oy) * iy, tf);                                 \
-        tf = fminf((fz.L - r.oz) * iz, tf);                                 \
-        if (tn <= tf) mask |= bit;                                          \
-    }
-    SLAB_LANE(x, 1u) SLAB_LANE(y, 2u) SLAB_LANE(z, 4u) SLAB_LANE(w, 8u)
-#undef SLAB_LANE
-    return mask;
-}
-
-// The same test with the near / far planes already selected by the caller (the selection depends only on the
-// sign of the ray direction, so the walk fetches lo or hi per axis by ADDRESS instead of fetching both and
-// selecting per lane): identical operands, identical operations.
 __device__ __forceinline__ uint32_t slab4NearFar(const float4 nx, const float4 ny, const float4 nz,
                                                  const float4 fx, const float4 fy, const float4 fz,
                                                  const Ray& r, float ix, float iy, float iz) {
@@ -78,17 +54,23 @@ __device__ __forceinline__ uint32_t slab4NearFar(const float4 nx, const float4 n
 #define SLAB_LANE(L, bit)                                                   \
     {                                                                       \
         float tn = r.tmin, tf = r.tmax;                                     \
-        tn = fmaxf((nx.L - r.ox) * ix, tn);                                 \
-        tn = fmaxf((ny.L - r.oy) * iy, tn);                                 \
-        tn = fmaxf((nz.L - r.oz) * iz, tn);                                 \
-        tf = fminf((fx.L - r.ox) * ix, tf);                                 \
-        tf = fminf((fy.L - r.oy) * iy, tf);                                 \
-        tf = fminf((fz.L - r.oz) * iz, tf);                                 \
+        tn = fmaxf(__fmul_rn(__fsub_rn(nx.L, r.ox), ix), tn);                                 \
+        tn = fmaxf(__fmul_rn(__fsub_rn(ny.L, r.oy), iy), tn);                                 \
+        tn = fmaxf(__fmul_rn(__fsub_rn(nz.L, r.oz), iz), tn);                                 \
+        tf = fminf(__fmul_rn(__fsub_rn(fx.L, r.ox), ix), tf);                                 \
+        tf = fminf(__fmul_rn(__fsub_rn(fy.L, r.oy), iy), tf);                                 \
+        tf = fminf(__fmul_rn(__fsub_rn(fz.L, r.oz), iz), tf);                                 \
         if (tn <= tf) mask |= bit;                                          \
     }
     SLAB_LANE(x, 1u) SLAB_LANE(y, 2u) SLAB_LANE(z, 4u) SLAB_LANE(w, 8u)
 #undef SLAB_LANE
     return mask;
+}
+
+// a*b - c*d and a*b + c*d + e*f, left to right, every product and sum rounded on its own
+__device__ __forceinline__ float cross2(float a, float b, float c, float d) { return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d)); }
+__device__ __forceinline__ float dot3(float a, float b, float c, float d, float e, float f) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(a, b), __fmul_rn(c, d)), __fmul_rn(e, f));
 }
 
 // Moller-Trumbore, two-sided, exactly the reference's sequence of operations and comparisons
@@ -97,43 +79,44 @@ __device__ __forceinline__ bool triangleTest(const float4 a, const float4 b, con
                                              float* tOut, float* b0Out, float* b1Out) {
     const float e1x = b.x, e1y = b.y, e1z = b.z;
     const float e2x = c.x, e2y = c.y, e2z = c.z;
-    const float px = r.dy * e2z - r.dz * e2y;
-    const float py = r.dz * e2x - r.dx * e2z;
-    const float pz = r.dx * e2y - r.dy * e2x;
-    const float det = e1x * px + e1y * py + e1z * pz;
+    const float px = cross2(r.dy, e2z, r.dz, e2y);
+    const float py = cross2(r.dz, e2x, r.dx, e2z);
+    const float pz = cross2(r.dx, e2y, r.dy, e2x);
+    const float det = dot3(e1x, px, e1y, py, e1z, pz);
     if (det == 0.0f) return false;
-    const float invDet = 1.0f / det;
-    const float dx = r.ox - a.x, dy = r.oy - a.y, dz = r.oz - a.z;
-    const float b1 = (dx * px + dy * py + dz * pz) * invDet;
+    const float invDet = __frcp_rn(det);
+    const float dx = __fsub_rn(r.ox, a.x), dy = __fsub_rn(r.oy, a.y), dz = __fsub_rn(r.oz, a.z);
+    const float b1 = __fmul_rn(dot3(dx, px, dy, py, dz, pz), invDet);
     if (b1 < 0.0f || b1 > 1.0f) return false;
-    const float qx = dy * e1z - dz * e1y;
-    const float qy = dz * e1x - dx * e1z;
-    const float qz = dx * e1y - dy * e1x;
-    const float b2 = (r.dx * qx + r.dy * qy + r.dz * qz) * invDet;
-    if (b2 < 0.0f || b1 + b2 > 1.0f) return false;
-    const float tt = (e2x * qx + e2y * qy + e2z * qz) * invDet;
+    const float qx = cross2(dy, e1z, dz, e1y);
+    const float qy = cross2(dz, e1x, dx, e1z);
+    const float qz = cross2(dx, e1y, dy, e1x);
+    const float b2 = __fmul_rn(dot3(r.dx, qx, r.dy, qy, r.dz, qz), invDet);
+    if (b2 < 0.0f || __fadd_rn(b1, b2) > 1.0f) return false;
+    const float tt = __fmul_rn(dot3(e2x, qx, e2y, qy, e2z, qz), invDet);
     if (tt < r.tmin || tt > r.tmax) return false;
     *tOut = tt;
-    *b0Out = 1.0f - b1 - b2;
+    *b0Out = __fsub_rn(__fsub_rn(1.0f, b1), b2);
     *b1Out = b1;
     return true;
 }
 
-// Matrix4x4 * Point3 with the reference's homogeneous divide rule (Matrix4x4.h:75-81); column-major m.
+// Matrix4x4 * Point3 with the reference's homogeneous divide rule (Matrix4x4.h:75-81); column-major m
+// (the reference's `m[12] * 1.0f` is m[12] bit for bit).
 __device__ __forceinline__ void mulPoint(const float* __restrict__ m, float x, float y, float z,
                                          float* ox, float* oy, float* oz) {
-    float tx = m[0] * x + m[4] * y + m[8] * z + m[12] * 1.0f;
-    float ty = m[1] * x + m[5] * y + m[9] * z + m[13] * 1.0f;
-    float tz = m[2] * x + m[6] * y + m[10] * z + m[14] * 1.0f;
-    float tw = m[3] * x + m[7] * y + m[11] * z + m[15] * 1.0f;
-    if (tw != 1.0f) { float rcp = 1.0f / tw; tx *= rcp; ty *= rcp; tz *= rcp; }
+    float tx = __fadd_rn(dot3(m[0], x, m[4], y, m[8], z), m[12]);
+    float ty = __fadd_rn(dot3(m[1], x, m[5], y, m[9], z), m[13]);
+    float tz = __fadd_rn(dot3(m[2], x, m[6], y, m[10], z), m[14]);
+    float tw = __fadd_rn(dot3(m[3], x, m[7], y, m[11], z), m[15]);
+    if (tw != 1.0f) { float rcp = __frcp_rn(tw); tx = __fmul_rn(tx, rcp); ty = __fmul_rn(ty, rcp); tz = __fmul_rn(tz, rcp); }
     *ox = tx; *oy = ty; *oz = tz;
 }
 __device__ __forceinline__ void mulVector(const float* __restrict__ m, float x, float y, float z,
                                           float* ox, float* oy, float* oz) {
-    *ox = m[0] * x + m[4] * y + m[8] * z;
-    *oy = m[1] * x + m[5] * y + m[9] * z;
-    *oz = m[2] * x + m[6] * y + m[10] * z;
+    *ox = dot3(m[0], x, m[4], y, m[8], z);
+    *oy = dot3(m[1], x, m[5], y, m[9], z);
+    *oz = dot3(m[2], x, m[6], y, m[10], z);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -215,7 +198,7 @@ struct InstanceWalkState {
 // pos bits 0-2: direction component >= 0 (child ordering, QBVH.h:309-312); bits 8-10: invDir > 0 per axis
 // (which plane is the near one, QBVH.h:68-73) -- the two differ for a component of -0.0
 __device__ __forceinline__ void walkSetRay(WalkState& w) {
-    w.ix = 1.0f / w.r.dx; w.iy = 1.0f / w.r.dy; w.iz = 1.0f / w.r.dz;
+    w.ix = __frcp_rn(w.r.dx); w.iy = __frcp_rn(w.r.dy); w.iz = __frcp_rn(w.r.dz);
     w.pos = (w.r.dx >= 0.0f ? 1u : 0u) | (w.r.dy >= 0.0f ? 2u : 0u) | (w.r.dz >= 0.0f ? 4u : 0u) |
             (w.ix > 0.0f ? 0x100u : 0u) | (w.iy > 0.0f ? 0x200u : 0u) | (w.iz > 0.0f ? 0x400u : 0u);
 }

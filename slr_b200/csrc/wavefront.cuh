@@ -68,6 +68,7 @@ struct WavefrontCounters {
     uint32_t genPass, genOffset;                  // pass / pixel-order position of the next camera sample
     uint32_t extendCursor, shadowCursor;          // chunk cursors of the warp-cooperative ray kernels (zero at launch)
     unsigned long long classTotal[16];            // hits shaded per material class over the whole call
+    uint32_t tailPaths, tailWaves;                // paths the tail kernel (tail.cu) finished / its longest run of bounces
 };
 
 // One entry of a material-class queue: position in the current path queue + the leaf material id.
@@ -95,6 +96,13 @@ struct RenderConstants {
 int launchExtend(const SlrGpuScene* sc, const PathQueue& q, const HitBuffer& hits, WavefrontCounters* counters, bool count, uint32_t grid, cudaStream_t stream);
 int launchShadow(const SlrGpuScene* sc, const ShadowQueue& q, float* accum, WavefrontCounters* counters, bool count, uint32_t grid, cudaStream_t stream);
 constexpr int kTraceBlock = 128;
+// tail.cu: the persistent kernel that finishes the last <= cap paths of a call once all camera samples are started
+// (a no-op before), followed by the single-thread kernel that closes the loop state; both go after a wave PAIR
+// (the current path queue is q0 again). cap = 0: nothing is launched.
+uint32_t tailCapacity(int numSMs);
+int launchTail(const SlrGpuScene* sc, const RenderConstants& rc, const PathQueue& q0, const PathQueue& q1, const HitBuffer& hits,
+               const ShadowQueue& sq, float* accum, WavefrontCounters* counters, WavefrontCounters* ring, uint32_t ringSize,
+               uint32_t cap, cudaStream_t stream);
 
 // Stratum of wavelength i for a path with stratification offset `wlOffset`: min(uint((lambda_i - 360)
 // / 470 * 16), 15) (SpectrumTypes.h:826-835) in uncontracted fp32 as the x86-64 reference computes it

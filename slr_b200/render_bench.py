@@ -271,7 +271,8 @@ def main(args, rank, world):
                        "scene_bytes": scene_bytes, "host_scene_build_s": round(hs.build_seconds, 3),
                        "l2_policy": "per-step working set (wavefront queues + accumulation buffer, > 500 MB) is larger than L2; "
                                     "the scene itself (QBVH + leaf records) is L2-resident by design",
-                       "stage_ms_profiled_frame": {k: round(v, 3) for k, v in stages.items()} | {"other": round(prof.other_ms, 3), "frame": round(prof.device_ms, 3)}},
+                       "stage_ms_profiled_frame": {k: round(v, 3) for k, v in stages.items()} | {"tailKernel": round(prof.tail_ms, 3), "other": round(prof.other_ms, 3), "frame": round(prof.device_ms, 3)},
+                       "tail_kernel": {"paths": int(prof.tail_paths), "bounces": int(prof.tail_waves)}},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                          "kernel": dom, "peak_source": peak_src, "kernel_share_of_step": share,
                          "algorithmic_bytes_per_launch_set": algo[dom],
