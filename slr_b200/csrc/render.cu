@@ -306,7 +306,7 @@ static void launchShadeStage(const SlrGpuScene* sc, const RenderConstants& rc, c
 
 static uint32_t poolCapacity(const SlrGpuRenderParams* p) {
     const unsigned long long totalSamples = (unsigned long long)p->width * p->height * (p->spp_end - p->spp_begin);
-    uint32_t P = p->pool_size ? p->pool_size : (1u << 23);     // 8 Mi paths in flight (3.5 GB of queues): measured +9 % over 2 Mi on C1
+    uint32_t P = p->pool_size ? p->pool_size : (1u << 24);     // 16 Mi paths in flight (7.4 GB of queues): C1 371 / 419 / 454 / 463 / 480 Mpaths/s at 1 / 2 / 4 / 8 / 16 Mi
     if ((unsigned long long)P > totalSamples) P = (uint32_t)totalSamples;
     P = (P + 127u) & ~127u;
     return P == 0 ? 128u : P;
@@ -392,10 +392,10 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
     // microseconds). Outside profiling two waves (one ping + one pong of the path queues) are captured
     // into a CUDA graph once per call and replayed: one driver call per ~20 kernel launches.
     constexpr int kLag = 2;
-    // the tail kernel (tail.cu) takes over when at most one path per thread of it is left; SLRGPU_TAIL_PATHS overrides
+    // the tail kernel (tail.cu) takes over when only a few paths per thread of it are left; SLRGPU_TAIL_PATHS overrides
     // the limit (0 = no tail kernel: every bounce is a wave) -- a tuning / test knob, the image does not depend on it
     uint32_t tailCap = tailCapacity(numSMs);
-    if (const char* e = getenv("SLRGPU_TAIL_PATHS")) tailCap = std::min((uint32_t)strtoul(e, nullptr, 10), tailCap);
+    if (const char* e = getenv("SLRGPU_TAIL_PATHS")) tailCap = (uint32_t)strtoul(e, nullptr, 10);
     const char* waveLogPath = getenv("SLRGPU_WAVE_LOG");
     ulonglong2* waveLog = waveLogPath ? w.dWaveLog : nullptr;
     auto enqueueTail = [&]() -> int {

@@ -7,11 +7,12 @@
 // waves per frame, the last ~90 of them with a few thousand paths each and 0.25-0.3 ms of launch floors and
 // cold-cache latency per wave, together about 40 % of the frame for well under 1 % of its rays.
 //
-// How: when `generated == total` and at most one path per thread of this kernel is left, every thread takes the
-// path in its queue slot and runs bounce after bounce -- walk (the same walkStep as the extend kernel), the
-// `surface` item, the `material` item of the hit's class, the shadow walk and splat -- reading and writing the
-// path state at its own slot of the two path queues. No queue compaction, no atomics, no grid-wide barrier: a
-// bounce costs the latency of its own loads, the BVH nodes of the spheres stay in L1. The arithmetic is the
+// How: when `generated == total` and only a few paths per thread of this kernel are left, every lane takes a path
+// from the queue the last wave left and runs it bounce after bounce -- walk (the same walkStep as the extend
+// kernel), the `surface` item, the `material` item of the hit's class, the shadow walk and splat -- reading and
+// writing the path state at the path's own entry of the two path queues; a lane whose path ended takes the next
+// entry (one atomic per warp and round). No queue compaction, no grid-wide barrier: a bounce costs the latency of
+// its own loads, the BVH nodes of the spheres stay in L1. The arithmetic is the
 // stages' own (stages.cuh, traverse.cuh: explicit round-to-nearest intrinsics), and a path's random numbers are
 // keyed by (pixel, sample, bounce), so which kernel runs a bounce does not change the path.
 //
@@ -19,10 +20,14 @@
 // (~3 us per pair); tailEndKernel then closes the loop state like endWaveKernel does.
 #include "ray_io.cuh"
 #include "stages.cuh"
+#include <algorithm>
 
 namespace slrgpu {
 
 constexpr int kTailBlock = 256;
+#ifndef SLR_TAIL_PATHS_PER_THREAD
+#define SLR_TAIL_PATHS_PER_THREAD 1u
+#endif
 
 __device__ __forceinline__ bool tailCondition(const WavefrontCounters* c, uint32_t cap) {
     const uint32_t n = c->numPaths;
@@ -63,20 +68,38 @@ tailKernel(const DeviceScene s, const RenderConstants rc, PathQueue q0, PathQueu
            float* __restrict__ accum, WavefrontCounters* counters, uint32_t cap, uint32_t classMask) {
     if (!tailCondition(counters, cap)) return;
     const uint32_t n = counters->numPaths;
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    bool alive = slot < n;
-    if (!__any_sync(0xFFFFFFFFu, alive)) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
 
     uint32_t stack[kStackSize];
-    uint32_t nExtend = 0, nShadow = 0, waves = 0;
+    uint32_t nExtend = 0, nShadow = 0, rounds = 0;
     uint32_t classHits[SC_COUNT];
 #pragma unroll
     for (int c = 0; c < (int)SC_COUNT; ++c) classHits[c] = 0;
     bool overflow = false;
     const TraversalCounters noCount = {0, 0};
-    uint32_t cur = 0;
+    // the lane's path: its entry of the path queue left by the last wave; the state of bounce b sits at that entry of
+    // q0 (b even) or q1 (b odd), its hit and its shadow ray at the same entry of the hit buffer and the shadow queue
+    uint32_t slot = 0, cur = 0;
+    bool alive = false;
+    bool exhausted = false;         // warp-uniform: the queue has no entries left to hand out
 
-    while (__any_sync(0xFFFFFFFFu, alive)) {
+    while (true) {
+        // lanes without a path take the next entries of the queue (one atomic per warp and round)
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !alive);
+        if (idle != 0 && !exhausted) {
+            const uint32_t want = (uint32_t)__popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&counters->tailCursor, want);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (!alive) {
+                const uint32_t i = base + (uint32_t)__popc(idle & lt);
+                if (i < n) { slot = i; cur = 0; alive = true; }
+            }
+            if (base + want >= n) exhausted = true;
+        }
+        if (!__any_sync(0xFFFFFFFFu, alive)) break;
+
         const PathQueue in = cur ? q1 : q0;
         const PathQueue out = cur ? q0 : q1;
         uint32_t cls = SC_NONE, leaf = SLRGPU_INVALID_ID;
@@ -105,17 +128,15 @@ tailKernel(const DeviceScene s, const RenderConstants rc, PathQueue q0, PathQueu
         }
         alive = next;
         cur ^= 1u;
-        ++waves;
+        ++rounds;
     }
 
     // the loop state's totals: one atomic per warp and counter
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t e = warpSum(nExtend), sh = warpSum(nShadow), started = warpSum(slot < n ? 1u : 0u);
+    const uint32_t e = warpSum(nExtend), sh = warpSum(nShadow);
     if (lane == 0) {
         atomicAdd(&counters->extendRays, (unsigned long long)e);
         atomicAdd(&counters->shadowRays, (unsigned long long)sh);
-        atomicAdd(&counters->tailPaths, started);
-        atomicMax(&counters->tailWaves, waves);
+        atomicMax(&counters->tailWaves, rounds);
     }
 #pragma unroll
     for (int c = 0; c < (int)SC_COUNT; ++c) {
@@ -128,19 +149,24 @@ tailKernel(const DeviceScene s, const RenderConstants rc, PathQueue q0, PathQueu
 // after the tail: nothing is in flight any more (single thread); rewrites the snapshot endWaveKernel left for the host
 __global__ void tailEndKernel(WavefrontCounters* counters, WavefrontCounters* ring, uint32_t ringSize, uint32_t cap) {
     if (!tailCondition(counters, cap)) return;
+    counters->tailPaths = counters->numPaths;
     counters->numPaths = 0;
     counters->done = 1u;
     ring[(counters->waves - 1u) % ringSize] = *counters;
     __threadfence_system();
 }
 
-uint32_t tailCapacity(int numSMs) { return (uint32_t)numSMs * (uint32_t)kTailBlock; }
+// default limit: one path per thread of the kernel. Sweep (profiles/r01_tail_kernel.md): C1 480 / 489 / 478 / 441 Mpaths/s at
+// 1 / 2 / 4 / 16 paths per thread, C2 (32 spp) 386 at 1 against 366 at 8: a round of the tail costs ~45 us whatever the load
+uint32_t tailCapacity(int numSMs) { return (uint32_t)numSMs * (uint32_t)kTailBlock * SLR_TAIL_PATHS_PER_THREAD; }
 
 int launchTail(const SlrGpuScene* sc, const RenderConstants& rc, const PathQueue& q0, const PathQueue& q1, const HitBuffer& hits,
                const ShadowQueue& sq, float* accum, WavefrontCounters* counters, WavefrontCounters* ring, uint32_t ringSize,
                uint32_t cap, cudaStream_t stream) {
     if (cap == 0) return SLRGPU_OK;
-    const uint32_t grid = (cap + kTailBlock - 1) / kTailBlock;
+    int numSMs = 148;
+    cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, sc->device);
+    const uint32_t grid = std::min((uint32_t)numSMs, (cap + kTailBlock - 1) / kTailBlock);      // one resident block per SM
     if (sc->channels == 3) tailKernel<3><<<grid, kTailBlock, 0, stream>>>(sc->dev, rc, q0, q1, hits, sq, accum, counters, cap, sc->classMask);
     else tailKernel<16><<<grid, kTailBlock, 0, stream>>>(sc->dev, rc, q0, q1, hits, sq, accum, counters, cap, sc->classMask);
     tailEndKernel<<<1, 1, 0, stream>>>(counters, ring, ringSize, cap);

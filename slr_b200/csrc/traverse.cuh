@@ -132,7 +132,10 @@ __device__ __forceinline__ void mulVector(const float* __restrict__ m, float x, 
 // is entered by pushing a return marker (see walkStep), as the reference's recursion does.
 // (A "while-while" split into separate node and leaf phases was measured too -- round 1, profiles/ --
 // and was slower on both benchmarks: rays here are short, the extra state and ballots cost more than
-// the leaf-phase coherence returns.)
+// the leaf-phase coherence returns. So was a warp-cooperative leaf phase -- the records waiting in all
+// lanes numbered by a prefix sum, one record per lane, owners' rays fetched by shuffles, hits taken in
+// record order from a shared-memory window: bit-exact, but 2695 -> 2289 Mrays/s on the intersect bench and
+// extend 10.9 -> 12.6 ms per C1 frame, profiles/r01_rejected_experiments.md.)
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kMaxChunk = 256;
 #ifndef SLR_WALK_STEPS_PER_ROUND

@@ -68,7 +68,8 @@ struct WavefrontCounters {
     uint32_t genPass, genOffset;                  // pass / pixel-order position of the next camera sample
     uint32_t extendCursor, shadowCursor;          // chunk cursors of the warp-cooperative ray kernels (zero at launch)
     unsigned long long classTotal[16];            // hits shaded per material class over the whole call
-    uint32_t tailPaths, tailWaves;                // paths the tail kernel (tail.cu) finished / its longest run of bounces
+    uint32_t tailPaths, tailWaves;                // paths the tail kernel (tail.cu) finished / bounce rounds of its longest-running warp
+    uint32_t tailCursor, tailPad;                 // next queue entry the tail kernel hands out
 };
 
 // One entry of a material-class queue: position in the current path queue + the leaf material id.

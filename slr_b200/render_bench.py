@@ -266,7 +266,7 @@ def main(args, rank, world):
                        "mrays_per_s": rays / (ms * 1e-3) / 1e6, "waves_per_frame": int(prof.waves),
                        "extend_nodes_per_ray": round(prof.extend_nodes / max(n_ext, 1), 3), "extend_leaf_records_per_ray": round(prof.extend_leaf_records / max(n_ext, 1), 3),
                        "shadow_nodes_per_ray": round(prof.shadow_nodes / max(n_sh, 1), 3), "shadow_leaf_records_per_ray": round(prof.shadow_leaf_records / max(n_sh, 1), 3),
-                       "class_hits_per_frame": [int(x) for x in prof.class_hits], "extend_rays_per_frame": int(n_ext), "shadow_rays_per_frame": int(n_sh), "pool": int(getattr(args, "pool", 0) or (1 << 23)),
+                       "class_hits_per_frame": [int(x) for x in prof.class_hits], "extend_rays_per_frame": int(n_ext), "shadow_rays_per_frame": int(n_sh), "pool": int(getattr(args, "pool", 0) or (1 << 24)),
                        "triangles": int(hs.desc.num_triangles), "qbvh_nodes": int(hs.desc.num_bvh_nodes),
                        "scene_bytes": scene_bytes, "host_scene_build_s": round(hs.build_seconds, 3),
                        "l2_policy": "per-step working set (wavefront queues + accumulation buffer, > 500 MB) is larger than L2; "
