@@ -76,15 +76,6 @@ template <int NC> __device__ __forceinline__ Spec<NC> operator*(float s, const S
 // wavelength i of a path with stratification offset `off`
 __device__ __forceinline__ float wavelengthOf(int i, float off) { return kWlLow + (kWlHigh - kWlLow) * (i + off) / 16; }
 
-__device__ __forceinline__ float evalRegular(const float* __restrict__ values, uint32_t n, float lo, float hi, float wl) {
-    const float binF = (wl - lo) / (hi - lo) * (n - 1);
-    if (binF <= 0.0f) return __ldg(values);
-    if (binF >= n - 1) return __ldg(values + n - 1);
-    const int bin = (int)binF;
-    const float t = binF - bin;
-    return (1 - t) * __ldg(values + bin) + t * __ldg(values + bin + 1);
-}
-
 // lower_bound over [base, n), then the reference's clamping; *base carries the running search start
 __device__ __forceinline__ float evalIrregular(const float* __restrict__ lambdas, const float* __restrict__ values, uint32_t n,
                                                float wl, uint32_t* base) {
@@ -153,19 +144,25 @@ static __device__ __noinline__ UpsampleWeights upsampleWeights(const DeviceScene
     return r;
 }
 
-__device__ __forceinline__ float evalUpsampled(const DeviceScene& s, const UpsampleWeights& w, float scale, float wl) {
-    if (w.n == 0) return 0.0f;
-    const float p = (wl - kWlLow) / (kWlHigh - kWlLow);
-    const float sBinF = p * (kUpNumWl - 1);
-    const uint32_t sBin = (uint32_t)sBinF;
-    const uint32_t sNext = (sBin + 1 < (uint32_t)kUpNumWl) ? (sBin + 1) : (kUpNumWl - 1);
-    const float t = sBinF - sBin;
-    float ret = 0.0f;
-    for (int j = 0; j < w.n; ++j) {
-        const float* sp = s.upsamplePoints + w.idx[j] * kUpPointStride + 4;
-        ret += w.w[j] * (__ldg(sp + sBin) * (1 - t) + __ldg(sp + sNext) * t);
+// UpsampledContinuousSpectrum::evaluate at the path's 16 wavelengths. The fractional bin (lambda_i - 360) / 470 * 94
+// is (i + offset) * 94 / 16: one multiply per wavelength instead of the subtraction / division / multiplication chain.
+template <int NC>
+__device__ __forceinline__ void evalUpsampledAll(const DeviceScene& s, const UpsampleWeights& w, float scale, float wlOffset, Spec<NC>* out) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) out->v[i] = 0.0f;
+    if (w.n == 0) return;
+    const float* sp[4];
+    for (int j = 0; j < 4; ++j) sp[j] = s.upsamplePoints + w.idx[j < w.n ? j : 0] * kUpPointStride + 4;
+#pragma unroll 4
+    for (int i = 0; i < NC; ++i) {
+        const float sBinF = ((float)i + wlOffset) * ((float)(kUpNumWl - 1) / 16.0f);
+        const uint32_t sBin = min((uint32_t)sBinF, (uint32_t)(kUpNumWl - 1));
+        const uint32_t sNext = min(sBin + 1u, (uint32_t)(kUpNumWl - 1));
+        const float t = sBinF - (float)sBin;
+        float ret = 0.0f;
+        for (int j = 0; j < w.n; ++j) ret += w.w[j] * (__ldg(sp[j] + sBin) * (1 - t) + __ldg(sp[j] + sNext) * t);
+        out->v[i] = ret * scale;
     }
-    return ret * scale;
 }
 
 // compiled irregular spectrum (scene.cu compileSpectra): the bin table gives the interval the reference's
@@ -196,9 +193,29 @@ static __device__ __noinline__ Spec<NC> evalInputSpectrum(const DeviceScene& s, 
         return out;
     }
     if (sp.kind == SLRGPU_SPECTRUM_REGULAR) {
+        // RegularContinuousSpectrum::evaluate at the path's 16 equally spaced wavelengths: the fractional bin
+        // (lambda_i - lo) / (hi - lo) * (n - 1) is linear in i, so one FMA per wavelength replaces its subtraction,
+        // IEEE division and multiplication (ncu on the Lambert kernel: 21 % of its stall samples sat on those three
+        // lines). The two end clamps become index / weight clamps of the same piecewise-linear function.
         const float* vals = s.spectrumData + sp.data_offset;
+        const int last = (int)sp.num_samples - 1;
+        if (last < 1) {
+            const float v = __ldg(vals);
 #pragma unroll
-        for (int i = 0; i < NC; ++i) out.v[i] = evalRegular(vals, sp.num_samples, sp.p0, sp.p1, wavelengthOf(i, wlOffset));
+            for (int i = 0; i < NC; ++i) out.v[i] = v;
+        } else {
+            const float perNm = (float)last / (sp.p1 - sp.p0);
+            const float step = (kWlHigh - kWlLow) / 16 * perNm;
+            const float first = (kWlLow - sp.p0 + (kWlHigh - kWlLow) / 16 * wlOffset) * perNm;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const float binF = fmaf(step, (float)i, first);
+                const int bin = min(max((int)binF, 0), last - 1);
+                const float t = __saturatef(binF - (float)bin);
+                const float v0 = __ldg(vals + bin), v1 = __ldg(vals + bin + 1);
+                out.v[i] = fmaf(t, v1 - v0, v0);
+            }
+        }
     } else if (sp.kind == SLRGPU_SPECTRUM_IRREGULAR_LUT) {
         const float* lam = s.spectrumData + sp.data_offset;
         const float* vals = lam + sp.num_samples;
@@ -213,8 +230,7 @@ static __device__ __noinline__ Spec<NC> evalInputSpectrum(const DeviceScene& s, 
         for (int i = 0; i < NC; ++i) out.v[i] = evalIrregular(lam, vals, sp.num_samples, wavelengthOf(i, wlOffset), &base);
     } else {
         const UpsampleWeights w = upsampleWeights(s, sp.p0, sp.p1);
-#pragma unroll 1
-        for (int i = 0; i < NC; ++i) out.v[i] = evalUpsampled(s, w, sp.p2, wavelengthOf(i, wlOffset));
+        evalUpsampledAll<NC>(s, w, sp.p2, wlOffset, &out);
     }
     return out;
 }
@@ -224,8 +240,7 @@ template <int NC>
 static __device__ __noinline__ Spec<NC> evalUVS(const DeviceScene& s, float u, float v, float scale, float wlOffset) {
     Spec<NC> out;
     const UpsampleWeights w = upsampleWeights(s, u, v);
-#pragma unroll
-    for (int i = 0; i < NC; ++i) out.v[i] = evalUpsampled(s, w, scale, wavelengthOf(i, wlOffset));
+    evalUpsampledAll<NC>(s, w, scale, wlOffset, &out);
     return out;
 }
 
