@@ -230,11 +230,13 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
         const uint32_t ox = (w.pos & 0x100u) ? 0u : 3u, oy = (w.pos & 0x200u) ? 0u : 3u, oz = (w.pos & 0x400u) ? 0u : 3u;
         const float4 nx = ldg4(n + ox), ny = ldg4(n + 1 + oy), nz = ldg4(n + 2 + oz);
         const float4 fx = ldg4(n + 3 - ox), fy = ldg4(n + 4 - oy), fz = ldg4(n + 5 - oz);
+        // the child words and split axes are fetched with the planes, not after the box test: one memory latency per
+        // step instead of two (ncu: the first use of `kids` was the hottest line of the extend kernel)
+        const uint4 kids = __ldg(reinterpret_cast<const uint4*>(n + 6));
+        const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(n + 7));
         if (COUNT) ++cnt.nodes;
         const uint32_t mask = slab4NearFar(nx, ny, nz, fx, fy, fz, r, w.ix, w.iy, w.iz);
         if (mask != 0) {
-            const uint4 kids = __ldg(reinterpret_cast<const uint4*>(n + 6));
-            const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(n + 7));
             const uint32_t T = (w.pos >> (axes & 0xFF)) & 1u;
             const uint32_t L = (w.pos >> ((axes >> 8) & 0xFF)) & 1u;
             const uint32_t R = (w.pos >> ((axes >> 16) & 0xFF)) & 1u;
@@ -279,7 +281,7 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
     }
     while (leaves.count != 0) {
         const float4* rec = s.leaves + (size_t)leaves.first * 3;
-        const float4 a = ldg4(rec);
+        const float4 a = ldg4(rec), b = ldg4(rec + 1), cc = ldg4(rec + 2);      // all 48 B at once (an instance record has them too)
         ++leaves.first;
         if (--leaves.count == 0) leaves.next();
         const uint32_t id = __float_as_uint(a.w);
@@ -305,7 +307,6 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
             }
             continue;
         }
-        const float4 b = ldg4(rec + 1), cc = ldg4(rec + 2);
         float t, b0, b1;
         if (triangleTest(a, b, cc, r, &t, &b0, &b1)) {
             r.tmax = t;
