@@ -211,10 +211,10 @@ def run_intersect_gpu(args, rank, world, dist):
     return {"ms_total": ms, "units": n * args.steps, "algo_bytes_per_launch": algo_bytes, "launches": args.steps,
             "nodes_per_ray": tot_nodes / n, "tris_per_ray": tot_tris / n, "hit_rate": hit_rate,
             "clocks": clocks.summary(), "e2e_units_per_s": n / e2e_s, "h2d": 32 * n, "d2h": 12 * n,
-            "scene_bytes": gs.device_bytes, "host_scene": hs, "rays": rays, "build_s": hs.build_seconds}
+            "scene_bytes": gs.device_bytes, "host_scene": hs, "rays": rays, "build_s": hs.build_seconds, "gpu_scene": gs}
 
 
-def cpu_baseline_intersect(args, sample_rays, kind_pref="reference"):
+def cpu_baseline_intersect(args, sample_rays, kind_pref="reference", gpu_scene=None):
     """The reference's own QBVH::intersect on the box's host cores (oracle/_ref/ref_intersect) on a
     bounded sample of the same workload; falls back to the scalar restatement (1 core)."""
     import oracle_util as ou
@@ -222,10 +222,19 @@ def cpu_baseline_intersect(args, sample_rays, kind_pref="reference"):
     pos, idx = synth.heightfield(args.grid)
     rays = synth.random_rays(sample_rays, pos.min(0), pos.max(0), seed=12345)
     if kind_pref == "reference" and ou.have_ref():
-        _, _, info = ou.run_ref_intersect([(pos, idx)], [(0, 0, None)], rays, want_trees=False)
+        ref_hits, _, info = ou.run_ref_intersect([(pos, idx)], [(0, 0, None)], rays, want_trees=False)
         best = min(info["qbvh_1t_s"], info["qbvh_nt_s"])
         cores = 1 if info["qbvh_1t_s"] <= info["qbvh_nt_s"] else info["threads"]
-        return {"value": sample_rays / best / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference",
+        parity = None
+        if gpu_scene is not None:
+            # the same sample through the CUDA path: hit ids against the reference's own QBVH on this box
+            got = gpu_scene.intersect(rays)
+            hit = ref_hits["prim"] != 0xFFFFFFFF
+            parity = {"rays": int(sample_rays), "hits": int(hit.sum()),
+                      "prim_ids_equal": bool(np.array_equal(got["prim"], ref_hits["prim"])),
+                      "t_bit_equal": bool(np.array_equal(got["t"].view(np.uint32)[hit], ref_hits["t"].view(np.uint32)[hit]))}
+        return {"value": sample_rays / best / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "reference", "parity_vs_gpu": parity,
+                "reference_build_s": round(info.get("sbvh_build_s", 0.0) + info.get("qbvh_build_s", 0.0), 2),
                 "sample": f"{sample_rays} rays of the same batch through QBVH::intersect; best of 1 thread "
                           f"({sample_rays / info['qbvh_1t_s'] / 1e6:.3f}) and {info['threads']} threads "
                           f"({sample_rays / info['qbvh_nt_s'] / 1e6:.3f} Mrays/s)",
@@ -305,7 +314,7 @@ def main():
     peak, peak_src = measured_peaks()
     value = r["units"] * world / (ms * 1e-3) / 1e6
     ach = r["algo_bytes_per_launch"] / (ms * 1e-3 / r["launches"]) / 1e9
-    cpu = cpu_baseline_intersect(args, args.cpu_sample)
+    cpu = cpu_baseline_intersect(args, args.cpu_sample, gpu_scene=r["gpu_scene"])
     line = {"metric": "Mrays/s (closest-hit, incoherent rays)", "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -1,6 +1,9 @@
 #include "bvh.h"
 #include <algorithm>
+#include <atomic>
+#include <future>
 #include <stdexcept>
+#include <thread>
 
 namespace slr {
 
@@ -111,37 +114,88 @@ constexpr uint32_t kSpatialBins = 16;
 constexpr float kTraversalCost = 1.2f;
 constexpr uint32_t kFragmentBudget = 5;
 
+// What the builder produces for one subtree: its nodes in depth-first pre-order (node 0 = the subtree's root, child
+// indices local to the subtree) and its leaf references, leaf by leaf in the same order.
+struct SubTree {
+    std::vector<SBVHNode> nodes;
+    std::vector<uint32_t> refs;
+    uint32_t depth = 0;          // deepest level reached, counted from the whole tree's root
+    uint64_t added = 0;          // fragments the subtree's spatial splits added
+};
+
+// The reference grows ONE fragment array in place (SBVH.h:57-348): an object split partitions its range, a spatial
+// split rewrites the range and shifts everything behind it. What a node decides depends only on its own fragments
+// and their order, never on where the range sits in the array -- so here every node owns its fragments as a vector
+// (same std::partition, same left / right order), which (1) drops the O(N) tail shift per spatial split and (2) makes
+// sibling subtrees independent: above kParallelMin fragments the left child is built by another thread and the two
+// results are spliced in pre-order. The tree is the reference's, node for node (tests/test_oracle_intersect.py).
+constexpr uint32_t kParallelMin = 1u << 15;
+std::atomic<int> g_buildThreads{0};
+
 struct Builder {
     const PrimitiveSet& ps;
-    SBVH& out;
-    std::vector<Fragment> frags;   // grows in place when spatial splits duplicate references
-    uint32_t live = 0;             // number of fragments currently in use
+    const BBox sceneBounds;
+    const int maxThreads;
 
-    Builder(const PrimitiveSet& p, SBVH& o) : ps(p), out(o) {}
+    Builder(const PrimitiveSet& p, const BBox& b)
+        : ps(p), sceneBounds(b), maxThreads((int)std::max(1u, std::thread::hardware_concurrency())) {}
 
     static uint32_t binOf(uint32_t numBins, float v, float lo, float hi) {
         uint32_t b = (uint32_t)(numBins * ((v - lo) / (hi - lo)));
         return std::min(b, numBins - 1);
     }
 
-    // Opens a gap of `count` fragments after position `end` (the fragments of later, not yet
-    // processed subtrees shift right), mirroring the in-place array the reference grows.
-    void shiftTail(uint32_t end, uint32_t count) {
-        if (count == 0) return;
-        if (live + count > frags.size()) frags.resize(std::max<size_t>(live + count, frags.size() * 2));
-        std::copy_backward(frags.begin() + end, frags.begin() + live, frags.begin() + live + count);
+    // children of the node `nodeIdx` of `out`: sequentially into `out` itself, or -- big ranges -- side by side
+    void buildChildren(std::vector<Fragment>&& lefts, std::vector<Fragment>&& rights, uint32_t depth, Axis axis, const BBox& box,
+                       uint32_t nodeIdx, SubTree& out) {
+        uint32_t c0, c1;
+        const bool parallel = lefts.size() + rights.size() >= kParallelMin && g_buildThreads.load(std::memory_order_relaxed) < maxThreads;
+        if (!parallel) {
+            c0 = recurse(std::move(lefts), depth, out);
+            c1 = recurse(std::move(rights), depth, out);
+        } else {
+            SubTree l, r;
+            g_buildThreads.fetch_add(1, std::memory_order_relaxed);
+            auto job = std::async(std::launch::async, [this, &lefts, depth, &l]() {
+                struct Done { ~Done() { g_buildThreads.fetch_sub(1, std::memory_order_relaxed); } } done;
+                recurse(std::move(lefts), depth, l);
+            });
+            try { recurse(std::move(rights), depth, r); } catch (...) { job.wait(); throw; }
+            job.get();
+            c0 = splice(out, l);
+            c1 = splice(out, r);
+        }
+        SBVHNode& nd = out.nodes[nodeIdx];
+        nd.bbox = box; nd.c0 = c0; nd.c1 = c1; nd.axis = axis; nd.firstRef = nd.numRefs = 0;
     }
 
-    // returns node index; *added = number of fragments this subtree added to the array
-    uint32_t recurse(uint32_t start, uint32_t end, uint32_t depth, uint32_t* added) {
-        *added = 0;
+    // appends a finished subtree to `out`; returns the index its root got
+    static uint32_t splice(SubTree& out, SubTree& sub) {
+        const uint32_t nodeBase = (uint32_t)out.nodes.size(), refBase = (uint32_t)out.refs.size();
+        out.nodes.reserve(out.nodes.size() + sub.nodes.size());
+        for (SBVHNode nd : sub.nodes) {
+            if (nd.numRefs > 0) nd.firstRef += refBase;
+            else { nd.c0 += nodeBase; nd.c1 += nodeBase; }
+            out.nodes.push_back(nd);
+        }
+        out.refs.insert(out.refs.end(), sub.refs.begin(), sub.refs.end());
+        out.depth = std::max(out.depth, sub.depth);
+        out.added += sub.added;
+        sub = SubTree();
+        return nodeBase;
+    }
+
+    // builds the subtree over `frags` (consumed) at the end of `out`; returns its root's index in `out`
+    uint32_t recurse(std::vector<Fragment>&& fragsIn, uint32_t depth, SubTree& out) {
+        std::vector<Fragment> frags = std::move(fragsIn);
         const uint32_t nodeIdx = (uint32_t)out.nodes.size();
         out.nodes.emplace_back();
         if (++depth > out.depth) out.depth = depth;
+        const uint32_t count = (uint32_t)frags.size();
 
         BBox box, centroidBox;
         float leafCost = 0.0f;
-        for (uint32_t i = start; i < end; ++i) {
+        for (uint32_t i = 0; i < count; ++i) {
             box.grow(frags[i].bbox);
             centroidBox.grow(frags[i].bbox.centroid());
             leafCost += frags[i].cost;
@@ -151,7 +205,6 @@ struct Builder {
         const float areaParent = box.surfaceArea();
         const float cLo = centroidBox.lo[axisO], cHi = centroidBox.hi[axisO];
         const float bLo = box.lo[axisS], bHi = box.hi[axisS];
-        const uint32_t count = end - start;
 
         auto makeLeaf = [&](uint32_t n) {
             SBVHNode& nd = out.nodes[nodeIdx];
@@ -159,7 +212,7 @@ struct Builder {
             nd.c0 = nd.c1 = 0;
             nd.firstRef = (uint32_t)out.refs.size();
             nd.numRefs = n;
-            for (uint32_t i = start; i < start + n; ++i) out.refs.push_back(frags[i].prim);
+            for (uint32_t i = 0; i < n; ++i) out.refs.push_back(frags[i].prim);
         };
         if (count == 1) { makeLeaf(1); return nodeIdx; }
 
@@ -168,7 +221,7 @@ struct Builder {
         uint32_t planeO = 0;
         float bestO = INFINITY;
         if ((cHi - cLo) > 0) {
-            for (uint32_t i = start; i < end; ++i) {
+            for (uint32_t i = 0; i < count; ++i) {
                 const Fragment& f = frags[i];
                 uint32_t b = binOf(kObjectBins, f.bbox.centerOf(axisO), cLo, cHi);
                 ++objBins[b].n;
@@ -198,8 +251,8 @@ struct Builder {
         uint32_t planeS = 0;
         float bestS = INFINITY;
         const float alpha = 1e-5;
-        if (overlapArea / out.bounds.surfaceArea() > alpha) {
-            for (uint32_t i = start; i < end; ++i) {
+        if (overlapArea / sceneBounds.surfaceArea() > alpha) {
+            for (uint32_t i = 0; i < count; ++i) {
                 const Fragment& f = frags[i];
                 uint32_t bIn = binOf(kSpatialBins, f.bbox.lo[axisS], bLo, bHi);
                 uint32_t bOut = binOf(kSpatialBins, f.bbox.hi[axisS], bLo, bHi);
@@ -228,16 +281,13 @@ struct Builder {
         if (bestO < bestS) {
             // ---- object partition about the chosen centroid plane
             float pivot = cLo + (cHi - cLo) / kObjectBins * (planeO + 1);
-            Fragment* first = frags.data() + start;
-            Fragment* mid = std::partition(first, frags.data() + end,
+            Fragment* first = frags.data();
+            Fragment* mid = std::partition(first, first + count,
                                            [axisO, pivot](const Fragment& f) { return f.bbox.centerOf(axisO) < pivot; });
-            uint32_t split = std::max((uint32_t)(mid - first), 1u) + start;
-            uint32_t addL, addR;
-            uint32_t c0 = recurse(start, split, depth, &addL);
-            uint32_t c1 = recurse(split + addL, end + addL, depth, &addR);
-            SBVHNode& nd = out.nodes[nodeIdx];
-            nd.bbox = box; nd.c0 = c0; nd.c1 = c1; nd.axis = axisO; nd.firstRef = nd.numRefs = 0;
-            *added += addL + addR;
+            const uint32_t split = std::max((uint32_t)(mid - first), 1u);
+            std::vector<Fragment> lefts(frags.begin(), frags.begin() + split), rights(frags.begin() + split, frags.end());
+            std::vector<Fragment>().swap(frags);
+            buildChildren(std::move(lefts), std::move(rights), depth, axisO, box, nodeIdx, out);
             return nodeIdx;
         }
 
@@ -248,7 +298,7 @@ struct Builder {
         std::vector<Fragment> lefts(maxL), rights(maxR);
         uint32_t nL = 0, nR = 0;
         const float splitPos = (planeS + 1) * binWidth + bLo;
-        for (uint32_t i = start; i < end; ++i) {
+        for (uint32_t i = 0; i < count; ++i) {
             const Fragment& f = frags[i];
             uint32_t bIn = binOf(kSpatialBins, f.bbox.lo[axisS], bLo, bHi);
             uint32_t bOut = binOf(kSpatialBins, f.bbox.hi[axisS], bLo, bHi);
@@ -269,20 +319,11 @@ struct Builder {
                 if (!sr.isValid()) --nR;
             }
         }
-        *added = (nL + nR) - count;
-        shiftTail(end, *added);
-        std::copy(lefts.begin(), lefts.begin() + nL, frags.begin() + start);
-        std::copy(rights.begin(), rights.begin() + nR, frags.begin() + start + nL);
-        live += *added;
-        lefts.clear(); lefts.shrink_to_fit();
-        rights.clear(); rights.shrink_to_fit();
-        uint32_t split = start + nL;
-        uint32_t addL, addR;
-        uint32_t c0 = recurse(start, split, depth, &addL);
-        uint32_t c1 = recurse(split + addL, end + *added + addL, depth, &addR);
-        SBVHNode& nd = out.nodes[nodeIdx];
-        nd.bbox = box; nd.c0 = c0; nd.c1 = c1; nd.axis = axisS; nd.firstRef = nd.numRefs = 0;
-        *added += addL + addR;
+        out.added += (uint64_t)(nL + nR) - count;
+        lefts.resize(nL);
+        rights.resize(nR);
+        std::vector<Fragment>().swap(frags);
+        buildChildren(std::move(lefts), std::move(rights), depth, axisS, box, nodeIdx, out);
         return nodeIdx;
     }
 };
@@ -292,21 +333,23 @@ struct Builder {
 void SBVH::build(const PrimitiveSet& ps) {
     nodes.clear(); refs.clear(); bounds = BBox(); depth = 0;
     if (ps.prims.empty()) throw std::runtime_error("SBVH::build: empty primitive set");
-    Builder b(ps, *this);
     const uint32_t n = (uint32_t)ps.prims.size();
-    b.frags.resize((size_t)n + n / 4 + 16);
+    std::vector<Fragment> frags(n);
     for (uint32_t i = 0; i < n; ++i) {
         bounds.grow(ps.prims[i].bounds);
-        b.frags[i].prim = i;
-        b.frags[i].bbox = ps.prims[i].bounds;
-        b.frags[i].cost = ps.prims[i].cost;
+        frags[i].prim = i;
+        frags[i].bbox = ps.prims[i].bounds;
+        frags[i].cost = ps.prims[i].cost;
     }
-    b.live = n;
-    uint32_t added = 0;
-    b.recurse(0, n, 0, &added);
-    if ((uint64_t)n + added > (uint64_t)kFragmentBudget * n)
+    Builder b(ps, bounds);
+    SubTree tree;
+    b.recurse(std::move(frags), 0, tree);
+    if ((uint64_t)n + tree.added > (uint64_t)kFragmentBudget * n)
         throw std::runtime_error("SBVH::build: spatial splits exceeded the 5x fragment budget of the reference (SBVH.h:385)");
-    numFragmentsAdded = added;
+    nodes = std::move(tree.nodes);
+    refs = std::move(tree.refs);
+    depth = tree.depth;
+    numFragmentsAdded = (uint32_t)tree.added;
 
     // SAH cost (traversal 1.2, leaf overhead 0)
     float cInt = 0.0f, cLeaf = 0.0f, cObj = 0.0f;
