@@ -29,8 +29,16 @@ constexpr int kRaygenBlock = 128;
 #define SLR_MATERIAL_MIN_BLOCKS 3
 #endif
 #ifndef SLR_SURFACE_MIN_BLOCKS
-#define SLR_SURFACE_MIN_BLOCKS 1
+#define SLR_SURFACE_MIN_BLOCKS 6
 #endif
+#ifndef SLR_MATERIAL_MIN_BLOCKS_HEAVY
+#define SLR_MATERIAL_MIN_BLOCKS_HEAVY 4
+#endif
+// Lambert and the two specular classes run best at 3 resident blocks (168 registers); the heavier BSDFs (Oren-Nayar, Ward,
+// Ashikhmin, the microfacet pair, multi-lobe) gain from a fourth block at 128 registers -- profiles/r01_variant_sweep.md
+constexpr int materialMinBlocks(int cls) {
+    return (cls == SC_LAMBERT || cls == SC_SPECULAR_BRDF || cls == SC_SPECULAR_BSDF) ? SLR_MATERIAL_MIN_BLOCKS : SLR_MATERIAL_MIN_BLOCKS_HEAVY;
+}
 
 
 // ---------------------------------------------------------------------------------------------
@@ -144,7 +152,7 @@ surfaceKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitBu
 }
 
 template <int NC, int CLASS>
-__global__ void __launch_bounds__(kMaterialBlock, SLR_MATERIAL_MIN_BLOCKS)
+__global__ void __launch_bounds__(kMaterialBlock, materialMinBlocks(CLASS))
 materialKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitBuffer hits, ClassQueue cq, PathQueue out, ShadowQueue sq,
                WavefrontCounters* counters) {
     materialStage<NC, CLASS>(s, rc, in, hits, cq, out, sq, counters, counters->classCount[CLASS]);

@@ -139,12 +139,12 @@ __device__ __forceinline__ void mulVector(const float* __restrict__ m, float x, 
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kMaxChunk = 256;
 #ifndef SLR_WALK_STEPS_PER_ROUND
-#define SLR_WALK_STEPS_PER_ROUND 4
+#define SLR_WALK_STEPS_PER_ROUND 1
 #endif
 #ifndef SLR_WALK_REFILL_IDLE
 #define SLR_WALK_REFILL_IDLE 8
 #endif
-constexpr int kStepsPerRound = SLR_WALK_STEPS_PER_ROUND;     // node visits between two refill checks
+constexpr int kStepsPerRound = SLR_WALK_STEPS_PER_ROUND;     // node visits between two refill checks (sweep: profiles/r01_variant_sweep.md)
 constexpr int kRefillIdle = SLR_WALK_REFILL_IDLE;            // idle lanes that trigger a refill
 
 struct WalkState {
