@@ -62,6 +62,7 @@ struct SlrGpuScene {
     bool hasShading = false;
     uint32_t channels = 16;
     uint32_t classMask = 0;           // material classes (wavefront.cuh: ShadeClass) the scene's materials can produce
+    int numSMs = 148;                 // of `device`
 };
 
 namespace slrgpu {
@@ -70,5 +71,15 @@ void releaseSceneArenas();
 // intersect.cu: closest hits of a device-resident SoA ray batch; dStatus = two zeroed ints (overflow flag, chunk cursor)
 int launchIntersect(SlrGpuScene* sc, const SlrGpuRayBatch& rays, uint64_t n, const SlrGpuHitBatch& hits, int* dStatus, cudaStream_t stream);        // scene.cu: drops the per-device arena cache
 int cudaFail(cudaError_t e, const char* what);
+// Grid of a grid-stride / persistent kernel: as many blocks as the device keeps resident (SMs x blocks per SM at the
+// kernel's register count), never more than the work needs. Launching 16 blocks per SM for kernels that hold 3-6 costs
+// ~10 us of block scheduling per launch -- with ~10 launches per wave that was the floor of the small waves.
+template <typename Kernel>
+inline uint32_t residentGrid(Kernel kernel, int blockSize, int numSMs, uint64_t maxBlocks) {
+    int perSM = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, blockSize, 0) != cudaSuccess || perSM < 1) { cudaGetLastError(); perSM = 1; }
+    const uint64_t g = (uint64_t)numSMs * (uint64_t)perSM;
+    return (uint32_t)(g < maxBlocks ? g : (maxBlocks ? maxBlocks : 1));
+}
 #define SLRGPU_CUDA_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return slrgpu::cudaFail(_e, #expr); } while (0)
 }

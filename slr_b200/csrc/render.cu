@@ -285,6 +285,8 @@ template <int NC, int CLASS>
 static void launchMaterial(const SlrGpuScene* sc, const RenderConstants& rc, const RenderWorkspace& w, int cur, uint32_t grid, cudaStream_t stream) {
     cudaStream_t st = w.side[CLASS];
     cudaStreamWaitEvent(st, w.forkEvent, 0);
+    static const int perSM = [] { int n = 0; if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, materialKernel<NC, CLASS>, kMaterialBlock, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; } return n; }();
+    grid = std::min(grid, (uint32_t)(sc->numSMs * perSM));
     materialKernel<NC, CLASS><<<grid, kMaterialBlock, 0, st>>>(sc->dev, rc, w.q[cur], w.hits, w.cq, w.q[cur ^ 1], w.sq, w.dCounters);
     cudaEventRecord(w.joinEvent[CLASS], st);
     cudaStreamWaitEvent(stream, w.joinEvent[CLASS], 0);
@@ -295,7 +297,7 @@ template <int NC, typename Mark>
 static void launchShadeStage(const SlrGpuScene* sc, const RenderConstants& rc, const RenderWorkspace& w, int cur, float* accum, uint32_t grid,
                              cudaStream_t stream, const Mark& mark) {
     mark(2);
-    surfaceKernel<NC><<<grid, kSurfaceBlock, 0, stream>>>(sc->dev, rc, w.q[cur], w.hits, w.cq, accum, w.dCounters);
+    surfaceKernel<NC><<<residentGrid(surfaceKernel<NC>, kSurfaceBlock, sc->numSMs, grid), kSurfaceBlock, 0, stream>>>(sc->dev, rc, w.q[cur], w.hits, w.cq, accum, w.dCounters);
     mark(2);
     mark(3);
     cudaEventRecord(w.forkEvent, stream);
@@ -358,11 +360,10 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
 
     int rcode = SLRGPU_OK;
 
-    // grid-stride launches: enough blocks to fill the machine, never more than the queue needs
-    int numSMs = 148;
-    cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, sc->device);
-    const uint32_t fullGrid = (uint32_t)numSMs * 16u;
-    const uint32_t grid = std::min(fullGrid, (P + 127u) / 128u);
+    // grid-stride launches: never more blocks than the queue needs; every launch site caps this at the blocks its kernel
+    // keeps resident (residentGrid)
+    const int numSMs = sc->numSMs;
+    const uint32_t grid = (P + 127u) / 128u;
 
     cudaEvent_t ev0, ev1;
     SLRGPU_CUDA_TRY(cudaEventCreate(&ev0));
@@ -416,8 +417,8 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
     unsigned long long wave = 0, launches = 0, round = 0;
     auto enqueueWave = [&](int cur) -> int {
         timer.mark(0);
-        if (rgb) raygenKernel<3><<<grid, kRaygenBlock, 0, stream>>>(sc->dev, rc, w.q[cur], w.dCounters);
-        else raygenKernel<16><<<grid, kRaygenBlock, 0, stream>>>(sc->dev, rc, w.q[cur], w.dCounters);
+        if (rgb) raygenKernel<3><<<residentGrid(raygenKernel<3>, kRaygenBlock, sc->numSMs, grid), kRaygenBlock, 0, stream>>>(sc->dev, rc, w.q[cur], w.dCounters);
+        else raygenKernel<16><<<residentGrid(raygenKernel<16>, kRaygenBlock, sc->numSMs, grid), kRaygenBlock, 0, stream>>>(sc->dev, rc, w.q[cur], w.dCounters);
         beginWaveKernel<<<1, 1, 0, stream>>>(rc, w.dCounters);
         timer.mark(0);
         timer.mark(1);

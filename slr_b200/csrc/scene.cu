@@ -238,6 +238,7 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
     SlrGpuScene* sc = new (std::nothrow) SlrGpuScene();
     if (!sc) { setError("host allocation failed"); return SLRGPU_ERR_OUT_OF_MEMORY; }
     sc->device = device;
+    if (cudaDeviceGetAttribute(&sc->numSMs, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sc->numSMs < 1) sc->numSMs = 148;
     DeviceScene& v = sc->dev;
     memset(&v, 0, sizeof(v));
     int rc = SLRGPU_OK;

@@ -22,6 +22,23 @@ __device__ __forceinline__ uint32_t warpAppend(bool alive, uint32_t* counter) {
     return base + __popc(mask & ((1u << lane) - 1u));
 }
 
+// positions of the `alive` lanes in the next path queue and of the `shadow` lanes in the shadow queue: both counters
+// sit in one 64-bit word (WavefrontCounters::numNext / numShadow), so one atomic per warp reserves both ranges
+__device__ __forceinline__ void warpAppendPair(bool alive, bool shadow, WavefrontCounters* counters, uint32_t* npos, uint32_t* spos) {
+    const unsigned am = __ballot_sync(0xFFFFFFFFu, alive), sm = __ballot_sync(0xFFFFFFFFu, shadow);
+    *npos = 0; *spos = 0;
+    if ((am | sm) == 0) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0)
+        base = atomicAdd(reinterpret_cast<unsigned long long*>(&counters->numNext),
+                         (unsigned long long)__popc(am) | ((unsigned long long)__popc(sm) << 32));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    const unsigned lt = (1u << lane) - 1u;
+    *npos = (uint32_t)(base & 0xFFFFFFFFull) + __popc(am & lt);
+    *spos = (uint32_t)(base >> 32) + __popc(sm & lt);
+}
+
 template <int NC> __device__ __forceinline__ void storeAlpha(const PathQueue& q, uint32_t pos, const Spec<NC>& a) {
     if (NC == 3) { q.alpha[pos] = make_float4(a.v[0], a.v[1], a.v[2], 0.0f); return; }
 #pragma unroll
@@ -315,8 +332,8 @@ __device__ __forceinline__ void materialStage(const DeviceScene& s, const Render
             const uint2 e = entries[k];
             materialItem<NC, CLASS>(s, rc, in, hits, e.x, e.y, o);
         }
-        const uint32_t spos = warpAppend(o.shadow, &counters->numShadow);
-        const uint32_t npos = warpAppend(o.alive, &counters->numNext);
+        uint32_t npos, spos;
+        warpAppendPair(o.alive, o.shadow, counters, &npos, &spos);
         materialWrite<NC>(out, sq, npos, spos, o);
     }
 }

@@ -35,12 +35,12 @@ shadowKernel(const DeviceScene s, ShadowQueue q, float* __restrict__ accum, Wave
 
 template <bool INSTANCES, bool COUNT>
 static void launchExtendT(const SlrGpuScene* sc, const PathQueue& q, const HitBuffer& hits, WavefrontCounters* counters, uint32_t grid, cudaStream_t stream) {
-    extendKernel<INSTANCES, COUNT><<<grid, kTraceBlock, 0, stream>>>(sc->dev, q, hits, counters);
+    extendKernel<INSTANCES, COUNT><<<residentGrid(extendKernel<INSTANCES, COUNT>, kTraceBlock, sc->numSMs, grid), kTraceBlock, 0, stream>>>(sc->dev, q, hits, counters);
 }
 template <bool INSTANCES, bool COUNT>
 static void launchShadowT(const SlrGpuScene* sc, const ShadowQueue& q, float* accum, WavefrontCounters* counters, uint32_t grid, cudaStream_t stream) {
-    if (sc->channels == 3) shadowKernel<INSTANCES, 3, COUNT><<<grid, kTraceBlock, 0, stream>>>(sc->dev, q, accum, counters);
-    else shadowKernel<INSTANCES, 16, COUNT><<<grid, kTraceBlock, 0, stream>>>(sc->dev, q, accum, counters);
+    if (sc->channels == 3) shadowKernel<INSTANCES, 3, COUNT><<<residentGrid(shadowKernel<INSTANCES, 3, COUNT>, kTraceBlock, sc->numSMs, grid), kTraceBlock, 0, stream>>>(sc->dev, q, accum, counters);
+    else shadowKernel<INSTANCES, 16, COUNT><<<residentGrid(shadowKernel<INSTANCES, 16, COUNT>, kTraceBlock, sc->numSMs, grid), kTraceBlock, 0, stream>>>(sc->dev, q, accum, counters);
 }
 
 int launchExtend(const SlrGpuScene* sc, const PathQueue& q, const HitBuffer& hits, WavefrontCounters* counters, bool count, uint32_t grid, cudaStream_t stream) {

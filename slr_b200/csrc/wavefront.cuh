@@ -56,9 +56,9 @@ enum ShadeClass : uint32_t {
 // Device-resident loop state: every kernel of a wave reads its work size from here, so the host
 // never has to wait for a count (it only polls, two waves behind, for termination).
 struct WavefrontCounters {
+    uint32_t numNext;          // entries appended to the next path queue   } one aligned 64-bit word: the material kernels
+    uint32_t numShadow;        // entries appended to the shadow queue      } reserve both positions with ONE atomic per warp
     uint32_t numPaths;         // entries of the current path queue
-    uint32_t numNext;          // entries appended to the next path queue
-    uint32_t numShadow;        // entries appended to the shadow queue
     uint32_t stackOverflow;
     uint32_t classCount[16];   // entries of each material-class queue (SC_COUNT used)
     unsigned long long generated, total;          // camera samples started / to render in this call

@@ -1,6 +1,6 @@
 """Hot source lines of one captured kernel: joins the SASS page of an ncu report (warp-stall samples per
 instruction) with nvdisasm's line table of the same kernel in the built object (needs -lineinfo).
-  python tools/ncu_hot_lines.py <file.ncu-rep> <launch index> <object.o> <mangled-name substring> [top N]
+  python tools/ncu_hot_lines.py <file.ncu-rep> <kernel name substring, demangled> <object.o> <mangled-name substring> [top N]
 """
 import csv
 import io
@@ -13,12 +13,13 @@ from collections import Counter
 
 
 def main():
-    rep, idx, obj, sym = sys.argv[1], int(sys.argv[2]), sys.argv[3], sys.argv[4]
+    rep, want, obj, sym = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4]
     top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
-    rows = rows[starts[idx]:starts[idx + 1]]           # the idx-th captured launch
+    idx = next(k for k, i in enumerate(starts[:-1]) if want in rows[i][1])
+    rows = rows[starts[idx]:starts[idx + 1]]           # the first captured launch of that kernel
     hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     cols = {n: i for i, n in enumerate(rows[hdr])}
     base = None
