@@ -49,6 +49,45 @@ struct DeviceScene {
     float integralCMF;
 };
 
+// Material class of a hit (wavefront.cuh: ShadeClass values, numbered like LobeType) and the leaf
+// material the class kernel builds its lobe from. Emitter wrappers are peeled (their BSDF is the
+// scattering material's, surface_material.h); sum / mix / inverse trees go to the generic kernel with
+// the ORIGINAL material id. Returns 0xFF when the hit has no BSDF (an emitter without a scattering part).
+__host__ __device__ inline uint32_t classifyMaterialIn(const SlrGpuMaterial* materials, uint32_t materialId, uint32_t* leaf) {
+    uint32_t id = materialId;
+    SlrGpuMaterial m = materials[id];
+    for (int depth = 0; depth < 4 && m.kind == SLRGPU_MAT_EMITTER; ++depth) {
+        if (m.sub[0] == SLRGPU_INVALID_ID) return 0xFFu;
+        id = m.sub[0];
+        m = materials[id];
+    }
+    *leaf = id;
+    switch (m.kind) {
+    case SLRGPU_MAT_DIFFUSE: return m.tex[1] == SLRGPU_INVALID_ID ? 0u : 1u;
+    case SLRGPU_MAT_SPECULAR_REFLECTION: return 2u;
+    case SLRGPU_MAT_SPECULAR_SCATTERING: return 3u;
+    case SLRGPU_MAT_WARD_DUR: return 4u;
+    case SLRGPU_MAT_ASHIKHMIN_SHIRLEY: return 5u;
+    case SLRGPU_MAT_MICROFACET_REFLECTION: return 6u;
+    case SLRGPU_MAT_MICROFACET_SCATTERING: return 7u;
+    default: *leaf = materialId; return 8u;
+    }
+}
+
+// What the `surface` stage needs to know about a hit triangle, worked out once at scene creation and kept in the
+// triangle record's spare word (SlrGpuTriangle::pad on the device copy): class | emitting << 8 | leaf material << 9.
+// It replaces two to three dependent loads of the material table per hit. kSurfaceInfoDynamic: not precomputed.
+constexpr uint32_t kSurfaceInfoDynamic = 0xFFFFFFFFu;
+inline uint32_t packSurfaceInfo(const SlrGpuMaterial* materials, uint32_t numMaterials, uint32_t materialId) {
+    if (materialId >= numMaterials || numMaterials >= (1u << 23)) return kSurfaceInfoDynamic;
+    uint32_t leaf = SLRGPU_INVALID_ID;
+    const uint32_t cls = classifyMaterialIn(materials, materialId, &leaf);
+    const uint32_t emitting = materials[materialId].kind == SLRGPU_MAT_EMITTER ? 1u : 0u;
+    if (cls == 0xFFu) leaf = 0;
+    if (leaf >= (1u << 23)) return kSurfaceInfoDynamic;
+    return cls | (emitting << 8) | (leaf << 9);
+}
+
 }  // namespace slrgpu
 
 struct SlrGpuScene {

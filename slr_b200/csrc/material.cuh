@@ -143,29 +143,9 @@ static __device__ __noinline__ void buildBsdf(const DeviceScene& s, uint32_t mat
     }
 }
 
-// Material class of a hit (wavefront.cuh: ShadeClass values, numbered like LobeType) and the leaf
-// material the class kernel builds its lobe from. Emitter wrappers are peeled (their BSDF is the
-// scattering material's, surface_material.h); sum / mix / inverse trees go to the generic kernel with
-// the ORIGINAL material id. Returns 0xFF when the hit has no BSDF (an emitter without a scattering part).
+// classifyMaterialIn (device_scene.h) on the device's material table
 __device__ __forceinline__ uint32_t classifyMaterial(const DeviceScene& s, uint32_t materialId, uint32_t* leaf) {
-    uint32_t id = materialId;
-    SlrGpuMaterial m = s.materials[id];
-    for (int depth = 0; depth < 4 && m.kind == SLRGPU_MAT_EMITTER; ++depth) {
-        if (m.sub[0] == SLRGPU_INVALID_ID) return 0xFFu;
-        id = m.sub[0];
-        m = s.materials[id];
-    }
-    *leaf = id;
-    switch (m.kind) {
-    case SLRGPU_MAT_DIFFUSE: return m.tex[1] == SLRGPU_INVALID_ID ? 0u : 1u;
-    case SLRGPU_MAT_SPECULAR_REFLECTION: return 2u;
-    case SLRGPU_MAT_SPECULAR_SCATTERING: return 3u;
-    case SLRGPU_MAT_WARD_DUR: return 4u;
-    case SLRGPU_MAT_ASHIKHMIN_SHIRLEY: return 5u;
-    case SLRGPU_MAT_MICROFACET_REFLECTION: return 6u;
-    case SLRGPU_MAT_MICROFACET_SCATTERING: return 7u;
-    default: *leaf = materialId; return 8u;
-    }
+    return classifyMaterialIn(s.materials, materialId, leaf);
 }
 // material kind behind a single-lobe class
 __host__ __device__ constexpr int classMaterialKind(int cls) {

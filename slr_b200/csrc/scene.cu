@@ -247,7 +247,14 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
     UP(reinterpret_cast<const float4*>(d->bvh_nodes), (uint64_t)d->num_bvh_nodes * 8, &v.nodes);
     UP(reinterpret_cast<const float4*>(d->leaf_records), (uint64_t)d->num_leaf_records * 3, &v.leaves);
     UP(d->instances, d->num_instances, &v.instances);
-    UP(d->triangles, d->num_triangles, &v.triangles);
+    // the device copy of the triangle records carries the surface stage's per-triangle facts in its spare word
+    std::vector<SlrGpuTriangle> triangles;
+    if (d->triangles && d->num_triangles) {
+        triangles.assign(d->triangles, d->triangles + d->num_triangles);
+        for (SlrGpuTriangle& t : triangles)
+            t.pad = d->materials ? packSurfaceInfo(d->materials, d->num_materials, t.material) : kSurfaceInfoDynamic;
+    }
+    UP(triangles.data(), triangles.size(), &v.triangles);
     UP(reinterpret_cast<const float4*>(d->vertices), (uint64_t)d->num_vertices * 3, &v.vertices);
     UP(d->materials, d->num_materials, &v.materials);
     UP(d->textures, d->num_textures, &v.textures);

@@ -88,8 +88,10 @@ static __device__ __noinline__ void surfaceEmission(const DeviceScene& s, const 
     const Spec<NC> Le = materialEmittance<NC>(s, material, sp, wlOffset);
     float v[NC == 3 ? 4 : NC];
     const float k = edf * mis * in.weight[i];
+    float sum = 0.0f;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) v[c] = alpha.v[c] * Le.v[c] * k;
+    for (int c = 0; c < NC; ++c) { v[c] = alpha.v[c] * Le.v[c] * k; sum += v[c]; }
+    if (!isfinite(sum)) return;          // see materialItem: a non-finite sample is dropped, never splatted
     splat<NC>(accum, meta.x, wlOffset, (flags & kFlagStrataInPlace) != 0, v);
 }
 
@@ -119,7 +121,7 @@ __device__ __forceinline__ void surfaceItem(const DeviceScene& s, const RenderCo
         if (!isEnv) {
             tri = s.triangles[hid.x];
             material = tri.material;
-            emitting = materialIsEmitting(s, material);
+            emitting = tri.pad != kSurfaceInfoDynamic ? ((tri.pad >> 8) & 1u) != 0 : materialIsEmitting(s, material);
         }
         if (emitting) surfaceEmission<NC>(s, in, hits, i, hid, meta, flags, material, tri, isEnv, accum);
         bool cont = !isEnv;
@@ -137,7 +139,8 @@ __device__ __forceinline__ void surfaceItem(const DeviceScene& s, const RenderCo
             if (pathLength >= rc.maxPathLength) cont = false;
         }
         if (cont) {
-            cls = classifyMaterial(s, material, &leaf);
+            if (tri.pad != kSurfaceInfoDynamic) { cls = tri.pad & 0xFFu; leaf = tri.pad >> 9; }
+            else cls = classifyMaterial(s, material, &leaf);
             if (cls != SC_NONE) in.meta[i].z = hero | (flags << 8) | (pathLength << 16);
         }
     }
@@ -262,13 +265,18 @@ __device__ __forceinline__ void materialItem(const DeviceScene& s, const RenderC
                 if (!isinf(ls.areaPDF)) mis = (ls.lightPDF * ls.lightPDF) / (ls.lightPDF * ls.lightPDF + bsdfPDF * bsdfPDF);
                 const float G = absDot(shadowDir_sn, gNorm) * cosLight / dist2;
                 const float kk = edf * (G * mis / ls.lightPDF) * o.weight;
+                float sum = 0.0f;
 #pragma unroll
-                for (int c = 0; c < NC; ++c) o.sContrib.v[c] = o.alpha.v[c] * M.v[c] * fs.v[c] * kk;
+                for (int c = 0; c < NC; ++c) { o.sContrib.v[c] = o.alpha.v[c] * M.v[c] * fs.v[c] * kk; sum += o.sContrib.v[c]; }
                 // Scene::testVisibility
                 o.sOrg = sp.p;
                 if (ls.sp.atInfinity) { o.sDir = shadowDir; o.sTmax = 3.402823466e+38f; }
                 else { const float dist = length(ls.sp.p - sp.p); o.sDir = (ls.sp.p - sp.p) / dist; o.sTmax = dist * (1.0f - 0.0001f); }
-                o.shadow = true;
+                // The shading TUs divide with the 2-ulp hardware reciprocal (Makefile SHADE_MATH): a denormal denominator
+                // gives inf where IEEE division gives a huge finite value (seen once per ~1e8 samples on the microfacet
+                // scene). A sample that is not finite is dropped here / the path ended below, so a NaN never reaches the
+                // sensor; the reference would have splatted a firefly.
+                o.shadow = isfinite(sum);
             }
         }
     }
@@ -288,7 +296,7 @@ __device__ __forceinline__ void materialItem(const DeviceScene& s, const RenderC
         if (dtIsDelta(res.type)) flags |= kFlagPrevDelta;
         o.meta.z = hero | (flags << 8) | (pathLength << 16);
         o.nImp = specImportance(o.alpha, hero);
-        o.alive = true;
+        o.alive = isfinite(o.nImp);
     }
 }
 

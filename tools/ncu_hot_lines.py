@@ -57,8 +57,13 @@ def main():
             inst_by_line[line] += ex
             total += n
     print(f"{total} samples")
+    inst_by_file = Counter()
+    for (f, ln), n in inst_by_line.items():
+        inst_by_file[f] += n
+    tot_inst = sum(inst_by_file.values())
+    print(f"{tot_inst} warp instructions executed")
     for f, n in by_file.most_common(12):
-        print(f"  {f:20s} {100 * n / max(total, 1):5.1f} %")
+        print(f"  {f:28s} {100 * n / max(total, 1):5.1f} % of samples  {100 * inst_by_file[f] / max(tot_inst, 1):5.1f} % of instructions")
     src_cache = {}
     root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "slr_b200", "csrc")
     for (f, ln), n in by_line.most_common(top):
