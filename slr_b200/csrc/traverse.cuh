@@ -153,6 +153,8 @@ struct WalkState {
     float ix, iy, iz;
     uint32_t pos;
     int sp;
+    uint32_t top;                // == stack[sp - 1] while sp > 0: the next pop comes from a register, its successor is
+                                 // re-loaded one step ahead (the local-memory load is off the node fetch's critical path)
     bool found;
     TraversalCounters cnt0;      // the lane's running counters when this ray started (per-ray counts = difference)
 };
@@ -164,6 +166,7 @@ __device__ __forceinline__ void walkBegin(WalkState& w, uint32_t* stack) {
     w.found = false;
     w.sp = 0;
     stack[w.sp++] = 0;      // the top-level root is node 0
+    w.top = 0;
 }
 
 // ---- the step of the walk; instancing is part of the same state machine ---------------------------
@@ -218,7 +221,8 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
     LeafQueue local;
     LeafQueue& leaves = INSTANCES ? iw.leaves : local;
     if (!INSTANCES) local.clear();
-    const uint32_t entry = stack[--w.sp];
+    const uint32_t entry = w.top;
+    if (--w.sp > 0) w.top = stack[w.sp - 1];
     if (INSTANCES && entry == kReturnMarker) {
         r.ox = iw.wox; r.oy = iw.woy; r.oz = iw.woz; r.dx = iw.wdx; r.dy = iw.wdy; r.dz = iw.wdz;   // tmax carries over (SurfaceObject.cpp:314)
         walkSetRay(w);
@@ -258,6 +262,7 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
                 if (c == kEmptyChild || (c >> 31)) continue;
                 if (w.sp >= kStackSize) { overflow = true; continue; }
                 stack[w.sp++] = c & 0x07FFFFFFu;
+                w.top = c & 0x07FFFFFFu;
             }
             // leaf children in visiting order: the first becomes the current range, up to three wait
             uint32_t q0 = kEmptyChild, q1 = kEmptyChild, q2 = kEmptyChild, q3 = kEmptyChild;
@@ -303,6 +308,7 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
                 iw.curInst = instId;
                 stack[w.sp++] = kReturnMarker;
                 stack[w.sp++] = inst->root_node;
+                w.top = inst->root_node;
                 return false;
             }
             continue;
