@@ -1,6 +1,7 @@
 // Ray-batch entry points: closest hit (Accelerator::intersect, libSLR/Core/Accelerator.h:17-34 /
 // QBVH::intersect, QBVH.h:295-337) and occlusion (Scene::testVisibility, SurfaceObject.cpp:418-430).
 // MUST be compiled with -fmad=false (see traverse.cuh).
+#define SLR_WALK_ONE_RECORD_PER_STEP 1      // measured faster for ray batches (traverse.cuh walkStep)
 #include "traverse.cuh"
 
 namespace slrgpu {

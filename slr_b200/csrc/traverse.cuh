@@ -209,18 +209,12 @@ __device__ __forceinline__ void walkSetRay(WalkState& w) {
             (w.ix > 0.0f ? 0x100u : 0u) | (w.iy > 0.0f ? 0x200u : 0u) | (w.iz > 0.0f ? 0x400u : 0u);
 }
 
-// One step of the walk: pop one stack entry -- a node: 4-box test, push the inner children that were hit
-// (far to near), queue the leaf children that were hit (near to far); or the return marker of an instance --
-// then test the queued leaf records in ONE loop shared by all child slots (so lanes whose leaves sit at
-// different child positions run the same instructions). An instance record enters the instance and ends
-// the step. Returns true when the ray is finished.
-template <bool INSTANCES, bool ANY_HIT, bool COUNT>
-__device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, InstanceWalkState& iw, uint32_t* stack,
+// The node half of a step: pops one entry -- a node: 4-box test, push the inner children that were hit (far to near),
+// queue the leaf children that were hit (near to far) in `leaves`; or the return marker of an instance.
+template <bool INSTANCES, bool COUNT>
+__device__ __forceinline__ void walkNode(const DeviceScene& s, WalkState& w, InstanceWalkState& iw, LeafQueue& leaves, uint32_t* stack,
                                          TraversalCounters& cnt, bool& overflow) {
     Ray& r = w.r;
-    LeafQueue local;
-    LeafQueue& leaves = INSTANCES ? iw.leaves : local;
-    if (!INSTANCES) local.clear();
     const uint32_t entry = w.top;
     if (--w.sp > 0) w.top = stack[w.sp - 1];
     if (INSTANCES && entry == kReturnMarker) {
@@ -284,7 +278,35 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
             }
         }
     }
+}
+
+// One step of a lane: a node visit if no leaf record is waiting, then the leaf records that visit queued -- all of
+// them (default), or AT MOST ONE per step with the rest left for the lane's next steps, before it pops another node
+// (SLR_WALK_ONE_RECORD_PER_STEP). Per ray the sequence of box and triangle tests is the reference's either way; what
+// changes is the interleaving across lanes: in the loop form the lanes that found no leaf wait for the lane with the
+// longest list, in the one-record form every lane advances by a node or a triangle per iteration of the warp's loop
+// but carries its leaf queue across iterations (5 more registers). Measured (profiles/r01_variant_sweep.md): the
+// batch kernels on the 500 k-triangle heightfield gain 7 % from one record per step (3604 -> 3860 Mrays/s), the
+// renderer's extend / shadow kernels lose 10 % (C1 extend 10.3 -> 11.4 ms) -- so intersect.cu sets it, trace.cu does not.
+// Returns true when the ray is finished.
+#ifndef SLR_WALK_ONE_RECORD_PER_STEP
+#define SLR_WALK_ONE_RECORD_PER_STEP 0
+#endif
+template <bool INSTANCES, bool ANY_HIT, bool COUNT>
+__device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, InstanceWalkState& iw, uint32_t* stack,
+                                         TraversalCounters& cnt, bool& overflow) {
+    Ray& r = w.r;
+#if SLR_WALK_ONE_RECORD_PER_STEP
+    LeafQueue& leaves = iw.leaves;
+    if (leaves.count == 0) walkNode<INSTANCES, COUNT>(s, w, iw, leaves, stack, cnt, overflow);
+    if (leaves.count != 0) {
+#else
+    LeafQueue local;                     // flat scenes: the queue lives for one step only
+    LeafQueue& leaves = INSTANCES ? iw.leaves : local;
+    if (!INSTANCES) local.clear();
+    walkNode<INSTANCES, COUNT>(s, w, iw, leaves, stack, cnt, overflow);
     while (leaves.count != 0) {
+#endif
         const float4* rec = s.leaves + (size_t)leaves.first * 3;
         const float4 a = ldg4(rec), b = ldg4(rec + 1), cc = ldg4(rec + 2);      // all 48 B at once (an instance record has them too)
         ++leaves.first;
@@ -293,36 +315,40 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
         if (COUNT) ++cnt.tris;
         if (id & 0x80000000u) {
             if constexpr (INSTANCES) {
-                if (iw.curInst != SLRGPU_INVALID_ID) continue;          // nested instancing is rejected at scene build
-                if (w.sp + 2 > kStackSize) { overflow = true; continue; }   // no room for marker + root: reported as overflow
-                const uint32_t instId = id & 0x7FFFFFFFu;
-                const SlrGpuInstance* inst = s.instances + instId;
-                iw.wox = r.ox; iw.woy = r.oy; iw.woz = r.oz; iw.wdx = r.dx; iw.wdy = r.dy; iw.wdz = r.dz;
-                iw.saved = iw.leaves;
-                iw.leaves.clear();
-                float lx, ly, lz, mx, my, mz;
-                mulPoint(inst->mat_inv, r.ox, r.oy, r.oz, &lx, &ly, &lz);
-                mulVector(inst->mat_inv, r.dx, r.dy, r.dz, &mx, &my, &mz);
-                r.ox = lx; r.oy = ly; r.oz = lz; r.dx = mx; r.dy = my; r.dz = mz;
-                walkSetRay(w);
-                iw.curInst = instId;
-                stack[w.sp++] = kReturnMarker;
-                stack[w.sp++] = inst->root_node;
-                w.top = inst->root_node;
-                return false;
+                // nested instancing is rejected at scene build; no room for marker + root is reported as overflow
+                if (iw.curInst == SLRGPU_INVALID_ID) {
+                    if (w.sp + 2 > kStackSize) overflow = true;
+                    else {
+                        const uint32_t instId = id & 0x7FFFFFFFu;
+                        const SlrGpuInstance* inst = s.instances + instId;
+                        iw.wox = r.ox; iw.woy = r.oy; iw.woz = r.oz; iw.wdx = r.dx; iw.wdy = r.dy; iw.wdz = r.dz;
+                        iw.saved = iw.leaves;
+                        iw.leaves.clear();
+                        float lx, ly, lz, mx, my, mz;
+                        mulPoint(inst->mat_inv, r.ox, r.oy, r.oz, &lx, &ly, &lz);
+                        mulVector(inst->mat_inv, r.dx, r.dy, r.dz, &mx, &my, &mz);
+                        r.ox = lx; r.oy = ly; r.oz = lz; r.dx = mx; r.dy = my; r.dz = mz;
+                        walkSetRay(w);
+                        iw.curInst = instId;
+                        stack[w.sp++] = kReturnMarker;
+                        stack[w.sp++] = inst->root_node;
+                        w.top = inst->root_node;
+                        return false;
+                    }
+                }
             }
-            continue;
-        }
-        float t, b0, b1;
-        if (triangleTest(a, b, cc, r, &t, &b0, &b1)) {
-            r.tmax = t;
-            w.hit.prim = id; w.hit.inst = INSTANCES ? iw.curInst : SLRGPU_INVALID_ID;
-            w.hit.t = t; w.hit.u = b0; w.hit.v = b1;
-            w.found = true;
-            if (ANY_HIT) return true;
+        } else {
+            float t, b0, b1;
+            if (triangleTest(a, b, cc, r, &t, &b0, &b1)) {
+                r.tmax = t;
+                w.hit.prim = id; w.hit.inst = INSTANCES ? iw.curInst : SLRGPU_INVALID_ID;
+                w.hit.t = t; w.hit.u = b0; w.hit.v = b1;
+                w.found = true;
+                if (ANY_HIT) return true;
+            }
         }
     }
-    return w.sp == 0;
+    return w.sp == 0 && leaves.count == 0;
 }
 
 // Runs `n` rays through the scene with one warp-cooperative loop. Source::load(i, Ray&) fetches ray i,
@@ -334,7 +360,7 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t stack[kStackSize];
     WalkState w;
-    InstanceWalkState iw;                       // only live in the INSTANCES instantiations
+    InstanceWalkState iw;                       // the leaf queue; the rest is only live in the INSTANCES instantiations
     bool active = false;
     uint32_t idx = 0;
     uint32_t chunkNext = 0, chunkEnd = 0;       // warp-uniform
@@ -364,7 +390,8 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
                     idx = chunkNext + rank;
                     source.load(idx, w.r);
                     walkBegin(w, stack);
-                    if (INSTANCES) { iw.leaves.clear(); iw.saved.clear(); iw.curInst = SLRGPU_INVALID_ID; }
+                    iw.leaves.clear();
+                    if (INSTANCES) { iw.saved.clear(); iw.curInst = SLRGPU_INVALID_ID; }
                     w.cnt0 = cnt;
                     active = true;
                 }
