@@ -395,6 +395,15 @@ SLRGPU_API int slrgpu_render(SlrGpuScene* scene, const SlrGpuRenderParams* param
 SLRGPU_API int slrgpu_render_device(SlrGpuScene* scene, const SlrGpuRenderParams* params, float* accum_device,
                                     void* stream, SlrGpuRenderStats* stats);
 
+/* Debug (AOV) renderer -- replaces DebugRenderer::render (libSLR/Renderers/DebugRenderer.cpp:29-217; chosen by
+ * setRenderer("method": "debug", ("outputs": (...),)), libSLRSceneGraph/API.cpp:1037-1062): ONE camera sample per pixel
+ * (global sample index params->spp_begin; spp_end must be greater), closest hit, Intersection::getSurfacePoint.
+ * out[(y*width + x) * SLRGPU_DEBUG_FLOATS + k], host buffer: k = 0 hit (1) / miss (0), 1-3 geometric normal, 4-6 shading
+ * normal, 7-9 shading tangent in world space -- the vectors the reference quantises as (uint8)clamp((0.5 v + 0.5) * 255)
+ * into geometric_normal.bmp / shading_normal.bmp / shading_tangent.bmp. A miss leaves zeros (DebugInfo()). */
+#define SLRGPU_DEBUG_FLOATS 10
+SLRGPU_API int slrgpu_render_debug(SlrGpuScene* scene, const SlrGpuRenderParams* params, float* out, SlrGpuRenderStats* stats);
+
 /* ---------------------------------------------------------------------------------------------
  * Shading probe (for parity tests): runs, for every probe ray, the same device functions the material
  * kernels run -- closest hit, surface point (normal map, instance transform), material -> BSDF with its

@@ -54,6 +54,12 @@ SLRGPU_API int slrhost_render(SlrHostScene* s, int device, int width, int height
  * front end calls before the sensors are summed (one process per GPU). */
 SLRGPU_API int slrhost_render_range(SlrHostScene* s, int device, int width, int height, int spp_begin, int spp, int seed,
                                     const char* bmp_dir, float* accum, double* stats6);
+/* Renderer::render through GPUDebugRenderer (the reference's DebugRenderer, setRenderer("method": "debug")): one camera
+ * sample per pixel; out (if non-NULL) receives width*height*SLRGPU_DEBUG_FLOATS floats (include/slrgpu.h
+ * slrgpu_render_debug), bmp_dir (if non-NULL) geometric_normal.bmp, shading_normal.bmp and shading_tangent.bmp.
+ * stats6 as slrhost_render. */
+SLRGPU_API int slrhost_render_debug(SlrHostScene* s, int device, int width, int height, int seed,
+                                    const char* bmp_dir, float* out, double* stats6);
 /* Tone-maps a frame buffer exactly like ImageSensor::saveImage (ImageSensor.cpp:138-186). */
 SLRGPU_API int slrhost_save_bmp(const char* path, const float* accum, int width, int height, int channels,
                                 float scale, float sensitivity);

@@ -15,6 +15,7 @@
 #include <libSLR/Accelerator/QBVH.h>
 #include <libSLR/Memory/ArenaAllocator.h>
 #include <libSLR/Renderers/PathTracingRenderer.h>
+#include <libSLR/Renderers/DebugRenderer.h>
 #include <libSLR/BasicTypes/Spectrum.h>
 #include <libSLR/BasicTypes/SpectrumTypes.h>
 #include <libSLRSceneGraph/Scene.h>
@@ -38,9 +39,10 @@ static void swapToQBVH(const SurfaceObjectAggregate* aggr, std::set<const Surfac
 }
 
 int main(int argc, char** argv) {
-    if (argc < 3) { fprintf(stderr, "usage: ref_render scene.txt out.bin [spp] [width] [height] [seed] [qbvh]\n"); return 2; }
+    if (argc < 3) { fprintf(stderr, "usage: ref_render scene.txt out.bin [spp] [width] [height] [seed] [qbvh] [debug]\n"); return 2; }
     const int spp = argc > 3 ? atoi(argv[3]) : 0, w = argc > 4 ? atoi(argv[4]) : 0, h = argc > 5 ? atoi(argv[5]) : 0;
     const int seed = argc > 6 ? atoi(argv[6]) : 0, qbvh = argc > 7 ? atoi(argv[7]) : 0;
+    const bool debugAOV = argc > 8 && std::string(argv[8]) == "debug";     // the reference's DebugRenderer instead of the path tracer
     initSpectrum();
     auto t0 = std::chrono::steady_clock::now();
     SLRSceneGraph::SceneRef scene = createShared<SLRSceneGraph::Scene>();
@@ -70,6 +72,15 @@ int main(int argc, char** argv) {
     std::string outDir = out.substr(0, out.find_last_of('/'));
     if (chdir(outDir.c_str()) != 0) perror("chdir");
 
+    if (debugAOV) {
+        // DebugRenderer writes geometric_normal.bmp / shading_normal.bmp / shading_tangent.bmp into the working directory
+        bool flags[(int)ExtraChannel::NumChannels];
+        for (int i = 0; i < (int)ExtraChannel::NumChannels; ++i) flags[i] = false;
+        flags[(int)ExtraChannel::GeometricNormal] = flags[(int)ExtraChannel::ShadingNormal] = flags[(int)ExtraChannel::ShadingTangent] = true;
+        DebugRenderer debugRenderer(flags);
+        debugRenderer.render(*rawScene, settings);
+        return 0;
+    }
     PathTracingRenderer renderer(useSpp);
     auto t3 = std::chrono::steady_clock::now();
     renderer.render(*rawScene, settings);

@@ -399,6 +399,8 @@ host.slrhost_scene_context.restype = C.c_int
 host.slrhost_scene_context.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
 host.slrhost_render.restype = C.c_int
 host.slrhost_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, PF, C.POINTER(C.c_double)]
+host.slrhost_render_debug.restype = C.c_int
+host.slrhost_render_debug.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, PF, C.POINTER(C.c_double)]
 host.slrhost_render_range.restype = C.c_int
 host.slrhost_render_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, PF, C.POINTER(C.c_double)]
 host.slrhost_save_bmp.restype = C.c_int
@@ -455,6 +457,22 @@ def gpu_render(gpu_scene, width, height, spp_begin, spp_end, seed=1509761209, ti
     st = RenderStats()
     _gpu_check(gpu.slrgpu_render(gpu_scene.handle, C.byref(p), _pf(accum), C.byref(st)), "slrgpu_render")
     return accum, {k: (list(getattr(st, k)) if k == "class_hits" else getattr(st, k)) for k, _ in RenderStats._fields_}
+
+
+DEBUG_FLOATS = 10
+
+
+def host_render_debug(host_scene, width=0, height=0, seed=0, bmp_dir=None, device=0):
+    """slrhost_render_debug: the GPU debug (AOV) renderer. Returns out[h, w, 10] (hit, geometric normal, shading
+    normal, shading tangent) and writes the three BMPs into bmp_dir if given."""
+    ctx = getattr(host_scene, "context", {"width": 0, "height": 0})
+    w = width or int(ctx["width"])
+    h = height or int(ctx["height"])
+    out = np.zeros((h, w, DEBUG_FLOATS), np.float32)
+    st = (C.c_double * 6)()
+    _host_check(host.slrhost_render_debug(host_scene.handle, device, w, h, seed, os.fsencode(bmp_dir) if bmp_dir else None, _pf(out), st),
+                "slrhost_render_debug")
+    return out, {"paths": st[0], "rays": st[1], "device_s": st[2], "wall_s": st[3]}
 
 
 def probe_shading(gpu_scene, probes):

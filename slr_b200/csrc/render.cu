@@ -9,6 +9,7 @@
 // and every kernel launch advances all of them by one stage. Finished paths are replaced by new
 // camera samples (path regeneration) until the sample range is exhausted.
 #include "stages.cuh"
+#include "traverse.cuh"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -41,6 +42,52 @@ constexpr int materialMinBlocks(int cls) {
 }
 
 
+// One camera sample of pixel (x, y): Job::kernel's first half (PathTracingRenderer.cpp:100-126; DebugRenderer.cpp:134-152
+// draws the same samples) -- time, jittered pixel position, wavelengths, lens position, PerspectiveCamera::sample and
+// PerspectiveIDF::sample.
+struct CameraSample {
+    V3 org, dir;
+    float weight, wlOffset;
+    uint32_t ipx, ipy, hero, flags;
+};
+template <int NC>
+__device__ __forceinline__ void sampleCamera(const DeviceScene& s, const RenderConstants& rc, uint32_t x, uint32_t y, uint32_t pixel, uint32_t sample,
+                                             CameraSample* o) {
+    const Rand4 r0 = pathRandom(rc.seed, pixel, sample, 0);    // time, pixel x, pixel y, wavelength offset
+    const Rand4 r1 = pathRandom(rc.seed, pixel, sample, 1);    // wavelength selection, lens u0, lens u1
+    const float px = x + r0.y, py = y + r0.z;
+    const float wlOffset = r0.w;
+    o->wlOffset = wlOffset;
+    o->hero = min((uint32_t)(NC * r1.x), (uint32_t)(NC - 1));
+
+    // PerspectiveCamera::sample
+    float lx, ly;
+    concentricSampleDisk(r1.y, r1.z, &lx, &ly);
+    const SlrGpuCamera& cam = s.camera;
+    const V3 orgLocal(cam.lens_radius * lx, cam.lens_radius * ly, 0.0f);
+    o->org = xfmPoint(cam.mat, orgLocal);
+    const V3 lensN = xfmNormal(cam.mat_inv, V3(0, 0, 1));
+    Frame f;
+    f.z = lensN;
+    f.x = xfmVector(cam.mat, V3(1, 0, 0));
+    f.y = cross(f.z, f.x);
+    // PerspectiveIDF::sample with (p.x / W, p.y / H)
+    const V3 pFocus(rc.opWidth * (0.5f - px / rc.width), rc.opHeight * (0.5f - py / rc.height), cam.obj_plane_dist);
+    const V3 dirLocal = normalize(pFocus - orgLocal);
+    const float dirPDF = cam.img_plane_dist * cam.img_plane_dist / ((dirLocal.z * dirLocal.z * dirLocal.z) * rc.imgPlaneArea);
+    const V3 dir = f.fromLocal(dirLocal);
+    o->dir = dir;
+    o->weight = absDot(dir, lensN) / (rc.lensAreaPDF * dirPDF * rc.selectWLPDF);
+
+    // ImageSensor::add bins by the float pixel position
+    o->ipx = min((uint32_t)px, rc.width - 1); o->ipy = min((uint32_t)py, rc.height - 1);
+    uint32_t flags = kFlagCameraRay;
+    // wavelength i lands in stratum i unless the offset sits within rounding distance of 0 or 1:
+    // only then is the exact (16 x 2 IEEE divisions) test needed
+    if (NC == 16 && ((wlOffset > 1e-4f && wlOffset < 1.0f - 1e-4f) || strataInPlace(wlOffset))) flags |= kFlagStrataInPlace;
+    o->flags = flags;
+}
+
 // ---------------------------------------------------------------------------------------------
 // ray generation: fills the free tail of the current queue with fresh camera samples
 // ---------------------------------------------------------------------------------------------
@@ -65,36 +112,11 @@ raygenKernel(const DeviceScene s, const RenderConstants rc, PathQueue out, const
         const uint32_t pixel = y * rc.width + x;
         const uint32_t sample = rc.sppBegin + pass;
 
-        const Rand4 r0 = pathRandom(rc.seed, pixel, sample, 0);    // time, pixel x, pixel y, wavelength offset
-        const Rand4 r1 = pathRandom(rc.seed, pixel, sample, 1);    // wavelength selection, lens u0, lens u1
-        const float px = x + r0.y, py = y + r0.z;
-        const float wlOffset = r0.w;
-        const uint32_t hero = min((uint32_t)(NC * r1.x), (uint32_t)(NC - 1));
-
-        // PerspectiveCamera::sample
-        float lx, ly;
-        concentricSampleDisk(r1.y, r1.z, &lx, &ly);
-        const SlrGpuCamera& cam = s.camera;
-        const V3 orgLocal(cam.lens_radius * lx, cam.lens_radius * ly, 0.0f);
-        const V3 org = xfmPoint(cam.mat, orgLocal);
-        const V3 lensN = xfmNormal(cam.mat_inv, V3(0, 0, 1));
-        Frame f;
-        f.z = lensN;
-        f.x = xfmVector(cam.mat, V3(1, 0, 0));
-        f.y = cross(f.z, f.x);
-        // PerspectiveIDF::sample with (p.x / W, p.y / H)
-        const V3 pFocus(rc.opWidth * (0.5f - px / rc.width), rc.opHeight * (0.5f - py / rc.height), cam.obj_plane_dist);
-        const V3 dirLocal = normalize(pFocus - orgLocal);
-        const float dirPDF = cam.img_plane_dist * cam.img_plane_dist / ((dirLocal.z * dirLocal.z * dirLocal.z) * rc.imgPlaneArea);
-        const V3 dir = f.fromLocal(dirLocal);
-        const float weight = absDot(dir, lensN) / (rc.lensAreaPDF * dirPDF * rc.selectWLPDF);
-
-        // ImageSensor::add bins by the float pixel position
-        const uint32_t ipx = min((uint32_t)px, rc.width - 1), ipy = min((uint32_t)py, rc.height - 1);
-        uint32_t flags = kFlagCameraRay;
-        // wavelength i lands in stratum i unless the offset sits within rounding distance of 0 or 1:
-        // only then is the exact (16 x 2 IEEE divisions) test needed
-        if (NC == 16 && ((wlOffset > 1e-4f && wlOffset < 1.0f - 1e-4f) || strataInPlace(wlOffset))) flags |= kFlagStrataInPlace;
+        CameraSample cs;
+        sampleCamera<NC>(s, rc, x, y, pixel, sample, &cs);
+        const V3 org = cs.org, dir = cs.dir;
+        const float weight = cs.weight, wlOffset = cs.wlOffset;
+        const uint32_t ipx = cs.ipx, ipy = cs.ipy, hero = cs.hero, flags = cs.flags;
 
         const uint32_t pos = outBase + j;
         out.org[pos] = make_float4(org.x, org.y, org.z, 0.0f);
@@ -156,6 +178,45 @@ __global__ void __launch_bounds__(kMaterialBlock, materialMinBlocks(CLASS))
 materialKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitBuffer hits, ClassQueue cq, PathQueue out, ShadowQueue sq,
                WavefrontCounters* counters) {
     materialStage<NC, CLASS>(s, rc, in, hits, cq, out, sq, counters, counters->classCount[CLASS]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// debug (AOV) renderer: DebugRenderer::Job::kernel / contribution (libSLR/Renderers/DebugRenderer.cpp:132-217) -- one
+// camera sample per pixel, closest hit, Intersection::getSurfacePoint; what the reference quantises into its
+// geometric_normal / shading_normal / shading_tangent images is written as floats:
+//   out[pixel * SLRGPU_DEBUG_FLOATS + 0] = 1 hit / 0 miss, 1-3 geometric normal, 4-6 shading normal, 7-9 shading tangent
+// (a miss leaves the zero vectors of the reference's default-constructed DebugInfo)
+// ---------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(128)
+debugKernel(const DeviceScene s, const RenderConstants rc, float* __restrict__ out, uint32_t* stackOverflow) {
+    const uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pixel >= rc.numPixels) return;
+    const uint32_t x = pixel % rc.width, y = pixel / rc.width;
+    CameraSample cs;
+    sampleCamera<NC>(s, rc, x, y, pixel, rc.sppBegin, &cs);
+    uint32_t stack[kStackSize];
+    WalkState w;
+    w.r.ox = cs.org.x; w.r.oy = cs.org.y; w.r.oz = cs.org.z; w.r.tmin = 0.0f;
+    w.r.dx = cs.dir.x; w.r.dy = cs.dir.y; w.r.dz = cs.dir.z; w.r.tmax = INFINITY;
+    InstanceWalkState iw;
+    iw.leaves.clear(); iw.saved.clear(); iw.curInst = SLRGPU_INVALID_ID;
+    TraversalCounters cnt = {0, 0};
+    bool overflow = false;
+    walkBegin(w, stack);
+    while (!walkStep<true, false, false>(s, w, iw, stack, cnt, overflow)) { }
+    if (overflow) atomicExch(stackOverflow, 1u);
+    float* o = out + (size_t)(cs.ipy * rc.width + cs.ipx) * SLRGPU_DEBUG_FLOATS;
+#pragma unroll
+    for (int k = 0; k < SLRGPU_DEBUG_FLOATS; ++k) o[k] = 0.0f;
+    if (w.hit.prim == SLRGPU_INVALID_ID) return;
+    SurfPt sp;
+    float localArea;
+    hitSurfacePoint(s, w.hit.prim, w.hit.inst, w.hit.t, w.hit.u, w.hit.v, cs.org, cs.dir, &sp, &localArea);
+    o[0] = 1.0f;
+    o[1] = sp.gn.x; o[2] = sp.gn.y; o[3] = sp.gn.z;
+    o[4] = sp.sf.z.x; o[5] = sp.sf.z.y; o[6] = sp.sf.z.z;
+    o[7] = sp.sf.x.x; o[8] = sp.sf.x.y; o[9] = sp.sf.x.z;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -335,18 +396,13 @@ static void dumpWaveLog(const char* path, const ulonglong2* dLog, uint32_t n, co
     fclose(f);
 }
 
-static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorkspace& w, float* accumDev, cudaStream_t stream, SlrGpuRenderStats* stats) {
+static RenderConstants makeRenderConstants(const SlrGpuScene* sc, const SlrGpuRenderParams* p, uint32_t capacity) {
     const bool rgb = sc->channels == 3;
-    const uint32_t W = p->width, H = p->height;
-    const unsigned long long numPixels = (unsigned long long)W * H;
-    const unsigned long long totalSamples = numPixels * (p->spp_end - p->spp_begin);
-    const uint32_t P = w.capacity;
-
     RenderConstants rc;
     memset(&rc, 0, sizeof(rc));
-    rc.width = W; rc.height = H; rc.numPixels = (uint32_t)numPixels;
+    rc.width = p->width; rc.height = p->height; rc.numPixels = p->width * p->height;
     rc.sppBegin = p->spp_begin;
-    rc.capacity = P;
+    rc.capacity = capacity;
     rc.maxPathLength = p->max_path_length ? p->max_path_length : 100;
     rc.seed = (uint32_t)p->rng_seed;
     rc.timeStart = p->time_start; rc.timeEnd = p->time_end;
@@ -357,6 +413,17 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
     rc.lensAreaPDF = cam.lens_radius > 0.0f ? (float)(1.0f / (M_PI * cam.lens_radius * cam.lens_radius)) : 1.0f;
     rc.selectWLPDF = rgb ? 1.0f : 16.0f / (830.0f - 360.0f);
     rc.recBinWidth = rgb ? 1.0f : 16.0f / (830.0f - 360.0f);
+    return rc;
+}
+
+static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorkspace& w, float* accumDev, cudaStream_t stream, SlrGpuRenderStats* stats) {
+    const bool rgb = sc->channels == 3;
+    const uint32_t W = p->width, H = p->height;
+    const unsigned long long numPixels = (unsigned long long)W * H;
+    const unsigned long long totalSamples = numPixels * (p->spp_end - p->spp_begin);
+    const uint32_t P = w.capacity;
+
+    const RenderConstants rc = makeRenderConstants(sc, p, P);
 
     int rcode = SLRGPU_OK;
 
@@ -634,6 +701,41 @@ SLRGPU_API int slrgpu_render_device(SlrGpuScene* sc, const SlrGpuRenderParams* p
     return renderImpl(sc, p, *w, accumDev, (cudaStream_t)stream, stats);
 }
 
+SLRGPU_API int slrgpu_render_debug(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* out, SlrGpuRenderStats* stats) {
+    int rc = checkRenderArgs(sc, p);
+    if (rc) return rc;
+    if (!out) { setError("slrgpu_render_debug: null output buffer"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    SLRGPU_CUDA_TRY(cudaSetDevice(sc->device));
+    const uint32_t numPixels = p->width * p->height;
+    const size_t bytes = (size_t)numPixels * SLRGPU_DEBUG_FLOATS * sizeof(float);
+    struct Buffers { void* p[2] = {}; ~Buffers() { for (void* q : p) if (q) cudaFree(q); } } bufs;
+    SLRGPU_CUDA_TRY(cudaMalloc(&bufs.p[0], bytes));
+    SLRGPU_CUDA_TRY(cudaMalloc(&bufs.p[1], sizeof(uint32_t)));
+    SLRGPU_CUDA_TRY(cudaMemset(bufs.p[0], 0, bytes));
+    SLRGPU_CUDA_TRY(cudaMemset(bufs.p[1], 0, sizeof(uint32_t)));
+    const RenderConstants rcs = makeRenderConstants(sc, p, 0);
+    cudaEvent_t ev0, ev1;
+    SLRGPU_CUDA_TRY(cudaEventCreate(&ev0));
+    SLRGPU_CUDA_TRY(cudaEventCreate(&ev1));
+    struct EventFree { cudaEvent_t a, b; ~EventFree() { cudaEventDestroy(a); cudaEventDestroy(b); } } eventFree{ev0, ev1};
+    SLRGPU_CUDA_TRY(cudaEventRecord(ev0, 0));
+    const uint32_t grid = (numPixels + 127u) / 128u;
+    if (sc->channels == 3) debugKernel<3><<<grid, 128>>>(sc->dev, rcs, (float*)bufs.p[0], (uint32_t*)bufs.p[1]);
+    else debugKernel<16><<<grid, 128>>>(sc->dev, rcs, (float*)bufs.p[0], (uint32_t*)bufs.p[1]);
+    SLRGPU_CUDA_TRY(cudaGetLastError());
+    SLRGPU_CUDA_TRY(cudaEventRecord(ev1, 0));
+    SLRGPU_CUDA_TRY(cudaMemcpy(out, bufs.p[0], bytes, cudaMemcpyDeviceToHost));
+    uint32_t overflow = 0;
+    SLRGPU_CUDA_TRY(cudaMemcpy(&overflow, bufs.p[1], sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->paths = numPixels; stats->rays = numPixels; stats->extend_rays = numPixels; stats->kernel_launches = 1;
+        cudaEventElapsedTime(&stats->device_ms, ev0, ev1);
+    }
+    if (overflow) { setError("traversal stack overflow (more than %d entries)", 64); return SLRGPU_ERR_STACK_OVERFLOW; }
+    return SLRGPU_OK;
+}
+
 SLRGPU_API int slrgpu_render(SlrGpuScene* sc, const SlrGpuRenderParams* p, float* accum, SlrGpuRenderStats* stats) {
     int rc = checkRenderArgs(sc, p);
     if (rc) return rc;
@@ -648,9 +750,22 @@ SLRGPU_API int slrgpu_render(SlrGpuScene* sc, const SlrGpuRenderParams* p, float
     SLRGPU_CUDA_TRY(cudaMemsetAsync(w->frame, 0, bytes, w->stream));
     rc = renderImpl(sc, p, *w, w->frame, w->stream, stats);
     if (rc) return rc;
-    SLRGPU_CUDA_TRY(cudaMemcpyAsync(w->frameHost, w->frame, bytes, cudaMemcpyDeviceToHost, w->stream));
-    SLRGPU_CUDA_TRY(cudaStreamSynchronize(w->stream));
-    memcpy(accum, w->frameHost, bytes);
+    // device -> pinned staging -> the caller's (pageable) buffer, in pieces: the host copy of piece k runs while piece
+    // k + 1 is still on the bus
+    constexpr int kPieces = 8;
+    const size_t piece = ((bytes / kPieces) + 4095) & ~(size_t)4095;
+    int pieces = 0;
+    for (size_t off = 0; off < bytes && pieces < kPieces; off += piece, ++pieces) {
+        const size_t len = std::min(piece, bytes - off);
+        SLRGPU_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(w->frameHost) + off, reinterpret_cast<const char*>(w->frame) + off, len,
+                                        cudaMemcpyDeviceToHost, w->stream));
+        SLRGPU_CUDA_TRY(cudaEventRecord(w->ringEvents[pieces], w->stream));
+    }
+    for (int k = 0; k < pieces; ++k) {
+        const size_t off = (size_t)k * piece;
+        SLRGPU_CUDA_TRY(cudaEventSynchronize(w->ringEvents[k]));
+        memcpy(reinterpret_cast<char*>(accum) + off, reinterpret_cast<const char*>(w->frameHost) + off, std::min(piece, bytes - off));
+    }
     return SLRGPU_OK;
 }
 

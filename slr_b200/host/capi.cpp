@@ -168,6 +168,37 @@ SLRGPU_API int slrhost_render_range(SlrHostScene* s, int device, int width, int 
     } catch (const std::exception& e) { return fail("%s", e.what()); }
 }
 
+SLRGPU_API int slrhost_render_debug(SlrHostScene* s, int device, int width, int height, int seed,
+                                    const char* bmp_dir, float* out, double* stats) {
+    if (!s) return fail("slrhost_render_debug: null scene");
+    try {
+        if (!s->flat.hasCamera) return fail("the scene has no camera");
+        RenderSettings settings;
+        settings.addItem(RenderSettingItem::ImageWidth, (int32_t)(width > 0 ? width : s->context.width));
+        settings.addItem(RenderSettingItem::ImageHeight, (int32_t)(height > 0 ? height : s->context.height));
+        settings.addItem(RenderSettingItem::TimeStart, s->context.timeStart);
+        settings.addItem(RenderSettingItem::TimeEnd, s->context.timeEnd);
+        settings.addItem(RenderSettingItem::Brightness, s->context.brightness);
+        settings.addItem(RenderSettingItem::RNGSeed, (int32_t)(seed != 0 ? seed : s->context.rngSeed));
+        // the channels the scene file asked for, or all three when it selected another renderer
+        bool flags[GPUDebugRenderer::NumChannels] = {true, true, true, false};
+        if (const GPUDebugRenderer* chosen = dynamic_cast<const GPUDebugRenderer*>(s->context.renderer.get()))
+            for (int i = 0; i < GPUDebugRenderer::NumChannels; ++i) flags[i] = chosen->channels[i];
+        if (!bmp_dir) for (bool& f : flags) f = false;
+        GPUDebugRenderer renderer(flags);
+        renderer.device = device;
+        renderer.rawOutput = out;
+        if (bmp_dir) renderer.outputDirectory = bmp_dir;
+        renderer.render(s->render, settings);
+        if (stats) {
+            const RenderStatistics& st = renderer.lastStatistics;
+            stats[0] = (double)st.paths; stats[1] = (double)st.rays; stats[2] = st.deviceSeconds; stats[3] = st.wallSeconds;
+            stats[4] = st.uploadSeconds; stats[5] = SLRGPU_DEBUG_FLOATS;
+        }
+        return 0;
+    } catch (const std::exception& e) { return fail("%s", e.what()); }
+}
+
 SLRGPU_API int slrhost_save_bmp(const char* path, const float* accum, int width, int height, int channels, float scale, float sensitivity) {
     if (!path || !accum || width <= 0 || height <= 0) return fail("slrhost_save_bmp: invalid argument");
     try {

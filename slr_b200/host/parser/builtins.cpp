@@ -554,7 +554,24 @@ void registerBuiltins(Interpreter& in) {
                 return Value();
             });
         }
-        if (method == "debug") in.fail("the debug (AOV) renderer is outside the GPU hot path");
+        if (method == "debug") {
+            // API.cpp:1037-1062: ("outputs": ("geometric normal", "shading normal", "shading tangent", "distance"))
+            return withConfig(cfg, {{"outputs", Type::Tuple}}, in, [ctx, method](const Args& c, Interpreter&) {
+                const ParameterList& outputs = c.at("outputs").tuple();
+                bool flags[GPUDebugRenderer::NumChannels] = {false, false, false, false};
+                for (size_t i = 0; i < outputs.unnamed.size(); ++i) {
+                    const Value& e = outputs.unnamed[i];
+                    if (e.type != Type::String) continue;
+                    if (e.s == "geometric normal") flags[GPUDebugRenderer::GeometricNormal] = true;
+                    else if (e.s == "shading normal") flags[GPUDebugRenderer::ShadingNormal] = true;
+                    else if (e.s == "shading tangent") flags[GPUDebugRenderer::ShadingTangent] = true;
+                    else if (e.s == "distance") flags[GPUDebugRenderer::Distance] = true;
+                }
+                ctx->rendererMethod = method;
+                ctx->renderer.reset(new GPUDebugRenderer(flags));
+                return Value();
+            });
+        }
         in.fail("Unknown method is specified.");
     }));
     def(in, "setRenderSettings",

@@ -147,4 +147,53 @@ void GPUPathTracingRenderer::render(const RenderScene& scene, const RenderSettin
     lastStatistics.wallSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
 }
 
+void GPUDebugRenderer::render(const RenderScene& scene, const RenderSettings& settings) const {
+    auto wall0 = std::chrono::steady_clock::now();
+    const uint32_t W = (uint32_t)settings.getInt(RenderSettingItem::ImageWidth);
+    const uint32_t H = (uint32_t)settings.getInt(RenderSettingItem::ImageHeight);
+    lastStatistics = RenderStatistics();
+    SlrGpuSceneDesc desc;
+    scene.flat.describe(&desc);
+    SlrGpuScene* gpu = nullptr;
+    if (slrgpu_scene_create(&desc, device, &gpu) != SLRGPU_OK)
+        throw std::runtime_error(std::string("slrgpu_scene_create failed: ") + slrgpu_last_error());
+    SlrGpuRenderParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.struct_size = sizeof(p);
+    p.width = W; p.height = H;
+    p.spp_begin = 0; p.spp_end = 1;
+    p.time_start = settings.getFloat(RenderSettingItem::TimeStart);
+    p.time_end = settings.getFloat(RenderSettingItem::TimeEnd);
+    p.rng_seed = settings.getInt(RenderSettingItem::RNGSeed);
+    std::vector<float> own;
+    float* raw = rawOutput;
+    if (!raw) { own.resize((size_t)W * H * SLRGPU_DEBUG_FLOATS); raw = own.data(); }
+    SlrGpuRenderStats st;
+    const int rc = slrgpu_render_debug(gpu, &p, raw, &st);
+    std::string msg = rc == SLRGPU_OK ? std::string() : std::string("slrgpu_render_debug failed: ") + slrgpu_last_error();
+    slrgpu_scene_destroy(gpu);
+    if (rc != SLRGPU_OK) throw std::runtime_error(msg);
+    lastStatistics.paths = st.paths; lastStatistics.rays = st.rays;
+    lastStatistics.deviceSeconds = st.device_ms * 1e-3;
+
+    // DebugRenderer.cpp:156-183 + Image2D::saveImage (Image.cpp:310-341): (uint8)clamp((0.5 v + 0.5) * 255, 0, 255), bottom-up BGR rows
+    static const char* names[NumChannels] = {"geometric_normal.bmp", "shading_normal.bmp", "shading_tangent.bmp", "distance.bmp"};
+    const uint32_t rowBytes = 3 * W + W % 4;
+    for (int ch = 0; ch < 3; ++ch) {
+        if (!channels[ch]) continue;
+        std::vector<uint8_t> bmp((size_t)rowBytes * H, 0);
+        for (uint32_t y = 0; y < H; ++y)
+            for (uint32_t x = 0; x < W; ++x) {
+                const float* v = raw + ((size_t)y * W + x) * SLRGPU_DEBUG_FLOATS + 1 + 3 * ch;
+                uint8_t* dst = &bmp[(size_t)(H - y - 1) * rowBytes + 3 * x];
+                for (int c = 0; c < 3; ++c) {
+                    const float q = std::min(std::max((0.5f * v[c] + 0.5f) * 255, 0.0f), 255.0f);
+                    dst[2 - c] = (uint8_t)q;
+                }
+            }
+        saveBMP(outputDirectory + "/" + names[ch], bmp.data(), W, H);
+    }
+    lastStatistics.wallSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+}
+
 }  // namespace slr

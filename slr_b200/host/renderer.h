@@ -101,6 +101,23 @@ public:
     void render(const RenderScene& scene, const RenderSettings& settings) const override;
 };
 
+// The debug (AOV) renderer on the GPU: DebugRenderer (libSLR/Renderers/DebugRenderer.h/.cpp) -- one camera sample per
+// pixel, the hit's geometric normal / shading normal / shading tangent quantised into <outputDirectory>/
+// geometric_normal.bmp, shading_normal.bmp, shading_tangent.bmp like the reference's chImages. The "distance"
+// channel is SLRAssert_NotImplemented in the reference (DebugRenderer.cpp:187) and is ignored here too.
+class GPUDebugRenderer : public Renderer {
+public:
+    enum Channel { GeometricNormal = 0, ShadingNormal, ShadingTangent, Distance, NumChannels };
+    bool channels[NumChannels] = {false, false, false, false};
+    std::string outputDirectory = ".";
+    int device = 0;
+    mutable RenderStatistics lastStatistics;
+    // caller-owned buffer of width*height*SLRGPU_DEBUG_FLOATS floats that receives the raw vectors (optional)
+    float* rawOutput = nullptr;
+    explicit GPUDebugRenderer(const bool flags[NumChannels]) { for (int i = 0; i < NumChannels; ++i) channels[i] = flags[i]; }
+    void render(const RenderScene& scene, const RenderSettings& settings) const override;
+};
+
 struct RenderingContext {
     std::unique_ptr<Renderer> renderer;
     std::string rendererMethod;          // "PT", "BPT", "debug" as written in the scene file

@@ -55,3 +55,21 @@ def test_unsupported_builtin_fails_loudly(tmp_path):
     with pytest.raises(capi.SlrError, match="scanXZFromYPlus|cannot open|not defined"):
         with capi.stdout_to_stderr():
             capi.read_scene(str(tmp_path / "RTC3.txt"))
+
+
+def test_debug_renderer_is_selected_by_the_scene_language(tmp_path):
+    """setRenderer("method": "debug", ("outputs": (...),)) (API.cpp:1037-1062) builds the GPU debug renderer; an unknown
+    method still fails like the reference."""
+    from slr_b200 import scenes
+    path = scenes.SCENES["diffuse"](str(tmp_path), width=32, height=32, spp=1)
+    text = open(path).read()
+    dbg = os.path.join(str(tmp_path), "debug_scene.txt")
+    with open(dbg, "w") as f:
+        f.write(text + '\nsetRenderer("method": "debug", ("outputs": ("geometric normal", "shading normal"),));\n')
+    hs = capi.read_scene(dbg)
+    assert hs.context["hasRenderer"]
+    bad = os.path.join(str(tmp_path), "bad_scene.txt")
+    with open(bad, "w") as f:
+        f.write(text + '\nsetRenderer("method": "photon mapping");\n')
+    with pytest.raises(capi.SlrError, match="Unknown method"):
+        capi.read_scene(bad)

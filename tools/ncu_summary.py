@@ -85,7 +85,7 @@ def traffic(path, workload):
     fam = {}
     for k, t in read_launches(path).items():
         name = re.sub(r"<.*$", "", k)
-        if name.endswith("Kernel") and name[:-6] in ("extend", "shadow", "surface", "material", "raygen"):
+        if name.endswith("Kernel") and name[:-6] in ("extend", "shadow", "surface", "material", "raygen", "tail"):
             f = fam.setdefault(name, {"dram_bytes_per_frame": 0.0, "launches": 0, "kernel_ms_per_frame_under_ncu": 0.0})
             f["dram_bytes_per_frame"] += t[2]
             f["launches"] += t[0]
