@@ -257,7 +257,7 @@ def main(args, rank, world):
             traffic = t["dram_bytes_per_frame"]
     except (OSError, ValueError, KeyError):
         traffic = None
-    cpu = cpu_baseline(path, w, h, spp)
+    cpu = cpu_baseline(path, w, h, spp) if world == 1 else None      # the CPU leg runs at N = 1 only
     line = {"metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",

@@ -10,7 +10,7 @@ for src in (sys.argv[1:] or ["-"]):
         j = json.loads(line)
         c = j.get("config", {})
         print(f"{src}: {j.get('impl', 'b200')} n_gpus={j.get('n_gpus')} value={j['value']:.2f} {j['unit']} ms/step={j['ms_per_step']:.2f} "
-              f"e2e={j['e2e']['value']:.2f} cpu={j.get('cpu_baseline', {}).get('value')} launches={j.get('gpu_launches')}")
+              f"e2e={j['e2e']['value']:.2f} cpu={(j.get('cpu_baseline') or {}).get('value')} launches={j.get('gpu_launches')}")
         if "stage_ms_profiled_frame" in c:
             print("   stages:", c["stage_ms_profiled_frame"], "rays/path", round(c.get("rays_per_path", 0), 3), "Mrays/s", round(c.get("mrays_per_s", 0), 1))
             print("   traversal: extend nodes/ray", c.get("extend_nodes_per_ray"), "leafrec/ray", c.get("extend_leaf_records_per_ray"), "| shadow", c.get("shadow_nodes_per_ray"), c.get("shadow_leaf_records_per_ray"), "| pool", c.get("pool"), "waves", c.get("waves_per_frame"))
