@@ -750,6 +750,14 @@ SLRGPU_API int slrgpu_render(SlrGpuScene* sc, const SlrGpuRenderParams* p, float
     SLRGPU_CUDA_TRY(cudaMemsetAsync(w->frame, 0, bytes, w->stream));
     rc = renderImpl(sc, p, *w, w->frame, w->stream, stats);
     if (rc) return rc;
+    // a caller buffer that is page-locked (cudaHostAlloc / cudaHostRegister, e.g. a pinned framework tensor) takes the DMA directly
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, accum) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+        SLRGPU_CUDA_TRY(cudaMemcpyAsync(accum, w->frame, bytes, cudaMemcpyDeviceToHost, w->stream));
+        SLRGPU_CUDA_TRY(cudaStreamSynchronize(w->stream));
+        return SLRGPU_OK;
+    }
+    cudaGetLastError();
     // device -> pinned staging -> the caller's (pageable) buffer, in pieces: the host copy of piece k runs while piece
     // k + 1 is still on the bus
     constexpr int kPieces = 8;

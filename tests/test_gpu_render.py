@@ -118,6 +118,25 @@ def test_pool_size_and_rerun_do_not_change_the_image(workdir):
     assert ru.rel_rmse(other, big) > 0.05
 
 
+def test_tail_kernel_does_not_change_the_paths(workdir, monkeypatch):
+    """The persistent tail kernel (csrc/tail.cu) runs the last long paths of a call inside one launch instead of one
+    wave per bounce. Same RNG keys, same stage functions: identical path / ray / per-class hit counts, and an image that
+    differs from the all-waves image by fp32 summation order only. SLRGPU_TAIL_PATHS=0 switches the tail kernel off."""
+    path = ru.scene_file("spheres", workdir, 160, 160, 16)
+    hs = capi.read_scene(path)
+    gs = capi.GpuScene(hs)
+    with_tail, st_tail = capi.gpu_render(gs, 160, 160, 0, 16)
+    monkeypatch.setenv("SLRGPU_TAIL_PATHS", "0")
+    waves_only, st_waves = capi.gpu_render(gs, 160, 160, 0, 16)
+    monkeypatch.delenv("SLRGPU_TAIL_PATHS")
+    assert st_tail["tail_paths"] > 0 and st_waves["tail_paths"] == 0
+    assert st_tail["waves"] < st_waves["waves"]          # the length cap of 100 bounces is reached by a few specular paths
+    for k in ("paths", "rays", "extend_rays", "shadow_rays", "class_hits"):
+        assert st_tail[k] == st_waves[k], k
+    np.testing.assert_allclose(with_tail, waves_only, rtol=2e-4, atol=1e-5 * float(waves_only.mean()))
+    assert np.isfinite(with_tail).all()
+
+
 def test_rgb_mode_is_close_to_spectral(workdir):
     """RGB mode (references.h:45-60 without Use_Spectral_Representation) on the diffuse box: same light
     transport with 3 channels; colours differ slightly from the spectral render (no metamerism), means agree."""
