@@ -3,6 +3,10 @@
 // MUST be compiled with -fmad=false (see traverse.cuh).
 #define SLR_WALK_ONE_RECORD_PER_STEP 1      // measured faster for ray batches (traverse.cuh walkStep)
 #include "traverse.cuh"
+#include <algorithm>
+#include <cstring>
+#include <thread>
+#include <vector>
 
 namespace slrgpu {
 
@@ -111,6 +115,131 @@ static int uploadRays(DeviceBuffers& bufs, const SlrGpuRayBatch* rays, uint64_t 
     return SLRGPU_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer batches in pieces: pageable caller arrays -> pinned staging (several host threads) -> device -> kernel ->
+// pinned staging -> caller arrays, three pieces in flight, so the host copies of piece k + 1 run while piece k is on
+// the bus / in the kernel. The plain path (one cudaMemcpy per array, then the kernel, then the copies back) moved the
+// 3 GB of the 64 Mi-ray batch at ~11 GB/s: 279 ms around a 30 ms kernel. Staging and device buffers are pooled per
+// thread (slrgpu_release_workspaces frees nothing here; they live until the thread ends / the process exits).
+// ---------------------------------------------------------------------------------------------
+constexpr uint64_t kPieceRays = 1ull << 21;
+constexpr int kPiecesInFlight = 3;
+constexpr int kMaxOutputs = 7;
+
+struct BatchPipeline {
+    int device = -1;
+    float* hIn[kPiecesInFlight] = {};        // pinned [8][kPieceRays]
+    float* dIn[kPiecesInFlight] = {};
+    uint32_t* hOut[kPiecesInFlight] = {};    // pinned [kMaxOutputs][kPieceRays]
+    uint32_t* dOut[kPiecesInFlight] = {};
+    int* dStatus[kPiecesInFlight] = {};
+    cudaStream_t stream[kPiecesInFlight] = {};
+    cudaEvent_t done[kPiecesInFlight] = {}, k0[kPiecesInFlight] = {}, k1[kPiecesInFlight] = {};
+    int ensure(int dev) {
+        if (device == dev) return SLRGPU_OK;
+        if (device >= 0) { setError("slrgpu_intersect_batch: one device per calling thread"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+        for (int i = 0; i < kPiecesInFlight; ++i) {
+            SLRGPU_CUDA_TRY(cudaMallocHost(&hIn[i], 8 * kPieceRays * sizeof(float)));
+            SLRGPU_CUDA_TRY(cudaMallocHost(&hOut[i], kMaxOutputs * kPieceRays * sizeof(uint32_t)));
+            SLRGPU_CUDA_TRY(cudaMalloc(&dIn[i], 8 * kPieceRays * sizeof(float)));
+            SLRGPU_CUDA_TRY(cudaMalloc(&dOut[i], kMaxOutputs * kPieceRays * sizeof(uint32_t)));
+            SLRGPU_CUDA_TRY(cudaMalloc(&dStatus[i], 2 * sizeof(int)));
+            SLRGPU_CUDA_TRY(cudaMemset(dStatus[i], 0, 2 * sizeof(int)));
+            SLRGPU_CUDA_TRY(cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking));
+            SLRGPU_CUDA_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+            SLRGPU_CUDA_TRY(cudaEventCreate(&k0[i]));
+            SLRGPU_CUDA_TRY(cudaEventCreate(&k1[i]));
+        }
+        device = dev;
+        return SLRGPU_OK;
+    }
+};
+
+// copies `count` arrays of `len` 4-byte elements each, array a from src[a] to dst[a], split over a few host threads
+static void parallelCopy(void* const* dst, const void* const* src, int count, uint64_t len) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int threads = (int)std::min<unsigned>(8u, std::max(1u, hw / 2));
+    const uint64_t total = (uint64_t)count * len;
+    if (threads == 1 || total < (1u << 18)) { for (int a = 0; a < count; ++a) memcpy(dst[a], src[a], len * 4); return; }
+    auto work = [&](int t) {
+        // thread t copies the t-th slice of every array
+        const uint64_t b = len * t / threads, e = len * (t + 1) / threads;
+        for (int a = 0; a < count; ++a)
+            memcpy(static_cast<char*>(dst[a]) + b * 4, static_cast<const char*>(src[a]) + b * 4, (e - b) * 4);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (std::thread& th : pool) th.join();
+}
+
+static int intersectBatchPipelined(SlrGpuScene* scene, const SlrGpuRayBatch* rays, uint64_t n, const SlrGpuHitBatch* hits, float* kernel_ms) {
+    static thread_local BatchPipeline pipe;
+    int rc = pipe.ensure(scene->device);
+    if (rc != SLRGPU_OK) return rc;
+    const void* src[8] = {rays->org_x, rays->org_y, rays->org_z, rays->dir_x, rays->dir_y, rays->dir_z, rays->tmin, rays->tmax};
+    for (const void* p : src) if (!p) { setError("ray batch: null component array"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    // outputs in staging order: prim, inst, t, then the optional ones
+    void* out[kMaxOutputs] = {hits->prim, hits->inst, hits->t, hits->u, hits->v, hits->nodes_visited, hits->tris_tested};
+    const uint64_t pieces = (n + kPieceRays - 1) / kPieceRays;
+    float msTotal = 0.0f;
+    int overflow = 0;
+    auto pieceLen = [&](uint64_t k) { return std::min(kPieceRays, n - k * kPieceRays); };
+    // takes the results of piece k (slot k % kPiecesInFlight) back to the caller's arrays
+    auto retire = [&](uint64_t k) -> int {
+        const int sl = (int)(k % kPiecesInFlight);
+        SLRGPU_CUDA_TRY(cudaEventSynchronize(pipe.done[sl]));
+        const uint64_t len = pieceLen(k), off = k * kPieceRays;
+        void* dst[kMaxOutputs]; const void* from[kMaxOutputs];
+        int cnt = 0;
+        for (int a = 0; a < kMaxOutputs; ++a)
+            if (out[a]) { dst[cnt] = static_cast<uint32_t*>(out[a]) + off; from[cnt] = pipe.hOut[sl] + (uint64_t)a * kPieceRays; ++cnt; }
+        parallelCopy(dst, from, cnt, len);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, pipe.k0[sl], pipe.k1[sl]);
+        msTotal += ms;
+        return SLRGPU_OK;
+    };
+    for (uint64_t k = 0; k < pieces; ++k) {
+        const int sl = (int)(k % kPiecesInFlight);
+        if (k >= (uint64_t)kPiecesInFlight && (rc = retire(k - kPiecesInFlight))) return rc;
+        const uint64_t len = pieceLen(k), off = k * kPieceRays;
+        void* dst[8]; const void* from[8];
+        for (int a = 0; a < 8; ++a) { dst[a] = pipe.hIn[sl] + (uint64_t)a * kPieceRays; from[a] = static_cast<const float*>(src[a]) + off; }
+        parallelCopy(dst, from, 8, len);
+        cudaStream_t st = pipe.stream[sl];
+        if (len == kPieceRays) SLRGPU_CUDA_TRY(cudaMemcpyAsync(pipe.dIn[sl], pipe.hIn[sl], 8 * kPieceRays * sizeof(float), cudaMemcpyHostToDevice, st));
+        else for (int a = 0; a < 8; ++a)
+            SLRGPU_CUDA_TRY(cudaMemcpyAsync(pipe.dIn[sl] + (uint64_t)a * kPieceRays, pipe.hIn[sl] + (uint64_t)a * kPieceRays, len * sizeof(float), cudaMemcpyHostToDevice, st));
+        float* d = pipe.dIn[sl];
+        const SlrGpuRayBatch dr = {d, d + kPieceRays, d + 2 * kPieceRays, d + 3 * kPieceRays, d + 4 * kPieceRays, d + 5 * kPieceRays, d + 6 * kPieceRays, d + 7 * kPieceRays};
+        uint32_t* o = pipe.dOut[sl];
+        SlrGpuHitBatch dh = {};
+        dh.prim = o; dh.inst = o + kPieceRays; dh.t = reinterpret_cast<float*>(o + 2 * kPieceRays);
+        if (hits->u) dh.u = reinterpret_cast<float*>(o + 3 * kPieceRays);
+        if (hits->v) dh.v = reinterpret_cast<float*>(o + 4 * kPieceRays);
+        if (hits->nodes_visited) dh.nodes_visited = o + 5 * kPieceRays;
+        if (hits->tris_tested) dh.tris_tested = o + 6 * kPieceRays;
+        SLRGPU_CUDA_TRY(cudaEventRecord(pipe.k0[sl], st));
+        if ((rc = launchIntersect(scene, dr, len, dh, pipe.dStatus[sl], st))) return rc;
+        SLRGPU_CUDA_TRY(cudaEventRecord(pipe.k1[sl], st));
+        for (int a = 0; a < kMaxOutputs; ++a)
+            if (out[a]) SLRGPU_CUDA_TRY(cudaMemcpyAsync(pipe.hOut[sl] + (uint64_t)a * kPieceRays, o + (uint64_t)a * kPieceRays, len * 4, cudaMemcpyDeviceToHost, st));
+        SLRGPU_CUDA_TRY(cudaEventRecord(pipe.done[sl], st));
+    }
+    for (uint64_t k = pieces > (uint64_t)kPiecesInFlight ? pieces - kPiecesInFlight : 0; k < pieces; ++k)
+        if ((rc = retire(k))) return rc;
+    for (int sl = 0; sl < kPiecesInFlight; ++sl) {
+        int status = 0;
+        SLRGPU_CUDA_TRY(cudaMemcpy(&status, pipe.dStatus[sl], sizeof(int), cudaMemcpyDeviceToHost));
+        if (status) { overflow = 1; cudaMemset(pipe.dStatus[sl], 0, sizeof(int)); }
+    }
+    if (kernel_ms) *kernel_ms = msTotal;
+    if (overflow) { setError("traversal stack overflow (more than %d pending nodes)", kStackSize); return SLRGPU_ERR_STACK_OVERFLOW; }
+    return SLRGPU_OK;
+}
+
 }  // namespace slrgpu
 
 using namespace slrgpu;
@@ -143,6 +272,7 @@ SLRGPU_API int slrgpu_intersect_batch(SlrGpuScene* scene, const SlrGpuRayBatch* 
     if (kernel_ms) *kernel_ms = 0.0f;
     if (n == 0) return SLRGPU_OK;
     SLRGPU_CUDA_TRY(cudaSetDevice(scene->device));
+    if (n >= 2 * kPieceRays) return intersectBatchPipelined(scene, rays, n, hits, kernel_ms);
     DeviceBuffers bufs;
     SlrGpuRayBatch dr;
     int rc = uploadRays(bufs, rays, n, &dr);

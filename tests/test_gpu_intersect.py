@@ -116,3 +116,24 @@ def test_edge_cases_through_abi():
     r = gs.intersect(rays)
     assert list(r["prim"]) == [0, 0xFFFFFFFF, 0xFFFFFFFF] and r["t"][0] == 1.0
     assert gs.device_bytes >= 128 + 48
+
+
+def test_pipelined_host_batches_equal_plain_batches():
+    """Host-buffer batches of >= 4 Mi rays go through the piece-wise pipeline (pinned staging, three pieces in flight,
+    intersect.cu intersectBatchPipelined); smaller ones through the plain copy-launch-copy path. Same kernel, same
+    rays: the results must be identical bit for bit, counters and a ragged last piece included."""
+    pos, idx = synth.heightfield(96)
+    hs = ou.build_host_scene([(pos, idx)], [(0, 0, None)])
+    gs = capi.GpuScene(hs)
+    n = 2 * (1 << 21) + 777_777          # two full pieces and a ragged third
+    rays = synth.random_rays(n, pos.min(0), pos.max(0), seed=2024)
+    whole = gs.intersect(rays, counters=True)
+    cut = 3_000_000                      # both parts below the pipeline's threshold
+    for lo, hi in ((0, cut), (cut, n)):
+        part = gs.intersect({k: v[lo:hi] for k, v in rays.items()}, counters=True)
+        for k in ("prim", "inst", "nodes", "tris"):
+            assert np.array_equal(whole[k][lo:hi], part[k]), k
+        hit = part["prim"] != 0xFFFFFFFF
+        for k in ("t", "u", "v"):
+            assert np.array_equal(whole[k][lo:hi].view(np.uint32)[hit], part[k].view(np.uint32)[hit]), k
+    assert (whole["prim"] != 0xFFFFFFFF).mean() > 0.1
