@@ -151,8 +151,14 @@ __device__ __forceinline__ void evalUpsampledAll(const DeviceScene& s, const Ups
 #pragma unroll
     for (int i = 0; i < NC; ++i) out->v[i] = 0.0f;
     if (w.n == 0) return;
+    // always four points (the fourth with weight 0 on the three-point boundary cells): straight-line code, no inner trip count
     const float* sp[4];
-    for (int j = 0; j < 4; ++j) sp[j] = s.upsamplePoints + w.idx[j < w.n ? j : 0] * kUpPointStride + 4;
+    float wj[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        sp[j] = s.upsamplePoints + w.idx[j < w.n ? j : 0] * kUpPointStride + 4;
+        wj[j] = (j < w.n ? w.w[j] : 0.0f) * scale;
+    }
 #pragma unroll 4
     for (int i = 0; i < NC; ++i) {
         const float sBinF = ((float)i + wlOffset) * ((float)(kUpNumWl - 1) / 16.0f);
@@ -160,8 +166,12 @@ __device__ __forceinline__ void evalUpsampledAll(const DeviceScene& s, const Ups
         const uint32_t sNext = min(sBin + 1u, (uint32_t)(kUpNumWl - 1));
         const float t = sBinF - (float)sBin;
         float ret = 0.0f;
-        for (int j = 0; j < w.n; ++j) ret += w.w[j] * (__ldg(sp[j] + sBin) * (1 - t) + __ldg(sp[j] + sNext) * t);
-        out->v[i] = ret * scale;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = __ldg(sp[j] + sBin), b = __ldg(sp[j] + sNext);
+            ret = fmaf(wj[j], fmaf(t, b - a, a), ret);
+        }
+        out->v[i] = ret;
     }
 }
 
