@@ -277,7 +277,9 @@ def main(args, rank, world):
                          "kernel": dom, "peak_source": peak_src, "kernel_share_of_step": share,
                          "algorithmic_bytes_per_launch_set": algo[dom],
                          "note": "achieved = algorithmic bytes of all launches of the kernel family in one frame / their summed device time; "
-                                 "traffic = ncu dram__bytes_read+write summed over the same launches (profiles/traffic.json), bytes per frame"},
+                                 "traffic = ncu dram__bytes_read+write summed over the same launches (profiles/traffic.json), bytes per frame. "
+                                 "The algorithmic bytes of the ray kernels count every node / leaf-record fetch (SURVEY 8d); with a scene "
+                                 "that fits L1/L2 most of them never reach HBM, so frac can approach or pass 1 while traffic stays small"},
             "cpu_baseline": cpu,
             "e2e": {"value": paths_per_step * world / e2e_s / 1e6, "unit": "Mpaths/s",
                     "h2d_bytes_per_step": scene_bytes + (accum_bytes if world > 1 else 0),
