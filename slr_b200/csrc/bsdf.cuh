@@ -119,16 +119,18 @@ __device__ __forceinline__ float pow2(float x) { return x * x; }
 __device__ __forceinline__ float pow4(float x) { const float y = x * x; return y * y; }
 __device__ __forceinline__ float pow5(float x) { const float y = x * x; return y * y * x; }
 
+// The reference writes tan(acos(z)) (MicrofacetBSDF.cpp GGX::evaluate / evaluateSmithG1); tan^2 = (1 - z^2) / z^2 is the
+// same quantity without the two libm calls (ncu: they were 20 % of the rough-glass kernel's stall samples). The two forms
+// differ by rounding only where z -> 1, and there tan^2 is negligible against alpha^2 / against 1.
+__device__ __forceinline__ float tan2FromCos(float z) { return fmaxf(0.0f, 1.0f - z * z) / (z * z); }
 __device__ __forceinline__ float ggxD(float alpha, const V3& m) {
     if (m.z <= 0) return 0.0f;
-    const float theta_m = acosf(m.z);
-    const float tanTheta = tanf(theta_m);
-    return alpha * alpha / (kPi * pow4(m.z) * pow2(alpha * alpha + tanTheta * tanTheta));
+    return alpha * alpha / (kPi * pow4(m.z) * pow2(alpha * alpha + tan2FromCos(m.z)));
 }
 __device__ __forceinline__ float ggxSmithG1(float alpha, const V3& v, const V3& m) {
     const float chi = (dot(v, m) / v.z) > 0 ? 1.0f : 0.0f;
-    const float theta_v = acosf(fminf(fmaxf(v.z, -1.0f), 1.0f));
-    return chi * 2 / (1 + sqrtf(1 + pow2(alpha * tanf(theta_v))));
+    const float z = fminf(fmaxf(v.z, -1.0f), 1.0f);
+    return chi * 2 / (1 + sqrtf(1 + alpha * alpha * tan2FromCos(z)));
 }
 __device__ __forceinline__ float ggxPdfVisible(float alpha, const V3& v, const V3& m) {
     return ggxSmithG1(alpha, v, m) * absDot(v, m) * ggxD(alpha, m) / fabsf(v.z);
@@ -136,18 +138,21 @@ __device__ __forceinline__ float ggxPdfVisible(float alpha, const V3& v, const V
 // Heitz's visible-normal sampling as the reference implements it (doubles where it uses double literals)
 static __device__ __noinline__ float ggxSampleVisible(float alpha, const V3& v, float u0, float u1, V3* m, float* normalPDF) {
     V3 sv = normalize(V3(alpha * v.x, alpha * v.y, v.z));
-    float theta_sv = acosf(sv.z);
-    float phi_sv = atan2f(sv.y, sv.x);
-    if (sv.z > 0.99999f) { theta_sv = 0.0f; phi_sv = 0.0f; }
+    // theta_sv = acos(sv.z), phi_sv = atan2(sv.y, sv.x) in the reference; only tan(theta), cos(phi), sin(phi) and the test
+    // theta < 1e-4 are used, all of which come from sv's components without the libm calls
+    float sinTheta = sqrtf(fmaxf(0.0f, 1.0f - sv.z * sv.z));
+    const float lenXY = sqrtf(sv.x * sv.x + sv.y * sv.y);
+    float cp = lenXY > 0.0f ? sv.x / lenXY : 1.0f, sp = lenXY > 0.0f ? sv.y / lenXY : 0.0f;
+    if (sv.z > 0.99999f) { sinTheta = 0.0f; cp = 1.0f; sp = 0.0f; }
     float slope_x, slope_y;
-    if (theta_sv < 0.0001f) {
+    if (sinTheta < 0.0001f && sv.z > 0.0f) {
         const float r = sqrtf(u0 / (1 - u0));
         const float phi = 2 * kPi * u1;
         float s, c;
         sincosf(phi, &s, &c);
         slope_x = r * c; slope_y = r * s;
     } else {
-        const float tan_theta_i = tanf(theta_sv);
+        const float tan_theta_i = sinTheta / sv.z;
         const float a = 1 / tan_theta_i;
         const float G1 = 2 / (1 + sqrtf(1.0f + 1.0f / (a * a)));
         const float A = 2.0f * u0 / G1 - 1.0f;
@@ -164,8 +169,6 @@ static __device__ __noinline__ float ggxSampleVisible(float alpha, const V3& v, 
         const float z = (u1 * (u1 * (u1 * 0.27385f - 0.73369f) + 0.46341f)) / (u1 * (u1 * (u1 * 0.093073f + 0.309420f) - 1.000000f) + 0.597999f);
         slope_y = S * z * sqrtf(1.0f + slope_x * slope_x);
     }
-    float sp, cp;
-    sincosf(phi_sv, &sp, &cp);
     const float tmp = cp * slope_x - sp * slope_y;
     slope_y = sp * slope_x + cp * slope_y;
     slope_x = tmp;
