@@ -1,6 +1,6 @@
 """Hot source lines of one captured kernel: joins the SASS page of an ncu report (warp-stall samples per
 instruction) with nvdisasm's line table of the same kernel in the built object (needs -lineinfo).
-  python tools/ncu_hot_lines.py <file.ncu-rep> <kernel name substring, demangled> <object.o> <mangled-name substring> [top N]
+  python tools/ncu_hot_lines.py <file.ncu-rep> <kernel name substring, demangled>[#k-th launch] <object.o> <mangled-name substring> [top N]
 """
 import csv
 import io
@@ -18,7 +18,9 @@ def main():
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
-    idx = next(k for k, i in enumerate(starts[:-1]) if want in rows[i][1])
+    want, _, nth = want.partition("#")              # "kernelName#k": the k-th captured launch of that kernel (0-based)
+    matches = [k for k, i in enumerate(starts[:-1]) if want in rows[i][1]]
+    idx = matches[2 * int(nth or 0)]                # every launch has two sections (SASS, then the same with source markers)
     rows = rows[starts[idx]:starts[idx + 1]]           # the first captured launch of that kernel
     hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     cols = {n: i for i, n in enumerate(rows[hdr])}
