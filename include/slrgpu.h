@@ -358,7 +358,7 @@ typedef struct SlrGpuRenderParams {
     float time_start, time_end;
     int32_t rng_seed;
     uint32_t max_path_length;        /* 0 = reference default (100, PathTracingRenderer.cpp:162) */
-    uint32_t pool_size;              /* paths in flight; 0 = default */
+    uint32_t pool_size;              /* paths in flight (about 440 B of device memory each); 0 = default (16 Mi) */
     uint32_t flags;
 } SlrGpuRenderParams;
 
