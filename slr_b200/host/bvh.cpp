@@ -1,6 +1,7 @@
 #include "bvh.h"
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <future>
 #include <stdexcept>
 #include <thread>
@@ -137,8 +138,12 @@ struct Builder {
     const BBox sceneBounds;
     const int maxThreads;
 
-    Builder(const PrimitiveSet& p, const BBox& b)
-        : ps(p), sceneBounds(b), maxThreads((int)std::max(1u, std::thread::hardware_concurrency())) {}
+    // SLRHOST_BUILD_THREADS=n caps the builder's threads (1 = the serial recursion; tests compare the two)
+    static int threadLimit() {
+        if (const char* e = std::getenv("SLRHOST_BUILD_THREADS")) { const int n = std::atoi(e); if (n >= 1) return n; }
+        return (int)std::max(1u, std::thread::hardware_concurrency());
+    }
+    Builder(const PrimitiveSet& p, const BBox& b) : ps(p), sceneBounds(b), maxThreads(threadLimit()) {}
 
     static uint32_t binOf(uint32_t numBins, float v, float lo, float hi) {
         uint32_t b = (uint32_t)(numBins * ((v - lo) / (hi - lo)));
@@ -149,7 +154,7 @@ struct Builder {
     void buildChildren(std::vector<Fragment>&& lefts, std::vector<Fragment>&& rights, uint32_t depth, Axis axis, const BBox& box,
                        uint32_t nodeIdx, SubTree& out) {
         uint32_t c0, c1;
-        const bool parallel = lefts.size() + rights.size() >= kParallelMin && g_buildThreads.load(std::memory_order_relaxed) < maxThreads;
+        const bool parallel = maxThreads > 1 && lefts.size() + rights.size() >= kParallelMin && g_buildThreads.load(std::memory_order_relaxed) < maxThreads;
         if (!parallel) {
             c0 = recurse(std::move(lefts), depth, out);
             c1 = recurse(std::move(rights), depth, out);

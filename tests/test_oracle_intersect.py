@@ -105,3 +105,22 @@ def test_empty_and_degenerate_inputs():
     b = capi.SceneBuilder()
     with pytest.raises(capi.SlrError):
         b.finish()
+
+
+def test_parallel_tree_build_equals_serial_build(monkeypatch):
+    """The host SBVH builder hands subtrees above 32 k fragments to other threads and splices the results in pre-order
+    (host/bvh.cpp). Whatever the thread count, the tree must be the same tree: SLRHOST_BUILD_THREADS=1 (plain
+    recursion) against the default, on a mesh large enough for several levels of parallel nodes, spatial splits included."""
+    import slr_b200.synth as synth
+    pos, idx = synth.heightfield(300)            # 180 000 triangles
+    monkeypatch.setenv("SLRHOST_BUILD_THREADS", "1")
+    serial = ou.split_trees(ou.build_host_scene([(pos, idx)], [(0, 0, None)]))
+    monkeypatch.setenv("SLRHOST_BUILD_THREADS", "8")
+    threaded = ou.split_trees(ou.build_host_scene([(pos, idx)], [(0, 0, None)]))
+    monkeypatch.delenv("SLRHOST_BUILD_THREADS")
+    default = ou.split_trees(ou.build_host_scene([(pos, idx)], [(0, 0, None)]))
+    for other in (threaded, default):
+        assert len(other) == len(serial) == 1
+        assert np.array_equal(other[0]["nodes"], serial[0]["nodes"])
+        assert np.array_equal(other[0]["refs"], serial[0]["refs"])
+        assert other[0]["sbvh_cost"] == serial[0]["sbvh_cost"] and other[0]["qbvh_cost"] == serial[0]["qbvh_cost"]
