@@ -126,6 +126,7 @@ static int uploadRays(DeviceBuffers& bufs, const SlrGpuRayBatch* rays, uint64_t 
 constexpr uint64_t kPieceRays = 1ull << 21;
 constexpr int kPiecesInFlight = 3;
 constexpr int kMaxOutputs = 7;
+constexpr int kMaxPipelineDevices = 16;
 
 struct BatchPipeline {
     int device = -1;
@@ -138,7 +139,6 @@ struct BatchPipeline {
     cudaEvent_t done[kPiecesInFlight] = {}, k0[kPiecesInFlight] = {}, k1[kPiecesInFlight] = {};
     int ensure(int dev) {
         if (device == dev) return SLRGPU_OK;
-        if (device >= 0) { setError("slrgpu_intersect_batch: one device per calling thread"); return SLRGPU_ERR_INVALID_ARGUMENT; }
         for (int i = 0; i < kPiecesInFlight; ++i) {
             SLRGPU_CUDA_TRY(cudaMallocHost(&hIn[i], 8 * kPieceRays * sizeof(float)));
             SLRGPU_CUDA_TRY(cudaMallocHost(&hOut[i], kMaxOutputs * kPieceRays * sizeof(uint32_t)));
@@ -175,7 +175,8 @@ static void parallelCopy(void* const* dst, const void* const* src, int count, ui
 }
 
 static int intersectBatchPipelined(SlrGpuScene* scene, const SlrGpuRayBatch* rays, uint64_t n, const SlrGpuHitBatch* hits, float* kernel_ms) {
-    static thread_local BatchPipeline pipe;
+    static thread_local BatchPipeline pipes[kMaxPipelineDevices];      // one per device this thread has used
+    BatchPipeline& pipe = pipes[scene->device];
     int rc = pipe.ensure(scene->device);
     if (rc != SLRGPU_OK) return rc;
     const void* src[8] = {rays->org_x, rays->org_y, rays->org_z, rays->dir_x, rays->dir_y, rays->dir_z, rays->tmin, rays->tmax};
@@ -272,7 +273,7 @@ SLRGPU_API int slrgpu_intersect_batch(SlrGpuScene* scene, const SlrGpuRayBatch* 
     if (kernel_ms) *kernel_ms = 0.0f;
     if (n == 0) return SLRGPU_OK;
     SLRGPU_CUDA_TRY(cudaSetDevice(scene->device));
-    if (n >= 2 * kPieceRays) return intersectBatchPipelined(scene, rays, n, hits, kernel_ms);
+    if (n >= 2 * kPieceRays && scene->device >= 0 && scene->device < kMaxPipelineDevices) return intersectBatchPipelined(scene, rays, n, hits, kernel_ms);
     DeviceBuffers bufs;
     SlrGpuRayBatch dr;
     int rc = uploadRays(bufs, rays, n, &dr);
