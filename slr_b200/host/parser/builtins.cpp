@@ -5,6 +5,7 @@
 #include "interp.h"
 #include "../assets/assbin.h"
 #include "../assets/images.h"
+#include "../raycast.h"
 #include <cmath>
 #include <iostream>
 
@@ -22,6 +23,30 @@ FunctionRef fn(const std::vector<ArgInfo>& sig, const Function::Native& body) { 
 FunctionRef fnOver(const std::vector<std::vector<ArgInfo>>& sigs, const std::vector<Function::Native>& bodies) {
     return std::make_shared<Function>(sigs, bodies);
 }
+// XORShiftRNG (libSLR/RNGs/XORShiftRNG.cpp:21-37, RandomNumberGenerator.cpp:12-15). The seed is a SIGNED 32-bit integer in the
+// reference's seeding loop, so `seed >> 30` is an arithmetic shift once an intermediate state has its top bit set.
+struct XorShift128 {
+    uint32_t s[4];
+    explicit XorShift128(int32_t seed) {
+        for (uint32_t i = 0; i < 4; ++i) {
+            s[i] = 1812433253U * (uint32_t)(seed ^ (seed >> 30)) + i;
+            seed = (int32_t)s[i];
+        }
+        for (int i = 0; i < 50; ++i) next();
+    }
+    uint32_t next() {
+        const uint32_t t = s[0] ^ (s[0] << 11);
+        s[0] = s[1]; s[1] = s[2]; s[2] = s[3];
+        return s[3] = (s[3] ^ (s[3] >> 19)) ^ (t ^ (t >> 8));
+    }
+    float float0cTo1o() {
+        const uint32_t bits = (next() >> 9) | 0x3f800000u;
+        float v;
+        std::memcpy(&v, &bits, 4);
+        return v - 1.0f;
+    }
+};
+
 void def(Interpreter& in, const char* name, const FunctionRef& f) { in.defineGlobal(name, Value::Ref(Type::Function, f)); }
 
 // Runs a nested "configuration" signature over a tuple (the reference's configFunc pattern).
@@ -215,19 +240,8 @@ void registerBuiltins(Interpreter& in) {
     };
     def(in, "getX", getter(0)); def(in, "getY", getter(1)); def(in, "getZ", getter(2));
     def(in, "random", fn({}, [](const Args&, Interpreter&) {
-        // xorshift128 seeded with 2112984105, as the reference's static generator (API.cpp:238-244)
-        static uint32_t s[4];
-        static bool init = false;
-        if (!init) {
-            uint32_t seed = 2112984105u;
-            for (uint32_t i = 0; i < 4; ++i) s[i] = seed = 1812433253U * (seed ^ (seed >> 30)) + i;
-            init = true;
-            for (int i = 0; i < 50; ++i) { uint32_t t = s[0] ^ (s[0] << 11); s[0] = s[1]; s[1] = s[2]; s[2] = s[3]; s[3] = (s[3] ^ (s[3] >> 19)) ^ (t ^ (t >> 8)); }
-        }
-        uint32_t t = s[0] ^ (s[0] << 11); s[0] = s[1]; s[1] = s[2]; s[2] = s[3]; s[3] = (s[3] ^ (s[3] >> 19)) ^ (t ^ (t >> 8));
-        uint32_t bits = (s[3] >> 9) | 0x3f800000u;
-        float v; std::memcpy(&v, &bits, 4);
-        return Value::Real(v - 1.0f);
+        static XorShift128 rng(2112984105);      // the reference's static generator (API.cpp:238-244)
+        return Value::Real(rng.float0cTo1o());
     }));
 
     // ---- math (BuiltinFunctions/builtin_math.cpp)
@@ -515,6 +529,50 @@ void registerBuiltins(Interpreter& in) {
         }
         def(in, "addChild", fnOver(sigs, bodies));
     }
+    // scanXZFromYPlus (API.cpp:926-983): a numX x numY grid of rays straight down onto `node` from 1.5 x the top of its bounds;
+    // `callback(position, tangent, bitangent, normal)` runs for every hit (RTC3*.txt scatter grass instances with it). The
+    // subtree is flattened and its SBVH -> QBVH built on the spot, the rays are cast on the host (host/raycast.cpp).
+    def(in, "scanXZFromYPlus", fn({{"node", Type::Node}, {"numX", Type::Integer}, {"numY", Type::Integer}, {"randomness", R, Value::Real(0.0)},
+                                   {"callback", Type::Function}}, [](const Args& a, Interpreter& in) -> Value {
+        InternalNodeRef node = a.at("node").as<InternalNode>();
+        const int numX = a.at("numX").i, numY = a.at("numY").i;
+        const float randomness = f(a, "randomness");
+        FunctionRef callback = a.at("callback").as<Function>();
+        XorShift128 rng(50287412);
+        FlatScene flat;
+        GpuSceneBuilder b(flat);
+        RenderingData data;
+        node->resetFlattening();
+        struct Reset { Node* n; ~Reset() { n->resetFlattening(); } } reset{node.get()};
+        node->getRenderingData(b, nullptr, &data);
+        if (data.objects.empty()) in.fail("scanXZFromYPlus: the node has no surfaces");
+        const uint32_t top = b.createAggregate(std::move(data.objects));
+        const BBox bounds = b.aggregates[top].sbvh.bounds;
+        b.finalize(top);
+        HostRayCaster caster(flat);
+        for (int i = 0; i < numY; ++i) {
+            for (int j = 0; j < numX; ++j) {
+                const float purturbX = randomness * (rng.float0cTo1o() - 0.5f);
+                const float purturbZ = randomness * (rng.float0cTo1o() - 0.5f);
+                const Vec3 org(bounds.lo.x + (bounds.hi.x - bounds.lo.x) * (j + 0.5f + purturbX) / numX,
+                               bounds.hi.y * 1.5f,
+                               bounds.lo.z + (bounds.hi.z - bounds.lo.z) * (i + 0.5f + purturbZ) / numY);
+                const Vec3 dir(0, -1, 0);
+                HostHit hit;
+                if (!caster.intersect(org, dir, 0.0f, INFINITY, &hit)) continue;
+                HostSurfacePoint sp;
+                caster.surfacePoint(hit, org, dir, &sp);
+                ParameterList params;
+                params.add("", Value::Vec(Type::Point, sp.p));
+                params.add("", Value::Vec(Type::Vector, sp.sx));
+                params.add("", Value::Vec(Type::Vector, sp.sy));
+                params.add("", Value::Vec(Type::Normal, sp.sz));
+                Value r = callback->call(params, in);
+                if (r.isError()) in.fail(r.s);
+            }
+        }
+        return Value();
+    }));
     def(in, "load3DModel", fn({{"path", Type::String}, {"matProc", Type::Function, Value::Ref(Type::Function, FunctionRef())}}, [](const Args& a, Interpreter& in) -> Value {
         const std::string path = in.sceneDir + a.at("path").s;
         const std::string prefix = path.substr(0, path.find_last_of('/') + 1);

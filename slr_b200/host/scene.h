@@ -58,6 +58,10 @@ public:
     virtual bool isInstanced() const { return false; }
     // `subTF` is the accumulated parent transform or null (nodes.cpp:110-141).
     virtual void getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) = 0;
+    // A flattening pass marks the nodes it has visited (a mesh reachable twice is an error, an instanced subtree is built once);
+    // this clears the marks so that the subtree can be flattened again by another pass (scanXZFromYPlus flattens a subtree while
+    // the scene is still being written; Scene::build flattens everything later).
+    virtual void resetFlattening() {}
 };
 typedef std::shared_ptr<Node> NodeRef;
 
@@ -70,6 +74,7 @@ public:
     const StaticTransform& getTransform() const { return m_localToWorld; }
     const std::vector<NodeRef>& children() const { return m_children; }
     void getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) override;
+    void resetFlattening() override { for (const NodeRef& c : m_children) c->resetFlattening(); }
 };
 typedef std::shared_ptr<InternalNode> InternalNodeRef;
 
@@ -92,6 +97,7 @@ public:
     const std::vector<Vertex>& vertices() const { return m_vertices; }
     const std::vector<MaterialGroup>& groups() const { return m_groups; }
     void getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) override;
+    void resetFlattening() override { m_flattened = false; }
 };
 typedef std::shared_ptr<TriangleMeshNode> TriangleMeshNodeRef;
 
@@ -103,6 +109,7 @@ public:
     explicit ReferenceNode(const NodeRef& n) : m_node(n) {}
     bool isInstanced() const override { return true; }
     void getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) override;
+    void resetFlattening() override { m_ready = false; m_aggregate = 0; m_node->resetFlattening(); }
 };
 
 class CameraNode : public Node {

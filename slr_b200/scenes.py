@@ -388,6 +388,91 @@ def _small_instanced(directory, width=128, height=128, spp=64):
     return write_instanced(directory, width, height, spp, base_segments=(48, 24), grid=4)
 
 
+def write_scatter(directory, width=128, height=128, spp=64, grid=14):
+    """The structure of TestScenes/RTC3.txt at a small scale: a terrain mesh, grid x grid instances of a tuft mesh scattered
+    over it by scanXZFromYPlus (a ray cast while the file is read; the callback aligns each instance with the surface normal
+    and turns it by random()), the reference's two-sided grass material (sum of a matte lobe and an inverse matte lobe),
+    an Ashikhmin object, all lit by the synthetic HDR environment; the root rotated as in RTC3.txt."""
+    os.makedirs(os.path.join(directory, "models"), exist_ok=True)
+    os.makedirs(os.path.join(directory, "images"), exist_ok=True)
+    capi.write_exr(os.path.join(directory, "images", "sky.exr"), synth.sky_environment(512, 256))
+    pos, idx = synth.heightfield(24)
+    p = pos.astype(np.float64)
+    fn = np.cross(p[idx[:, 1]] - p[idx[:, 0]], p[idx[:, 2]] - p[idx[:, 0]])
+    acc = np.zeros_like(p)
+    for k in range(3):
+        np.add.at(acc, idx[:, k], fn)
+    nrm = (acc / np.linalg.norm(acc, axis=1, keepdims=True)).astype(np.float32)
+    tng = np.tile(np.array([1, 0, 0], np.float32), (pos.shape[0], 1))
+    capi.write_assbin(os.path.join(directory, "models", "plain.assbin"), pos, idx, nrm, tng, np.ascontiguousarray(pos[:, [0, 2]], np.float32),
+                      material_name="plain", diffuse=(0.35, 0.3, 0.2))
+    bp, bi, bn, bt, buv = synth.displaced_sphere(16, 8)
+    capi.write_assbin(os.path.join(directory, "models", "tuft.assbin"), bp * np.array([0.35, 1.0, 0.35], np.float32) + np.array([0, 1.0, 0], np.float32),
+                      bi, bn, bt, buv, material_name="tuft", diffuse=(0.15, 0.35, 0.1))
+    cp, ci, cn, ct, cuv = synth.displaced_sphere(32, 16)
+    capi.write_assbin(os.path.join(directory, "models", "toy.assbin"), cp, ci, cn, ct, cuv, material_name="toy", diffuse=(0.5, 0.1, 0.1))
+    t = f'setRenderer("method": "PT", ("samples": {spp},));\nsetRenderSettings("width": {width}, "height": {height}, "brightness": 2.0);\n'
+    t += 'setEnvironment("images/sky.exr");\n\n'
+    t += f"""function plainMaterial(name, attrs) {{
+    difCol = attrs["diffuse color"];
+    return createSurfaceMaterial("matte", (SpectrumTexture(Spectrum(difCol[0], difCol[1], difCol[2])),));
+}}
+plain = load3DModel("models/plain.assbin", plainMaterial);
+setTransform(plain, translate(-1.0, 0.0, -1.0) * scale(2.0, 1.5, 2.0));
+addChild(root, plain);
+
+function grassMaterial(name, attrs) {{
+    difCol = attrs["diffuse color"];
+    baseColor = Spectrum("Reflectance", "sRGB", 2 * difCol[0], 2 * difCol[1], 2 * difCol[2]);
+    r = createSurfaceMaterial("matte", (SpectrumTexture(baseColor * 0.7),));
+    tBase = createSurfaceMaterial("matte", (SpectrumTexture(baseColor * 0.3),));
+    t = createSurfaceMaterial("inverse", (tBase,));
+    return createSurfaceMaterial("sum", (r, t));
+}}
+grass = load3DModel("models/tuft.assbin", grassMaterial);
+grassReference = createReferenceNode(grass);
+
+function scanCallback(p, t, b, n) {{
+    trans = translate(getX(p), getY(p), getZ(p));
+    axis = cross(Vector(0, 1, 0), n);
+    angle = acos(clamp(dot(Vector(0, 1, 0), n), -1, 1));
+    if (angle < 0.0001)
+        axis = Vector(1, 0, 0);
+    rot = rotate(angle, axis);
+    sc = scale(0.06);
+    rotY = rotateY(2 * 3.1415926536 * random());
+    instanceNode = createNode();
+    addChild(instanceNode, grassReference);
+    setTransform(instanceNode, trans * rot * sc * rotY);
+    addChild(root, instanceNode);
+}}
+scanXZFromYPlus(plain, {grid}, {grid}, 0.6, scanCallback);
+
+function toyMaterial(name, attrs) {{
+    difCol = attrs["diffuse color"];
+    RdTex = SpectrumTexture(Spectrum(1.5 * difCol[0], 1.5 * difCol[1], 1.5 * difCol[2]));
+    RsTex = SpectrumTexture(Spectrum("type": "Reflectance", 0.025));
+    nxTex = nyTex = FloatTexture(100.0);
+    return createSurfaceMaterial("Ashikhmin", (RdTex, RsTex, nxTex, nyTex));
+}}
+toy = load3DModel("models/toy.assbin", toyMaterial);
+setTransform(toy, translate(0.1, 0.45, 0.2) * rotateY(0.7) * scale(0.22));
+addChild(root, toy);
+
+cameraNode = createNode();
+camera = createPerspectiveCamera("aspect": {width / height:.6f}, "fovY": 0.6, "radius": 0.0025, "imgDist": 1.0, "objDist": 3.0);
+addChild(cameraNode, camera);
+setTransform(cameraNode, translate(0.0, 1.6, 2.9) * rotateY(3.1415926536) * rotateX(0.45));
+addChild(root, cameraNode);
+
+setTransform(root, rotateY(-1.5707963268));
+"""
+    path = os.path.join(directory, "Scatter.txt")
+    with open(path, "w") as f:
+        f.write(t)
+    return path
+
+
 SCENES = {
     "diffuse": write_cornell_diffuse,
     "spheres": write_cornell_spheres,
@@ -395,6 +480,7 @@ SCENES = {
     "ibl": lambda d, width=1024, height=1024, spp=256: write_ibl_test(d, width, height, spp, env_size=(512, 256)),
     "ibl_full": write_ibl_test,
     "instanced": _small_instanced,
+    "scatter": write_scatter,
     "instanced_full": write_instanced,
     "instanced_10m": lambda d, width=1920, height=1080, spp=1024: write_instanced(d, width, height, spp, base_segments=(318, 159)),
 }

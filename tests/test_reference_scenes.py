@@ -1,7 +1,7 @@
 """CPU: the reference's own TestScenes/*.txt are read UNCHANGED by the host scene language (north_star: "TestScenes/*.txt
 render unchanged"). Runs only where /root/reference is mounted (the files are copied to a temp directory at test time and
 never into this repository); the models / environment maps they load are replaced by synthetic assets because the
-reference does not ship them (README.md:69-72)."""
+reference does not ship them (README.md:69-72). All seven shipped scene files are covered."""
 import os
 import re
 import shutil
@@ -18,7 +18,11 @@ EXPECT = {
     "Cornell_Box_ColorChecker.txt": (1024, 1024, 16384, 4.0),
     "Cornell_Box_ColorChecker_OverrideMaterial.txt": (1024, 1024, 512, 4.0),
     "IBL_Test.txt": (1024, 1024, 16384, 4.0),
+    # environment-lit, 60 x 60 grass instances scattered by scanXZFromYPlus (a host ray cast while the file is read)
+    "RTC3.txt": (1920, 1080, 16384, 2.0),
+    "RTC3_pika.txt": (1920, 1080, 16384, 2.0),
 }
+ENV_LIT = {"IBL_Test.txt", "RTC3.txt", "RTC3_pika.txt"}
 
 
 @pytest.mark.skipif(not os.path.isdir(SRC), reason="the reference is not mounted on this machine")
@@ -42,19 +46,22 @@ def test_reference_scene_file_reads_unchanged(name, tmp_path):
     w, h, spp, brightness = EXPECT[name]
     c = hs.context
     assert (c["width"], c["height"], c["samples"]) == (w, h, spp) and c["brightness"] == brightness and c["hasRenderer"]
-    assert hs.desc.num_triangles >= 60 and hs.desc.num_materials >= 8 and hs.desc.num_lights >= (0 if "IBL" in name else 2)
-    assert bool(hs.desc.environment.present) == ("IBL" in name)
+    assert hs.desc.num_triangles >= 60 and hs.desc.num_materials >= 8 and hs.desc.num_lights >= (0 if name in ENV_LIT else 2)
+    assert bool(hs.desc.environment.present) == (name in ENV_LIT)
+    if name.startswith("RTC3"):
+        assert hs.desc.num_instances > 1000        # the scan's hits, one grass instance each
     assert hs.desc.camera.obj_plane_dist > 0
 
 
-@pytest.mark.skipif(not os.path.isdir(SRC), reason="the reference is not mounted on this machine")
-def test_unsupported_builtin_fails_loudly(tmp_path):
-    """RTC3*.txt scatter instances with scanXZFromYPlus (a CPU ray cast during scene construction, API.cpp:926-983),
-    which this host library does not provide: reading them must fail with a message, not build a wrong scene."""
-    shutil.copy(os.path.join(SRC, "RTC3.txt"), str(tmp_path / "RTC3.txt"))
-    with pytest.raises(capi.SlrError, match="scanXZFromYPlus|cannot open|not defined"):
+def test_unknown_builtin_fails_loudly(tmp_path):
+    """A scene file that calls a function the language does not have must fail with a message, not build a wrong scene."""
+    path = scenes.SCENES["diffuse"](str(tmp_path), width=16, height=16, spp=1)
+    bad = os.path.join(str(tmp_path), "bad.txt")
+    with open(bad, "w") as f:
+        f.write(open(path).read() + "\nscatterOnSurface(root, 10);\n")
+    with pytest.raises(capi.SlrError, match="scatterOnSurface|not defined"):
         with capi.stdout_to_stderr():
-            capi.read_scene(str(tmp_path / "RTC3.txt"))
+            capi.read_scene(bad)
 
 
 def test_debug_renderer_is_selected_by_the_scene_language(tmp_path):
