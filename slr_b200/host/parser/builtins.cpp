@@ -239,10 +239,12 @@ void registerBuiltins(Interpreter& in) {
         return fnOver({{{"point", Type::Point}}, {{"vector", Type::Vector}}, {{"normal", Type::Normal}}}, fs);
     };
     def(in, "getX", getter(0)); def(in, "getY", getter(1)); def(in, "getZ", getter(2));
-    def(in, "random", fn({}, [](const Args&, Interpreter&) {
-        static XorShift128 rng(2112984105);      // the reference's static generator (API.cpp:238-244)
-        return Value::Real(rng.float0cTo1o());
-    }));
+    {
+        // the reference's generator is a static of its process (API.cpp:238-244) and a process reads one scene file: here
+        // every interpreter (= every scene file read) starts the stream afresh, whatever the process read before
+        auto rng = std::make_shared<XorShift128>(2112984105);
+        def(in, "random", fn({}, [rng](const Args&, Interpreter&) { return Value::Real(rng->float0cTo1o()); }));
+    }
 
     // ---- math (BuiltinFunctions/builtin_math.cpp)
     def(in, "min", fn({{"x0", R}, {"x1", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::fmin(a.at("x0").d, a.at("x1").d)); }));
