@@ -512,6 +512,11 @@ void registerBuiltins(Interpreter& in) {
         return Value::Ref(Type::Mesh, mesh);
     }));
     def(in, "createNode", fn({}, [](const Args&, Interpreter&) { return Value::Ref(Type::Node, std::make_shared<InternalNode>()); }));
+    def(in, "copyNode", fn({{"src", Type::Node}}, [](const Args& a, Interpreter& in) -> Value {
+        NodeRef copied;
+        try { copied = a.at("src").as<InternalNode>()->copy(); } catch (const std::exception& e) { in.fail(e.what()); }
+        return Value::Ref(Type::Node, std::static_pointer_cast<InternalNode>(copied));
+    }));
     def(in, "createReferenceNode", fn({{"node", Type::Node}}, [](const Args& a, Interpreter&) {
         return Value::Ref(Type::ReferenceNode, std::make_shared<ReferenceNode>(a.at("node").as<InternalNode>()));
     }));

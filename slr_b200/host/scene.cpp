@@ -33,6 +33,24 @@ bool InternalNode::addChildNode(const NodeRef& n) {
     return true;
 }
 
+NodeRef InternalNode::copy() const {
+    auto ret = std::make_shared<InternalNode>();
+    ret->m_localToWorld = m_localToWorld;
+    for (const NodeRef& c : m_children) {
+        NodeRef cc = c->copy();
+        if (!cc) throw std::runtime_error("copyNode: the subtree holds a node that cannot be copied (a reference or camera node)");
+        ret->m_children.push_back(cc);
+    }
+    return ret;
+}
+
+NodeRef TriangleMeshNode::copy() const {
+    auto ret = std::make_shared<TriangleMeshNode>();
+    ret->m_vertices = m_vertices;
+    ret->m_groups = m_groups;
+    return ret;
+}
+
 void InternalNode::getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) {
     // parent * local, with the inverse recomputed from the product as StaticTransform's ctor does
     StaticTransform reduced = subTF ? (*subTF * m_localToWorld) : m_localToWorld;

@@ -62,6 +62,8 @@ public:
     // this clears the marks so that the subtree can be flattened again by another pass (scanXZFromYPlus flattens a subtree while
     // the scene is still being written; Scene::build flattens everything later).
     virtual void resetFlattening() {}
+    // deep copy (nodes.cpp:69-77, TriangleMeshNode.cpp:52-57); node kinds the reference cannot copy return null
+    virtual std::shared_ptr<Node> copy() const { return nullptr; }
 };
 typedef std::shared_ptr<Node> NodeRef;
 
@@ -75,6 +77,7 @@ public:
     const std::vector<NodeRef>& children() const { return m_children; }
     void getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) override;
     void resetFlattening() override { for (const NodeRef& c : m_children) c->resetFlattening(); }
+    NodeRef copy() const override;
 };
 typedef std::shared_ptr<InternalNode> InternalNodeRef;
 
@@ -98,6 +101,7 @@ public:
     const std::vector<MaterialGroup>& groups() const { return m_groups; }
     void getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) override;
     void resetFlattening() override { m_flattened = false; }
+    NodeRef copy() const override;
 };
 typedef std::shared_ptr<TriangleMeshNode> TriangleMeshNodeRef;
 

@@ -80,3 +80,24 @@ def test_debug_renderer_is_selected_by_the_scene_language(tmp_path):
         f.write(text + '\nsetRenderer("method": "photon mapping");\n')
     with pytest.raises(capi.SlrError, match="Unknown method"):
         capi.read_scene(bad)
+
+
+# every name libSLRSceneGraph/API.cpp puts on the global stack (stack["..."] = ..., API.cpp:246-1090)
+REFERENCE_BUILTINS = """root print addItem numElements Point Vector getX getY getZ random min clamp sqrt pow sin cos tan asin acos atan
+dot cross distance translate rotate rotateX rotateY rotateZ scale lookAt AnimatedTransform Texture2DMapping Texture3DMapping
+SpectrumTexture NormalTexture FloatTexture createVertex Spectrum Image2D createSurfaceMaterial createEmitterSurfaceProperty
+createMesh createNode copyNode createReferenceNode setTransform addChild load3DModel scanXZFromYPlus createPerspectiveCamera
+setRenderer setRenderSettings setEnvironment""".split()
+
+
+def test_every_reference_builtin_is_defined(tmp_path):
+    """The scene language knows every global of the reference's (functions are first-class values, so naming one is enough)."""
+    path = scenes.SCENES["diffuse"](str(tmp_path), width=16, height=16, spp=1)
+    probe = os.path.join(str(tmp_path), "probe.txt")
+    with open(probe, "w") as f:
+        f.write(open(path).read() + "\n" + "".join(f"probe_{i} = {name};\n" for i, name in enumerate(REFERENCE_BUILTINS)))
+    with capi.stdout_to_stderr():
+        capi.read_scene(probe)
+    if os.path.isdir(SRC):      # the list above is the reference's own, where it can be checked
+        api = open(os.path.join(os.path.dirname(SRC), "libSLRSceneGraph", "API.cpp")).read()
+        assert sorted(set(re.findall(r'stack\["(\w+)"\]', api))) == sorted(REFERENCE_BUILTINS)

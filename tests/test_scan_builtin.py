@@ -5,7 +5,8 @@ being read and calls a script function with the hit's position and shading frame
 The host interpreter flattens the subtree, builds its SBVH -> QBVH and casts the rays on the host (host/raycast.cpp).
 Parity: the same scene file is read by the compiled reference (oracle/_ref/ref_render prints while it parses) and by
 libslrhost; the callback prints every component it receives, and the two transcripts must agree number for number
-(the reference prints 6 significant digits). Fixture: tests/golden/scan_builtin.txt, the reference's transcript, made
+(the reference prints 6 significant digits). Fixtures: tests/golden/scan_builtin.txt and scan_copy.txt (a second scene
+that also exercises copyNode), the reference's transcripts, made
 by `python tests/test_scan_builtin.py --make-golden` in the container that has /root/reference."""
 import os
 import subprocess
@@ -19,7 +20,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle_util as ou  # noqa: E402
 from slr_b200 import capi, scenes, synth  # noqa: E402
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scan_builtin.txt")
+def golden_path(which):
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", which + ".txt")
 
 SCRIPT = """
 function terrainMat(name, attrs) {
@@ -59,7 +61,18 @@ setRenderSettings("width": 8, "height": 8);
 """
 
 
-def write_scene(directory):
+# copyNode (API.cpp:736-744, nodes.cpp:69-77): a deep copy that can be placed on its own; scanned together with the original
+SCRIPT_COPY = SCRIPT.replace("scanXZFromYPlus(group, 7, 5, 0.5, show);\nscanXZFromYPlus(terrain, 3, 3, show);",
+                             "terrain2 = copyNode(terrain);\n"
+                             "setTransform(terrain2, translate(2.5, 0.9, 0.3) * rotateY(-0.4) * scale(1.2));\n"
+                             "pair = createNode();\nsetTransform(pair, translate(0, 0, 0));\n"
+                             "addChild(pair, terrain2);\naddChild(root, pair);\n"
+                             "scanXZFromYPlus(pair, 5, 4, 0.3, show);\nscanXZFromYPlus(root, 6, 6, show);")
+assert SCRIPT_COPY != SCRIPT
+SCRIPTS = {"scan_builtin": SCRIPT, "scan_copy": SCRIPT_COPY}
+
+
+def write_scene(directory, which="scan_builtin"):
     os.makedirs(os.path.join(directory, "models"), exist_ok=True)
     pos, idx = synth.heightfield(24)
     nrm = np.zeros_like(pos)
@@ -84,7 +97,7 @@ def write_scene(directory):
          'surfMat = createSurfaceMaterial("emitter", (scatterMat, emitterMat));']).replace("CBNode", "lightNode") + "addChild(root, lightNode);\n"
     path = os.path.join(directory, "scan_scene.txt")
     with open(path, "w") as f:
-        f.write(SCRIPT % {"light": light})
+        f.write(SCRIPTS[which] % {"light": light})
     return path
 
 
@@ -126,10 +139,11 @@ def test_random_builtin_matches_reference_stream(tmp_path):
     assert got.shape == (8,) and np.allclose(got, want, rtol=0, atol=5e-7), out
 
 
-def test_scan_builtin_matches_golden(tmp_path):
-    path = write_scene(str(tmp_path))
+@pytest.mark.parametrize("which", sorted(SCRIPTS))
+def test_scan_builtin_matches_golden(which, tmp_path):
+    path = write_scene(str(tmp_path), which)
     got = numbers(host_transcript(path))
-    want = numbers(open(GOLDEN).read())
+    want = numbers(open(golden_path(which)).read())
     assert want.size >= 13 * 20, "the golden holds a useful number of hits"
     assert got.shape == want.shape, f"{got.size} numbers printed, the reference printed {want.size}"
     # 6 significant digits in the transcript; positions within 2e-5 relative, unit vectors within 2e-5 absolute
@@ -137,8 +151,9 @@ def test_scan_builtin_matches_golden(tmp_path):
 
 
 @pytest.mark.skipif(not ou.have_ref(), reason="compiled reference (oracle/_ref) not present")
-def test_scan_builtin_matches_live_reference(tmp_path):
-    path = write_scene(str(tmp_path))
+@pytest.mark.parametrize("which", sorted(SCRIPTS))
+def test_scan_builtin_matches_live_reference(which, tmp_path):
+    path = write_scene(str(tmp_path), which)
     want = numbers(reference_transcript(path))
     got = numbers(host_transcript(path))
     assert got.shape == want.shape and want.size > 0
@@ -147,9 +162,10 @@ def test_scan_builtin_matches_live_reference(tmp_path):
 
 if __name__ == "__main__" and "--make-golden" in sys.argv:
     import tempfile
-    with tempfile.TemporaryDirectory() as d:
-        text = reference_transcript(write_scene(d))
-    keep = [l for l in text.splitlines() if l.strip() and numbers(l).size == 1]
-    with open(GOLDEN, "w") as f:
-        f.write("\n".join(keep) + "\n")
-    print(len(keep), "numbers written to", GOLDEN)
+    for which in sorted(SCRIPTS):
+        with tempfile.TemporaryDirectory() as d:
+            text = reference_transcript(write_scene(d, which))
+        keep = [l for l in text.splitlines() if l.strip() and numbers(l).size == 1]
+        with open(golden_path(which), "w") as f:
+            f.write("\n".join(keep) + "\n")
+        print(len(keep), "numbers written to", golden_path(which))
