@@ -247,21 +247,24 @@ void registerBuiltins(Interpreter& in) {
     }
 
     // ---- math (BuiltinFunctions/builtin_math.cpp)
-    def(in, "min", fn({{"x0", R}, {"x1", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::fmin(a.at("x0").d, a.at("x1").d)); }));
-    def(in, "max", fn({{"x0", R}, {"x1", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::fmax(a.at("x0").d, a.at("x1").d)); }));
+    // the reference takes every argument as a `float` and calls the float overloads (builtin_math.cpp:15-84): sin(0.3) is
+    // sinf(0.3f), not the double value -- the results feed transforms, so they are kept to the bit
+    def(in, "min", fn({{"x0", R}, {"x1", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::min(f(a, "x0"), f(a, "x1"))); }));
+    def(in, "max", fn({{"x0", R}, {"x1", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::max(f(a, "x0"), f(a, "x1"))); }));
     def(in, "clamp", fn({{"x", R}, {"min", R}, {"max", R}}, [](const Args& a, Interpreter&) {
-        return Value::Real(std::min(a.at("max").d, std::max(a.at("min").d, a.at("x").d)));
+        const float x = f(a, "x"), lo = f(a, "min"), hi = f(a, "max");
+        return Value::Real(x < lo ? lo : (hi < x ? hi : x));           // std::clamp(x, min, max)
     }));
-    def(in, "sqrt", fn({{"x", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::sqrt(a.at("x").d)); }));
-    def(in, "pow", fn({{"x", R}, {"e", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::pow(a.at("x").d, a.at("e").d)); }));
-    def(in, "sin", fn({{"x", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::sin(a.at("x").d)); }));
-    def(in, "cos", fn({{"x", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::cos(a.at("x").d)); }));
-    def(in, "tan", fn({{"x", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::tan(a.at("x").d)); }));
-    def(in, "asin", fn({{"x", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::asin(a.at("x").d)); }));
-    def(in, "acos", fn({{"x", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::acos(a.at("x").d)); }));
+    def(in, "sqrt", fn({{"x", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::sqrt(f(a, "x"))); }));
+    def(in, "pow", fn({{"x", R}, {"e", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::pow(f(a, "x"), f(a, "e"))); }));
+    def(in, "sin", fn({{"x", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::sin(f(a, "x"))); }));
+    def(in, "cos", fn({{"x", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::cos(f(a, "x"))); }));
+    def(in, "tan", fn({{"x", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::tan(f(a, "x"))); }));
+    def(in, "asin", fn({{"x", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::asin(f(a, "x"))); }));
+    def(in, "acos", fn({{"x", R}}, [](const Args& a, Interpreter&) { return Value::Real(std::acos(f(a, "x"))); }));
     def(in, "atan", fnOver({{{"x", R}}, {{"y", R}, {"x", R}}},
-                           {[](const Args& a, Interpreter&) { return Value::Real(std::atan(a.at("x").d)); },
-                            [](const Args& a, Interpreter&) { return Value::Real(std::atan2(a.at("y").d, a.at("x").d)); }}));
+                           {[](const Args& a, Interpreter&) { return Value::Real(std::atan(f(a, "x"))); },
+                            [](const Args& a, Interpreter&) { return Value::Real(std::atan2(f(a, "y"), f(a, "x"))); }}));
     def(in, "dot", fn({{"v0", Type::Vector}, {"v1", Type::Vector}}, [](const Args& a, Interpreter&) { return Value::Real(dot(a.at("v0").v3, a.at("v1").v3)); }));
     def(in, "cross", fn({{"v0", Type::Vector}, {"v1", Type::Vector}}, [](const Args& a, Interpreter&) { return Value::Vec(Type::Vector, cross(a.at("v0").v3, a.at("v1").v3)); }));
     def(in, "distance", fn({{"p0", Type::Point}, {"p1", Type::Point}}, [](const Args& a, Interpreter&) { return Value::Real((a.at("p1").v3 - a.at("p0").v3).length()); }));

@@ -137,7 +137,10 @@ static Value arith(const std::string& op, const Value& l, const Value& r) {
         if (op == "%") { if (b == 0) return Value::Error("integer remainder by zero"); return Value::Int(a % b); }
         if (op == "<") return Value::Bool(a < b);
         if (op == ">") return Value::Bool(a > b);
-        if (op == "==") return Value::Bool(a == b);
+        // Reference quirk kept (a scene file must mean here what it means there): Integer == converts the RIGHT operand to
+        // Bool before comparing (SceneParser.cpp:699-706, `lVal == v1.asRaw<TypeMap::Bool>()`), so 3 == 3 is false and
+        // 1 == 7 is true; <=, >= and != are derived from it (SceneParser.cpp:515-527).
+        if (op == "==") return Value::Bool(a == (b != 0 ? 1 : 0));
     } else {
         if (op == "%") return Value::Error("% operator does not support the right operand type.");
         double a = l.number(), b = r.number();
