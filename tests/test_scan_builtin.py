@@ -61,10 +61,12 @@ setRenderSettings("width": 8, "height": 8);
 """
 
 
-# copyNode (API.cpp:736-744, nodes.cpp:69-77): a deep copy that can be placed on its own; scanned together with the original
+# copyNode (API.cpp:736-744, nodes.cpp:69-77): a deep copy that can be placed on its own; scanned together with the original.
+# Its transform goes through lookAt / rotateX / rotateZ / rotate(angle, axis) (builtin_transform.cpp), seen through the hits.
 SCRIPT_COPY = SCRIPT.replace("scanXZFromYPlus(group, 7, 5, 0.5, show);\nscanXZFromYPlus(terrain, 3, 3, show);",
                              "terrain2 = copyNode(terrain);\n"
-                             "setTransform(terrain2, translate(2.5, 0.9, 0.3) * rotateY(-0.4) * scale(1.2));\n"
+                             "setTransform(terrain2, lookAt((2.5, 0.9, 0.3), (2.1, 0.7, -5.0), (0.05, 1, 0)) * rotateX(0.15) * rotateZ(-0.1) *\n"
+                             "                        rotate(0.2, Vector(1, 1, 0)) * scale(1.2));\n"
                              "pair = createNode();\nsetTransform(pair, translate(0, 0, 0));\n"
                              "addChild(pair, terrain2);\naddChild(root, pair);\n"
                              "scanXZFromYPlus(pair, 5, 4, 0.3, show);\nscanXZFromYPlus(root, 6, 6, show);")
