@@ -101,3 +101,61 @@ def test_every_reference_builtin_is_defined(tmp_path):
     if os.path.isdir(SRC):      # the list above is the reference's own, where it can be checked
         api = open(os.path.join(os.path.dirname(SRC), "libSLRSceneGraph", "API.cpp")).read()
         assert sorted(set(re.findall(r'stack\["(\w+)"\]', api))) == sorted(REFERENCE_BUILTINS)
+
+
+SHOW = """
+function slrB200ProbeShow(p, t, b, n) {
+    print(getX(p)); print(getY(p)); print(getZ(p));
+    print(getX(t)); print(getY(t)); print(getZ(t));
+    print(getX(b)); print(getY(b)); print(getZ(b));
+    print(getX(n)); print(getY(n)); print(getZ(n));
+}
+scanXZFromYPlus(root, 14, 14, 0.37, slrB200ProbeShow);
+"""
+
+
+def _numbers(text):
+    out = []
+    for line in text.splitlines():
+        try:
+            out.append(float(line.strip()))
+        except ValueError:
+            pass
+    return out
+
+
+@pytest.mark.skipif(not os.path.isdir(SRC) or not os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "ref_render")),
+                    reason="needs the mounted reference and its compiled oracle")
+@pytest.mark.parametrize("name", sorted(EXPECT))
+def test_reference_scene_geometry_matches_live_reference(name, tmp_path):
+    """The WHOLE scene a shipped scene file describes, as seen by a 14 x 14 grid of rays from above: a scan appended to a
+    temporary copy of the file makes both interpreters print every hit's position and shading frame after the scene graph is
+    complete (loops, integer arithmetic, tuples, createMesh, load3DModel with material callbacks, transforms, reference nodes,
+    RTC3's own 60 x 60 scan with random() rotations). Compared number for number with the compiled reference, live."""
+    import subprocess
+    import sys
+    import numpy as np
+    d = str(tmp_path)
+    text = open(os.path.join(SRC, name)).read()
+    with open(os.path.join(d, name), "w") as f:
+        f.write(text + SHOW)
+    pos, idx, nrm, tng, uv = synth.uv_sphere(32, 16)
+    for asset in set(re.findall(r'"([^"]*\.(?:assbin|exr))"', text)):
+        p = os.path.join(d, asset)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        if asset.endswith(".exr"):
+            capi.write_exr(p, synth.sky_environment(64, 32))
+        elif "Cornell_box_RB" in asset:
+            scenes.write_cornell_box_rb_asset(d)
+        else:
+            capi.write_assbin(p, pos, idx, nrm, tng, uv, material_name="m", diffuse=(0.7, 0.6, 0.5))
+    ref = subprocess.run([os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "ref_render"), name, "out.bin", "1", "8", "8"],
+                         cwd=d, capture_output=True, text=True, timeout=600)
+    code = ("import sys; sys.path.insert(0, %r)\nfrom slr_b200 import capi\ncapi.read_scene(%r)\n" %
+            (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(d, name)))
+    host = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert host.returncode == 0, host.stderr[-1500:]
+    want, got = np.array(_numbers(ref.stdout)), np.array(_numbers(host.stdout))
+    assert want.size >= 12 * 20, f"the reference printed only {want.size} numbers: {ref.stderr[-300:]}"
+    assert got.shape == want.shape, f"{got.size} numbers against the reference's {want.size}"
+    assert np.allclose(got, want, rtol=3e-5, atol=3e-5), float(np.abs(got - want).max())
