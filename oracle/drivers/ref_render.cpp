@@ -14,8 +14,10 @@
 #include <libSLR/Accelerator/SBVH.h>
 #include <libSLR/Accelerator/QBVH.h>
 #include <libSLR/Memory/ArenaAllocator.h>
+#include <cstring>
 #include <libSLR/Renderers/PathTracingRenderer.h>
 #include <libSLR/Renderers/DebugRenderer.h>
+#include <libSLR/Core/distributions.h>
 #include <libSLR/BasicTypes/Spectrum.h>
 #include <libSLR/BasicTypes/SpectrumTypes.h>
 #include <libSLRSceneGraph/Scene.h>
@@ -72,6 +74,17 @@ int main(int argc, char** argv) {
     std::string outDir = out.substr(0, out.find_last_of('/'));
     if (chdir(outDir.c_str()) != 0) perror("chdir");
 
+    if (argc > 8 && std::string(argv[8]) == "lights") {
+        // the light-selection distribution the path tracer samples (SurfaceObject.cpp:232-243, 432-466, distributions.cpp:97-119),
+        // as raw float bits: world centre / radius, the top-level aggregate's PMF, CDF and integral
+        const SurfaceObjectAggregate* ag = rawScene->m_aggregate;
+        const RegularConstantDiscrete1D* d = ag->m_lightDist1D;
+        auto bits = [](float v) { uint32_t b; memcpy(&b, &v, 4); return b; };
+        printf("world %08x %08x %08x %08x\n", bits(rawScene->m_worldCenter.x), bits(rawScene->m_worldCenter.y), bits(rawScene->m_worldCenter.z), bits(rawScene->m_worldRadius));
+        printf("lights %u integral %08x\n", d->m_numValues, bits(d->m_integral));
+        for (uint32_t i = 0; i < d->m_numValues; ++i) printf("pmf %u %08x cdf %08x %08x\n", i, bits(d->m_PMF[i]), bits(d->m_CDF[i]), bits(d->m_CDF[i + 1]));
+        return 0;
+    }
     if (debugAOV) {
         // DebugRenderer writes geometric_normal.bmp / shading_normal.bmp / shading_tangent.bmp into the working directory
         bool flags[(int)ExtraChannel::NumChannels];
