@@ -83,6 +83,27 @@ int main(int argc, char** argv) {
         printf("world %08x %08x %08x %08x\n", bits(rawScene->m_worldCenter.x), bits(rawScene->m_worldCenter.y), bits(rawScene->m_worldCenter.z), bits(rawScene->m_worldRadius));
         printf("lights %u integral %08x\n", d->m_numValues, bits(d->m_integral));
         for (uint32_t i = 0; i < d->m_numValues; ++i) printf("pmf %u %08x cdf %08x %08x\n", i, bits(d->m_PMF[i]), bits(d->m_CDF[i]), bits(d->m_CDF[i + 1]));
+        // the environment's importance map (InfiniteSphereSurfaceObject::m_dist, built by IBLEmission::createIBLImportanceMap):
+        // size, integrals, an FNV-1a hash over all pdf / cdf bits and a few entries in the clear
+        if (const InfiniteSphereSurfaceObject* env = rawScene->m_envSphere) {
+            const RegularConstantContinuous2D* m = env->m_dist;
+            const uint32_t H = m->m_num1DDists, W = m->m_1DDists[0].m_numValues;
+            uint64_t h = 1469598103934665603ull;
+            auto mix = [&h, &bits](float v) { uint32_t b = bits(v); for (int k = 0; k < 4; ++k) { h ^= (b >> (8 * k)) & 0xFFu; h *= 1099511628211ull; } };
+            for (uint32_t y = 0; y < H; ++y) {
+                const RegularConstantContinuous1D& r = m->m_1DDists[y];
+                for (uint32_t x = 0; x < W; ++x) mix(r.m_PDF[x]);
+                for (uint32_t x = 0; x <= W; ++x) mix(r.m_CDF[x]);
+                mix(r.m_integral);
+            }
+            for (uint32_t y = 0; y < H; ++y) mix(m->m_top1DDist->m_PDF[y]);
+            for (uint32_t y = 0; y <= H; ++y) mix(m->m_top1DDist->m_CDF[y]);
+            printf("env %u %u integral %08x top %08x hash %016llx\n", W, H, bits(m->m_integral), bits(m->m_top1DDist->m_integral), (unsigned long long)h);
+            for (uint32_t k = 0; k < 8; ++k) {
+                const uint32_t y = (k * 2654435761u) % H, x = (k * 40503u + 17u) % W;
+                printf("envpdf %u %u %08x %08x %08x\n", x, y, bits(m->m_1DDists[y].m_PDF[x]), bits(m->m_1DDists[y].m_CDF[x]), bits(m->m_top1DDist->m_PDF[y]));
+            }
+        }
         return 0;
     }
     if (debugAOV) {

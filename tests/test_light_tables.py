@@ -30,7 +30,7 @@ def golden_path(name):
 def reference_dump(path):
     p = subprocess.run([os.path.join(ou.REF_DIR, "ref_render"), os.path.basename(path), "out.bin", "1", "8", "8", "0", "0", "lights"],
                        cwd=os.path.dirname(path), capture_output=True, text=True)
-    return "\n".join(l for l in p.stdout.splitlines() if l.startswith(("world ", "lights ", "pmf "))) + "\n"
+    return "\n".join(l for l in p.stdout.splitlines() if l.startswith(("world ", "lights ", "pmf ", "env ", "envpdf "))) + "\n"
 
 
 def parse(text):
@@ -64,6 +64,28 @@ def check(name, text, tmp):
     for i, (pmf, lo, hi) in enumerate(rows):
         L = d.lights[i]
         assert (bits(L.pmf), bits(L.cdf_lo), bits(L.cdf_hi)) == (pmf, lo, hi), f"light {i}"
+    # the environment's importance map (IBLEmission::createIBLImportanceMap -> RegularConstantContinuous2D): every pdf, cdf and
+    # row integral of the reference's map enters an FNV-1a hash in a fixed order; the host's arrays must hash to the same value
+    env = [l.split() for l in text.splitlines() if l.startswith("env ")]
+    e = d.environment
+    assert bool(e.present) == bool(env)
+    if env:
+        w, h = int(env[0][1]), int(env[0][2])
+        assert (e.map_width, e.map_height) == (w, h)
+        f32 = lambda ptr, n: np.ctypeslib.as_array(ptr, shape=(n,)).view(np.uint32)
+        row_pdf, row_cdf = f32(e.row_pdf, w * h).reshape(h, w), f32(e.row_cdf, (w + 1) * h).reshape(h, w + 1)
+        row_int, mpdf, mcdf = f32(e.row_integral, h), f32(e.marginal_pdf, h), f32(e.marginal_cdf, h + 1)
+        stream = np.concatenate([np.concatenate([row_pdf[y], row_cdf[y], row_int[y:y + 1]]) for y in range(h)] + [mpdf, mcdf]).astype(np.uint32)
+        hsh = 1469598103934665603
+        for b in stream.view(np.uint8).tolist():
+            hsh = ((hsh ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        assert bits(e.marginal_integral) == int(env[0][6], 16)
+        assert hsh == int(env[0][8], 16), "importance map differs from the reference's"
+        for l in text.splitlines():
+            if l.startswith("envpdf "):
+                t = l.split()
+                x, y = int(t[1]), int(t[2])
+                assert (int(row_pdf[y, x]), int(row_cdf[y, x]), int(mpdf[y])) == (int(t[3], 16), int(t[4], 16), int(t[5], 16))
 
 
 @pytest.mark.parametrize("name", SCENES)
