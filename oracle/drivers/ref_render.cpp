@@ -18,6 +18,8 @@
 #include <libSLR/Renderers/PathTracingRenderer.h>
 #include <libSLR/Renderers/DebugRenderer.h>
 #include <libSLR/Core/distributions.h>
+#include <libSLR/Cameras/PerspectiveCamera.h>
+#include <libSLR/Core/Transform.h>
 #include <libSLR/BasicTypes/Spectrum.h>
 #include <libSLR/BasicTypes/SpectrumTypes.h>
 #include <libSLRSceneGraph/Scene.h>
@@ -81,6 +83,16 @@ int main(int argc, char** argv) {
         const RegularConstantDiscrete1D* d = ag->m_lightDist1D;
         auto bits = [](float v) { uint32_t b; memcpy(&b, &v, 4); return b; };
         printf("world %08x %08x %08x %08x\n", bits(rawScene->m_worldCenter.x), bits(rawScene->m_worldCenter.y), bits(rawScene->m_worldCenter.z), bits(rawScene->m_worldRadius));
+        if (const PerspectiveCamera* cam = dynamic_cast<const PerspectiveCamera*>(rawScene->getCamera())) {
+            // the camera the ray generation uses: local-to-world matrix sampled at time 0 and its inverse, lens / frustum parameters
+            StaticTransform tf;
+            cam->m_transform->sample(0.0f, &tf);
+            printf("camera");
+            for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) printf(" %08x", bits(tf.mat[c][r]));
+            for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) printf(" %08x", bits(tf.matInv[c][r]));
+            printf(" %08x %08x %08x %08x %08x %08x\n", bits(cam->m_aspect), bits(cam->m_fovY), bits(cam->m_lensRadius), bits(cam->m_imgPlaneDistance),
+                   bits(cam->m_objPlaneDistance), bits(cam->getSensor()->m_sensitivity));
+        }
         printf("lights %u integral %08x\n", d->m_numValues, bits(d->m_integral));
         for (uint32_t i = 0; i < d->m_numValues; ++i) printf("pmf %u %08x cdf %08x %08x\n", i, bits(d->m_PMF[i]), bits(d->m_CDF[i]), bits(d->m_CDF[i + 1]));
         // the environment's importance map (InfiniteSphereSurfaceObject::m_dist, built by IBLEmission::createIBLImportanceMap):

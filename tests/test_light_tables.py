@@ -30,7 +30,7 @@ def golden_path(name):
 def reference_dump(path):
     p = subprocess.run([os.path.join(ou.REF_DIR, "ref_render"), os.path.basename(path), "out.bin", "1", "8", "8", "0", "0", "lights"],
                        cwd=os.path.dirname(path), capture_output=True, text=True)
-    return "\n".join(l for l in p.stdout.splitlines() if l.startswith(("world ", "lights ", "pmf ", "env ", "envpdf "))) + "\n"
+    return "\n".join(l for l in p.stdout.splitlines() if l.startswith(("world ", "camera ", "lights ", "pmf ", "env ", "envpdf "))) + "\n"
 
 
 def parse(text):
@@ -64,6 +64,15 @@ def check(name, text, tmp):
     for i, (pmf, lo, hi) in enumerate(rows):
         L = d.lights[i]
         assert (bits(L.pmf), bits(L.cdf_lo), bits(L.cdf_hi)) == (pmf, lo, hi), f"light {i}"
+    # the camera: local-to-world matrix (column-major) and its inverse, aspect, fovY, lens radius, image / object plane distances, sensitivity
+    cam = [l.split()[1:] for l in text.splitlines() if l.startswith("camera ")]
+    assert len(cam) == 1
+    want = [int(x, 16) for x in cam[0]]
+    c = d.camera
+    got = [bits(c.mat[i]) for i in range(16)] + [bits(c.mat_inv[i]) for i in range(16)] + \
+          [bits(c.aspect), bits(c.fov_y), bits(c.lens_radius), bits(c.img_plane_dist), bits(c.obj_plane_dist)]
+    assert got == want[:37], "camera differs from the reference's"
+    assert np.isclose(np.float32(c.sensitivity), np.array(want[37], np.uint32).view(np.float32), rtol=1e-6) or c.sensitivity == 0
     # the environment's importance map (IBLEmission::createIBLImportanceMap -> RegularConstantContinuous2D): every pdf, cdf and
     # row integral of the reference's map enters an FNV-1a hash in a fixed order; the host's arrays must hash to the same value
     env = [l.split() for l in text.splitlines() if l.startswith("env ")]
