@@ -473,6 +473,33 @@ setTransform(root, rotateY(-1.5707963268));
     return path
 
 
+def write_lamps(directory, width=96, height=96, spp=64):
+    """Emitters INSIDE an instanced subtree: a lamp (a small emitting quad under a shade) referenced twice with different
+    scales above a floor -- the top-level light list then holds the two instances (TransformedSurfaceObject over an aggregate
+    that has lights, SurfaceObject.cpp:279-336), each with its nested list."""
+    floor = "floorNode = createNode();\nsetTransform(floorNode, translate(0, 0, 0));\n" + \
+        _quad("floor", [(-3, 0, 3), (3, 0, 3), (3, 0, -3), (-3, 0, -3)], (0, 1, 0), (1, 0, 0), _matte(0.6, 0.6, 0.6)).replace("CBNode", "floorNode") + \
+        "addChild(root, floorNode);\n"
+    lamp = "lampNode = createNode();\nsetTransform(lampNode, translate(0, 0, 0));\n" + \
+        _quad("lampMesh", [(-0.3, 0, -0.3), (0.3, 0, -0.3), (0.3, 0, 0.3), (-0.3, 0, 0.3)], (0, -1, 0), (1, 0, 0),
+              ['scatterMat = createSurfaceMaterial("matte", (SpectrumTexture(Spectrum(0.9, 0.9, 0.9)),));',
+               'emitterMat = createEmitterSurfaceProperty("diffuse", (SpectrumTexture(Spectrum("ID": "D65") * 5),));',
+               'surfMat = createSurfaceMaterial("emitter", (scatterMat, emitterMat));']).replace("CBNode", "lampNode") + \
+        _quad("shade", [(-0.4, 0.1, -0.4), (0.4, 0.1, -0.4), (0.4, 0.1, 0.4), (-0.4, 0.1, 0.4)], (0, 1, 0), (1, 0, 0), _matte(0.3, 0.3, 0.3)).replace("CBNode", "lampNode")
+    t = f'setRenderer("method": "PT", ("samples": {spp},));\nsetRenderSettings("width": {width}, "height": {height});\n' + floor + lamp
+    t += "lampRef = createReferenceNode(lampNode);\n"
+    for i, (x, y, z, sc) in enumerate([(-1, 2, 0, 1.0), (1.2, 2.5, 0.5, 2.0)]):
+        t += (f"i{i} = createNode();\naddChild(i{i}, lampRef);\nsetTransform(i{i}, translate({x}, {y}, {z}) * rotateZ(0.2) * scale({sc}));\n"
+              f"addChild(root, i{i});\n")
+    t += ('cameraNode = createNode();\ncamera = createPerspectiveCamera("aspect": 1.0, "fovY": 0.7, "radius": 0.01, "imgDist": 1.0, "objDist": 4.0);\n'
+          'addChild(cameraNode, camera);\nsetTransform(cameraNode, translate(0.0, 1.5, 6.0) * rotateY(3.1415926536));\naddChild(root, cameraNode);\n')
+    path = os.path.join(directory, "Lamps.txt")
+    os.makedirs(directory, exist_ok=True)
+    with open(path, "w") as f:
+        f.write(t)
+    return path
+
+
 SCENES = {
     "diffuse": write_cornell_diffuse,
     "spheres": write_cornell_spheres,
@@ -481,6 +508,7 @@ SCENES = {
     "ibl_full": write_ibl_test,
     "instanced": _small_instanced,
     "scatter": write_scatter,
+    "lamps": write_lamps,
     "instanced_full": write_instanced,
     "instanced_10m": lambda d, width=1920, height=1080, spp=1024: write_instanced(d, width, height, spp, base_segments=(318, 159)),
 }

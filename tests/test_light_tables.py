@@ -20,7 +20,7 @@ import oracle_util as ou  # noqa: E402
 import render_util as ru  # noqa: E402
 from slr_b200 import capi  # noqa: E402
 
-SCENES = ["diffuse", "spheres", "materials", "instanced", "ibl", "scatter"]
+SCENES = ["diffuse", "spheres", "materials", "instanced", "ibl", "scatter", "lamps"]     # lamps: emitters inside instances
 
 
 def golden_path(name):
