@@ -70,7 +70,7 @@ def test_image_matches_reference_within_noise_floor(name, size, spp, workdir):
     assert bgot <= 1.5 * bfloor + 0.002, f"16x16-block relRMSE {bgot:.4f} vs floor {bfloor:.4f}"
 
 
-@pytest.mark.parametrize("name", ["diffuse", "spheres", "materials", "ibl", "instanced", "scatter"])
+@pytest.mark.parametrize("name", ["diffuse", "spheres", "materials", "ibl", "instanced", "scatter", "lamps"])
 def test_image_matches_golden_block_means(name, workdir):
     f = os.path.join(ru.GOLDEN, f"render_{name}.npz")
     g = np.load(f)
