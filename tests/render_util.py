@@ -35,6 +35,30 @@ def run_ref_render(scene_path, spp, width, height, seed=0, qbvh=0, timeout=3600)
     return accum, timing
 
 
+def run_ref_render_with_bmps(scene_path, spp, width, height, seed=0):
+    """run_ref_render plus the bytes of the NNN.bmp files the reference's renderer exported on the way (in order)."""
+    import glob
+    d = os.path.dirname(os.path.abspath(scene_path))
+    for f in glob.glob(os.path.join(d, "[0-9][0-9][0-9].bmp")):
+        os.remove(f)
+    accum, timing = run_ref_render(scene_path, spp, width, height, seed=seed)
+    bmps = []
+    for f in sorted(glob.glob(os.path.join(d, "[0-9][0-9][0-9].bmp"))):
+        with open(f, "rb") as fh:
+            bmps.append(fh.read())
+        os.remove(f)
+    return accum, timing, bmps
+
+
+def bmp_pixels(data, width, height):
+    """(header bytes, pixel bytes [h, w, 3]) of a 24-bit BMP written by saveBMP (Helper/bmp_exporter.cpp:14-53): rows are
+    3 * width + width % 4 bytes; the padding bytes are uninitialised heap in the reference and are left out."""
+    data = np.frombuffer(data, np.uint8)
+    row = 3 * width + width % 4
+    assert data.size == 54 + row * height
+    return data[:54].copy(), data[54:].reshape(height, row)[:, :3 * width].reshape(height, width, 3).copy()
+
+
 def scene_file(name, directory, width, height, spp):
     from slr_b200 import scenes
     if os.path.exists(name):
