@@ -338,9 +338,14 @@ typedef struct SlrGpuHitBatch {
  * traversal kernel alone (CUDA events on the launch stream). */
 SLRGPU_API int slrgpu_intersect_batch(SlrGpuScene* scene, const SlrGpuRayBatch* rays, uint64_t num_rays,
                                       const SlrGpuHitBatch* hits, float* kernel_ms);
-/* Device buffers in/out; enqueues on `stream` and returns without synchronising. */
+/* Device buffers in/out; enqueues on `stream` and returns without synchronising. Launches on different streams
+ * (and from different threads) may be in flight at once -- each takes its own status slot on the scene's device, at
+ * most 64 per scene. A traversal-stack overflow in such a launch is reported by slrgpu_scene_poll_overflow. */
 SLRGPU_API int slrgpu_intersect_batch_device(SlrGpuScene* scene, const SlrGpuRayBatch* rays, uint64_t num_rays,
                                              const SlrGpuHitBatch* hits, void* stream);
+/* Waits for the scene's device and sets *overflow to 1 if any slrgpu_intersect_batch_device launch since the last
+ * poll overflowed its traversal stack (QBVH.h:299 holds 64 entries; the reference would write out of bounds). */
+SLRGPU_API int slrgpu_scene_poll_overflow(SlrGpuScene* scene, int* overflow);
 /* Launch geometry the traversal kernel uses for n rays, for reporting (grid, block). */
 SLRGPU_API int slrgpu_intersect_launch_config(SlrGpuScene* scene, uint64_t num_rays, uint32_t* grid, uint32_t* block);
 

@@ -169,6 +169,8 @@ gpu.slrgpu_intersect_batch.restype = C.c_int
 gpu.slrgpu_intersect_batch.argtypes = [C.c_void_p, C.POINTER(RayBatch), c_u64, C.POINTER(HitBatch), PF]
 gpu.slrgpu_intersect_batch_device.restype = C.c_int
 gpu.slrgpu_intersect_batch_device.argtypes = [C.c_void_p, C.POINTER(RayBatch), c_u64, C.POINTER(HitBatch), C.c_void_p]
+gpu.slrgpu_scene_poll_overflow.restype = C.c_int
+gpu.slrgpu_scene_poll_overflow.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
 gpu.slrgpu_intersect_launch_config.restype = C.c_int
 gpu.slrgpu_intersect_launch_config.argtypes = [C.c_void_p, c_u64, PU32, PU32]
 gpu.slrgpu_occluded_batch.restype = C.c_int

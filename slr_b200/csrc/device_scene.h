@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
+#include <mutex>
 #include "../../include/slrgpu.h"
 
 namespace slrgpu {
@@ -42,6 +44,7 @@ struct DeviceScene {
     float envMarginalIntegral;
     float topLightImportance;     // SurfaceObjectAggregate::importance() of the top-level aggregate
     uint32_t rgbMode;
+    uint32_t hasAlpha;            // some leaf record carries SLRGPU_LEAF_FLAG_ALPHA_TEST
     float worldCenter[3];
     float worldRadius;
     SlrGpuCamera camera;
@@ -98,13 +101,19 @@ struct SlrGpuScene {
     uint64_t deviceBytes = 0;
     uint64_t arenaBytes = 0;          // size of allocations[0], the single arena all scene buffers live in
     bool hasInstances = false;
+    bool hasAlpha = false;            // alpha-mapped (cut-out) triangles: the walk kernels run their general instantiation
     bool hasShading = false;
     uint32_t channels = 16;
     uint32_t classMask = 0;           // material classes (wavefront.cuh: ShadeClass) the scene's materials can produce
     int numSMs = 148;                 // of `device`
+    // slrgpu_intersect_batch_device: kStatusSlots x (overflow flag, chunk cursor) on `device`, one slot per launch in flight
+    int* statusRing = nullptr;
+    std::atomic<uint32_t> statusNext{0};
+    std::mutex statusMutex;
 };
 
 namespace slrgpu {
+constexpr uint32_t kStatusSlots = 64;
 void setError(const char* fmt, ...);
 void releaseSceneArenas();
 // intersect.cu: closest hits of a device-resident SoA ray batch; dStatus = two zeroed ints (overflow flag, chunk cursor)

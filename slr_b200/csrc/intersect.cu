@@ -5,6 +5,7 @@
 #include "traverse.cuh"
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -41,21 +42,21 @@ struct OccludedSink {
     __device__ __forceinline__ void done(uint32_t i, const WalkState& w, const TraversalCounters&) const { occluded[i] = w.found ? 1 : 0; }
 };
 
-template <bool INSTANCES, bool COUNT>
+template <bool INSTANCES, bool COUNT, bool ALPHA>
 __global__ void __launch_bounds__(kIntersectBlock)
 intersectBatchKernel(const DeviceScene s, SlrGpuRayBatch rays, uint32_t n, SlrGpuHitBatch hits, int* status) {
     TraversalCounters cnt = {0, 0};
     bool overflow = false;
-    walkQueue<INSTANCES, false, COUNT>(s, n, reinterpret_cast<uint32_t*>(status + 1), BatchRaySource{rays}, BatchHitSink<COUNT>{hits}, cnt, overflow);
+    walkQueue<INSTANCES, false, COUNT, ALPHA>(s, n, reinterpret_cast<uint32_t*>(status + 1), BatchRaySource{rays}, BatchHitSink<COUNT>{hits}, cnt, overflow);
     if (overflow) atomicExch(status, 1);
 }
 
-template <bool INSTANCES>
+template <bool INSTANCES, bool ALPHA>
 __global__ void __launch_bounds__(kIntersectBlock)
 occludedBatchKernel(const DeviceScene s, SlrGpuRayBatch rays, uint32_t n, uint8_t* occluded, int* status) {
     TraversalCounters cnt = {0, 0};
     bool overflow = false;
-    walkQueue<INSTANCES, true, false>(s, n, reinterpret_cast<uint32_t*>(status + 1), BatchRaySource{rays}, OccludedSink{occluded}, cnt, overflow);
+    walkQueue<INSTANCES, true, false, ALPHA>(s, n, reinterpret_cast<uint32_t*>(status + 1), BatchRaySource{rays}, OccludedSink{occluded}, cnt, overflow);
     if (overflow) atomicExch(status, 1);
 }
 
@@ -76,14 +77,28 @@ int launchIntersect(SlrGpuScene* sc, const SlrGpuRayBatch& rays, uint64_t n, con
     const bool count = hits.nodes_visited || hits.tris_tested;
     const dim3 grid(batchGrid(sc, n)), block(kIntersectBlock);
     const uint32_t n32 = (uint32_t)n;
-    if (sc->hasInstances) {
-        if (count) intersectBatchKernel<true, true><<<grid, block, 0, stream>>>(sc->dev, rays, n32, hits, dStatus);
-        else       intersectBatchKernel<true, false><<<grid, block, 0, stream>>>(sc->dev, rays, n32, hits, dStatus);
+    if (sc->hasAlpha) {        // the general instantiation: instances and / or alpha-mapped triangles
+        if (count) intersectBatchKernel<true, true, true><<<grid, block, 0, stream>>>(sc->dev, rays, n32, hits, dStatus);
+        else       intersectBatchKernel<true, false, true><<<grid, block, 0, stream>>>(sc->dev, rays, n32, hits, dStatus);
+    } else if (sc->hasInstances) {
+        if (count) intersectBatchKernel<true, true, false><<<grid, block, 0, stream>>>(sc->dev, rays, n32, hits, dStatus);
+        else       intersectBatchKernel<true, false, false><<<grid, block, 0, stream>>>(sc->dev, rays, n32, hits, dStatus);
     } else {
-        if (count) intersectBatchKernel<false, true><<<grid, block, 0, stream>>>(sc->dev, rays, n32, hits, dStatus);
-        else       intersectBatchKernel<false, false><<<grid, block, 0, stream>>>(sc->dev, rays, n32, hits, dStatus);
+        if (count) intersectBatchKernel<false, true, false><<<grid, block, 0, stream>>>(sc->dev, rays, n32, hits, dStatus);
+        else       intersectBatchKernel<false, false, false><<<grid, block, 0, stream>>>(sc->dev, rays, n32, hits, dStatus);
     }
     SLRGPU_CUDA_TRY(cudaGetLastError());
+    return SLRGPU_OK;
+}
+
+// lazily allocated ring of status slots for slrgpu_intersect_batch_device (one slot per launch in flight)
+static int sceneStatusRing(SlrGpuScene* sc, int** ring) {
+    std::lock_guard<std::mutex> lock(sc->statusMutex);
+    if (!sc->statusRing) {
+        SLRGPU_CUDA_TRY(cudaMalloc(&sc->statusRing, 2 * kStatusSlots * sizeof(int)));
+        SLRGPU_CUDA_TRY(cudaMemset(sc->statusRing, 0, 2 * kStatusSlots * sizeof(int)));
+    }
+    *ring = sc->statusRing;
     return SLRGPU_OK;
 }
 
@@ -260,9 +275,26 @@ SLRGPU_API int slrgpu_intersect_batch_device(SlrGpuScene* scene, const SlrGpuRay
         setError("slrgpu_intersect_batch_device: null argument"); return SLRGPU_ERR_INVALID_ARGUMENT;
     }
     SLRGPU_CUDA_TRY(cudaSetDevice(scene->device));
-    static thread_local int* dStatus = nullptr;
-    if (!dStatus) { SLRGPU_CUDA_TRY(cudaMalloc(&dStatus, 2 * sizeof(int))); SLRGPU_CUDA_TRY(cudaMemset(dStatus, 0, 2 * sizeof(int))); }
-    return launchIntersect(scene, *rays, num_rays, *hits, dStatus, (cudaStream_t)stream);
+    // status words (overflow flag, chunk cursor) of this launch: the next slot of the scene's ring, on the scene's device.
+    // The cursor is zeroed on `stream` before the kernel; the overflow flag is sticky until slrgpu_scene_poll_overflow.
+    int* ring = nullptr;
+    int rc = sceneStatusRing(scene, &ring);
+    if (rc != SLRGPU_OK) return rc;
+    const uint32_t slot = scene->statusNext.fetch_add(1u) % kStatusSlots;
+    return launchIntersect(scene, *rays, num_rays, *hits, ring + 2 * slot, (cudaStream_t)stream);
+}
+
+SLRGPU_API int slrgpu_scene_poll_overflow(SlrGpuScene* scene, int* overflow) {
+    if (!scene || !overflow) { setError("slrgpu_scene_poll_overflow: null argument"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    *overflow = 0;
+    if (!scene->statusRing) return SLRGPU_OK;
+    SLRGPU_CUDA_TRY(cudaSetDevice(scene->device));
+    SLRGPU_CUDA_TRY(cudaDeviceSynchronize());
+    int host[2 * kStatusSlots];
+    SLRGPU_CUDA_TRY(cudaMemcpy(host, scene->statusRing, sizeof(host), cudaMemcpyDeviceToHost));
+    for (uint32_t k = 0; k < kStatusSlots; ++k) if (host[2 * k]) *overflow = 1;
+    if (*overflow) SLRGPU_CUDA_TRY(cudaMemset(scene->statusRing, 0, sizeof(host)));
+    return SLRGPU_OK;
 }
 
 SLRGPU_API int slrgpu_intersect_batch(SlrGpuScene* scene, const SlrGpuRayBatch* rays, uint64_t n,
@@ -332,8 +364,9 @@ SLRGPU_API int slrgpu_occluded_batch(SlrGpuScene* scene, const SlrGpuRayBatch* r
     SLRGPU_CUDA_TRY(cudaEventCreate(&e0));
     SLRGPU_CUDA_TRY(cudaEventCreate(&e1));
     cudaEventRecord(e0, 0);
-    if (scene->hasInstances) occludedBatchKernel<true><<<blocks, kIntersectBlock>>>(scene->dev, dr, (uint32_t)n, dOcc, dStatus);
-    else                     occludedBatchKernel<false><<<blocks, kIntersectBlock>>>(scene->dev, dr, (uint32_t)n, dOcc, dStatus);
+    if (scene->hasAlpha)          occludedBatchKernel<true, true><<<blocks, kIntersectBlock>>>(scene->dev, dr, (uint32_t)n, dOcc, dStatus);
+    else if (scene->hasInstances) occludedBatchKernel<true, false><<<blocks, kIntersectBlock>>>(scene->dev, dr, (uint32_t)n, dOcc, dStatus);
+    else                          occludedBatchKernel<false, false><<<blocks, kIntersectBlock>>>(scene->dev, dr, (uint32_t)n, dOcc, dStatus);
     cudaError_t le = cudaGetLastError();
     cudaEventRecord(e1, 0);
     cudaError_t se = cudaEventSynchronize(e1);

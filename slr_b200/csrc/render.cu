@@ -204,7 +204,7 @@ debugKernel(const DeviceScene s, const RenderConstants rc, float* __restrict__ o
     TraversalCounters cnt = {0, 0};
     bool overflow = false;
     walkBegin(w, stack);
-    while (!walkStep<true, false, false>(s, w, iw, stack, cnt, overflow)) { }
+    while (!walkStep<true, false, false, true>(s, w, iw, stack, cnt, overflow)) { }
     if (overflow) atomicExch(stackOverflow, 1u);
     float* o = out + (size_t)(cs.ipy * rc.width + cs.ipx) * SLRGPU_DEBUG_FLOATS;
 #pragma unroll

@@ -188,6 +188,195 @@ static void compileSpectra(const SlrGpuSceneDesc* d, std::vector<SlrGpuSpectrum>
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// One host pass over the caller's tables before anything is uploaded: every index the device (or compileSpectra)
+// dereferences is range-checked here, so a malformed description is SLRGPU_ERR_INVALID_ARGUMENT instead of a GPU
+// fault, and what the device code cannot represent (material trees with more than 4 leaf lobes or deeper than its
+// 8-entry stack, emitter wrappers nested deeper than classifyMaterialIn peels) is SLRGPU_ERR_UNSUPPORTED instead of
+// a silently different image. Also derives which material-class kernels the scene needs from the classification the
+// device itself uses (classifyMaterialIn over the triangles' materials), and whether any leaf record asks for the
+// alpha test.
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int kMaxLobes = 4, kMaterialStack = 8, kMaxEmitterNesting = 4;
+
+struct Validator {
+    const SlrGpuSceneDesc* d;
+    int fail(int code, const char* fmt, ...) {
+        char buf[400];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+        setError("slrgpu_scene_create: %s", buf);
+        return code;
+    }
+    bool texOk(uint32_t t, bool optional) const { return t < d->num_textures || (optional && t == SLRGPU_INVALID_ID); }
+
+    // leaf lobes and DFS stack depth of a material tree as buildBsdf walks it; -1: too deep / cyclic
+    int countLobes(uint32_t id, int depth, int* maxStack, int stackNow) const {
+        if (id == SLRGPU_INVALID_ID) return 0;
+        if (id >= d->num_materials || depth > 16) return -1;
+        const SlrGpuMaterial& m = d->materials[id];
+        if (stackNow > *maxStack) *maxStack = stackNow;
+        switch (m.kind) {
+        case SLRGPU_MAT_EMITTER: case SLRGPU_MAT_INVERSE: return countLobes(m.sub[0], depth + 1, maxStack, stackNow);
+        case SLRGPU_MAT_SUMMED: case SLRGPU_MAT_MIXED: {
+            // sub[0] is walked with sub[1] still waiting on the stack
+            const int a = countLobes(m.sub[0], depth + 1, maxStack, stackNow + 1);
+            const int b = countLobes(m.sub[1], depth + 1, maxStack, stackNow);
+            return (a < 0 || b < 0) ? -1 : a + b;
+        }
+        default: return 1;
+        }
+    }
+
+    int materials() {
+        for (uint32_t i = 0; i < d->num_materials; ++i) {
+            const SlrGpuMaterial& m = d->materials[i];
+            auto needTex = [&](int k, bool optional = false) { return texOk(m.tex[k], optional); };
+            auto subOk = [&](int k, bool optional) { return m.sub[k] < d->num_materials || (optional && m.sub[k] == SLRGPU_INVALID_ID); };
+            bool ok = true;
+            switch (m.kind) {
+            case SLRGPU_MAT_DIFFUSE: ok = needTex(0) && needTex(1, true); break;
+            case SLRGPU_MAT_SPECULAR_REFLECTION: case SLRGPU_MAT_SPECULAR_SCATTERING: case SLRGPU_MAT_WARD_DUR:
+            case SLRGPU_MAT_MICROFACET_REFLECTION: case SLRGPU_MAT_MICROFACET_SCATTERING: ok = needTex(0) && needTex(1) && needTex(2); break;
+            case SLRGPU_MAT_ASHIKHMIN_SHIRLEY: ok = needTex(0) && needTex(1) && needTex(2) && needTex(3); break;
+            case SLRGPU_MAT_INVERSE: ok = subOk(0, false); break;
+            case SLRGPU_MAT_SUMMED: ok = subOk(0, false) && subOk(1, false); break;
+            case SLRGPU_MAT_MIXED: ok = subOk(0, false) && subOk(1, false) && needTex(0); break;
+            case SLRGPU_MAT_EMITTER: ok = subOk(0, true) && subOk(1, false); break;
+            case SLRGPU_MAT_DIFFUSE_EMISSION: case SLRGPU_MAT_IBL_EMISSION: ok = needTex(0); break;
+            default: return fail(SLRGPU_ERR_INVALID_ARGUMENT, "material %u has unknown kind %u", i, m.kind);
+            }
+            if (!ok) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "material %u (kind %u) refers to a texture / sub-material out of range", i, m.kind);
+            if (m.kind == SLRGPU_MAT_EMITTER) {
+                const uint32_t ek = d->materials[m.sub[1]].kind;
+                if (ek != SLRGPU_MAT_DIFFUSE_EMISSION && ek != SLRGPU_MAT_IBL_EMISSION)
+                    return fail(SLRGPU_ERR_INVALID_ARGUMENT, "material %u: emitter property %u is not an emission material", i, m.sub[1]);
+                int nest = 0;
+                for (uint32_t id = i; id != SLRGPU_INVALID_ID && id < d->num_materials && d->materials[id].kind == SLRGPU_MAT_EMITTER; id = d->materials[id].sub[0])
+                    if (++nest > kMaxEmitterNesting) return fail(SLRGPU_ERR_UNSUPPORTED, "material %u: emitter wrappers nested deeper than %d", i, kMaxEmitterNesting);
+            }
+        }
+        return SLRGPU_OK;
+    }
+
+    int textures() {
+        for (uint32_t i = 0; i < d->num_textures; ++i) {
+            const SlrGpuTexture& t = d->textures[i];
+            bool ok = true;
+            switch (t.kind) {
+            case SLRGPU_TEX_CONSTANT_SPECTRUM: ok = t.i0 < d->num_spectra; break;
+            case SLRGPU_TEX_CHECKER_SPECTRUM: ok = t.i0 < d->num_spectra && t.i1 < d->num_spectra; break;
+            case SLRGPU_TEX_IMAGE_SPECTRUM: case SLRGPU_TEX_IMAGE_NORMAL: case SLRGPU_TEX_IMAGE_FLOAT: ok = t.i0 < d->num_images; break;
+            case SLRGPU_TEX_CONSTANT_FLOAT: case SLRGPU_TEX_CHECKER_NORMAL: case SLRGPU_TEX_CHECKER_FLOAT:
+            case SLRGPU_TEX_VORONOI_SPECTRUM: case SLRGPU_TEX_VORONOI_NORMAL: case SLRGPU_TEX_VORONOI_FLOAT: break;
+            default: return fail(SLRGPU_ERR_INVALID_ARGUMENT, "texture %u has unknown kind %u", i, t.kind);
+            }
+            if (!ok) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "texture %u (kind %u) refers to a spectrum / image out of range", i, t.kind);
+            if (t.mapping > SLRGPU_MAP_WORLD_POS) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "texture %u has unknown mapping %u", i, t.mapping);
+        }
+        for (uint32_t i = 0; i < d->num_spectra; ++i) {
+            const SlrGpuSpectrum& sp = d->spectra[i];
+            uint64_t need = 0;
+            if (sp.kind == SLRGPU_SPECTRUM_REGULAR) need = sp.num_samples;
+            else if (sp.kind == SLRGPU_SPECTRUM_IRREGULAR) need = 2ull * sp.num_samples;
+            else if (sp.kind != SLRGPU_SPECTRUM_UPSAMPLED && sp.kind != SLRGPU_SPECTRUM_RGB)
+                return fail(SLRGPU_ERR_INVALID_ARGUMENT, "spectrum %u has unknown kind %u", i, sp.kind);
+            if (need && ((uint64_t)sp.data_offset + need > d->num_spectrum_floats || !d->spectrum_data))
+                return fail(SLRGPU_ERR_INVALID_ARGUMENT, "spectrum %u: samples [%u, +%llu) exceed spectrum_data (%u floats)", i, sp.data_offset,
+                            (unsigned long long)need, d->num_spectrum_floats);
+            if ((sp.kind == SLRGPU_SPECTRUM_REGULAR || sp.kind == SLRGPU_SPECTRUM_IRREGULAR) && sp.num_samples < 2)
+                return fail(SLRGPU_ERR_INVALID_ARGUMENT, "spectrum %u: a sampled spectrum needs at least 2 samples", i);
+        }
+        static const uint32_t texelBytes[] = {3, 4, 4, 8, 1, 6, 8, 4};
+        for (uint32_t i = 0; i < d->num_images; ++i) {
+            const SlrGpuImage& im = d->images[i];
+            if (im.format > SLRGPU_IMG_FLOAT32 || im.width == 0 || im.height == 0)
+                return fail(SLRGPU_ERR_INVALID_ARGUMENT, "image %u: unknown format %u or empty size", i, im.format);
+            const uint64_t bytes = (uint64_t)im.width * im.height * texelBytes[im.format];
+            if (!d->image_data || im.data_offset + bytes > d->image_data_bytes)
+                return fail(SLRGPU_ERR_INVALID_ARGUMENT, "image %u: texels exceed image_data", i);
+        }
+        return SLRGPU_OK;
+    }
+
+    int geometry(bool* hasAlpha, uint32_t* classMask) {
+        // a scene without materials is geometry only (intersect entry points): its triangle table, if any, is not read
+        const bool shaded = d->triangles && d->num_triangles && d->materials && d->num_materials;
+        if (shaded && (!d->vertices || !d->num_vertices)) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "triangles without vertices");
+        for (uint32_t i = 0; i < d->num_bvh_nodes; ++i) {
+            const SlrGpuBvhNode& n = d->bvh_nodes[i];
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t c = n.child[k];
+                if (c == 0xFFFFFFFFu) continue;
+                const uint32_t idx = c & 0x07FFFFFFu, cnt = (c >> 27) & 0xFu;
+                if (c >> 31) { if ((uint64_t)idx + cnt > d->num_leaf_records) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "node %u child %d: leaf records [%u, +%u) out of range", i, k, idx, cnt); }
+                else if (idx >= d->num_bvh_nodes) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "node %u child %d: node index %u out of range", i, k, idx);
+            }
+            if (n.top_axis > 2 || n.left_axis > 2 || n.right_axis > 2) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "node %u: split axis out of range", i);
+        }
+        *hasAlpha = false;
+        for (uint32_t i = 0; i < d->num_leaf_records; ++i) {
+            uint32_t id, flags;
+            memcpy(&id, &d->leaf_records[i].a[3], 4);
+            memcpy(&flags, &d->leaf_records[i].b[3], 4);
+            if (id & 0x80000000u) {
+                if ((id & 0x7FFFFFFFu) >= d->num_instances) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "leaf record %u: instance %u out of range", i, id & 0x7FFFFFFFu);
+                continue;
+            }
+            if (shaded && id >= d->num_triangles) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "leaf record %u: triangle %u out of range", i, id);
+            if (flags & SLRGPU_LEAF_FLAG_ALPHA_TEST) {
+                if (!shaded || !d->textures) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "leaf record %u asks for the alpha test but the scene has no triangle / texture tables", i);
+                *hasAlpha = true;
+            }
+        }
+        for (uint32_t i = 0; i < d->num_instances; ++i) {
+            const SlrGpuInstance& in = d->instances[i];
+            if (in.root_node >= d->num_bvh_nodes) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "instance %u: root node out of range", i);
+            if (in.num_lights && (in.light_base == SLRGPU_INVALID_ID || (uint64_t)in.light_base + in.num_lights > d->num_lights))
+                return fail(SLRGPU_ERR_INVALID_ARGUMENT, "instance %u: light list out of range", i);
+            if (in.light_index != SLRGPU_INVALID_ID && in.light_index >= d->num_lights) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "instance %u: light index out of range", i);
+        }
+        if (d->num_top_lights > d->num_lights) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "num_top_lights exceeds num_lights");
+        if (d->environment.present) {
+            const SlrGpuEnvironment& e = d->environment;
+            if (e.material >= d->num_materials) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "environment material out of range");
+            if (!e.map_width || !e.map_height || !e.row_pdf || !e.row_cdf || !e.row_integral || !e.marginal_pdf || !e.marginal_cdf)
+                return fail(SLRGPU_ERR_INVALID_ARGUMENT, "environment importance map missing");
+        }
+        for (uint32_t i = 0; i < d->num_lights; ++i) {
+            const uint32_t o = d->lights[i].object;
+            if (o & 0x80000000u) { if ((o & 0x7FFFFFFFu) >= d->num_instances) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "light %u: instance out of range", i); }
+            else if (!shaded || o >= d->num_triangles) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "light %u: triangle out of range", i);
+        }
+        *classMask = 0;
+        if (!shaded) return SLRGPU_OK;
+        // per material: class bit and tree limits, worked out once
+        std::vector<uint32_t> matClass(d->num_materials, 0xFFFFFFFFu);
+        for (uint32_t i = 0; i < d->num_triangles; ++i) {
+            const SlrGpuTriangle& t = d->triangles[i];
+            if (t.v[0] >= d->num_vertices || t.v[1] >= d->num_vertices || t.v[2] >= d->num_vertices)
+                return fail(SLRGPU_ERR_INVALID_ARGUMENT, "triangle %u: vertex index out of range", i);
+            if (t.material >= d->num_materials) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "triangle %u: material %u out of range", i, t.material);
+            if (!texOk(t.normal_map, true) || !texOk(t.alpha_map, true)) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "triangle %u: normal / alpha map out of range", i);
+            if (t.light_index != SLRGPU_INVALID_ID && t.light_index >= d->num_lights) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "triangle %u: light index out of range", i);
+            if (matClass[t.material] == 0xFFFFFFFFu) {
+                int maxStack = 1;
+                const int lobes = countLobes(t.material, 0, &maxStack, 1);
+                if (lobes < 0) return fail(SLRGPU_ERR_UNSUPPORTED, "material %u: tree deeper than 16 levels (or cyclic)", t.material);
+                if (lobes > kMaxLobes) return fail(SLRGPU_ERR_UNSUPPORTED, "material %u has %d leaf lobes; at most %d are supported (MultiBSDF.h:17)", t.material, lobes, kMaxLobes);
+                if (maxStack > kMaterialStack) return fail(SLRGPU_ERR_UNSUPPORTED, "material %u: tree needs a traversal stack of %d (limit %d)", t.material, maxStack, kMaterialStack);
+                uint32_t leaf = SLRGPU_INVALID_ID;
+                const uint32_t cls = classifyMaterialIn(d->materials, t.material, &leaf);
+                matClass[t.material] = cls == 0xFFu ? 0x100u : cls;
+            }
+            if (matClass[t.material] < 16u) *classMask |= 1u << matClass[t.material];
+        }
+        return SLRGPU_OK;
+    }
+};
+}  // namespace
+
 }  // namespace slrgpu
 
 using namespace slrgpu;
@@ -229,6 +418,13 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
     if (d->num_bvh_nodes > 0x07FFFFFFu || d->num_leaf_records > 0x07FFFFFFu) {
         setError("slrgpu_scene_create: node / leaf-record count exceeds the 27-bit child index");
         return SLRGPU_ERR_UNSUPPORTED;
+    }
+    bool hasAlpha = false;
+    uint32_t classMask = 0;
+    {
+        Validator v{d};
+        int vr;
+        if ((vr = v.materials()) || (vr = v.textures()) || (vr = v.geometry(&hasAlpha, &classMask))) return vr;
     }
     int n = slrgpu_device_count();
     if (n == 0) { setError("no CUDA device available (this library has no CPU fallback)"); return SLRGPU_ERR_NO_DEVICE; }
@@ -299,22 +495,11 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
     sc->hasInstances = d->num_instances > 0;
     sc->hasShading = d->num_materials > 0 && d->num_triangles > 0;
     sc->channels = d->rgb_mode ? 3 : 16;
-    // which material-class kernels a wave has to launch (same numbering as ShadeClass / LobeType)
-    sc->classMask = 0;
-    for (uint32_t i = 0; i < d->num_materials; ++i) {
-        const SlrGpuMaterial& m = d->materials[i];
-        switch (m.kind) {
-            case SLRGPU_MAT_DIFFUSE: sc->classMask |= m.tex[1] == SLRGPU_INVALID_ID ? 1u << 0 : 1u << 1; break;
-            case SLRGPU_MAT_SPECULAR_REFLECTION: sc->classMask |= 1u << 2; break;
-            case SLRGPU_MAT_SPECULAR_SCATTERING: sc->classMask |= 1u << 3; break;
-            case SLRGPU_MAT_WARD_DUR: sc->classMask |= 1u << 4; break;
-            case SLRGPU_MAT_ASHIKHMIN_SHIRLEY: sc->classMask |= 1u << 5; break;
-            case SLRGPU_MAT_MICROFACET_REFLECTION: sc->classMask |= 1u << 6; break;
-            case SLRGPU_MAT_MICROFACET_SCATTERING: sc->classMask |= 1u << 7; break;
-            case SLRGPU_MAT_INVERSE: case SLRGPU_MAT_SUMMED: case SLRGPU_MAT_MIXED: sc->classMask |= 1u << 8; break;
-            default: break;
-        }
-    }
+    // which material-class kernels a wave has to launch: the classes the device's own classification (classifyMaterialIn)
+    // gives the triangles' materials, worked out by the validation pass
+    sc->classMask = classMask;
+    sc->hasAlpha = hasAlpha;
+    v.hasAlpha = hasAlpha ? 1u : 0u;
     *out = sc;
     return SLRGPU_OK;
 }
@@ -326,6 +511,7 @@ SLRGPU_API void slrgpu_scene_destroy(SlrGpuScene* sc) {
         if (i == 0 && sc->arenaBytes && cacheArena(sc->device, sc->allocations[0], sc->arenaBytes)) continue;
         cudaFree(sc->allocations[i]);
     }
+    if (sc->statusRing) cudaFree(sc->statusRing);
     delete sc;
 }
 

@@ -18,6 +18,7 @@
 // a leaf record is 48 B = three. One thread owns one ray; the 64-entry stack lives in local memory.
 #pragma once
 #include "device_scene.h"
+#include "textures.cuh"
 
 namespace slrgpu {
 
@@ -76,7 +77,7 @@ __device__ __forceinline__ float dot3(float a, float b, float c, float d, float 
 // Moller-Trumbore, two-sided, exactly the reference's sequence of operations and comparisons
 // (NaNs fall through the range checks the same way because the comparisons are not negated).
 __device__ __forceinline__ bool triangleTest(const float4 a, const float4 b, const float4 c, const Ray& r,
-                                             float* tOut, float* b0Out, float* b1Out) {
+                                             float* tOut, float* b0Out, float* b1Out, float* b2Out) {
     const float e1x = b.x, e1y = b.y, e1z = b.z;
     const float e2x = c.x, e2y = c.y, e2z = c.z;
     const float px = cross2(r.dy, e2z, r.dz, e2y);
@@ -98,7 +99,30 @@ __device__ __forceinline__ bool triangleTest(const float4 a, const float4 b, con
     *tOut = tt;
     *b0Out = __fsub_rn(__fsub_rn(1.0f, b1), b2);
     *b1Out = b1;
+    *b2Out = b2;
     return true;
+}
+
+// The alpha-texture reject of Triangle::intersect (TriangleMesh.cpp:160-168): the candidate hit's texture coordinate
+// b0 tc0 + b1 tc1 + b2 tc2 (left to right, every product and sum rounded on its own) looked up in the triangle's
+// alpha map; a value of exactly 0 means the ray passes through. The reference evaluates the texture with a surface
+// point that carries only the texture coordinate (FloatTexture::evaluate(TexCoord2D), Core/textures.h:84-88), so a
+// world-position mapping sees the origin here (it sees an indeterminate point there). Only leaf records flagged
+// SLRGPU_LEAF_FLAG_ALPHA_TEST come here: kept out of line, cut-out geometry is the exception.
+static __device__ __noinline__ bool alphaTestPasses(const DeviceScene& s, uint32_t prim, float b0, float b1, float b2) {
+    const SlrGpuTriangle tri = s.triangles[prim];
+    if (tri.alpha_map == SLRGPU_INVALID_ID) return true;
+    const float4* va = s.vertices + (size_t)tri.v[0] * 3;
+    const float4* vb = s.vertices + (size_t)tri.v[1] * 3;
+    const float4* vc = s.vertices + (size_t)tri.v[2] * 3;
+    const float u0 = __ldg(va).w, v0 = __ldg(va + 1).w, u1 = __ldg(vb).w, v1 = __ldg(vb + 1).w, u2 = __ldg(vc).w, v2 = __ldg(vc + 1).w;
+    SurfPt sp;
+    sp.p = V3(0, 0, 0); sp.gn = V3(0, 0, 1);
+    sp.sf.x = V3(1, 0, 0); sp.sf.y = V3(0, 1, 0); sp.sf.z = V3(0, 0, 1);
+    sp.u = b0; sp.v = b1; sp.prim = prim; sp.inst = SLRGPU_INVALID_ID; sp.atInfinity = false;
+    sp.tu = dot3(b0, u0, b1, u1, b2, u2);
+    sp.tv = dot3(b0, v0, b1, v1, b2, v2);
+    return evalFloatTexture(s, tri.alpha_map, sp) != 0.0f;
 }
 
 // Matrix4x4 * Point3 with the reference's homogeneous divide rule (Matrix4x4.h:75-81); column-major m
@@ -292,7 +316,7 @@ __device__ __forceinline__ void walkNode(const DeviceScene& s, WalkState& w, Ins
 #ifndef SLR_WALK_ONE_RECORD_PER_STEP
 #define SLR_WALK_ONE_RECORD_PER_STEP 0
 #endif
-template <bool INSTANCES, bool ANY_HIT, bool COUNT>
+template <bool INSTANCES, bool ANY_HIT, bool COUNT, bool ALPHA = false>
 __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, InstanceWalkState& iw, uint32_t* stack,
                                          TraversalCounters& cnt, bool& overflow) {
     Ray& r = w.r;
@@ -338,8 +362,10 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
                 }
             }
         } else {
-            float t, b0, b1;
-            if (triangleTest(a, b, cc, r, &t, &b0, &b1)) {
+            float t, b0, b1, b2;
+            bool accept = triangleTest(a, b, cc, r, &t, &b0, &b1, &b2);
+            if (ALPHA && accept && (__float_as_uint(b.w) & SLRGPU_LEAF_FLAG_ALPHA_TEST)) accept = alphaTestPasses(s, id, b0, b1, b2);
+            if (accept) {
                 r.tmax = t;
                 w.hit.prim = id; w.hit.inst = INSTANCES ? iw.curInst : SLRGPU_INVALID_ID;
                 w.hit.t = t; w.hit.u = b0; w.hit.v = b1;
@@ -353,7 +379,7 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
 
 // Runs `n` rays through the scene with one warp-cooperative loop. Source::load(i, Ray&) fetches ray i,
 // Sink::done(i, state) consumes its result. *cursor must be 0 at launch.
-template <bool INSTANCES, bool ANY_HIT, bool COUNT, typename Source, typename Sink>
+template <bool INSTANCES, bool ANY_HIT, bool COUNT, bool ALPHA, typename Source, typename Sink>
 __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint32_t* cursor, const Source& source, const Sink& sink,
                                           TraversalCounters& cnt, bool& overflow) {
     const uint32_t lane = threadIdx.x & 31;
@@ -405,7 +431,7 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
 #pragma unroll 1
         for (int it = 0; it < kStepsPerRound; ++it) {
             if (active) {
-                if (walkStep<INSTANCES, ANY_HIT, COUNT>(s, w, iw, stack, cnt, overflow)) {
+                if (walkStep<INSTANCES, ANY_HIT, COUNT, ALPHA>(s, w, iw, stack, cnt, overflow)) {
                     sink.done(idx, w, cnt);
                     active = false;
                 }

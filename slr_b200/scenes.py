@@ -500,7 +500,43 @@ def write_lamps(directory, width=96, height=96, spp=64):
     return path
 
 
+def _alpha_quad(name, parent, verts, normal, tangent, uv_scale, mat_setup, alpha_expr):
+    """A quad whose material group carries an alpha texture ("alpha": FloatTexture, createMesh's matGroups signature,
+    libSLRSceneGraph/API.cpp:672-679): hits where the texture evaluates to 0 are passed through (TriangleMesh.cpp:160-168)."""
+    uv = [(0, 0), (uv_scale, 0), (uv_scale, uv_scale), (0, uv_scale)]
+    vs = ",\n".join(f"    (({v[0]}, {v[1]}, {v[2]}), ({normal[0]}, {normal[1]}, {normal[2]}), "
+                    f"({tangent[0]}, {tangent[1]}, {tangent[2]}), ({uv[i][0]}, {uv[i][1]}))" for i, v in enumerate(verts))
+    lines = list(mat_setup) + [f"alphaTex = {alpha_expr};",
+                               f'{name} = createMesh(\n  (\n{vs}\n  ),\n  (\n    (surfMat, "alpha": alphaTex, ((0, 1, 2), (0, 2, 3))),\n  )\n);',
+                               f"addChild({parent}, {name});"]
+    return "\n".join(lines) + "\n"
+
+
+def write_cutout(directory, width=128, height=128, spp=64):
+    """Alpha-mapped (cut-out) geometry: the Cornell box with a checker-perforated screen between camera and back wall (so
+    camera rays, bounce rays and shadow rays all meet the alpha test) and a perforated leaf quad inside a subtree that is
+    referenced twice (the alpha test inside instances)."""
+    os.makedirs(directory, exist_ok=True)
+    t = f'setRenderer("method": "PT", ("samples": {spp},));\nsetRenderSettings("width": {width}, "height": {height});\n\n'
+    t += cornell_box_shell()
+    t += _alpha_quad("screen", "CBNode", [(-1.1, 0.2, -0.6), (1.1, 0.2, -0.6), (1.1, 2.1, -0.6), (-1.1, 2.1, -0.6)], (0, 0, 1), (1, 0, 0), 3.5,
+                     _matte(0.2, 0.7, 0.3), 'FloatTexture("checker board", (0.0, 1.0))')
+    t += "leafNode = createNode();\nsetTransform(leafNode, translate(0, 0, 0));\n"
+    t += _alpha_quad("leaf", "leafNode", [(-0.5, 0, 0.5), (0.5, 0, 0.5), (0.5, 0, -0.5), (-0.5, 0, -0.5)], (0, 1, 0), (1, 0, 0), 2.5,
+                     _matte(0.8, 0.6, 0.1), 'FloatTexture("checker board", (1.0, 0.0))')
+    t += "leafRef = createReferenceNode(leafNode);\n"
+    for i, (x, y, z, rot, sc) in enumerate([(-0.6, 0.9, 0.9, 0.5, 1.0), (0.7, 1.5, 0.4, -0.8, 0.7)]):
+        t += (f"l{i} = createNode();\naddChild(l{i}, leafRef);\nsetTransform(l{i}, translate({x}, {y}, {z}) * rotateZ({rot}) * scale({sc}));\n"
+              f"addChild(root, l{i});\n")
+    t += CORNELL_CAMERA
+    path = os.path.join(directory, "Cutout.txt")
+    with open(path, "w") as f:
+        f.write(t)
+    return path
+
+
 SCENES = {
+    "cutout": write_cutout,
     "diffuse": write_cornell_diffuse,
     "spheres": write_cornell_spheres,
     "materials": write_cornell_materials,

@@ -23,7 +23,7 @@ import render_util as ru
 from slr_b200 import capi
 
 pytestmark = pytest.mark.gpu
-SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced"]
+SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced", "cutout"]
 
 
 @pytest.fixture(scope="module", autouse=True)
