@@ -3,7 +3,7 @@
 // with the renderer/size/seed overridable from the command line, the sensor dumped as raw floats and
 // a timing JSON on stderr.
 //   ref_render scene.txt out.bin [spp] [width] [height] [seed] [qbvh=0|1]
-// out.bin: u32 width, height, channels(16), then width*height*16 f32 (row-major, un-normalised sums,
+// out.bin: u32 width, height, channels (16; 3 in the RGB-mode build ref_render_rgb), then width*height*channels f32 (row-major, un-normalised sums,
 // i.e. ImageSensor::pixel(x, y) after PathTracingRenderer::render). spp/width/height/seed <= 0 keep the
 // scene file's values. The renderer is always the unidirectional PathTracingRenderer. With qbvh=1 every
 // aggregate's accelerator is swapped for QBVH(SBVH) after construction.
@@ -133,14 +133,23 @@ int main(int argc, char** argv) {
     auto t4 = std::chrono::steady_clock::now();
 
     ImageSensor* sensor = rawScene->getCamera()->getSensor();
+#ifdef Use_Spectral_Representation
     uint32_t W = sensor->width(), H = sensor->height(), C = 16;
+#else
+    uint32_t W = sensor->width(), H = sensor->height(), C = 3;      // the RGB-mode build (oracle/Makefile, -DSLR_ORACLE_RGB)
+#endif
     FILE* f = fopen(out.c_str(), "wb");
     if (!f) { perror(out.c_str()); return 1; }
     fwrite(&W, 4, 1, f); fwrite(&H, 4, 1, f); fwrite(&C, 4, 1, f);
     for (uint32_t y = 0; y < H; ++y)
         for (uint32_t x = 0; x < W; ++x) {
             DiscretizedSpectrum px = ((const ImageSensor*)sensor)->pixel(x, y);
+#ifdef Use_Spectral_Representation
             fwrite(px.values, 4, 16, f);
+#else
+            const float rgb[3] = {px.r, px.g, px.b};
+            fwrite(rgb, 4, 3, f);
+#endif
         }
     fclose(f);
     auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };

@@ -20,3 +20,9 @@ static inline void* slr_oracle_memalign(size_t size, size_t alignment) {
 #ifndef SLR_alignof
 #define SLR_alignof(T) alignof(T)
 #endif
+// RGB-mode oracle (make ref builds it next to the spectral one): the reference selects its 3-channel twins with a compile-time
+// switch at the end of libSLR/defines.h:160; the guard above makes every later include of defines.h a no-op, so dropping
+// the macro here compiles the untouched sources in RGB mode (references.h:45-60).
+#ifdef SLR_ORACLE_RGB
+#undef Use_Spectral_Representation
+#endif

@@ -8,19 +8,21 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_RENDER = os.path.join(ROOT, "oracle", "_ref", "ref_render")
+REF_RENDER_RGB = os.path.join(ROOT, "oracle", "_ref", "ref_render_rgb")      # the reference built without Use_Spectral_Representation
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-def have_ref_render():
-    return os.access(REF_RENDER, os.X_OK)
+def have_ref_render(rgb=False):
+    return os.access(REF_RENDER_RGB if rgb else REF_RENDER, os.X_OK)
 
 
-def run_ref_render(scene_path, spp, width, height, seed=0, qbvh=0, timeout=3600):
-    """Returns (accum[h, w, 16] float32, timing dict) from the reference's PathTracingRenderer."""
+def run_ref_render(scene_path, spp, width, height, seed=0, qbvh=0, timeout=3600, rgb=False):
+    """Returns (accum[h, w, 16] float32, timing dict) from the reference's PathTracingRenderer; rgb=True runs the
+    reference's RGB-mode build (accum[h, w, 3])."""
     scene_path = os.path.abspath(scene_path)
     out = scene_path + f".ref_{spp}_{width}x{height}_{seed}.bin"
     # the reference resolves asset paths as <cwd>/<dirname(scene)>/<asset>: run it on the bare file name
-    p = subprocess.run([REF_RENDER, os.path.basename(scene_path), out, str(spp), str(width), str(height), str(seed), str(qbvh)],
+    p = subprocess.run([REF_RENDER_RGB if rgb else REF_RENDER, os.path.basename(scene_path), out, str(spp), str(width), str(height), str(seed), str(qbvh)],
                        capture_output=True, text=True, timeout=timeout, cwd=os.path.dirname(scene_path))
     if p.returncode != 0:
         raise RuntimeError(f"ref_render failed: {p.stderr[-2000:]}")
