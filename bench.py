@@ -260,8 +260,14 @@ def main():
     ap.add_argument("--size", type=int, default=0, help="render workloads: override the image size")
     ap.add_argument("--spp", type=int, default=0, help="render workloads: override the samples per pixel (per GPU)")
     ap.add_argument("--pool", type=int, default=0, help="render workloads: paths in flight (0 = library default)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="render workloads, N > 1: weak = --spp samples per GPU (frame = spp x N, the default the driver measures); "
+                         "strong = --spp is the frame's sample count, partitioned over the GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # the reference's shipped scene files, where the oracle build put them (git-ignored, travels to the GPU box): C1 renders
+    # TestScenes/Cornell_Box_Spheres.txt unchanged when present
+    args.ref_scenes = os.path.join(ROOT, "oracle", "_ref", "TestScenes")
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -2,6 +2,7 @@
 // libSLRSceneGraph/API.cpp:99-1115 and Parser/BuiltinFunctions/*.cpp, implemented over the host
 // classes of this repo. Model import (load3DModel) follows libSLRSceneGraph/node_constructor.cpp
 // with the in-repo .assbin reader instead of assimp.
+#include <cstdio>
 #include "interp.h"
 #include "../assets/assbin.h"
 #include "../assets/images.h"
@@ -618,6 +619,9 @@ void registerBuiltins(Interpreter& in) {
             return withConfig(cfg, {{"samples", Type::Integer, Value::Int(8)}}, in, [ctx, method](const Args& c, Interpreter&) {
                 ctx->samples = (uint32_t)c.at("samples").i;
                 ctx->rendererMethod = method;
+                if (method == "BPT")
+                    std::fprintf(stderr, "slr: warning: setRenderer(\"BPT\"): bidirectional path tracing is not implemented on the GPU; "
+                                         "rendering with the unidirectional path tracer (same expected image, different noise).\n");
                 ctx->renderer.reset(new GPUPathTracingRenderer(ctx->samples));
                 return Value();
             });

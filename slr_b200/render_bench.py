@@ -42,25 +42,46 @@ WORKLOADS = {
 }
 
 
-def _scene(args):
+def _scene(args, directory=None):
+    """Writes the workload's scene file (+ synthetic assets) and returns (path, width, height, spp, description).
+    cornell_spheres renders the reference's own TestScenes/Cornell_Box_Spheres.txt UNCHANGED (size / sample override
+    appended) when bench.py found the shipped scene files (args.ref_scenes); else the re-emitted text of scenes.py."""
     from . import scenes
     key, w, h, spp, desc = WORKLOADS[args.workload]
     if getattr(args, "size", 0):
         w = h = args.size
     if getattr(args, "spp", 0):
         spp = args.spp
-    d = tempfile.mkdtemp(prefix="slr_bench_")
-    path = scenes.SCENES[key](d, width=w, height=h, spp=spp)
+    d = directory or tempfile.mkdtemp(prefix="slr_bench_")
+    src = os.path.join(getattr(args, "ref_scenes", "") or "", "Cornell_Box_Spheres.txt")
+    if args.workload == "cornell_spheres" and os.path.exists(src):
+        path = scenes.write_reference_scene(src, d, w, h, spp)
+        desc += "; scene file = the reference's TestScenes/Cornell_Box_Spheres.txt unchanged + appended size/spp override"
+    else:
+        path = scenes.SCENES[key](d, width=w, height=h, spp=spp)
     return path, w, h, spp, desc
 
 
-def _ref_step(path, w, h, spp):
+def _scene_in_subprocess(args):
+    """The same scene file written by a child process: the reference arm must not map this repo's native libraries
+    (the synthetic .assbin / .exr writers live in libslrhost.so), so the parent only receives the path."""
+    import subprocess
+    d = tempfile.mkdtemp(prefix="slr_bench_ref_")
+    code = ("import json, sys, types; sys.path.insert(0, %r); from slr_b200 import render_bench as rb; "
+            "a = types.SimpleNamespace(**json.loads(sys.argv[1])); print(json.dumps(rb._scene(a, sys.argv[2])))" % ROOT)
+    cfg = {"workload": args.workload, "size": getattr(args, "size", 0), "spp": getattr(args, "spp", 0),
+           "ref_scenes": getattr(args, "ref_scenes", "")}
+    out = subprocess.run([sys.executable, "-c", code, json.dumps(cfg), d], capture_output=True, text=True, check=True).stdout
+    return tuple(json.loads(out.strip().splitlines()[-1]))
+
+
+def _ref_step(path, w, h, spp, seed=0, want_image=False):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import render_util as ru
     t0 = time.perf_counter()
-    _, j = ru.run_ref_render(path, spp, w, h)
+    img, j = ru.run_ref_render(path, spp, w, h, seed=seed)
     wall = time.perf_counter() - t0
-    return j, wall
+    return (j, wall, img) if want_image else (j, wall)
 
 
 def bounded_spp(w, h, spp, max_paths=40e6):
@@ -84,9 +105,11 @@ def cpu_baseline(path, w, h, spp):
 def run_reference(args, rank):
     if rank != 0:
         return
-    path, w, h, spp, desc = _scene(args)
+    path, w, h, spp, desc = _scene_in_subprocess(args)
     total = args.steps + args.warmup
-    step_spp = bounded_spp(w, h, spp, 40e6 if total <= 20 else 10e6)     # keep the whole run within a few minutes
+    # C1 (16.8 M paths, ~4 s of host time) is rendered whole every step -- the same 64 spp the GPU arm renders; the larger
+    # workloads render a bounded number of passes per step (Mpaths/s is a rate: the reference's per-pass time is constant)
+    step_spp = bounded_spp(w, h, spp)
     vals = []
     t0 = time.perf_counter()
     for i in range(total):
@@ -106,6 +129,69 @@ def run_reference(args, rank):
             "cpu_baseline": cb,
             "e2e": {"value": mp, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def _profile_json(name):
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
+def roofline_line(workload, kernel, algo_bytes, achieved_gbs, peak, peak_src, share, paths_per_frame):
+    """The roofline object of the JSON line for the frame's dominant kernel family.
+
+    The algorithmic-bytes figure (every node / leaf-record fetch counted at full size) over the kernel's
+    measured time is always reported against the measured HBM peak (`hbm`). Whether HBM is what BOUNDS the kernel is decided
+    from the committed ncu evidence of this workload: profiles/traffic.json holds the DRAM bytes the kernel family really
+    moved per path; when that is under half of the algorithmic bytes the fetches are served by L1 / L2 (the scene is cache
+    resident), the HBM fraction says nothing about kernel quality, and the line is labelled with what ncu shows bounds it:
+    issue slots at the measured lanes-active (profiles/kernel_metrics.json, copied from the `--set full` capture)."""
+    t = _profile_json("traffic.json").get(workload, {}).get(kernel)
+    traffic = None
+    if t is not None:
+        per_path = t.get("dram_bytes_per_path")
+        traffic = per_path * paths_per_frame if per_path is not None else t.get("dram_bytes_per_frame")
+    m = _profile_json("kernel_metrics.json").get(workload, {}).get(kernel)
+    hbm = {"achieved": achieved_gbs, "peak": peak, "unit": "GB/s", "frac": achieved_gbs / peak, "peak_source": peak_src,
+           "algorithmic_bytes_per_frame": algo_bytes}
+    cache_resident = traffic is not None and traffic < 0.5 * algo_bytes
+    if cache_resident and m is not None:
+        return {"bound": "issue", "achieved": m["issue_slot_utilisation_pct"], "peak": 100.0, "unit": "% of issue slots",
+                "frac": m["issue_slot_utilisation_pct"] / 100.0, "traffic": traffic, "kernel": kernel, "kernel_share_of_step": share,
+                "lanes_active_of_32": m["lanes_active"], "l1_hit_pct": m.get("l1_hit_pct"), "achieved_occupancy_pct": m.get("occupancy_pct"),
+                "source": m["source"], "hbm": hbm,
+                "note": "the kernel's node / leaf-record fetches hit L1 / L2 (measured DRAM traffic is %.0f %% of the algorithmic bytes), "
+                        "so the bound is instruction issue on partly filled warps, not bandwidth: achieved = ncu smsp__issue_active of the "
+                        "committed capture of this workload (not re-measured in this run); `hbm` = the algorithmic bytes of all launches of "
+                        "the kernel family in one frame / their device time in THIS run, against the measured HBM peak"
+                        % (100.0 * traffic / algo_bytes)}
+    return {"bound": "hbm", "achieved": achieved_gbs, "peak": peak, "unit": "GB/s", "frac": achieved_gbs / peak, "traffic": traffic,
+            "kernel": kernel, "peak_source": peak_src, "kernel_share_of_step": share, "algorithmic_bytes_per_launch_set": algo_bytes,
+            "lanes_active_of_32": m["lanes_active"] if m else None, "issue_slot_utilisation_pct": m["issue_slot_utilisation_pct"] if m else None,
+            "note": "achieved = algorithmic bytes of all launches of the kernel family in one frame / their summed device time; "
+                    "traffic = ncu dram__bytes_read+write of the same launches (profiles/traffic.json), scaled to this frame's paths"}
+
+
+def image_parity(capi, path, w, h, spp, gpu_accum):
+    """The frame the e2e leg just rendered (final pipeline, full size) against the reference's PathTracingRenderer at the same
+    size and sample count: relRMSE(gpu, ref1) next to the reference's own two-seed noise floor relRMSE(ref2, ref1), on
+    linear sRGB with the largest 0.5 % of squared errors trimmed on both sides (tests/test_gpu_render.py's statistic)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import render_util as ru
+    gpu = capi.accum_to_rgb(np.array(gpu_accum, copy=True), 1.0 / spp)
+    ref1 = capi.accum_to_rgb(_ref_step(path, w, h, spp, seed=1509761209, want_image=True)[2], 1.0 / spp)
+    ref2 = capi.accum_to_rgb(_ref_step(path, w, h, spp, seed=20240229, want_image=True)[2], 1.0 / spp)
+    (ref1, gpu, ref2), d1 = ru.sanitize_reference(ref1, gpu, ref2)
+    (ref2, gpu, ref1), d2 = ru.sanitize_reference(ref2, gpu, ref1)
+    floor = ru.rel_rmse(ref2, ref1, trim=0.005)
+    got = ru.rel_rmse(gpu, ref1, trim=0.005)
+    clip = float(np.percentile(ref1, 99.8))
+    ratio = np.minimum(gpu, clip).reshape(-1, 3).mean(0) / np.minimum(ref1, clip).reshape(-1, 3).mean(0)
+    return {"width": w, "height": h, "spp": spp, "rel_rmse_gpu_vs_ref": round(got, 5), "rel_rmse_floor_ref_vs_ref": round(floor, 5),
+            "ratio_to_floor": round(got / floor, 4), "tolerance": "<= 1.25 x floor", "within_tolerance": bool(got <= 1.25 * floor),
+            "image_mean_ratio_rgb": [round(float(x), 5) for x in ratio], "reference_nan_pixels_dropped": int(d1 + d2)}
 
 
 def main(args, rank, world):
@@ -132,7 +218,12 @@ def main(args, rank, world):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     seed = 1509761209
-    spp_begin, spp_end = sample_range(rank, world, spp, "weak")
+    # weak (default, what the driver's scaling run measures): every rank renders `spp` samples of its own, the frame has
+    # spp x N; strong (--scaling strong): `spp` is the FRAME's sample count, partitioned over the ranks (north_star: "the
+    # frame's samples-per-pixel are partitioned across the GPUs")
+    mode = getattr(args, "scaling", "weak") or "weak"
+    spp_begin, spp_end = sample_range(rank, world, spp, mode)
+    my_spp = spp_end - spp_begin
     params = capi.RenderParams(C.sizeof(capi.RenderParams), w, h, spp_begin, spp_end, 0.0, 0.0, seed, 0,
                                getattr(args, "pool", 0) or 0, 0)
 
@@ -159,21 +250,25 @@ def main(args, rank, world):
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # one event per step boundary: the K-step span e[0] -> e[K] is the contract's number; the per-step times next to it
+    # show whether a single host stall (the reduce of a straggling rank, a scheduler hiccup) sits inside it
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     launches = 0
     rays = 0
     with bench.ClockSampler(dev) as clocks:
-        e0.record(stream)
-        for _ in range(args.steps):
+        ev[0].record(stream)
+        for k in range(args.steps):
             st = frame()
+            ev[k + 1].record(stream)
             launches += st.kernel_launches + (1 if dist is not None else 0) + 1     # + reduce, + clear
             rays += st.rays
-        e1.record(stream)
         torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    ms = e0.elapsed_time(e1)
-    paths_per_step = w * h * spp
+    ms = ev[0].elapsed_time(ev[-1])
+    step_ms = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps))
+    my_steps = {"median": step_ms[len(step_ms) // 2], "min": step_ms[0], "max": step_ms[-1], "sum": float(sum(step_ms))}
+    paths_per_step = w * h * my_spp
 
     # ---- end to end with host buffers
     # every rank: Renderer::render of its sample range through the host front end (scene upload + render +
@@ -186,7 +281,7 @@ def main(args, rank, world):
 
     def e2e_frame():
         nonlocal hst
-        _, hst = capi.host_render(hs, w, h, spp, seed, dev, spp_begin=spp_begin, out=pinned.numpy())
+        _, hst = capi.host_render(hs, w, h, my_spp, seed, dev, spp_begin=spp_begin, out=pinned.numpy())
         if dist is not None:
             staged.copy_(pinned, non_blocking=True)
             reduce_frame(staged, dist)
@@ -211,13 +306,19 @@ def main(args, rank, world):
     scene_bytes = int(gs.device_bytes)
     accum_bytes = w * h * chan * 4
 
+    per_rank_steps = [my_steps]
+    total_paths_per_step = paths_per_step
     if dist is not None:
         t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
-        tr = torch.tensor([float(rays)], device="cuda", dtype=torch.float64)
+        tr = torch.tensor([float(rays), float(paths_per_step)], device="cuda", dtype=torch.float64)
         dist.all_reduce(tr)
-        rays = float(tr[0])
+        rays, total_paths_per_step = float(tr[0]), int(tr[1])
+        g = torch.zeros((world, 4), device="cuda", dtype=torch.float64)
+        g[rank] = torch.tensor([my_steps["median"], my_steps["min"], my_steps["max"], my_steps["sum"]], dtype=torch.float64)
+        dist.all_reduce(g)
+        per_rank_steps = [{"median": float(r[0]), "min": float(r[1]), "max": float(r[2]), "sum": float(r[3])} for r in g.cpu()]
     else:
         rays = float(rays)
     if rank != 0:
@@ -225,7 +326,7 @@ def main(args, rank, world):
         return
 
     peak, peak_src = bench.measured_peaks()
-    value = paths_per_step * world * args.steps / (ms * 1e-3) / 1e6
+    value = total_paths_per_step * args.steps / (ms * 1e-3) / 1e6
     # dominant kernel by the profiled frame's stage times
     stages = {"extendKernel": prof.extend_ms, "surfaceKernel": prof.surface_ms, "materialKernel": prof.material_ms,
               "shadowKernel": prof.shadow_ms, "raygenKernel": prof.raygen_ms}
@@ -248,21 +349,14 @@ def main(args, rank, world):
     share = stages[dom] / max(prof.device_ms, 1e-9)
     dom_ms_per_step = share * ms / args.steps
     ach = algo[dom] / (dom_ms_per_step * 1e-3) / 1e9
-    # measured DRAM traffic of that kernel family over one frame, from the committed ncu capture of this workload
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f).get(args.workload, {}).get(dom)
-        if t is not None:
-            traffic = t["dram_bytes_per_frame"]
-    except (OSError, ValueError, KeyError):
-        traffic = None
+    roof = roofline_line(args.workload, dom, algo[dom], ach, peak, peak_src, share, paths_per_step)
     cpu = cpu_baseline(path, w, h, spp) if world == 1 else None      # the CPU leg runs at N = 1 only
+    parity = image_parity(capi, path, w, h, my_spp, pinned.numpy()) if (world == 1 and w * h * my_spp <= 40e6) else None
     line = {"metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": mode, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "width": w, "height": h, "spp_per_gpu": spp, "frame_spp": spp * world,
-                       "paths_per_gpu_per_step": paths_per_step, "rays_per_path": rays / (paths_per_step * world * args.steps),
+            "config": {"workload": desc, "width": w, "height": h, "spp_per_gpu": my_spp, "frame_spp": total_paths_per_step // (w * h),
+                       "paths_per_gpu_per_step": paths_per_step, "rays_per_path": rays / (total_paths_per_step * args.steps),
                        "mrays_per_s": rays / (ms * 1e-3) / 1e6, "waves_per_frame": int(prof.waves),
                        "extend_nodes_per_ray": round(prof.extend_nodes / max(n_ext, 1), 3), "extend_leaf_records_per_ray": round(prof.extend_leaf_records / max(n_ext, 1), 3),
                        "shadow_nodes_per_ray": round(prof.shadow_nodes / max(n_sh, 1), 3), "shadow_leaf_records_per_ray": round(prof.shadow_leaf_records / max(n_sh, 1), 3),
@@ -272,19 +366,18 @@ def main(args, rank, world):
                        "l2_policy": "per-step working set (wavefront queues + accumulation buffer, > 500 MB) is larger than L2; "
                                     "the scene itself (QBVH + leaf records) is L2-resident by design",
                        "stage_ms_profiled_frame": {k: round(v, 3) for k, v in stages.items()} | {"tailKernel": round(prof.tail_ms, 3), "other": round(prof.other_ms, 3), "frame": round(prof.device_ms, 3)},
-                       "tail_kernel": {"paths": int(prof.tail_paths), "bounces": int(prof.tail_waves)}},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                         "kernel": dom, "peak_source": peak_src, "kernel_share_of_step": share,
-                         "algorithmic_bytes_per_launch_set": algo[dom],
-                         "note": "achieved = algorithmic bytes of all launches of the kernel family in one frame / their summed device time; "
-                                 "traffic = ncu dram__bytes_read+write summed over the same launches (profiles/traffic.json), bytes per frame. "
-                                 "The algorithmic bytes of the ray kernels count every node / leaf-record fetch (SURVEY 8d); with a scene "
-                                 "that fits L1/L2 most of them never reach HBM, so frac can approach or pass 1 while traffic stays small"},
+                       "tail_kernel": {"paths": int(prof.tail_paths), "bounces": int(prof.tail_waves)},
+                       # device time of every timed step (CUDA events at the step boundaries), per rank: a straggler or a
+                       # host stall inside the K-step span shows up as max >> median
+                       "step_ms_per_rank": [{k: round(v, 3) for k, v in r.items()} for r in per_rank_steps]},
+            "roofline": roof,
             "cpu_baseline": cpu,
-            "e2e": {"value": paths_per_step * world / e2e_s / 1e6, "unit": "Mpaths/s",
+            "e2e": {"value": total_paths_per_step / e2e_s / 1e6, "unit": "Mpaths/s",
                     "h2d_bytes_per_step": scene_bytes + (accum_bytes if world > 1 else 0),
                     "d2h_bytes_per_step": accum_bytes * (2 if world > 1 else 1), "breakdown": e2e_detail},
             "gpu_launches": int(launches), "clocks": clocks.summary()}
+    if parity is not None:
+        line["image_parity"] = parity
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

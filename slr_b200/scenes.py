@@ -500,6 +500,39 @@ def write_lamps(directory, width=96, height=96, spp=64):
     return path
 
 
+def write_reference_scene(src_path, directory, width=0, height=0, spp=0, method="PT"):
+    """One of the reference's shipped TestScenes/*.txt, byte for byte, with nothing but an override block APPENDED
+    (renderer method / samples and image size, the way SURVEY.md section 7 hard part 7 prescribes -- the last
+    setRenderer / setRenderSettings wins in both interpreters) and the synthetic stand-ins for the assets the file loads
+    (the reference does not ship its models / environment maps, README.md:69-72). `src_path` is the caller's copy of
+    the file; this module never looks for the reference itself."""
+    import re
+    os.makedirs(directory, exist_ok=True)
+    with open(src_path) as f:
+        text = f.read()
+    for asset in sorted(set(re.findall(r'"([^"]*\.(?:assbin|exr))"', text))):
+        p = os.path.join(directory, asset)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        if asset.endswith(".exr"):
+            capi.write_exr(p, synth.sky_environment(2048, 1024))
+        elif "Cornell_box_RB" in asset:
+            write_cornell_box_rb_asset(directory)
+        elif asset.endswith("sphere.assbin"):
+            write_sphere_asset(directory)
+        else:
+            pos, idx, nrm, tng, uv = synth.displaced_sphere(96, 48)
+            capi.write_assbin(p, pos, idx, nrm, tng, uv, material_name="m", diffuse=(0.7, 0.6, 0.5))
+    override = "\n// ---- appended override (everything above is the reference's file, unchanged) ----\n"
+    if spp:
+        override += f'setRenderer("method": "{method}", ("samples": {spp},));\n'
+    if width and height:
+        override += f'setRenderSettings("width": {width}, "height": {height});\n'
+    path = os.path.join(directory, os.path.basename(src_path))
+    with open(path, "w") as f:
+        f.write(text + override)
+    return path
+
+
 def _alpha_quad(name, parent, verts, normal, tangent, uv_scale, mat_setup, alpha_expr):
     """A quad whose material group carries an alpha texture ("alpha": FloatTexture, createMesh's matGroups signature,
     libSLRSceneGraph/API.cpp:672-679): hits where the texture evaluates to 0 are passed through (TriangleMesh.cpp:160-168)."""

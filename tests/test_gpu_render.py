@@ -70,6 +70,33 @@ def test_image_matches_reference_within_noise_floor(name, size, spp, workdir):
     assert bgot <= 1.5 * bfloor + 0.002, f"16x16-block relRMSE {bgot:.4f} vs floor {bfloor:.4f}"
 
 
+@pytest.mark.parametrize("name,size,spp", [("Cornell_Box_Spheres.txt", 128, 256), ("Cornell_Box_ColorChecker.txt", 96, 128), ("IBL_Test.txt", 96, 128)])
+def test_unchanged_reference_scene_file_renders_like_the_reference(name, size, spp, workdir):
+    """north_star: "TestScenes/*.txt render unchanged with the GPU path dropped in". The reference's own scene file, byte
+    for byte, plus an appended size / sample-count override (both interpreters let the last setRenderer win; the files ask
+    for BPT, whose expected image is the path tracer's) and synthetic assets, read by the host scene language and rendered
+    on the GPU, against the reference interpreter + PathTracingRenderer on the very same file. Same bars as above."""
+    path = ru.reference_scene_file(name, os.path.join(workdir, "ref_" + name[:-4]), size, size, spp)
+    if path is None or not ru.have_ref_render():
+        pytest.skip("the reference's scene files / ref_render did not travel to this machine")
+    gpu, _ = _gpu_rgb(path, size, spp)
+    ref1 = capi.accum_to_rgb(ru.run_ref_render(path, spp, size, size, seed=1509761209)[0], 1.0 / spp)
+    ref2 = capi.accum_to_rgb(ru.run_ref_render(path, spp, size, size, seed=20240229)[0], 1.0 / spp)
+    (ref1, gpu, ref2), dropped1 = ru.sanitize_reference(ref1, gpu, ref2)
+    (ref2, gpu, ref1), dropped2 = ru.sanitize_reference(ref2, gpu, ref1)
+    assert dropped1 + dropped2 <= 4
+    floor = ru.rel_rmse(ref2, ref1, trim=0.005)
+    got = ru.rel_rmse(gpu, ref1, trim=0.005)
+    assert got <= 1.25 * floor, f"relRMSE {got:.4f} vs noise floor {floor:.4f}"
+    clip = float(np.percentile(ref1, 99.8))
+    gpu_c, ref1_c, ref2_c = np.minimum(gpu, clip), np.minimum(ref1, clip), np.minimum(ref2, clip)
+    ratio = gpu_c.reshape(-1, 3).mean(0) / ref1_c.reshape(-1, 3).mean(0)
+    assert np.all(np.abs(ratio - 1.0) < 0.01), f"image mean ratio {ratio}"
+    bfloor = ru.block_rel_rmse(ref2_c, ref1_c, 16, trim=0.03)
+    bgot = ru.block_rel_rmse(gpu_c, ref1_c, 16, trim=0.03)
+    assert bgot <= 1.5 * bfloor + 0.002, f"16x16-block relRMSE {bgot:.4f} vs floor {bfloor:.4f}"
+
+
 @pytest.mark.parametrize("name", ["diffuse", "spheres", "materials", "ibl", "instanced", "scatter", "lamps", "cutout"])
 def test_image_matches_golden_block_means(name, workdir):
     f = os.path.join(ru.GOLDEN, f"render_{name}.npz")
