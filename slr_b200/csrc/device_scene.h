@@ -81,13 +81,14 @@ __host__ __device__ inline uint32_t classifyMaterialIn(const SlrGpuMaterial* mat
 // triangle record's spare word (SlrGpuTriangle::pad on the device copy): class | emitting << 8 | leaf material << 9.
 // It replaces two to three dependent loads of the material table per hit. kSurfaceInfoDynamic: not precomputed.
 constexpr uint32_t kSurfaceInfoDynamic = 0xFFFFFFFFu;
+constexpr uint32_t kSurfaceInfoMiss = 0xFFFFFFFEu;       // hit record of a ray that left the scene
 inline uint32_t packSurfaceInfo(const SlrGpuMaterial* materials, uint32_t numMaterials, uint32_t materialId) {
     if (materialId >= numMaterials || numMaterials >= (1u << 23)) return kSurfaceInfoDynamic;
     uint32_t leaf = SLRGPU_INVALID_ID;
     const uint32_t cls = classifyMaterialIn(materials, materialId, &leaf);
     const uint32_t emitting = materials[materialId].kind == SLRGPU_MAT_EMITTER ? 1u : 0u;
     if (cls == 0xFFu) leaf = 0;
-    if (leaf >= (1u << 23)) return kSurfaceInfoDynamic;
+    if (leaf >= (1u << 23) - 2u) return kSurfaceInfoDynamic;      // keeps the two reserved words out of the packed range
     return cls | (emitting << 8) | (leaf << 9);
 }
 

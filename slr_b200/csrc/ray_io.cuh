@@ -27,7 +27,7 @@ struct HitSink {
     HitBuffer hits;
     __device__ __forceinline__ void done(uint32_t i, const WalkState& w, const TraversalCounters&) const {
         hits.id[i] = make_uint2(w.hit.prim, w.hit.inst);
-        hits.tuv[i] = make_float4(w.hit.t, w.hit.u, w.hit.v, 0.0f);
+        hits.tuv[i] = make_float4(w.hit.t, w.hit.u, w.hit.v, __uint_as_float(w.hit.info));
     }
 };
 

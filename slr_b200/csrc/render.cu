@@ -123,8 +123,7 @@ raygenKernel(const DeviceScene s, const RenderConstants rc, PathQueue out, const
         out.dir[pos] = make_float4(dir.x, dir.y, dir.z, 0.0f);
         out.meta[pos] = make_uint4(ipy * rc.width + ipx, sample, hero | (flags << 8), __float_as_uint(wlOffset));
         out.weight[pos] = weight * rc.recBinWidth;
-        out.aux[pos] = 1.0f;
-        storeAlpha<NC>(out, pos, specConst<NC>(1.0f));
+        // no throughput (it is 1) and no roulette slot for a camera ray: the stages know from the flag (stages.cuh)
     }
 }
 
@@ -163,6 +162,11 @@ __global__ void endWaveKernel(WavefrontCounters* counters, WavefrontCounters* ri
     counters->waves += 1;
     ring[slot] = *counters;
     __threadfence_system();
+}
+
+// last node of the device-driven loop's body: the WHILE node (renderImpl) runs the body again while paths are in flight
+__global__ void loopConditionKernel(const WavefrontCounters* __restrict__ counters, cudaGraphConditionalHandle handle) {
+    cudaGraphSetConditional(handle, counters->done ? 0u : 1u);
 }
 
 // the shade stages (stages.cuh) as grid-stride kernels over the device-resident counts
@@ -243,6 +247,16 @@ struct RenderWorkspace {
     // joined to the render stream with events (parallel branches of the captured graph)
     cudaStream_t side[SC_COUNT] = {};
     cudaEvent_t forkEvent = nullptr, joinEvent[SC_COUNT] = {};
+    // the instantiated device-driven loop of the last render call and everything that is baked into its kernel nodes: a
+    // call with the same scene view, constants and buffers (a bench / progressive loop) relaunches it without re-capture
+    cudaGraph_t loopGraph = nullptr;
+    cudaGraphExec_t loopExec = nullptr;
+    std::vector<unsigned char> loopKey;
+    void dropLoopGraph() {
+        if (loopExec) cudaGraphExecDestroy(loopExec);
+        if (loopGraph) cudaGraphDestroy(loopGraph);
+        loopExec = nullptr; loopGraph = nullptr; loopKey.clear();
+    }
     int ensureFrame(size_t bytes) {
         if (frame && frameBytes >= bytes) return SLRGPU_OK;
         if (frame) cudaFree(frame);
@@ -256,6 +270,7 @@ struct RenderWorkspace {
         return SLRGPU_OK;
     }
     ~RenderWorkspace() {
+        dropLoopGraph();
         for (int i = 0; i < n; ++i) cudaFree(ptrs[i]);
         if (frame) cudaFree(frame);
         if (frameHost) cudaFreeHost(frameHost);
@@ -501,10 +516,68 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
         timer.mark(4);
         return SLRGPU_OK;
     };
+    // ---- the loop, device driven: ONE graph launch per render call. The graph is a WHILE conditional node (CUDA 12.4+)
+    // whose body is the wave pair + tail kernel above plus loopConditionKernel, which re-arms the node while paths are in
+    // flight: no host thread in the loop, no empty waves enqueued past the end, no stall when the host is descheduled
+    // (with one process per GPU a stalled host used to show up as a straggler rank in the frame's reduce).
+    // SLRGPU_HOST_LOOP=1 (and the per-stage profiling mode, which needs events between the kernels) takes the host-driven
+    // loop below instead: two waves per graph launch, termination read from the pinned snapshot ring two launches behind.
+    WavefrontCounters last = init;
+    bool deviceLoop = false;
+    if (!profile && !getenv("SLRGPU_HOST_LOOP")) {
+        std::vector<unsigned char> key(sizeof(DeviceScene) + sizeof(RenderConstants) + 4 * sizeof(void*) + 4 * sizeof(uint32_t));
+        {
+            unsigned char* k = key.data();
+            memcpy(k, &sc->dev, sizeof(DeviceScene)); k += sizeof(DeviceScene);
+            memcpy(k, &rc, sizeof(RenderConstants)); k += sizeof(RenderConstants);
+            const void* ptrs[4] = {accumDev, waveLog, w.dCounters, nullptr};
+            memcpy(k, ptrs, sizeof(ptrs)); k += sizeof(ptrs);
+            const uint32_t words[4] = {tailCap, sc->classMask, (uint32_t)sc->hasInstances | ((uint32_t)sc->hasAlpha << 1), sc->channels};
+            memcpy(k, words, sizeof(words));
+        }
+        if (!w.loopExec || w.loopKey != key) {
+            w.dropLoopGraph();
+            bool ok = cudaGraphCreate(&w.loopGraph, 0) == cudaSuccess;
+            cudaGraphConditionalHandle handle = 0;
+            ok = ok && cudaGraphConditionalHandleCreate(&handle, w.loopGraph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+            cudaGraph_t body = nullptr;
+            if (ok) {
+                cudaGraphNodeParams np = {};
+                np.type = cudaGraphNodeTypeConditional;
+                np.conditional.handle = handle;
+                np.conditional.type = cudaGraphCondTypeWhile;
+                np.conditional.size = 1;
+                cudaGraphNode_t node;
+                ok = cudaGraphAddNode(&node, w.loopGraph, nullptr, 0, &np) == cudaSuccess;
+                if (ok) body = np.conditional.phGraph_out[0];
+            }
+            if (ok && cudaStreamBeginCaptureToGraph(stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                int r = enqueueWave(0);
+                if (!r) r = enqueueWave(1);
+                if (!r) r = enqueueTail();
+                if (!r) loopConditionKernel<<<1, 1, 0, stream>>>(w.dCounters, handle);
+                cudaGraph_t captured = nullptr;
+                const cudaError_t ce = cudaStreamEndCapture(stream, &captured);
+                if (r) { w.dropLoopGraph(); return r; }
+                ok = ce == cudaSuccess && cudaGraphInstantiate(&w.loopExec, w.loopGraph, 0) == cudaSuccess;
+            } else ok = false;
+            if (ok) w.loopKey = key;
+            else { w.dropLoopGraph(); cudaGetLastError(); }      // e.g. an older driver: fall back to the host-driven loop
+        }
+        if (w.loopExec) {
+            SLRGPU_CUDA_TRY(cudaGraphLaunch(w.loopExec, stream));
+            SLRGPU_CUDA_TRY(cudaEventRecord(ev1, stream));
+            SLRGPU_CUDA_TRY(cudaEventSynchronize(ev1));
+            SLRGPU_CUDA_TRY(cudaMemcpy(&last, w.dCounters, sizeof(last), cudaMemcpyDeviceToHost));
+            wave = last.waves;
+            launches = 1ull + (wave / 2ull) * (2ull * launchesPerWave + (tailCap ? 2u : 0u) + 1u);
+            deviceLoop = true;
+        }
+    }
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graphExec = nullptr;
     struct GraphFree { cudaGraph_t* g; cudaGraphExec_t* e; ~GraphFree() { if (*e) cudaGraphExecDestroy(*e); if (*g) cudaGraphDestroy(*g); } } graphFree{&graph, &graphExec};
-    if (!profile) {
+    if (!profile && !deviceLoop) {
         if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             int r0 = enqueueWave(0);
             int r1 = r0 ? r0 : enqueueWave(1);
@@ -515,8 +588,7 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
         }
         cudaGetLastError();     // a failed capture falls back to plain launches
     }
-    WavefrontCounters last = init;
-    while (true) {
+    while (!deviceLoop) {
         if (graphExec) { SLRGPU_CUDA_TRY(cudaGraphLaunch(graphExec, stream)); }
         else {
             if ((rcode = enqueueWave(0))) return rcode;
@@ -535,10 +607,12 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
             if (last.done) break;
         }
     }
-    SLRGPU_CUDA_TRY(cudaEventRecord(ev1, stream));
-    SLRGPU_CUDA_TRY(cudaEventSynchronize(ev1));
-    last = w.hCounters[(wave - 1) % kRing];
-    wave = last.waves;
+    if (!deviceLoop) {
+        SLRGPU_CUDA_TRY(cudaEventRecord(ev1, stream));
+        SLRGPU_CUDA_TRY(cudaEventSynchronize(ev1));
+        last = w.hCounters[(wave - 1) % kRing];
+        wave = last.waves;
+    }
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         stats->paths = totalSamples;

@@ -2,6 +2,7 @@
 // Replaces, on the GPU side, the object graph a reference renderer receives from
 // SLRSceneGraph::Scene::build (libSLRSceneGraph/Scene.cpp:28-44).
 #include "device_scene.h"
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -377,6 +378,18 @@ struct Validator {
 };
 }  // namespace
 
+// Copies every triangle's surface word (class | emitting | leaf material, packSurfaceInfo) into the spare word of the
+// leaf records that refer to it, on the device copy: the traversal hands it on with the hit (traverse.cuh Hit::info), so
+// the `surface` stage never has to fetch the triangle record of a hit.
+__global__ void patchLeafSurfaceInfoKernel(float4* leaves, uint32_t numLeaves, const SlrGpuTriangle* __restrict__ triangles, uint32_t numTriangles) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < numLeaves; i += gridDim.x * blockDim.x) {
+        const uint32_t id = __float_as_uint(leaves[(size_t)i * 3].w);
+        uint32_t info = kSurfaceInfoDynamic;
+        if (!(id & 0x80000000u) && id < numTriangles) info = triangles[id].pad;
+        leaves[(size_t)i * 3 + 2].w = __uint_as_float(info);
+    }
+}
+
 }  // namespace slrgpu
 
 using namespace slrgpu;
@@ -476,6 +489,13 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
 #undef UP
     rc = plan.commit(sc);
     if (rc != SLRGPU_OK) { slrgpu_scene_destroy(sc); return rc; }
+    if (v.triangles && v.leaves) {
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>(((uint64_t)d->num_leaf_records + 255) / 256, 148 * 8);
+        patchLeafSurfaceInfoKernel<<<blocks, 256>>>(const_cast<float4*>(v.leaves), d->num_leaf_records, v.triangles, d->num_triangles);
+        cudaError_t pe = cudaGetLastError();
+        if (pe == cudaSuccess) pe = cudaDeviceSynchronize();
+        if (pe != cudaSuccess) { slrgpu_scene_destroy(sc); return cudaFail(pe, "patchLeafSurfaceInfoKernel"); }
+    }
 
     v.numNodes = d->num_bvh_nodes; v.numLeaves = d->num_leaf_records; v.numInstances = d->num_instances;
     v.numTriangles = d->num_triangles; v.numVertices = d->num_vertices; v.numMaterials = d->num_materials;

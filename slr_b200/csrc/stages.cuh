@@ -60,18 +60,27 @@ template <int NC> __device__ __forceinline__ Spec<NC> loadAlpha(const PathQueue&
 // MIS weight of implicit light sampling (PathTracingRenderer.cpp:152-156, 232-249). Kept out of line:
 // only a few per cent of the hits take it, and inlined it doubles the register count of the surface kernel.
 template <int NC>
-static __device__ __noinline__ void surfaceEmission(const DeviceScene& s, const PathQueue& in, const HitBuffer& hits, uint32_t i, uint2 hid, uint4 meta,
-                                             uint32_t flags, uint32_t material, const SlrGpuTriangle& tri, bool isEnv, float* __restrict__ accum) {
-    const Spec<NC> alpha = loadAlpha<NC>(in, i);
+static __device__ __noinline__ void surfaceEmission(const DeviceScene& s, const PathQueue& in, const HitBuffer& hits, uint32_t i, uint4 meta,
+                                                    uint32_t flags, bool isEnv, float* __restrict__ accum) {
+    const bool cameraRay = flags & kFlagCameraRay;
+    // a camera ray's throughput is 1: ray generation does not store it
+    const Spec<NC> alpha = cameraRay ? specConst<NC>(1.0f) : loadAlpha<NC>(in, i);
     const float4 o4 = in.org[i], d4 = in.dir[i];
     const V3 org(o4.x, o4.y, o4.z), dir(d4.x, d4.y, d4.z);
     const float prevPdf = d4.w;
     const float wlOffset = __uint_as_float(meta.w);
-    const bool cameraRay = flags & kFlagCameraRay;
     SurfPt sp;
     float localArea = 1.0f;
+    uint32_t material = s.envMaterial;
+    uint2 hid = make_uint2(SLRGPU_INVALID_ID, SLRGPU_INVALID_ID);
+    SlrGpuTriangle tri = {};
     if (isEnv) envSurfacePoint(dir, &sp);
-    else { const float4 htuv = hits.tuv[i]; hitSurfacePoint(s, hid.x, hid.y, htuv.x, htuv.y, htuv.z, org, dir, &sp, &localArea); }
+    else {
+        hid = hits.id[i];
+        const float4 htuv = hits.tuv[i];
+        tri = hitSurfacePoint(s, hid.x, hid.y, htuv.x, htuv.y, htuv.z, org, dir, &sp, &localArea);
+        material = tri.material;
+    }
     const V3 dirOut = sp.sf.toLocal(-dir);
     // DiffuseEDF: 1/pi on the front side; IBLEDF: 1/pi
     const float edf = (sp.atInfinity || dirOut.z > 0.0f) ? 1.0f / kPi : 0.0f;
@@ -100,6 +109,9 @@ static __device__ __noinline__ void surfaceEmission(const DeviceScene& s, const 
 // ray that arrived (implicit light sampling with MIS), the environment for rays that left the scene,
 // Russian roulette and the path-length cap (PathTracingRenderer.cpp:147-163, 225-258). Survivors are
 // sorted into one queue per material class.
+// What the stage needs to know about the hit triangle (class | emitting | leaf material) arrives with the hit record:
+// the traversal copies the spare word of the leaf record it accepted (device_scene.h packSurfaceInfo) into tuv.w, so an
+// entry costs three streaming loads (hit, meta, roulette slot) and no dependent fetch of the triangle / material tables.
 // ---------------------------------------------------------------------------------------------
 // One path-queue entry: *cls = the material class of the surviving hit (SC_NONE: the path ended here), *leaf = its
 // leaf material.
@@ -107,23 +119,25 @@ template <int NC>
 __device__ __forceinline__ void surfaceItem(const DeviceScene& s, const RenderConstants& rc, const PathQueue& in, const HitBuffer& hits,
                                             float* __restrict__ accum, uint32_t i, uint32_t* clsOut, uint32_t* leafOut) {
     uint32_t cls = SC_NONE, leaf = SLRGPU_INVALID_ID;
-    const uint2 hid = hits.id[i];
+    uint32_t info = __float_as_uint(hits.tuv[i].w);
     uint4 meta = in.meta[i];
     const uint32_t hero = meta.z & 0xFFu;
     const uint32_t flags = (meta.z >> 8) & 0xFFu;
     uint32_t pathLength = meta.z >> 16;
     const bool cameraRay = flags & kFlagCameraRay;
-    const bool isEnv = hid.x == SLRGPU_INVALID_ID;
+    const bool isEnv = info == kSurfaceInfoMiss;
     if (!isEnv || s.envPresent) {
-        uint32_t material = s.envMaterial;
-        SlrGpuTriangle tri = {};
         bool emitting = true;
         if (!isEnv) {
-            tri = s.triangles[hid.x];
-            material = tri.material;
-            emitting = tri.pad != kSurfaceInfoDynamic ? ((tri.pad >> 8) & 1u) != 0 : materialIsEmitting(s, material);
+            if (info == kSurfaceInfoDynamic) {          // not precomputed (more than 2^23 materials): work it out from the tables
+                const uint32_t material = s.triangles[hits.id[i].x].material;
+                uint32_t lf = 0;
+                const uint32_t c = classifyMaterial(s, material, &lf);
+                info = c | ((materialIsEmitting(s, material) ? 1u : 0u) << 8) | ((c == 0xFFu ? 0u : lf) << 9);
+            }
+            emitting = ((info >> 8) & 1u) != 0;
         }
-        if (emitting) surfaceEmission<NC>(s, in, hits, i, hid, meta, flags, material, tri, isEnv, accum);
+        if (emitting) surfaceEmission<NC>(s, in, hits, i, meta, flags, isEnv, accum);
         bool cont = !isEnv;
         if (cont && !cameraRay) {
             // Russian roulette; initY = importance of a unit spectrum = 1. importance(alpha) was left in
@@ -139,8 +153,7 @@ __device__ __forceinline__ void surfaceItem(const DeviceScene& s, const RenderCo
             if (pathLength >= rc.maxPathLength) cont = false;
         }
         if (cont) {
-            if (tri.pad != kSurfaceInfoDynamic) { cls = tri.pad & 0xFFu; leaf = tri.pad >> 9; }
-            else cls = classifyMaterial(s, material, &leaf);
+            cls = info & 0xFFu; leaf = info >> 9;
             if (cls != SC_NONE) in.meta[i].z = hero | (flags << 8) | (pathLength << 16);
         }
     }
@@ -223,7 +236,8 @@ __device__ __forceinline__ void materialItem(const DeviceScene& s, const RenderC
     const float4 o4 = in.org[i], d4 = in.dir[i];
     o.meta = in.meta[i];
     o.weight = in.weight[i];
-    o.alpha = loadAlpha<NC>(in, i) * in.aux[i];          // Russian-roulette scale decided by `surface`
+    // Russian-roulette scale decided by `surface`; a camera ray carries throughput 1 and ray generation stores neither
+    o.alpha = ((o.meta.z >> 8) & kFlagCameraRay) ? specConst<NC>(1.0f) : loadAlpha<NC>(in, i) * in.aux[i];
     const uint2 hid = hits.id[i];
     const float4 htuv = hits.tuv[i];
     const V3 org(o4.x, o4.y, o4.z), dir(d4.x, d4.y, d4.z);

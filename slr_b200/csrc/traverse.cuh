@@ -35,6 +35,8 @@ struct Hit {
     uint32_t prim;      // SLRGPU_INVALID_ID = miss
     uint32_t inst;
     float t, u, v;
+    uint32_t info;      // the hit leaf record's spare word: what the `surface` stage needs to know about the triangle
+                        // (device_scene.h packSurfaceInfo, written into the device copy of the records at scene creation)
 };
 
 struct TraversalCounters {
@@ -186,7 +188,7 @@ struct WalkState {
 __device__ __forceinline__ void walkSetRay(WalkState& w);
 __device__ __forceinline__ void walkBegin(WalkState& w, uint32_t* stack) {
     walkSetRay(w);
-    w.hit.prim = SLRGPU_INVALID_ID; w.hit.inst = SLRGPU_INVALID_ID; w.hit.t = INFINITY; w.hit.u = 0.0f; w.hit.v = 0.0f;
+    w.hit.prim = SLRGPU_INVALID_ID; w.hit.inst = SLRGPU_INVALID_ID; w.hit.t = INFINITY; w.hit.u = 0.0f; w.hit.v = 0.0f; w.hit.info = kSurfaceInfoMiss;
     w.found = false;
     w.sp = 0;
     stack[w.sp++] = 0;      // the top-level root is node 0
@@ -368,7 +370,7 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
             if (accept) {
                 r.tmax = t;
                 w.hit.prim = id; w.hit.inst = INSTANCES ? iw.curInst : SLRGPU_INVALID_ID;
-                w.hit.t = t; w.hit.u = b0; w.hit.v = b1;
+                w.hit.t = t; w.hit.u = b0; w.hit.v = b1; w.hit.info = __float_as_uint(cc.w);
                 w.found = true;
                 if (ANY_HIT) return true;
             }

@@ -10,7 +10,7 @@
 //               weight[i]= camera-sample weight (Job::kernel, PathTracingRenderer.cpp:126)  4 B
 //               aux[i]   = importance(alpha), then the Russian-roulette scale                4 B
 //               alpha[q*P + i], q < NC/4 = path throughput, four components per 16 B load   64 B (16 B in RGB mode)
-//   HitBuffer   id[i] = (prim, inst), tuv[i] = (t, b0, b1, -)                 24 B
+//   HitBuffer   id[i] = (prim, inst), tuv[i] = (t, b0, b1, bits(surface info of the hit triangle | miss))   24 B
 //   ShadowQueue org/dir (distMin / distMax in .w), pixel+wavelength offset, contribution[q*P + i]   108 B
 // S_state = 120 B per path per stage transition in spectral mode.
 #pragma once

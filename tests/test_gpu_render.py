@@ -164,6 +164,30 @@ def test_tail_kernel_does_not_change_the_paths(workdir, monkeypatch):
     assert np.isfinite(with_tail).all()
 
 
+def test_device_driven_loop_equals_host_driven_loop(workdir, monkeypatch):
+    """The wavefront loop runs as ONE graph launch (a WHILE conditional node re-armed on the device, render.cu renderImpl);
+    SLRGPU_HOST_LOOP=1 selects the host-driven loop (two waves per graph launch, termination polled from pinned memory).
+    Same kernels, same queues: identical counts, images equal to fp32 summation order -- also across calls that reuse the
+    cached graph and calls that must rebuild it (different sample range)."""
+    path = ru.scene_file("spheres", workdir, 160, 160, 16)
+    hs = capi.read_scene(path)
+    gs = capi.GpuScene(hs)
+    dev1, st_dev1 = capi.gpu_render(gs, 160, 160, 0, 16)
+    dev2, st_dev2 = capi.gpu_render(gs, 160, 160, 0, 16)          # cached graph
+    other, st_other = capi.gpu_render(gs, 160, 160, 16, 24)       # new constants: rebuilt
+    dev3, st_dev3 = capi.gpu_render(gs, 160, 160, 0, 16)
+    monkeypatch.setenv("SLRGPU_HOST_LOOP", "1")
+    host, st_host = capi.gpu_render(gs, 160, 160, 0, 16)
+    monkeypatch.delenv("SLRGPU_HOST_LOOP")
+    for st in (st_dev1, st_dev2, st_dev3):
+        for k in ("paths", "rays", "extend_rays", "shadow_rays", "class_hits", "tail_paths"):
+            assert st[k] == st_host[k], k
+    assert st_other["paths"] == 160 * 160 * 8
+    for img in (dev1, dev2, dev3):
+        np.testing.assert_allclose(img, host, rtol=2e-4, atol=1e-5 * float(host.mean()))
+    assert st_dev1["waves"] <= st_host["waves"]                   # the host loop enqueues waves past the end
+
+
 @pytest.mark.parametrize("name,size,spp", [("diffuse", 96, 256), ("spheres", 128, 256), ("materials", 128, 256), ("instanced", 128, 128)])
 def test_rgb_mode_matches_the_reference_rgb_build(name, size, spp, workdir):
     """RGB mode (libSLR/defines.h:160 without Use_Spectral_Representation: RGBTypes.h:19-180, the RGB branch of
