@@ -396,6 +396,17 @@ SLRGPU_API uint32_t slrgpu_scene_channels(const SlrGpuScene* scene);
  * exactly what ImageSensor::pixel(x,y) holds after PathTracingRenderer::render). Host buffer. */
 SLRGPU_API int slrgpu_render(SlrGpuScene* scene, const SlrGpuRenderParams* params, float* accum,
                              SlrGpuRenderStats* stats);
+/* One frame on several GPUs of one box (the frame's samples-per-pixel are partitioned, the scene is
+ * replicated, the float accumulation buffers are combined once per frame): `scenes` are `num_replicas` (1..16) replicas of
+ * the same scene, normally one per device; replica g renders global sample indices
+ * [spp_begin + g n / N, spp_begin + (g + 1) n / N), n = spp_end - spp_begin, on its own device from its own host thread;
+ * the accumulation buffers are then summed onto scenes[0]'s device by one kernel reading the other devices' buffers over
+ * NVLink peer access (staged peer copies where a pair has none) and downloaded into `accum` (host). stats: sums over the
+ * replicas; device_ms = slowest replica + the exchange step, other_ms = the exchange step alone. Replaces nothing in the
+ * reference (it renders on the host's threads, PathTracingRenderer.cpp:31-56); it is what Renderer::render calls when
+ * more than one GPU is visible. */
+SLRGPU_API int slrgpu_render_multi(SlrGpuScene* const* scenes, uint32_t num_replicas, const SlrGpuRenderParams* params, float* accum,
+                                   SlrGpuRenderStats* stats);
 /* Same, accumulating INTO a device buffer (not cleared), on `stream`, synchronised before return. */
 SLRGPU_API int slrgpu_render_device(SlrGpuScene* scene, const SlrGpuRenderParams* params, float* accum_device,
                                     void* stream, SlrGpuRenderStats* stats);

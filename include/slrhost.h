@@ -44,9 +44,10 @@ SLRGPU_API int slrhost_read_scene(const char* path, int rgb_mode, SlrHostScene**
 /* Rendering context read from the file (setRenderer / setRenderSettings):
  * ctx8 = {width, height, samples, rngSeed, timeStart, timeEnd, brightness, 1 if a renderer was set}. */
 SLRGPU_API int slrhost_scene_context(const SlrHostScene* s, double* ctx8);
-/* Renderer::render through GPUPathTracingRenderer on `device`: width/height/spp <= 0 take the
+/* Renderer::render through GPUPathTracingRenderer on `device` (>= 0), or on EVERY visible device with the frame's
+ * samples partitioned over them (device < 0; slrgpu_render_multi): width/height/spp <= 0 take the
  * scene file's values. On return accum (if non-NULL, width*height*channels floats) holds the
- * sensor's un-normalised sums; stats6 = {paths, rays, deviceSeconds, wallSeconds, uploadSeconds, channels}.
+ * sensor's un-normalised sums; stats6 = {paths, rays, deviceSeconds, wallSeconds, uploadSeconds, channels + 1000 * devices used}.
  * bmp_dir: directory for the progressive NNN.bmp files, or NULL to skip image export. */
 SLRGPU_API int slrhost_render(SlrHostScene* s, int device, int width, int height, int spp, int seed,
                               const char* bmp_dir, float* accum, double* stats6);

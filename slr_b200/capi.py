@@ -169,6 +169,8 @@ gpu.slrgpu_intersect_batch.restype = C.c_int
 gpu.slrgpu_intersect_batch.argtypes = [C.c_void_p, C.POINTER(RayBatch), c_u64, C.POINTER(HitBatch), PF]
 gpu.slrgpu_intersect_batch_device.restype = C.c_int
 gpu.slrgpu_intersect_batch_device.argtypes = [C.c_void_p, C.POINTER(RayBatch), c_u64, C.POINTER(HitBatch), C.c_void_p]
+gpu.slrgpu_render_multi.restype = C.c_int
+gpu.slrgpu_render_multi.argtypes = [C.POINTER(C.c_void_p), c_u32, C.POINTER(RenderParams), PF, C.POINTER(RenderStats)]
 gpu.slrgpu_scene_poll_overflow.restype = C.c_int
 gpu.slrgpu_scene_poll_overflow.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
 gpu.slrgpu_intersect_launch_config.restype = C.c_int
@@ -445,8 +447,8 @@ def host_render(host_scene, width=0, height=0, spp=0, seed=0, device=0, bmp_dir=
     _host_check(host.slrhost_render_range(host_scene.handle, device, width, height, spp_begin, spp, seed,
                                           os.fsencode(bmp_dir) if bmp_dir else None, _pf(accum), st), "slrhost_render_range")
     call_s = time.perf_counter() - t0
-    return accum, {"paths": int(st[0]), "rays": int(st[1]), "device_s": st[2], "wall_s": st[3], "upload_s": st[4], "channels": int(st[5]),
-                   "call_s": call_s}
+    return accum, {"paths": int(st[0]), "rays": int(st[1]), "device_s": st[2], "wall_s": st[3], "upload_s": st[4], "channels": int(st[5]) % 1000,
+                   "devices": int(st[5]) // 1000, "call_s": call_s}
 
 
 def gpu_render(gpu_scene, width, height, spp_begin, spp_end, seed=1509761209, time_start=0.0, time_end=0.0, flags=0,
@@ -458,6 +460,17 @@ def gpu_render(gpu_scene, width, height, spp_begin, spp_end, seed=1509761209, ti
                      pool_size, flags)
     st = RenderStats()
     _gpu_check(gpu.slrgpu_render(gpu_scene.handle, C.byref(p), _pf(accum), C.byref(st)), "slrgpu_render")
+    return accum, {k: (list(getattr(st, k)) if k == "class_hits" else getattr(st, k)) for k, _ in RenderStats._fields_}
+
+
+def gpu_render_multi(gpu_scenes, width, height, spp_begin, spp_end, seed=1509761209, pool_size=0):
+    """slrgpu_render_multi over scene replicas (normally one per device). Returns (accum[h, w, c], RenderStats as dict)."""
+    chan = gpu.slrgpu_scene_channels(gpu_scenes[0].handle)
+    accum = np.zeros((height, width, chan), np.float32)
+    p = RenderParams(C.sizeof(RenderParams), width, height, spp_begin, spp_end, 0.0, 0.0, seed, 0, pool_size, 0)
+    st = RenderStats()
+    handles = (C.c_void_p * len(gpu_scenes))(*[g.handle for g in gpu_scenes])
+    _gpu_check(gpu.slrgpu_render_multi(handles, len(gpu_scenes), C.byref(p), _pf(accum), C.byref(st)), "slrgpu_render_multi")
     return accum, {k: (list(getattr(st, k)) if k == "class_hits" else getattr(st, k)) for k, _ in RenderStats._fields_}
 
 

@@ -18,6 +18,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 namespace slrgpu {
@@ -711,6 +712,57 @@ probeShadeKernel(const DeviceScene s, const float* __restrict__ probes, uint32_t
     }
 }
 
+// device -> caller's host buffer, on the workspace's stream, synchronised before return
+static int downloadFrame(RenderWorkspace& w, float* accum, size_t bytes) {
+    // a caller buffer that is page-locked (cudaHostAlloc / cudaHostRegister, e.g. a pinned framework tensor) takes the DMA directly
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, accum) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+        SLRGPU_CUDA_TRY(cudaMemcpyAsync(accum, w.frame, bytes, cudaMemcpyDeviceToHost, w.stream));
+        SLRGPU_CUDA_TRY(cudaStreamSynchronize(w.stream));
+        return SLRGPU_OK;
+    }
+    cudaGetLastError();
+    // device -> pinned staging -> the caller's (pageable) buffer, in pieces: the host copy of piece k runs while piece
+    // k + 1 is still on the bus
+    constexpr int kPieces = 8;
+    const size_t piece = ((bytes / kPieces) + 4095) & ~(size_t)4095;
+    int pieces = 0;
+    for (size_t off = 0; off < bytes && pieces < kPieces; off += piece, ++pieces) {
+        const size_t len = std::min(piece, bytes - off);
+        SLRGPU_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(w.frameHost) + off, reinterpret_cast<const char*>(w.frame) + off, len,
+                                        cudaMemcpyDeviceToHost, w.stream));
+        SLRGPU_CUDA_TRY(cudaEventRecord(w.ringEvents[pieces], w.stream));
+    }
+    for (int k = 0; k < pieces; ++k) {
+        const size_t off = (size_t)k * piece;
+        SLRGPU_CUDA_TRY(cudaEventSynchronize(w.ringEvents[k]));
+        memcpy(reinterpret_cast<char*>(accum) + off, reinterpret_cast<const char*>(w.frameHost) + off, std::min(piece, bytes - off));
+    }
+    return SLRGPU_OK;
+}
+
+// the multi-GPU exchange step: dst += sum of the other replicas' frames, read where they lie (peer memory over NVLink)
+constexpr uint32_t kMaxReplicas = 16;
+struct PeerFrames { const float* frame[kMaxReplicas]; uint32_t count; };
+__global__ void __launch_bounds__(256)
+sumFramesKernel(float* __restrict__ dst, const PeerFrames peers, uint32_t count) {
+    const uint32_t n4 = count / 4;
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        float4 a = d4[i];
+        for (uint32_t g = 0; g < peers.count; ++g) {
+            const float4 b = reinterpret_cast<const float4*>(peers.frame[g])[i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        d4[i] = a;
+    }
+    for (uint32_t i = n4 * 4 + blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        float a = dst[i];
+        for (uint32_t g = 0; g < peers.count; ++g) a += peers.frame[g][i];
+        dst[i] = a;
+    }
+}
+
 static int checkRenderArgs(SlrGpuScene* sc, const SlrGpuRenderParams* p) {
     if (!sc || !p) { setError("slrgpu_render: null argument"); return SLRGPU_ERR_INVALID_ARGUMENT; }
     if (p->struct_size != sizeof(SlrGpuRenderParams)) { setError("slrgpu_render: params struct_size mismatch"); return SLRGPU_ERR_INVALID_ARGUMENT; }
@@ -824,31 +876,129 @@ SLRGPU_API int slrgpu_render(SlrGpuScene* sc, const SlrGpuRenderParams* p, float
     SLRGPU_CUDA_TRY(cudaMemsetAsync(w->frame, 0, bytes, w->stream));
     rc = renderImpl(sc, p, *w, w->frame, w->stream, stats);
     if (rc) return rc;
-    // a caller buffer that is page-locked (cudaHostAlloc / cudaHostRegister, e.g. a pinned framework tensor) takes the DMA directly
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, accum) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
-        SLRGPU_CUDA_TRY(cudaMemcpyAsync(accum, w->frame, bytes, cudaMemcpyDeviceToHost, w->stream));
-        SLRGPU_CUDA_TRY(cudaStreamSynchronize(w->stream));
-        return SLRGPU_OK;
+    return downloadFrame(*w, accum, bytes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One frame on several GPUs of one box: the frame's sample range is partitioned over the scene
+// replicas -- replica g renders [begin + g n / N, begin + (g + 1) n / N) of every pixel on its own device, one host thread
+// per device -- and the float accumulation buffers are then summed onto the first replica's device by ONE kernel that
+// reads the other devices' buffers directly over NVLink (peer access; a device pair without peer access goes through a
+// staged peer copy), followed by one download. A path's random numbers are keyed by (pixel, global sample index), so the
+// set of paths is the one a single GPU renders; only the fp32 summation order differs.
+// ---------------------------------------------------------------------------------------------
+SLRGPU_API int slrgpu_render_multi(SlrGpuScene* const* scenes, uint32_t numReplicas, const SlrGpuRenderParams* p, float* accum,
+                                   SlrGpuRenderStats* stats) {
+    if (!scenes || numReplicas == 0 || numReplicas > kMaxReplicas) { setError("slrgpu_render_multi: need 1..%u scene replicas", kMaxReplicas); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    for (uint32_t g = 0; g < numReplicas; ++g) {
+        int rc = checkRenderArgs(scenes[g], p);
+        if (rc) return rc;
+        if (scenes[g]->channels != scenes[0]->channels) { setError("slrgpu_render_multi: replicas differ in channel count"); return SLRGPU_ERR_INVALID_ARGUMENT; }
     }
-    cudaGetLastError();
-    // device -> pinned staging -> the caller's (pageable) buffer, in pieces: the host copy of piece k runs while piece
-    // k + 1 is still on the bus
-    constexpr int kPieces = 8;
-    const size_t piece = ((bytes / kPieces) + 4095) & ~(size_t)4095;
-    int pieces = 0;
-    for (size_t off = 0; off < bytes && pieces < kPieces; off += piece, ++pieces) {
-        const size_t len = std::min(piece, bytes - off);
-        SLRGPU_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(w->frameHost) + off, reinterpret_cast<const char*>(w->frame) + off, len,
-                                        cudaMemcpyDeviceToHost, w->stream));
-        SLRGPU_CUDA_TRY(cudaEventRecord(w->ringEvents[pieces], w->stream));
+    if (!accum) { setError("slrgpu_render_multi: null accumulation buffer"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    if (numReplicas == 1) return slrgpu_render(scenes[0], p, accum, stats);
+
+    const uint32_t n = p->spp_end - p->spp_begin;
+    const size_t bytes = (size_t)p->width * p->height * scenes[0]->channels * sizeof(float);
+    struct Replica {
+        RenderWorkspace* w = nullptr;
+        SlrGpuRenderParams params;
+        SlrGpuRenderStats st;
+        int rc = SLRGPU_OK;
+        bool rendered = false;
+        char error[256] = "";
+    };
+    std::vector<Replica> reps(numReplicas);
+    struct ReleaseAll {
+        std::vector<Replica>& r; SlrGpuScene* const* sc;
+        ~ReleaseAll() { for (size_t g = 0; g < r.size(); ++g) if (r[g].w) { cudaSetDevice(sc[g]->device); releaseWorkspace(sc[g]->device, r[g].w); } }
+    } releaseAll{reps, scenes};
+
+    auto work = [&](uint32_t g) {
+        Replica& r = reps[g];
+        SlrGpuScene* sc = scenes[g];
+        r.params = *p;
+        r.params.spp_begin = p->spp_begin + (uint32_t)((unsigned long long)n * g / numReplicas);
+        r.params.spp_end = p->spp_begin + (uint32_t)((unsigned long long)n * (g + 1) / numReplicas);
+        memset(&r.st, 0, sizeof(r.st));
+        cudaError_t e = cudaSetDevice(sc->device);
+        if (e != cudaSuccess) { r.rc = cudaFail(e, "cudaSetDevice"); }
+        // replica 0 always owns a (cleared) frame: it is the destination of the sum
+        const bool empty = r.params.spp_end <= r.params.spp_begin;
+        if (!r.rc && (!empty || g == 0)) {
+            r.rc = acquireWorkspace(sc, poolCapacity(empty ? p : &r.params), &r.w);
+            if (!r.rc) r.rc = r.w->ensureFrame(bytes);
+            if (!r.rc && (e = cudaMemsetAsync(r.w->frame, 0, bytes, r.w->stream)) != cudaSuccess) r.rc = cudaFail(e, "cudaMemsetAsync(frame)");
+            if (!r.rc && !empty) { r.rc = renderImpl(sc, &r.params, *r.w, r.w->frame, r.w->stream, &r.st); r.rendered = !r.rc; }
+            if (!r.rc && (e = cudaStreamSynchronize(r.w->stream)) != cudaSuccess) r.rc = cudaFail(e, "cudaStreamSynchronize");
+        }
+        if (r.rc) snprintf(r.error, sizeof(r.error), "%s", slrgpu_last_error());       // the message is thread local
+    };
+    {
+        std::vector<std::thread> pool;
+        for (uint32_t g = 1; g < numReplicas; ++g) pool.emplace_back(work, g);
+        work(0);
+        for (std::thread& t : pool) t.join();
     }
-    for (int k = 0; k < pieces; ++k) {
-        const size_t off = (size_t)k * piece;
-        SLRGPU_CUDA_TRY(cudaEventSynchronize(w->ringEvents[k]));
-        memcpy(reinterpret_cast<char*>(accum) + off, reinterpret_cast<const char*>(w->frameHost) + off, std::min(piece, bytes - off));
+    for (uint32_t g = 0; g < numReplicas; ++g)
+        if (reps[g].rc) { setError("slrgpu_render_multi: replica %u (device %d): %s", g, scenes[g]->device, reps[g].error); return reps[g].rc; }
+
+    // ---- the exchange step: frames of replicas 1.. summed into replica 0's frame, on replica 0's device
+    const int dev0 = scenes[0]->device;
+    SLRGPU_CUDA_TRY(cudaSetDevice(dev0));
+    RenderWorkspace& w0 = *reps[0].w;
+    PeerFrames peers;
+    peers.count = 0;
+    float* staging = nullptr;
+    struct StagingFree { float** p; ~StagingFree() { if (*p) cudaFree(*p); } } stagingFree{&staging};
+    const uint32_t count = (uint32_t)(bytes / sizeof(float));
+    cudaEvent_t r0, r1;
+    SLRGPU_CUDA_TRY(cudaEventCreate(&r0));
+    SLRGPU_CUDA_TRY(cudaEventCreate(&r1));
+    struct EventFree { cudaEvent_t a, b; ~EventFree() { cudaEventDestroy(a); cudaEventDestroy(b); } } eventFree{r0, r1};
+    SLRGPU_CUDA_TRY(cudaEventRecord(r0, w0.stream));
+    for (uint32_t g = 1; g < numReplicas; ++g) {
+        if (!reps[g].rendered) continue;
+        const int dev = scenes[g]->device;
+        bool direct = dev == dev0;
+        if (!direct) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, dev0, dev) == cudaSuccess && can) {
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(dev, 0);
+                direct = pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled;
+            }
+            cudaGetLastError();
+        }
+        if (direct) peers.frame[peers.count++] = reps[g].w->frame;
+        else {
+            // no peer access between the pair: copy through the driver and add from local memory
+            if (!staging) SLRGPU_CUDA_TRY(cudaMalloc(&staging, bytes));
+            SLRGPU_CUDA_TRY(cudaMemcpyPeerAsync(staging, dev0, reps[g].w->frame, dev, bytes, w0.stream));
+            PeerFrames one; one.count = 1; one.frame[0] = staging;
+            sumFramesKernel<<<148 * 4, 256, 0, w0.stream>>>(w0.frame, one, count);
+        }
     }
-    return SLRGPU_OK;
+    if (peers.count) sumFramesKernel<<<148 * 4, 256, 0, w0.stream>>>(w0.frame, peers, count);
+    SLRGPU_CUDA_TRY(cudaGetLastError());
+    SLRGPU_CUDA_TRY(cudaEventRecord(r1, w0.stream));
+    SLRGPU_CUDA_TRY(cudaStreamSynchronize(w0.stream));
+    float reduceMs = 0.0f;
+    cudaEventElapsedTime(&reduceMs, r0, r1);
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        for (uint32_t g = 0; g < numReplicas; ++g) {
+            const SlrGpuRenderStats& s = reps[g].st;
+            stats->paths += s.paths; stats->rays += s.rays; stats->extend_rays += s.extend_rays; stats->shadow_rays += s.shadow_rays;
+            stats->kernel_launches += s.kernel_launches; stats->waves = std::max(stats->waves, s.waves);
+            stats->device_ms = std::max(stats->device_ms, s.device_ms);
+            for (int c = 0; c < 9; ++c) stats->class_hits[c] += s.class_hits[c];
+            stats->tail_paths += s.tail_paths; stats->tail_waves = std::max(stats->tail_waves, s.tail_waves);
+        }
+        stats->kernel_launches += peers.count ? 1 : 0;
+        stats->device_ms += reduceMs;          // slowest replica + the exchange step
+        stats->other_ms = reduceMs;
+    }
+    return downloadFrame(w0, accum, bytes);
 }
 
 }  // extern "C"

@@ -150,7 +150,9 @@ SLRGPU_API int slrhost_render_range(SlrHostScene* s, int device, int width, int 
         settings.addItem(RenderSettingItem::Brightness, s->context.brightness);
         settings.addItem(RenderSettingItem::RNGSeed, (int32_t)(seed != 0 ? seed : s->context.rngSeed));
         GPUPathTracingRenderer renderer(spp > 0 ? (uint32_t)spp : s->context.samples);
-        renderer.device = device;
+        // device >= 0: that one device; device < 0: every visible device, the frame's samples partitioned over them
+        renderer.device = device >= 0 ? device : 0;
+        renderer.deviceCount = device >= 0 ? 1 : 0;
         renderer.sampleBegin = (uint32_t)spp_begin;
         renderer.exportProgressiveImages = bmp_dir != nullptr;
         if (bmp_dir) renderer.outputDirectory = bmp_dir;
@@ -161,7 +163,7 @@ SLRGPU_API int slrhost_render_range(SlrHostScene* s, int device, int width, int 
         if (stats) {
             const RenderStatistics& st = renderer.lastStatistics;
             stats[0] = (double)st.paths; stats[1] = (double)st.rays; stats[2] = st.deviceSeconds; stats[3] = st.wallSeconds;
-            stats[4] = st.uploadSeconds; stats[5] = sensor.channels();
+            stats[4] = st.uploadSeconds; stats[5] = sensor.channels() + 1000.0 * st.devices;     // channels + 1000 x devices used
         }
         s->render.sensor->bindExternal(nullptr);
         return 0;

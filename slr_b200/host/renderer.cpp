@@ -1,5 +1,6 @@
 #include "renderer.h"
 #include "spectrum.h"
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -82,14 +83,26 @@ void GPUPathTracingRenderer::render(const RenderScene& scene, const RenderSettin
     lastStatistics = RenderStatistics();
     SlrGpuSceneDesc desc;
     scene.flat.describe(&desc);
-    SlrGpuScene* gpu = nullptr;
+    // the scene goes to every device the frame is split over (replicated)
+    const int visible = slrgpu_device_count();
+    int count = deviceCount > 0 ? deviceCount : std::max(1, visible - device);
+    if (visible > 0 && device + count > visible) count = std::max(1, visible - device);
+    // more devices than samples make no sense: a device would render nothing
+    count = (int)std::min<uint32_t>((uint32_t)count, std::max(1u, m_samplesPerPixel));
+    std::vector<SlrGpuScene*> replicas;
+    struct DestroyAll { std::vector<SlrGpuScene*>& r; ~DestroyAll() { for (SlrGpuScene* g : r) slrgpu_scene_destroy(g); } } destroyAll{replicas};
     auto up0 = std::chrono::steady_clock::now();
-    if (slrgpu_scene_create(&desc, device, &gpu) != SLRGPU_OK)
-        throw std::runtime_error(std::string("slrgpu_scene_create failed: ") + slrgpu_last_error());
+    for (int g = 0; g < count; ++g) {
+        SlrGpuScene* gpu = nullptr;
+        if (slrgpu_scene_create(&desc, device + g, &gpu) != SLRGPU_OK)
+            throw std::runtime_error(std::string("slrgpu_scene_create failed: ") + slrgpu_last_error());
+        replicas.push_back(gpu);
+    }
     lastStatistics.uploadSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - up0).count();
-    const uint32_t channels = slrgpu_scene_channels(gpu);
+    lastStatistics.devices = (uint32_t)count;
+    const uint32_t channels = slrgpu_scene_channels(replicas[0]);
     if (exportProgressiveImages) sensor->init(W, H, channels);
-    else sensor->initForOverwrite(W, H, channels);      // slrgpu_render overwrites the whole frame
+    else sensor->initForOverwrite(W, H, channels);      // the render call overwrites the whole frame
 
     SlrGpuRenderParams p;
     std::memset(&p, 0, sizeof(p));
@@ -99,19 +112,20 @@ void GPUPathTracingRenderer::render(const RenderScene& scene, const RenderSettin
     p.time_end = settings.getFloat(RenderSettingItem::TimeEnd);
     p.rng_seed = settings.getInt(RenderSettingItem::RNGSeed);
     const float brightness = settings.getFloat(RenderSettingItem::Brightness);
+    // one frame segment [begin, end) of the sample range on all devices, into `dst` (overwritten)
+    auto renderSegment = [&](uint32_t begin, uint32_t end, float* dst) {
+        p.spp_begin = sampleBegin + begin; p.spp_end = sampleBegin + end;
+        SlrGpuRenderStats st;
+        const int rc = replicas.size() > 1 ? slrgpu_render_multi(replicas.data(), (uint32_t)replicas.size(), &p, dst, &st)
+                                           : slrgpu_render(replicas[0], &p, dst, &st);
+        if (rc != SLRGPU_OK) throw std::runtime_error(std::string("slrgpu_render failed: ") + slrgpu_last_error());
+        lastStatistics.paths += st.paths; lastStatistics.rays += st.rays;
+        lastStatistics.deviceSeconds += st.device_ms * 1e-3;
+    };
 
     if (!exportProgressiveImages) {
-        // one GPU call for the whole sample range, straight into the sensor
-        p.spp_begin = sampleBegin; p.spp_end = sampleBegin + m_samplesPerPixel;
-        SlrGpuRenderStats st;
-        if (slrgpu_render(gpu, &p, sensor->data(), &st) != SLRGPU_OK) {
-            std::string msg = std::string("slrgpu_render failed: ") + slrgpu_last_error();
-            slrgpu_scene_destroy(gpu);
-            throw std::runtime_error(msg);
-        }
-        lastStatistics.paths = st.paths; lastStatistics.rays = st.rays;
-        lastStatistics.deviceSeconds = st.device_ms * 1e-3;
-        slrgpu_scene_destroy(gpu);
+        // one call for the whole sample range, straight into the sensor
+        renderSegment(0, m_samplesPerPixel, sensor->data());
         lastStatistics.wallSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
         return;
     }
@@ -120,19 +134,11 @@ void GPUPathTracingRenderer::render(const RenderScene& scene, const RenderSettin
     // images, PathTracingRenderer.cpp:63-65,83-94). Each segment [begin, end) is one GPU render call.
     uint32_t begin = 0, exportAt = 1, imgIdx = 0;
     while (begin < m_samplesPerPixel) {
-        uint32_t end = exportProgressiveImages ? std::min(exportAt, m_samplesPerPixel) : m_samplesPerPixel;
-        p.spp_begin = sampleBegin + begin; p.spp_end = sampleBegin + end;
-        SlrGpuRenderStats st;
-        if (slrgpu_render(gpu, &p, pass.data(), &st) != SLRGPU_OK) {
-            std::string msg = std::string("slrgpu_render failed: ") + slrgpu_last_error();
-            slrgpu_scene_destroy(gpu);
-            throw std::runtime_error(msg);
-        }
+        const uint32_t end = std::min(exportAt, m_samplesPerPixel);
+        renderSegment(begin, end, pass.data());
         float* dst = sensor->data();
         for (size_t i = 0; i < pass.size(); ++i) dst[i] += pass[i];
-        lastStatistics.paths += st.paths; lastStatistics.rays += st.rays;
-        lastStatistics.deviceSeconds += st.device_ms * 1e-3;
-        if (exportProgressiveImages && end == exportAt) {
+        if (end == exportAt) {
             char name[64];
             std::snprintf(name, sizeof(name), "%03u.bmp", imgIdx);
             sensor->saveImage(outputDirectory + "/" + name, brightness / end);
@@ -143,7 +149,6 @@ void GPUPathTracingRenderer::render(const RenderScene& scene, const RenderSettin
         }
         begin = end;
     }
-    slrgpu_scene_destroy(gpu);
     lastStatistics.wallSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
 }
 

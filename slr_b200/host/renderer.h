@@ -95,7 +95,11 @@ public:
     mutable RenderStatistics lastStatistics;
     bool exportProgressiveImages = true;     // NNN.bmp at 1, 2, 4, ... samples like the reference
     std::string outputDirectory = ".";
+    // First device and number of devices the frame's samples are partitioned over (slrgpu_render_multi: scene replicated,
+    // sample ranges split, accumulation buffers summed over NVLink onto `device`). deviceCount 0 = every visible device
+    // from `device` on -- what a scene file's setRenderer("PT") gets; 1 = the single device `device`.
     int device = 0;
+    int deviceCount = 0;
     explicit GPUPathTracingRenderer(uint32_t spp) : m_samplesPerPixel(spp) {}
     uint32_t samplesPerPixel() const { return m_samplesPerPixel; }
     void render(const RenderScene& scene, const RenderSettings& settings) const override;

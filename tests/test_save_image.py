@@ -64,7 +64,9 @@ def test_gpu_renderer_export_cadence_and_bytes(tmp_path):
     assert files == ["000.bmp", "001.bmp", "002.bmp", "003.bmp"]
     # 003.bmp = the sensor after 8 samples (same RNG keys: the first 8 samples of the 12-sample call)
     mine = str(tmp_path / "mine.bmp")
-    capi.save_bmp(mine, accum8, 1.0 / 8, hs.sensitivity() if hasattr(hs, "sensitivity") else float(hs.desc.camera.sensitivity))
+    cam = hs.desc.camera        # PerspectiveCamera's default sensitivity: 1 / lens area (PerspectiveCamera.cpp:15-24)
+    sens = float(cam.sensitivity) if cam.sensitivity > 0 else float(np.float32(1.0 / (np.pi * cam.lens_radius * cam.lens_radius)))
+    capi.save_bmp(mine, accum8, 1.0 / 8, sens)
     with open(mine, "rb") as f, open(os.path.join(bdir, "003.bmp"), "rb") as g:
         a, b = ru.bmp_pixels(f.read(), w, h)[1], ru.bmp_pixels(g.read(), w, h)[1]
     # summation order of the progressive segments differs from one 8-sample call by fp32 rounding: at most one code value
