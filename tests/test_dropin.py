@@ -1,0 +1,85 @@
+"""The reference-side binding, compiled and run: integration/GPUPathTracingRenderer.{h,cpp} is a SLR::Renderer subclass
+built INSIDE the reference build (oracle/Makefile `dropin` -> oracle/_ref/slr_gpu: the reference's own HostProgram flow --
+its scene interpreter, its scene graph, its SBVH builder and QBVH collapse, its ImageSensor -- with the Renderer swapped
+for the GPU one, which flattens the SLR::Scene it receives into include/slrgpu.h's tables and calls the C ABI).
+Nothing of libslrhost.so is involved: this is the drop-in of SURVEY.md section 8b proven end to end, and an independent
+producer of SlrGpuSceneDesc next to the repo's own host library.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import render_util as ru
+from slr_b200 import capi
+
+SLR_GPU = os.path.join(ru.ROOT, "oracle", "_ref", "slr_gpu")
+needs_binary = pytest.mark.skipif(not os.access(SLR_GPU, os.X_OK), reason="oracle/_ref/slr_gpu not built on this machine")
+
+
+def run_slr_gpu(scene_path, dump=True):
+    d = os.path.dirname(os.path.abspath(scene_path))
+    out = os.path.join(d, "dropin_sensor.bin")
+    p = subprocess.run([SLR_GPU, os.path.basename(scene_path)] + ([out] if dump else []), capture_output=True, text=True, cwd=d, timeout=1200)
+    return p, out
+
+
+def read_sensor(path):
+    with open(path, "rb") as f:
+        w, h, c = np.frombuffer(f.read(12), np.uint32)
+        return np.frombuffer(f.read(), np.float32).reshape(h, w, c).copy()
+
+
+@needs_binary
+@pytest.mark.parametrize("name", ["spheres", "materials", "instanced", "lamps", "cutout"])
+def test_exported_scene_passes_the_library_validation(name, tmp_path):
+    """CPU: the exporter's tables are accepted by slrgpu_scene_create's validation pass -- without a device the call gets as
+    far as SLRGPU_ERR_NO_DEVICE (validation runs first), with one the render succeeds."""
+    path = ru.scene_file(name, str(tmp_path), 24, 24, 2)
+    p, _ = run_slr_gpu(path)
+    if capi.gpu.slrgpu_device_count() == 0:
+        assert p.returncode == 1 and "no CUDA device" in p.stderr, p.stderr[-500:]
+    else:
+        assert p.returncode == 0, p.stderr[-500:]
+
+
+@needs_binary
+def test_unsupported_content_fails_loudly(tmp_path):
+    path = ru.scene_file("ibl", str(tmp_path), 24, 24, 2)
+    p, _ = run_slr_gpu(path)
+    assert p.returncode == 1 and "environment lighting is not exported" in p.stderr
+
+
+@needs_binary
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,size,spp", [("spheres", 96, 256), ("materials", 96, 256), ("instanced", 96, 128), ("cutout", 96, 256)])
+def test_dropin_renders_like_the_reference(name, size, spp, tmp_path):
+    """The sensor the GPU renderer leaves behind (read through the reference's own ImageSensor::pixel) against the
+    reference's PathTracingRenderer on the same file: the image-parity bars of tests/test_gpu_render.py. And against the
+    repo's own host library on the same file: same RNG keys, same trees -> the same image up to fp32 summation order."""
+    assert capi.gpu.slrgpu_device_count() > 0
+    path = ru.scene_file(name, str(tmp_path), size, size, spp)
+    p, out = run_slr_gpu(path)
+    assert p.returncode == 0, p.stderr[-800:]
+    sensor = read_sensor(out)
+    assert sensor.shape == (size, size, 16) and np.isfinite(sensor).all()
+    gpu = capi.accum_to_rgb(sensor, 1.0 / spp)
+    ref1 = capi.accum_to_rgb(ru.run_ref_render(path, spp, size, size, seed=1509761209)[0], 1.0 / spp)
+    ref2 = capi.accum_to_rgb(ru.run_ref_render(path, spp, size, size, seed=20240229)[0], 1.0 / spp)
+    (ref1, gpu, ref2), d1 = ru.sanitize_reference(ref1, gpu, ref2)
+    (ref2, gpu, ref1), d2 = ru.sanitize_reference(ref2, gpu, ref1)
+    floor = ru.rel_rmse(ref2, ref1, trim=0.005)
+    got = ru.rel_rmse(gpu, ref1, trim=0.005)
+    assert got <= 1.25 * floor, f"relRMSE {got:.4f} vs noise floor {floor:.4f}"
+    clip = float(np.percentile(ref1, 99.8))
+    ratio = np.minimum(gpu, clip).reshape(-1, 3).mean(0) / np.minimum(ref1, clip).reshape(-1, 3).mean(0)
+    assert np.all(np.abs(ratio - 1.0) < 0.01), f"image mean ratio {ratio}"
+    # the same file through the repo's own host library (seed = the file's default, like slr_gpu)
+    with capi.stdout_to_stderr():
+        hs = capi.read_scene(path)
+    mine, _ = capi.host_render(hs, size, size, spp, device=0)
+    mine = capi.accum_to_rgb(mine, 1.0 / spp)
+    np.testing.assert_allclose(ru.block_means(capi.accum_to_rgb(sensor, 1.0 / spp), 8), ru.block_means(mine, 8), rtol=2e-3, atol=1e-6)
+    # the progressive BMPs the renderer wrote through the reference's own ImageSensor::saveImage
+    assert os.path.exists(os.path.join(os.path.dirname(path), "000.bmp"))
