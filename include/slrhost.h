@@ -73,6 +73,16 @@ SLRGPU_API int slrhost_write_assbin(const char* path, const float* positions, co
                                     const uint32_t* indices, uint32_t num_triangles, const char* material_name,
                                     const float* diffuse_rgb);
 SLRGPU_API int slrhost_write_exr(const char* path, uint32_t width, uint32_t height, const float* rgba);
+/* The EXR reader behind Image2D / setEnvironment (scanline, uncompressed, half or float channels): width*height*4 floats
+ * (R, G, B, A; a missing A reads 1), top row first. rgba may be NULL to query the size. */
+SLRGPU_API int slrhost_read_exr(const char* path, uint32_t* width, uint32_t* height, float* rgba, uint64_t capacity_floats);
+
+/* Decodes a PNG the way the reference's loadPNG asks libpng to (image_loader.cpp:186-280: strip 16 -> 8 bits, unpack
+ * 1/2/4-bit samples, palette -> RGB, 0xFF filler after RGB, libpng's 8-bit gamma table for screen gamma 1.0 -- or 2.2 with
+ * gamma_correction -- against the file's gAMA or 0.45455). *channels = 1 (grey) or 4, | 0x100 when the 4th byte is the
+ * file's alpha. pixels (may be NULL to query the size) receives width*height*(channels & 0xFF) bytes, top row first. */
+SLRGPU_API int slrhost_decode_png(const char* path, int gamma_correction, uint32_t* width, uint32_t* height, uint32_t* channels,
+                                  uint8_t* pixels, uint64_t capacity);
 
 SLRGPU_API void slrhost_scene_destroy(SlrHostScene* s);
 /* Fills `desc` with pointers into the scene's buffers (valid until slrhost_scene_destroy). */

@@ -498,6 +498,34 @@ def probe_shading(gpu_scene, probes):
     return out
 
 
+host.slrhost_decode_png.restype = C.c_int
+host.slrhost_decode_png.argtypes = [C.c_char_p, C.c_int, C.POINTER(c_u32), C.POINTER(c_u32), C.POINTER(c_u32), PU8, c_u64]
+
+
+def decode_png(path, gamma_correction=False):
+    """slrhost_decode_png: (pixels[h, w, c] uint8, has_alpha) the way the reference's loadPNG + libpng deliver them."""
+    w, h, ch = c_u32(), c_u32(), c_u32()
+    _host_check(host.slrhost_decode_png(os.fsencode(path), int(gamma_correction), C.byref(w), C.byref(h), C.byref(ch), None, 0), "slrhost_decode_png")
+    c = ch.value & 0xFF
+    out = np.empty((h.value, w.value, c), np.uint8)
+    _host_check(host.slrhost_decode_png(os.fsencode(path), int(gamma_correction), C.byref(w), C.byref(h), C.byref(ch),
+                                        out.ctypes.data_as(PU8), out.size), "slrhost_decode_png")
+    return out, bool(ch.value & 0x100)
+
+
+host.slrhost_read_exr.restype = C.c_int
+host.slrhost_read_exr.argtypes = [C.c_char_p, C.POINTER(c_u32), C.POINTER(c_u32), PF, c_u64]
+
+
+def read_exr(path):
+    """slrhost_read_exr: rgba[h, w, 4] float32 through the host library's EXR reader."""
+    w, h = c_u32(), c_u32()
+    _host_check(host.slrhost_read_exr(os.fsencode(path), C.byref(w), C.byref(h), None, 0), "slrhost_read_exr")
+    out = np.empty((h.value, w.value, 4), np.float32)
+    _host_check(host.slrhost_read_exr(os.fsencode(path), C.byref(w), C.byref(h), _pf(out), out.size), "slrhost_read_exr")
+    return out
+
+
 def accum_to_rgb(accum, scale):
     h, w, c = accum.shape
     rgb = np.empty((h, w, 3), np.float32)

@@ -9,6 +9,11 @@
 #ifndef SLR_TRACE_MIN_BLOCKS
 #define SLR_TRACE_MIN_BLOCKS 1
 #endif
+// the instanced walk sits at the 80-register boundary between 6 and 5 resident blocks per SM (registers are allocated
+// 8 at a time per thread): bounded for 6
+#ifndef SLR_TRACE_MIN_BLOCKS_INSTANCED
+#define SLR_TRACE_MIN_BLOCKS_INSTANCED 6
+#endif
 
 namespace slrgpu {
 
@@ -16,7 +21,7 @@ namespace slrgpu {
 // ALPHA: the scene has alpha-mapped (cut-out) triangles (TriangleMesh.cpp:160-168); such scenes run the general
 // instantiation <INSTANCES = true, ALPHA = true>, which handles flat scenes too.
 template <bool INSTANCES, bool COUNT, bool ALPHA>
-__global__ void __launch_bounds__(kTraceBlock, SLR_TRACE_MIN_BLOCKS)
+__global__ void __launch_bounds__(kTraceBlock, (INSTANCES && !ALPHA) ? SLR_TRACE_MIN_BLOCKS_INSTANCED : SLR_TRACE_MIN_BLOCKS)
 extendKernel(const DeviceScene s, PathQueue q, HitBuffer hits, WavefrontCounters* counters) {
     TraversalCounters cnt = {0, 0};
     bool overflow = false;
@@ -26,7 +31,7 @@ extendKernel(const DeviceScene s, PathQueue q, HitBuffer hits, WavefrontCounters
 }
 
 template <bool INSTANCES, int NC, bool COUNT, bool ALPHA>
-__global__ void __launch_bounds__(kTraceBlock, SLR_TRACE_MIN_BLOCKS)
+__global__ void __launch_bounds__(kTraceBlock, (INSTANCES && !ALPHA) ? SLR_TRACE_MIN_BLOCKS_INSTANCED : SLR_TRACE_MIN_BLOCKS)
 shadowKernel(const DeviceScene s, ShadowQueue q, float* __restrict__ accum, WavefrontCounters* counters) {
     TraversalCounters cnt = {0, 0};
     bool overflow = false;

@@ -170,18 +170,10 @@ constexpr uint32_t kMaxChunk = 256;
 #ifndef SLR_WALK_REFILL_IDLE
 #define SLR_WALK_REFILL_IDLE 8
 #endif
-// SLR_WALK_PREFETCH: every inner child a node visit pushes and the first record of every leaf child it queues are
-// prefetched into L2 at once (prefetch.global.L2, one instruction per 128 B node). A pushed child is popped only after
-// the nearer siblings' subtrees are done, so on a scene larger than L2 (C5: 0.8 GB of nodes + records) its DRAM latency
-// is overlapped with that work instead of being paid at the pop. Off for cache-resident scenes (nothing to gain).
-#ifndef SLR_WALK_PREFETCH
-#define SLR_WALK_PREFETCH 0
-#endif
-__device__ __forceinline__ void prefetchL2(const void* p) {
-#if SLR_WALK_PREFETCH
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#endif
-}
+// (Measured and dropped, round 2: an L2 prefetch -- prefetch.global.L2 -- of every pushed inner child and of the first record
+// of every queued leaf child at push time: C5 (10 M triangles, scene larger than L2) 2581 -> 1797 Mrays/s, C4 299 -> 288
+// Mpaths/s. The walk already keeps the memory system busy; the extra requests for nodes that are never popped cost more
+// than the latency they hide. profiles/r02_rejected_experiments.md)
 constexpr int kStepsPerRound = SLR_WALK_STEPS_PER_ROUND;     // node visits between two refill checks (sweep: profiles/r01_variant_sweep.md)
 constexpr int kRefillIdle = SLR_WALK_REFILL_IDLE;            // idle lanes that trigger a refill
 
@@ -232,12 +224,17 @@ struct LeafQueue {
     }
 };
 
+#ifndef SLR_WALK_KEEP_WORLD_RCP
+#define SLR_WALK_KEEP_WORLD_RCP 1
+#endif
 struct InstanceWalkState {
     LeafQueue leaves;        // of the level the lane is walking
     LeafQueue saved;         // top-level queue while inside an instance
     float wox, woy, woz, wdx, wdy, wdz;      // world-space ray while inside an instance ...
+#if SLR_WALK_KEEP_WORLD_RCP
     float wix, wiy, wiz;                     // ... with its reciprocal direction and sign word (three IEEE reciprocals are
     uint32_t wpos;                           // ~30 instructions: kept, not recomputed, when the walk leaves the instance)
+#endif
     uint32_t curInst;        // SLRGPU_INVALID_ID at the top level
 };
 
@@ -259,7 +256,11 @@ __device__ __forceinline__ void walkNode(const DeviceScene& s, WalkState& w, Ins
     if (--w.sp > 0) w.top = stack[w.sp - 1];
     if (INSTANCES && entry == kReturnMarker) {
         r.ox = iw.wox; r.oy = iw.woy; r.oz = iw.woz; r.dx = iw.wdx; r.dy = iw.wdy; r.dz = iw.wdz;   // tmax carries over (SurfaceObject.cpp:314)
+#if SLR_WALK_KEEP_WORLD_RCP
         w.ix = iw.wix; w.iy = iw.wiy; w.iz = iw.wiz; w.pos = iw.wpos;
+#else
+        walkSetRay(w);
+#endif
         iw.leaves = iw.saved;
         iw.curInst = SLRGPU_INVALID_ID;
     } else {
@@ -297,7 +298,6 @@ __device__ __forceinline__ void walkNode(const DeviceScene& s, WalkState& w, Ins
                 if (w.sp >= kStackSize) { overflow = true; continue; }
                 stack[w.sp++] = c & 0x07FFFFFFu;
                 w.top = c & 0x07FFFFFFu;
-                prefetchL2(s.nodes + (size_t)(c & 0x07FFFFFFu) * 8);
             }
             // leaf children in visiting order: the first becomes the current range, up to three wait
             uint32_t q0 = kEmptyChild, q1 = kEmptyChild, q2 = kEmptyChild, q3 = kEmptyChild;
@@ -305,7 +305,6 @@ __device__ __forceinline__ void walkNode(const DeviceScene& s, WalkState& w, Ins
             for (int i = 0; i < 4; ++i) {
                 const uint32_t c = ch[i];
                 if (c != kEmptyChild && (c >> 31)) {
-                    prefetchL2(s.leaves + (size_t)(c & 0x07FFFFFFu) * 3);
                     if (q0 == kEmptyChild) q0 = c;
                     else if (q1 == kEmptyChild) q1 = c;
                     else if (q2 == kEmptyChild) q2 = c;
@@ -364,7 +363,9 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
                         const uint32_t instId = id & 0x7FFFFFFFu;
                         const SlrGpuInstance* inst = s.instances + instId;
                         iw.wox = r.ox; iw.woy = r.oy; iw.woz = r.oz; iw.wdx = r.dx; iw.wdy = r.dy; iw.wdz = r.dz;
+#if SLR_WALK_KEEP_WORLD_RCP
                         iw.wix = w.ix; iw.wiy = w.iy; iw.wiz = w.iz; iw.wpos = w.pos;
+#endif
                         iw.saved = iw.leaves;
                         iw.leaves.clear();
                         float lx, ly, lz, mx, my, mz;

@@ -1,5 +1,6 @@
 #include "images.h"
 #include "exr.h"
+#include "png.h"
 #include <map>
 #include <stdexcept>
 
@@ -41,13 +42,65 @@ void uvs_to_sRGB(SpectrumType type, const float uvs[3], float rgb[3]) {
     }
 }
 
+// An 8-bit PNG converted to the texel format the renderer samples, case by case as TiledImage2D's constructor does
+// (libSLR/Core/Image.h:121-335): RGB_8x4 / RGBA8x4 / Gray8 sources x AsIs / NormalTexture / AlphaTexture store modes.
+static Image2DRef loadPNGImage(const std::string& path, ImageStoreMode mode, SpectrumType type, bool rgbMode) {
+    png::Image src;
+    std::string err;
+    if (!png::load(path, false, &src, &err)) throw std::runtime_error(err);        // gammaCorrection = false: API.hpp:33
+    auto img = std::make_shared<Image2D>();
+    img->width = src.width; img->height = src.height; img->spectrumType = type;
+    const size_t n = (size_t)src.width * src.height;
+    const uint8_t* p = src.pixels.data();
+    if (src.channels == 1) {
+        if (mode == ImageStoreMode::NormalTexture) throw std::runtime_error("a grey-scale image cannot be used as a normal map: " + path);
+        img->format = SLRGPU_IMG_GRAY8;
+        img->data.assign(p, p + n);
+        return img;
+    }
+    if (mode == ImageStoreMode::NormalTexture) {
+        img->format = SLRGPU_IMG_RGB8x3;
+        img->data.resize(n * 3);
+        for (size_t i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) img->data[3 * i + c] = p[4 * i + c];
+    } else if (mode == ImageStoreMode::AlphaTexture) {
+        img->format = SLRGPU_IMG_GRAY8;
+        img->data.resize(n);
+        for (size_t i = 0; i < n; ++i) img->data[i] = src.hasAlpha ? p[4 * i + 3] : p[4 * i];      // RGBA: .a, RGB_: .r
+    } else if (rgbMode) {
+        if (src.hasAlpha) { img->format = SLRGPU_IMG_RGBA8x4; img->data.assign(p, p + n * 4); }
+        else {
+            img->format = SLRGPU_IMG_RGB8x3;
+            img->data.resize(n * 3);
+            for (size_t i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) img->data[3 * i + c] = p[4 * i + c];
+        }
+    } else {
+        const int stride = src.hasAlpha ? 4 : 3;
+        img->format = src.hasAlpha ? SLRGPU_IMG_UVSA16Fx4 : SLRGPU_IMG_UVS16Fx3;
+        img->data.resize(n * stride * 2);
+        uint16_t* dst = reinterpret_cast<uint16_t*>(img->data.data());
+        for (size_t i = 0; i < n; ++i) {
+            const float rgb[3] = {p[4 * i] / 255.0f, p[4 * i + 1] / 255.0f, p[4 * i + 2] / 255.0f};
+            float uvs[3];
+            sRGB_to_uvs(type, rgb, uvs);
+            for (int c = 0; c < 3; ++c) dst[stride * i + c] = exr::floatToHalf(uvs[c]);
+            if (src.hasAlpha) dst[4 * i + 3] = exr::floatToHalf(p[4 * i + 3] / 255.0f);
+        }
+    }
+    return img;
+}
+
 Image2DRef loadImageCached(const std::string& path, ImageStoreMode mode, SpectrumType type, bool rgbMode) {
     static std::map<std::string, Image2DRef> cache;
     auto it = cache.find(path);
     if (it != cache.end()) return it->second;      // keyed by path only, as the reference does
     const size_t dot = path.find_last_of('.');
     const std::string ext = dot == std::string::npos ? "" : path.substr(dot + 1);
-    if (ext != "exr") throw std::runtime_error("image format ." + ext + " is not supported by this build (only uncompressed .exr): " + path);
+    if (ext == "png") {
+        Image2DRef img = loadPNGImage(path, mode, type, rgbMode);
+        cache[path] = img;
+        return img;
+    }
+    if (ext != "exr") throw std::runtime_error("image format ." + ext + " is not supported by this build (.png and uncompressed .exr are): " + path);
     exr::Image src;
     std::string err;
     if (!exr::load(path, &src, &err)) throw std::runtime_error(err);

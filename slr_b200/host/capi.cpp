@@ -2,6 +2,7 @@
 #include "../../include/slrhost.h"
 #include "scene.h"
 #include "renderer.h"
+#include "assets/png.h"
 #include "assets/assbin.h"
 #include "assets/exr.h"
 #include "parser/scene_parser.h"
@@ -212,6 +213,20 @@ SLRGPU_API int slrhost_save_bmp(const char* path, const float* accum, int width,
     } catch (const std::exception& e) { return fail("%s", e.what()); }
 }
 
+SLRGPU_API int slrhost_decode_png(const char* path, int gamma_correction, uint32_t* width, uint32_t* height, uint32_t* channels,
+                                  uint8_t* pixels, uint64_t capacity) {
+    if (!path || !width || !height || !channels) return fail("slrhost_decode_png: null argument");
+    slr::png::Image img;
+    std::string err;
+    if (!slr::png::load(path, gamma_correction != 0, &img, &err)) return fail("%s", err.c_str());
+    *width = img.width; *height = img.height; *channels = img.channels | (img.hasAlpha ? 0x100u : 0u);
+    if (pixels) {
+        if (capacity < img.pixels.size()) return fail("slrhost_decode_png: output buffer too small");
+        std::memcpy(pixels, img.pixels.data(), img.pixels.size());
+    }
+    return 0;
+}
+
 SLRGPU_API int slrhost_accum_to_rgb(const float* accum, int width, int height, int channels, float scale, float* rgb) {
     if (!accum || !rgb || width <= 0 || height <= 0) return fail("slrhost_accum_to_rgb: invalid argument");
     try {
@@ -261,6 +276,19 @@ SLRGPU_API int slrhost_write_assbin(const char* path, const float* positions, co
 SLRGPU_API int slrhost_write_exr(const char* path, uint32_t width, uint32_t height, const float* rgba) {
     if (!path || !rgba || !width || !height) return fail("slrhost_write_exr: invalid argument");
     return exr::save(path, width, height, rgba) ? 0 : fail("cannot write %s", path);
+}
+
+SLRGPU_API int slrhost_read_exr(const char* path, uint32_t* width, uint32_t* height, float* rgba, uint64_t capacity_floats) {
+    if (!path || !width || !height) return fail("slrhost_read_exr: null argument");
+    exr::Image img;
+    std::string err;
+    if (!exr::load(path, &img, &err)) return fail("%s", err.c_str());
+    *width = img.width; *height = img.height;
+    if (rgba) {
+        if (capacity_floats < img.rgba.size()) return fail("slrhost_read_exr: output buffer too small");
+        for (size_t i = 0; i < img.rgba.size(); ++i) rgba[i] = exr::halfToFloat(img.rgba[i]);
+    }
+    return 0;
 }
 
 SLRGPU_API void slrhost_scene_destroy(SlrHostScene* s) { delete s; }

@@ -428,8 +428,8 @@ void registerBuiltins(Interpreter& in) {
                               ImageStoreMode mode;
                               const std::string& ms = a.at("mode").s;
                               if (ms == "AsIs") mode = ImageStoreMode::AsIs;
-                              else if (ms == "NormalTexture") mode = ImageStoreMode::NormalTexture;
-                              else if (ms == "AlphaTexture") mode = ImageStoreMode::AlphaTexture;
+                              else if (ms == "Normal") mode = ImageStoreMode::NormalTexture;          // strToImageStoreMode, API.cpp:35-45
+                              else if (ms == "Alpha") mode = ImageStoreMode::AlphaTexture;
                               else in.fail("Specified image store mode is invalid.");
                               SpectrumType t;
                               if (!strToSpectrumType(a.at("type").s, &t)) in.fail("Specified spectrum type is invalid.");

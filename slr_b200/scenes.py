@@ -568,7 +568,64 @@ def write_cutout(directory, width=128, height=128, spp=64):
     return path
 
 
+def _tex_quad(name, parent, verts, normal, tangent, uv_scale, mat_setup, group):
+    """A quad whose material group is written out by the caller (`group` = the tuple after the material: normal / alpha maps)."""
+    uv = [(0, 0), (uv_scale, 0), (uv_scale, uv_scale), (0, uv_scale)]
+    vs = ",\n".join(f"    (({v[0]}, {v[1]}, {v[2]}), ({normal[0]}, {normal[1]}, {normal[2]}), "
+                    f"({tangent[0]}, {tangent[1]}, {tangent[2]}), ({uv[i][0]}, {uv[i][1]}))" for i, v in enumerate(verts))
+    lines = list(mat_setup) + [f'{name} = createMesh(\n  (\n{vs}\n  ),\n  (\n    (surfMat, {group}((0, 1, 2), (0, 2, 3))),\n  )\n);',
+                               f"addChild({parent}, {name});"]
+    return "\n".join(lines) + "\n"
+
+
+def write_textured(directory, width=128, height=128, spp=64):
+    """Image textures ON SURFACES (Textures/image_textures.cpp:13-79,136-209): a PNG colour texture on a matte panel, an EXR
+    (half float) colour texture on another, a PNG normal map on a Ward panel, and a PNG whose alpha channel cuts holes into
+    a third (ImageStoreMode AsIs / NormalTexture / AlphaTexture, Image.h:121-335). Image2D takes paths as written, i.e.
+    relative to the working directory (API.cpp:466): the scene file names the images by absolute path."""
+    from PIL import Image as PILImage
+    os.makedirs(os.path.join(directory, "images"), exist_ok=True)
+    img = os.path.abspath(os.path.join(directory, "images"))
+    yy, xx = np.mgrid[0:64, 0:64]
+    colour = np.stack([(xx * 4) % 256, (yy * 4) % 256, ((xx // 8 + yy // 8) % 2) * 200 + 30], -1).astype(np.uint8)
+    PILImage.fromarray(colour, "RGB").save(os.path.join(img, "colour.png"))
+    # bumps: a grid of domes, encoded as (n * 0.5 + 0.5) * 255 (the loader's gamma table is applied by both sides)
+    u, v = (xx % 16 - 7.5) / 8.0, (yy % 16 - 7.5) / 8.0
+    r2 = np.minimum(u * u + v * v, 0.8)
+    n = np.stack([-u, -v, np.sqrt(1.0 - r2) + 0.6], -1)
+    n /= np.linalg.norm(n, axis=-1, keepdims=True)
+    PILImage.fromarray(np.clip((n * 0.5 + 0.5) * 255 + 0.5, 0, 255).astype(np.uint8), "RGB").save(os.path.join(img, "normal.png"))
+    holes = np.full((64, 64, 4), 255, np.uint8)
+    holes[..., :3] = (90, 160, 220)
+    holes[((xx % 16 - 8) ** 2 + (yy % 16 - 8) ** 2) < 25, 3] = 0
+    PILImage.fromarray(holes, "RGBA").save(os.path.join(img, "holes.png"))
+    rgba = np.zeros((32, 32, 4), np.float32)
+    gy, gx = np.mgrid[0:32, 0:32]
+    rgba[..., 0] = 0.15 + 0.7 * gx / 31.0; rgba[..., 1] = 0.15 + 0.7 * gy / 31.0; rgba[..., 2] = 0.3; rgba[..., 3] = 1.0
+    capi.write_exr(os.path.join(img, "ramp.exr"), rgba)
+
+    t = f'setRenderer("method": "PT", ("samples": {spp},));\nsetRenderSettings("width": {width}, "height": {height});\n\n'
+    t += cornell_box_shell()
+    t += _tex_quad("pngPanel", "CBNode", [(-1.3, 0.3, -2.2), (-0.2, 0.3, -2.2), (-0.2, 1.4, -2.2), (-1.3, 1.4, -2.2)], (0, 0, 1), (1, 0, 0), 1.0,
+                   [f'diffuseTex = SpectrumTexture(Image2D("{img}/colour.png"));', 'surfMat = createSurfaceMaterial("matte", (diffuseTex,));'], "")
+    t += _tex_quad("exrPanel", "CBNode", [(0.2, 0.3, -2.2), (1.3, 0.3, -2.2), (1.3, 1.4, -2.2), (0.2, 1.4, -2.2)], (0, 0, 1), (1, 0, 0), 2.0,
+                   [f'diffuseTex = SpectrumTexture(Image2D("{img}/ramp.exr"));', 'surfMat = createSurfaceMaterial("matte", (diffuseTex,));'], "")
+    t += _tex_quad("bumpPanel", "CBNode", [(-1.0, 0.02, 1.0), (1.0, 0.02, 1.0), (1.0, 0.02, -1.0), (-1.0, 0.02, -1.0)], (0, 1, 0), (1, 0, 0), 2.0,
+                   ['wardTex = SpectrumTexture(Spectrum(0.6, 0.55, 0.5));',
+                    'surfMat = createSurfaceMaterial("Ward", (wardTex, FloatTexture(0.15), FloatTexture(0.15)));',
+                    f'bumpTex = NormalTexture(Image2D("{img}/normal.png", "Normal"));'], '"normal": bumpTex, ')
+    t += _tex_quad("holePanel", "CBNode", [(-0.9, 1.2, 0.2), (0.9, 1.2, 0.2), (0.9, 2.2, -0.6), (-0.9, 2.2, -0.6)], (0, 0.6247, 0.7809), (1, 0, 0), 1.5,
+                   [f'holeCol = SpectrumTexture(Image2D("{img}/holes.png"));', 'surfMat = createSurfaceMaterial("matte", (holeCol,));',
+                    f'holeAlpha = FloatTexture(Image2D("{img}/holes.png", "Alpha"));'], '"alpha": holeAlpha, ')
+    t += CORNELL_CAMERA
+    path = os.path.join(directory, "Textured.txt")
+    with open(path, "w") as f:
+        f.write(t)
+    return path
+
+
 SCENES = {
+    "textured": write_textured,
     "cutout": write_cutout,
     "diffuse": write_cornell_diffuse,
     "spheres": write_cornell_spheres,
