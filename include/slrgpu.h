@@ -85,6 +85,15 @@ typedef struct SlrGpuLeafRecord {
 
 #define SLRGPU_LEAF_FLAG_ALPHA_TEST 0x1u   /* triangle has an alpha texture (TriangleMesh.cpp:163-168) */
 
+/* 32-byte node of the binary spatial-split BVH the reference builds and -- in the shipped build -- traverses
+ * (SBVH::Node, Accelerator/SBVH.h:21-45; SBVH::intersect :417-442). Optional second accelerator of a scene, used by
+ * slrgpu_intersect_batch_sbvh. Inner node: a = child 0, b = child 1 | split axis << 28 (global node indices); leaf:
+ * a = first record in sbvh_leaf_records, b = 0x80000000 | number of records. */
+typedef struct SlrGpuSbvhNode {
+    float lo[3], hi[3];
+    uint32_t a, b;
+} SlrGpuSbvhNode;
+
 /* One TransformedSurfaceObject (SurfaceObject.cpp:303-392) over a nested aggregate.
  * Matrices are column-major (element (r,c) at [4*c + r]) like Matrix4x4 (Matrix4x4.h:23-38). */
 typedef struct SlrGpuInstance {
@@ -95,7 +104,8 @@ typedef struct SlrGpuInstance {
     uint32_t num_lights;
     uint32_t light_index;   /* position of this instance in ITS parent's light list, or INVALID */
     float light_importance; /* integral of the nested light distribution (importance of the instance) */
-    uint32_t pad[3];
+    uint32_t sbvh_root_node; /* global index of the nested SBVH's root in sbvh_nodes (when the scene carries the SBVH) */
+    uint32_t pad[2];
 } SlrGpuInstance;
 
 /* 32-byte per-triangle shading record (indexed by prim_id). */
@@ -146,7 +156,7 @@ typedef enum SlrGpuTextureKind {
     SLRGPU_TEX_CHECKER_NORMAL = 3,     /* f0: stepWidth, i0: reverse; mapping */
     SLRGPU_TEX_CHECKER_FLOAT = 4,      /* f0,f1: values; mapping */
     SLRGPU_TEX_VORONOI_SPECTRUM = 5,   /* f0: scale, f1: brightness; mapping (3D) */
-    SLRGPU_TEX_VORONOI_NORMAL = 6,     /* f0: scale, f1: thetaMax */
+    SLRGPU_TEX_VORONOI_NORMAL = 6,     /* f0: scale, f1: cos(thetaMax) (voronoi_textures.h:37) */
     SLRGPU_TEX_VORONOI_FLOAT = 7,      /* f0: scale, f1: valueScale, i0: flat */
     SLRGPU_TEX_IMAGE_SPECTRUM = 8,     /* i0: image id; mapping */
     SLRGPU_TEX_IMAGE_NORMAL = 9,
@@ -286,6 +296,11 @@ typedef struct SlrGpuSceneDesc {
     SlrGpuCamera camera;
     SlrGpuEnvironment environment;
     SlrGpuSpectralTables spectral;
+
+    /* optional: the binary SBVH of every aggregate (top level first: its root is node 0) with leaf records in the SBVH's own
+     * leaf order, for slrgpu_intersect_batch_sbvh; NULL / 0 when not exported */
+    const SlrGpuSbvhNode* sbvh_nodes;              uint32_t num_sbvh_nodes;
+    const SlrGpuLeafRecord* sbvh_leaf_records;     uint32_t num_sbvh_leaf_records;
 } SlrGpuSceneDesc;
 
 typedef struct SlrGpuScene SlrGpuScene;
@@ -305,7 +320,7 @@ SLRGPU_API const char* slrgpu_last_error(void);
 /* sizeof() of the ABI structs, so FFI bindings (ctypes, cgo, JNI) can verify their mirrors:
  * 0 SceneDesc, 1 BvhNode, 2 LeafRecord, 3 Instance, 4 Triangle, 5 Vertex, 6 Spectrum, 7 Texture,
  * 8 Image, 9 Material, 10 Light, 11 Camera, 12 Environment, 13 SpectralTables, 14 RayBatch,
- * 15 HitBatch, 16 RenderParams, 17 RenderStats. Unknown index -> 0. */
+ * 15 HitBatch, 16 RenderParams, 17 RenderStats, 18 SbvhNode. Unknown index -> 0. */
 SLRGPU_API uint32_t slrgpu_struct_size(int which);
 
 /* Copies every buffer of `desc` to `device` (the caller keeps ownership of the host buffers, which
@@ -346,6 +361,14 @@ SLRGPU_API int slrgpu_intersect_batch_device(SlrGpuScene* scene, const SlrGpuRay
 /* Waits for the scene's device and sets *overflow to 1 if any slrgpu_intersect_batch_device launch since the last
  * poll overflowed its traversal stack (QBVH.h:299 holds 64 entries; the reference would write out of bounds). */
 SLRGPU_API int slrgpu_scene_poll_overflow(SlrGpuScene* scene, int* overflow);
+/* Closest hits through the scene's binary SBVH instead of the QBVH: SBVH::intersect (Accelerator/SBVH.h:417-442) with
+ * BoundingBox3D::intersect (Core/geometry.h:112-126) -- the accelerator the reference's shipped build traverses
+ * (SurfaceObject.cpp:226-230). It visits leaves in a different order than the QBVH, so on rays that meet two primitives
+ * at bit-equal distances (shared edges / vertices) it can report the other primitive: this entry point reproduces the
+ * SBVH's answer, slrgpu_intersect_batch the QBVH's. Needs a scene created with sbvh_nodes (SLRGPU_ERR_INVALID_ARGUMENT
+ * otherwise). Host buffers; u, v optional; the counters are not filled. */
+SLRGPU_API int slrgpu_intersect_batch_sbvh(SlrGpuScene* scene, const SlrGpuRayBatch* rays, uint64_t num_rays,
+                                           const SlrGpuHitBatch* hits, float* kernel_ms);
 /* Launch geometry the traversal kernel uses for n rays, for reporting (grid, block). */
 SLRGPU_API int slrgpu_intersect_launch_config(SlrGpuScene* scene, uint64_t num_rays, uint32_t* grid, uint32_t* block);
 

@@ -18,6 +18,10 @@ typedef struct SlrHostScene SlrHostScene;       /* a flattened scene (owns the S
 
 SLRGPU_API const char* slrhost_last_error(void);
 
+/* Process-wide options for scenes built / read afterwards. "export_sbvh" (0 / 1, default 0): the flattened scene also
+ * carries every aggregate's binary SBVH (SlrGpuSceneDesc::sbvh_nodes) for slrgpu_intersect_batch_sbvh. */
+SLRGPU_API int slrhost_set_option(const char* name, int value);
+
 /* --- programmatic scene graph (what the scene language's builtins do, API.cpp:663-800) --- */
 SLRGPU_API SlrHostBuilder* slrhost_builder_create(void);
 SLRGPU_API void slrhost_builder_destroy(SlrHostBuilder* b);

@@ -3,7 +3,7 @@
 //   spec : "SLRG" u32 version(1) u32 numMeshes { u32 nv u32 nt  f32 pos[3nv]  u32 idx[3nt] }*
 //          u32 numPlacements { u32 mesh u32 mode(0 bake, 1 instance) f32 mat[16] column-major }*
 //   rays : u64 n, then 8 arrays of n f32: ox oy oz dx dy dz tmin tmax
-//   hits : u64 n, u32 prim[n], u32 inst[n], f32 t[n], f32 u[n], f32 v[n]
+//   hits : u64 n, u32 prim[n], u32 inst[n], f32 t[n], f32 u[n], f32 v[n] (QBVH::intersect), then the same five arrays from SBVH::intersect
 #pragma once
 #include <cstdint>
 #include <cstdio>

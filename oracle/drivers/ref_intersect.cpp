@@ -18,6 +18,7 @@
 #include <libSLRSceneGraph/TriangleMeshNode.h>
 #include <libSLRSceneGraph/surface_materials.hpp>
 #include <libSLRSceneGraph/textures.hpp>
+#include <functional>
 #include <map>
 #include <thread>
 #include "geom_spec.h"
@@ -105,9 +106,13 @@ int main(int argc, char** argv) {
     auto tq1 = std::chrono::steady_clock::now();
 
     const uint64_t n = rays.n;
-    std::vector<uint32_t> prim(n), inst(n), primS(n);
-    std::vector<float> t(n), u(n), v(n);
+    std::vector<uint32_t> prim(n), inst(n), primS(n), instS(n);
+    std::vector<float> t(n), u(n), v(n), tS(n), uS(n), vS(n);
     auto trace = [&](bool useQ, unsigned nth, std::vector<uint32_t>& outPrim, bool writeAll) {
+        uint32_t* const instOut = useQ ? inst.data() : instS.data();
+        float* const tOut = useQ ? t.data() : tS.data();
+        float* const uOut = useQ ? u.data() : uS.data();
+        float* const vOut = useQ ? v.data() : vS.data();
         for (auto& a : aggs) const_cast<SurfaceObjectAggregate*>(a.aggr)->m_accelerator = useQ ? (Accelerator*)a.qbvh : (Accelerator*)a.sbvh;
         auto t0 = std::chrono::steady_clock::now();
         std::vector<std::thread> pool;
@@ -125,7 +130,7 @@ int main(int argc, char** argv) {
                         else p = top;
                     }
                     outPrim[i] = p;
-                    if (writeAll) { inst[i] = in; t[i] = isect.dist; u[i] = p == 0xFFFFFFFFu ? 0.0f : isect.u; v[i] = p == 0xFFFFFFFFu ? 0.0f : isect.v; }
+                    if (writeAll) { instOut[i] = in; tOut[i] = isect.dist; uOut[i] = p == 0xFFFFFFFFu ? 0.0f : isect.u; vOut[i] = p == 0xFFFFFFFFu ? 0.0f : isect.v; }
                 }
             });
         }
@@ -134,7 +139,7 @@ int main(int argc, char** argv) {
     };
     double secQ1 = trace(true, 1, prim, true);
     double secQN = threads > 1 ? trace(true, threads, prim, true) : secQ1;
-    double secS1 = trace(false, 1, primS, false);
+    double secS1 = trace(false, 1, primS, true);       // the shipped default accelerator: its answers are dumped too
     uint64_t mism = 0, nhit = 0;
     for (uint64_t i = 0; i < n; ++i) { mism += prim[i] != primS[i]; nhit += prim[i] != 0xFFFFFFFFu; }
 
@@ -142,6 +147,9 @@ int main(int argc, char** argv) {
     fwrite(&n, 8, 1, f);
     fwrite(prim.data(), 4, n, f); fwrite(inst.data(), 4, n, f);
     fwrite(t.data(), 4, n, f); fwrite(u.data(), 4, n, f); fwrite(v.data(), 4, n, f);
+    // then the same five arrays from SBVH::intersect
+    fwrite(primS.data(), 4, n, f); fwrite(instS.data(), 4, n, f);
+    fwrite(tS.data(), 4, n, f); fwrite(uS.data(), 4, n, f); fwrite(vS.data(), 4, n, f);
     fclose(f);
 
     if (treesOut) {

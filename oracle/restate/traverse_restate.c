@@ -164,3 +164,81 @@ RESTATE_API int slr_restate_intersect(const SlrGpuSceneDesc* d, const SlrGpuRayB
     if (totalLeaves) *totalLeaves = s.leavesTested;
     return s.overflow;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * The binary SBVH as the reference's SHIPPED build traverses it (SurfaceObject.cpp:226-230 picks SBVH):
+ *   SBVH::intersect            libSLR/Accelerator/SBVH.h:417-442
+ *   BoundingBox3D::intersect   libSLR/Core/geometry.h:112-126
+ * on the optional sbvh_nodes / sbvh_leaf_records tables of the flattened scene. Pinned against ref_intersect's SBVH pass
+ * (tests/golden/intersect_*.npz, fields *_sbvh).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { const SlrGpuSbvhNode* nodes; const SlrGpuLeafRecord* leaves; const SlrGpuInstance* instances; int overflow; } SScene;
+
+static int sbvh_box(const SlrGpuSbvhNode* n, const RRay* r, float ix, float iy, float iz) {
+    float dist0 = r->tmin, dist1 = r->tmax;
+    const float org[3] = {r->ox, r->oy, r->oz}, inv[3] = {ix, iy, iz};
+    for (int i = 0; i < 3; ++i) {
+        float tn = (n->lo[i] - org[i]) * inv[i], tf = (n->hi[i] - org[i]) * inv[i];
+        if (tn > tf) { float sw = tn; tn = tf; tf = sw; }
+        dist0 = tn > dist0 ? tn : dist0;
+        dist1 = tf < dist1 ? tf : dist1;
+        if (dist0 > dist1) return 0;
+    }
+    return 1;
+}
+
+static int sbvh_traverse(SScene* s, uint32_t root, RRay* r, RHit* h, int level) {
+    const float ix = 1.0f / r->dx, iy = 1.0f / r->dy, iz = 1.0f / r->dz;
+    const int dirPos[3] = {r->dx >= 0.0f, r->dy >= 0.0f, r->dz >= 0.0f};
+    uint32_t stack[64];
+    int depth = 0, found = 0;
+    stack[depth++] = root;
+    while (depth > 0) {
+        const SlrGpuSbvhNode* n = &s->nodes[stack[--depth]];
+        if (!sbvh_box(n, r, ix, iy, iz)) continue;
+        if (!(n->b & 0x80000000u)) {
+            if (depth + 2 > 64) { s->overflow = 1; continue; }
+            const uint32_t c0 = n->a, c1 = n->b & 0x0FFFFFFFu;
+            const int positive = dirPos[(n->b >> 28) & 3u];
+            stack[depth++] = positive ? c1 : c0;
+            stack[depth++] = positive ? c0 : c1;
+            continue;
+        }
+        const uint32_t count = n->b & 0x7FFFFFFFu;
+        for (uint32_t j = 0; j < count; ++j) {
+            const SlrGpuLeafRecord* rec = &s->leaves[n->a + j];
+            uint32_t id; memcpy(&id, &rec->a[3], 4);
+            if (id & 0x80000000u) {
+                if (level >= 1) continue;
+                const SlrGpuInstance* inst = &s->instances[id & 0x7FFFFFFFu];
+                RRay lr; float o[3];
+                mul_point(inst->mat_inv, r->ox, r->oy, r->oz, o);
+                lr.ox = o[0]; lr.oy = o[1]; lr.oz = o[2];
+                const float* m = inst->mat_inv;
+                lr.dx = m[0] * r->dx + m[4] * r->dy + m[8] * r->dz;
+                lr.dy = m[1] * r->dx + m[5] * r->dy + m[9] * r->dz;
+                lr.dz = m[2] * r->dx + m[6] * r->dy + m[10] * r->dz;
+                lr.tmin = r->tmin; lr.tmax = r->tmax;
+                if (sbvh_traverse(s, inst->sbvh_root_node, &lr, h, level + 1)) { r->tmax = lr.tmax; h->inst = id & 0x7FFFFFFFu; found = 1; }
+                continue;
+            }
+            float t, b0, b1;
+            if (triangle(rec, r, &t, &b0, &b1)) { r->tmax = t; h->prim = id; h->inst = 0xFFFFFFFFu; h->t = t; h->u = b0; h->v = b1; found = 1; }
+        }
+    }
+    return found;
+}
+
+RESTATE_API int slr_restate_intersect_sbvh(const SlrGpuSceneDesc* d, const SlrGpuRayBatch* rays, uint64_t n, const SlrGpuHitBatch* out) {
+    if (!d->sbvh_nodes || !d->sbvh_leaf_records) return -1;
+    SScene s = {d->sbvh_nodes, d->sbvh_leaf_records, d->instances, 0};
+    for (uint64_t i = 0; i < n; ++i) {
+        RRay r = {rays->org_x[i], rays->org_y[i], rays->org_z[i], rays->dir_x[i], rays->dir_y[i], rays->dir_z[i], rays->tmin[i], rays->tmax[i]};
+        RHit h = {0xFFFFFFFFu, 0xFFFFFFFFu, INFINITY, 0.0f, 0.0f};
+        sbvh_traverse(&s, 0, &r, &h, 0);
+        out->prim[i] = h.prim; out->inst[i] = h.inst; out->t[i] = h.t;
+        if (out->u) out->u[i] = h.u;
+        if (out->v) out->v[i] = h.v;
+    }
+    return s.overflow;
+}

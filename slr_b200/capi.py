@@ -35,7 +35,7 @@ class LeafRecord(C.Structure):
 class Instance(C.Structure):
     _fields_ = [("mat", c_f * 16), ("mat_inv", c_f * 16), ("root_node", c_u32),
                 ("light_base", c_u32), ("num_lights", c_u32), ("light_index", c_u32),
-                ("light_importance", c_f), ("pad", c_u32 * 3)]
+                ("light_importance", c_f), ("sbvh_root_node", c_u32), ("pad", c_u32 * 2)]
 
 
 class Triangle(C.Structure):
@@ -57,6 +57,10 @@ class Texture(C.Structure):
     _fields_ = [("kind", c_u32), ("mapping", c_u32), ("i0", c_u32), ("i1", c_u32),
                 ("f0", c_f), ("f1", c_f), ("f2", c_f), ("f3", c_f),
                 ("map_offset", c_f * 2), ("map_scale", c_f * 2)]
+
+
+class SbvhNode(C.Structure):
+    _fields_ = [("lo", c_f * 3), ("hi", c_f * 3), ("a", c_u32), ("b", c_u32)]
 
 
 class Image(C.Structure):
@@ -106,7 +110,9 @@ class SceneDesc(C.Structure):
                 ("lights", C.POINTER(Light)), ("num_lights", c_u32),
                 ("num_top_lights", c_u32), ("top_light_importance", c_f),
                 ("world_center", c_f * 3), ("world_radius", c_f),
-                ("camera", Camera), ("environment", Environment), ("spectral", SpectralTables)]
+                ("camera", Camera), ("environment", Environment), ("spectral", SpectralTables),
+                ("sbvh_nodes", C.POINTER(SbvhNode)), ("num_sbvh_nodes", c_u32),
+                ("sbvh_leaf_records", C.POINTER(LeafRecord)), ("num_sbvh_leaf_records", c_u32)]
 
 
 class RayBatch(C.Structure):
@@ -134,7 +140,7 @@ class RenderStats(C.Structure):
 
 _ABI_STRUCTS = [SceneDesc, BvhNode, LeafRecord, Instance, Triangle, Vertex, Spectrum, Texture, Image,
                 Material, Light, Camera, Environment, SpectralTables, RayBatch, HitBatch, RenderParams,
-                RenderStats]
+                RenderStats, SbvhNode]
 
 RENDER_PROFILE_STAGES = 0x1
 
@@ -169,6 +175,8 @@ gpu.slrgpu_intersect_batch.restype = C.c_int
 gpu.slrgpu_intersect_batch.argtypes = [C.c_void_p, C.POINTER(RayBatch), c_u64, C.POINTER(HitBatch), PF]
 gpu.slrgpu_intersect_batch_device.restype = C.c_int
 gpu.slrgpu_intersect_batch_device.argtypes = [C.c_void_p, C.POINTER(RayBatch), c_u64, C.POINTER(HitBatch), C.c_void_p]
+gpu.slrgpu_intersect_batch_sbvh.restype = C.c_int
+gpu.slrgpu_intersect_batch_sbvh.argtypes = [C.c_void_p, C.POINTER(RayBatch), c_u64, C.POINTER(HitBatch), PF]
 gpu.slrgpu_render_multi.restype = C.c_int
 gpu.slrgpu_render_multi.argtypes = [C.POINTER(C.c_void_p), c_u32, C.POINTER(RenderParams), PF, C.POINTER(RenderStats)]
 gpu.slrgpu_scene_poll_overflow.restype = C.c_int
@@ -386,6 +394,20 @@ class GpuScene:
         out["kernel_ms"] = ms.value
         return out
 
+    def intersect_sbvh(self, rays):
+        """slrgpu_intersect_batch_sbvh: closest hits through the binary SBVH (the scene must carry it: set_option export_sbvh)."""
+        comps = [_f32(rays[k]) for k in ("ox", "oy", "oz", "dx", "dy", "dz", "tmin", "tmax")]
+        n = comps[0].shape[0]
+        rb = RayBatch(*[_pf(c) for c in comps])
+        out = {"prim": np.empty(n, np.uint32), "inst": np.empty(n, np.uint32), "t": np.empty(n, np.float32),
+               "u": np.empty(n, np.float32), "v": np.empty(n, np.float32)}
+        hb = HitBatch(out["prim"].ctypes.data_as(PU32), out["inst"].ctypes.data_as(PU32), _pf(out["t"]), _pf(out["u"]),
+                      _pf(out["v"]), None, None)
+        ms = c_f(0)
+        _gpu_check(gpu.slrgpu_intersect_batch_sbvh(self._s, C.byref(rb), n, C.byref(hb), C.byref(ms)), "slrgpu_intersect_batch_sbvh")
+        out["kernel_ms"] = ms.value
+        return out
+
     def occluded(self, rays):
         comps = [_f32(rays[k]) for k in ("ox", "oy", "oz", "dx", "dy", "dz", "tmin", "tmax")]
         n = comps[0].shape[0]
@@ -496,6 +518,15 @@ def probe_shading(gpu_scene, probes):
     out = np.zeros((p.shape[0], 64), np.float32)
     _gpu_check(gpu.slrgpu_probe_shading(gpu_scene.handle, _pf(p), p.shape[0], _pf(out)), "slrgpu_probe_shading")
     return out
+
+
+host.slrhost_set_option.restype = C.c_int
+host.slrhost_set_option.argtypes = [C.c_char_p, C.c_int]
+
+
+def set_option(name, value):
+    """slrhost_set_option: process-wide options of the host library ("export_sbvh")."""
+    _host_check(host.slrhost_set_option(name.encode(), int(value)), "slrhost_set_option")
 
 
 host.slrhost_decode_png.restype = C.c_int

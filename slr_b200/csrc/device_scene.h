@@ -20,6 +20,8 @@ struct DeviceScene {
     const float4* nodes;
     const float4* leaves;
     const SlrGpuInstance* instances;
+    const SlrGpuSbvhNode* sbvhNodes;     // optional second accelerator (slrgpu_intersect_batch_sbvh)
+    const float4* sbvhLeaves;
     const SlrGpuTriangle* triangles;
     const float4* vertices;          // 3 float4 per vertex (SlrGpuVertex)
     const SlrGpuMaterial* materials;

@@ -60,6 +60,92 @@ occludedBatchKernel(const DeviceScene s, SlrGpuRayBatch rays, uint32_t n, uint8_
     if (overflow) atomicExch(status, 1);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The binary SBVH, traversed as the reference's shipped build does:
+//   SBVH::intersect              libSLR/Accelerator/SBVH.h:417-442   (stack of node indices, near child on top, a node's box is
+//                                                                     tested when it is POPPED, leaves tested in list order)
+//   BoundingBox3D::intersect     libSLR/Core/geometry.h:112-126      (per axis: swap so that tNear <= tFar, tighten, early out)
+// One thread per ray -- this entry point exists for parity with the default accelerator (tie rays resolve differently than in
+// the QBVH), not for speed; the renderer and the benchmarks run the QBVH walk of traverse.cuh.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool sbvhBoxTest(const SlrGpuSbvhNode& n, const Ray& r, float ix, float iy, float iz) {
+    float dist0 = r.tmin, dist1 = r.tmax;
+    float tn, tf;
+#define SBVH_AXIS(LO, HI, O, I)                                              \
+    tn = __fmul_rn(__fsub_rn(LO, O), I); tf = __fmul_rn(__fsub_rn(HI, O), I); \
+    if (tn > tf) { const float sw = tn; tn = tf; tf = sw; }                   \
+    dist0 = tn > dist0 ? tn : dist0;                                          \
+    dist1 = tf < dist1 ? tf : dist1;                                          \
+    if (dist0 > dist1) return false;
+    SBVH_AXIS(n.lo[0], n.hi[0], r.ox, ix)
+    SBVH_AXIS(n.lo[1], n.hi[1], r.oy, iy)
+    SBVH_AXIS(n.lo[2], n.hi[2], r.oz, iz)
+#undef SBVH_AXIS
+    return true;
+}
+
+// LEVEL 0: the top-level aggregate (instance records descend into LEVEL 1); LEVEL 1: a nested aggregate
+template <int LEVEL>
+__device__ bool sbvhTraverse(const DeviceScene& s, uint32_t root, Ray& r, Hit& hit, bool& overflow) {
+    const float ix = __frcp_rn(r.dx), iy = __frcp_rn(r.dy), iz = __frcp_rn(r.dz);       // Vector3D::reciprocal
+    const bool dirPos[3] = {r.dx >= 0.0f, r.dy >= 0.0f, r.dz >= 0.0f};
+    uint32_t stack[kStackSize];
+    int depth = 0;
+    stack[depth++] = root;
+    bool found = false;
+    while (depth > 0) {
+        const SlrGpuSbvhNode n = s.sbvhNodes[stack[--depth]];
+        if (!sbvhBoxTest(n, r, ix, iy, iz)) continue;
+        if (!(n.b & 0x80000000u)) {
+            if (depth + 2 > kStackSize) { overflow = true; continue; }
+            const uint32_t c0 = n.a, c1 = n.b & 0x0FFFFFFFu;
+            const bool positive = dirPos[(n.b >> 28) & 3u];
+            stack[depth++] = positive ? c1 : c0;
+            stack[depth++] = positive ? c0 : c1;
+            continue;
+        }
+        const uint32_t count = n.b & 0x7FFFFFFFu;
+        for (uint32_t i = 0; i < count; ++i) {
+            const float4* rec = s.sbvhLeaves + (size_t)(n.a + i) * 3;
+            const float4 a = ldg4(rec), b = ldg4(rec + 1), c = ldg4(rec + 2);
+            const uint32_t id = __float_as_uint(a.w);
+            if (id & 0x80000000u) {
+                if constexpr (LEVEL == 0) {
+                    // TransformedSurfaceObject::intersect (SurfaceObject.cpp:307-318): the ray in the instance's space, distMax carried
+                    const SlrGpuInstance* inst = s.instances + (id & 0x7FFFFFFFu);
+                    Ray lr = r;
+                    mulPoint(inst->mat_inv, r.ox, r.oy, r.oz, &lr.ox, &lr.oy, &lr.oz);
+                    mulVector(inst->mat_inv, r.dx, r.dy, r.dz, &lr.dx, &lr.dy, &lr.dz);
+                    if (sbvhTraverse<1>(s, inst->sbvh_root_node, lr, hit, overflow)) { r.tmax = lr.tmax; hit.inst = id & 0x7FFFFFFFu; found = true; }
+                }
+                continue;
+            }
+            float t, b0, b1, b2;
+            bool accept = triangleTest(a, b, c, r, &t, &b0, &b1, &b2);
+            if (accept && (__float_as_uint(b.w) & SLRGPU_LEAF_FLAG_ALPHA_TEST)) accept = alphaTestPasses(s, id, b0, b1, b2);
+            if (accept) { r.tmax = t; hit.prim = id; hit.inst = SLRGPU_INVALID_ID; hit.t = t; hit.u = b0; hit.v = b1; found = true; }
+        }
+    }
+    return found;
+}
+
+__global__ void __launch_bounds__(kIntersectBlock)
+intersectSbvhKernel(const DeviceScene s, SlrGpuRayBatch rays, uint32_t n, SlrGpuHitBatch hits, int* status) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Ray r;
+        BatchRaySource{rays}.load(i, r);
+        Hit hit;
+        hit.prim = SLRGPU_INVALID_ID; hit.inst = SLRGPU_INVALID_ID; hit.t = INFINITY; hit.u = 0.0f; hit.v = 0.0f; hit.info = kSurfaceInfoMiss;
+        bool overflow = false;
+        sbvhTraverse<0>(s, 0u, r, hit, overflow);
+        hits.prim[i] = hit.prim; hits.inst[i] = hit.inst; hits.t[i] = hit.t;
+        if (hits.u) hits.u[i] = hit.u;
+        if (hits.v) hits.v[i] = hit.v;
+        if (overflow) atomicExch(status, 1);
+    }
+}
+
 // grid of the warp-cooperative kernels: enough resident warps to fill the machine, no more than the batch needs
 static uint32_t batchGrid(const SlrGpuScene* sc, uint64_t n) {
     int numSMs = 148;
@@ -339,6 +425,46 @@ SLRGPU_API int slrgpu_intersect_batch(SlrGpuScene* scene, const SlrGpuRayBatch* 
     if (hits->v) SLRGPU_CUDA_TRY(cudaMemcpy(hits->v, dh.v, n * 4, cudaMemcpyDeviceToHost));
     if (hits->nodes_visited) SLRGPU_CUDA_TRY(cudaMemcpy(hits->nodes_visited, dh.nodes_visited, n * 4, cudaMemcpyDeviceToHost));
     if (hits->tris_tested) SLRGPU_CUDA_TRY(cudaMemcpy(hits->tris_tested, dh.tris_tested, n * 4, cudaMemcpyDeviceToHost));
+    int status = 0;
+    SLRGPU_CUDA_TRY(cudaMemcpy(&status, dStatus, sizeof(int), cudaMemcpyDeviceToHost));
+    if (status) { setError("traversal stack overflow (more than %d pending nodes)", kStackSize); return SLRGPU_ERR_STACK_OVERFLOW; }
+    return SLRGPU_OK;
+}
+
+SLRGPU_API int slrgpu_intersect_batch_sbvh(SlrGpuScene* scene, const SlrGpuRayBatch* rays, uint64_t n, const SlrGpuHitBatch* hits, float* kernel_ms) {
+    if (!scene || !rays || !hits || !hits->prim || !hits->inst || !hits->t) { setError("slrgpu_intersect_batch_sbvh: null argument"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    if (!scene->dev.sbvhNodes) { setError("slrgpu_intersect_batch_sbvh: the scene was created without sbvh_nodes"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    if (kernel_ms) *kernel_ms = 0.0f;
+    if (n == 0) return SLRGPU_OK;
+    if (n >= 0xFFFF0000ull) { setError("ray batch too large (at most 2^32 - 65536 rays per call)"); return SLRGPU_ERR_INVALID_ARGUMENT; }
+    SLRGPU_CUDA_TRY(cudaSetDevice(scene->device));
+    DeviceBuffers bufs;
+    SlrGpuRayBatch dr;
+    int rc = uploadRays(bufs, rays, n, &dr);
+    if (rc != SLRGPU_OK) return rc;
+    SlrGpuHitBatch dh = {};
+    int* dStatus = nullptr;
+    if ((rc = bufs.alloc(&dh.prim, n)) || (rc = bufs.alloc(&dh.inst, n)) || (rc = bufs.alloc(&dh.t, n)) || (rc = bufs.alloc(&dStatus, 2))) return rc;
+    if (hits->u && (rc = bufs.alloc(&dh.u, n))) return rc;
+    if (hits->v && (rc = bufs.alloc(&dh.v, n))) return rc;
+    SLRGPU_CUDA_TRY(cudaMemset(dStatus, 0, 2 * sizeof(int)));
+    cudaEvent_t e0, e1;
+    SLRGPU_CUDA_TRY(cudaEventCreate(&e0));
+    SLRGPU_CUDA_TRY(cudaEventCreate(&e1));
+    struct EventFree { cudaEvent_t a, b; ~EventFree() { cudaEventDestroy(a); cudaEventDestroy(b); } } eventFree{e0, e1};
+    SLRGPU_CUDA_TRY(cudaEventRecord(e0, 0));
+    intersectSbvhKernel<<<batchGrid(scene, n), kIntersectBlock>>>(scene->dev, dr, (uint32_t)n, dh, dStatus);
+    SLRGPU_CUDA_TRY(cudaGetLastError());
+    SLRGPU_CUDA_TRY(cudaEventRecord(e1, 0));
+    SLRGPU_CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (kernel_ms) *kernel_ms = ms;
+    SLRGPU_CUDA_TRY(cudaMemcpy(hits->prim, dh.prim, n * 4, cudaMemcpyDeviceToHost));
+    SLRGPU_CUDA_TRY(cudaMemcpy(hits->inst, dh.inst, n * 4, cudaMemcpyDeviceToHost));
+    SLRGPU_CUDA_TRY(cudaMemcpy(hits->t, dh.t, n * 4, cudaMemcpyDeviceToHost));
+    if (hits->u) SLRGPU_CUDA_TRY(cudaMemcpy(hits->u, dh.u, n * 4, cudaMemcpyDeviceToHost));
+    if (hits->v) SLRGPU_CUDA_TRY(cudaMemcpy(hits->v, dh.v, n * 4, cudaMemcpyDeviceToHost));
     int status = 0;
     SLRGPU_CUDA_TRY(cudaMemcpy(&status, dStatus, sizeof(int), cudaMemcpyDeviceToHost));
     if (status) { setError("traversal stack overflow (more than %d pending nodes)", kStackSize); return SLRGPU_ERR_STACK_OVERFLOW; }

@@ -316,6 +316,22 @@ struct Validator {
             }
             if (n.top_axis > 2 || n.left_axis > 2 || n.right_axis > 2) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "node %u: split axis out of range", i);
         }
+        if (d->sbvh_nodes && d->num_sbvh_nodes) {
+            if (!d->sbvh_leaf_records || !d->num_sbvh_leaf_records) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "sbvh_nodes without sbvh_leaf_records");
+            for (uint32_t i = 0; i < d->num_sbvh_nodes; ++i) {
+                const SlrGpuSbvhNode& n = d->sbvh_nodes[i];
+                if (n.b & 0x80000000u) { if ((uint64_t)n.a + (n.b & 0x7FFFFFFFu) > d->num_sbvh_leaf_records) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "SBVH node %u: leaf records out of range", i); }
+                else if (n.a >= d->num_sbvh_nodes || (n.b & 0x0FFFFFFFu) >= d->num_sbvh_nodes || ((n.b >> 28) & 3u) > 2u) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "SBVH node %u: child / axis out of range", i);
+            }
+            for (uint32_t i = 0; i < d->num_sbvh_leaf_records; ++i) {
+                uint32_t id;
+                memcpy(&id, &d->sbvh_leaf_records[i].a[3], 4);
+                if ((id & 0x80000000u) ? (id & 0x7FFFFFFFu) >= d->num_instances : (shaded && id >= d->num_triangles))
+                    return fail(SLRGPU_ERR_INVALID_ARGUMENT, "SBVH leaf record %u: object out of range", i);
+            }
+            for (uint32_t i = 0; i < d->num_instances; ++i)
+                if (d->instances[i].sbvh_root_node >= d->num_sbvh_nodes) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "instance %u: SBVH root out of range", i);
+        }
         *hasAlpha = false;
         for (uint32_t i = 0; i < d->num_leaf_records; ++i) {
             uint32_t id, flags;
@@ -402,7 +418,7 @@ SLRGPU_API int slrgpu_device_count(void) {
     return n;
 }
 
-SLRGPU_API uint32_t slrgpu_abi_version(void) { return (1u << 16) | 0u; }
+SLRGPU_API uint32_t slrgpu_abi_version(void) { return (1u << 16) | 1u; }      // 1.1: SBVH tables, slrgpu_render_multi
 
 SLRGPU_API const char* slrgpu_last_error(void) { return g_error; }
 
@@ -412,7 +428,7 @@ SLRGPU_API uint32_t slrgpu_struct_size(int which) {
         sizeof(SlrGpuTriangle), sizeof(SlrGpuVertex), sizeof(SlrGpuSpectrum), sizeof(SlrGpuTexture),
         sizeof(SlrGpuImage), sizeof(SlrGpuMaterial), sizeof(SlrGpuLight), sizeof(SlrGpuCamera),
         sizeof(SlrGpuEnvironment), sizeof(SlrGpuSpectralTables), sizeof(SlrGpuRayBatch), sizeof(SlrGpuHitBatch),
-        sizeof(SlrGpuRenderParams), sizeof(SlrGpuRenderStats)};
+        sizeof(SlrGpuRenderParams), sizeof(SlrGpuRenderStats), sizeof(SlrGpuSbvhNode)};
     if (which < 0 || which >= (int)(sizeof(sizes) / sizeof(sizes[0]))) return 0;
     return sizes[which];
 }
@@ -456,6 +472,10 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
     UP(reinterpret_cast<const float4*>(d->bvh_nodes), (uint64_t)d->num_bvh_nodes * 8, &v.nodes);
     UP(reinterpret_cast<const float4*>(d->leaf_records), (uint64_t)d->num_leaf_records * 3, &v.leaves);
     UP(d->instances, d->num_instances, &v.instances);
+    if (d->sbvh_nodes && d->num_sbvh_nodes && d->sbvh_leaf_records && d->num_sbvh_leaf_records) {
+        UP(d->sbvh_nodes, d->num_sbvh_nodes, &v.sbvhNodes);
+        UP(reinterpret_cast<const float4*>(d->sbvh_leaf_records), (uint64_t)d->num_sbvh_leaf_records * 3, &v.sbvhLeaves);
+    }
     // the device copy of the triangle records carries the surface stage's per-triangle facts in its spare word
     std::vector<SlrGpuTriangle> triangles;
     if (d->triangles && d->num_triangles) {

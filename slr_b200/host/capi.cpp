@@ -43,6 +43,12 @@ extern "C" {
 
 SLRGPU_API const char* slrhost_last_error(void) { return g_err; }
 
+SLRGPU_API int slrhost_set_option(const char* name, int value) {
+    if (!name) return fail("slrhost_set_option: null name");
+    if (!std::strcmp(name, "export_sbvh")) { FlatScene::exportSbvh = value != 0; return 0; }
+    return fail("slrhost_set_option: unknown option %s", name);
+}
+
 SLRGPU_API SlrHostBuilder* slrhost_builder_create(void) {
     try { return new SlrHostBuilder(); } catch (...) { fail("allocation failed"); return nullptr; }
 }

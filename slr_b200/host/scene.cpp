@@ -7,6 +7,8 @@
 
 namespace slr {
 
+bool FlatScene::exportSbvh = false;
+
 // ---------------------------------------------------------------------------------------------
 // nodes
 // ---------------------------------------------------------------------------------------------
@@ -232,6 +234,52 @@ void GpuSceneBuilder::finalize(uint32_t top) {
     flat.topLightImportance = aggregates[top].lightImportance;
     flat.stats.clear();
 
+    auto fillLeafRecord = [this](const ObjectRef& o, SlrGpuLeafRecord& r) {
+        std::memset(&r, 0, sizeof(r));
+        uint32_t idBits;
+        if (!o.isInstance) {
+            const SlrGpuTriangle& t = flat.triangles[o.id];
+            Vec3 p0 = vpos(flat.vertices[t.v[0]]), p1 = vpos(flat.vertices[t.v[1]]), p2 = vpos(flat.vertices[t.v[2]]);
+            Vec3 e1 = p1 - p0, e2 = p2 - p0;
+            r.a[0] = p0.x; r.a[1] = p0.y; r.a[2] = p0.z;
+            r.b[0] = e1.x; r.b[1] = e1.y; r.b[2] = e1.z;
+            r.c[0] = e2.x; r.c[1] = e2.y; r.c[2] = e2.z;
+            uint32_t flags = t.alpha_map != SLRGPU_INVALID_ID ? SLRGPU_LEAF_FLAG_ALPHA_TEST : 0u;
+            std::memcpy(&r.b[3], &flags, 4);
+            idBits = o.id;
+        } else {
+            idBits = 0x80000000u | o.id;
+        }
+        std::memcpy(&r.a[3], &idBits, 4);
+    };
+    // optional: the binary SBVHs as they are (SBVH.h:21-45), global indices, leaf records in the SBVH's own leaf order
+    std::vector<uint32_t> sbvhNodeBase(aggregates.size(), 0);
+    flat.sbvhNodes.clear(); flat.sbvhLeaves.clear();
+    if (FlatScene::exportSbvh) {
+        uint64_t nS = 0, nL = 0;
+        for (uint32_t a : order) { nS += aggregates[a].sbvh.nodes.size(); nL += aggregates[a].sbvh.refs.size(); }
+        if (nS >= 0x10000000ull || nL >= 0x80000000ull) throw std::runtime_error("scene too large for the SBVH export (28-bit node index)");
+        flat.sbvhNodes.reserve(nS); flat.sbvhLeaves.reserve(nL);
+        for (uint32_t a : order) {
+            const Aggregate& ag = aggregates[a];
+            const uint32_t nb = (uint32_t)flat.sbvhNodes.size(), lb = (uint32_t)flat.sbvhLeaves.size();
+            sbvhNodeBase[a] = nb;
+            for (const SBVHNode& s : ag.sbvh.nodes) {
+                SlrGpuSbvhNode d;
+                d.lo[0] = s.bbox.lo.x; d.lo[1] = s.bbox.lo.y; d.lo[2] = s.bbox.lo.z;
+                d.hi[0] = s.bbox.hi.x; d.hi[1] = s.bbox.hi.y; d.hi[2] = s.bbox.hi.z;
+                if (s.numRefs > 0) { d.a = lb + s.firstRef; d.b = 0x80000000u | s.numRefs; }
+                else { d.a = nb + s.c0; d.b = (nb + s.c1) | ((uint32_t)s.axis << 28); }
+                flat.sbvhNodes.push_back(d);
+            }
+            for (uint32_t ref : ag.sbvh.refs) {
+                SlrGpuLeafRecord r;
+                fillLeafRecord(ag.objects[ref], r);
+                flat.sbvhLeaves.push_back(r);
+            }
+        }
+    }
+
     for (uint32_t a : order) {
         const Aggregate& ag = aggregates[a];
         for (size_t i = 0; i < ag.qbvh.nodes.size(); ++i) {
@@ -247,24 +295,7 @@ void GpuSceneBuilder::finalize(uint32_t top) {
             }
         }
         for (size_t i = 0; i < ag.qbvh.refs.size(); ++i) {
-            const ObjectRef& o = ag.objects[ag.qbvh.refs[i]];
-            SlrGpuLeafRecord& r = flat.leaves[leafBase[a] + i];
-            std::memset(&r, 0, sizeof(r));
-            uint32_t idBits;
-            if (!o.isInstance) {
-                const SlrGpuTriangle& t = flat.triangles[o.id];
-                Vec3 p0 = vpos(flat.vertices[t.v[0]]), p1 = vpos(flat.vertices[t.v[1]]), p2 = vpos(flat.vertices[t.v[2]]);
-                Vec3 e1 = p1 - p0, e2 = p2 - p0;
-                r.a[0] = p0.x; r.a[1] = p0.y; r.a[2] = p0.z;
-                r.b[0] = e1.x; r.b[1] = e1.y; r.b[2] = e1.z;
-                r.c[0] = e2.x; r.c[1] = e2.y; r.c[2] = e2.z;
-                uint32_t flags = t.alpha_map != SLRGPU_INVALID_ID ? SLRGPU_LEAF_FLAG_ALPHA_TEST : 0u;
-                std::memcpy(&r.b[3], &flags, 4);
-                idBits = o.id;
-            } else {
-                idBits = 0x80000000u | o.id;
-            }
-            std::memcpy(&r.a[3], &idBits, 4);
+            fillLeafRecord(ag.objects[ag.qbvh.refs[i]], flat.leaves[leafBase[a] + i]);
         }
         for (size_t i = 0; i < ag.lights.size(); ++i) flat.lights[lightBase[a] + i] = ag.lights[i];
         FlatScene::AggregateStats st;
@@ -278,6 +309,7 @@ void GpuSceneBuilder::finalize(uint32_t top) {
     for (size_t i = 0; i < flat.instances.size(); ++i) {
         const uint32_t a = instanceAggregate[i];
         flat.instances[i].root_node = nodeBase[a];
+        flat.instances[i].sbvh_root_node = sbvhNodeBase[a];
         flat.instances[i].light_base = aggregates[a].lights.empty() ? SLRGPU_INVALID_ID : lightBase[a];
         flat.instances[i].num_lights = (uint32_t)aggregates[a].lights.size();
     }
@@ -314,6 +346,10 @@ void FlatScene::describe(SlrGpuSceneDesc* d) const {
     for (int i = 0; i < 3; ++i) d->world_center[i] = worldCenter[i];
     d->world_radius = worldRadius;
     d->camera = camera;
+    if (!sbvhNodes.empty()) {
+        d->sbvh_nodes = sbvhNodes.data(); d->num_sbvh_nodes = (uint32_t)sbvhNodes.size();
+        d->sbvh_leaf_records = sbvhLeaves.data(); d->num_sbvh_leaf_records = (uint32_t)sbvhLeaves.size();
+    }
     d->environment.present = envPresent ? 1 : 0;
     d->environment.material = envMaterial;
     d->environment.map_width = envMapWidth; d->environment.map_height = envMapHeight;

@@ -136,6 +136,9 @@ struct FlatScene {
     std::vector<SlrGpuBvhNode> nodes;
     std::vector<SlrGpuLeafRecord> leaves;
     std::vector<SlrGpuInstance> instances;
+    // the binary SBVHs themselves (optional export, exportSbvh: the accelerator the reference's shipped build traverses)
+    std::vector<SlrGpuSbvhNode> sbvhNodes;
+    std::vector<SlrGpuLeafRecord> sbvhLeaves;
     std::vector<SlrGpuTriangle> triangles;
     std::vector<SlrGpuVertex> vertices;
     std::vector<SlrGpuMaterial> materials;
@@ -157,6 +160,7 @@ struct FlatScene {
     float worldCenter[3] = {0, 0, 0};
     float worldRadius = 0.0f;
     bool rgbMode = false;
+    static bool exportSbvh;          // process-wide option (slrhost_set_option "export_sbvh"): also flatten the SBVHs
     // build statistics (per aggregate: 0 = top level)
     struct AggregateStats { uint32_t numObjects, sbvhNodes, sbvhRefs, sbvhDepth, qbvhNodes, qbvhDepth, nodeBase, leafBase; float sbvhCost, qbvhCost; };
     std::vector<AggregateStats> stats;

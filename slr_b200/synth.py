@@ -197,7 +197,13 @@ def read_hits(path):
         t = np.frombuffer(f.read(4 * n), np.float32)
         u = np.frombuffer(f.read(4 * n), np.float32)
         v = np.frombuffer(f.read(4 * n), np.float32)
-    return {"prim": prim, "inst": inst, "t": t, "u": u, "v": v}
+        out = {"prim": prim, "inst": inst, "t": t, "u": u, "v": v}
+        rest = f.read()
+        if len(rest) == 20 * n:          # the SBVH pass of the same batch (ref_intersect)
+            a = np.frombuffer(rest, np.uint32).reshape(5, n)
+            out.update({"prim_sbvh": a[0].copy(), "inst_sbvh": a[1].copy(), "t_sbvh": a[2].view(np.float32).copy(),
+                        "u_sbvh": a[3].view(np.float32).copy(), "v_sbvh": a[4].view(np.float32).copy()})
+    return out
 
 
 def read_trees(path):

@@ -29,6 +29,9 @@ def main():
         # distances (different visiting order, later primitive wins): the goldens are QBVH's answers.
         out = {"prim": hits["prim"], "inst": hits["inst"], "t_bits": hits["t"].view(np.uint32),
                "u_bits": hits["u"].view(np.uint32), "v_bits": hits["v"].view(np.uint32),
+               # ... and SBVH's own answers (the shipped default accelerator, SBVH::intersect), for the SBVH entry point
+               "prim_sbvh": hits["prim_sbvh"], "inst_sbvh": hits["inst_sbvh"], "t_sbvh_bits": hits["t_sbvh"].view(np.uint32),
+               "u_sbvh_bits": hits["u_sbvh"].view(np.uint32), "v_sbvh_bits": hits["v_sbvh"].view(np.uint32),
                "num_trees": np.array(len(trees)), "qbvh_vs_sbvh_mismatches": np.array(info["qbvh_vs_sbvh_mismatches"]),
                "ray_digest": np.array(digest(np.stack([rays[k] for k in ("ox", "oy", "oz", "dx", "dy", "dz", "tmin", "tmax")])))}
         for i, t in enumerate(trees):

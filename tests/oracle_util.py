@@ -50,6 +50,24 @@ def restate_intersect(host_scene, rays, counters=True):
     return out
 
 
+def restate_intersect_sbvh(host_scene, rays):
+    """Closest hits of the CPU restatement of SBVH::intersect (the scene must carry the SBVH tables)."""
+    lib = restate_lib()
+    lib.slr_restate_intersect_sbvh.restype = C.c_int
+    lib.slr_restate_intersect_sbvh.argtypes = [C.POINTER(capi.SceneDesc), C.POINTER(capi.RayBatch), C.c_uint64, C.POINTER(capi.HitBatch)]
+    comps = [np.ascontiguousarray(rays[k], np.float32) for k in ("ox", "oy", "oz", "dx", "dy", "dz", "tmin", "tmax")]
+    n = comps[0].shape[0]
+    rb = capi.RayBatch(*[c.ctypes.data_as(capi.PF) for c in comps])
+    out = {"prim": np.empty(n, np.uint32), "inst": np.empty(n, np.uint32), "t": np.empty(n, np.float32),
+           "u": np.empty(n, np.float32), "v": np.empty(n, np.float32)}
+    hb = capi.HitBatch(out["prim"].ctypes.data_as(capi.PU32), out["inst"].ctypes.data_as(capi.PU32),
+                       out["t"].ctypes.data_as(capi.PF), out["u"].ctypes.data_as(capi.PF), out["v"].ctypes.data_as(capi.PF), None, None)
+    rc = lib.slr_restate_intersect_sbvh(C.byref(host_scene.desc), C.byref(rb), n, C.byref(hb))
+    assert rc >= 0, "the scene carries no SBVH tables (capi.set_option('export_sbvh', 1) before building it)"
+    out["overflow"] = rc
+    return out
+
+
 def have_ref(binary="ref_intersect"):
     return os.path.exists(os.path.join(REF_DIR, binary))
 
@@ -149,7 +167,17 @@ def case_instanced(rays_each=3000):
 CASES = {"heightfield": case_heightfield, "objects": case_objects, "instanced": case_instanced}
 
 
-def build_host_scene(meshes, placements):
+def build_host_scene(meshes, placements, with_sbvh=False):
+    if with_sbvh:
+        capi.set_option("export_sbvh", 1)
+    try:
+        return _build_host_scene(meshes, placements)
+    finally:
+        if with_sbvh:
+            capi.set_option("export_sbvh", 0)
+
+
+def _build_host_scene(meshes, placements):
     b = capi.SceneBuilder()
     ids = [b.add_mesh(p, i) for p, i in meshes]
     for mesh, mode, m in placements:
