@@ -44,9 +44,8 @@ def test_golden_records_where_the_two_accelerators_disagree(name):
     g = golden(name)
     differ = g["prim"] != g["prim_sbvh"]
     assert int(differ.sum()) == int(g["qbvh_vs_sbvh_mismatches"])
-    both = differ & (g["prim"] != 0xFFFFFFFF) & (g["prim_sbvh"] != 0xFFFFFFFF)
-    tq, ts = g["t_bits"][both].view(np.float32), g["t_sbvh_bits"][both].view(np.float32)
-    assert np.all(np.abs(tq - ts) <= 1e-5 * np.abs(tq))
+    # (no closeness bar on those rays: in the `objects` batch a ray lying in a cube face is hit at t = 1 by the QBVH and at
+    # t = 3, the far wall, by the SBVH -- each entry point must give ITS accelerator's answer, which is what is pinned)
     same = ~differ & (g["prim"] != 0xFFFFFFFF)
     assert np.array_equal(g["t_bits"][same], g["t_sbvh_bits"][same])
 
