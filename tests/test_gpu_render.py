@@ -70,7 +70,7 @@ def test_image_matches_reference_within_noise_floor(name, size, spp, workdir):
     assert bgot <= 1.5 * bfloor + 0.002, f"16x16-block relRMSE {bgot:.4f} vs floor {bfloor:.4f}"
 
 
-@pytest.mark.parametrize("name,size,spp", [("Cornell_Box_Spheres.txt", 128, 256), ("Cornell_Box_ColorChecker.txt", 96, 128), ("IBL_Test.txt", 96, 128)])
+@pytest.mark.parametrize("name,size,spp", [("Cornell_Box_Spheres.txt", 128, 256), ("Cornell_Box_ColorChecker.txt", 128, 256), ("IBL_Test.txt", 128, 256)])
 def test_unchanged_reference_scene_file_renders_like_the_reference(name, size, spp, workdir):
     """north_star: "TestScenes/*.txt render unchanged with the GPU path dropped in". The reference's own scene file, byte
     for byte, plus an appended size / sample-count override (both interpreters let the last setRenderer win; the files ask
