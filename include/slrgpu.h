@@ -105,8 +105,22 @@ typedef struct SlrGpuInstance {
     uint32_t light_index;   /* position of this instance in ITS parent's light list, or INVALID */
     float light_importance; /* integral of the nested light distribution (importance of the instance) */
     uint32_t sbvh_root_node; /* global index of the nested SBVH's root in sbvh_nodes (when the scene carries the SBVH) */
-    uint32_t pad[2];
+    uint32_t motion;         /* 0 = static; else 1 + index into `motions`: mat / mat_inv are then the key frame at t_begin */
+    uint32_t pad;
 } SlrGpuInstance;
+
+/* AnimatedTransform (libSLR/Core/Transform.h:89-144) of an instance or of the camera -- motion blur. The transform at ray
+ * time `time` is: the begin key frame (the owner's mat / mat_inv) for time <= t_begin, the end key frame for
+ * time >= t_end, else translate(lerp(T0, T1, t)) * Slerp(t, R0, R1).toMatrix() * lerp(S0, S1, t) with
+ * t = (time - t_begin) / (t_end - t_begin); T, R (quaternion x y z w), S are the host's decomposition of the two key
+ * frames (Quaternion.cpp:15-43). Matrices column-major. */
+typedef struct SlrGpuMotion {
+    float mat_end[16], mat_end_inv[16];
+    float T0[3], t_begin;
+    float T1[3], t_end;
+    float R0[4], R1[4];
+    float S0[16], S1[16];
+} SlrGpuMotion;
 
 /* 32-byte per-triangle shading record (indexed by prim_id). */
 typedef struct SlrGpuTriangle {
@@ -301,6 +315,11 @@ typedef struct SlrGpuSceneDesc {
      * leaf order, for slrgpu_intersect_batch_sbvh; NULL / 0 when not exported */
     const SlrGpuSbvhNode* sbvh_nodes;              uint32_t num_sbvh_nodes;
     const SlrGpuLeafRecord* sbvh_leaf_records;     uint32_t num_sbvh_leaf_records;
+
+    /* optional: animated transforms (SlrGpuInstance::motion, camera_motion); camera_motion: 0 = static camera, else 1 +
+     * index (camera.mat / mat_inv are then the begin key frame) */
+    const SlrGpuMotion* motions;                   uint32_t num_motions;
+    uint32_t camera_motion;                        uint32_t pad_motion;
 } SlrGpuSceneDesc;
 
 typedef struct SlrGpuScene SlrGpuScene;
@@ -320,7 +339,7 @@ SLRGPU_API const char* slrgpu_last_error(void);
 /* sizeof() of the ABI structs, so FFI bindings (ctypes, cgo, JNI) can verify their mirrors:
  * 0 SceneDesc, 1 BvhNode, 2 LeafRecord, 3 Instance, 4 Triangle, 5 Vertex, 6 Spectrum, 7 Texture,
  * 8 Image, 9 Material, 10 Light, 11 Camera, 12 Environment, 13 SpectralTables, 14 RayBatch,
- * 15 HitBatch, 16 RenderParams, 17 RenderStats, 18 SbvhNode. Unknown index -> 0. */
+ * 15 HitBatch, 16 RenderParams, 17 RenderStats, 18 SbvhNode, 19 Motion. Unknown index -> 0. */
 SLRGPU_API uint32_t slrgpu_struct_size(int which);
 
 /* Copies every buffer of `desc` to `device` (the caller keeps ownership of the host buffers, which

@@ -88,6 +88,12 @@ SLRGPU_API int slrhost_read_exr(const char* path, uint32_t* width, uint32_t* hei
 SLRGPU_API int slrhost_decode_png(const char* path, int gamma_correction, uint32_t* width, uint32_t* height, uint32_t* channels,
                                   uint8_t* pixels, uint64_t capacity);
 
+/* The host's AnimatedTransform (motion blur; libSLR/Core/Transform.h:89-144) for tests: decomposition of the two key
+ * matrices (T0[3] R0[4] S0[16] T1[3] R1[4] S1[16] = 46 floats), motionBounds of a box, and the transform sampled at n
+ * times (mat[16], matInv[16] each, column-major). Any output may be NULL. */
+SLRGPU_API int slrhost_sample_animated(const float* mat_begin, const float* mat_end, float t_begin, float t_end, const float* box6,
+                                       const float* times, uint32_t n, float* decomposition46, float* bounds6, float* out32n);
+
 SLRGPU_API void slrhost_scene_destroy(SlrHostScene* s);
 /* Fills `desc` with pointers into the scene's buffers (valid until slrhost_scene_destroy). */
 SLRGPU_API int slrhost_scene_describe(const SlrHostScene* s, SlrGpuSceneDesc* desc);

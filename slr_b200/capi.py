@@ -35,7 +35,7 @@ class LeafRecord(C.Structure):
 class Instance(C.Structure):
     _fields_ = [("mat", c_f * 16), ("mat_inv", c_f * 16), ("root_node", c_u32),
                 ("light_base", c_u32), ("num_lights", c_u32), ("light_index", c_u32),
-                ("light_importance", c_f), ("sbvh_root_node", c_u32), ("pad", c_u32 * 2)]
+                ("light_importance", c_f), ("sbvh_root_node", c_u32), ("motion", c_u32), ("pad", c_u32)]
 
 
 class Triangle(C.Structure):
@@ -61,6 +61,11 @@ class Texture(C.Structure):
 
 class SbvhNode(C.Structure):
     _fields_ = [("lo", c_f * 3), ("hi", c_f * 3), ("a", c_u32), ("b", c_u32)]
+
+
+class Motion(C.Structure):
+    _fields_ = [("mat_end", c_f * 16), ("mat_end_inv", c_f * 16), ("T0", c_f * 3), ("t_begin", c_f), ("T1", c_f * 3), ("t_end", c_f),
+                ("R0", c_f * 4), ("R1", c_f * 4), ("S0", c_f * 16), ("S1", c_f * 16)]
 
 
 class Image(C.Structure):
@@ -112,7 +117,8 @@ class SceneDesc(C.Structure):
                 ("world_center", c_f * 3), ("world_radius", c_f),
                 ("camera", Camera), ("environment", Environment), ("spectral", SpectralTables),
                 ("sbvh_nodes", C.POINTER(SbvhNode)), ("num_sbvh_nodes", c_u32),
-                ("sbvh_leaf_records", C.POINTER(LeafRecord)), ("num_sbvh_leaf_records", c_u32)]
+                ("sbvh_leaf_records", C.POINTER(LeafRecord)), ("num_sbvh_leaf_records", c_u32),
+                ("motions", C.POINTER(Motion)), ("num_motions", c_u32), ("camera_motion", c_u32), ("pad_motion", c_u32)]
 
 
 class RayBatch(C.Structure):
@@ -140,7 +146,7 @@ class RenderStats(C.Structure):
 
 _ABI_STRUCTS = [SceneDesc, BvhNode, LeafRecord, Instance, Triangle, Vertex, Spectrum, Texture, Image,
                 Material, Light, Camera, Environment, SpectralTables, RayBatch, HitBatch, RenderParams,
-                RenderStats, SbvhNode]
+                RenderStats, SbvhNode, Motion]
 
 RENDER_PROFILE_STAGES = 0x1
 
@@ -527,6 +533,20 @@ host.slrhost_set_option.argtypes = [C.c_char_p, C.c_int]
 def set_option(name, value):
     """slrhost_set_option: process-wide options of the host library ("export_sbvh")."""
     _host_check(host.slrhost_set_option(name.encode(), int(value)), "slrhost_set_option")
+
+
+host.slrhost_sample_animated.restype = C.c_int
+host.slrhost_sample_animated.argtypes = [PF, PF, c_f, c_f, PF, PF, c_u32, PF, PF, PF]
+
+
+def sample_animated(mat_begin, mat_end, t_begin, t_end, box, times):
+    """slrhost_sample_animated -> (decomposition[46], motion bounds[6], sampled[n, 32])."""
+    mb, me = _f32(np.asarray(mat_begin).T.reshape(-1)), _f32(np.asarray(mat_end).T.reshape(-1))        # row-major in, column-major ABI
+    bx, tm = _f32(box), _f32(times)
+    dec, bounds, out = np.zeros(46, np.float32), np.zeros(6, np.float32), np.zeros((tm.shape[0], 32), np.float32)
+    _host_check(host.slrhost_sample_animated(_pf(mb), _pf(me), t_begin, t_end, _pf(bx), _pf(tm), tm.shape[0], _pf(dec), _pf(bounds), _pf(out)),
+                "slrhost_sample_animated")
+    return dec, bounds, out
 
 
 host.slrhost_decode_png.restype = C.c_int

@@ -20,6 +20,7 @@ struct DeviceScene {
     const float4* nodes;
     const float4* leaves;
     const SlrGpuInstance* instances;
+    const SlrGpuMotion* motions;         // animated transforms (motion blur), SlrGpuInstance::motion / cameraMotion index + 1
     const SlrGpuSbvhNode* sbvhNodes;     // optional second accelerator (slrgpu_intersect_batch_sbvh)
     const float4* sbvhLeaves;
     const SlrGpuTriangle* triangles;
@@ -46,7 +47,8 @@ struct DeviceScene {
     float envMarginalIntegral;
     float topLightImportance;     // SurfaceObjectAggregate::importance() of the top-level aggregate
     uint32_t rgbMode;
-    uint32_t hasAlpha;            // some leaf record carries SLRGPU_LEAF_FLAG_ALPHA_TEST
+    uint32_t hasAlpha;            // the scene needs the GENERAL walk: some leaf record carries SLRGPU_LEAF_FLAG_ALPHA_TEST, or an instance moves
+    uint32_t cameraMotion;        // 0 = static camera, else 1 + index into motions
     float worldCenter[3];
     float worldRadius;
     SlrGpuCamera camera;
@@ -104,7 +106,8 @@ struct SlrGpuScene {
     uint64_t deviceBytes = 0;
     uint64_t arenaBytes = 0;          // size of allocations[0], the single arena all scene buffers live in
     bool hasInstances = false;
-    bool hasAlpha = false;            // alpha-mapped (cut-out) triangles: the walk kernels run their general instantiation
+    bool hasAlpha = false;            // alpha-mapped (cut-out) triangles or moving instances: the walk kernels run their general instantiation
+    bool hasMotion = false;           // animated transforms present: rays carry their time through the queues
     bool hasShading = false;
     uint32_t channels = 16;
     uint32_t classMask = 0;           // material classes (wavefront.cuh: ShadeClass) the scene's materials can produce

@@ -22,6 +22,7 @@ struct BatchRaySource {
         r.dx = rays.dir_x[i]; r.dy = rays.dir_y[i]; r.dz = rays.dir_z[i];
         r.tmin = rays.tmin[i]; r.tmax = rays.tmax[i];
     }
+    __device__ __forceinline__ float time(uint32_t) const { return 0.0f; }      // ray batches carry no time: moving instances stand at their begin key frame
 };
 template <bool COUNT> struct BatchHitSink {
     SlrGpuHitBatch hits;

@@ -22,6 +22,7 @@ struct PathRaySource {
         r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = o.w;
         r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = INFINITY;
     }
+    __device__ __forceinline__ float time(uint32_t i) const { return q.time ? q.time[i] : 0.0f; }
 };
 struct HitSink {
     HitBuffer hits;
@@ -38,6 +39,7 @@ struct ShadowRaySource {
         r.ox = o.x; r.oy = o.y; r.oz = o.z; r.tmin = o.w;
         r.dx = d.x; r.dy = d.y; r.dz = d.z; r.tmax = d.w;
     }
+    __device__ __forceinline__ float time(uint32_t i) const { return q.time ? q.time[i] : 0.0f; }
 };
 template <int NC> struct SplatSink {
     ShadowQueue q;

@@ -48,7 +48,7 @@ constexpr int materialMinBlocks(int cls) {
 // PerspectiveIDF::sample.
 struct CameraSample {
     V3 org, dir;
-    float weight, wlOffset;
+    float weight, wlOffset, time;
     uint32_t ipx, ipy, hero, flags;
 };
 template <int NC>
@@ -59,18 +59,29 @@ __device__ __forceinline__ void sampleCamera(const DeviceScene& s, const RenderC
     const float px = x + r0.y, py = y + r0.z;
     const float wlOffset = r0.w;
     o->wlOffset = wlOffset;
+    // IndependentLightPathSampler::getTimeSample (light_path_samplers.h:50)
+    const float time = rc.timeStart * (1 - r0.x) + rc.timeEnd * r0.x;
+    o->time = time;
     o->hero = min((uint32_t)(NC * r1.x), (uint32_t)(NC - 1));
 
     // PerspectiveCamera::sample
     float lx, ly;
     concentricSampleDisk(r1.y, r1.z, &lx, &ly);
     const SlrGpuCamera& cam = s.camera;
+    // the camera's transform at the sample's time (PerspectiveCamera::sample, PerspectiveCamera.cpp:34-36)
+    float camScratch[32];
+    const float* camMat = cam.mat;
+    const float* camInv = cam.mat_inv;
+    if (s.cameraMotion != 0u && s.motions != nullptr) {
+        sampleMotion(s.motions[s.cameraMotion - 1u], cam.mat, cam.mat_inv, time, camScratch, camScratch + 16);
+        camMat = camScratch; camInv = camScratch + 16;
+    }
     const V3 orgLocal(cam.lens_radius * lx, cam.lens_radius * ly, 0.0f);
-    o->org = xfmPoint(cam.mat, orgLocal);
-    const V3 lensN = xfmNormal(cam.mat_inv, V3(0, 0, 1));
+    o->org = xfmPoint(camMat, orgLocal);
+    const V3 lensN = xfmNormal(camInv, V3(0, 0, 1));
     Frame f;
     f.z = lensN;
-    f.x = xfmVector(cam.mat, V3(1, 0, 0));
+    f.x = xfmVector(camMat, V3(1, 0, 0));
     f.y = cross(f.z, f.x);
     // PerspectiveIDF::sample with (p.x / W, p.y / H)
     const V3 pFocus(rc.opWidth * (0.5f - px / rc.width), rc.opHeight * (0.5f - py / rc.height), cam.obj_plane_dist);
@@ -124,6 +135,7 @@ raygenKernel(const DeviceScene s, const RenderConstants rc, PathQueue out, const
         out.dir[pos] = make_float4(dir.x, dir.y, dir.z, 0.0f);
         out.meta[pos] = make_uint4(ipy * rc.width + ipx, sample, hero | (flags << 8), __float_as_uint(wlOffset));
         out.weight[pos] = weight * rc.recBinWidth;
+        if (out.time) out.time[pos] = cs.time;
         // no throughput (it is 1) and no roulette slot for a camera ray: the stages know from the flag (stages.cuh)
     }
 }
@@ -204,6 +216,7 @@ debugKernel(const DeviceScene s, const RenderConstants rc, float* __restrict__ o
     WalkState w;
     w.r.ox = cs.org.x; w.r.oy = cs.org.y; w.r.oz = cs.org.z; w.r.tmin = 0.0f;
     w.r.dx = cs.dir.x; w.r.dy = cs.dir.y; w.r.dz = cs.dir.z; w.r.tmax = INFINITY;
+    w.time = cs.time;
     InstanceWalkState iw;
     iw.leaves.clear(); iw.saved.clear(); iw.curInst = SLRGPU_INVALID_ID;
     TraversalCounters cnt = {0, 0};
@@ -217,7 +230,7 @@ debugKernel(const DeviceScene s, const RenderConstants rc, float* __restrict__ o
     if (w.hit.prim == SLRGPU_INVALID_ID) return;
     SurfPt sp;
     float localArea;
-    hitSurfacePoint(s, w.hit.prim, w.hit.inst, w.hit.t, w.hit.u, w.hit.v, cs.org, cs.dir, &sp, &localArea);
+    hitSurfacePoint(s, w.hit.prim, w.hit.inst, w.hit.t, w.hit.u, w.hit.v, cs.org, cs.dir, cs.time, &sp, &localArea);
     o[0] = 1.0f;
     o[1] = sp.gn.x; o[2] = sp.gn.y; o[3] = sp.gn.z;
     o[4] = sp.sf.z.x; o[5] = sp.sf.z.y; o[6] = sp.sf.z.z;
@@ -231,6 +244,7 @@ struct RenderWorkspace {
     void* ptrs[48] = {};
     int n = 0;
     uint32_t capacity = 0, channels = 0;
+    bool motion = false;                         // the queues carry ray times (scene with animated transforms)
     PathQueue q[2];
     HitBuffer hits;
     ShadowQueue sq;
@@ -294,8 +308,10 @@ struct RenderWorkspace {
 constexpr int kRing = 8;
 constexpr uint32_t kWaveLogSize = 4096;
 
-static int allocPathQueue(RenderWorkspace& b, PathQueue* q, uint32_t P, int quarters) {
+static int allocPathQueue(RenderWorkspace& b, PathQueue* q, uint32_t P, int quarters, bool motion) {
     int rc;
+    q->time = nullptr;
+    if (motion && (rc = b.alloc(&q->time, P))) return rc;
     if ((rc = b.alloc(&q->org, P))) return rc;
     if ((rc = b.alloc(&q->dir, P))) return rc;
     if ((rc = b.alloc(&q->meta, P))) return rc;
@@ -325,19 +341,21 @@ static int acquireWorkspace(SlrGpuScene* sc, uint32_t P, RenderWorkspace** out) 
         std::lock_guard<std::mutex> lock(g_poolMutex);
         if (sc->device >= 0 && sc->device < 64) { w = g_pool[sc->device]; g_pool[sc->device] = nullptr; }
     }
-    if (w && w->capacity == P && w->channels == sc->channels) { *out = w; return SLRGPU_OK; }
+    if (w && w->capacity == P && w->channels == sc->channels && w->motion == sc->hasMotion) { *out = w; return SLRGPU_OK; }
     delete w;
     w = new (std::nothrow) RenderWorkspace();
     if (!w) { setError("host allocation failed"); return SLRGPU_ERR_OUT_OF_MEMORY; }
     const int quarters = sc->channels == 3 ? 1 : 4;
     int rc = SLRGPU_OK;
-    for (int k = 0; k < 2 && !rc; ++k) rc = allocPathQueue(*w, &w->q[k], P, quarters);
+    for (int k = 0; k < 2 && !rc; ++k) rc = allocPathQueue(*w, &w->q[k], P, quarters, sc->hasMotion);
     if (!rc) rc = w->alloc(&w->hits.id, P);
     if (!rc) rc = w->alloc(&w->hits.tuv, P);
     if (!rc) rc = w->alloc(&w->sq.org, P);
     if (!rc) rc = w->alloc(&w->sq.dir, P);
     if (!rc) rc = w->alloc(&w->sq.pixelWl, P);
     if (!rc) rc = w->alloc(&w->sq.contrib, (uint64_t)P * quarters);
+    w->sq.time = nullptr;
+    if (!rc && sc->hasMotion) rc = w->alloc(&w->sq.time, P);
     if (!rc) rc = w->alloc(&w->cq.entries, (uint64_t)P * SC_COUNT);
     if (!rc) rc = w->alloc(&w->dCounters, 1);
     if (!rc) rc = w->alloc(&w->dWaveLog, kWaveLogSize);
@@ -352,7 +370,7 @@ static int acquireWorkspace(SlrGpuScene* sc, uint32_t P, RenderWorkspace** out) 
     if (!rc) { cudaError_t e = cudaEventCreateWithFlags(&w->forkEvent, cudaEventDisableTiming); if (e != cudaSuccess) rc = cudaFail(e, "cudaEventCreate"); }
     if (rc) { delete w; return rc; }
     w->sq.capacity = P; w->cq.capacity = P;
-    w->capacity = P; w->channels = sc->channels;
+    w->capacity = P; w->channels = sc->channels; w->motion = sc->hasMotion;
     *out = w;
     return SLRGPU_OK;
 }
@@ -683,7 +701,7 @@ probeShadeKernel(const DeviceScene s, const float* __restrict__ probes, uint32_t
     const uint32_t hero = min((uint32_t)(16 * p[7]), 15u);
     SurfPt sp;
     float localArea;
-    const SlrGpuTriangle tri = hitSurfacePoint(s, prim, hits.inst[i], hits.t[i], hits.u[i], hits.v[i], org, dir, &sp, &localArea);
+    const SlrGpuTriangle tri = hitSurfacePoint(s, prim, hits.inst[i], hits.t[i], hits.u[i], hits.v[i], org, dir, 0.0f, &sp, &localArea);
     o[0] = 1.0f; o[1] = hits.t[i];
     o[2] = sp.p.x; o[3] = sp.p.y; o[4] = sp.p.z;
     o[5] = sp.sf.z.x; o[6] = sp.sf.z.y; o[7] = sp.sf.z.z;

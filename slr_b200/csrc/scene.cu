@@ -347,8 +347,12 @@ struct Validator {
                 *hasAlpha = true;
             }
         }
+        if (d->camera_motion > d->num_motions || (d->num_motions && !d->motions)) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "camera_motion / motions out of range");
+        for (uint32_t i = 0; i < d->num_motions; ++i)
+            if (!(d->motions[i].t_end > d->motions[i].t_begin)) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "motion %u: t_end must be greater than t_begin", i);
         for (uint32_t i = 0; i < d->num_instances; ++i) {
             const SlrGpuInstance& in = d->instances[i];
+            if (in.motion > d->num_motions) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "instance %u: motion index out of range", i);
             if (in.root_node >= d->num_bvh_nodes) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "instance %u: root node out of range", i);
             if (in.num_lights && (in.light_base == SLRGPU_INVALID_ID || (uint64_t)in.light_base + in.num_lights > d->num_lights))
                 return fail(SLRGPU_ERR_INVALID_ARGUMENT, "instance %u: light list out of range", i);
@@ -428,7 +432,7 @@ SLRGPU_API uint32_t slrgpu_struct_size(int which) {
         sizeof(SlrGpuTriangle), sizeof(SlrGpuVertex), sizeof(SlrGpuSpectrum), sizeof(SlrGpuTexture),
         sizeof(SlrGpuImage), sizeof(SlrGpuMaterial), sizeof(SlrGpuLight), sizeof(SlrGpuCamera),
         sizeof(SlrGpuEnvironment), sizeof(SlrGpuSpectralTables), sizeof(SlrGpuRayBatch), sizeof(SlrGpuHitBatch),
-        sizeof(SlrGpuRenderParams), sizeof(SlrGpuRenderStats), sizeof(SlrGpuSbvhNode)};
+        sizeof(SlrGpuRenderParams), sizeof(SlrGpuRenderStats), sizeof(SlrGpuSbvhNode), sizeof(SlrGpuMotion)};
     if (which < 0 || which >= (int)(sizeof(sizes) / sizeof(sizes[0]))) return 0;
     return sizes[which];
 }
@@ -472,6 +476,7 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
     UP(reinterpret_cast<const float4*>(d->bvh_nodes), (uint64_t)d->num_bvh_nodes * 8, &v.nodes);
     UP(reinterpret_cast<const float4*>(d->leaf_records), (uint64_t)d->num_leaf_records * 3, &v.leaves);
     UP(d->instances, d->num_instances, &v.instances);
+    UP(d->motions, d->num_motions, &v.motions);
     if (d->sbvh_nodes && d->num_sbvh_nodes && d->sbvh_leaf_records && d->num_sbvh_leaf_records) {
         UP(d->sbvh_nodes, d->num_sbvh_nodes, &v.sbvhNodes);
         UP(reinterpret_cast<const float4*>(d->sbvh_leaf_records), (uint64_t)d->num_sbvh_leaf_records * 3, &v.sbvhLeaves);
@@ -538,8 +543,13 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
     // which material-class kernels a wave has to launch: the classes the device's own classification (classifyMaterialIn)
     // gives the triangles' materials, worked out by the validation pass
     sc->classMask = classMask;
-    sc->hasAlpha = hasAlpha;
-    v.hasAlpha = hasAlpha ? 1u : 0u;
+    sc->hasMotion = d->camera_motion != 0;
+    bool movingInstance = false;
+    for (uint32_t i = 0; i < d->num_instances; ++i) movingInstance = movingInstance || d->instances[i].motion != 0;
+    sc->hasMotion = sc->hasMotion || movingInstance;
+    sc->hasAlpha = hasAlpha || movingInstance;         // both take the general instantiation of the walk kernels
+    v.hasAlpha = sc->hasAlpha ? 1u : 0u;
+    v.cameraMotion = d->camera_motion;
     *out = sc;
     return SLRGPU_OK;
 }

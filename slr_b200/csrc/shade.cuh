@@ -8,6 +8,7 @@
 //   DiffuseEDF / IBLEDF                               libSLR/EDFs/basic_EDFs.cpp:12-29, IBLEDF.cpp:11-29
 #pragma once
 #include "material.cuh"
+#include "motion.cuh"
 
 namespace slrgpu {
 
@@ -58,18 +59,19 @@ __device__ __forceinline__ void applyNormalMap(const DeviceScene& s, uint32_t no
 
 // operator*(StaticTransform, SurfacePoint) (geometry.cpp:63-78): normal by the transposed inverse,
 // the frame vectors as plain vectors, everything re-normalised
-__device__ __forceinline__ void transformSurfPt(const SlrGpuInstance& inst, SurfPt* sp) {
-    sp->p = xfmPoint(inst.mat, sp->p);
-    sp->gn = normalize(xfmNormal(inst.mat_inv, sp->gn));
-    sp->sf.x = normalize(xfmVector(inst.mat, sp->sf.x));
-    sp->sf.y = normalize(xfmVector(inst.mat, sp->sf.y));
-    sp->sf.z = normalize(xfmVector(inst.mat, sp->sf.z));
+__device__ __forceinline__ void transformSurfPt(const InstanceXfm& x, SurfPt* sp) {
+    sp->p = xfmPoint(x.mat, sp->p);
+    sp->gn = normalize(xfmNormal(x.matInv, sp->gn));
+    sp->sf.x = normalize(xfmVector(x.mat, sp->sf.x));
+    sp->sf.y = normalize(xfmVector(x.mat, sp->sf.y));
+    sp->sf.z = normalize(xfmVector(x.mat, sp->sf.z));
 }
 
 // Intersection -> SurfacePoint for a triangle hit. Returns the hit triangle's record; *localArea is
-// the area evaluateAreaPDF uses (object space, also for instances -- as the reference).
+// the area evaluateAreaPDF uses (object space, also for instances -- as the reference). `time`: the ray's time, at which a
+// moving instance's transform is sampled (TransformedSurfaceObject::getSurfacePoint, SurfaceObject.cpp:320-336).
 static __device__ __noinline__ SlrGpuTriangle hitSurfacePoint(const DeviceScene& s, uint32_t prim, uint32_t inst, float t, float b0, float b1,
-                                                 const V3& org, const V3& dir, SurfPt* sp, float* localArea) {
+                                                 const V3& org, const V3& dir, float time, SurfPt* sp, float* localArea) {
     const SlrGpuTriangle tri = s.triangles[prim];
     const TriVerts tv = loadTriangle(s, tri);
     sp->atInfinity = false;
@@ -81,11 +83,12 @@ static __device__ __noinline__ SlrGpuTriangle hitSurfacePoint(const DeviceScene&
         sp->p = org + dir * t;
         if (tri.normal_map != SLRGPU_INVALID_ID) applyNormalMap(s, tri.normal_map, sp);
     } else {
-        const SlrGpuInstance& in = s.instances[inst];
-        const V3 lo = xfmPoint(in.mat_inv, org), ld = xfmVector(in.mat_inv, dir);
+        float scratch[32];
+        const InstanceXfm x = instanceTransformAt(s, s.instances[inst], time, scratch);
+        const V3 lo = xfmPoint(x.matInv, org), ld = xfmVector(x.matInv, dir);
         sp->p = lo + ld * t;
         if (tri.normal_map != SLRGPU_INVALID_ID) applyNormalMap(s, tri.normal_map, sp);
-        transformSurfPt(in, sp);
+        transformSurfPt(x, sp);
     }
     return tri;
 }
@@ -151,7 +154,7 @@ struct LightSample {
 };
 
 // Scene::selectLight + Light::sample (SurfaceObject.cpp:432-452, 82-91, 158-185, 351-364)
-static __device__ __noinline__ void sampleLight(const DeviceScene& s, float uSel, float u0, float u1, LightSample* ls) {
+static __device__ __noinline__ void sampleLight(const DeviceScene& s, float uSel, float u0, float u1, float time, LightSample* ls) {
     float prob = 1.0f;
     bool env = false;
     const float aggrImp = s.topLightImportance;
@@ -212,7 +215,11 @@ static __device__ __noinline__ void sampleLight(const DeviceScene& s, float uSel
     sp.prim = object; sp.inst = inst;
     triangleFrame(tv, b0, b1, b2, false, &sp);
     ls->areaPDF = 1.0f / triangleArea(tv);
-    if (inst != SLRGPU_INVALID_ID) transformSurfPt(s.instances[inst], &sp);
+    if (inst != SLRGPU_INVALID_ID) {
+        // a light inside an instance: the instance's transform at the query's time (SurfaceObject.cpp:351-364)
+        float scratch[32];
+        transformSurfPt(instanceTransformAt(s, s.instances[inst], time, scratch), &sp);
+    }
     ls->lightPDF = prob * ls->areaPDF;
     ls->material = tri.material;
 }

@@ -78,7 +78,7 @@ static __device__ __noinline__ void surfaceEmission(const DeviceScene& s, const 
     else {
         hid = hits.id[i];
         const float4 htuv = hits.tuv[i];
-        tri = hitSurfacePoint(s, hid.x, hid.y, htuv.x, htuv.y, htuv.z, org, dir, &sp, &localArea);
+        tri = hitSurfacePoint(s, hid.x, hid.y, htuv.x, htuv.y, htuv.z, org, dir, in.time ? in.time[i] : 0.0f, &sp, &localArea);
         material = tri.material;
     }
     const V3 dirOut = sp.sf.toLocal(-dir);
@@ -220,12 +220,13 @@ template <int NC> struct MaterialResult {
     Spec<NC> alpha;
     V3 sOrg, sDir;
     float sTmax;
+    float time;                 // the path's ray time, handed on to the continued path and to the shadow ray
     Spec<NC> sContrib;
     __device__ __forceinline__ void clear() {
         alive = false; shadow = false;
         nOrg = V3(0, 0, 0); nDir = V3(0, 0, 1); nPdf = 0.0f; nImp = 0.0f;
         meta = make_uint4(0, 0, 0, 0); weight = 0.0f; alpha = specConst<NC>(0.0f);
-        sOrg = V3(0, 0, 0); sDir = V3(0, 0, 1); sTmax = 0.0f; sContrib = specConst<NC>(0.0f);
+        sOrg = V3(0, 0, 0); sDir = V3(0, 0, 1); sTmax = 0.0f; time = 0.0f; sContrib = specConst<NC>(0.0f);
     }
 };
 
@@ -248,7 +249,8 @@ __device__ __forceinline__ void materialItem(const DeviceScene& s, const RenderC
 
     SurfPt sp;
     float localArea;
-    hitSurfacePoint(s, hid.x, hid.y, htuv.x, htuv.y, htuv.z, org, dir, &sp, &localArea);
+    o.time = in.time ? in.time[i] : 0.0f;
+    hitSurfacePoint(s, hid.x, hid.y, htuv.x, htuv.y, htuv.z, org, dir, o.time, &sp, &localArea);
     const V3 dirOut = sp.sf.toLocal(-dir);
     const V3 gNorm = sp.sf.toLocal(sp.gn);
     HitBsdf<NC, CLASS> bsdf;
@@ -261,7 +263,7 @@ __device__ __forceinline__ void materialItem(const DeviceScene& s, const RenderC
     // next event estimation
     if (bsdf.hasNonDelta() && (s.numTopLights > 0 || s.envPresent)) {
         LightSample ls;
-        sampleLight(s, ra.x, ra.y, ra.z, &ls);
+        sampleLight(s, ra.x, ra.y, ra.z, o.time, &ls);
         float dist2;
         V3 shadowDir;
         if (ls.sp.atInfinity) { dist2 = 1.0f; shadowDir = normalize(ls.sp.p); }
@@ -322,6 +324,7 @@ __device__ __forceinline__ void materialWrite(const PathQueue& out, const Shadow
         sq.dir[spos] = make_float4(o.sDir.x, o.sDir.y, o.sDir.z, o.sTmax);
         const bool inPlace = ((o.meta.z >> 8) & kFlagStrataInPlace) != 0;
         sq.pixelWl[spos] = make_uint2(o.meta.x | (inPlace ? 0x80000000u : 0u), o.meta.w);
+        if (sq.time) sq.time[spos] = o.time;
         if (NC == 3) sq.contrib[spos] = make_float4(o.sContrib.v[0], o.sContrib.v[1], o.sContrib.v[2], 0.0f);
         else {
 #pragma unroll
@@ -336,6 +339,7 @@ __device__ __forceinline__ void materialWrite(const PathQueue& out, const Shadow
         out.meta[npos] = o.meta;
         out.weight[npos] = o.weight;
         out.aux[npos] = o.nImp;
+        if (out.time) out.time[npos] = o.time;
         storeAlpha<NC>(out, npos, o.alpha);
     }
 }

@@ -47,7 +47,7 @@ __device__ __noinline__ void tailWalkT(const DeviceScene& s, WalkState& w, uint3
     if (ovf) *overflow = true;
 }
 template <bool ANY_HIT>
-__device__ __forceinline__ void tailWalk(const DeviceScene& s, WalkState& w, uint32_t* stack, bool* overflow) {
+__device__ __forceinline__ void tailWalk(const DeviceScene& s, WalkState& w, uint32_t* stack, bool* overflow) {   // w.time set by the caller
     if (s.hasAlpha) tailWalkT<ANY_HIT, true, true>(s, w, stack, overflow);
     else if (s.numInstances != 0) tailWalkT<ANY_HIT, true, false>(s, w, stack, overflow);
     else tailWalkT<ANY_HIT, false, false>(s, w, stack, overflow);
@@ -114,6 +114,7 @@ tailKernel(const DeviceScene s, const RenderConstants rc, PathQueue q0, PathQueu
             ++nExtend;
             WalkState w;
             PathRaySource{in}.load(slot, w.r);
+            w.time = PathRaySource{in}.time(slot);
             tailWalk<false>(s, w, stack, &overflow);
             HitSink{hits}.done(slot, w, noCount);
             surfaceItem<NC>(s, rc, in, hits, accum, slot, &cls, &leaf);
@@ -130,6 +131,7 @@ tailKernel(const DeviceScene s, const RenderConstants rc, PathQueue q0, PathQueu
             ++nShadow;
             WalkState w;
             ShadowRaySource{sq}.load(slot, w.r);
+            w.time = ShadowRaySource{sq}.time(slot);
             tailWalk<true>(s, w, stack, &overflow);
             SplatSink<NC>{sq, accum}.done(slot, w, noCount);
         }

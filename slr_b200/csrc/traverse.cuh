@@ -18,6 +18,7 @@
 // a leaf record is 48 B = three. One thread owns one ray; the 64-entry stack lives in local memory.
 #pragma once
 #include "device_scene.h"
+#include "motion.cuh"
 #include "textures.cuh"
 
 namespace slrgpu {
@@ -186,6 +187,7 @@ struct WalkState {
     uint32_t top;                // == stack[sp - 1] while sp > 0: the next pop comes from a register, its successor is
                                  // re-loaded one step ahead (the local-memory load is off the node fetch's critical path)
     bool found;
+    float time;                  // the ray's time (motion blur): read only by the general instantiation, at a moving instance
     TraversalCounters cnt0;      // the lane's running counters when this ray started (per-ray counts = difference)
 };
 
@@ -369,8 +371,16 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
                         iw.saved = iw.leaves;
                         iw.leaves.clear();
                         float lx, ly, lz, mx, my, mz;
-                        mulPoint(inst->mat_inv, r.ox, r.oy, r.oz, &lx, &ly, &lz);
-                        mulVector(inst->mat_inv, r.dx, r.dy, r.dz, &mx, &my, &mz);
+                        if (ALPHA && inst->motion != 0u && s.motions != nullptr) {
+                            // a moving instance (general instantiation only): its transform at the ray's time (Transform.cpp:31-35)
+                            float xf[32];
+                            sampleMotion(s.motions[inst->motion - 1u], inst->mat, inst->mat_inv, w.time, xf, xf + 16);
+                            mulPoint(xf + 16, r.ox, r.oy, r.oz, &lx, &ly, &lz);
+                            mulVector(xf + 16, r.dx, r.dy, r.dz, &mx, &my, &mz);
+                        } else {
+                            mulPoint(inst->mat_inv, r.ox, r.oy, r.oz, &lx, &ly, &lz);
+                            mulVector(inst->mat_inv, r.dx, r.dy, r.dz, &mx, &my, &mz);
+                        }
                         r.ox = lx; r.oy = ly; r.oz = lz; r.dx = mx; r.dy = my; r.dz = mz;
                         walkSetRay(w);
                         iw.curInst = instId;
@@ -435,6 +445,7 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
                 if (!active && rank < avail) {
                     idx = chunkNext + rank;
                     source.load(idx, w.r);
+                    w.time = ALPHA ? source.time(idx) : 0.0f;
                     walkBegin(w, stack);
                     iw.leaves.clear();
                     if (INSTANCES) { iw.saved.clear(); iw.curInst = SLRGPU_INVALID_ID; }

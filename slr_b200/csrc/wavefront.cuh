@@ -28,6 +28,7 @@ struct PathQueue {
     float* aux;            // written by the stage that produced the entry: importance(alpha) (the Russian-roulette
                            // probability of the next hit); overwritten by `surface` with the roulette scale 1/q
     float4* alpha;
+    float* time;           // ray time (Ray::time), only allocated for scenes with animated transforms (else null)
     uint32_t capacity;     // stride of the alpha quarters
 };
 
@@ -41,6 +42,7 @@ struct ShadowQueue {
     float4* dir;
     uint2* pixelWl;        // pixel | strataInPlace << 31, bits(wavelength offset)
     float4* contrib;
+    float* time;           // as PathQueue::time
     uint32_t capacity;     // stride of the contribution quarters
 };
 

@@ -284,6 +284,32 @@ SLRGPU_API int slrhost_write_exr(const char* path, uint32_t width, uint32_t heig
     return exr::save(path, width, height, rgba) ? 0 : fail("cannot write %s", path);
 }
 
+SLRGPU_API int slrhost_sample_animated(const float* mat_begin, const float* mat_end, float t_begin, float t_end, const float* box6,
+                                       const float* times, uint32_t n, float* decomposition46, float* bounds6, float* out32n) {
+    if (!mat_begin || !mat_end) return fail("slrhost_sample_animated: null argument");
+    try {
+        const AnimatedTransform a(toTransform(mat_begin), toTransform(mat_end), t_begin, t_end);
+        if (decomposition46) {
+            float* o = decomposition46;
+            for (int k = 0; k < 2; ++k) {
+                *o++ = a.T[k].x; *o++ = a.T[k].y; *o++ = a.T[k].z;
+                *o++ = a.R[k].x; *o++ = a.R[k].y; *o++ = a.R[k].z; *o++ = a.R[k].w;
+                std::memcpy(o, &a.S[k], 64); o += 16;
+            }
+        }
+        if (bounds6 && box6) {
+            const BBox b = a.motionBounds(BBox(Vec3(box6[0], box6[1], box6[2]), Vec3(box6[3], box6[4], box6[5])));
+            bounds6[0] = b.lo.x; bounds6[1] = b.lo.y; bounds6[2] = b.lo.z; bounds6[3] = b.hi.x; bounds6[4] = b.hi.y; bounds6[5] = b.hi.z;
+        }
+        for (uint32_t i = 0; i < n && times && out32n; ++i) {
+            const StaticTransform tf = a.sample(times[i]);
+            std::memcpy(out32n + 32 * (size_t)i, &tf.mat, 64);
+            std::memcpy(out32n + 32 * (size_t)i + 16, &tf.matInv, 64);
+        }
+        return 0;
+    } catch (const std::exception& e) { return fail("%s", e.what()); }
+}
+
 SLRGPU_API int slrhost_read_exr(const char* path, uint32_t* width, uint32_t* height, float* rgba, uint64_t capacity_floats) {
     if (!path || !width || !height) return fail("slrhost_read_exr: null argument");
     exr::Image img;

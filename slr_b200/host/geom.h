@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdint>
 #include <limits>
+#include <memory>
 
 namespace slr {
 
@@ -96,9 +97,15 @@ Mat4 scale(float x, float y, float z);         // Matrix4x4.h:204-222
 Mat4 rotate(float angle, const Vec3& axis);    // Matrix4x4.cpp:111-137
 Mat4 lookAt(const Vec3& eye, const Vec3& tgt, const Vec3& up);  // Matrix4x4.cpp:92-107
 
-// mat + cached inverse; normals go through the transposed inverse (Transform.h:38-51)
+struct AnimatedTransform;
+
+// mat + cached inverse; normals go through the transposed inverse (Transform.h:38-51).
+// `anim` (normally null) makes the value stand for an AnimatedTransform whose key frame at the begin time is mat / matInv:
+// this is how the scene language's Transform values and InternalNode::setTransform carry motion (Transform.h:89-144)
+// through code that is otherwise static. operator* and inverse() are defined for static values only.
 struct StaticTransform {
     Mat4 mat, matInv;
+    std::shared_ptr<const AnimatedTransform> anim;
     StaticTransform() : mat(Mat4::identity()), matInv(Mat4::identity()) {}
     explicit StaticTransform(const Mat4& m) : mat(m), matInv(invert(m)) {}
     StaticTransform(const Mat4& m, const Mat4& mi) : mat(m), matInv(mi) {}
@@ -111,8 +118,20 @@ struct StaticTransform {
     }
     StaticTransform operator*(const StaticTransform& t) const { return StaticTransform(mat * t.mat); }
     StaticTransform inverse() const { return StaticTransform(matInv, mat); }
-    bool isIdentity() const { return mat.isIdentity(); }
+    bool isIdentity() const { return mat.isIdentity() && !anim; }
 };
+
+// Quaternion (libSLR/BasicTypes/Quaternion.h:17-127): built from a rotation matrix, toMatrix, Slerp.
+struct Quat {
+    float x = 0, y = 0, z = 0, w = 1;
+    Quat() {}
+    Quat(float xx, float yy, float zz, float ww) : x(xx), y(yy), z(zz), w(ww) {}
+    explicit Quat(const Mat4& m);
+    Mat4 toMatrix() const;
+};
+Quat slerp(float t, const Quat& q0, const Quat& q1);
+// polar decomposition M = translate(T) * R * S by the iteration R <- (R + (R^T)^-1) / 2 (Quaternion.cpp:15-43)
+void decompose(const Mat4& m, Vec3* T, Quat* R, Mat4* S);
 
 enum Axis : uint8_t { Axis_X = 0, Axis_Y = 1, Axis_Z = 2 };
 
@@ -136,6 +155,24 @@ struct BBox {
 };
 inline BBox intersection(const BBox& a, const BBox& b) { return BBox(vmax(a.lo, b.lo), vmin(a.hi, b.hi)); }
 BBox transformBounds(const Mat4& m, const BBox& b);  // 8-corner transform, Transform.h:54-65
+
+// AnimatedTransform (libSLR/Core/Transform.h:89-144): two key frames, decomposed into translation, rotation and
+// scale / shear; between the key times the three parts are interpolated (lerp, Slerp, lerp) and recomposed.
+struct AnimatedTransform {
+    StaticTransform begin, end;
+    float tBegin, tEnd;
+    Vec3 T[2];
+    Quat R[2];
+    Mat4 S[2];
+    AnimatedTransform(const StaticTransform& b, const StaticTransform& e, float tb, float te);
+    bool isStatic() const { return begin.mat == end.mat; }
+    StaticTransform sample(float time) const;
+    // union of the transformed box at 128 times across [tBegin, tEnd] (Transform.h:131-143: sampling, not a guaranteed bound)
+    BBox motionBounds(const BBox& b) const;
+    // static * this and this * static (Transform.cpp:67-72)
+    std::shared_ptr<const AnimatedTransform> mulLeft(const StaticTransform& s) const;
+    std::shared_ptr<const AnimatedTransform> mulRight(const StaticTransform& s) const;
+};
 
 // One mesh vertex as the reference stores it (geometry.h:148-156): 44 bytes.
 struct Vertex {

@@ -284,8 +284,12 @@ void registerBuiltins(Interpreter& in) {
         return Value::Matrix(invert(raw) * rotate((float)M_PI, Vec3(0, 1, 0)));
     }));
     def(in, "AnimatedTransform", fn({{"tfStart", Type::Matrix}, {"tfEnd", Type::Matrix}, {"tBegin", R}, {"tEnd", R}}, [](const Args& a, Interpreter& in) -> Value {
+        // builtin_transform.cpp:81-90: an AnimatedTransform between two key matrices; a Transform value carries it in
+        // StaticTransform::anim (geom.h), with the begin key frame as its static part
         if (a.at("tfStart").m == a.at("tfEnd").m) return a.at("tfStart").convertTo(Type::Transform);
-        in.fail("AnimatedTransform with different begin/end matrices (motion blur) is not supported by the GPU path yet");
+        auto tf = std::make_shared<StaticTransform>(a.at("tfStart").m);
+        tf->anim = std::make_shared<AnimatedTransform>(*tf, StaticTransform(a.at("tfEnd").m), f(a, "tBegin"), f(a, "tEnd"));
+        return Value::Ref(Type::Transform, tf);
     }));
 
     // ---- textures (BuiltinFunctions/builtin_texture.cpp)

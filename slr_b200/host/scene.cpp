@@ -54,9 +54,37 @@ NodeRef TriangleMeshNode::copy() const {
 }
 
 void InternalNode::getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) {
-    // parent * local, with the inverse recomputed from the product as StaticTransform's ctor does
-    StaticTransform reduced = subTF ? (*subTF * m_localToWorld) : m_localToWorld;
-    for (const NodeRef& c : m_children) c->getRenderingData(b, &reduced, data);
+    if (subTF && subTF->anim) throw std::runtime_error("internal: an animated transform was handed down the scene graph");
+    if (!m_localToWorld.anim) {
+        // parent * local, with the inverse recomputed from the product as StaticTransform's ctor does
+        StaticTransform reduced = subTF ? (*subTF * m_localToWorld) : m_localToWorld;
+        for (const NodeRef& c : m_children) c->getRenderingData(b, &reduced, data);
+        return;
+    }
+    // An animated node (nodes.cpp:117-141): its subtree is flattened in its own space into a nested aggregate, which the
+    // parent sees through a TransformedSurfaceObject carrying the animated transform -- an instance that moves. A static
+    // parent transform is folded into both key frames (ChainedTransform::reduce -> createByMulLeft, Transform.cpp:67-69).
+    const std::shared_ptr<const AnimatedTransform> reduced = subTF ? m_localToWorld.anim->mulLeft(*subTF) : m_localToWorld.anim;
+    RenderingData sub;
+    for (const NodeRef& c : m_children) c->getRenderingData(b, nullptr, &sub);
+    if (!sub.objects.empty()) {
+        for (const ObjectRef& o : sub.objects)
+            if (o.isInstance && b.instanceIsAnimated(o.id))
+                throw std::runtime_error("an animated node inside an animated node (a chain of two moving transforms) is not supported");
+        const uint32_t aggregate = b.createAggregate(std::move(sub.objects));
+        StaticTransform tf(reduced->begin.mat, reduced->begin.matInv);
+        tf.anim = reduced;
+        data->objects.push_back(ObjectRef{true, b.addInstance(aggregate, tf)});
+    }
+    if (sub.camera) {
+        // the camera rides on the animated node: animated * (static camera transform) (createByMulRight, Transform.cpp:70-72)
+        if (sub.cameraTransform.anim) throw std::runtime_error("a camera under two animated nodes is not supported");
+        data->camera = sub.camera;
+        const std::shared_ptr<const AnimatedTransform> camAnim = sub.hasCameraTransform ? reduced->mulRight(sub.cameraTransform) : reduced;
+        data->cameraTransform = StaticTransform(camAnim->begin.mat, camAnim->begin.matInv);
+        data->cameraTransform.anim = camAnim;
+        data->hasCameraTransform = true;
+    }
 }
 
 void TriangleMeshNode::addTriangles(const SurfaceMaterialRef& mat, const Normal3DTextureRef& normalMap,
@@ -126,6 +154,21 @@ void CameraNode::getRenderingData(GpuSceneBuilder&, const StaticTransform* subTF
     data->hasCameraTransform = subTF != nullptr;
 }
 
+uint32_t GpuSceneBuilder::addMotion(const AnimatedTransform& a) {
+    SlrGpuMotion m;
+    std::memset(&m, 0, sizeof(m));
+    std::memcpy(m.mat_end, &a.end.mat, 64);
+    std::memcpy(m.mat_end_inv, &a.end.matInv, 64);
+    for (int k = 0; k < 3; ++k) { m.T0[k] = a.T[0][k]; m.T1[k] = a.T[1][k]; }
+    m.t_begin = a.tBegin; m.t_end = a.tEnd;
+    m.R0[0] = a.R[0].x; m.R0[1] = a.R[0].y; m.R0[2] = a.R[0].z; m.R0[3] = a.R[0].w;
+    m.R1[0] = a.R[1].x; m.R1[1] = a.R[1].y; m.R1[2] = a.R[1].z; m.R1[3] = a.R[1].w;
+    std::memcpy(m.S0, &a.S[0], 64);
+    std::memcpy(m.S1, &a.S[1], 64);
+    flat.motions.push_back(m);
+    return (uint32_t)flat.motions.size();
+}
+
 // ---------------------------------------------------------------------------------------------
 // aggregates
 // ---------------------------------------------------------------------------------------------
@@ -151,9 +194,11 @@ uint32_t GpuSceneBuilder::createAggregate(std::vector<ObjectRef>&& objects) {
                 throw std::runtime_error("instancing nested deeper than one level is not supported by the GPU traversal yet");
             Mat4 m;
             std::memcpy(static_cast<void*>(&m), flat.instances[o.id].mat, sizeof(float) * 16);
-            // TransformedSurfaceObject::bounds / costForIntersect (SurfaceObject.cpp:303-305, SurfaceObject.h:206)
+            // TransformedSurfaceObject::bounds / costForIntersect (SurfaceObject.cpp:303-305, SurfaceObject.h:206): the
+            // transform's motionBounds of the nested bounds -- for a static transform that is the transformed box
             float cost = nested.objects.size() == 1 ? 1.0f : nested.sbvh.cost;
-            ps.addBox(transformBounds(m, nested.sbvh.bounds), cost);
+            const std::shared_ptr<const AnimatedTransform>& anim = instanceAnim[o.id];
+            ps.addBox(anim ? anim->motionBounds(nested.sbvh.bounds) : transformBounds(m, nested.sbvh.bounds), cost);
         }
     }
     ag.sbvh.build(ps);
@@ -207,8 +252,10 @@ uint32_t GpuSceneBuilder::addInstance(uint32_t aggregate, const StaticTransform&
     inst.light_base = SLRGPU_INVALID_ID;
     inst.num_lights = 0;
     inst.light_index = SLRGPU_INVALID_ID;
+    inst.motion = tf.anim ? addMotion(*tf.anim) : 0u;
     flat.instances.push_back(inst);
     instanceAggregate.push_back(aggregate);
+    instanceAnim.push_back(tf.anim);
     return (uint32_t)flat.instances.size() - 1;
 }
 
@@ -346,6 +393,8 @@ void FlatScene::describe(SlrGpuSceneDesc* d) const {
     for (int i = 0; i < 3; ++i) d->world_center[i] = worldCenter[i];
     d->world_radius = worldRadius;
     d->camera = camera;
+    if (!motions.empty()) { d->motions = motions.data(); d->num_motions = (uint32_t)motions.size(); }
+    d->camera_motion = cameraMotion;
     if (!sbvhNodes.empty()) {
         d->sbvh_nodes = sbvhNodes.data(); d->num_sbvh_nodes = (uint32_t)sbvhNodes.size();
         d->sbvh_leaf_records = sbvhLeaves.data(); d->num_sbvh_leaf_records = (uint32_t)sbvhLeaves.size();

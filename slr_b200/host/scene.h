@@ -47,7 +47,7 @@ struct ObjectRef {
 struct RenderingData {
     std::vector<ObjectRef> objects;
     std::shared_ptr<PerspectiveCamera> camera;
-    StaticTransform cameraTransform;
+    StaticTransform cameraTransform;       // with .anim set when the camera sits under an animated node
     bool hasCameraTransform = false;
 };
 
@@ -137,6 +137,8 @@ struct FlatScene {
     std::vector<SlrGpuLeafRecord> leaves;
     std::vector<SlrGpuInstance> instances;
     // the binary SBVHs themselves (optional export, exportSbvh: the accelerator the reference's shipped build traverses)
+    std::vector<SlrGpuMotion> motions;     // animated transforms of instances / the camera (motion blur)
+    uint32_t cameraMotion = 0;             // 0 = static, else 1 + index into motions
     std::vector<SlrGpuSbvhNode> sbvhNodes;
     std::vector<SlrGpuLeafRecord> sbvhLeaves;
     std::vector<SlrGpuTriangle> triangles;
@@ -197,12 +199,16 @@ public:
     FlatScene& flat;
     std::vector<Aggregate> aggregates;       // nested ones first as they are discovered; index = aggregate id
     std::vector<uint32_t> instanceAggregate; // instance id -> aggregate id
+    std::vector<std::shared_ptr<const AnimatedTransform>> instanceAnim;     // instance id -> its motion (null: static)
+    bool instanceIsAnimated(uint32_t id) const { return id < instanceAnim.size() && instanceAnim[id] != nullptr; }
     std::vector<uint8_t> triangleEmits;      // prim_id -> is emitting
 
     explicit GpuSceneBuilder(FlatScene& f) : flat(f) {}
     // Builds trees + light list for `objects`; returns the aggregate id.
     uint32_t createAggregate(std::vector<ObjectRef>&& objects);
+    // tf.anim set: the instance moves (its record refers to a new entry of flat.motions)
     uint32_t addInstance(uint32_t aggregate, const StaticTransform& tf);
+    uint32_t addMotion(const AnimatedTransform& a);       // returns 1 + index
     // Concatenates all aggregates (top level = `top` first) into flat.nodes / flat.leaves.
     void finalize(uint32_t top);
     // shading tables (materials.cpp)

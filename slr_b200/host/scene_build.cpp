@@ -25,6 +25,7 @@ void Scene::build(FlatScene* out, bool rgbMode) {
         std::memcpy(g.mat_inv, &data.cameraTransform.matInv, sizeof(float) * 16);
         g.sensitivity = c.sensitivity; g.aspect = c.aspect; g.fov_y = c.fovY;
         g.lens_radius = c.lensRadius; g.img_plane_dist = c.imgPlaneDistance; g.obj_plane_dist = c.objPlaneDistance;
+        if (data.cameraTransform.anim) out->cameraMotion = b.addMotion(*data.cameraTransform.anim);       // the camera moves
         out->hasCamera = true;
     }
     if (m_env) exportEnvironment(b, *m_env);

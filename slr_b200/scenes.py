@@ -624,7 +624,51 @@ def write_textured(directory, width=128, height=128, spp=64):
     return path
 
 
+def write_motion(directory, width=128, height=128, spp=64):
+    """Motion blur (AnimatedTransform, libSLR/Core/Transform.h:89-144): the Cornell box over the shutter interval [0, 1]
+    with a matte ball that flies and turns, an emitting panel that slides (a moving light: the transform is sampled at the
+    ray's time in light sampling too, SurfaceObject.cpp:351-364) and a camera that dollies sideways."""
+    write_sphere_asset(directory, 32, 16)
+    t = f'setRenderer("method": "PT", ("samples": {spp},));\nsetRenderSettings("width": {width}, "height": {height}, "timeStart": 0.0, "timeEnd": 1.0);\n\n'
+    t += cornell_box_shell()
+    t += """function ballMat(name, attrs) {
+    return createSurfaceMaterial("matte", (SpectrumTexture(Spectrum(0.2, 0.6, 0.8)),));
+}
+ball = load3DModel("models/sphere.assbin", ballMat);
+setTransform(ball, scale(0.35));
+flyer = createNode();
+addChild(flyer, ball);
+setTransform(flyer, AnimatedTransform(translate(-0.9, 0.6, -0.6), translate(0.7, 1.3, -0.2) * rotateY(1.6) * scale(1.3), 0.0, 1.0));
+addChild(root, flyer);
+
+slider = createNode();
+"""
+    t += _quad("panel", [(-0.25, 0, -0.25), (0.25, 0, -0.25), (0.25, 0, 0.25), (-0.25, 0, 0.25)], (0, 1, 0), (1, 0, 0),
+               ['scatterMat = createSurfaceMaterial("matte", (SpectrumTexture(Spectrum(0.8, 0.8, 0.8)),));',
+                'emitterMat = createEmitterSurfaceProperty("diffuse", (SpectrumTexture(Spectrum("ID": "D65") * 3),));',
+                'surfMat = createSurfaceMaterial("emitter", (scatterMat, emitterMat));']).replace("CBNode", "slider")
+    t += _quad("panelBack", [(-0.3, -0.02, 0.3), (0.3, -0.02, 0.3), (0.3, -0.02, -0.3), (-0.3, -0.02, -0.3)], (0, -1, 0), (1, 0, 0),
+               _matte(0.4, 0.4, 0.4)).replace("CBNode", "slider")
+    t += """setTransform(slider, AnimatedTransform(translate(0.9, 0.3, 0.9), translate(-0.2, 0.5, 1.2) * rotateZ(0.5), 0.0, 1.0));
+addChild(root, slider);
+
+dolly = createNode();
+cameraNode = createNode();
+camera = createPerspectiveCamera("aspect": 4.0 / 3.0, "fovY": 0.4807705238, "radius": 0.025, "imgDist": 1.0, "objDist": 6.3);
+addChild(cameraNode, camera);
+setTransform(cameraNode, translate(0.0, 1.689714, 6.70284) * rotateY(3.1415926536) * rotateX(0.0563936));
+addChild(dolly, cameraNode);
+setTransform(dolly, AnimatedTransform(translate(-0.15, 0, 0), translate(0.15, 0.05, 0), 0.0, 1.0));
+addChild(root, dolly);
+"""
+    path = os.path.join(directory, "Motion.txt")
+    with open(path, "w") as f:
+        f.write(t)
+    return path
+
+
 SCENES = {
+    "motion": write_motion,
     "textured": write_textured,
     "cutout": write_cutout,
     "diffuse": write_cornell_diffuse,

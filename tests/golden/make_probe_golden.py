@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import render_util as ru  # noqa: E402
 from slr_b200 import capi  # noqa: E402
 
-SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced", "cutout", "textured"]
+SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced", "cutout", "textured", "motion"]
 N, SEED = 2048, 20261018
 
 

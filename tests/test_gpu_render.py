@@ -43,7 +43,7 @@ def _gpu_rgb(path, size, spp, **kw):
 
 
 @pytest.mark.parametrize("name,size,spp", [("diffuse", 96, 256), ("spheres", 128, 256), ("materials", 128, 256), ("ibl", 128, 256),
-                                           ("instanced", 128, 128), ("cutout", 128, 256), ("textured", 128, 256)])
+                                           ("instanced", 128, 128), ("cutout", 128, 256), ("textured", 128, 256), ("motion", 128, 256)])
 def test_image_matches_reference_within_noise_floor(name, size, spp, workdir):
     if not ru.have_ref_render():
         pytest.skip("oracle/_ref/ref_render not built")
@@ -97,7 +97,7 @@ def test_unchanged_reference_scene_file_renders_like_the_reference(name, size, s
     assert bgot <= 1.5 * bfloor + 0.002, f"16x16-block relRMSE {bgot:.4f} vs floor {bfloor:.4f}"
 
 
-@pytest.mark.parametrize("name", ["diffuse", "spheres", "materials", "ibl", "instanced", "scatter", "lamps", "cutout", "textured"])
+@pytest.mark.parametrize("name", ["diffuse", "spheres", "materials", "ibl", "instanced", "scatter", "lamps", "cutout", "textured", "motion"])
 def test_image_matches_golden_block_means(name, workdir):
     f = os.path.join(ru.GOLDEN, f"render_{name}.npz")
     g = np.load(f)
@@ -235,3 +235,19 @@ def test_render_argument_errors(workdir):
         capi.gpu_render(gs, 0, 32, 0, 1)
     with pytest.raises(capi.SlrError):
         capi.gpu_render(gs, 32, 32, 4, 4)
+
+
+def test_motion_blur_is_really_sampled_over_the_shutter(workdir):
+    """The `motion` scene with the shutter closed at time 0 (timeEnd = timeStart) is a different image than with the
+    shutter open over [0, 1] -- the ball is sharp at its start position instead of a streak -- and both are deterministic.
+    (Parity of the open-shutter image with the reference is in the live / golden tests above.)"""
+    path = ru.scene_file("motion", workdir, 96, 96, 64)
+    hs = capi.read_scene(path)
+    gs = capi.GpuScene(hs)
+    open_, st = capi.gpu_render(gs, 96, 96, 0, 64, time_start=0.0, time_end=1.0)
+    again, _ = capi.gpu_render(gs, 96, 96, 0, 64, time_start=0.0, time_end=1.0)
+    closed, _ = capi.gpu_render(gs, 96, 96, 0, 64, time_start=0.0, time_end=0.0)
+    np.testing.assert_allclose(open_, again, rtol=2e-4, atol=1e-5 * float(open_.mean()))
+    a, b = capi.accum_to_rgb(open_, 1 / 64), capi.accum_to_rgb(closed, 1 / 64)
+    assert ru.block_rel_rmse(a, b, 8) > 0.05
+    assert np.isfinite(open_).all() and st["paths"] == 96 * 96 * 64

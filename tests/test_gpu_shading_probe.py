@@ -23,7 +23,7 @@ import render_util as ru
 from slr_b200 import capi
 
 pytestmark = pytest.mark.gpu
-SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced", "cutout", "textured"]
+SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced", "cutout", "textured", "motion"]
 
 
 @pytest.fixture(scope="module", autouse=True)

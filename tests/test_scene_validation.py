@@ -52,7 +52,7 @@ def patched(desc, field, count_field, elem_type, mutate):
     return c, arr
 
 
-@pytest.mark.parametrize("name", ["diffuse", "spheres", "materials", "ibl", "instanced", "scatter", "lamps", "cutout", "textured"])
+@pytest.mark.parametrize("name", ["diffuse", "spheres", "materials", "ibl", "instanced", "scatter", "lamps", "cutout", "textured", "motion"])
 def test_every_test_scene_passes_validation(name, tmp_path):
     path = ru.scene_file(name, str(tmp_path), 32, 32, 1)
     with capi.stdout_to_stderr():
