@@ -25,6 +25,9 @@
 namespace slrgpu {
 
 constexpr int kTailBlock = 256;
+#ifndef SLR_TAIL_PREFETCH
+#define SLR_TAIL_PREFETCH 1
+#endif
 #ifndef SLR_TAIL_PATHS_PER_THREAD
 #define SLR_TAIL_PATHS_PER_THREAD 1u
 #endif
@@ -43,7 +46,7 @@ __device__ __noinline__ void tailWalkT(const DeviceScene& s, WalkState& w, uint3
     TraversalCounters cnt = {0, 0};
     bool ovf = false;
     walkBegin(w, stack);
-    while (!walkStep<INSTANCES, ANY_HIT, false, ALPHA>(s, w, iw, stack, cnt, ovf)) { }
+    while (!walkStep<INSTANCES, ANY_HIT, false, ALPHA, SLR_TAIL_PREFETCH != 0>(s, w, iw, stack, cnt, ovf)) { }
     if (ovf) *overflow = true;
 }
 template <bool ANY_HIT>

@@ -175,6 +175,9 @@ constexpr uint32_t kMaxChunk = 256;
 // of every queued leaf child at push time: C5 (10 M triangles, scene larger than L2) 2581 -> 1797 Mrays/s, C4 299 -> 288
 // Mpaths/s. The walk already keeps the memory system busy; the extra requests for nodes that are never popped cost more
 // than the latency they hide. profiles/r02_rejected_experiments.md)
+#ifndef SLR_WALK_DEFER_SINK
+#define SLR_WALK_DEFER_SINK 1
+#endif
 constexpr int kStepsPerRound = SLR_WALK_STEPS_PER_ROUND;     // node visits between two refill checks (sweep: profiles/r01_variant_sweep.md)
 constexpr int kRefillIdle = SLR_WALK_REFILL_IDLE;            // idle lanes that trigger a refill
 
@@ -250,7 +253,13 @@ __device__ __forceinline__ void walkSetRay(WalkState& w) {
 
 // The node half of a step: pops one entry -- a node: 4-box test, push the inner children that were hit (far to near),
 // queue the leaf children that were hit (near to far) in `leaves`; or the return marker of an instance.
-template <bool INSTANCES, bool COUNT>
+// PREFETCH (the persistent tail kernel only): every inner child a node visit pushes and every leaf child it queues is
+// prefetched into L1 at once. The tail runs a handful of paths per SM, each a chain of dependent node fetches at L2
+// latency: a pushed child is popped only after its nearer siblings' subtrees, so its fetch overlaps that work. (In the
+// throughput kernels the same hint costs more than it hides -- measured, see the note above walkQueue.)
+__device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+template <bool INSTANCES, bool COUNT, bool PREFETCH = false>
 __device__ __forceinline__ void walkNode(const DeviceScene& s, WalkState& w, InstanceWalkState& iw, LeafQueue& leaves, uint32_t* stack,
                                          TraversalCounters& cnt, bool& overflow) {
     Ray& r = w.r;
@@ -300,6 +309,7 @@ __device__ __forceinline__ void walkNode(const DeviceScene& s, WalkState& w, Ins
                 if (w.sp >= kStackSize) { overflow = true; continue; }
                 stack[w.sp++] = c & 0x07FFFFFFu;
                 w.top = c & 0x07FFFFFFu;
+                if (PREFETCH) prefetchL1(s.nodes + (size_t)(c & 0x07FFFFFFu) * 8);
             }
             // leaf children in visiting order: the first becomes the current range, up to three wait
             uint32_t q0 = kEmptyChild, q1 = kEmptyChild, q2 = kEmptyChild, q3 = kEmptyChild;
@@ -307,6 +317,7 @@ __device__ __forceinline__ void walkNode(const DeviceScene& s, WalkState& w, Ins
             for (int i = 0; i < 4; ++i) {
                 const uint32_t c = ch[i];
                 if (c != kEmptyChild && (c >> 31)) {
+                    if (PREFETCH) prefetchL1(s.leaves + (size_t)(c & 0x07FFFFFFu) * 3);
                     if (q0 == kEmptyChild) q0 = c;
                     else if (q1 == kEmptyChild) q1 = c;
                     else if (q2 == kEmptyChild) q2 = c;
@@ -335,19 +346,19 @@ __device__ __forceinline__ void walkNode(const DeviceScene& s, WalkState& w, Ins
 #ifndef SLR_WALK_ONE_RECORD_PER_STEP
 #define SLR_WALK_ONE_RECORD_PER_STEP 0
 #endif
-template <bool INSTANCES, bool ANY_HIT, bool COUNT, bool ALPHA = false>
+template <bool INSTANCES, bool ANY_HIT, bool COUNT, bool ALPHA = false, bool PREFETCH = false>
 __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, InstanceWalkState& iw, uint32_t* stack,
                                          TraversalCounters& cnt, bool& overflow) {
     Ray& r = w.r;
 #if SLR_WALK_ONE_RECORD_PER_STEP
     LeafQueue& leaves = iw.leaves;
-    if (leaves.count == 0) walkNode<INSTANCES, COUNT>(s, w, iw, leaves, stack, cnt, overflow);
+    if (leaves.count == 0) walkNode<INSTANCES, COUNT, PREFETCH>(s, w, iw, leaves, stack, cnt, overflow);
     if (leaves.count != 0) {
 #else
     LeafQueue local;                     // flat scenes: the queue lives for one step only
     LeafQueue& leaves = INSTANCES ? iw.leaves : local;
     if (!INSTANCES) local.clear();
-    walkNode<INSTANCES, COUNT>(s, w, iw, leaves, stack, cnt, overflow);
+    walkNode<INSTANCES, COUNT, PREFETCH>(s, w, iw, leaves, stack, cnt, overflow);
     while (leaves.count != 0) {
 #endif
         const float4* rec = s.leaves + (size_t)leaves.first * 3;
@@ -426,9 +437,17 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
     const uint32_t totalWarps = (gridDim.x * blockDim.x) >> 5;
     uint32_t chunk = 32;
     while (chunk < kMaxChunk && (unsigned long long)chunk * 2ull * totalWarps <= (unsigned long long)n / 2ull) chunk <<= 1;
+    // SLR_WALK_DEFER_SINK: a lane that finishes its ray keeps the result in its registers and hands it to the sink when the
+    // warp next services its idle lanes (the refill point), so the sink's code -- the hit record stores of `extend`, the
+    // contribution loads + four 16-byte reductions of `shadow` -- runs once for all lanes that finished since, instead of
+    // once per finishing lane at 1-3 active lanes (shadow: 14 % of the kernel's stall samples sat on the splat).
+    bool finished = false;
     while (true) {
         const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
         const int numIdle = __popc(idle);
+#if SLR_WALK_DEFER_SINK
+        if ((numIdle >= kRefillIdle || exhausted) && finished) { sink.done(idx, w, cnt); finished = false; }
+#endif
         // refill when a quarter of the warp is idle (or nothing is running)
         if (!exhausted && (numIdle >= kRefillIdle)) {
             if (chunkNext >= chunkEnd) {
@@ -463,7 +482,11 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
         for (int it = 0; it < kStepsPerRound; ++it) {
             if (active) {
                 if (walkStep<INSTANCES, ANY_HIT, COUNT, ALPHA>(s, w, iw, stack, cnt, overflow)) {
+#if SLR_WALK_DEFER_SINK
+                    finished = true;
+#else
                     sink.done(idx, w, cnt);
+#endif
                     active = false;
                 }
             }
