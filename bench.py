@@ -321,6 +321,18 @@ def main():
     value = r["units"] * world / (ms * 1e-3) / 1e6
     ach = r["algo_bytes_per_launch"] / (ms * 1e-3 / r["launches"]) / 1e9
     cpu = cpu_baseline_intersect(args, args.cpu_sample, gpu_scene=r["gpu_scene"])
+    # measured DRAM bytes per ray and the issue / lane figures of the committed ncu capture of this mesh size, if there is one
+    traffic, km = None, None
+    try:
+        key = f"intersect_grid{args.grid}"
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(key, {}).get("intersectBatchKernel")
+        if t is not None:
+            traffic = t["dram_bytes_per_ray"] * args.rays
+        with open(os.path.join(ROOT, "profiles", "kernel_metrics.json")) as f:
+            km = json.load(f).get(key, {}).get("intersectBatchKernel")
+    except (OSError, ValueError, KeyError):
+        pass
     line = {"metric": "Mrays/s (closest-hit, incoherent rays)", "value": value, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -329,9 +341,16 @@ def main():
                        "nodes_per_ray": round(r["nodes_per_ray"], 3), "tris_per_ray": round(r["tris_per_ray"], 3),
                        "l2_policy": "inputs larger than L2 (ray SoA + results >= 44 B/ray x rays)",
                        "scene_bytes": int(r["scene_bytes"]), "host_bvh_build_s": round(r["build_s"], 2)},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                          "kernel": "intersectBatchKernel", "peak_source": peak_src,
-                         "algorithmic_bytes_per_ray": r["algo_bytes_per_launch"] / args.rays},
+                         "algorithmic_bytes_per_ray": r["algo_bytes_per_launch"] / args.rays,
+                         "lanes_active_of_32": km["lanes_active"] if km else None,
+                         "issue_slot_utilisation_pct": km["issue_slot_utilisation_pct"] if km else None,
+                         "note": "achieved = algorithmic bytes (32 B ray + 128 B per node popped + 48 B per leaf record tested + 16 B hit) of one "
+                                 "launch / its device time; traffic = ncu dram__bytes of one launch of this mesh size (profiles/traffic.json), "
+                                 "bytes per launch -- below the algorithmic figure because the upper tree levels are served by L2. The kernel is "
+                                 "bound by the LATENCY of its dependent node fetches (ncu: long-scoreboard stalls dominate, DRAM throughput "
+                                 "14 %), see profiles/r02_ncu_c4_c5.md"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e * world / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
             "gpu_launches": args.steps, "clocks": r["clocks"]}

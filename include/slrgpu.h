@@ -95,7 +95,12 @@ typedef struct SlrGpuSbvhNode {
 } SlrGpuSbvhNode;
 
 /* One TransformedSurfaceObject (SurfaceObject.cpp:303-392) over a nested aggregate.
- * Matrices are column-major (element (r,c) at [4*c + r]) like Matrix4x4 (Matrix4x4.h:23-38). */
+ * Matrices are column-major (element (r,c) at [4*c + r]) like Matrix4x4 (Matrix4x4.h:23-38).
+ * LIMIT: one level of instancing. An instance record may only appear in the top-level BVH; a nested aggregate's leaf
+ * records must all be triangles (the reference recurses to any depth, SurfaceObject.cpp:307-336). The host library and
+ * the reference-side exporter reject deeper nesting when they flatten a scene, and slrgpu_scene_create walks every nested
+ * BVH and returns SLRGPU_ERR_UNSUPPORTED for an instance record inside one. Hit records, surface points and light
+ * sampling all assume the limit (one instance id per hit). */
 typedef struct SlrGpuInstance {
     float mat[16];          /* local -> parent */
     float mat_inv[16];      /* parent -> local, as computed by the host's invert() */

@@ -358,6 +358,35 @@ struct Validator {
                 return fail(SLRGPU_ERR_INVALID_ARGUMENT, "instance %u: light list out of range", i);
             if (in.light_index != SLRGPU_INVALID_ID && in.light_index >= d->num_lights) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "instance %u: light index out of range", i);
         }
+        // one level of instancing (slrgpu.h, SlrGpuInstance): no instance record inside a nested BVH
+        {
+            std::vector<uint32_t> roots;
+            for (uint32_t i = 0; i < d->num_instances; ++i) roots.push_back(d->instances[i].root_node);
+            std::sort(roots.begin(), roots.end());
+            roots.erase(std::unique(roots.begin(), roots.end()), roots.end());
+            std::vector<uint32_t> stack;
+            for (uint32_t root : roots) {
+                stack.assign(1, root);
+                uint64_t visited = 0;
+                while (!stack.empty()) {
+                    const SlrGpuBvhNode& n = d->bvh_nodes[stack.back()];
+                    stack.pop_back();
+                    if (++visited > d->num_bvh_nodes) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "the BVH under node %u is not a tree", root);
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t c = n.child[k];
+                        if (c == 0xFFFFFFFFu) continue;
+                        const uint32_t idx = c & 0x07FFFFFFu, cnt = (c >> 27) & 0xFu;
+                        if (!(c >> 31)) { stack.push_back(idx); continue; }
+                        for (uint32_t j = 0; j < cnt; ++j) {
+                            uint32_t id;
+                            memcpy(&id, &d->leaf_records[idx + j].a[3], 4);
+                            if (id & 0x80000000u)
+                                return fail(SLRGPU_ERR_UNSUPPORTED, "instancing nested deeper than one level (instance %u inside the BVH of another instance)", id & 0x7FFFFFFFu);
+                        }
+                    }
+                }
+            }
+        }
         if (d->num_top_lights > d->num_lights) return fail(SLRGPU_ERR_INVALID_ARGUMENT, "num_top_lights exceeds num_lights");
         if (d->environment.present) {
             const SlrGpuEnvironment& e = d->environment;
