@@ -115,9 +115,7 @@ static __device__ __noinline__ void surfaceEmission(const DeviceScene& s, const 
 // ---------------------------------------------------------------------------------------------
 // One path-queue entry: *cls = the material class of the surviving hit (SC_NONE: the path ended here), *leaf = its
 // leaf material.
-// The three streaming loads of an entry (hit record, meta, roulette slot), separated from the work on them so that the
-// wave kernel can have the loads of two entries in flight per thread: the stage is latency bound (13 % issue utilisation
-// at 37 % occupancy in the round-1 capture), not bandwidth bound.
+// The three streaming loads of an entry (hit record, meta, roulette slot), issued together before any of them is used.
 struct SurfaceInput { uint32_t info; uint4 meta; float aux; };
 __device__ __forceinline__ SurfaceInput surfaceLoad(const PathQueue& in, const HitBuffer& hits, uint32_t i) {
     SurfaceInput x;
@@ -190,27 +188,20 @@ __device__ __forceinline__ void classAppend(const ClassQueue& cq, WavefrontCount
     }
 }
 
-// Work items [0, n) are spread over the whole grid, one warp per 32 consecutive entries, two such groups per iteration
-// with their loads issued together.
+// Work items [0, n) are spread over the whole grid, one warp per 32 consecutive entries.
+// (Two groups per iteration with both groups' loads issued up front were measured in round 2 and dropped: surface
+// 2.54 -> 2.85 ms per C1 frame -- the extra registers cost more than the second set of loads in flight buys,
+// profiles/r02_rejected_experiments.md.)
 template <int NC>
 __device__ __forceinline__ void surfaceStage(const DeviceScene& s, const RenderConstants& rc, const PathQueue& in, const HitBuffer& hits,
                                              const ClassQueue& cq, float* __restrict__ accum, WavefrontCounters* counters, uint32_t n) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += 2 * stride) {
-        const uint32_t i0 = base + lane, i1 = base + stride + lane;
-        const bool has0 = i0 < n, has1 = i1 < n;
-        SurfaceInput x0 = {}, x1 = {};
-        if (has0) x0 = surfaceLoad(in, hits, i0);
-        if (has1) x1 = surfaceLoad(in, hits, i1);
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const uint32_t i = base + lane;
         uint32_t cls = SC_NONE, leaf = SLRGPU_INVALID_ID;
-        if (has0) surfaceItem<NC>(s, rc, in, hits, accum, i0, x0, &cls, &leaf);
-        classAppend(cq, counters, lane, i0, cls, leaf);
-        if (base + stride < n) {           // warp-uniform
-            cls = SC_NONE; leaf = SLRGPU_INVALID_ID;
-            if (has1) surfaceItem<NC>(s, rc, in, hits, accum, i1, x1, &cls, &leaf);
-            classAppend(cq, counters, lane, i1, cls, leaf);
-        }
+        if (i < n) surfaceItem<NC>(s, rc, in, hits, accum, i, &cls, &leaf);
+        classAppend(cq, counters, lane, i, cls, leaf);
     }
 }
 

@@ -25,8 +25,10 @@
 namespace slrgpu {
 
 constexpr int kTailBlock = 256;
+// L1 prefetch of pushed children in the tail's walk (traverse.cuh walkNode PREFETCH): measured in round 2 and left off --
+// tail kernel 2.95 -> 3.23 ms per C1 frame (profiles/r02_rejected_experiments.md)
 #ifndef SLR_TAIL_PREFETCH
-#define SLR_TAIL_PREFETCH 1
+#define SLR_TAIL_PREFETCH 0
 #endif
 #ifndef SLR_TAIL_PATHS_PER_THREAD
 #define SLR_TAIL_PATHS_PER_THREAD 1u

@@ -175,6 +175,9 @@ constexpr uint32_t kMaxChunk = 256;
 // of every queued leaf child at push time: C5 (10 M triangles, scene larger than L2) 2581 -> 1797 Mrays/s, C4 299 -> 288
 // Mpaths/s. The walk already keeps the memory system busy; the extra requests for nodes that are never popped cost more
 // than the latency they hide. profiles/r02_rejected_experiments.md)
+// 0 = never, 1 = always, 2 = only in the instanced instantiations. Measured (profiles/r02_variant_sweep.md): the batch
+// kernels gain 6 % (C5 2557 -> 2708 Mrays/s), the instanced renderer kernels 1-4 % (C4 extend 59.3 -> 58.8, shadow 23.5 ->
+// 22.6 ms), the flat renderer kernels lose 3 % on extend (C1 9.43 -> 9.77 ms): intersect.cu sets 1, trace.cu 2.
 #ifndef SLR_WALK_DEFER_SINK
 #define SLR_WALK_DEFER_SINK 1
 #endif
@@ -440,14 +443,13 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
     // SLR_WALK_DEFER_SINK: a lane that finishes its ray keeps the result in its registers and hands it to the sink when the
     // warp next services its idle lanes (the refill point), so the sink's code -- the hit record stores of `extend`, the
     // contribution loads + four 16-byte reductions of `shadow` -- runs once for all lanes that finished since, instead of
-    // once per finishing lane at 1-3 active lanes (shadow: 14 % of the kernel's stall samples sat on the splat).
+    // once per finishing lane at 1-3 active lanes.
     bool finished = false;
     while (true) {
         const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
         const int numIdle = __popc(idle);
-#if SLR_WALK_DEFER_SINK
-        if ((numIdle >= kRefillIdle || exhausted) && finished) { sink.done(idx, w, cnt); finished = false; }
-#endif
+        constexpr bool kDefer = SLR_WALK_DEFER_SINK == 1 || (SLR_WALK_DEFER_SINK == 2 && INSTANCES);
+        if (kDefer && (numIdle >= kRefillIdle || exhausted) && finished) { sink.done(idx, w, cnt); finished = false; }
         // refill when a quarter of the warp is idle (or nothing is running)
         if (!exhausted && (numIdle >= kRefillIdle)) {
             if (chunkNext >= chunkEnd) {
@@ -482,11 +484,8 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
         for (int it = 0; it < kStepsPerRound; ++it) {
             if (active) {
                 if (walkStep<INSTANCES, ANY_HIT, COUNT, ALPHA>(s, w, iw, stack, cnt, overflow)) {
-#if SLR_WALK_DEFER_SINK
-                    finished = true;
-#else
-                    sink.done(idx, w, cnt);
-#endif
+                    if (kDefer) finished = true;
+                    else sink.done(idx, w, cnt);
                     active = false;
                 }
             }
