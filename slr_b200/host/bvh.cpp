@@ -27,7 +27,40 @@ void PrimitiveSet::addBox(const BBox& b, float cost) {
 
 namespace {
 
-inline Vec3 lerpPoint(const Vec3& a, const Vec3& b, float t) { return (1 - t) * a + t * b; }
+// ---- clipping a primitive's bounds against axis-aligned planes (what the spatial splits of the SBVH need) ----------------
+// The reference does this in Triangle::choppedBounds / splitBounds (libSLR/Surface/TriangleMesh.cpp:19-125) and, for
+// opaque boxes, SurfaceObject.h:58-86. Trees must come out bit-identical, which pins the ARITHMETIC of a cut point -- the
+// edge is taken from its lower to its upper end along the axis, t = (c - a) / (b - a), point = (1 - t) a + t b -- and the
+// boundary conventions (an end point exactly on the plane counts as above it). The organisation here is this file's own:
+// the triangle's corners ordered along the axis, a table of its three edges, one `pierce` primitive, and the bounds
+// assembled as "corners inside the region + points where edges pierce its planes" (min / max are order independent).
+
+struct OrderedCorners {
+    Vec3 v[3];            // the triangle's corners, ascending along `axis` (std::sort on the same keys as the reference: ties alike)
+    OrderedCorners(const PrimitiveSet::Prim& pr, Axis axis) {
+        v[0] = pr.p[0]; v[1] = pr.p[1]; v[2] = pr.p[2];
+        std::sort(v, v + 3, [axis](const Vec3& a, const Vec3& b) { return a[axis] < b[axis]; });
+    }
+};
+constexpr int kEdge[3][2] = {{0, 1}, {0, 2}, {1, 2}};     // (lower end, upper end) in the ordered corners
+
+// Where the edge a -> b (a not above b along the axis) pierces the plane `axis = c`: only if a lies strictly below the plane
+// and b on or above it. (c - a > 0 and c - b <= 0 in the reference's form; the same predicate for IEEE floats.)
+inline bool pierce(const Vec3& a, const Vec3& b, Axis axis, float c, Vec3* at) {
+    const float toPlane = c - a[axis], pastPlane = c - b[axis];
+    if (!(toPlane > 0 && pastPlane <= 0)) return false;
+    const float t = toPlane / (b[axis] - a[axis]);
+    *at = (1 - t) * a + t * b;
+    return true;
+}
+
+// an opaque box (an instance's bounds) restricted to [lo, hi] along the axis; empty when it misses the region
+inline BBox restrictBox(const BBox& base, Axis axis, float lo, float hi) {
+    BBox r = base;
+    r.lo[axis] = std::max(lo, r.lo[axis]);
+    r.hi[axis] = std::min(hi, r.hi[axis]);
+    return r;
+}
 
 // Bounds of the part of a primitive that lies in the slab [lo, hi) along `axis`.
 BBox choppedBounds(const PrimitiveSet::Prim& pr, Axis axis, float lo, float hi) {
@@ -35,37 +68,24 @@ BBox choppedBounds(const PrimitiveSet::Prim& pr, Axis axis, float lo, float hi) 
         const BBox& base = pr.bounds;
         if (hi < base.lo[axis] || lo > base.hi[axis]) return BBox();
         if (lo < base.lo[axis] && hi > base.hi[axis]) return base;
-        BBox r = base;
-        r.lo[axis] = std::max(lo, r.lo[axis]);
-        r.hi[axis] = std::min(hi, r.hi[axis]);
-        return r;
+        return restrictBox(base, axis, lo, hi);
     }
-    const float planes[2] = {lo, hi};
-    Vec3 p[3] = {pr.p[0], pr.p[1], pr.p[2]};
-    std::sort(p, p + 3, [axis](const Vec3& a, const Vec3& b) { return a[axis] < b[axis]; });
-    const float pmin = p[0][axis], pmax = p[2][axis];
-    if (pmin >= hi || pmax <= lo) return BBox();
-    if (pmin >= lo && pmax <= hi) return pr.bounds;
+    const OrderedCorners tri(pr, axis);
+    const float lowest = tri.v[0][axis], middle = tri.v[1][axis], highest = tri.v[2][axis];
+    if (lowest >= hi || highest <= lo) return BBox();             // misses the slab
+    if (lowest >= lo && highest <= hi) return pr.bounds;          // lies inside it
 
-    uint32_t n = 0;
-    Vec3 cuts[4];
-    for (int from = 0; from < 2; ++from) {
-        const Vec3& a = p[from];
-        for (int to = from + 1; to < 3; ++to) {
-            const Vec3& b = p[to];
-            float dAB = b[axis] - a[axis];
-            for (int k = 0; k < 2; ++k) {
-                float dAP = planes[k] - a[axis];
-                float dPB = planes[k] - b[axis];
-                float t = dAP / dAB;
-                if (dAP > 0 && dPB <= 0) cuts[n++] = lerpPoint(a, b, t);
-            }
-        }
-    }
     BBox r;
-    if (p[1][axis] >= lo && p[1][axis] < hi) r.grow(p[1]);
-    for (uint32_t i = 0; i < n; ++i) r.grow(cuts[i]);
-    if (n == 2) r.grow(pmax < hi ? p[2] : p[0]);
+    int pierced = 0;
+    for (const auto& e : kEdge)
+        for (const float plane : {lo, hi}) {
+            Vec3 at;
+            if (pierce(tri.v[e[0]], tri.v[e[1]], axis, plane, &at)) { r.grow(at); ++pierced; }
+        }
+    // corners inside the slab: the middle one by its own coordinate; when only ONE of the two planes cuts the triangle
+    // (two edges pierced), the extreme corner on the side of the other plane is inside as well
+    if (middle >= lo && middle < hi) r.grow(tri.v[1]);
+    if (pierced == 2) r.grow(highest < hi ? tri.v[2] : tri.v[0]);
     return r;
 }
 
@@ -75,33 +95,23 @@ void splitBounds(const PrimitiveSet::Prim& pr, Axis axis, float pos, BBox* left,
         const BBox& base = pr.bounds;
         if (pos < base.lo[axis]) { *left = BBox(); *right = base; return; }
         if (pos > base.hi[axis]) { *left = base; *right = BBox(); return; }
-        *left = base;  left->hi[axis] = std::min(left->hi[axis], pos);
-        *right = base; right->lo[axis] = std::max(right->lo[axis], pos);
+        *left = restrictBox(base, axis, -INFINITY, pos);
+        *right = restrictBox(base, axis, pos, INFINITY);
         return;
     }
-    Vec3 p[3] = {pr.p[0], pr.p[1], pr.p[2]};
-    std::sort(p, p + 3, [axis](const Vec3& a, const Vec3& b) { return a[axis] < b[axis]; });
-    const float pmin = p[0][axis], pmax = p[2][axis];
-    if (pos <= pmin) { *left = BBox(); *right = pr.bounds; return; }
-    if (pos >= pmax) { *left = pr.bounds; *right = BBox(); return; }
-
-    uint32_t n = 0;
-    Vec3 cuts[2];
-    for (int from = 0; from < 2; ++from) {
-        const Vec3& a = p[from];
-        for (int to = from + 1; to < 3; ++to) {
-            const Vec3& b = p[to];
-            float dAB = b[axis] - a[axis];
-            float dAP = pos - a[axis];
-            float dPB = pos - b[axis];
-            float t = dAP / dAB;
-            if (dAP > 0 && dPB <= 0 && n < 2) cuts[n++] = lerpPoint(a, b, t);
-        }
+    const OrderedCorners tri(pr, axis);
+    if (pos <= tri.v[0][axis]) { *left = BBox(); *right = pr.bounds; return; }
+    if (pos >= tri.v[2][axis]) { *left = pr.bounds; *right = BBox(); return; }
+    // the plane passes strictly between the lowest and the highest corner: those two seed the halves, the middle corner
+    // joins the side it lies on, and the (two) points where edges pierce the plane belong to both
+    *left = BBox(tri.v[0]);
+    *right = BBox(tri.v[2]);
+    (tri.v[1][axis] < pos ? left : right)->grow(tri.v[1]);
+    int pierced = 0;
+    for (const auto& e : kEdge) {
+        Vec3 at;
+        if (pierced < 2 && pierce(tri.v[e[0]], tri.v[e[1]], axis, pos, &at)) { left->grow(at); right->grow(at); ++pierced; }
     }
-    *left = BBox(p[0]);
-    *right = BBox(p[2]);
-    if (p[1][axis] < pos) left->grow(p[1]); else right->grow(p[1]);
-    for (uint32_t i = 0; i < n; ++i) { left->grow(cuts[i]); right->grow(cuts[i]); }
 }
 
 struct Fragment {
