@@ -30,6 +30,9 @@ constexpr int kTailBlock = 256;
 #ifndef SLR_TAIL_PREFETCH
 #define SLR_TAIL_PREFETCH 0
 #endif
+#ifndef SLR_TAIL_SPREAD
+#define SLR_TAIL_SPREAD 1
+#endif
 #ifndef SLR_TAIL_PATHS_PER_THREAD
 #define SLR_TAIL_PATHS_PER_THREAD 1u
 #endif
@@ -95,18 +98,27 @@ tailKernel(const DeviceScene s, const RenderConstants rc, PathQueue q0, PathQueu
     uint32_t slot = 0, cur = 0;
     bool alive = false;
     bool exhausted = false;         // warp-uniform: the queue has no entries left to hand out
+    // the warp's fair share of the handed-over paths (SLR_TAIL_SPREAD): with one cursor and 32 entries per grab the first
+    // n / 32 warps would each run 32 paths in lockstep -- every round as long as its slowest lane's walk, the material
+    // classes of all its lanes one after the other -- while the other warps of the grid idle; a round of a warp that holds
+    // a third as many paths is that much shorter, and the kernel's time is the sum of one warp's rounds
+    const uint32_t numWarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t quota = SLR_TAIL_SPREAD ? max(1u, (n + numWarps - 1u) / numWarps) : 32u;
+    uint32_t taken = 0;             // warp-uniform: entries this warp has taken so far
 
     while (true) {
         // lanes without a path take the next entries of the queue (one atomic per warp and round)
         const unsigned idle = __ballot_sync(0xFFFFFFFFu, !alive);
-        if (idle != 0 && !exhausted) {
-            const uint32_t want = (uint32_t)__popc(idle);
+        if (idle != 0 && !exhausted && taken < quota) {
+            const uint32_t want = min((uint32_t)__popc(idle), quota - taken);
+            taken += want;
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(&counters->tailCursor, want);
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
             if (!alive) {
-                const uint32_t i = base + (uint32_t)__popc(idle & lt);
-                if (i < n) { slot = i; cur = 0; alive = true; }
+                const uint32_t rank = (uint32_t)__popc(idle & lt);
+                const uint32_t i = base + rank;
+                if (rank < want && i < n) { slot = i; cur = 0; alive = true; }
             }
             if (base + want >= n) exhausted = true;
         }
