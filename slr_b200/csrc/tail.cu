@@ -30,8 +30,11 @@ constexpr int kTailBlock = 256;
 #ifndef SLR_TAIL_PREFETCH
 #define SLR_TAIL_PREFETCH 0
 #endif
+// the handed-over paths dealt out as equal shares per warp instead of 32 at a time: measured in round 2 and left off -- C1
+// 622.0 vs 620.0 Mpaths/s (nothing), C2 728 vs 744 (worse: its warps then hold paths of more material classes each) --
+// profiles/r02_rejected_experiments.md
 #ifndef SLR_TAIL_SPREAD
-#define SLR_TAIL_SPREAD 1
+#define SLR_TAIL_SPREAD 0
 #endif
 #ifndef SLR_TAIL_PATHS_PER_THREAD
 #define SLR_TAIL_PATHS_PER_THREAD 1u
@@ -103,7 +106,7 @@ tailKernel(const DeviceScene s, const RenderConstants rc, PathQueue q0, PathQueu
     // classes of all its lanes one after the other -- while the other warps of the grid idle; a round of a warp that holds
     // a third as many paths is that much shorter, and the kernel's time is the sum of one warp's rounds
     const uint32_t numWarps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t quota = SLR_TAIL_SPREAD ? max(1u, (n + numWarps - 1u) / numWarps) : 32u;
+    const uint32_t quota = SLR_TAIL_SPREAD ? max(1u, (n + numWarps - 1u) / numWarps) : 0xFFFFFFFFu;    // no share: a warp refills while entries are left
     uint32_t taken = 0;             // warp-uniform: entries this warp has taken so far
 
     while (true) {

@@ -350,8 +350,10 @@ def main(args, rank, world):
     dom_ms_per_step = share * ms / args.steps
     ach = algo[dom] / (dom_ms_per_step * 1e-3) / 1e9
     roof = roofline_line(args.workload, dom, algo[dom], ach, peak, peak_src, share, paths_per_step)
-    cpu = cpu_baseline(path, w, h, spp) if world == 1 else None      # the CPU leg runs at N = 1 only
-    parity = image_parity(capi, path, w, h, my_spp, pinned.numpy()) if (world == 1 and w * h * my_spp <= 40e6) else None
+    # SLR_BENCH_AB=1 (kernel A/B sweeps, tools/r02_call*.sh): skip the CPU legs, only the device numbers are read
+    ab = os.environ.get("SLR_BENCH_AB") == "1"
+    cpu = cpu_baseline(path, w, h, spp) if (world == 1 and not ab) else None      # the CPU leg runs at N = 1 only
+    parity = image_parity(capi, path, w, h, my_spp, pinned.numpy()) if (world == 1 and not ab and w * h * my_spp <= 40e6) else None
     line = {"metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": mode, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
