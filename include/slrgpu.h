@@ -435,6 +435,14 @@ typedef struct SlrGpuRenderStats {
 } SlrGpuRenderStats;
 
 #define SLRGPU_RENDER_PROFILE_STAGES 0x1u
+/* Bidirectional path tracing instead of unidirectional -- replaces BidirectionalPathTracingRenderer::render
+ * (libSLR/Renderers/BidirectionalPathTracingRenderer.cpp:25-414; chosen by setRenderer("method": "BPT", "samples": n),
+ * libSLRSceneGraph/API.cpp): per camera sample one light subpath, one eye subpath, every (s, t) connection with its
+ * visibility ray and power-heuristic MIS weight; light-tracing connections (t = 1) land on the pixel the lens sees them in.
+ * Same accumulation buffer, sample-range and multi-GPU semantics as the path tracer; max_path_length and pool_size are
+ * ignored (the reference's BPT has no length cap; subpaths are cut at 64 vertices here). Stats: paths, rays (subpath +
+ * connection rays), device_ms, class_hits[8] = connections examined, tail_paths = subpaths cut at the vertex limit. */
+#define SLRGPU_RENDER_BPT 0x2u
 
 /* Number of accumulation channels per pixel: 16 (spectral strata) or 3 (RGB). */
 SLRGPU_API uint32_t slrgpu_scene_channels(const SlrGpuScene* scene);
@@ -483,6 +491,15 @@ SLRGPU_API int slrgpu_render_debug(SlrGpuScene* scene, const SlrGpuRenderParams*
 #define SLRGPU_PROBE_IN_FLOATS 14
 #define SLRGPU_PROBE_OUT_FLOATS 64
 SLRGPU_API int slrgpu_probe_shading(SlrGpuScene* scene, const float* probes, uint64_t num_probes, float* out);
+
+/* The same for the queries of the bidirectional path tracer (BidirectionalPathTracingRenderer.cpp:184-196, 302-325): probe i
+ * is a radiance query for even i and an importance query (BSDFQuery::adjoint = true) for odd i; sample() is asked for its
+ * reverse information, evaluatePDF() for the reverse pdf. Same probe input layout.
+ * out: n x 64 floats:
+ *   [0] 0 miss / 1 surface hit / 2 environment   [1] t   [2..17] sampled fs   [18..20] sampled dir_sn   [21] dirPDF
+ *   [22] dirType   [23..38] reverse->fs   [39] reverse->dirPDF (both 0 when nothing was sampled)
+ *   [40] evaluatePDF   [41] its revPDF   [42..57] evaluate (the reference's rev_fs equals it for every model) */
+SLRGPU_API int slrgpu_probe_shading_bpt(SlrGpuScene* scene, const float* probes, uint64_t num_probes, float* out);
 
 /* Render calls keep their wavefront queues (about 440 bytes per path in flight) in a per-device pool
  * for reuse by later calls; this frees the pool. */

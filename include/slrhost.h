@@ -59,6 +59,12 @@ SLRGPU_API int slrhost_render(SlrHostScene* s, int device, int width, int height
  * front end calls before the sensors are summed (one process per GPU). */
 SLRGPU_API int slrhost_render_range(SlrHostScene* s, int device, int width, int height, int spp_begin, int spp, int seed,
                                     const char* bmp_dir, float* accum, double* stats6);
+/* Renderer::render through GPUBidirectionalPathTracingRenderer (the reference's BidirectionalPathTracingRenderer,
+ * setRenderer("method": "BPT"); include/slrgpu.h SLRGPU_RENDER_BPT): arguments and results as slrhost_render_range. */
+SLRGPU_API int slrhost_render_bpt(SlrHostScene* s, int device, int width, int height, int spp_begin, int spp, int seed,
+                                  const char* bmp_dir, float* accum, double* stats6);
+/* The method the scene file's setRenderer named ("PT", "BPT", "debug"; empty when it set none), NUL-terminated. */
+SLRGPU_API int slrhost_scene_renderer_method(const SlrHostScene* s, char* method, uint32_t capacity);
 /* Renderer::render through GPUDebugRenderer (the reference's DebugRenderer, setRenderer("method": "debug")): one camera
  * sample per pixel; out (if non-NULL) receives width*height*SLRGPU_DEBUG_FLOATS floats (include/slrgpu.h
  * slrgpu_render_debug), bmp_dir (if non-NULL) geometric_normal.bmp, shading_normal.bmp and shading_tangent.bmp.

@@ -427,6 +427,7 @@ void GPUPathTracingRenderer::render(const Scene &scene, const RenderSettings &se
     p.time_start = settings.getFloat(RenderSettingItem::TimeStart);
     p.time_end = settings.getFloat(RenderSettingItem::TimeEnd);
     p.rng_seed = settings.getInt(RenderSettingItem::RNGSeed);
+    if (bidirectional) p.flags |= SLRGPU_RENDER_BPT;
     const float brightness = settings.getFloat(RenderSettingItem::Brightness);
     std::vector<float> pass((size_t)W * H * channels);
 

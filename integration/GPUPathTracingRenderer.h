@@ -21,7 +21,14 @@ namespace SLR {
         // device < 0: every visible GPU, the frame's samples partitioned over them (slrgpu_render_multi)
         int device = -1;
         bool exportProgressiveImages = true;      // NNN.bmp after 1, 2, 4, ... samples (PathTracingRenderer.cpp:63-65,83-94)
+        bool bidirectional = false;               // SLRGPU_RENDER_BPT: what GPUBidirectionalPathTracingRenderer sets
         explicit GPUPathTracingRenderer(uint32_t spp) : m_samplesPerPixel(spp) { }
         void render(const Scene &scene, const RenderSettings &settings) const override;
+    };
+    // next to BidirectionalPathTracingRenderer (libSLR/Renderers/BidirectionalPathTracingRenderer.h): same seam, same pass
+    // loop and export cadence, bidirectional samples on the GPU (the light-tracing splats land in the sensor's main buffer)
+    class GPUBidirectionalPathTracingRenderer : public GPUPathTracingRenderer {
+    public:
+        explicit GPUBidirectionalPathTracingRenderer(uint32_t spp) : GPUPathTracingRenderer(spp) { bidirectional = true; }
     };
 }

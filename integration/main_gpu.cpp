@@ -4,7 +4,10 @@
 // libSLRSceneGraph/API.cpp:1016-1036) is replaced by SLR::GPUPathTracingRenderer with the same sample count. In a merge
 // this is a two-line change at API.cpp:1025 (`new GPUPathTracingRenderer(samples)`); it is done here so that the
 // reference's sources stay untouched.
-//   slr_gpu scene.txt [sensor_out.bin]
+//   slr_gpu scene.txt [sensor_out.bin] [bpt]
+// Without the third argument every scene renders with the unidirectional GPU path tracer (the configuration the headline
+// benchmark and the PT parity tests use); with "bpt" a scene that selected "BPT" gets SLR::GPUBidirectionalPathTracingRenderer
+// -- in a merge the second line of the change, at API.cpp:1033.
 // With a second argument the camera's ImageSensor is dumped after rendering (u32 width, height, 16, then
 // width*height*16 f32 = ImageSensor::pixel(x, y)), the same format oracle/drivers/ref_render.cpp writes: the parity test
 // compares the two.
@@ -59,9 +62,14 @@ int main(int argc, const char* argv[]) {
 
     // ---- the drop-in: same seam (Renderer::render), GPU implementation
     uint32_t spp = 8;
+    bool bidirectional = false;
     if (auto pt = dynamic_cast<SLR::PathTracingRenderer*>(context.renderer.get())) spp = pt->m_samplesPerPixel;
-    else if (auto bpt = dynamic_cast<SLR::BidirectionalPathTracingRenderer*>(context.renderer.get())) spp = bpt->m_samplesPerPixel;
-    context.renderer.reset(new SLR::GPUPathTracingRenderer(spp));
+    else if (auto bpt = dynamic_cast<SLR::BidirectionalPathTracingRenderer*>(context.renderer.get())) {
+        spp = bpt->m_samplesPerPixel;
+        bidirectional = argc > 3 && std::string(argv[3]) == "bpt";
+    }
+    if (bidirectional) context.renderer.reset(new SLR::GPUBidirectionalPathTracingRenderer(spp));
+    else context.renderer.reset(new SLR::GPUPathTracingRenderer(spp));
 
     // the renderer writes NNN.bmp into the working directory, like the reference's
     std::string out = argc > 2 ? argv[2] : "";

@@ -4,7 +4,11 @@
 // GPU's slrgpu_probe_shading. Pins surface points (incl. normal maps, instances), every material / texture /
 // spectrum evaluation and every BSDF model at function level (PathTracingRenderer.cpp:147-210 is exactly
 // this sequence of calls).
-//   ref_probe scene.txt probes.bin out.bin
+//   ref_probe scene.txt probes.bin out.bin [bpt]
+// With "bpt" the queries are the bidirectional path tracer's (BidirectionalPathTracingRenderer.cpp:184-196, 302-325):
+// BSDF::sample with result->reverse, BSDF::evaluatePDF with revPDF, BSDF::evaluate with rev_fs, as a radiance query for even
+// probes and an importance query (adjoint = true) for odd probes; output layout: include/slrgpu.h slrgpu_probe_shading_bpt,
+// plus [58] = the largest |rev_fs - fs| of the evaluate call (the GPU side relies on it being zero).
 // probes.bin: u32 n, then n x 14 f32: org[3] dir[3] wlOffset uLambda uComponent uDir0 uDir1 evalDirWorld[3]
 // out.bin:    u32 n, u32 64, then n x 64 f32 (layout: include/slrgpu.h SLRGPU_PROBE_*)
 #include <libSLR/Core/SurfaceObject.h>
@@ -17,12 +21,15 @@
 #include <libSLRSceneGraph/API.hpp>
 #include <cstdio>
 #include <cstring>
+#include <cmath>
+#include <string>
 #include <vector>
 
 using namespace SLR;
 
 int main(int argc, char** argv) {
-    if (argc < 4) { fprintf(stderr, "usage: ref_probe scene.txt probes.bin out.bin\n"); return 2; }
+    if (argc < 4) { fprintf(stderr, "usage: ref_probe scene.txt probes.bin out.bin [bpt]\n"); return 2; }
+    const bool bptMode = argc > 4 && std::string(argv[4]) == "bpt";
     initSpectrum();
     SLRSceneGraph::SceneRef scene = createShared<SLRSceneGraph::Scene>();
     SLRSceneGraph::RenderingContext context;
@@ -55,6 +62,35 @@ int main(int argc, char** argv) {
         if (sp.atInfinity) { o[0] = 2.0f; mem.reset(); continue; }
         o[0] = 1.0f;
         o[1] = isect.dist;
+        if (bptMode) {
+            Vector3D dirOut_sn = sp.shadingFrame.toLocal(-ray.dir);
+            Normal3D gNorm_sn = sp.shadingFrame.toLocal(sp.gNormal);
+            BSDF* bsdf = sp.createBSDF(wls, mem);
+            BSDFQuery query(dirOut_sn, gNorm_sn, wls.selectedLambda, DirectionType::All, (i & 1u) != 0);
+            BSDFQueryResult res;
+            BSDFReverseInfo rev;
+            rev.fs = SampledSpectrum::Zero; rev.dirPDF = 0.0f;
+            res.reverse = &rev;
+            SampledSpectrum fs = bsdf->sample(query, BSDFSample(p[8], p[9], p[10]), &res);
+            for (int k = 0; k < 16; ++k) o[2 + k] = fs[k];
+            o[18] = res.dir_sn.x; o[19] = res.dir_sn.y; o[20] = res.dir_sn.z;
+            o[21] = res.dirPDF;
+            o[22] = (float)res.dirType.value;
+            const bool sampled = !(fs == SampledSpectrum::Zero) && res.dirPDF != 0.0f;
+            for (int k = 0; k < 16; ++k) o[23 + k] = sampled ? rev.fs[k] : 0.0f;
+            o[39] = sampled ? rev.dirPDF : 0.0f;
+            Vector3D evalDir_sn = sp.shadingFrame.toLocal(Vector3D(p[11], p[12], p[13]));
+            float revPDF = 0.0f;
+            o[40] = bsdf->evaluatePDF(query, evalDir_sn, &revPDF);
+            o[41] = revPDF;
+            SampledSpectrum revFs;
+            SampledSpectrum fe = bsdf->evaluate(query, evalDir_sn, &revFs);
+            float worst = 0.0f;
+            for (int k = 0; k < 16; ++k) { o[42 + k] = fe[k]; worst = std::fmax(worst, std::fabs(revFs[k] - fe[k])); }
+            o[58] = worst;
+            mem.reset();
+            continue;
+        }
         o[2] = sp.p.x; o[3] = sp.p.y; o[4] = sp.p.z;
         o[5] = sp.shadingFrame.z.x; o[6] = sp.shadingFrame.z.y; o[7] = sp.shadingFrame.z.z;
         o[8] = sp.shadingFrame.x.x; o[9] = sp.shadingFrame.x.y; o[10] = sp.shadingFrame.x.z;

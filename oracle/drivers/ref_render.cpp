@@ -5,7 +5,9 @@
 //   ref_render scene.txt out.bin [spp] [width] [height] [seed] [qbvh=0|1]
 // out.bin: u32 width, height, channels (16; 3 in the RGB-mode build ref_render_rgb), then width*height*channels f32 (row-major, un-normalised sums,
 // i.e. ImageSensor::pixel(x, y) after PathTracingRenderer::render). spp/width/height/seed <= 0 keep the
-// scene file's values. The renderer is always the unidirectional PathTracingRenderer. With qbvh=1 every
+// scene file's values. The renderer is the unidirectional PathTracingRenderer unless the 8th argument says "bpt" (the
+// reference's BidirectionalPathTracingRenderer; its light-tracing splats live in per-thread "separated" buffers, which the
+// dump adds to the pixel exactly like ImageSensor::saveImage does, ImageSensor.cpp:153-156). With qbvh=1 every
 // aggregate's accelerator is swapped for QBVH(SBVH) after construction.
 #include <libSLR/Core/SurfaceObject.h>
 #include <libSLR/Core/RenderSettings.h>
@@ -16,6 +18,7 @@
 #include <libSLR/Memory/ArenaAllocator.h>
 #include <cstring>
 #include <libSLR/Renderers/PathTracingRenderer.h>
+#include <libSLR/Renderers/BidirectionalPathTracingRenderer.h>
 #include <libSLR/Renderers/DebugRenderer.h>
 #include <libSLR/Core/distributions.h>
 #include <libSLR/Cameras/PerspectiveCamera.h>
@@ -127,9 +130,11 @@ int main(int argc, char** argv) {
         debugRenderer.render(*rawScene, settings);
         return 0;
     }
-    PathTracingRenderer renderer(useSpp);
+    const bool bpt = argc > 8 && std::string(argv[8]) == "bpt";
+    if (bpt && spp <= 0) if (BidirectionalPathTracingRenderer* b = dynamic_cast<BidirectionalPathTracingRenderer*>(context.renderer.get())) useSpp = b->m_samplesPerPixel;
     auto t3 = std::chrono::steady_clock::now();
-    renderer.render(*rawScene, settings);
+    if (bpt) { BidirectionalPathTracingRenderer renderer(useSpp); renderer.render(*rawScene, settings); }
+    else { PathTracingRenderer renderer(useSpp); renderer.render(*rawScene, settings); }
     auto t4 = std::chrono::steady_clock::now();
 
     ImageSensor* sensor = rawScene->getCamera()->getSensor();
@@ -144,6 +149,7 @@ int main(int argc, char** argv) {
     for (uint32_t y = 0; y < H; ++y)
         for (uint32_t x = 0; x < W; ++x) {
             DiscretizedSpectrum px = ((const ImageSensor*)sensor)->pixel(x, y);
+            for (uint32_t b = 0; b < sensor->m_numSeparated; ++b) px += ((const ImageSensor*)sensor)->pixel(b, x, y);
 #ifdef Use_Spectral_Representation
             fwrite(px.values, 4, 16, f);
 #else
@@ -155,8 +161,8 @@ int main(int argc, char** argv) {
     auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     double paths = (double)W * H * useSpp;
     fprintf(stderr, "{\"width\": %u, \"height\": %u, \"spp\": %u, \"threads\": %u, \"read_s\": %.3f, \"build_s\": %.3f, \"render_s\": %.4f, "
-                    "\"mpaths_per_s\": %.5f, \"accelerator\": \"%s\", \"sensitivity\": %.9g}\n",
+                    "\"mpaths_per_s\": %.5f, \"accelerator\": \"%s\", \"sensitivity\": %.9g, \"renderer\": \"%s\"}\n",
             W, H, useSpp, std::thread::hardware_concurrency(), sec(t0, t1), sec(t1, t2), sec(t3, t4), paths / sec(t3, t4) / 1e6,
-            qbvh ? "QBVH" : "SBVH", (double)sensor->m_sensitivity);
+            qbvh ? "QBVH" : "SBVH", (double)sensor->m_sensitivity, bpt ? "BPT" : "PT");
     return 0;
 }

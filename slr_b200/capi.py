@@ -149,6 +149,7 @@ _ABI_STRUCTS = [SceneDesc, BvhNode, LeafRecord, Instance, Triangle, Vertex, Spec
                 RenderStats, SbvhNode, Motion]
 
 RENDER_PROFILE_STAGES = 0x1
+RENDER_BPT = 0x2                 # bidirectional path tracing (include/slrgpu.h SLRGPU_RENDER_BPT)
 
 
 def _load(name):
@@ -194,6 +195,8 @@ gpu.slrgpu_occluded_batch.argtypes = [C.c_void_p, C.POINTER(RayBatch), c_u64, PU
 
 gpu.slrgpu_probe_shading.restype = C.c_int
 gpu.slrgpu_probe_shading.argtypes = [C.c_void_p, PF, c_u64, PF]
+gpu.slrgpu_probe_shading_bpt.restype = C.c_int
+gpu.slrgpu_probe_shading_bpt.argtypes = [C.c_void_p, PF, c_u64, PF]
 gpu.slrgpu_release_workspaces.restype = None
 
 # ---- slrhost.h prototypes
@@ -435,6 +438,10 @@ host.slrhost_render_debug.restype = C.c_int
 host.slrhost_render_debug.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, PF, C.POINTER(C.c_double)]
 host.slrhost_render_range.restype = C.c_int
 host.slrhost_render_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, PF, C.POINTER(C.c_double)]
+host.slrhost_render_bpt.restype = C.c_int
+host.slrhost_render_bpt.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, PF, C.POINTER(C.c_double)]
+host.slrhost_scene_renderer_method.restype = C.c_int
+host.slrhost_scene_renderer_method.argtypes = [C.c_void_p, C.c_char_p, c_u32]
 host.slrhost_save_bmp.restype = C.c_int
 host.slrhost_save_bmp.argtypes = [C.c_char_p, PF, C.c_int, C.c_int, C.c_int, c_f, c_f]
 host.slrhost_accum_to_rgb.restype = C.c_int
@@ -458,11 +465,15 @@ def read_scene(path, rgb_mode=False):
     host.slrhost_scene_context(hs.handle, buf)
     hs.context = {"width": int(buf[0]), "height": int(buf[1]), "samples": int(buf[2]), "rngSeed": int(buf[3]),
                   "timeStart": buf[4], "timeEnd": buf[5], "brightness": buf[6], "hasRenderer": bool(buf[7])}
+    name = C.create_string_buffer(32)
+    host.slrhost_scene_renderer_method(hs.handle, name, 32)
+    hs.context["method"] = name.value.decode()      # "PT", "BPT", "debug" as the scene file's setRenderer wrote it
     return hs
 
 
-def host_render(host_scene, width=0, height=0, spp=0, seed=0, device=0, bmp_dir=None, spp_begin=0, out=None):
-    """Renderer::render through the host's GPUPathTracingRenderer (global samples [spp_begin, spp_begin + spp)).
+def host_render(host_scene, width=0, height=0, spp=0, seed=0, device=0, bmp_dir=None, spp_begin=0, out=None, method="PT"):
+    """Renderer::render through the host's GPUPathTracingRenderer (method "PT") or GPUBidirectionalPathTracingRenderer
+    ("BPT"), global samples [spp_begin, spp_begin + spp).
     Returns (accum[h, w, c], stats); `out` may supply the destination array (e.g. a pinned torch tensor's numpy view)."""
     ctx = getattr(host_scene, "context", {"width": 0, "height": 0})
     w = width or ctx["width"]
@@ -472,8 +483,9 @@ def host_render(host_scene, width=0, height=0, spp=0, seed=0, device=0, bmp_dir=
     assert accum.shape == (h, w, chan) and accum.dtype == np.float32 and accum.flags["C_CONTIGUOUS"]
     st = (C.c_double * 6)()
     t0 = time.perf_counter()
-    _host_check(host.slrhost_render_range(host_scene.handle, device, width, height, spp_begin, spp, seed,
-                                          os.fsencode(bmp_dir) if bmp_dir else None, _pf(accum), st), "slrhost_render_range")
+    entry = {"PT": host.slrhost_render_range, "BPT": host.slrhost_render_bpt}[method]
+    _host_check(entry(host_scene.handle, device, width, height, spp_begin, spp, seed,
+                      os.fsencode(bmp_dir) if bmp_dir else None, _pf(accum), st), "slrhost_render_range")
     call_s = time.perf_counter() - t0
     return accum, {"paths": int(st[0]), "rays": int(st[1]), "device_s": st[2], "wall_s": st[3], "upload_s": st[4], "channels": int(st[5]) % 1000,
                    "devices": int(st[5]) // 1000, "call_s": call_s}
@@ -523,6 +535,15 @@ def probe_shading(gpu_scene, probes):
     p = _f32(probes).reshape(-1, 14)
     out = np.zeros((p.shape[0], 64), np.float32)
     _gpu_check(gpu.slrgpu_probe_shading(gpu_scene.handle, _pf(p), p.shape[0], _pf(out)), "slrgpu_probe_shading")
+    return out
+
+
+def probe_shading_bpt(gpu_scene, probes):
+    """slrgpu_probe_shading_bpt: the bidirectional path tracer's BSDF queries (reverse values, adjoint on odd probes):
+    probes[n, 14] -> out[n, 64] (layout in include/slrgpu.h)."""
+    p = _f32(probes).reshape(-1, 14)
+    out = np.zeros((p.shape[0], 64), np.float32)
+    _gpu_check(gpu.slrgpu_probe_shading_bpt(gpu_scene.handle, _pf(p), p.shape[0], _pf(out)), "slrgpu_probe_shading_bpt")
     return out
 
 

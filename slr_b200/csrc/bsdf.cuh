@@ -57,7 +57,18 @@ struct BsdfQuery {
     V3 gn;           // gNormal_sn
     uint32_t hero;   // wlHint
     uint32_t flags;
+    // BSDFQuery::adjoint: false for radiance transport (every query of the path tracer), true for the queries of a light
+    // subpath (bidirectional path tracing, bpt.cu). It moves the shading-normal correction to the query direction and drops
+    // the (eta_enter / eta_exit)^2 radiance scaling of refraction.
+    bool adjoint = false;
 };
+// BSDF::sample / evaluate (directional_distribution_functions.h:231-275): |cos| ratio between shading and geometric normal,
+// taken at the sampled / evaluated direction for radiance and at the query direction for importance
+__device__ __forceinline__ float snCorrectionOf(const BsdfQuery& q, const V3& dir) {
+    return q.adjoint ? fabsf(q.dir.z / dot(q.dir, q.gn)) : fabsf(dir.z / dot(dir, q.gn));
+}
+// BSDF::weight (directional_distribution_functions.h:276-285)
+__device__ __forceinline__ float snWeightCorrectionOf(const BsdfQuery& q) { return q.adjoint ? fabsf(q.dir.z / dot(q.dir, q.gn)) : 1.0f; }
 
 struct BsdfSampleResult {
     V3 dir;
@@ -232,8 +243,9 @@ static __device__ __noinline__ Spec<NC> mfTransmissionEval(const Lobe<NC>& L, co
     const float inv = 1.0f / fabsf(q.dir.z * dir.z);
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-        const float eEnter = entering ? L.s0.v[i] : L.s1.v[i];
-        ret.v[i] = ret.v[i] * inv * (eEnter * eEnter);
+        // adjoint: the eEnter^2 / eExit^2 of radiance transport is cancelled (MicrofacetBSDF.cpp:187,239)
+        const float eScale = (entering != q.adjoint) ? L.s0.v[i] : L.s1.v[i];
+        ret.v[i] = ret.v[i] * inv * (eScale * eScale);
     }
     return ret;
 }
@@ -299,7 +311,7 @@ __device__ __forceinline__ Spec<NC> baseSampleT(const Lobe<NC>& L, const BsdfQue
         res->pdf = 1.0f - reflectProb;
         res->type = DT_Transmission | DT_Delta0D | (L.baseDirType & DT_Dispersive);
         float v = specAt(L.s0, q.hero) * (1.0f - specAt(F, q.hero));
-        v *= (eEnter * eEnter) / (eExit * eExit);
+        if (!q.adjoint) v *= (eEnter * eEnter) / (eExit * eExit);
         v /= fabsf(cosExit);
         Spec<NC> ret;
 #pragma unroll
@@ -606,7 +618,7 @@ template <int NC>
 __device__ __forceinline__ Spec<NC> basePublicSample(const Lobe<NC>& L, const BsdfQuery& q, float uComp, float u0, float u1, BsdfSampleResult* res) {
     if (!dtMatches(L.baseDirType, q.flags)) { res->pdf = 0.0f; res->type = 0; return specZero<NC>(); }
     const Spec<NC> fs = baseSample(L, q, uComp, u0, u1, res);
-    const float snCorrection = fabsf(res->dir.z / dot(res->dir, q.gn));
+    const float snCorrection = snCorrectionOf(q, res->dir);
     return fs * snCorrection;
 }
 template <int NC>
@@ -615,7 +627,7 @@ __device__ __forceinline__ Spec<NC> basePublicEvaluate(const Lobe<NC>& L, const 
     mq.flags &= sideTest(q.gn, q.dir, dir);
     if (!dtMatches(L.baseDirType, mq.flags)) return specZero<NC>();
     const Spec<NC> fs = baseEvaluate(L, mq, dir);
-    const float snCorrection = fabsf(dir.z / dot(dir, q.gn));
+    const float snCorrection = snCorrectionOf(q, dir);
     return fs * snCorrection;
 }
 template <int NC>
@@ -626,7 +638,7 @@ __device__ __forceinline__ float basePublicPdf(const Lobe<NC>& L, const BsdfQuer
 template <int NC>
 __device__ __forceinline__ float basePublicWeight(const Lobe<NC>& L, const BsdfQuery& q) {
     if (!dtMatches(L.baseDirType, q.flags)) return 0.0f;
-    return baseWeight(L, q);
+    return baseWeight(L, q) * snWeightCorrectionOf(q);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -660,10 +672,10 @@ __device__ __forceinline__ float lobePdfInternal(const Lobe<NC>& L, const BsdfQu
 template <int NC>
 __device__ __forceinline__ float lobeWeight(const Lobe<NC>& L, const BsdfQuery& q) {    // BSDF::weight (public)
     if (!dtMatches(lobeDirType(L), q.flags)) return 0.0f;
-    if (!L.inverse) return baseWeight(L, q);
+    if (!L.inverse) return baseWeight(L, q) * snWeightCorrectionOf(q);
     BsdfQuery mq = q;
     mq.flags = dtFlip(q.flags);
-    return basePublicWeight(L, mq);
+    return basePublicWeight(L, mq) * snWeightCorrectionOf(q);       // InverseBSDF::weightInternal inside BSDF::weight: corrected twice (kept)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -737,7 +749,7 @@ __device__ inline Spec<NC> bsdfSample(const Bsdf<NC, ML>& b, const BsdfQuery& q,
         }
         res->pdf /= sumWeights;
     }
-    const float snCorrection = fabsf(res->dir.z / dot(res->dir, q.gn));
+    const float snCorrection = snCorrectionOf(q, res->dir);
     return value * snCorrection;
 }
 
@@ -747,7 +759,7 @@ __device__ __forceinline__ Spec<NC> lobeSample(const Lobe<NC>& L, const BsdfQuer
     res->pdf = 0.0f; res->type = 0; res->dir = V3(0, 0, 1);
     if (!dtMatches(L.baseDirType, q.flags)) return specZero<NC>();
     const Spec<NC> value = baseSampleT<NC, LT>(L, q, uComp, u0, u1, res);
-    const float snCorrection = fabsf(res->dir.z / dot(res->dir, q.gn));
+    const float snCorrection = snCorrectionOf(q, res->dir);
     return value * snCorrection;
 }
 template <int NC, int LT>
@@ -756,7 +768,7 @@ __device__ __forceinline__ Spec<NC> lobeEvaluate(const Lobe<NC>& L, const BsdfQu
     mq.flags &= sideTest(q.gn, q.dir, dir);
     if (!dtMatches(L.baseDirType, mq.flags)) return specZero<NC>();
     const Spec<NC> fs = baseEvaluateT<NC, LT>(L, mq, dir);
-    const float snCorrection = fabsf(dir.z / dot(dir, q.gn));
+    const float snCorrection = snCorrectionOf(q, dir);
     return fs * snCorrection;
 }
 template <int NC, int LT>
@@ -780,7 +792,7 @@ __device__ inline Spec<NC> bsdfEvaluate(const Bsdf<NC, ML>& b, const BsdfQuery& 
             if (i < b.numLobes && dtMatches(lobeDirType(b.lobes[i]), mq.flags))
                 fs = fs + lobeEvaluateInternal(b.lobes[i], mq, dir);
     }
-    const float snCorrection = fabsf(dir.z / dot(dir, q.gn));
+    const float snCorrection = snCorrectionOf(q, dir);
     return fs * snCorrection;
 }
 

@@ -19,6 +19,7 @@
 // The kernel sits in the wave graph after every wave pair and returns at once while its condition is false
 // (~3 us per pair); tailEndKernel then closes the loop state like endWaveKernel does.
 #include "ray_io.cuh"
+#include "single_ray.cuh"
 #include "stages.cuh"
 #include <algorithm>
 
@@ -46,22 +47,10 @@ __device__ __forceinline__ bool tailCondition(const WavefrontCounters* c, uint32
 }
 
 // one ray, start to end, by its own lane (60 % of the tail kernel's instructions: the long paths live in and between the
-// two sphere meshes, whose interior rays visit many nodes); flat scenes take the leaner step without instance handling
-template <bool ANY_HIT, bool INSTANCES, bool ALPHA>
-__device__ __noinline__ void tailWalkT(const DeviceScene& s, WalkState& w, uint32_t* stack, bool* overflow) {
-    InstanceWalkState iw;
-    iw.leaves.clear(); iw.saved.clear(); iw.curInst = SLRGPU_INVALID_ID;
-    TraversalCounters cnt = {0, 0};
-    bool ovf = false;
-    walkBegin(w, stack);
-    while (!walkStep<INSTANCES, ANY_HIT, false, ALPHA, SLR_TAIL_PREFETCH != 0>(s, w, iw, stack, cnt, ovf)) { }
-    if (ovf) *overflow = true;
-}
+// two sphere meshes, whose interior rays visit many nodes): single_ray.cuh
 template <bool ANY_HIT>
 __device__ __forceinline__ void tailWalk(const DeviceScene& s, WalkState& w, uint32_t* stack, bool* overflow) {   // w.time set by the caller
-    if (s.hasAlpha) tailWalkT<ANY_HIT, true, true>(s, w, stack, overflow);
-    else if (s.numInstances != 0) tailWalkT<ANY_HIT, true, false>(s, w, stack, overflow);
-    else tailWalkT<ANY_HIT, false, false>(s, w, stack, overflow);
+    singleRayWalk<ANY_HIT, SLR_TAIL_PREFETCH != 0>(s, w, stack, overflow);
 }
 
 template <int NC, int CLASS>

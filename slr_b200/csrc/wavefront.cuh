@@ -107,6 +107,10 @@ int launchTail(const SlrGpuScene* sc, const RenderConstants& rc, const PathQueue
                const ShadowQueue& sq, float* accum, WavefrontCounters* counters, WavefrontCounters* ring, uint32_t ringSize,
                uint32_t cap, cudaStream_t stream);
 
+// bpt.cu: the bidirectional path tracer behind SLRGPU_RENDER_BPT (one kernel launch per call, synchronised before return)
+int renderBpt(SlrGpuScene* sc, const SlrGpuRenderParams* p, const RenderConstants& rc, float* accumDev, cudaStream_t stream, SlrGpuRenderStats* stats);
+void releaseBptWorkspaces();
+
 // Stratum of wavelength i for a path with stratification offset `wlOffset`: min(uint((lambda_i - 360)
 // / 470 * 16), 15) (SpectrumTypes.h:826-835) in uncontracted fp32 as the x86-64 reference computes it
 // (the index is a rounding decision). It equals i except at rounding boundaries.

@@ -138,8 +138,27 @@ SLRGPU_API int slrhost_render(SlrHostScene* s, int device, int width, int height
     return slrhost_render_range(s, device, width, height, 0, spp, seed, bmp_dir, accum, stats);
 }
 
+static int renderRange(SlrHostScene* s, bool bidirectional, int device, int width, int height, int spp_begin, int spp, int seed,
+                       const char* bmp_dir, float* accum, double* stats);
+
 SLRGPU_API int slrhost_render_range(SlrHostScene* s, int device, int width, int height, int spp_begin, int spp, int seed,
                                     const char* bmp_dir, float* accum, double* stats) {
+    return renderRange(s, false, device, width, height, spp_begin, spp, seed, bmp_dir, accum, stats);
+}
+
+SLRGPU_API int slrhost_render_bpt(SlrHostScene* s, int device, int width, int height, int spp_begin, int spp, int seed,
+                                  const char* bmp_dir, float* accum, double* stats) {
+    return renderRange(s, true, device, width, height, spp_begin, spp, seed, bmp_dir, accum, stats);
+}
+
+SLRGPU_API int slrhost_scene_renderer_method(const SlrHostScene* s, char* method, uint32_t capacity) {
+    if (!s || !method || capacity == 0) return fail("slrhost_scene_renderer_method: invalid argument");
+    std::snprintf(method, capacity, "%s", s->context.rendererMethod.c_str());
+    return 0;
+}
+
+static int renderRange(SlrHostScene* s, bool bidirectional, int device, int width, int height, int spp_begin, int spp, int seed,
+                       const char* bmp_dir, float* accum, double* stats) {
     if (!s) return fail("slrhost_render: null scene");
     if (spp_begin < 0) return fail("slrhost_render_range: negative first sample index");
     try {
@@ -161,6 +180,7 @@ SLRGPU_API int slrhost_render_range(SlrHostScene* s, int device, int width, int 
         renderer.device = device >= 0 ? device : 0;
         renderer.deviceCount = device >= 0 ? 1 : 0;
         renderer.sampleBegin = (uint32_t)spp_begin;
+        renderer.bidirectional = bidirectional;
         renderer.exportProgressiveImages = bmp_dir != nullptr;
         if (bmp_dir) renderer.outputDirectory = bmp_dir;
         // with a caller buffer the sensor renders straight into it (no frame-sized copies on the way out)

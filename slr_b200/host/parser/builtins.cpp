@@ -617,16 +617,12 @@ void registerBuiltins(Interpreter& in) {
         const ParameterList& cfg = a.at("config").tuple();
         RenderingContext* ctx = in.context;
         if (method == "PT" || method == "BPT") {
-            // "PT" selects the GPU path tracer. "BPT" (bidirectional) has no GPU implementation yet:
-            // the scene still loads (6 of the 7 shipped scenes ask for it) and renders with the
-            // unidirectional GPU path, which converges to the same image.
+            // API.cpp setRenderer: "PT" -> PathTracingRenderer, "BPT" -> BidirectionalPathTracingRenderer; here their GPU twins
             return withConfig(cfg, {{"samples", Type::Integer, Value::Int(8)}}, in, [ctx, method](const Args& c, Interpreter&) {
                 ctx->samples = (uint32_t)c.at("samples").i;
                 ctx->rendererMethod = method;
-                if (method == "BPT")
-                    std::fprintf(stderr, "slr: warning: setRenderer(\"BPT\"): bidirectional path tracing is not implemented on the GPU; "
-                                         "rendering with the unidirectional path tracer (same expected image, different noise).\n");
-                ctx->renderer.reset(new GPUPathTracingRenderer(ctx->samples));
+                if (method == "BPT") ctx->renderer.reset(new GPUBidirectionalPathTracingRenderer(ctx->samples));
+                else ctx->renderer.reset(new GPUPathTracingRenderer(ctx->samples));
                 return Value();
             });
         }

@@ -111,6 +111,7 @@ void GPUPathTracingRenderer::render(const RenderScene& scene, const RenderSettin
     p.time_start = settings.getFloat(RenderSettingItem::TimeStart);
     p.time_end = settings.getFloat(RenderSettingItem::TimeEnd);
     p.rng_seed = settings.getInt(RenderSettingItem::RNGSeed);
+    if (bidirectional) p.flags |= SLRGPU_RENDER_BPT;
     const float brightness = settings.getFloat(RenderSettingItem::Brightness);
     // one frame segment [begin, end) of the sample range on all devices, into `dst` (overwritten)
     auto renderSegment = [&](uint32_t begin, uint32_t end, float* dst) {

@@ -100,9 +100,19 @@ public:
     // from `device` on -- what a scene file's setRenderer("PT") gets; 1 = the single device `device`.
     int device = 0;
     int deviceCount = 0;
+    // true: every sample is a bidirectional one (SLRGPU_RENDER_BPT) -- what GPUBidirectionalPathTracingRenderer sets
+    bool bidirectional = false;
     explicit GPUPathTracingRenderer(uint32_t spp) : m_samplesPerPixel(spp) {}
     uint32_t samplesPerPixel() const { return m_samplesPerPixel; }
     void render(const RenderScene& scene, const RenderSettings& settings) const override;
+};
+
+// Drop-in for BidirectionalPathTracingRenderer (Renderers/BidirectionalPathTracingRenderer.cpp:25-100): the same pass loop,
+// export cadence, sample partition over devices and sensor as the path tracer above, with bidirectional samples
+// (csrc/bpt.cu). What setRenderer("BPT") creates.
+class GPUBidirectionalPathTracingRenderer : public GPUPathTracingRenderer {
+public:
+    explicit GPUBidirectionalPathTracingRenderer(uint32_t spp) : GPUPathTracingRenderer(spp) { bidirectional = true; }
 };
 
 // The debug (AOV) renderer on the GPU: DebugRenderer (libSLR/Renderers/DebugRenderer.h/.cpp) -- one camera sample per

@@ -3,7 +3,10 @@ from /root/reference): for 2048 probe rays per scene the reference's Scene::inte
 createBSDF, BSDF::sample / evaluate / evaluatePDF and emittance outputs (layout: include/slrgpu.h,
 slrgpu_probe_shading). The probe rays are stored with the results.
 
-    python tests/golden/make_probe_golden.py [scene ...]
+    python tests/golden/make_probe_golden.py [--bpt] [scene ...]
+
+--bpt: the bidirectional path tracer's queries (ref_probe ... bpt: reverse values, adjoint on odd probes; layout:
+slrgpu_probe_shading_bpt) -> probe_bpt_<scene>.npz.
 """
 import os
 import sys
@@ -23,17 +26,18 @@ N, SEED = 2048, 20261018
 
 def main():
     work = tempfile.mkdtemp(prefix="slr_probe_golden_")
-    for name in sys.argv[1:] or SCENES:
+    bpt = "--bpt" in sys.argv[1:]
+    for name in [a for a in sys.argv[1:] if a != "--bpt"] or SCENES:
         path = ru.scene_file(name, work, 64, 64, 1)
         with capi.stdout_to_stderr():
             hs = capi.read_scene(path)
         center = [hs.desc.world_center[i] for i in range(3)]
         probes = ru.make_probes(center, hs.desc.world_radius, N, SEED)
-        want = ru.run_ref_probe(path, probes)
-        out = os.path.join(ru.GOLDEN, f"probe_{name}.npz")
+        want = ru.run_ref_probe(path, probes, bpt=bpt)
+        out = os.path.join(ru.GOLDEN, f"probe_bpt_{name}.npz" if bpt else f"probe_{name}.npz")
         np.savez_compressed(out, probes=probes, reference=want)
         hit = want[:, 0] == 1
-        types, counts = np.unique(want[hit, 32].astype(int), return_counts=True)
+        types, counts = np.unique(want[hit, 22 if bpt else 32].astype(int), return_counts=True)
         print(f"{name}: {int(hit.sum())} of {N} probes hit a surface; sampled direction types {dict(zip(types.tolist(), counts.tolist()))}; wrote {out}")
 
 

@@ -1,7 +1,12 @@
 """Generates tests/golden/render_<scene>.npz from the REFERENCE renderer (oracle/_ref/ref_render, built by
 oracle/Makefile from /root/reference): block means of the converged image and their standard error.
 
-    python tests/golden/make_render_golden.py [scene ...]
+    python tests/golden/make_render_golden.py [--bpt] [scene ...]
+
+--bpt: the reference's BidirectionalPathTracingRenderer instead (oracle/_ref/ref_render ... bpt) -> render_bpt_<scene>.npz,
+the expectation of tests/test_gpu_bpt.py. It is NOT always the path tracer's: with emitters inside scaled instances (`lamps`)
+the reference's bidirectional estimator converges to a darker image than its path tracer (object-space area pdfs and an
+un-normalised emission direction), and the GPU twin is held to what the reference's BPT renders.
 
 For every scene of slr_b200.scenes.SCENES used by tests/test_gpu_render.py the reference's
 PathTracingRenderer renders SEEDS (8) independent images at SIZE x SIZE (64), SPP_EACH (2048) spp; the golden is the
@@ -26,13 +31,15 @@ SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced", "scatter", "lam
 
 
 def main():
-    names = sys.argv[1:] or SCENES
+    args = sys.argv[1:]
+    bpt = "--bpt" in args
+    names = [a for a in args if a != "--bpt"] or SCENES
     work = tempfile.mkdtemp(prefix="slr_golden_")
     for name in names:
         path = ru.scene_file(name, work, SIZE, SIZE, SPP_EACH)
         means = []
         for k in range(SEEDS):
-            accum, timing = ru.run_ref_render(path, SPP_EACH, SIZE, SIZE, seed=1000 + 7919 * k)
+            accum, timing = ru.run_ref_render(path, SPP_EACH, SIZE, SIZE, seed=1000 + 7919 * k, bpt=bpt)
             means.append(ru.block_means(capi.accum_to_rgb(accum, 1.0 / SPP_EACH), BLOCK))
         # a block that contains a NaN pixel in one seed (the reference's own defect, see render_util.sanitize_reference)
         # is left out of that seed's contribution
@@ -41,7 +48,7 @@ def main():
         assert count.min() >= SEEDS // 2, "too many NaN blocks in the reference renders"
         block_mean = np.nanmean(means, 0)
         block_sigma = np.nanstd(means, 0, ddof=1) / np.sqrt(count)
-        out = os.path.join(ru.GOLDEN, f"render_{name}.npz")
+        out = os.path.join(ru.GOLDEN, f"render_bpt_{name}.npz" if bpt else f"render_{name}.npz")
         np.savez_compressed(out, block_mean=block_mean.astype(np.float32), block_sigma=block_sigma.astype(np.float32),
                             size=SIZE, block=BLOCK, ref_spp=SEEDS * SPP_EACH, gpu_spp=GPU_SPP,
                             reference_threads=timing.get("threads", 0))

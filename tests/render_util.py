@@ -16,14 +16,15 @@ def have_ref_render(rgb=False):
     return os.access(REF_RENDER_RGB if rgb else REF_RENDER, os.X_OK)
 
 
-def run_ref_render(scene_path, spp, width, height, seed=0, qbvh=0, timeout=3600, rgb=False):
-    """Returns (accum[h, w, 16] float32, timing dict) from the reference's PathTracingRenderer; rgb=True runs the
-    reference's RGB-mode build (accum[h, w, 3])."""
+def run_ref_render(scene_path, spp, width, height, seed=0, qbvh=0, timeout=3600, rgb=False, bpt=False):
+    """Returns (accum[h, w, 16] float32, timing dict) from the reference's PathTracingRenderer (bpt=True: its
+    BidirectionalPathTracingRenderer, separated light-tracing buffers added in); rgb=True runs the reference's RGB-mode
+    build (accum[h, w, 3])."""
     scene_path = os.path.abspath(scene_path)
     out = scene_path + f".ref_{spp}_{width}x{height}_{seed}.bin"
     # the reference resolves asset paths as <cwd>/<dirname(scene)>/<asset>: run it on the bare file name
-    p = subprocess.run([REF_RENDER_RGB if rgb else REF_RENDER, os.path.basename(scene_path), out, str(spp), str(width), str(height), str(seed), str(qbvh)],
-                       capture_output=True, text=True, timeout=timeout, cwd=os.path.dirname(scene_path))
+    p = subprocess.run([REF_RENDER_RGB if rgb else REF_RENDER, os.path.basename(scene_path), out, str(spp), str(width), str(height), str(seed), str(qbvh)]
+                       + (["bpt"] if bpt else []), capture_output=True, text=True, timeout=timeout, cwd=os.path.dirname(scene_path))
     if p.returncode != 0:
         raise RuntimeError(f"ref_render failed: {p.stderr[-2000:]}")
     timing = {}
@@ -149,13 +150,13 @@ def make_probes(center, radius, n, seed):
     return np.concatenate([o, d, u, e], 1).astype(np.float32)
 
 
-def run_ref_probe(scene_path, probes, timeout=600):
+def run_ref_probe(scene_path, probes, timeout=600, bpt=False):
     scene_path = os.path.abspath(scene_path)
     pin, pout = scene_path + ".probes.bin", scene_path + ".probes.out"
     with open(pin, "wb") as f:
         f.write(np.uint32(probes.shape[0]).tobytes())
         f.write(np.ascontiguousarray(probes, np.float32).tobytes())
-    p = subprocess.run([REF_PROBE, os.path.basename(scene_path), pin, pout], capture_output=True, text=True, timeout=timeout,
+    p = subprocess.run([REF_PROBE, os.path.basename(scene_path), pin, pout] + (["bpt"] if bpt else []), capture_output=True, text=True, timeout=timeout,
                        cwd=os.path.dirname(scene_path))
     if p.returncode != 0:
         raise RuntimeError(f"ref_probe failed: {p.stderr[-2000:]}")
@@ -195,4 +196,31 @@ def compare_probes(got, want, rel=2e-3):
     res["emitting_mismatch"] = float(np.mean(g[:, 50] != w[:, 50]))
     em = w[:, 50] == 1
     res["emittance_worst_rel"] = float(relerr(g[em, 51:64], w[em, 51:64], 1e-6).max()) if em.any() else 0.0
+    return res
+
+
+def compare_bpt_probes(got, want, rel=2e-3):
+    """Mismatch fractions between two bidirectional probe result arrays [n, 64] (include/slrgpu.h slrgpu_probe_shading_bpt):
+    sampled value / direction / pdf, the reverse value and pdf of the sample, evaluatePDF with its reverse pdf, evaluate."""
+    res = {"status_mismatch": float(np.mean(got[:, 0] != want[:, 0]))}
+    hit = (got[:, 0] == 1) & (want[:, 0] == 1)
+    g, w = got[hit].astype(np.float64), want[hit].astype(np.float64)
+    res["hits"] = int(hit.sum())
+
+    def relerr(a, b, floor):
+        return np.abs(a - b) / (np.abs(b) + floor)
+
+    def spec_bad(a, b):
+        scale = np.abs(b).max(1, keepdims=True) + 1e-6
+        return (np.abs(a - b) / scale).max(1) > rel
+    same_type = g[:, 22] == w[:, 22]
+    res["sample_type_mismatch"] = float(np.mean(~same_type))
+    gs, ws = g[same_type], w[same_type]
+    bad = spec_bad(gs[:, 2:18], ws[:, 2:18]) | (np.abs(gs[:, 18:21] - ws[:, 18:21]).max(1) > 2e-3) | (relerr(gs[:, 21], ws[:, 21], 1e-6) > rel)
+    res["sample_value_mismatch"] = float(np.mean(bad))
+    res["sample_reverse_fs_mismatch"] = float(np.mean(spec_bad(gs[:, 23:39], ws[:, 23:39])))
+    res["sample_reverse_pdf_mismatch"] = float(np.mean(relerr(gs[:, 39], ws[:, 39], 1e-5) > rel))
+    res["pdf_mismatch"] = float(np.mean(relerr(g[:, 40], w[:, 40], 1e-6) > rel))
+    res["reverse_pdf_mismatch"] = float(np.mean(relerr(g[:, 41], w[:, 41], 1e-5) > rel))
+    res["eval_mismatch"] = float(np.mean(spec_bad(g[:, 42:58], w[:, 42:58])))
     return res
