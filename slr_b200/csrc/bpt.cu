@@ -7,11 +7,11 @@
 //   Camera::sampleRay, PerspectiveIDF                         libSLR/Core/cameras.h:46-57, Cameras/PerspectiveCamera.cpp:63-99
 //   DiffuseEDF / IBLEDF                                       libSLR/EDFs/basic_EDFs.cpp:12-29, IBLEDF.cpp:11-29
 //
-// One lane carries one camera sample from start to end: the light subpath, the eye subpath (with the implicit s = 0 paths),
-// then every (s, t) connection with its shadow ray and MIS weight. The reference keeps the two vertex lists in std::vectors
-// of ~300-byte objects per CPU thread; here they live in HBM, interleaved by lane in 16-byte words (word w of vertex v of
-// lane l at ((v * W + w) * lanes + l) * 16 B), so the lanes of a warp that walk their lists in step read and write whole
-// 512-byte lines. The rays are the traversal of traverse.cuh (single_ray.cuh), surface points / lights / materials / BSDFs the
+// Samples are processed in batches of up to 262 144: one thread per SUBPATH traces the light / eye subpaths of the batch
+// (the eye threads also add the implicit s = 0 paths), then one thread per CONNECTION (slot, s, t) runs its shadow ray and MIS
+// weight. The reference keeps the two vertex lists in std::vectors of ~300-byte objects per CPU thread; here they live in
+// HBM, interleaved by batch slot in 16-byte words (word w of vertex v of slot l at ((v * W + w) * slots + l) * 16 B), so the
+// threads of a warp that walk their lists in step read and write whole 512-byte lines. The rays are the traversal of traverse.cuh (single_ray.cuh), surface points / lights / materials / BSDFs the
 // path tracer's device functions; a vertex stores its surface point and material, and the BSDF is rebuilt from them when a
 // connection needs it (the reference keeps the arena-allocated object instead).
 //
@@ -424,118 +424,39 @@ static __device__ __noinline__ void connectVertices(const DeviceScene& s, const 
     }
 }
 
-template <int NC>
-__global__ void __launch_bounds__(kBptBlock, SLR_BPT_MIN_BLOCKS)
-bptKernel(const DeviceScene s, const RenderConstants rc, BptStore st, float* __restrict__ accum, BptCounters* counters, unsigned long long totalSamples) {
-    const uint32_t lane = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t stack[kStackSize];
-    bool overflow = false;
-    BptLocalCounts counts = {0, 0, 0, 0};
-    for (unsigned long long lin = lane; lin < totalSamples; lin += st.lanes) {
-        // pixel order of the path tracer's ray generation: bands of 8 rows, column-major inside a band
-        const uint32_t pass = (uint32_t)(lin / rc.numPixels);
-        const uint32_t r = (uint32_t)(lin % rc.numPixels);
-        const uint32_t band = r / (8u * rc.width);
-        const uint32_t local = r - band * 8u * rc.width;
-        const uint32_t rows = min(8u, rc.height - band * 8u);
-        const uint32_t x = local / rows, y = band * 8u + local % rows;
-        const uint32_t pixel = y * rc.width + x;
+// ---------------------------------------------------------------------------------------------
+// The stages of a batch of samples (slot i of the batch = sample firstSample + i):
+//   subpathKernel   2 x batch threads: thread i < batch traces the eye subpath of slot i (and keeps what the sample's other
+//                   stages need), thread batch + i its light subpath -- a warp is all eye or all light
+//   countKernel     connections per slot = numE x numL (then an exclusive prefix sum over the slots)
+//   connectKernel   one thread per (slot, s, t): the thread's slot by binary search in the prefix sums
+// A first version ran a whole sample per lane in one kernel: ncu showed 4 of 32 lanes active per instruction and 24 cycles
+// of instruction-fetch stall per issue (the lanes of a warp sat in different phases of a 700 KB kernel), profiles/r02_bpt.md.
+// ---------------------------------------------------------------------------------------------
+struct BptSlotCommon {          // written by the slot's eye thread
+    uint32_t pixelKey, sample, sensorPixel, heroInPlace;     // hero | inPlace << 8
+    float wlOffset, time;
+};
+struct BptSlotEnd { unsigned long long delta; uint32_t num, pad; };
+struct BptBatch {
+    BptSlotCommon* common;
+    BptSlotEnd* eyeEnd;
+    BptSlotEnd* lightEnd;
+    uint32_t* connCount;        // [batch] connections of a slot; connBase[batch + 1] = their exclusive prefix sums
+    uint32_t* connBase;
+};
 
-        // time, pixel position, wavelengths (Job::kernel, BidirectionalPathTracingRenderer.cpp:104-110) + the lens sample
-        CameraSample cs;
-        sampleCamera<NC>(s, rc, x, y, pixel, rc.sppBegin + pass, &cs);
-        BptSample smp;
-        smp.pixelKey = pixel; smp.sample = rc.sppBegin + pass;
-        smp.sensorPixel = cs.ipy * rc.width + cs.ipx;
-        smp.wlOffset = cs.wlOffset; smp.time = cs.time; smp.hero = cs.hero;
-        smp.inPlace = (cs.flags & kFlagStrataInPlace) != 0;
-        smp.eyeDelta = 0; smp.lightDelta = 0; smp.numE = 0; smp.numL = 0;
+__device__ __forceinline__ void samplePixel(const RenderConstants& rc, unsigned long long lin, uint32_t* x, uint32_t* y, uint32_t* pass) {
+    // pixel order of the path tracer's ray generation: bands of 8 rows, column-major inside a band
+    *pass = (uint32_t)(lin / rc.numPixels);
+    const uint32_t r = (uint32_t)(lin % rc.numPixels);
+    const uint32_t band = r / (8u * rc.width);
+    const uint32_t local = r - band * 8u * rc.width;
+    const uint32_t rows = min(8u, rc.height - band * 8u);
+    *x = local / rows; *y = band * 8u + local % rows;
+}
 
-        // ---- light subpath
-        if (s.numTopLights > 0 || s.envPresent) {
-            const Rand4 l0 = bptRandom(rc, smp, 0x10000u);      // light selection, light position u0, u1
-            const Rand4 l1 = bptRandom(rc, smp, 0x10001u);      // EDF direction u0, u1
-            LightSample ls;
-            sampleLight(s, l0.x, l0.y, l0.z, smp.time, &ls);
-            const Spec<NC> Le0 = materialEmittance<NC>(s, ls.material, ls.sp, smp.wlOffset);
-            V3 org, dir;
-            float dirPDF, dirZ, tmin;
-            if (ls.isEnv) {
-                // InfiniteSphereSurfaceObject::sampleRay: parallel rays towards the scene through a disc of the world's radius
-                dirZ = 1.0f; dirPDF = 1.0f / worldDiscArea(s);
-                const V3 vz = ls.sp.sf.z;
-                V3 vx, vy;
-                makeCoordinateSystem(vz, &vx, &vy);
-                float dx, dy;
-                concentricSampleDisk(l1.x, l1.y, &dx, &dy);
-                const float R = s.worldRadius;
-                org = V3(s.worldCenter[0], s.worldCenter[1], s.worldCenter[2]) + (1.1f * R) * ls.sp.p + R * (dx * vx + dy * vy);
-                dir = vz; tmin = 0.0f;
-            } else {
-                const V3 d = cosineSampleHemisphere(l1.x, l1.y);      // DiffuseEDF::sample
-                dirZ = d.z; dirPDF = d.z / kPi;
-                org = ls.sp.p; dir = ls.sp.sf.fromLocal(d); tmin = 0.0001f;
-                if (ls.sp.inst != SLRGPU_INVALID_ID) {
-                    // TransformedSurfaceObject::sampleRay (SurfaceObject.cpp:374-391): the ray is built in the object's space
-                    // and then transformed -- its direction is NOT re-normalised, so under a scaled instance the first
-                    // segment of the light subpath carries the scale in |dir| (into the cosine of its throughput and into
-                    // dirOut_sn at its first hit), exactly as the reference's does
-                    const SlrGpuTriangle tri = s.triangles[ls.sp.prim];
-                    SurfPt obj;
-                    triangleFrame(loadTriangle(s, tri), ls.sp.u, ls.sp.v, 1.0f - ls.sp.u - ls.sp.v, false, &obj);
-                    float scratch[32];
-                    const InstanceXfm x = instanceTransformAt(s, s.instances[ls.sp.inst], smp.time, scratch);
-                    dir = xfmVector(x.mat, obj.sf.fromLocal(d));
-                }
-            }
-            const float lightAreaPDF = ls.lightPDF;
-            BptVertex<NC> v0;
-            v0.sp = ls.sp;
-            v0.dirIn = V3(0, 0, 0); v0.gn = V3(0, 0, 1);
-            v0.material = ls.material;
-            v0.kindFlags = ls.isEnv ? BV_EDF_IBL : BV_EDF_DIFFUSE;
-            v0.alpha = Le0 * (1.0f / lightAreaPDF);
-            storeVertex<NC>(st, lane, 1, 0, v0);
-            const float4 mis0 = make_float4(lightAreaPDF, 1.0f, CUDART_NAN_F, CUDART_NAN_F);
-            misRecord(st, lane, 1, 0) = mis0;
-            smp.numL = 1;
-            const Spec<NC> alpha = v0.alpha * ((1.0f / kPi) * (absDot(dir, ls.sp.gn) / dirPDF));
-            generateSubPath<NC>(s, rc, st, lane, 1, smp, org, dir, tmin, alpha, dirPDF, DT_Reflection | DT_LowFreq, dirZ,
-                                ls.sp.p, ls.sp.atInfinity, mis0, accum, stack, &counts, &overflow);
-        }
-
-        // ---- eye subpath
-        {
-            BptVertex<NC> v0;
-            v0.sp.p = cs.org; v0.sp.gn = cs.lensFrame.z; v0.sp.sf = cs.lensFrame;
-            v0.sp.u = cs.lensU; v0.sp.v = cs.lensV; v0.sp.tu = 0.0f; v0.sp.tv = 0.0f;
-            v0.sp.prim = SLRGPU_INVALID_ID; v0.sp.inst = SLRGPU_INVALID_ID; v0.sp.atInfinity = false;
-            v0.dirIn = V3(0, 0, 0); v0.gn = V3(0, 0, 1);
-            v0.material = SLRGPU_INVALID_ID;
-            v0.kindFlags = BV_IDF;
-            v0.alpha = specConst<NC>(1.0f / (rc.lensAreaPDF * rc.selectWLPDF));
-            storeVertex<NC>(st, lane, 0, 0, v0);
-            const float4 mis0 = make_float4(rc.lensAreaPDF, 1.0f, CUDART_NAN_F, CUDART_NAN_F);
-            misRecord(st, lane, 0, 0) = mis0;
-            if (!(s.camera.lens_radius > 0.0f)) smp.eyeDelta |= 1ull;       // posType Delta0D for a pinhole
-            smp.numE = 1;
-            const Spec<NC> alpha = v0.alpha * (absDot(cs.dir, cs.lensFrame.z) / cs.dirPDF);
-            generateSubPath<NC>(s, rc, st, lane, 0, smp, cs.org, cs.dir, 0.0f, alpha, cs.dirPDF, DT_Reflection | DT_LowFreq, cs.dirLocalZ,
-                                cs.org, false, mis0, accum, stack, &counts, &overflow);
-        }
-
-        // ---- connections
-        for (uint32_t t = 1; t <= smp.numE; ++t) {
-            BptVertex<NC> eVtx;
-            loadVertex<NC>(st, lane, 0, (int)t - 1, &eVtx);
-            Bsdf<NC, 4> eBsdf;
-            if (eVtx.kind() == BV_BSDF) buildBsdf<NC, 4>(s, eVtx.material, eVtx.sp, smp.wlOffset, (eVtx.wlFlags() & kWlLambdaIsSelected) != 0, &eBsdf);
-            for (uint32_t sIdx = 1; sIdx <= smp.numL; ++sIdx) {
-                connectVertices<NC>(s, rc, st, lane, smp, eVtx, eBsdf, t, sIdx, accum, stack, &counts, &overflow);
-                ++counts.connections;
-            }
-        }
-    }
+__device__ __forceinline__ void flushCounts(const BptLocalCounts& counts, bool overflow, BptCounters* counters) {
     // one atomic per warp and counter
     uint32_t e = counts.extendRays, sh = counts.shadowRays, cn = counts.connections, tr = counts.truncated;
 #pragma unroll
@@ -544,25 +465,212 @@ bptKernel(const DeviceScene s, const RenderConstants rc, BptStore st, float* __r
         cn += __shfl_xor_sync(0xFFFFFFFFu, cn, o); tr += __shfl_xor_sync(0xFFFFFFFFu, tr, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&counters->extendRays, (unsigned long long)e); atomicAdd(&counters->shadowRays, (unsigned long long)sh);
-        atomicAdd(&counters->connections, (unsigned long long)cn);
+        if (e) atomicAdd(&counters->extendRays, (unsigned long long)e);
+        if (sh) atomicAdd(&counters->shadowRays, (unsigned long long)sh);
+        if (cn) atomicAdd(&counters->connections, (unsigned long long)cn);
         if (tr) atomicAdd(&counters->truncated, (unsigned long long)tr);
     }
     if (overflow) atomicExch(&counters->stackOverflow, 1u);
 }
 
+template <int NC>
+__global__ void __launch_bounds__(kBptBlock, SLR_BPT_MIN_BLOCKS)
+subpathKernel(const DeviceScene s, const RenderConstants rc, BptStore st, BptBatch batch, float* __restrict__ accum, BptCounters* counters,
+              unsigned long long firstSample, uint32_t count) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;       // count is a multiple of the warp size or the last batch
+    const bool lightThread = tid >= st.lanes;
+    const uint32_t slot = lightThread ? tid - st.lanes : tid;
+    uint32_t stack[kStackSize];
+    bool overflow = false;
+    BptLocalCounts counts = {0, 0, 0, 0};
+    if (slot < count) {
+        uint32_t x, y, pass;
+        samplePixel(rc, firstSample + slot, &x, &y, &pass);
+        const uint32_t pixel = y * rc.width + x;
+        BptSample smp;
+        smp.pixelKey = pixel; smp.sample = rc.sppBegin + pass;
+        smp.eyeDelta = 0; smp.lightDelta = 0; smp.numE = 0; smp.numL = 0;
+        if (lightThread) {
+            // ---- light subpath; of the camera sample it needs the time, the wavelengths and the hero wavelength
+            const Rand4 r0 = pathRandom(rc.seed, pixel, smp.sample, 0);
+            const Rand4 r1 = pathRandom(rc.seed, pixel, smp.sample, 1);
+            smp.wlOffset = r0.w;
+            smp.time = rc.timeStart * (1 - r0.x) + rc.timeEnd * r0.x;
+            smp.hero = min((uint32_t)(NC * r1.x), (uint32_t)(NC - 1));
+            smp.sensorPixel = 0; smp.inPlace = false;
+            if (s.numTopLights > 0 || s.envPresent) {
+                const Rand4 l0 = bptRandom(rc, smp, 0x10000u);      // light selection, light position u0, u1
+                const Rand4 l1 = bptRandom(rc, smp, 0x10001u);      // EDF direction u0, u1
+                LightSample ls;
+                sampleLight(s, l0.x, l0.y, l0.z, smp.time, &ls);
+                const Spec<NC> Le0 = materialEmittance<NC>(s, ls.material, ls.sp, smp.wlOffset);
+                V3 org, dir;
+                float dirPDF, dirZ, tmin;
+                if (ls.isEnv) {
+                    // InfiniteSphereSurfaceObject::sampleRay: parallel rays towards the scene through a disc of the world's radius
+                    dirZ = 1.0f; dirPDF = 1.0f / worldDiscArea(s);
+                    const V3 vz = ls.sp.sf.z;
+                    V3 vx, vy;
+                    makeCoordinateSystem(vz, &vx, &vy);
+                    float dx, dy;
+                    concentricSampleDisk(l1.x, l1.y, &dx, &dy);
+                    const float R = s.worldRadius;
+                    org = V3(s.worldCenter[0], s.worldCenter[1], s.worldCenter[2]) + (1.1f * R) * ls.sp.p + R * (dx * vx + dy * vy);
+                    dir = vz; tmin = 0.0f;
+                } else {
+                    const V3 d = cosineSampleHemisphere(l1.x, l1.y);      // DiffuseEDF::sample
+                    dirZ = d.z; dirPDF = d.z / kPi;
+                    org = ls.sp.p; dir = ls.sp.sf.fromLocal(d); tmin = 0.0001f;
+                    if (ls.sp.inst != SLRGPU_INVALID_ID) {
+                        // TransformedSurfaceObject::sampleRay (SurfaceObject.cpp:374-391): the ray is built in the object's space
+                        // and then transformed -- its direction is NOT re-normalised, so under a scaled instance the first
+                        // segment of the light subpath carries the scale in |dir| (into the cosine of its throughput and into
+                        // dirOut_sn at its first hit), exactly as the reference's does
+                        const SlrGpuTriangle tri = s.triangles[ls.sp.prim];
+                        SurfPt obj;
+                        triangleFrame(loadTriangle(s, tri), ls.sp.u, ls.sp.v, 1.0f - ls.sp.u - ls.sp.v, false, &obj);
+                        float scratch[32];
+                        const InstanceXfm xf = instanceTransformAt(s, s.instances[ls.sp.inst], smp.time, scratch);
+                        dir = xfmVector(xf.mat, obj.sf.fromLocal(d));
+                    }
+                }
+                const float lightAreaPDF = ls.lightPDF;
+                BptVertex<NC> v0;
+                v0.sp = ls.sp;
+                v0.dirIn = V3(0, 0, 0); v0.gn = V3(0, 0, 1);
+                v0.material = ls.material;
+                v0.kindFlags = ls.isEnv ? BV_EDF_IBL : BV_EDF_DIFFUSE;
+                v0.alpha = Le0 * (1.0f / lightAreaPDF);
+                storeVertex<NC>(st, slot, 1, 0, v0);
+                const float4 mis0 = make_float4(lightAreaPDF, 1.0f, CUDART_NAN_F, CUDART_NAN_F);
+                misRecord(st, slot, 1, 0) = mis0;
+                smp.numL = 1;
+                const Spec<NC> alpha = v0.alpha * ((1.0f / kPi) * (absDot(dir, ls.sp.gn) / dirPDF));
+                generateSubPath<NC>(s, rc, st, slot, 1, smp, org, dir, tmin, alpha, dirPDF, DT_Reflection | DT_LowFreq, dirZ,
+                                    ls.sp.p, ls.sp.atInfinity, mis0, accum, stack, &counts, &overflow);
+            }
+            BptSlotEnd end;
+            end.delta = smp.lightDelta; end.num = smp.numL; end.pad = 0;
+            batch.lightEnd[slot] = end;
+        } else {
+            // ---- eye subpath: time, pixel position, wavelengths (Job::kernel, BidirectionalPathTracingRenderer.cpp:104-110), lens sample
+            CameraSample cs;
+            sampleCamera<NC>(s, rc, x, y, pixel, smp.sample, &cs);
+            smp.sensorPixel = cs.ipy * rc.width + cs.ipx;
+            smp.wlOffset = cs.wlOffset; smp.time = cs.time; smp.hero = cs.hero;
+            smp.inPlace = (cs.flags & kFlagStrataInPlace) != 0;
+            BptSlotCommon c;
+            c.pixelKey = smp.pixelKey; c.sample = smp.sample; c.sensorPixel = smp.sensorPixel;
+            c.heroInPlace = smp.hero | (smp.inPlace ? 0x100u : 0u);
+            c.wlOffset = smp.wlOffset; c.time = smp.time;
+            batch.common[slot] = c;
+            BptVertex<NC> v0;
+            v0.sp.p = cs.org; v0.sp.gn = cs.lensFrame.z; v0.sp.sf = cs.lensFrame;
+            v0.sp.u = cs.lensU; v0.sp.v = cs.lensV; v0.sp.tu = 0.0f; v0.sp.tv = 0.0f;
+            v0.sp.prim = SLRGPU_INVALID_ID; v0.sp.inst = SLRGPU_INVALID_ID; v0.sp.atInfinity = false;
+            v0.dirIn = V3(0, 0, 0); v0.gn = V3(0, 0, 1);
+            v0.material = SLRGPU_INVALID_ID;
+            v0.kindFlags = BV_IDF;
+            v0.alpha = specConst<NC>(1.0f / (rc.lensAreaPDF * rc.selectWLPDF));
+            storeVertex<NC>(st, slot, 0, 0, v0);
+            const float4 mis0 = make_float4(rc.lensAreaPDF, 1.0f, CUDART_NAN_F, CUDART_NAN_F);
+            misRecord(st, slot, 0, 0) = mis0;
+            if (!(s.camera.lens_radius > 0.0f)) smp.eyeDelta |= 1ull;       // posType Delta0D for a pinhole
+            smp.numE = 1;
+            const Spec<NC> alpha = v0.alpha * (absDot(cs.dir, cs.lensFrame.z) / cs.dirPDF);
+            generateSubPath<NC>(s, rc, st, slot, 0, smp, cs.org, cs.dir, 0.0f, alpha, cs.dirPDF, DT_Reflection | DT_LowFreq, cs.dirLocalZ,
+                                cs.org, false, mis0, accum, stack, &counts, &overflow);
+            BptSlotEnd end;
+            end.delta = smp.eyeDelta; end.num = smp.numE; end.pad = 0;
+            batch.eyeEnd[slot] = end;
+        }
+    }
+    flushCounts(counts, overflow, counters);
+}
+
+__global__ void __launch_bounds__(256)
+countKernel(BptBatch batch, uint32_t count) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot < count) batch.connCount[slot] = batch.eyeEnd[slot].num * batch.lightEnd[slot].num;
+}
+
+// exclusive prefix sums of connCount[0, count) into connBase[0, count], one block (a batch is a few hundred thousand slots)
+__global__ void __launch_bounds__(1024)
+scanKernel(BptBatch batch, uint32_t count) {
+    __shared__ uint32_t warpSums[32];
+    __shared__ uint32_t carry;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < count; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < count ? batch.connCount[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += n; }
+        if (lane == 31) warpSums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warpSums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, w, o); if ((int)lane >= o) w += n; }
+            warpSums[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t before = carry + (warp ? warpSums[warp - 1] : 0u) + incl - v;
+        if (i < count) batch.connBase[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) batch.connBase[count] = carry;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kBptBlock, SLR_BPT_MIN_BLOCKS)
+connectKernel(const DeviceScene s, const RenderConstants rc, BptStore st, BptBatch batch, float* __restrict__ accum, BptCounters* counters, uint32_t count) {
+    uint32_t stack[kStackSize];
+    bool overflow = false;
+    BptLocalCounts counts = {0, 0, 0, 0};
+    const uint32_t total = batch.connBase[count];
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < total; c += gridDim.x * blockDim.x) {
+        // the slot whose range [connBase[slot], connBase[slot + 1]) holds c
+        uint32_t lo = 0, hi = count;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (batch.connBase[mid] <= c) lo = mid; else hi = mid; }
+        const uint32_t slot = lo;
+        const BptSlotCommon cm = batch.common[slot];
+        const BptSlotEnd ee = batch.eyeEnd[slot], le = batch.lightEnd[slot];
+        BptSample smp;
+        smp.pixelKey = cm.pixelKey; smp.sample = cm.sample; smp.sensorPixel = cm.sensorPixel;
+        smp.hero = cm.heroInPlace & 0xFFu; smp.inPlace = (cm.heroInPlace & 0x100u) != 0;
+        smp.wlOffset = cm.wlOffset; smp.time = cm.time;
+        smp.eyeDelta = ee.delta; smp.lightDelta = le.delta; smp.numE = ee.num; smp.numL = le.num;
+        const uint32_t k = c - batch.connBase[slot];
+        const uint32_t t = k / le.num + 1u, sIdx = k % le.num + 1u;
+        BptVertex<NC> eVtx;
+        loadVertex<NC>(st, slot, 0, (int)t - 1, &eVtx);
+        Bsdf<NC, 4> eBsdf;
+        if (eVtx.kind() == BV_BSDF) buildBsdf<NC, 4>(s, eVtx.material, eVtx.sp, smp.wlOffset, (eVtx.wlFlags() & kWlLambdaIsSelected) != 0, &eBsdf);
+        connectVertices<NC>(s, rc, st, slot, smp, eVtx, eBsdf, t, sIdx, accum, stack, &counts, &overflow);
+        ++counts.connections;
+    }
+    flushCounts(counts, overflow, counters);
+}
+
 // ---------------------------------------------------------------------------------------------
-// host side: vertex storage per device (kept for later calls), launch, statistics
+// host side: vertex storage per device (kept for later calls), the batch loop, statistics
 // ---------------------------------------------------------------------------------------------
+constexpr uint32_t kBptBatchSlots = 1u << 18;        // 262 144 samples per batch: 6.7 GB of vertex storage in spectral mode
+
 struct BptWorkspace {
     BptStore store = {};
+    BptBatch batch = {};
     BptCounters* dCounters = nullptr;
     size_t vertWords = 0;
     void release() {
-        if (store.verts) cudaFree(store.verts);
-        if (store.mis) cudaFree(store.mis);
-        if (dCounters) cudaFree(dCounters);
-        store = {}; dCounters = nullptr; vertWords = 0;
+        void* ptrs[] = {store.verts, store.mis, batch.common, batch.eyeEnd, batch.lightEnd, batch.connCount, batch.connBase, dCounters};
+        for (void* q : ptrs) if (q) cudaFree(q);
+        store = {}; batch = {}; dCounters = nullptr; vertWords = 0;
     }
 };
 static std::mutex g_bptMutex;
@@ -576,12 +684,7 @@ void releaseBptWorkspaces() {
 
 template <int NC>
 static int renderBptT(SlrGpuScene* sc, const RenderConstants& rc, unsigned long long totalSamples, float* accumDev, cudaStream_t stream, SlrGpuRenderStats* stats) {
-    int perSM = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, bptKernel<NC>, kBptBlock, 0) != cudaSuccess || perSM < 1) { cudaGetLastError(); perSM = 1; }
-    unsigned long long blocks = (unsigned long long)sc->numSMs * (unsigned long long)perSM;
-    const unsigned long long need = (totalSamples + kBptBlock - 1) / kBptBlock;
-    if (blocks > need) blocks = need;
-    const uint32_t lanes = (uint32_t)blocks * kBptBlock;
+    const uint32_t slots = (uint32_t)std::min<unsigned long long>(kBptBatchSlots, (totalSamples + 127ull) & ~127ull);
 
     BptWorkspace* w = nullptr;
     {
@@ -597,13 +700,18 @@ static int renderBptT(SlrGpuScene* sc, const RenderConstants& rc, unsigned long 
             else { w->release(); delete w; }
         }
     } release{sc->device, w};
-    const size_t vertWords = (size_t)2 * kBptMaxVerts * bptVertexWords<NC>() * lanes;
-    if (w->store.lanes != lanes || w->vertWords != vertWords) {
+    const size_t vertWords = (size_t)2 * kBptMaxVerts * bptVertexWords<NC>() * slots;
+    if (w->store.lanes != slots || w->vertWords != vertWords) {
         w->release();
         SLRGPU_CUDA_TRY(cudaMalloc(&w->store.verts, vertWords * sizeof(float4)));
-        SLRGPU_CUDA_TRY(cudaMalloc(&w->store.mis, (size_t)2 * kBptMaxVerts * lanes * sizeof(float4)));
+        SLRGPU_CUDA_TRY(cudaMalloc(&w->store.mis, (size_t)2 * kBptMaxVerts * slots * sizeof(float4)));
+        SLRGPU_CUDA_TRY(cudaMalloc(&w->batch.common, (size_t)slots * sizeof(BptSlotCommon)));
+        SLRGPU_CUDA_TRY(cudaMalloc(&w->batch.eyeEnd, (size_t)slots * sizeof(BptSlotEnd)));
+        SLRGPU_CUDA_TRY(cudaMalloc(&w->batch.lightEnd, (size_t)slots * sizeof(BptSlotEnd)));
+        SLRGPU_CUDA_TRY(cudaMalloc(&w->batch.connCount, (size_t)slots * sizeof(uint32_t)));
+        SLRGPU_CUDA_TRY(cudaMalloc(&w->batch.connBase, ((size_t)slots + 1) * sizeof(uint32_t)));
         SLRGPU_CUDA_TRY(cudaMalloc(&w->dCounters, sizeof(BptCounters)));
-        w->store.lanes = lanes; w->vertWords = vertWords;
+        w->store.lanes = slots; w->vertWords = vertWords;
     }
     SLRGPU_CUDA_TRY(cudaMemsetAsync(w->dCounters, 0, sizeof(BptCounters), stream));
     cudaEvent_t ev0, ev1;
@@ -611,7 +719,17 @@ static int renderBptT(SlrGpuScene* sc, const RenderConstants& rc, unsigned long 
     SLRGPU_CUDA_TRY(cudaEventCreate(&ev1));
     struct EventFree { cudaEvent_t a, b; ~EventFree() { cudaEventDestroy(a); cudaEventDestroy(b); } } eventFree{ev0, ev1};
     SLRGPU_CUDA_TRY(cudaEventRecord(ev0, stream));
-    bptKernel<NC><<<(uint32_t)blocks, kBptBlock, 0, stream>>>(sc->dev, rc, w->store, accumDev, w->dCounters, totalSamples);
+    const uint32_t connectGrid = residentGrid(connectKernel<NC>, kBptBlock, sc->numSMs, 1u << 20);
+    unsigned long long launches = 0;
+    for (unsigned long long first = 0; first < totalSamples; first += slots) {
+        const uint32_t count = (uint32_t)std::min<unsigned long long>(slots, totalSamples - first);
+        // thread i < slots: eye subpath of slot i, thread slots + i: its light subpath
+        subpathKernel<NC><<<2u * slots / kBptBlock, kBptBlock, 0, stream>>>(sc->dev, rc, w->store, w->batch, accumDev, w->dCounters, first, count);
+        countKernel<<<(count + 255u) / 256u, 256, 0, stream>>>(w->batch, count);
+        scanKernel<<<1, 1024, 0, stream>>>(w->batch, count);
+        connectKernel<NC><<<connectGrid, kBptBlock, 0, stream>>>(sc->dev, rc, w->store, w->batch, accumDev, w->dCounters, count);
+        launches += 4;
+    }
     SLRGPU_CUDA_TRY(cudaGetLastError());
     SLRGPU_CUDA_TRY(cudaEventRecord(ev1, stream));
     SLRGPU_CUDA_TRY(cudaEventSynchronize(ev1));
@@ -622,8 +740,8 @@ static int renderBptT(SlrGpuScene* sc, const RenderConstants& rc, unsigned long 
         stats->paths = totalSamples;
         stats->extend_rays = c.extendRays; stats->shadow_rays = c.shadowRays;
         stats->rays = c.extendRays + c.shadowRays;
-        stats->kernel_launches = 1;
-        stats->waves = 1;
+        stats->kernel_launches = launches;
+        stats->waves = launches / 4;            // batches
         stats->tail_paths = c.truncated;        // subpaths cut at kBptMaxVerts vertices
         stats->class_hits[8] = c.connections;   // (s, t) pairs examined
         cudaEventElapsedTime(&stats->device_ms, ev0, ev1);

@@ -66,7 +66,10 @@ def test_bpt_image_matches_golden_block_means(name, workdir):
         # +3.7 % of green), and 8 seeds do not pin the spread of such a block
         assert bad.mean() <= 0.02, f"{bad.sum()} of {bad.size} block means outside 6 sigma + 1 %: worst {np.max(err / tol):.2f}x"
         ratio = got.mean((0, 1)) / want.mean((0, 1))
-        assert np.all(np.abs(ratio - 1.0) < 0.01), f"image mean ratio {ratio}"
+        # 1 % + six standard errors of the image mean itself (negligible except for `scatter`, whose heavy-tailed
+        # light-tracing splats leave 0.5-0.8 % of noise in the mean of a 4096-spp image)
+        mean_sigma = np.sqrt((sig ** 2).sum((0, 1))) / (sig.shape[0] * sig.shape[1]) / want.mean((0, 1))
+        assert np.all(np.abs(ratio - 1.0) < 0.01 + 6.0 * mean_sigma), f"image mean ratio {ratio}"
     within(g)
     if name not in ("lamps", "scatter"):      # where the reference's two renderers agree: the path tracer's golden too
         within(np.load(os.path.join(ru.GOLDEN, f"render_{name}.npz")))
