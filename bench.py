@@ -11,6 +11,8 @@ Workloads
               spectral -- the configuration north_star's >= 100x target is quoted on; metric Mpaths/s
               (slr_b200/render_bench.py).
   materials | ibl | instanced   BASELINE configs[1..3] through the same code (slr_b200/render_bench.py WORKLOADS).
+  cornell_spheres_bpt   the same scene through the GPU twin of the reference's BidirectionalPathTracingRenderer -- the renderer
+              the shipped scene file selects -- next to the reference's own (slr_b200/bpt_bench.py); metric Msamples/s.
   intersect   incoherent-ray closest-hit microbench (BASELINE.json configs[4] at a single-GPU size):
               heightfield triangle mesh -> host SBVH -> QBVH, random rays; metric Mrays/s.
 
@@ -278,6 +280,9 @@ def main():
         render_bench = None
     if args.workload is None:
         args.workload = "cornell_spheres" if render_bench is not None else "intersect"
+    if args.workload == "cornell_spheres_bpt":
+        from slr_b200 import bpt_bench
+        return bpt_bench.main(args, rank, world)
     if args.workload != "intersect":
         if render_bench is None:
             raise SystemExit(f"workload {args.workload} needs the renderer")

@@ -32,7 +32,7 @@ constexpr int kBptMaxVerts = 64;
 constexpr int kBptBlock = 128;
 // resident blocks per SM the kernel's register allocation is bounded for (tuning knob, profiles/r02_bpt.md)
 #ifndef SLR_BPT_MIN_BLOCKS
-#define SLR_BPT_MIN_BLOCKS 2
+#define SLR_BPT_MIN_BLOCKS 4
 #endif
 constexpr uint32_t kWlLambdaIsSelected = 1u;       // WavelengthSamples::LambdaIsSelected
 
