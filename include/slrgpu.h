@@ -96,11 +96,14 @@ typedef struct SlrGpuSbvhNode {
 
 /* One TransformedSurfaceObject (SurfaceObject.cpp:303-392) over a nested aggregate.
  * Matrices are column-major (element (r,c) at [4*c + r]) like Matrix4x4 (Matrix4x4.h:23-38).
- * LIMIT: one level of instancing. An instance record may only appear in the top-level BVH; a nested aggregate's leaf
- * records must all be triangles (the reference recurses to any depth, SurfaceObject.cpp:307-336). The host library and
- * the reference-side exporter reject deeper nesting when they flatten a scene, and slrgpu_scene_create walks every nested
- * BVH and returns SLRGPU_ERR_UNSUPPORTED for an instance record inside one. Hit records, surface points and light
- * sampling all assume the limit (one instance id per hit). */
+ * ONE LEVEL ON THE DEVICE: an instance record may only appear in the top-level BVH; a nested aggregate's leaf records must
+ * all be triangles (slrgpu_scene_create walks every nested BVH and returns SLRGPU_ERR_UNSUPPORTED for an instance record
+ * inside one; hit records, surface points and light sampling carry one instance id per hit). The reference recurses to
+ * any depth (SurfaceObject.cpp:307-336): the producer of the tables expands a chain instead -- an instance found inside a
+ * referenced subtree is placed again under (outer transform x its own), the subtree's own triangles become an aggregate
+ * of their own. The host library does that when it flattens a scene (host/scene.h PlacedSubtree: same closest hits up to
+ * the rounding of the composed matrix, same light-selection probabilities); the reference-side exporter still rejects
+ * nesting. */
 typedef struct SlrGpuInstance {
     float mat[16];          /* local -> parent */
     float mat_inv[16];      /* parent -> local, as computed by the host's invert() */

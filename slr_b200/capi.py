@@ -313,6 +313,15 @@ class HostScene:
         n = self.desc.num_leaf_records
         return np.ctypeslib.as_array(C.cast(self.desc.leaf_records, PU32), shape=(n, 12)).copy()
 
+    def lights_array(self):
+        """The light lists (top-level entries first) as a structured array with the fields of SlrGpuLight."""
+        n = self.desc.num_lights
+        dt = np.dtype([("object", np.uint32), ("importance", np.float32), ("pmf", np.float32), ("cdf_lo", np.float32),
+                       ("cdf_hi", np.float32), ("pad", np.uint32, (3,))])
+        assert dt.itemsize == C.sizeof(Light)
+        raw = np.ctypeslib.as_array(C.cast(self.desc.lights, C.POINTER(C.c_uint8)), shape=(n * dt.itemsize,)).copy()
+        return raw.view(dt)
+
 
 class SceneBuilder:
     """Programmatic scene graph (the subset of the scene language's builtins needed for geometry)."""

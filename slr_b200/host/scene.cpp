@@ -68,13 +68,11 @@ void InternalNode::getRenderingData(GpuSceneBuilder& b, const StaticTransform* s
     RenderingData sub;
     for (const NodeRef& c : m_children) c->getRenderingData(b, nullptr, &sub);
     if (!sub.objects.empty()) {
-        for (const ObjectRef& o : sub.objects)
-            if (o.isInstance && b.instanceIsAnimated(o.id))
-                throw std::runtime_error("an animated node inside an animated node (a chain of two moving transforms) is not supported");
-        const uint32_t aggregate = b.createAggregate(std::move(sub.objects));
+        PlacedSubtree subtree;
+        b.prepare(subtree, std::move(sub.objects));
         StaticTransform tf(reduced->begin.mat, reduced->begin.matInv);
         tf.anim = reduced;
-        data->objects.push_back(ObjectRef{true, b.addInstance(aggregate, tf)});
+        b.place(subtree, tf, &data->objects);
     }
     if (sub.camera) {
         // the camera rides on the animated node: animated * (static camera transform) (createByMulRight, Transform.cpp:70-72)
@@ -137,15 +135,13 @@ void TriangleMeshNode::getRenderingData(GpuSceneBuilder& b, const StaticTransfor
 }
 
 void ReferenceNode::getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) {
-    if (!m_ready) {
+    if (!m_subtree.ready) {
         RenderingData sub;
         m_node->getRenderingData(b, nullptr, &sub);
         if (sub.objects.empty()) throw std::runtime_error("ReferenceNode refers to a subtree without surfaces");
-        m_aggregate = b.createAggregate(std::move(sub.objects));
-        m_ready = true;
+        b.prepare(m_subtree, std::move(sub.objects));
     }
-    StaticTransform tf = subTF ? *subTF : StaticTransform();
-    data->objects.push_back(ObjectRef{true, b.addInstance(m_aggregate, tf)});
+    b.place(m_subtree, subTF ? *subTF : StaticTransform(), &data->objects);
 }
 
 void CameraNode::getRenderingData(GpuSceneBuilder&, const StaticTransform* subTF, RenderingData* data) {
@@ -241,6 +237,44 @@ uint32_t GpuSceneBuilder::createAggregate(std::vector<ObjectRef>&& objects) {
         for (size_t i = 0; i < n; ++i) { ag.lights[i].cdf_lo = cdf[i]; ag.lights[i].cdf_hi = cdf[i + 1]; }
     }
     return id;
+}
+
+void GpuSceneBuilder::prepare(PlacedSubtree& ps, std::vector<ObjectRef>&& objects) {
+    std::vector<ObjectRef> triangles;
+    for (const ObjectRef& o : objects) {
+        if (o.isInstance) ps.nested.push_back(o.id);
+        else triangles.push_back(o);
+    }
+    ps.hasTriangles = !triangles.empty();
+    if (ps.hasTriangles) ps.triangleAggregate = createAggregate(std::move(triangles));
+    ps.ready = true;
+}
+
+void GpuSceneBuilder::place(const PlacedSubtree& ps, const StaticTransform& tf, std::vector<ObjectRef>* out) {
+    if (ps.hasTriangles) out->push_back(ObjectRef{true, addInstance(ps.triangleAggregate, tf)});
+    for (uint32_t t : ps.nested) {
+        // the template's own transform (inside the subtree's space), then the subtree's placement
+        Mat4 m, mi;
+        std::memcpy(static_cast<void*>(&m), flat.instances[t].mat, sizeof(float) * 16);
+        std::memcpy(static_cast<void*>(&mi), flat.instances[t].mat_inv, sizeof(float) * 16);
+        const StaticTransform inner(m, mi);
+        const std::shared_ptr<const AnimatedTransform> innerAnim = instanceAnim[t];
+        StaticTransform composed;
+        if (tf.anim && innerAnim)
+            throw std::runtime_error("an animated node inside an animated node (a chain of two moving transforms) is not supported");
+        if (tf.anim) {
+            const std::shared_ptr<const AnimatedTransform> a = tf.anim->mulRight(inner);       // animated * static (Transform.cpp:70-72)
+            composed = StaticTransform(a->begin.mat, a->begin.matInv);
+            composed.anim = a;
+        } else if (innerAnim) {
+            const std::shared_ptr<const AnimatedTransform> a = innerAnim->mulLeft(tf);         // static * animated (Transform.cpp:67-69)
+            composed = StaticTransform(a->begin.mat, a->begin.matInv);
+            composed.anim = a;
+        } else {
+            composed = tf * inner;        // the inverse recomputed from the product, as StaticTransform's operator* does
+        }
+        out->push_back(ObjectRef{true, addInstance(instanceAggregate[t], composed)});
+    }
 }
 
 uint32_t GpuSceneBuilder::addInstance(uint32_t aggregate, const StaticTransform& tf) {

@@ -44,6 +44,22 @@ struct ObjectRef {
     uint32_t id;            // triangle prim_id, or instance id
 };
 
+// A subtree flattened in its own space, ready to be placed any number of times (ReferenceNode, animated nodes): its own
+// triangles as one aggregate plus the instances found INSIDE it (instancing nested in instancing), kept as templates.
+// place() appends what the parent sees: an instance of the triangle aggregate under `tf` and, for every nested template, an
+// instance of that template's aggregate under tf * template -- the reference walks the same chain of
+// TransformedSurfaceObjects recursively (SurfaceObject.cpp:307-336); composing the transforms on the host keeps the
+// device traversal at one level for any nesting depth. Light-selection probabilities are unchanged by the expansion:
+// an aggregate's importance is the sum of its lights' (SurfaceObject.cpp:232-252, 283-285), so the product of the
+// pmfs along a chain equals the pmf of the expanded entry.
+struct PlacedSubtree {
+    bool ready = false;
+    bool hasTriangles = false;
+    uint32_t triangleAggregate = 0;
+    std::vector<uint32_t> nested;            // template instance ids (never referenced by a leaf record themselves)
+    bool empty() const { return !hasTriangles && nested.empty(); }
+};
+
 struct RenderingData {
     std::vector<ObjectRef> objects;
     std::shared_ptr<PerspectiveCamera> camera;
@@ -107,13 +123,12 @@ typedef std::shared_ptr<TriangleMeshNode> TriangleMeshNodeRef;
 
 class ReferenceNode : public Node {
     NodeRef m_node;
-    bool m_ready = false;
-    uint32_t m_aggregate = 0;
+    PlacedSubtree m_subtree;
 public:
     explicit ReferenceNode(const NodeRef& n) : m_node(n) {}
     bool isInstanced() const override { return true; }
     void getRenderingData(GpuSceneBuilder& b, const StaticTransform* subTF, RenderingData* data) override;
-    void resetFlattening() override { m_ready = false; m_aggregate = 0; m_node->resetFlattening(); }
+    void resetFlattening() override { m_subtree = PlacedSubtree(); m_node->resetFlattening(); }
 };
 
 class CameraNode : public Node {
@@ -206,6 +221,8 @@ public:
     explicit GpuSceneBuilder(FlatScene& f) : flat(f) {}
     // Builds trees + light list for `objects`; returns the aggregate id.
     uint32_t createAggregate(std::vector<ObjectRef>&& objects);
+    void prepare(PlacedSubtree& ps, std::vector<ObjectRef>&& objects);
+    void place(const PlacedSubtree& ps, const StaticTransform& tf, std::vector<ObjectRef>* out);
     // tf.anim set: the instance moves (its record refers to a new entry of flat.motions)
     uint32_t addInstance(uint32_t aggregate, const StaticTransform& tf);
     uint32_t addMotion(const AnimatedTransform& a);       // returns 1 + index

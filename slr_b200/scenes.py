@@ -388,6 +388,62 @@ def _small_instanced(directory, width=128, height=128, spp=64):
     return write_instanced(directory, width, height, spp, base_segments=(48, 24), grid=4)
 
 
+def write_nested(directory, width=128, height=128, spp=64):
+    """Instancing nested in instancing (TransformedSurfaceObject over an aggregate that itself holds TransformedSurfaceObjects,
+    SurfaceObject.cpp:307-336): a `cluster` = three references to the bumpy ball (rotated / scaled) + a pedestal of its own
+    triangles + a small emitting panel of its own, referenced three times from the root (rotated, one of them scaled), over a
+    ground quad under a dim ceiling light. The panels are lights two instance levels below the root for the balls' shading and
+    one level below for selection. No emitter sits under a scale (the reference's area pdfs are object-space)."""
+    os.makedirs(os.path.join(directory, "models"), exist_ok=True)
+    pos, idx, nrm, tng, uv = synth.displaced_sphere(40, 20)
+    capi.write_assbin(os.path.join(directory, "models", "bumpy_ball.assbin"), pos, idx, nrm, tng, uv, material_name="ball", diffuse=(0.7, 0.7, 0.7))
+    t = f'setRenderer("method": "PT", ("samples": {spp},));\nsetRenderSettings("width": {width}, "height": {height});\n\n'
+    ext = 9.0
+    t += "groundNode = createNode();\nsetTransform(groundNode, translate(0, 0, 0));\n"
+    t += _quad("ground", [(-ext, 0, ext), (ext, 0, ext), (ext, 0, -ext), (-ext, 0, -ext)], (0, 1, 0), (1, 0, 0),
+               ['diffuseTex = SpectrumTexture("checker board", (Spectrum(0.7, 0.7, 0.7), Spectrum(0.3, 0.3, 0.35)));',
+                'surfMat = createSurfaceMaterial("matte", (diffuseTex,));']).replace("CBNode", "groundNode")
+    light = ['scatterMat = createSurfaceMaterial("matte", (SpectrumTexture(Spectrum(0.9, 0.9, 0.9)),));',
+             'emitterMat = createEmitterSurfaceProperty("diffuse", (SpectrumTexture(Spectrum("ID": "D65") * 1.5),));',
+             'surfMat = createSurfaceMaterial("emitter", (scatterMat, emitterMat));']
+    t += _quad("lightMesh", [(-3, 8, -3), (3, 8, -3), (3, 8, 3), (-3, 8, 3)], (0, -1, 0), (1, 0, 0), light).replace("CBNode", "groundNode")
+    t += "addChild(root, groundNode);\n\n"
+    t += """function ballMat(name, attrs) {
+    difTex = SpectrumTexture(Spectrum(0.75, 0.55, 0.3));
+    return createSurfaceMaterial("matte", (difTex,));
+}
+ballNode = load3DModel("models/bumpy_ball.assbin", ballMat);
+ballRef = createReferenceNode(ballNode);
+clusterNode = createNode();
+setTransform(clusterNode, translate(0, 0, 0));
+"""
+    for k, (x, y, z, rot, sc) in enumerate([(-0.9, 0.85, 0.0, 0.3, 0.55), (0.9, 0.95, 0.2, 1.7, 0.65), (0.0, 0.8, -0.9, 4.0, 0.5)]):
+        t += (f"b{k} = createNode();\naddChild(b{k}, ballRef);\n"
+              f"setTransform(b{k}, translate({x}, {y}, {z}) * rotateY({rot}) * scale({sc}));\naddChild(clusterNode, b{k});\n")
+    t += "pedestalNode = createNode();\nsetTransform(pedestalNode, translate(0, 0, 0));\n"
+    t += _quad("pedestal", [(-1.6, 0.25, 1.6), (1.6, 0.25, 1.6), (1.6, 0.25, -1.6), (-1.6, 0.25, -1.6)], (0, 1, 0), (1, 0, 0),
+               ['surfMat = createSurfaceMaterial("matte", (SpectrumTexture(Spectrum(0.25, 0.5, 0.7)),));']).replace("CBNode", "pedestalNode")
+    panel = ['scatterMat = createSurfaceMaterial("matte", (SpectrumTexture(Spectrum(0.8, 0.8, 0.8)),));',
+             'emitterMat = createEmitterSurfaceProperty("diffuse", (SpectrumTexture(Spectrum("ID": "D65") * 12),));',
+             'surfMat = createSurfaceMaterial("emitter", (scatterMat, emitterMat));']
+    t += _quad("panel", [(-0.35, 2.2, -0.35), (0.35, 2.2, -0.35), (0.35, 2.2, 0.35), (-0.35, 2.2, 0.35)], (0, -1, 0), (1, 0, 0), panel).replace("CBNode", "pedestalNode")
+    t += "addChild(clusterNode, pedestalNode);\nclusterRef = createReferenceNode(clusterNode);\n"
+    for k, (x, z, rot) in enumerate([(-3.4, 0.5, 0.4), (3.2, -0.6, 2.2), (0.2, -3.6, 5.1)]):
+        t += (f"c{k} = createNode();\naddChild(c{k}, clusterRef);\n"
+              f"setTransform(c{k}, translate({x}, 0.0, {z}) * rotateY({rot}));\naddChild(root, c{k});\n")
+    t += f"""
+cameraNode = createNode();
+camera = createPerspectiveCamera("aspect": {width / height:.6f}, "fovY": 0.75, "radius": 0.01, "imgDist": 1.0, "objDist": 11.0);
+addChild(cameraNode, camera);
+setTransform(cameraNode, translate(0.0, 6.0, 9.5) * rotateY(3.1415926536) * rotateX(0.5));
+addChild(root, cameraNode);
+"""
+    path = os.path.join(directory, "Nested_Instances.txt")
+    with open(path, "w") as f:
+        f.write(t)
+    return path
+
+
 def write_scatter(directory, width=128, height=128, spp=64, grid=14):
     """The structure of TestScenes/RTC3.txt at a small scale: a terrain mesh, grid x grid instances of a tuft mesh scattered
     over it by scanXZFromYPlus (a ray cast while the file is read; the callback aligns each instance with the surface normal
@@ -679,6 +735,7 @@ SCENES = {
     "instanced": _small_instanced,
     "scatter": write_scatter,
     "lamps": write_lamps,
+    "nested": write_nested,
     "instanced_full": write_instanced,
     "instanced_10m": lambda d, width=1920, height=1080, spp=1024: write_instanced(d, width, height, spp, base_segments=(318, 159)),
 }

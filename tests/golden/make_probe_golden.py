@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import render_util as ru  # noqa: E402
 from slr_b200 import capi  # noqa: E402
 
-SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced", "cutout", "textured", "motion"]
+SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced", "cutout", "textured", "motion", "nested"]
 N, SEED = 2048, 20261018
 
 

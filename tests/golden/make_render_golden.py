@@ -27,7 +27,7 @@ import render_util as ru  # noqa: E402
 from slr_b200 import capi  # noqa: E402
 
 SIZE, BLOCK, SEEDS, SPP_EACH, GPU_SPP = 64, 8, 8, 2048, 16384
-SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced", "scatter", "lamps", "cutout", "textured", "motion"]
+SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced", "scatter", "lamps", "cutout", "textured", "motion", "nested"]
 
 
 def main():

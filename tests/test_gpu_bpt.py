@@ -46,7 +46,7 @@ def _bpt_rgb(path, size, spp):
     return capi.accum_to_rgb(accum, 1.0 / spp), st
 
 
-@pytest.mark.parametrize("name", ["diffuse", "spheres", "materials", "ibl", "instanced", "scatter", "lamps", "cutout", "textured", "motion"])
+@pytest.mark.parametrize("name", ["diffuse", "spheres", "materials", "ibl", "instanced", "scatter", "lamps", "cutout", "textured", "motion", "nested"])
 def test_bpt_image_matches_golden_block_means(name, workdir):
     g = np.load(os.path.join(ru.GOLDEN, f"render_bpt_{name}.npz"))
     size, block = int(g["size"]), int(g["block"])

@@ -18,7 +18,7 @@ import render_util as ru
 from slr_b200 import capi
 
 pytestmark = pytest.mark.gpu
-SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced", "cutout", "textured", "motion"]
+SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced", "cutout", "textured", "motion", "nested"]
 
 
 @pytest.fixture(scope="module", autouse=True)

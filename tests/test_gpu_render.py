@@ -43,7 +43,7 @@ def _gpu_rgb(path, size, spp, **kw):
 
 
 @pytest.mark.parametrize("name,size,spp", [("diffuse", 96, 256), ("spheres", 128, 256), ("materials", 128, 256), ("ibl", 128, 256),
-                                           ("instanced", 128, 128), ("cutout", 128, 256), ("textured", 128, 256), ("motion", 128, 256)])
+                                           ("instanced", 128, 128), ("cutout", 128, 256), ("textured", 128, 256), ("motion", 128, 256), ("nested", 128, 256)])
 def test_image_matches_reference_within_noise_floor(name, size, spp, workdir):
     if not ru.have_ref_render():
         pytest.skip("oracle/_ref/ref_render not built")
@@ -97,7 +97,7 @@ def test_unchanged_reference_scene_file_renders_like_the_reference(name, size, s
     assert bgot <= 1.5 * bfloor + 0.002, f"16x16-block relRMSE {bgot:.4f} vs floor {bfloor:.4f}"
 
 
-@pytest.mark.parametrize("name", ["diffuse", "spheres", "materials", "ibl", "instanced", "scatter", "lamps", "cutout", "textured", "motion"])
+@pytest.mark.parametrize("name", ["diffuse", "spheres", "materials", "ibl", "instanced", "scatter", "lamps", "cutout", "textured", "motion", "nested"])
 def test_image_matches_golden_block_means(name, workdir):
     f = os.path.join(ru.GOLDEN, f"render_{name}.npz")
     g = np.load(f)

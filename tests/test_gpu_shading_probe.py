@@ -23,7 +23,7 @@ import render_util as ru
 from slr_b200 import capi
 
 pytestmark = pytest.mark.gpu
-SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced", "cutout", "textured", "motion"]
+SCENES = ["diffuse", "spheres", "materials", "ibl", "instanced", "cutout", "textured", "motion", "nested"]
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -36,12 +36,18 @@ def workdir(tmp_path_factory):
     return str(tmp_path_factory.mktemp("probe_scenes"))
 
 
-def check(got, want):
+def check(got, want, composed_transforms=False):
+    """composed_transforms (`nested`): instancing nested in instancing reaches the device as ONE level with the transforms of
+    a chain multiplied on the host (host/scene.h PlacedSubtree), where the reference transforms the ray once per level: the
+    hit is the same, its distance and frame agree to rounding instead of bit for bit."""
     r = ru.compare_probes(got, want, rel=1e-4)
     loose = ru.compare_probes(got, want, rel=2e-3)
-    assert r["status_mismatch"] == 0.0 and r["nondelta_mismatch"] == 0.0 and r["emitting_mismatch"] == 0.0, r
-    assert r["t_worst_rel"] == 0.0, r
-    assert r["frame_worst_abs"] <= 5e-6, r
+    assert r["nondelta_mismatch"] == 0.0 and r["emitting_mismatch"] == 0.0, r
+    if composed_transforms:
+        assert r["status_mismatch"] <= 0.001 and r["t_worst_rel"] <= 1e-3 and r["frame_worst_abs"] <= 5e-5, r      # distances: tests/test_nested_instancing.py
+    else:
+        assert r["status_mismatch"] == 0.0 and r["t_worst_rel"] == 0.0, r
+        assert r["frame_worst_abs"] <= 5e-6, r
     assert r["sample_type_mismatch"] <= 0.002, r
     assert r["sample_value_mismatch"] <= 0.005 and r["eval_mismatch"] <= 0.005, r
     assert loose["sample_value_mismatch"] <= 0.001 and loose["eval_mismatch"] <= 0.001, loose
@@ -61,7 +67,7 @@ def test_probe_matches_golden(name, workdir):
     g = np.load(os.path.join(ru.GOLDEN, f"probe_{name}.npz"))
     _, hs, gs = gpu_scene(name, workdir)
     got = capi.probe_shading(gs, g["probes"])
-    r = check(got, g["reference"])
+    r = check(got, g["reference"], composed_transforms=name == "nested")
     assert r["hits"] >= 500
 
 
@@ -72,7 +78,7 @@ def test_probe_matches_live_reference(name, workdir):
     path, hs, gs = gpu_scene(name, workdir)
     center = [hs.desc.world_center[i] for i in range(3)]
     probes = ru.make_probes(center, hs.desc.world_radius, 20000, 7)
-    check(capi.probe_shading(gs, probes), ru.run_ref_probe(path, probes))
+    check(capi.probe_shading(gs, probes), ru.run_ref_probe(path, probes), composed_transforms=name == "nested")
 
 
 def test_probe_argument_errors(workdir):
