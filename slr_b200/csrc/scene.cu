@@ -451,7 +451,7 @@ SLRGPU_API int slrgpu_device_count(void) {
     return n;
 }
 
-SLRGPU_API uint32_t slrgpu_abi_version(void) { return (1u << 16) | 1u; }      // 1.1: SBVH tables, slrgpu_render_multi
+SLRGPU_API uint32_t slrgpu_abi_version(void) { return (1u << 16) | 2u; }      // 1.1: SBVH tables, slrgpu_render_multi; 1.2: SLRGPU_RENDER_BPT, slrgpu_probe_shading_bpt
 
 SLRGPU_API const char* slrgpu_last_error(void) { return g_error; }
 
