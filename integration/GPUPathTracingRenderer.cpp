@@ -1,7 +1,7 @@
 // See GPUPathTracingRenderer.h. The exporter below reads the reference's private members (QBVH::m_nodes,
 // SurfaceObjectAggregate::m_lightList, the materials' texture pointers, ...): the oracle build compiles this file with
 // -fno-access-control; in a real merge these would be `friend class GpuSceneExporter;` lines or accessors.
-// Unsupported content (animated transforms, image textures on surfaces, an environment sphere, instancing nested deeper
+// Unsupported content (animated transforms, instancing nested deeper
 // than one level) throws std::runtime_error -- never a silently different image.
 #include "GPUPathTracingRenderer.h"
 
@@ -10,6 +10,7 @@
 #include <libSLR/BasicTypes/Spectrum.h>
 #include <libSLR/BasicTypes/SpectrumTypes.h>
 #include <libSLR/Cameras/PerspectiveCamera.h>
+#include <libSLR/Core/Image.h>
 #include <libSLR/Core/ImageSensor.h>
 #include <libSLR/Core/RenderSettings.h>
 #include <libSLR/Core/SurfaceObject.h>
@@ -20,6 +21,7 @@
 #include <libSLR/Surface/TriangleMesh.h>
 #include <libSLR/SurfaceMaterials/AshikhminShirleyReflection.h>
 #include <libSLR/SurfaceMaterials/DiffuseEmission.h>
+#include <libSLR/SurfaceMaterials/IBLEmission.h>
 #include <libSLR/SurfaceMaterials/MicrofacetSurfaceMaterial.h>
 #include <libSLR/SurfaceMaterials/MixedSurfaceMaterial.h>
 #include <libSLR/SurfaceMaterials/ModifiedWardDurReflection.h>
@@ -27,6 +29,7 @@
 #include <libSLR/SurfaceMaterials/basic_SurfaceMaterials.h>
 #include <libSLR/Textures/checker_board_textures.h>
 #include <libSLR/Textures/constant_textures.h>
+#include <libSLR/Textures/image_textures.h>
 #include <libSLR/Textures/voronoi_textures.h>
 
 #include <slrgpu.h>
@@ -58,6 +61,11 @@ class GpuSceneExporter {
     std::vector<float> spectrumData;
     std::vector<SlrGpuLight> lights;
     std::vector<float> gridFloats;
+    std::vector<SlrGpuImage> images;
+    std::vector<uint8_t> imageData;
+    std::map<const void*, uint32_t> imageIds;
+    // environment importance map (InfiniteSphereSurfaceObject::m_dist), row-major copies of the reference's own arrays
+    std::vector<float> envRowPdf, envRowCdf, envRowIntegral, envMarginalPdf, envMarginalCdf;
     uint32_t numTopLights = 0;
     float topLightImportance = 0.0f;
 
@@ -101,6 +109,24 @@ class GpuSceneExporter {
         t->map_scale[0] = t->map_scale[1] = 1.0f;
     }
     uint32_t addTexture(const void* key, const SlrGpuTexture &t) { textures.push_back(t); return textureIds[key] = (uint32_t)textures.size() - 1; }
+    // TiledImage2D (Core/Image.h:77-353): texels un-tiled into rows; ColorFormat's values are SlrGpuImageFormat's
+    uint32_t image(const TiledImage2D* img) {
+        auto it = imageIds.find(img);
+        if (it != imageIds.end()) return it->second;
+        SlrGpuImage g;
+        memset(&g, 0, sizeof(g));
+        g.format = (uint32_t)img->format(); g.width = img->width(); g.height = img->height();
+        g.spectrum_type = (uint32_t)img->spectrumType();
+        const size_t texel = sizesOfColorFormats[g.format];
+        while (imageData.size() % 16) imageData.push_back(0);
+        g.data_offset = imageData.size();
+        imageData.resize(imageData.size() + texel * g.width * g.height);
+        uint8_t* dst = imageData.data() + g.data_offset;
+        for (uint32_t y = 0; y < g.height; ++y)
+            for (uint32_t x = 0; x < g.width; ++x, dst += texel) memcpy(dst, img->getInternal(x, y), texel);
+        images.push_back(g);
+        return imageIds[img] = (uint32_t)images.size() - 1;
+    }
     uint32_t spectrumTexture(const SpectrumTexture* tex) {
         auto it = textureIds.find(tex);
         if (it != textureIds.end()) return it->second;
@@ -112,7 +138,9 @@ class GpuSceneExporter {
             t.kind = SLRGPU_TEX_CHECKER_SPECTRUM; mapping2D(cb->m_mapping, &t); t.i0 = spectrum(cb->m_values[0]); t.i1 = spectrum(cb->m_values[1]);
         } else if (auto v = dynamic_cast<const VoronoiSpectrumTexture*>(tex)) {
             t.kind = SLRGPU_TEX_VORONOI_SPECTRUM; mapping3D(v->m_mapping, &t); t.f0 = v->m_scale; t.f1 = v->m_brightness;
-        } else unsupported("image spectrum textures are not exported by this binding yet");
+        } else if (auto im = dynamic_cast<const ImageSpectrumTexture*>(tex)) {
+            t.kind = SLRGPU_TEX_IMAGE_SPECTRUM; mapping2D(im->m_mapping, &t); t.i0 = image(im->m_data);
+        } else unsupported("unknown SpectrumTexture class");
         return addTexture(tex, t);
     }
     uint32_t floatTexture(const FloatTexture* tex) {
@@ -126,7 +154,9 @@ class GpuSceneExporter {
             t.kind = SLRGPU_TEX_CHECKER_FLOAT; mapping2D(cb->m_mapping, &t); t.f0 = cb->m_values[0]; t.f1 = cb->m_values[1];
         } else if (auto v = dynamic_cast<const VoronoiFloatTexture*>(tex)) {
             t.kind = SLRGPU_TEX_VORONOI_FLOAT; mapping3D(v->m_mapping, &t); t.f0 = v->m_scale; t.f1 = v->m_valueScale; t.i0 = v->m_flat ? 1 : 0;
-        } else unsupported("image float textures are not exported by this binding yet");
+        } else if (auto im = dynamic_cast<const ImageFloatTexture*>(tex)) {
+            t.kind = SLRGPU_TEX_IMAGE_FLOAT; mapping2D(im->m_mapping, &t); t.i0 = image(im->m_data);
+        } else unsupported("unknown FloatTexture class");
         return addTexture(tex, t);
     }
     uint32_t normalTexture(const Normal3DTexture* tex) {
@@ -139,7 +169,9 @@ class GpuSceneExporter {
             t.kind = SLRGPU_TEX_CHECKER_NORMAL; mapping2D(cb->m_mapping, &t); t.f0 = cb->m_stepWidth; t.i0 = cb->m_reverse ? 1 : 0;
         } else if (auto v = dynamic_cast<const VoronoiNormal3DTexture*>(tex)) {
             t.kind = SLRGPU_TEX_VORONOI_NORMAL; mapping3D(v->m_mapping, &t); t.f0 = v->m_scale; t.f1 = v->m_cosThetaMax;
-        } else unsupported("image normal textures are not exported by this binding yet");
+        } else if (auto im = dynamic_cast<const ImageNormal3DTexture*>(tex)) {
+            t.kind = SLRGPU_TEX_IMAGE_NORMAL; mapping2D(im->m_mapping, &t); t.i0 = image(im->m_data);
+        } else unsupported("unknown Normal3DTexture class");
         return addTexture(tex, t);
     }
     uint32_t alphaG(const SVMicrofacetDistribution* D) {
@@ -161,8 +193,14 @@ class GpuSceneExporter {
     uint32_t emitter(const EmitterSurfaceProperty* e) {
         auto it = materialIds.find(e);
         if (it != materialIds.end()) return it->second;
+        if (auto ibl = dynamic_cast<const IBLEmission*>(e)) {        // SurfaceMaterials/IBLEmission.cpp:15-17: pi * coeffM * scale
+            SlrGpuMaterial m = blank(SLRGPU_MAT_IBL_EMISSION);
+            m.tex[0] = spectrumTexture(ibl->m_coeffM);
+            m.f0 = ibl->m_scale;
+            return addMaterial(e, m);
+        }
         auto d = dynamic_cast<const DiffuseEmission*>(e);
-        if (!d) unsupported("only DiffuseEmission emitters are exported by this binding (no environment sphere yet)");
+        if (!d) unsupported("unknown EmitterSurfaceProperty class");
         SlrGpuMaterial m = blank(SLRGPU_MAT_DIFFUSE_EMISSION);
         m.tex[0] = spectrumTexture(d->m_emittance);
         return addMaterial(e, m);
@@ -332,7 +370,6 @@ public:
     SlrGpuSceneDesc desc;
 
     explicit GpuSceneExporter(const Scene &scene) {
-        if (scene.m_envSphere) unsupported("environment lighting is not exported by this binding yet");
         // the top-level aggregate must own node 0: export it first
         const AggregateInfo top = aggregate(scene.m_aggregate, 0);
         numTopLights = top.numLights;
@@ -369,6 +406,42 @@ public:
         desc.top_light_importance = topLightImportance;
         desc.world_center[0] = scene.m_worldCenter.x; desc.world_center[1] = scene.m_worldCenter.y; desc.world_center[2] = scene.m_worldCenter.z;
         desc.world_radius = scene.m_worldRadius;
+
+        desc.images = images.data(); desc.num_images = (uint32_t)images.size();
+        desc.image_data = imageData.data(); desc.image_data_bytes = imageData.size();
+
+        // the environment (InfiniteSphereSurfaceObject, SurfaceObject.cpp:140-222): its emitter and the importance map the
+        // reference built for it (IBLEmission::createIBLImportanceMap), copied array by array
+        if (const InfiniteSphereSurfaceObject* env = scene.m_envSphere) {
+            auto em = dynamic_cast<const EmitterSurfaceMaterial*>(env->m_material);
+            if (!em) unsupported("the environment sphere's material is not an EmitterSurfaceMaterial");
+            const RegularConstantContinuous2D* dist = env->m_dist;
+            const uint32_t H = dist->m_num1DDists, W = dist->m_1DDists[0].m_numValues;
+            envRowPdf.resize((size_t)W * H); envRowCdf.resize((size_t)(W + 1) * H); envRowIntegral.resize(H);
+            envMarginalPdf.resize(H); envMarginalCdf.resize(H + 1);
+            for (uint32_t y = 0; y < H; ++y) {
+                const RegularConstantContinuous1D &row = dist->m_1DDists[y];
+                memcpy(&envRowPdf[(size_t)y * W], row.m_PDF, sizeof(float) * W);
+                memcpy(&envRowCdf[(size_t)y * (W + 1)], row.m_CDF, sizeof(float) * (W + 1));
+                envRowIntegral[y] = row.m_integral;
+            }
+            memcpy(envMarginalPdf.data(), dist->m_top1DDist->m_PDF, sizeof(float) * H);
+            memcpy(envMarginalCdf.data(), dist->m_top1DDist->m_CDF, sizeof(float) * (H + 1));
+            desc.environment.present = 1;
+            desc.environment.material = emitter(em->m_emit);
+            desc.environment.map_width = W; desc.environment.map_height = H;
+            desc.environment.row_pdf = envRowPdf.data(); desc.environment.row_cdf = envRowCdf.data();
+            desc.environment.row_integral = envRowIntegral.data();
+            desc.environment.marginal_pdf = envMarginalPdf.data(); desc.environment.marginal_cdf = envMarginalCdf.data();
+            desc.environment.marginal_integral = dist->m_top1DDist->m_integral;
+            // the tables may have grown: the pointers taken above are refreshed below
+        }
+        desc.materials = materials.data(); desc.num_materials = (uint32_t)materials.size();
+        desc.textures = textures.data(); desc.num_textures = (uint32_t)textures.size();
+        desc.spectra = spectra.data(); desc.num_spectra = (uint32_t)spectra.size();
+        desc.spectrum_data = spectrumData.data(); desc.num_spectrum_floats = (uint32_t)spectrumData.size();
+        desc.images = images.data(); desc.num_images = (uint32_t)images.size();
+        desc.image_data = imageData.data(); desc.image_data_bytes = imageData.size();
 
         auto cam = dynamic_cast<const PerspectiveCamera*>(scene.getCamera());
         if (!cam) unsupported("only PerspectiveCamera is exported");

@@ -65,14 +65,14 @@ def bmp_pixels(data, width, height):
 REF_SCENES = os.path.join(ROOT, "oracle", "_ref", "TestScenes")     # the reference's shipped scene files (oracle/Makefile `scenes`)
 
 
-def reference_scene_file(name, directory, width, height, spp):
+def reference_scene_file(name, directory, width, height, spp, method="PT"):
     """The reference's TestScenes/<name>, unchanged, with the size / sample-count override appended and synthetic assets
     written next to it (slr_b200.scenes.write_reference_scene). None when the file did not travel to this machine."""
     from slr_b200 import scenes
     src = os.path.join(REF_SCENES, name)
     if not os.path.exists(src):
         return None
-    return scenes.write_reference_scene(src, directory, width, height, spp)
+    return scenes.write_reference_scene(src, directory, width, height, spp, method=method)
 
 
 def scene_file(name, directory, width, height, spp):

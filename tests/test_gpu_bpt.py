@@ -134,11 +134,11 @@ def test_scene_file_that_selects_bpt_renders_bidirectionally(workdir):
     """setRenderer("BPT") in a scene file creates the bidirectional GPU renderer (6 of the reference's 7 TestScenes ask for
     it); the unchanged Cornell_Box_Spheres.txt through it meets the reference BPT's noise floor."""
     size, spp = 96, 32
-    path = ru.reference_scene_file("Cornell_Box_Spheres.txt", os.path.join(workdir, "ref_cbs"), size, size, spp)
+    path = ru.reference_scene_file("Cornell_Box_Spheres.txt", os.path.join(workdir, "ref_cbs"), size, size, spp, method="BPT")
     if path is None or not ru.have_ref_render():
         pytest.skip("the reference's scene files / ref_render did not travel to this machine")
     hs = capi.read_scene(path)
-    assert hs.context["method"] in ("BPT", "PT")
+    assert hs.context["method"] == "BPT"
     gpu, _ = _bpt_rgb(path, size, spp)
     ref1 = capi.accum_to_rgb(ru.run_ref_render(path, spp, size, size, seed=1509761209, bpt=True)[0], 1.0 / spp)
     ref2 = capi.accum_to_rgb(ru.run_ref_render(path, spp, size, size, seed=20240229, bpt=True)[0], 1.0 / spp)
