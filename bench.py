@@ -262,6 +262,8 @@ def main():
     ap.add_argument("--size", type=int, default=0, help="render workloads: override the image size")
     ap.add_argument("--spp", type=int, default=0, help="render workloads: override the samples per pixel (per GPU)")
     ap.add_argument("--pool", type=int, default=0, help="render workloads: paths in flight (0 = library default)")
+    ap.add_argument("--parity-paths", type=float, default=40e6,
+                    help="render workloads: largest frame (paths) whose image is also compared with two seeds of the reference (image_parity)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="render workloads, N > 1: weak = --spp samples per GPU (frame = spp x N, the default the driver measures); "
                          "strong = --spp is the frame's sample count, partitioned over the GPUs")

@@ -512,11 +512,11 @@ def gpu_render(gpu_scene, width, height, spp_begin, spp_end, seed=1509761209, ti
     return accum, {k: (list(getattr(st, k)) if k == "class_hits" else getattr(st, k)) for k, _ in RenderStats._fields_}
 
 
-def gpu_render_multi(gpu_scenes, width, height, spp_begin, spp_end, seed=1509761209, pool_size=0):
+def gpu_render_multi(gpu_scenes, width, height, spp_begin, spp_end, seed=1509761209, pool_size=0, flags=0):
     """slrgpu_render_multi over scene replicas (normally one per device). Returns (accum[h, w, c], RenderStats as dict)."""
     chan = gpu.slrgpu_scene_channels(gpu_scenes[0].handle)
     accum = np.zeros((height, width, chan), np.float32)
-    p = RenderParams(C.sizeof(RenderParams), width, height, spp_begin, spp_end, 0.0, 0.0, seed, 0, pool_size, 0)
+    p = RenderParams(C.sizeof(RenderParams), width, height, spp_begin, spp_end, 0.0, 0.0, seed, 0, pool_size, flags)
     st = RenderStats()
     handles = (C.c_void_p * len(gpu_scenes))(*[g.handle for g in gpu_scenes])
     _gpu_check(gpu.slrgpu_render_multi(handles, len(gpu_scenes), C.byref(p), _pf(accum), C.byref(st)), "slrgpu_render_multi")

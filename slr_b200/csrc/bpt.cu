@@ -10,8 +10,9 @@
 // Samples are processed in batches of up to 262 144: one thread per SUBPATH traces the light / eye subpaths of the batch
 // (the eye threads also add the implicit s = 0 paths), then one thread per CONNECTION (slot, s, t) runs its shadow ray and MIS
 // weight. The reference keeps the two vertex lists in std::vectors of ~300-byte objects per CPU thread; here they live in
-// HBM, interleaved by batch slot in 16-byte words (word w of vertex v of slot l at ((v * W + w) * slots + l) * 16 B), so the
-// threads of a warp that walk their lists in step read and write whole 512-byte lines. The rays are the traversal of traverse.cuh (single_ray.cuh), surface points / lights / materials / BSDFs the
+// HBM as [subpath][vertex index][slot] records of 192 B (208 with the MIS record kept apart): the subpath threads of a warp
+// (adjacent slots, same vertex index) write one contiguous 6 KB block, a connection thread reads its two vertices as two
+// contiguous records. The rays are the traversal of traverse.cuh (single_ray.cuh), surface points / lights / materials / BSDFs the
 // path tracer's device functions; a vertex stores its surface point and material, and the BSDF is rebuilt from them when a
 // connection needs it (the reference keeps the arena-allocated object instead).
 //
@@ -52,7 +53,7 @@ template <int NC> struct alignas(16) BptVertex {
 template <int NC> __host__ __device__ constexpr int bptVertexWords() { return (int)((sizeof(BptVertex<NC>) + 15) / 16); }
 
 struct BptStore {
-    float4* verts;           // [2 subpaths][kBptMaxVerts][W][lanes]
+    float4* verts;           // [2 subpaths][kBptMaxVerts][lanes][W]: a vertex is W contiguous 16-byte words
     float4* mis;             // [2][kBptMaxVerts][lanes]: areaPDF, RRProb, revAreaPDF, revRRProb
     uint32_t lanes;
 };
@@ -66,17 +67,17 @@ template <int NC>
 __device__ __forceinline__ void storeVertex(const BptStore& st, uint32_t lane, int sub, int v, const BptVertex<NC>& vtx) {
     constexpr int W = bptVertexWords<NC>();
     const float4* src = reinterpret_cast<const float4*>(&vtx);
-    float4* dst = st.verts + (size_t)(sub * kBptMaxVerts + v) * W * st.lanes + lane;
+    float4* dst = st.verts + ((size_t)(sub * kBptMaxVerts + v) * st.lanes + lane) * W;
 #pragma unroll
-    for (int w = 0; w < W; ++w) dst[(size_t)w * st.lanes] = src[w];
+    for (int w = 0; w < W; ++w) dst[w] = src[w];
 }
 template <int NC>
 __device__ __forceinline__ void loadVertex(const BptStore& st, uint32_t lane, int sub, int v, BptVertex<NC>* vtx) {
     constexpr int W = bptVertexWords<NC>();
     float4* dst = reinterpret_cast<float4*>(vtx);
-    const float4* src = st.verts + (size_t)(sub * kBptMaxVerts + v) * W * st.lanes + lane;
+    const float4* src = st.verts + ((size_t)(sub * kBptMaxVerts + v) * st.lanes + lane) * W;
 #pragma unroll
-    for (int w = 0; w < W; ++w) dst[w] = src[(size_t)w * st.lanes];
+    for (int w = 0; w < W; ++w) dst[w] = src[w];
 }
 // position, geometric normal and atInfinity of a stored vertex (SurfPt starts with p, gn; atInfinity is its last member)
 template <int NC>

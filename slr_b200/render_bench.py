@@ -353,7 +353,7 @@ def main(args, rank, world):
     # SLR_BENCH_AB=1 (kernel A/B sweeps, tools/r02_call*.sh): skip the CPU legs, only the device numbers are read
     ab = os.environ.get("SLR_BENCH_AB") == "1"
     cpu = cpu_baseline(path, w, h, spp) if (world == 1 and not ab) else None      # the CPU leg runs at N = 1 only
-    parity = image_parity(capi, path, w, h, my_spp, pinned.numpy()) if (world == 1 and not ab and w * h * my_spp <= 40e6) else None
+    parity = image_parity(capi, path, w, h, my_spp, pinned.numpy()) if (world == 1 and not ab and w * h * my_spp <= getattr(args, "parity_paths", 40e6)) else None
     line = {"metric": METRIC, "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": mode, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",

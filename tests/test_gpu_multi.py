@@ -37,6 +37,17 @@ def test_partitioned_frame_equals_single_gpu_frame(scene, replicas):
     assert stn["other_ms"] > 0.0                     # the exchange step ran and was timed
 
 
+def test_partitioned_bidirectional_frame_equals_single_gpu_frame(scene):
+    """SLRGPU_RENDER_BPT through slrgpu_render_multi: the same sample partition and exchange step; a bidirectional sample's
+    random numbers are keyed by (pixel, global sample index) too."""
+    gss = [capi.GpuScene(scene, device=d) for d in _devices(2)]
+    whole, st1 = capi.gpu_render(gss[0], 96, 96, 0, 8, flags=capi.RENDER_BPT)
+    multi, stn = capi.gpu_render_multi(gss, 96, 96, 0, 8, flags=capi.RENDER_BPT)
+    for k in ("paths", "rays", "extend_rays", "shadow_rays"):
+        assert stn[k] == st1[k], k
+    np.testing.assert_allclose(multi, whole, rtol=5e-4, atol=1e-4 * float(whole.mean()))
+
+
 def test_more_replicas_than_samples(scene):
     """A replica whose share of the sample range is empty renders nothing; the frame is still complete."""
     gss = [capi.GpuScene(scene, device=d) for d in _devices(4)]
