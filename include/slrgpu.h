@@ -102,8 +102,8 @@ typedef struct SlrGpuSbvhNode {
  * any depth (SurfaceObject.cpp:307-336): the producer of the tables expands a chain instead -- an instance found inside a
  * referenced subtree is placed again under (outer transform x its own), the subtree's own triangles become an aggregate
  * of their own. The host library does that when it flattens a scene (host/scene.h PlacedSubtree: same closest hits up to
- * the rounding of the composed matrix, same light-selection probabilities); the reference-side exporter still rejects
- * nesting. */
+ * the rounding of the composed matrix, same light-selection probabilities), and so does the reference-side exporter
+ * (integration/GPUPathTracingRenderer.cpp expandNesting, with the reference's own aggregate and transform classes). */
 typedef struct SlrGpuInstance {
     float mat[16];          /* local -> parent */
     float mat_inv[16];      /* parent -> local, as computed by the host's invert() */

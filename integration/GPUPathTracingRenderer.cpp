@@ -1,8 +1,9 @@
 // See GPUPathTracingRenderer.h. The exporter below reads the reference's private members (QBVH::m_nodes,
 // SurfaceObjectAggregate::m_lightList, the materials' texture pointers, ...): the oracle build compiles this file with
 // -fno-access-control; in a real merge these would be `friend class GpuSceneExporter;` lines or accessors.
-// Unsupported content (animated transforms, instancing nested deeper
-// than one level) throws std::runtime_error -- never a silently different image.
+// Instancing nested in instancing is expanded to the one level the device walks (expandNesting); animated transforms are
+// exported with the reference's own decomposition. Unsupported content (a chain of two animated transforms, surfaces
+// other than triangles) throws std::runtime_error -- never a silently different image.
 #include "GPUPathTracingRenderer.h"
 
 #include <libSLR/Accelerator/QBVH.h>
@@ -18,6 +19,7 @@
 #include <libSLR/Core/distributions.h>
 #include <libSLR/Core/surface_material.h>
 #include <libSLR/Core/textures.h>
+#include <libSLR/Memory/ArenaAllocator.h>
 #include <libSLR/Surface/TriangleMesh.h>
 #include <libSLR/SurfaceMaterials/AshikhminShirleyReflection.h>
 #include <libSLR/SurfaceMaterials/DiffuseEmission.h>
@@ -35,6 +37,8 @@
 #include <slrgpu.h>
 
 #include <chrono>
+#include <memory>
+#include <set>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -53,6 +57,7 @@ class GpuSceneExporter {
     std::vector<SlrGpuBvhNode> nodes;
     std::vector<SlrGpuLeafRecord> leaves;
     std::vector<SlrGpuInstance> instances;
+    std::vector<SlrGpuMotion> motions;
     std::vector<SlrGpuTriangle> triangles;
     std::vector<SlrGpuVertex> vertices;
     std::vector<SlrGpuMaterial> materials;
@@ -74,6 +79,84 @@ class GpuSceneExporter {
     std::map<const void*, uint32_t> materialIds, textureIds, spectrumIds;
     struct AggregateInfo { uint32_t nodeBase, lightBase, numLights; float importance; bool hasInstances; };
     std::map<const SurfaceObjectAggregate*, AggregateInfo> aggregates;
+
+    // ---- instancing nested in instancing --------------------------------------------------------------------------
+    // The device walks ONE level of instances (include/slrgpu.h). A TransformedSurfaceObject whose aggregate holds further
+    // TransformedSurfaceObjects (the reference recurses to any depth, SurfaceObject.cpp:307-336) is expanded here before
+    // anything is exported: its own triangles become one aggregate placed under its transform, every instance inside it is
+    // placed again under the composed transform (recursively), and the parent aggregate is rebuilt over the expanded list.
+    // All of it with the reference's own classes -- SurfaceObjectAggregate's constructor builds the SBVH and the light
+    // distribution, ChainedTransform::reduce composes static and animated transforms as the scene graph does
+    // (Transform.cpp:74-152) -- so the exporter below sees an ordinary one-level scene. Light selection is unchanged in
+    // distribution: an aggregate's importance is the sum of its entries' importances (SurfaceObject.cpp:232-252), so the
+    // product of pmfs along a chain equals the pmf of the expanded entry.
+    ArenaAllocator expandMem;
+    std::vector<std::unique_ptr<SurfaceObject>> expandOwned;
+    std::map<const SurfaceObjectAggregate*, SurfaceObjectAggregate*> ownTriangles;     // aggregate -> aggregate of its triangles only
+    std::map<const SurfaceObject*, SurfaceObjectAggregate*> wrapped;                    // lone object -> one-object aggregate
+
+    static std::vector<const SurfaceObject*> objectsOf(const SurfaceObjectAggregate* ag) {
+        auto sbvh = dynamic_cast<const SBVH*>(ag->m_accelerator);
+        if (!sbvh) unsupported("the aggregate's accelerator is not the SBVH the reference builds by default");
+        std::vector<const SurfaceObject*> objs;            // a spatial split references an object from several leaves
+        std::set<const SurfaceObject*> seen;
+        for (const SurfaceObject* o : sbvh->m_objLists) if (seen.insert(o).second) objs.push_back(o);
+        return objs;
+    }
+    static const SurfaceObjectAggregate* nestedOf(const SurfaceObject* o) {
+        auto tso = dynamic_cast<const TransformedSurfaceObject*>(o);
+        return tso ? dynamic_cast<const SurfaceObjectAggregate*>(tso->m_surfObj) : nullptr;
+    }
+    static bool holdsInstances(const SurfaceObjectAggregate* ag) {
+        for (const SurfaceObject* o : objectsOf(ag)) if (dynamic_cast<const TransformedSurfaceObject*>(o)) return true;
+        return false;
+    }
+    template <typename T, typename... Args> T* own(Args&&... args) {
+        T* p = new T(std::forward<Args>(args)...);
+        expandOwned.emplace_back(p);
+        return p;
+    }
+    // what the parent of `tso` sees once tso's aggregate holds no instances any more
+    bool expanded = false;
+    void place(const TransformedSurfaceObject* tso, std::vector<SurfaceObject*>* out) {
+        const SurfaceObjectAggregate* ag = nestedOf(tso);
+        if (!ag) {
+            // an animated node with a single object below it is a TransformedSurfaceObject over that object itself
+            // (nodes.cpp:131-134): give it the one-object aggregate the device's instance record needs
+            auto it = wrapped.find(tso->m_surfObj);
+            if (it == wrapped.end()) {
+                std::vector<SurfaceObject*> one{const_cast<SurfaceObject*>(tso->m_surfObj)};
+                it = wrapped.emplace(tso->m_surfObj, own<SurfaceObjectAggregate>(one)).first;
+            }
+            ag = it->second;
+            tso = own<TransformedSurfaceObject>(ag, tso->m_transform);
+            expanded = true;
+        }
+        if (!holdsInstances(ag)) { out->push_back(const_cast<TransformedSurfaceObject*>(tso)); return; }
+        expanded = true;
+        auto it = ownTriangles.find(ag);
+        if (it == ownTriangles.end()) {
+            std::vector<SurfaceObject*> singles;
+            for (const SurfaceObject* o : objectsOf(ag))
+                if (!dynamic_cast<const TransformedSurfaceObject*>(o)) singles.push_back(const_cast<SurfaceObject*>(o));
+            it = ownTriangles.emplace(ag, singles.empty() ? nullptr : own<SurfaceObjectAggregate>(singles)).first;
+        }
+        if (it->second) out->push_back(own<TransformedSurfaceObject>(it->second, tso->m_transform));
+        for (const SurfaceObject* o : objectsOf(ag)) {
+            auto inner = dynamic_cast<const TransformedSurfaceObject*>(o);
+            if (!inner) continue;
+            const Transform* composed = ChainedTransform(tso->m_transform, inner->m_transform).reduce(expandMem);
+            place(own<TransformedSurfaceObject>(inner->m_surfObj, composed), out);
+        }
+    }
+    const SurfaceObjectAggregate* expandNesting(const SurfaceObjectAggregate* top) {
+        std::vector<SurfaceObject*> objs;
+        for (const SurfaceObject* o : objectsOf(top)) {
+            if (auto tso = dynamic_cast<const TransformedSurfaceObject*>(o)) place(tso, &objs);
+            else objs.push_back(const_cast<SurfaceObject*>(o));
+        }
+        return expanded ? own<SurfaceObjectAggregate>(objs) : top;       // untouched scenes keep the reference's own top-level tree
+    }
 
     // ---- spectra (BasicTypes/SpectrumTypes.h:70-346) ----
     uint32_t spectrum(const InputSpectrum* s) {
@@ -344,17 +427,43 @@ class GpuSceneExporter {
         lights.insert(lights.end(), mine.begin(), mine.end());
         return aggregates[ag] = info;
     }
+    // A node's transform after the scene graph's ChainedTransform::reduce (Transform.cpp:74-152): a StaticTransform, or ONE
+    // AnimatedTransform with the static transforms around it folded into its key frames (createByMulLeft / Right).
+    // mat / matInv receive the (begin) key frame; returns SlrGpuInstance::motion / SlrGpuSceneDesc::camera_motion:
+    // 0 = static, else 1 + index of the SlrGpuMotion that carries the end key frame and the reference's own decomposition
+    // (AnimatedTransform's T / R / S members, Transform.h:89-123), so the device interpolates what sample() would.
+    uint32_t keyFrames(const Transform* tf, float* mat, float* matInv) {
+        if (auto st = dynamic_cast<const StaticTransform*>(tf)) {
+            memcpy(mat, &st->mat, 64);          // Matrix4x4 is four column vectors: column-major like SlrGpuInstance
+            memcpy(matInv, &st->matInv, 64);
+            return 0u;
+        }
+        auto at = dynamic_cast<const AnimatedTransform*>(tf);
+        if (!at) unsupported("a chain of two animated transforms (motion blur inside motion blur)");
+        memcpy(mat, &at->m_tfBegin.mat, 64);
+        memcpy(matInv, &at->m_tfBegin.matInv, 64);
+        if (at->isStatic()) return 0u;
+        SlrGpuMotion m;
+        memset(&m, 0, sizeof(m));
+        memcpy(m.mat_end, &at->m_tfEnd.mat, 64);
+        memcpy(m.mat_end_inv, &at->m_tfEnd.matInv, 64);
+        for (int k = 0; k < 3; ++k) { m.T0[k] = at->m_T[0][k]; m.T1[k] = at->m_T[1][k]; }
+        m.t_begin = at->m_tBegin; m.t_end = at->m_tEnd;
+        m.R0[0] = at->m_R[0].x; m.R0[1] = at->m_R[0].y; m.R0[2] = at->m_R[0].z; m.R0[3] = at->m_R[0].w;
+        m.R1[0] = at->m_R[1].x; m.R1[1] = at->m_R[1].y; m.R1[2] = at->m_R[1].z; m.R1[3] = at->m_R[1].w;
+        memcpy(m.S0, &at->m_S[0], 64);
+        memcpy(m.S1, &at->m_S[1], 64);
+        motions.push_back(m);
+        return (uint32_t)motions.size();
+    }
     uint32_t instance(const TransformedSurfaceObject* tso, int depth) {
         auto it = instanceIds.find(tso);
         if (it != instanceIds.end()) return it->second;
-        auto st = dynamic_cast<const StaticTransform*>(tso->m_transform);
-        if (!st) unsupported("animated transforms (motion blur) are not exported by this binding");
         auto nested = dynamic_cast<const SurfaceObjectAggregate*>(tso->m_surfObj);
         if (!nested) unsupported("a TransformedSurfaceObject over something other than an aggregate");
         SlrGpuInstance inst;
         memset(&inst, 0, sizeof(inst));
-        memcpy(inst.mat, &st->mat, 64);          // Matrix4x4 is four column vectors: column-major like SlrGpuInstance
-        memcpy(inst.mat_inv, &st->matInv, 64);
+        inst.motion = keyFrames(tso->m_transform, inst.mat, inst.mat_inv);
         inst.light_index = SLRGPU_INVALID_ID;
         const uint32_t id = (uint32_t)instances.size();
         instances.push_back(inst);
@@ -371,7 +480,7 @@ public:
 
     explicit GpuSceneExporter(const Scene &scene) {
         // the top-level aggregate must own node 0: export it first
-        const AggregateInfo top = aggregate(scene.m_aggregate, 0);
+        const AggregateInfo top = aggregate(expandNesting(scene.m_aggregate), 0);
         numTopLights = top.numLights;
         topLightImportance = top.importance;
         // top-level lights must come first in `lights` (slrgpu.h): aggregate() appends an aggregate's own list after its
@@ -445,11 +554,8 @@ public:
 
         auto cam = dynamic_cast<const PerspectiveCamera*>(scene.getCamera());
         if (!cam) unsupported("only PerspectiveCamera is exported");
-        StaticTransform tf;
-        if (!cam->m_transform->isStatic()) unsupported("animated camera transforms (motion blur) are not exported by this binding");
-        cam->m_transform->sample(0.0f, &tf);
-        memcpy(desc.camera.mat, &tf.mat, 64);
-        memcpy(desc.camera.mat_inv, &tf.matInv, 64);
+        desc.camera_motion = keyFrames(cam->m_transform, desc.camera.mat, desc.camera.mat_inv);
+        desc.motions = motions.empty() ? nullptr : motions.data(); desc.num_motions = (uint32_t)motions.size();
         desc.camera.sensitivity = cam->getSensor()->m_sensitivity;
         desc.camera.aspect = cam->m_aspect; desc.camera.fov_y = cam->m_fovY; desc.camera.lens_radius = cam->m_lensRadius;
         desc.camera.img_plane_dist = cam->m_imgPlaneDistance; desc.camera.obj_plane_dist = cam->m_objPlaneDistance;

@@ -56,6 +56,11 @@ struct DeviceScene {
     float integralCMF;
 };
 
+#ifdef __CUDACC__
+// cache hint for a queue entry a later iteration / refill will stream (no register is held for it)
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+
 // Material class of a hit (wavefront.cuh: ShadeClass values, numbered like LobeType) and the leaf
 // material the class kernel builds its lobe from. Emitter wrappers are peeled (their BSDF is the
 // scattering material's, surface_material.h); sum / mix / inverse trees go to the generic kernel with

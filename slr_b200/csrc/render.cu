@@ -24,7 +24,10 @@
 
 namespace slrgpu {
 
-constexpr int kSurfaceBlock = 128;
+#ifndef SLR_SURFACE_BLOCK
+#define SLR_SURFACE_BLOCK 128
+#endif
+constexpr int kSurfaceBlock = SLR_SURFACE_BLOCK;
 constexpr int kMaterialBlock = 128;
 constexpr int kRaygenBlock = 128;
 // resident blocks per SM the register allocation of the shade kernels is bounded for (tuning knobs, see profiles/)
@@ -131,7 +134,7 @@ template <int NC>
 __global__ void __launch_bounds__(kSurfaceBlock, SLR_SURFACE_MIN_BLOCKS)
 surfaceKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitBuffer hits, ClassQueue cq,
               float* __restrict__ accum, WavefrontCounters* counters) {
-    surfaceStage<NC>(s, rc, in, hits, cq, accum, counters, counters->numPaths);
+    surfaceStage<NC, kSurfaceBlock>(s, rc, in, hits, cq, accum, counters, counters->numPaths);
 }
 
 template <int NC, int CLASS>

@@ -8,6 +8,12 @@
 #include "shade.cuh"
 #include "wavefront.cuh"
 
+// material stage: next iteration's class-queue entry loaded ahead and its path state hinted into L2 (materialStage).
+// Measured (profiles/r02_variant_sweep.md): material 7.19 -> 6.72 ms per C1 frame, C1 617 -> 625-632 Mpaths/s.
+#ifndef SLR_STAGE_PREFETCH
+#define SLR_STAGE_PREFETCH 1
+#endif
+
 namespace slrgpu {
 
 // position of `alive` lanes in an output queue: one atomic per warp
@@ -188,21 +194,69 @@ __device__ __forceinline__ void classAppend(const ClassQueue& cq, WavefrontCount
     }
 }
 
-// Work items [0, n) are spread over the whole grid, one warp per 32 consecutive entries.
+// append to the class queues, one atomic per (BLOCK, class): the warps' per-class counts meet in shared memory, the first
+// 16 threads reserve the block's ranges (one ATOMG with a lane per class), every entry then takes its place behind the
+// entries of the warps before it. With one atomic per warp the stage was bound by the return latency of half a million
+// atomics on ONE address per wave (classCount of the dominant class): ncu, first wave of C1 -- 52 % of the kernel's stall
+// samples on the shuffle that broadcasts the atomic's result, 1.1 G atomics/s = the serialisation limit of the L2 slice.
+// Must be called by every thread of the block (two barriers).
+template <int WARPS>
+__device__ __forceinline__ void classAppendBlock(const ClassQueue& cq, WavefrontCounters* counters, uint32_t i, uint32_t cls, uint32_t leaf) {
+    __shared__ uint32_t warpCount[WARPS][16];     // entries of class c in warp w
+    __shared__ uint32_t blockBase[16];            // first queue position of the block's entries of class c
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < 16) warpCount[warp][lane] = 0;
+    __syncwarp();
+    uint32_t rank = 0;
+    const unsigned active = __ballot_sync(0xFFFFFFFFu, cls != SC_NONE);
+    if (cls != SC_NONE) {
+        const unsigned grp = __match_any_sync(active, cls);
+        rank = __popc(grp & ((1u << lane) - 1u));
+        if (rank == 0) warpCount[warp][cls] = (uint32_t)__popc(grp);
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) total += warpCount[w][threadIdx.x];
+        if (total) blockBase[threadIdx.x] = atomicAdd(&counters->classCount[threadIdx.x], total);
+    }
+    __syncthreads();
+    if (cls != SC_NONE) {
+        uint32_t pos = blockBase[cls] + rank;
+        for (uint32_t w = 0; w < warp; ++w) pos += warpCount[w][cls];
+        cq.entries[(size_t)cls * cq.capacity + pos] = make_uint2(i, leaf);
+    }
+    __syncthreads();          // the tables are rewritten by the next iteration
+}
+
+// Work items [0, n) are spread over the whole grid, one block per blockDim.x consecutive entries per iteration.
 // (Two groups per iteration with both groups' loads issued up front were measured in round 2 and dropped: surface
-// 2.54 -> 2.85 ms per C1 frame -- the extra registers cost more than the second set of loads in flight buys,
-// profiles/r02_rejected_experiments.md.)
-template <int NC>
+// 2.54 -> 2.85 ms per C1 frame -- the extra registers cost more than the second set of loads in flight buys; an L2 hint
+// for the next iteration's three loads changed nothing, 2.78 vs 2.80 ms -- profiles/r02_rejected_experiments.md.)
+#ifndef SLR_SURFACE_BLOCK_APPEND
+#define SLR_SURFACE_BLOCK_APPEND 1
+#endif
+template <int NC, int BLOCK>
 __device__ __forceinline__ void surfaceStage(const DeviceScene& s, const RenderConstants& rc, const PathQueue& in, const HitBuffer& hits,
                                              const ClassQueue& cq, float* __restrict__ accum, WavefrontCounters* counters, uint32_t n) {
-    const uint32_t lane = threadIdx.x & 31;
     const uint32_t stride = gridDim.x * blockDim.x;
+#if SLR_SURFACE_BLOCK_APPEND
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {          // block-uniform trip count
+        const uint32_t i = base + threadIdx.x;
+        uint32_t cls = SC_NONE, leaf = SLRGPU_INVALID_ID;
+        if (i < n) surfaceItem<NC>(s, rc, in, hits, accum, i, &cls, &leaf);
+        classAppendBlock<BLOCK / 32>(cq, counters, i, cls, leaf);
+    }
+#else
+    const uint32_t lane = threadIdx.x & 31;
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
         const uint32_t i = base + lane;
         uint32_t cls = SC_NONE, leaf = SLRGPU_INVALID_ID;
         if (i < n) surfaceItem<NC>(s, rc, in, hits, accum, i, &cls, &leaf);
         classAppend(cq, counters, lane, i, cls, leaf);
     }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -372,6 +426,35 @@ __device__ __forceinline__ void materialStage(const DeviceScene& s, const Render
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint2* __restrict__ entries = cq.entries + (size_t)CLASS * cq.capacity;
+#if SLR_STAGE_PREFETCH
+    // The class-queue entry of the NEXT iteration is loaded one iteration ahead (two registers), and the path state / hit
+    // record it points at is hinted into L2 while this iteration's hit is shaded: the entry -> state indirection otherwise
+    // costs two serial DRAM round trips at the top of every iteration (ncu: 15 % of the kernel's stall samples).
+    const uint32_t first = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+    uint2 eNext = make_uint2(0, 0);
+    if (first + lane < n) eNext = entries[first + lane];
+    for (uint32_t base = first; base < n; base += stride) {
+        const uint32_t k = base + lane;
+        const uint2 e = eNext;
+        const bool more = k + stride < n;
+        if (more) eNext = entries[k + stride];
+        MaterialResult<NC> o;
+        o.clear();
+        if (k < n) materialItem<NC, CLASS>(s, rc, in, hits, e.x, e.y, o);
+        if (more) {
+            const uint32_t j = eNext.x;
+            prefetchL2(in.org + j); prefetchL2(in.dir + j); prefetchL2(in.meta + j); prefetchL2(hits.tuv + j);
+            prefetchL2(hits.id + j); prefetchL2(in.weight + j); prefetchL2(in.aux + j);
+            if (!((o.meta.z >> 8) & kFlagCameraRay)) {      // this entry carried a throughput: the next one most likely does too
+#pragma unroll
+                for (int c = 0; c < (NC == 3 ? 1 : NC / 4); ++c) prefetchL2(in.alpha + (size_t)c * in.capacity + j);
+            }
+        }
+        uint32_t npos, spos;
+        warpAppendPair(o.alive, o.shadow, counters, &npos, &spos);
+        materialWrite<NC>(out, sq, npos, spos, o);
+    }
+#else
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
         const uint32_t k = base + lane;
         MaterialResult<NC> o;
@@ -384,6 +467,7 @@ __device__ __forceinline__ void materialStage(const DeviceScene& s, const Render
         warpAppendPair(o.alive, o.shadow, counters, &npos, &spos);
         materialWrite<NC>(out, sq, npos, spos, o);
     }
+#endif
 }
 
 }  // namespace slrgpu
