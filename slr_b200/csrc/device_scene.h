@@ -56,6 +56,14 @@ struct DeviceScene {
     float integralCMF;
 };
 
+// The axis word of a node ON THE DEVICE (scene.cu patchNodeAxesKernel rewrites it at scene creation): byte 0 = 1 << topAxis,
+// byte 1 = 1 << leftAxis, byte 2 = 1 << rightAxis, byte 3 = 0 -- one AND with the ray's replicated direction signs
+// (traverse.cuh walkSetRay) answers the three ordering questions of a node visit. The table handed to
+// slrgpu_scene_create keeps QBVH::Node's plain axis numbers.
+__host__ __device__ inline uint32_t nodeAxisMasks(uint32_t top, uint32_t left, uint32_t right) {
+    return (1u << top) | ((1u << left) << 8) | ((1u << right) << 16);
+}
+
 #ifdef __CUDACC__
 // cache hint for a queue entry a later iteration / refill will stream (no register is held for it)
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }

@@ -43,8 +43,13 @@ struct OccludedSink {
     __device__ __forceinline__ void done(uint32_t i, const WalkState& w, const TraversalCounters&) const { occluded[i] = w.found ? 1 : 0; }
 };
 
+// the flat closest-hit kernel is bounded for 9 resident blocks (56 registers): it waits on dependent node fetches from a
+// scene larger than L2, so a resident block more is worth more than the registers (C5 3838 Mrays/s at 62 registers / 8 blocks)
+#ifndef SLR_INTERSECT_MIN_BLOCKS
+#define SLR_INTERSECT_MIN_BLOCKS 9
+#endif
 template <bool INSTANCES, bool COUNT, bool ALPHA>
-__global__ void __launch_bounds__(kIntersectBlock)
+__global__ void __launch_bounds__(kIntersectBlock, (!INSTANCES && !COUNT && !ALPHA) ? SLR_INTERSECT_MIN_BLOCKS : 1)
 intersectBatchKernel(const DeviceScene s, SlrGpuRayBatch rays, uint32_t n, SlrGpuHitBatch hits, int* status) {
     TraversalCounters cnt = {0, 0};
     bool overflow = false;

@@ -439,6 +439,15 @@ __global__ void patchLeafSurfaceInfoKernel(float4* leaves, uint32_t numLeaves, c
     }
 }
 
+// QBVH::Node's three axis numbers -> the three axis masks the walk tests (device_scene.h nodeAxisMasks), on the device copy
+__global__ void patchNodeAxesKernel(float4* nodes, uint32_t numNodes) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < numNodes; i += gridDim.x * blockDim.x) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(nodes + (size_t)i * 8 + 7);
+        const uint32_t a = *w;
+        *w = nodeAxisMasks(a & 0xFFu, (a >> 8) & 0xFFu, (a >> 16) & 0xFFu);
+    }
+}
+
 }  // namespace slrgpu
 
 using namespace slrgpu;
@@ -549,6 +558,14 @@ SLRGPU_API int slrgpu_scene_create(const SlrGpuSceneDesc* d, int device, SlrGpuS
         cudaError_t pe = cudaGetLastError();
         if (pe == cudaSuccess) pe = cudaDeviceSynchronize();
         if (pe != cudaSuccess) { slrgpu_scene_destroy(sc); return cudaFail(pe, "patchLeafSurfaceInfoKernel"); }
+    }
+
+    {
+        const uint32_t blocks = (uint32_t)std::min<uint64_t>(((uint64_t)d->num_bvh_nodes + 255) / 256, 148 * 8);
+        patchNodeAxesKernel<<<blocks, 256>>>(const_cast<float4*>(v.nodes), d->num_bvh_nodes);
+        cudaError_t pe = cudaGetLastError();
+        if (pe == cudaSuccess) pe = cudaDeviceSynchronize();
+        if (pe != cudaSuccess) { slrgpu_scene_destroy(sc); return cudaFail(pe, "patchNodeAxesKernel"); }
     }
 
     v.numNodes = d->num_bvh_nodes; v.numLeaves = d->num_leaf_records; v.numInstances = d->num_instances;

@@ -234,19 +234,56 @@ __device__ __forceinline__ void classAppendBlock(const ClassQueue& cq, Wavefront
 // (Two groups per iteration with both groups' loads issued up front were measured in round 2 and dropped: surface
 // 2.54 -> 2.85 ms per C1 frame -- the extra registers cost more than the second set of loads in flight buys; an L2 hint
 // for the next iteration's three loads changed nothing, 2.78 vs 2.80 ms -- profiles/r02_rejected_experiments.md.)
-#ifndef SLR_SURFACE_BLOCK_APPEND
-#define SLR_SURFACE_BLOCK_APPEND 1
+// SLR_SURFACE_APPEND: 0 = one atomic per (warp, class) and 32 entries; 1 = one per (block, class) and blockDim entries
+// (classAppendBlock, two barriers per iteration); 2 = one per (warp, class) and kSurfaceGroups x 32 entries, no barrier.
+#ifndef SLR_SURFACE_APPEND
+#define SLR_SURFACE_APPEND 2
 #endif
+constexpr int kSurfaceGroups = 4;
+
 template <int NC, int BLOCK>
 __device__ __forceinline__ void surfaceStage(const DeviceScene& s, const RenderConstants& rc, const PathQueue& in, const HitBuffer& hits,
                                              const ClassQueue& cq, float* __restrict__ accum, WavefrontCounters* counters, uint32_t n) {
     const uint32_t stride = gridDim.x * blockDim.x;
-#if SLR_SURFACE_BLOCK_APPEND
+#if SLR_SURFACE_APPEND == 1
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {          // block-uniform trip count
         const uint32_t i = base + threadIdx.x;
         uint32_t cls = SC_NONE, leaf = SLRGPU_INVALID_ID;
         if (i < n) surfaceItem<NC>(s, rc, in, hits, accum, i, &cls, &leaf);
         classAppendBlock<BLOCK / 32>(cq, counters, i, cls, leaf);
+    }
+#elif SLR_SURFACE_APPEND == 2
+    // A warp takes kSurfaceGroups x 32 consecutive entries per iteration and reserves their places in the class queues with
+    // ONE atomic per class: the groups' per-class counts are summed in a 16-word table of shared memory owned by the warp
+    // (shared-memory atomics hand every group its offset inside the warp's range), lanes 0-15 then reserve one class each.
+    __shared__ uint32_t table[BLOCK / 32][16];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* mine = table[warp];
+    for (uint32_t base = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * kSurfaceGroups; base < n; base += stride * kSurfaceGroups) {
+        if (lane < 16) mine[lane] = 0;
+        __syncwarp();
+        uint32_t cls[kSurfaceGroups], leaf[kSurfaceGroups], off[kSurfaceGroups];
+#pragma unroll 1
+        for (int g = 0; g < kSurfaceGroups; ++g) {
+            const uint32_t i = base + g * 32 + lane;
+            uint32_t c = SC_NONE, l = SLRGPU_INVALID_ID, o = 0;
+            if (i < n) surfaceItem<NC>(s, rc, in, hits, accum, i, &c, &l);
+            const unsigned active = __ballot_sync(0xFFFFFFFFu, c != SC_NONE);
+            if (c != SC_NONE) {
+                const unsigned grp = __match_any_sync(active, c);
+                const int leader = __ffs(grp) - 1;
+                if ((int)lane == leader) o = atomicAdd(&mine[c], (uint32_t)__popc(grp));       // this group's offset in the warp's range
+                o = __shfl_sync(grp, o, leader) + __popc(grp & ((1u << lane) - 1u));
+            }
+            cls[g] = c; leaf[g] = l; off[g] = o;
+        }
+        __syncwarp();
+        if (lane < 16) { const uint32_t total = mine[lane]; if (total) mine[lane] = atomicAdd(&counters->classCount[lane], total); }
+        __syncwarp();
+#pragma unroll 1
+        for (int g = 0; g < kSurfaceGroups; ++g)
+            if (cls[g] != SC_NONE) cq.entries[(size_t)cls[g] * cq.capacity + mine[cls[g]] + off[g]] = make_uint2(base + g * 32 + lane, leaf[g]);
+        __syncwarp();
     }
 #else
     const uint32_t lane = threadIdx.x & 31;

@@ -71,6 +71,28 @@ __device__ __forceinline__ uint32_t slab4NearFar(const float4 nx, const float4 n
     return mask;
 }
 
+// The same test with the outcome applied to the child words: lane l's child if its box is hit, else kEmptyChild
+// (the predicates feed four selects directly; building a mask first and testing its bits again cost ~12 instructions).
+__device__ __forceinline__ uint4 slab4Children(const float4 nx, const float4 ny, const float4 nz,
+                                               const float4 fx, const float4 fy, const float4 fz,
+                                               const Ray& r, float ix, float iy, float iz, const uint4 kids) {
+    uint4 c;
+#define SLAB_LANE(L)                                                        \
+    {                                                                       \
+        float tn = r.tmin, tf = r.tmax;                                     \
+        tn = fmaxf(__fmul_rn(__fsub_rn(nx.L, r.ox), ix), tn);                                 \
+        tn = fmaxf(__fmul_rn(__fsub_rn(ny.L, r.oy), iy), tn);                                 \
+        tn = fmaxf(__fmul_rn(__fsub_rn(nz.L, r.oz), iz), tn);                                 \
+        tf = fminf(__fmul_rn(__fsub_rn(fx.L, r.ox), ix), tf);                                 \
+        tf = fminf(__fmul_rn(__fsub_rn(fy.L, r.oy), iy), tf);                                 \
+        tf = fminf(__fmul_rn(__fsub_rn(fz.L, r.oz), iz), tf);                                 \
+        c.L = (tn <= tf) ? kids.L : 0xFFFFFFFFu;                            \
+    }
+    SLAB_LANE(x) SLAB_LANE(y) SLAB_LANE(z) SLAB_LANE(w)
+#undef SLAB_LANE
+    return c;
+}
+
 // a*b - c*d and a*b + c*d + e*f, left to right, every product and sum rounded on its own
 __device__ __forceinline__ float cross2(float a, float b, float c, float d) { return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d)); }
 __device__ __forceinline__ float dot3(float a, float b, float c, float d, float e, float f) {
@@ -219,16 +241,12 @@ struct LeafQueue {
     uint32_t first, count;               // current range of leaf records
     uint32_t pending0, pending1, pending2;   // packed leaf child words still to come, kEmptyChild = none
     __device__ __forceinline__ void clear() { first = 0; count = 0; pending0 = pending1 = pending2 = kEmptyChild; }
+    // the next waiting leaf child becomes the current range (a leaf child without records never enters the queue)
     __device__ __forceinline__ void next() {
-        count = 0;
-#pragma unroll
-        for (int k = 0; k < 3 && count == 0; ++k) {
-            const uint32_t c = pending0;
-            pending0 = pending1; pending1 = pending2; pending2 = kEmptyChild;
-            if (c == kEmptyChild) return;
-            first = c & 0x07FFFFFFu;
-            count = (c >> 27) & 0xFu;
-        }
+        const uint32_t c = pending0;
+        pending0 = pending1; pending1 = pending2; pending2 = kEmptyChild;
+        first = c & 0x07FFFFFFu;
+        count = c == kEmptyChild ? 0u : (c >> 27) & 0xFu;
     }
 };
 
@@ -246,14 +264,15 @@ struct InstanceWalkState {
     uint32_t curInst;        // SLRGPU_INVALID_ID at the top level
 };
 
-// pos bits 0-2: direction component >= 0 (child ordering, QBVH.h:309-312); bits 8-10: invDir > 0 per axis
-// (which plane is the near one, QBVH.h:68-73) -- the two differ for a component of -0.0
+// pos: direction component >= 0 per axis (child ordering, QBVH.h:309-312) in bits 0-2, repeated in bits 8-10 and 16-18
+// so that one AND with a node's three axis masks (kNodeAxisMasks below) answers all three ordering questions; bits
+// 24-26: invDir > 0 per axis (which plane is the near one, QBVH.h:68-73) -- the two differ for a component of -0.0
+constexpr uint32_t kPosNearX = 0x1000000u, kPosNearY = 0x2000000u, kPosNearZ = 0x4000000u;
 __device__ __forceinline__ void walkSetRay(WalkState& w) {
     w.ix = __frcp_rn(w.r.dx); w.iy = __frcp_rn(w.r.dy); w.iz = __frcp_rn(w.r.dz);
-    w.pos = (w.r.dx >= 0.0f ? 1u : 0u) | (w.r.dy >= 0.0f ? 2u : 0u) | (w.r.dz >= 0.0f ? 4u : 0u) |
-            (w.ix > 0.0f ? 0x100u : 0u) | (w.iy > 0.0f ? 0x200u : 0u) | (w.iz > 0.0f ? 0x400u : 0u);
+    w.pos = ((w.r.dx >= 0.0f ? 1u : 0u) | (w.r.dy >= 0.0f ? 2u : 0u) | (w.r.dz >= 0.0f ? 4u : 0u)) * 0x010101u |
+            (w.ix > 0.0f ? kPosNearX : 0u) | (w.iy > 0.0f ? kPosNearY : 0u) | (w.iz > 0.0f ? kPosNearZ : 0u);
 }
-
 // The node half of a step: pops one entry -- a node: 4-box test, push the inner children that were hit (far to near),
 // queue the leaf children that were hit (near to far) in `leaves`; or the return marker of an instance.
 // PREFETCH (the persistent tail kernel only): every inner child a node visit pushes and every leaf child it queues is
@@ -280,58 +299,53 @@ __device__ __forceinline__ void walkNode(const DeviceScene& s, WalkState& w, Ins
     } else {
         const float4* n = s.nodes + (size_t)entry * 8;
         // lo planes at n+0..2, hi planes at n+3..5: near = lo where invDir > 0, else hi
-        const uint32_t ox = (w.pos & 0x100u) ? 0u : 3u, oy = (w.pos & 0x200u) ? 0u : 3u, oz = (w.pos & 0x400u) ? 0u : 3u;
+        const uint32_t ox = (w.pos & kPosNearX) ? 0u : 3u, oy = (w.pos & kPosNearY) ? 0u : 3u, oz = (w.pos & kPosNearZ) ? 0u : 3u;
         const float4 nx = ldg4(n + ox), ny = ldg4(n + 1 + oy), nz = ldg4(n + 2 + oz);
         const float4 fx = ldg4(n + 3 - ox), fy = ldg4(n + 4 - oy), fz = ldg4(n + 5 - oz);
-        // the child words and split axes are fetched with the planes, not after the box test: one memory latency per
-        // step instead of two (ncu: the first use of `kids` was the hottest line of the extend kernel)
+        // the child words are fetched with the planes, not after the box test: one memory latency per step instead of two
         const uint4 kids = __ldg(reinterpret_cast<const uint4*>(n + 6));
-        const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(n + 7));
+        const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(n + 7));      // (ptxas sinks this one behind the box test: an L1 hit by then, the line has just arrived)
         if (COUNT) ++cnt.nodes;
-        const uint32_t mask = slab4NearFar(nx, ny, nz, fx, fy, fz, r, w.ix, w.iy, w.iz);
-        if (mask != 0) {
-            const uint32_t T = (w.pos >> (axes & 0xFF)) & 1u;
-            const uint32_t L = (w.pos >> ((axes >> 8) & 0xFF)) & 1u;
-            const uint32_t R = (w.pos >> ((axes >> 16) & 0xFF)) & 1u;
-            // visiting order (OrderTable, QBVH.h:309-312): near side pair first, near child first inside a pair
-            const uint32_t l0 = L ? 0u : 1u, r0 = R ? 2u : 3u;
-            uint32_t order[4];
-            order[0] = T ? l0 : r0;        order[1] = T ? (l0 ^ 1u) : (r0 ^ 1u);
-            order[2] = T ? r0 : l0;        order[3] = T ? (r0 ^ 1u) : (l0 ^ 1u);
-            uint32_t ch[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t lane = order[i];
-                uint32_t c = lane == 0 ? kids.x : lane == 1 ? kids.y : lane == 2 ? kids.z : kids.w;
-                ch[i] = ((mask >> lane) & 1u) ? c : kEmptyChild;
-            }
-#pragma unroll
-            for (int i = 3; i >= 0; --i) {
-                const uint32_t c = ch[i];
-                if (c == kEmptyChild || (c >> 31)) continue;
-                if (w.sp >= kStackSize) { overflow = true; continue; }
-                stack[w.sp++] = c & 0x07FFFFFFu;
-                w.top = c & 0x07FFFFFFu;
-                if (PREFETCH) prefetchL1(s.nodes + (size_t)(c & 0x07FFFFFFu) * 8);
-            }
-            // leaf children in visiting order: the first becomes the current range, up to three wait
-            uint32_t q0 = kEmptyChild, q1 = kEmptyChild, q2 = kEmptyChild, q3 = kEmptyChild;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t c = ch[i];
-                if (c != kEmptyChild && (c >> 31)) {
-                    if (PREFETCH) prefetchL1(s.leaves + (size_t)(c & 0x07FFFFFFu) * 3);
-                    if (q0 == kEmptyChild) q0 = c;
-                    else if (q1 == kEmptyChild) q1 = c;
-                    else if (q2 == kEmptyChild) q2 = c;
-                    else q3 = c;
+        // children in storage order (left pair 0 1, right pair 2 3), the lanes whose box was missed emptied
+        const uint4 c = slab4Children(nx, ny, nz, fx, fy, fz, r, w.ix, w.iy, w.iz, kids);
+        if ((c.x & c.y & c.z & c.w) != kEmptyChild) {
+            // Visiting order (OrderTable, QBVH.h:309-312): the pair on the near side of the top split first, inside a pair
+            // the child on the near side of the pair's split first -- as three conditional swaps, branch free. (The first
+            // version picked the four children through an index table; ptxas compiled the indexed picks into ~220
+            // instructions of branches per node visit, more than the box tests themselves.)
+            const uint32_t side = w.pos & axes;
+            const bool T = (side & 0x0000FFu) != 0, L = (side & 0x00FF00u) != 0, R = (side & 0xFF0000u) != 0;
+            const uint32_t a0 = L ? c.x : c.y, a1 = L ? c.y : c.x;
+            const uint32_t b0 = R ? c.z : c.w, b1 = R ? c.w : c.z;
+            const uint32_t o0 = T ? a0 : b0, o1 = T ? a1 : b1, o2 = T ? b0 : a0, o3 = T ? b1 : a1;
+            // inner children (bit 31 clear; the empty word has it set) are pushed far to near
+            if (w.sp + 4 <= kStackSize) {
+#define SLR_PUSH(o) if ((int32_t)(o) >= 0) { const uint32_t k = (o) & 0x07FFFFFFu; stack[w.sp++] = k; w.top = k; if (PREFETCH) prefetchL1(s.nodes + (size_t)k * 8); }
+                SLR_PUSH(o3) SLR_PUSH(o2) SLR_PUSH(o1) SLR_PUSH(o0)
+#undef SLR_PUSH
+            } else {
+                const uint32_t ord[4] = {o0, o1, o2, o3};
+                for (int i = 3; i >= 0; --i) {
+                    if ((int32_t)ord[i] < 0) continue;
+                    if (w.sp >= kStackSize) { overflow = true; continue; }
+                    stack[w.sp++] = ord[i] & 0x07FFFFFFu;
+                    w.top = ord[i] & 0x07FFFFFFu;
                 }
             }
+            // leaf children (bit 31 set, not the empty word: as a signed number below -1) that hold records, in visiting
+            // order: the first becomes the current range, up to three wait
+#define SLR_IS_LEAF(o) ((int32_t)(o) < -1 && ((o) & 0x78000000u) != 0)
+            uint32_t q0 = kEmptyChild, q1 = kEmptyChild, q2 = kEmptyChild, q3 = kEmptyChild;
+            if (SLR_IS_LEAF(o3)) { q0 = o3; }
+            if (SLR_IS_LEAF(o2)) { q1 = q0; q0 = o2; }
+            if (SLR_IS_LEAF(o1)) { q2 = q1; q1 = q0; q0 = o1; }
+            if (SLR_IS_LEAF(o0)) { q3 = q2; q2 = q1; q1 = q0; q0 = o0; }
+#undef SLR_IS_LEAF
             if (q0 != kEmptyChild) {
+                if (PREFETCH) prefetchL1(s.leaves + (size_t)(q0 & 0x07FFFFFFu) * 3);
                 leaves.first = q0 & 0x07FFFFFFu;
                 leaves.count = (q0 >> 27) & 0xFu;
                 leaves.pending0 = q1; leaves.pending1 = q2; leaves.pending2 = q3;
-                if (leaves.count == 0) leaves.next();
             }
         }
     }
@@ -370,7 +384,9 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
         if (--leaves.count == 0) leaves.next();
         const uint32_t id = __float_as_uint(a.w);
         if (COUNT) ++cnt.tris;
-        if (id & 0x80000000u) {
+        // (a flat scene holds no instance records -- slrgpu_scene_create refuses one without an instance table -- so the flat
+        // instantiations do not test for them: the three loads of a record issue together instead of a.w first)
+        if (INSTANCES && (id & 0x80000000u)) {
             if constexpr (INSTANCES) {
                 // nested instancing is rejected at scene build; no room for marker + root is reported as overflow
                 if (iw.curInst == SLRGPU_INVALID_ID) {

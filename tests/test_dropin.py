@@ -92,7 +92,13 @@ def test_dropin_renders_like_the_reference(name, size, spp, tmp_path):
         hs = capi.read_scene(path)
     mine, _ = capi.host_render(hs, size, size, spp, device=0)
     mine = capi.accum_to_rgb(mine, 1.0 / spp)
-    np.testing.assert_allclose(ru.block_means(capi.accum_to_rgb(sensor, 1.0 / spp), 8), ru.block_means(mine, 8), rtol=2e-3, atol=1e-6)
+    if name == "nested":
+        # the two producers expand the nesting on their own (different object order in the rebuilt aggregates, so different
+        # trees and light lists): the same estimator, not the same samples -- held to the reference's noise floor instead
+        got2 = ru.rel_rmse(mine, ref1, trim=0.005)
+        assert got2 <= 1.25 * floor, f"host library: relRMSE {got2:.4f} vs noise floor {floor:.4f}"
+    else:
+        np.testing.assert_allclose(ru.block_means(capi.accum_to_rgb(sensor, 1.0 / spp), 8), ru.block_means(mine, 8), rtol=2e-3, atol=1e-6)
     # the progressive BMPs the renderer wrote through the reference's own ImageSensor::saveImage
     assert os.path.exists(os.path.join(os.path.dirname(path), "000.bmp"))
 
