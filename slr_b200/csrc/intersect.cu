@@ -2,7 +2,6 @@
 // QBVH::intersect, QBVH.h:295-337) and occlusion (Scene::testVisibility, SurfaceObject.cpp:418-430).
 // MUST be compiled with -fmad=false (see traverse.cuh).
 #define SLR_WALK_ONE_RECORD_PER_STEP 1      // measured faster for ray batches (traverse.cuh walkStep)
-#define SLR_WALK_LOAD256_TU
 #include "traverse.cuh"
 #include <algorithm>
 #include <cstring>

@@ -5,7 +5,6 @@
 //                           query and keeps only the boolean; any-hit with early exit gives the same boolean)
 // MUST be compiled with -fmad=false like intersect.cu: the renderer's rays use the bit-exact traversal.
 #define SLR_WALK_DEFER_SINK 2      // results handed to the sink at the refill point: instanced instantiations only (traverse.cuh)
-#define SLR_WALK_LOAD256_TU
 #include "ray_io.cuh"
 
 #ifndef SLR_TRACE_MIN_BLOCKS

@@ -45,19 +45,6 @@ struct TraversalCounters {
 };
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
-// SLR_WALK_LOAD256 is honoured only by the translation units of the throughput kernels (trace.cu, intersect.cu define
-// SLR_WALK_LOAD256_TU): nvcc 12.9 crashes on the 8-output load inside the larger kernels of tail.cu / bpt.cu
-#if !defined(SLR_WALK_LOAD256) || !defined(SLR_WALK_LOAD256_TU)
-#undef SLR_WALK_LOAD256
-#define SLR_WALK_LOAD256 0
-#endif
-// 32 bytes (two consecutive float4, 32-byte aligned) through the read-only path in one instruction
-__device__ __forceinline__ void ldg256(const float4* p, float4* a, float4* b) {
-    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-        : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w), "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w) : "l"(p));
-}
-__device__ __forceinline__ float4 pick4(bool c, const float4& a, const float4& b) { return make_float4(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z, c ? a.w : b.w); }
-
 // 4-lane slab test; returns the 4-bit mask of lanes whose [tNear, tFar] is non-empty. The near / far planes
 // are already selected by the caller (the selection depends only on the sign of the ray direction, so the
 // walk fetches lo or hi per axis by ADDRESS instead of fetching both and selecting per lane).
@@ -311,27 +298,14 @@ __device__ __forceinline__ void walkNode(const DeviceScene& s, WalkState& w, Ins
     } else {
         const float4* n = s.nodes + (size_t)entry * 8;
         // lo planes at n+0..2, hi planes at n+3..5: near = lo where invDir > 0, else hi
-#if SLR_WALK_LOAD256
-        // the whole 128-byte node as four 32-byte loads (LDG.E.256, new on sm_100), near / far planes picked in registers:
-        // with the lanes of a warp at 32 different nodes every load instruction costs the L1 one tag lookup per lane,
-        // whatever its width -- four instead of eight per node visit
-        float4 lx, ly, lz, hx, hy, hz;
-        uint4 kids, last;
-        ldg256(n, &lx, &ly); ldg256(n + 2, &lz, &hx); ldg256(n + 4, &hy, &hz);
-        { float4 k, l; ldg256(n + 6, &k, &l); kids = make_uint4(__float_as_uint(k.x), __float_as_uint(k.y), __float_as_uint(k.z), __float_as_uint(k.w)); last.x = __float_as_uint(l.x); }
-        const bool px = (w.pos & kPosNearX) != 0, py = (w.pos & kPosNearY) != 0, pz = (w.pos & kPosNearZ) != 0;
-        const float4 nx = pick4(px, lx, hx), fx = pick4(px, hx, lx);
-        const float4 ny = pick4(py, ly, hy), fy = pick4(py, hy, ly);
-        const float4 nz = pick4(pz, lz, hz), fz = pick4(pz, hz, lz);
-        const uint32_t axes = last.x;
-#else
         const uint32_t ox = (w.pos & kPosNearX) ? 0u : 3u, oy = (w.pos & kPosNearY) ? 0u : 3u, oz = (w.pos & kPosNearZ) ? 0u : 3u;
         const float4 nx = ldg4(n + ox), ny = ldg4(n + 1 + oy), nz = ldg4(n + 2 + oz);
         const float4 fx = ldg4(n + 3 - ox), fy = ldg4(n + 4 - oy), fz = ldg4(n + 5 - oz);
         // the child words are fetched with the planes, not after the box test: one memory latency per step instead of two
         const uint4 kids = __ldg(reinterpret_cast<const uint4*>(n + 6));
         const uint32_t axes = __ldg(reinterpret_cast<const uint32_t*>(n + 7));      // (ptxas sinks this one behind the box test: an L1 hit by then, the line has just arrived)
-#endif
+        // (Measured and dropped, round 2: the node as four 32-byte loads -- LDG.E.256, new on sm_100 -- with the near / far
+        // planes picked in registers: C1 extend 8.67 vs 8.73 ms, C4 unchanged, C5 3685 vs 3870 Mrays/s.)
         if (COUNT) ++cnt.nodes;
         // children in storage order (left pair 0 1, right pair 2 3), the lanes whose box was missed emptied
         const uint4 c = slab4Children(nx, ny, nz, fx, fy, fz, r, w.ix, w.iy, w.iz, kids);
