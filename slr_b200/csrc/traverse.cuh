@@ -17,6 +17,7 @@
 // Data movement: a node is 128 B = eight 16-byte loads through the read-only path (LDG.E.128);
 // a leaf record is 48 B = three. One thread owns one ray; the 64-entry stack lives in local memory.
 #pragma once
+#include <cstddef>
 #include "device_scene.h"
 #include "motion.cuh"
 #include "textures.cuh"
@@ -24,6 +25,7 @@
 namespace slrgpu {
 
 constexpr int kStackSize = 64;            // QBVH.h:299
+static_assert(sizeof(SlrGpuInstance) % 16 == 0 && offsetof(SlrGpuInstance, mat_inv) % 16 == 0, "walkStep loads mat_inv as float4");
 constexpr uint32_t kEmptyChild = 0xFFFFFFFFu;
 
 struct Ray {
@@ -387,6 +389,8 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
         if (COUNT) ++cnt.tris;
         // (a flat scene holds no instance records -- slrgpu_scene_create refuses one without an instance table -- so the flat
         // instantiations do not test for them: the three loads of a record issue together instead of a.w first)
+        // (Measured and dropped for the instanced kernels: running the triangle test before the record is told apart, so
+        // that its three loads issue together there too -- C4 extend 50.1 -> 52.1 ms.)
         if (INSTANCES && (id & 0x80000000u)) {
             if constexpr (INSTANCES) {
                 // nested instancing is rejected at scene build; no room for marker + root is reported as overflow
@@ -409,8 +413,14 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
                             mulPoint(xf + 16, r.ox, r.oy, r.oz, &lx, &ly, &lz);
                             mulVector(xf + 16, r.dx, r.dy, r.dz, &mx, &my, &mz);
                         } else {
-                            mulPoint(inst->mat_inv, r.ox, r.oy, r.oz, &lx, &ly, &lz);
-                            mulVector(inst->mat_inv, r.dx, r.dy, r.dz, &mx, &my, &mz);
+                            // the inverse matrix as four 16-byte loads (the instance table is 256-byte aligned on the
+                            // device and a record is 160 bytes: mat_inv sits on a 16-byte boundary)
+                            float mi[16];
+                            const float4* q = reinterpret_cast<const float4*>(inst->mat_inv);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) { const float4 col = __ldg(q + c); mi[4 * c] = col.x; mi[4 * c + 1] = col.y; mi[4 * c + 2] = col.z; mi[4 * c + 3] = col.w; }
+                            mulPoint(mi, r.ox, r.oy, r.oz, &lx, &ly, &lz);
+                            mulVector(mi, r.dx, r.dy, r.dz, &mx, &my, &mz);
                         }
                         r.ox = lx; r.oy = ly; r.oz = lz; r.dx = mx; r.dy = my; r.dz = mz;
                         walkSetRay(w);

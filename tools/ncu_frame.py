@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--warm", type=int, default=2)
     args = ap.parse_args()
     args.ref_scenes = os.path.join(ROOT, "oracle", "_ref", "TestScenes")
+    # the device-driven wave loop is a conditional graph node, whose kernels ncu cannot profile one by one: take the
+    # host-driven loop (same kernels, two waves per plain graph launch)
+    os.environ.setdefault("SLRGPU_HOST_LOOP", "1")
     import torch
     from slr_b200 import capi, render_bench
     torch.cuda.set_device(0)

@@ -1,0 +1,10 @@
+#!/bin/bash
+# round 2, GPU call 20: ncu record of the current pipeline on C1 -- launch list of one frame, full captures of wave 0 and wave 2
+set -u
+O=gpurun_out
+NCU_L="ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv"
+timeout 900 $NCU_L --log-file $O/r2D_launches_c1.csv python tools/ncu_frame.py --workload cornell_spheres > $O/r2D_ncu_c1.log 2>&1; echo "launch list c1 rc=$?"
+K='materialKernel|extendKernel|surfaceKernel|shadowKernel|raygenKernel'
+timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"$K" -c 7 -f -o $O/r2D_prof_c1_w0 python tools/ncu_frame.py --workload cornell_spheres > $O/r2D_ncu_full_c1_w0.log 2>&1; echo "full c1 wave 0 rc=$?"
+timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"$K" -s 14 -c 7 -f -o $O/r2D_prof_c1_w2 python tools/ncu_frame.py --workload cornell_spheres > $O/r2D_ncu_full_c1_w2.log 2>&1; echo "full c1 wave 2 rc=$?"
+ls -la $O/*.ncu-rep; du -sh $O
