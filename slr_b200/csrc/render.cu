@@ -137,6 +137,12 @@ surfaceKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitBu
     surfaceStage<NC, kSurfaceBlock>(s, rc, in, hits, cq, accum, counters, counters->numPaths);
 }
 
+template <int NC>
+__global__ void __launch_bounds__(128)
+emissionKernel(const DeviceScene s, PathQueue in, HitBuffer hits, ClassQueue cq, float* __restrict__ accum, const WavefrontCounters* counters) {
+    emissionStage<NC>(s, in, hits, cq, accum, counters->classCount[kEmissionRow]);
+}
+
 template <int NC, int CLASS>
 __global__ void __launch_bounds__(kMaterialBlock, materialMinBlocks(CLASS))
 materialKernel(const DeviceScene s, const RenderConstants rc, PathQueue in, HitBuffer hits, ClassQueue cq, PathQueue out, ShadowQueue sq,
@@ -207,8 +213,8 @@ struct RenderWorkspace {
     cudaStream_t stream = nullptr;               // non-blocking stream of the host-buffer entry point (graph capture needs one)
     // the material kernels of a wave are independent of each other: they run on side streams, forked from and
     // joined to the render stream with events (parallel branches of the captured graph)
-    cudaStream_t side[SC_COUNT] = {};
-    cudaEvent_t forkEvent = nullptr, joinEvent[SC_COUNT] = {};
+    cudaStream_t side[kClassQueueRows] = {};
+    cudaEvent_t forkEvent = nullptr, joinEvent[kClassQueueRows] = {};
     // the instantiated device-driven loop of the last render call and everything that is baked into its kernel nodes: a
     // call with the same scene view, constants and buffers (a bench / progressive loop) relaunches it without re-capture
     cudaGraph_t loopGraph = nullptr;
@@ -303,13 +309,13 @@ static int acquireWorkspace(SlrGpuScene* sc, uint32_t P, RenderWorkspace** out) 
     if (!rc) rc = w->alloc(&w->sq.contrib, (uint64_t)P * quarters);
     w->sq.time = nullptr;
     if (!rc && sc->hasMotion) rc = w->alloc(&w->sq.time, P);
-    if (!rc) rc = w->alloc(&w->cq.entries, (uint64_t)P * SC_COUNT);
+    if (!rc) rc = w->alloc(&w->cq.entries, (uint64_t)P * kClassQueueRows);
     if (!rc) rc = w->alloc(&w->dCounters, 1);
     if (!rc) rc = w->alloc(&w->dWaveLog, kWaveLogSize);
     if (!rc) { cudaError_t e = cudaMallocHost(&w->hCounters, sizeof(WavefrontCounters) * kRing); if (e != cudaSuccess) rc = cudaFail(e, "cudaMallocHost"); }
     for (int k = 0; k < kRing && !rc; ++k) { cudaError_t e = cudaEventCreateWithFlags(&w->ringEvents[k], cudaEventDisableTiming); if (e != cudaSuccess) rc = cudaFail(e, "cudaEventCreate"); }
     if (!rc) { cudaError_t e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking); if (e != cudaSuccess) rc = cudaFail(e, "cudaStreamCreate"); }
-    for (int k = 0; k < (int)SC_COUNT && !rc; ++k) {
+    for (int k = 0; k < (int)kClassQueueRows && !rc; ++k) {
         cudaError_t e = cudaStreamCreateWithFlags(&w->side[k], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->joinEvent[k], cudaEventDisableTiming);
         if (e != cudaSuccess) rc = cudaFail(e, "cudaStreamCreate(side)");
@@ -353,6 +359,13 @@ static void launchShadeStage(const SlrGpuScene* sc, const RenderConstants& rc, c
     if (m & (1u << SC_MF_BRDF)) launchMaterial<NC, SC_MF_BRDF>(sc, rc, w, cur, grid, stream);
     if (m & (1u << SC_MF_BSDF)) launchMaterial<NC, SC_MF_BSDF>(sc, rc, w, cur, grid, stream);
     if (m & (1u << SC_GENERIC)) launchMaterial<NC, SC_GENERIC>(sc, rc, w, cur, grid, stream);
+    {   // the entries that see emission, beside the material kernels (both only read the current queue)
+        cudaStream_t st = w.side[kEmissionRow];
+        cudaStreamWaitEvent(st, w.forkEvent, 0);
+        emissionKernel<NC><<<std::min(grid, (uint32_t)(sc->numSMs * 4)), 128, 0, st>>>(sc->dev, w.q[cur], w.hits, w.cq, accum, w.dCounters);
+        cudaEventRecord(w.joinEvent[kEmissionRow], st);
+        cudaStreamWaitEvent(stream, w.joinEvent[kEmissionRow], 0);
+    }
     mark(3);
 }
 
@@ -464,7 +477,7 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
         timer.mark(5);
         return r;
     };
-    const uint32_t launchesPerWave = 6u + (uint32_t)__builtin_popcount(sc->classMask);
+    const uint32_t launchesPerWave = 7u + (uint32_t)__builtin_popcount(sc->classMask);      // raygen, begin, extend, surface, emission, shadow, end + one per class
     unsigned long long wave = 0, launches = 0, round = 0;
     auto enqueueWave = [&](int cur) -> int {
         timer.mark(0);

@@ -131,9 +131,12 @@ __device__ __forceinline__ SurfaceInput surfaceLoad(const PathQueue& in, const H
     return x;
 }
 
+// emitOut == nullptr: the emission seen by the arriving ray is added here (the tail kernel); else *emitOut says whether the
+// entry sees emission (1 = an emitter was hit, 2 = the environment) and the caller queues it for emissionKernel.
 template <int NC>
 __device__ __forceinline__ void surfaceItem(const DeviceScene& s, const RenderConstants& rc, const PathQueue& in, const HitBuffer& hits,
-                                            float* __restrict__ accum, uint32_t i, const SurfaceInput& x, uint32_t* clsOut, uint32_t* leafOut) {
+                                            float* __restrict__ accum, uint32_t i, const SurfaceInput& x, uint32_t* clsOut, uint32_t* leafOut,
+                                            uint32_t* emitOut = nullptr) {
     uint32_t cls = SC_NONE, leaf = SLRGPU_INVALID_ID;
     uint32_t info = x.info;
     const uint4 meta = x.meta;
@@ -153,7 +156,10 @@ __device__ __forceinline__ void surfaceItem(const DeviceScene& s, const RenderCo
             }
             emitting = ((info >> 8) & 1u) != 0;
         }
-        if (emitting) surfaceEmission<NC>(s, in, hits, i, meta, flags, isEnv, accum);
+        if (emitting) {
+            if (emitOut) *emitOut = isEnv ? 2u : 1u;
+            else surfaceEmission<NC>(s, in, hits, i, meta, flags, isEnv, accum);
+        }
         bool cont = !isEnv;
         if (cont && !cameraRay) {
             // Russian roulette; initY = importance of a unit spectrum = 1. importance(alpha) was left in
@@ -177,8 +183,8 @@ __device__ __forceinline__ void surfaceItem(const DeviceScene& s, const RenderCo
 }
 template <int NC>
 __device__ __forceinline__ void surfaceItem(const DeviceScene& s, const RenderConstants& rc, const PathQueue& in, const HitBuffer& hits,
-                                            float* __restrict__ accum, uint32_t i, uint32_t* clsOut, uint32_t* leafOut) {
-    surfaceItem<NC>(s, rc, in, hits, accum, i, surfaceLoad(in, hits, i), clsOut, leafOut);
+                                            float* __restrict__ accum, uint32_t i, uint32_t* clsOut, uint32_t* leafOut, uint32_t* emitOut = nullptr) {
+    surfaceItem<NC>(s, rc, in, hits, accum, i, surfaceLoad(in, hits, i), clsOut, leafOut, emitOut);
 }
 
 // append to the class queues: one atomic per (warp, class)
@@ -194,48 +200,13 @@ __device__ __forceinline__ void classAppend(const ClassQueue& cq, WavefrontCount
     }
 }
 
-// append to the class queues, one atomic per (BLOCK, class): the warps' per-class counts meet in shared memory, the first
-// 16 threads reserve the block's ranges (one ATOMG with a lane per class), every entry then takes its place behind the
-// entries of the warps before it. With one atomic per warp the stage was bound by the return latency of half a million
-// atomics on ONE address per wave (classCount of the dominant class): ncu, first wave of C1 -- 52 % of the kernel's stall
-// samples on the shuffle that broadcasts the atomic's result, 1.1 G atomics/s = the serialisation limit of the L2 slice.
-// Must be called by every thread of the block (two barriers).
-template <int WARPS>
-__device__ __forceinline__ void classAppendBlock(const ClassQueue& cq, WavefrontCounters* counters, uint32_t i, uint32_t cls, uint32_t leaf) {
-    __shared__ uint32_t warpCount[WARPS][16];     // entries of class c in warp w
-    __shared__ uint32_t blockBase[16];            // first queue position of the block's entries of class c
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane < 16) warpCount[warp][lane] = 0;
-    __syncwarp();
-    uint32_t rank = 0;
-    const unsigned active = __ballot_sync(0xFFFFFFFFu, cls != SC_NONE);
-    if (cls != SC_NONE) {
-        const unsigned grp = __match_any_sync(active, cls);
-        rank = __popc(grp & ((1u << lane) - 1u));
-        if (rank == 0) warpCount[warp][cls] = (uint32_t)__popc(grp);
-    }
-    __syncthreads();
-    if (threadIdx.x < 16) {
-        uint32_t total = 0;
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) total += warpCount[w][threadIdx.x];
-        if (total) blockBase[threadIdx.x] = atomicAdd(&counters->classCount[threadIdx.x], total);
-    }
-    __syncthreads();
-    if (cls != SC_NONE) {
-        uint32_t pos = blockBase[cls] + rank;
-        for (uint32_t w = 0; w < warp; ++w) pos += warpCount[w][cls];
-        cq.entries[(size_t)cls * cq.capacity + pos] = make_uint2(i, leaf);
-    }
-    __syncthreads();          // the tables are rewritten by the next iteration
-}
-
-// Work items [0, n) are spread over the whole grid, one block per blockDim.x consecutive entries per iteration.
+// Work items [0, n) are spread over the whole grid.
 // (Two groups per iteration with both groups' loads issued up front were measured in round 2 and dropped: surface
 // 2.54 -> 2.85 ms per C1 frame -- the extra registers cost more than the second set of loads in flight buys; an L2 hint
 // for the next iteration's three loads changed nothing, 2.78 vs 2.80 ms -- profiles/r02_rejected_experiments.md.)
-// SLR_SURFACE_APPEND: 0 = one atomic per (warp, class) and 32 entries; 1 = one per (block, class) and blockDim entries
-// (classAppendBlock, two barriers per iteration); 2 = one per (warp, class) and kSurfaceGroups x 32 entries, no barrier.
+// SLR_SURFACE_APPEND: 0 = one atomic per (warp, class) and 32 entries, emission added inline (round 1); 2 = one per (warp,
+// class) and kSurfaceGroups x 32 entries, entries that see emission queued for emissionKernel. (1 = one per block and
+// class with the counts meeting in shared memory behind two barriers was measured and dropped: profiles/r02_variant_sweep.md.)
 #ifndef SLR_SURFACE_APPEND
 #define SLR_SURFACE_APPEND 2
 #endif
@@ -245,14 +216,7 @@ template <int NC, int BLOCK>
 __device__ __forceinline__ void surfaceStage(const DeviceScene& s, const RenderConstants& rc, const PathQueue& in, const HitBuffer& hits,
                                              const ClassQueue& cq, float* __restrict__ accum, WavefrontCounters* counters, uint32_t n) {
     const uint32_t stride = gridDim.x * blockDim.x;
-#if SLR_SURFACE_APPEND == 1
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride) {          // block-uniform trip count
-        const uint32_t i = base + threadIdx.x;
-        uint32_t cls = SC_NONE, leaf = SLRGPU_INVALID_ID;
-        if (i < n) surfaceItem<NC>(s, rc, in, hits, accum, i, &cls, &leaf);
-        classAppendBlock<BLOCK / 32>(cq, counters, i, cls, leaf);
-    }
-#elif SLR_SURFACE_APPEND == 2
+#if SLR_SURFACE_APPEND == 2
     // A warp takes kSurfaceGroups x 32 consecutive entries per iteration and reserves their places in the class queues with
     // ONE atomic per class: the groups' per-class counts are summed in a 16-word table of shared memory owned by the warp
     // (shared-memory atomics hand every group its offset inside the warp's range), lanes 0-15 then reserve one class each.
@@ -262,12 +226,12 @@ __device__ __forceinline__ void surfaceStage(const DeviceScene& s, const RenderC
     for (uint32_t base = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * kSurfaceGroups; base < n; base += stride * kSurfaceGroups) {
         if (lane < 16) mine[lane] = 0;
         __syncwarp();
-        uint32_t cls[kSurfaceGroups], leaf[kSurfaceGroups], off[kSurfaceGroups];
+        uint32_t cls[kSurfaceGroups], leaf[kSurfaceGroups], off[kSurfaceGroups], emit[kSurfaceGroups];      // emit: kind << 28 | offset
 #pragma unroll 1
         for (int g = 0; g < kSurfaceGroups; ++g) {
             const uint32_t i = base + g * 32 + lane;
-            uint32_t c = SC_NONE, l = SLRGPU_INVALID_ID, o = 0;
-            if (i < n) surfaceItem<NC>(s, rc, in, hits, accum, i, &c, &l);
+            uint32_t c = SC_NONE, l = SLRGPU_INVALID_ID, o = 0, em = 0;
+            if (i < n) surfaceItem<NC>(s, rc, in, hits, accum, i, &c, &l, &em);
             const unsigned active = __ballot_sync(0xFFFFFFFFu, c != SC_NONE);
             if (c != SC_NONE) {
                 const unsigned grp = __match_any_sync(active, c);
@@ -275,14 +239,25 @@ __device__ __forceinline__ void surfaceStage(const DeviceScene& s, const RenderC
                 if ((int)lane == leader) o = atomicAdd(&mine[c], (uint32_t)__popc(grp));       // this group's offset in the warp's range
                 o = __shfl_sync(grp, o, leader) + __popc(grp & ((1u << lane) - 1u));
             }
-            cls[g] = c; leaf[g] = l; off[g] = o;
+            // the entries that see emission: one more row of the class queues (kEmissionRow)
+            const unsigned seen = __ballot_sync(0xFFFFFFFFu, em != 0);
+            if (seen) {
+                const int leader = __ffs(seen) - 1;
+                uint32_t eo = 0;
+                if ((int)lane == leader) eo = atomicAdd(&mine[kEmissionRow], (uint32_t)__popc(seen));
+                eo = __shfl_sync(0xFFFFFFFFu, eo, leader) + __popc(seen & ((1u << lane) - 1u));
+                if (em) em = (em << 28) | eo;
+            }
+            cls[g] = c; leaf[g] = l; off[g] = o; emit[g] = em;
         }
         __syncwarp();
         if (lane < 16) { const uint32_t total = mine[lane]; if (total) mine[lane] = atomicAdd(&counters->classCount[lane], total); }
         __syncwarp();
 #pragma unroll 1
-        for (int g = 0; g < kSurfaceGroups; ++g)
+        for (int g = 0; g < kSurfaceGroups; ++g) {
             if (cls[g] != SC_NONE) cq.entries[(size_t)cls[g] * cq.capacity + mine[cls[g]] + off[g]] = make_uint2(base + g * 32 + lane, leaf[g]);
+            if (emit[g]) cq.entries[(size_t)kEmissionRow * cq.capacity + mine[kEmissionRow] + (emit[g] & 0x0FFFFFFFu)] = make_uint2(base + g * 32 + lane, emit[g] >> 28);
+        }
         __syncwarp();
     }
 #else
@@ -294,6 +269,18 @@ __device__ __forceinline__ void surfaceStage(const DeviceScene& s, const RenderC
         classAppend(cq, counters, lane, i, cls, leaf);
     }
 #endif
+}
+
+// the entries of a wave that see emission (queued by the surface stage), one per thread
+template <int NC>
+__device__ __forceinline__ void emissionStage(const DeviceScene& s, const PathQueue& in, const HitBuffer& hits, const ClassQueue& cq,
+                                              float* __restrict__ accum, uint32_t n) {
+    const uint2* __restrict__ entries = cq.entries + (size_t)kEmissionRow * cq.capacity;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint2 e = entries[k];
+        const uint4 meta = in.meta[e.x];
+        surfaceEmission<NC>(s, in, hits, e.x, meta, (meta.z >> 8) & 0xFFu, e.y == 2u, accum);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -429,34 +416,37 @@ __device__ __forceinline__ void materialItem(const DeviceScene& s, const RenderC
     }
 }
 
-// the continued path goes to position npos of the next path queue, the shadow ray to position spos of the shadow queue
+// the shadow ray of a light sample goes to position spos of the shadow queue ...
 template <int NC>
-__device__ __forceinline__ void materialWrite(const PathQueue& out, const ShadowQueue& sq, uint32_t npos, uint32_t spos, const MaterialResult<NC>& o) {
-    if (o.shadow) {
-        sq.org[spos] = make_float4(o.sOrg.x, o.sOrg.y, o.sOrg.z, 0.0001f);
-        sq.dir[spos] = make_float4(o.sDir.x, o.sDir.y, o.sDir.z, o.sTmax);
-        const bool inPlace = ((o.meta.z >> 8) & kFlagStrataInPlace) != 0;
-        sq.pixelWl[spos] = make_uint2(o.meta.x | (inPlace ? 0x80000000u : 0u), o.meta.w);
-        if (sq.time) sq.time[spos] = o.time;
-        if (NC == 3) sq.contrib[spos] = make_float4(o.sContrib.v[0], o.sContrib.v[1], o.sContrib.v[2], 0.0f);
-        else {
+__device__ __forceinline__ void materialWriteShadow(const ShadowQueue& sq, uint32_t spos, const MaterialResult<NC>& o) {
+    sq.org[spos] = make_float4(o.sOrg.x, o.sOrg.y, o.sOrg.z, 0.0001f);
+    sq.dir[spos] = make_float4(o.sDir.x, o.sDir.y, o.sDir.z, o.sTmax);
+    const bool inPlace = ((o.meta.z >> 8) & kFlagStrataInPlace) != 0;
+    sq.pixelWl[spos] = make_uint2(o.meta.x | (inPlace ? 0x80000000u : 0u), o.meta.w);
+    if (sq.time) sq.time[spos] = o.time;
+    if (NC == 3) sq.contrib[spos] = make_float4(o.sContrib.v[0], o.sContrib.v[1], o.sContrib.v[2], 0.0f);
+    else {
 #pragma unroll
-            for (int c = 0; c < NC / 4; ++c)
-                sq.contrib[(size_t)c * sq.capacity + spos] =
-                    make_float4(o.sContrib.v[4 * c], o.sContrib.v[(4 * c + 1) % NC], o.sContrib.v[(4 * c + 2) % NC], o.sContrib.v[(4 * c + 3) % NC]);
-        }
-    }
-    if (o.alive) {
-        out.org[npos] = make_float4(o.nOrg.x, o.nOrg.y, o.nOrg.z, 0.0001f);      // Ray::Epsilon
-        out.dir[npos] = make_float4(o.nDir.x, o.nDir.y, o.nDir.z, o.nPdf);
-        out.meta[npos] = o.meta;
-        out.weight[npos] = o.weight;
-        out.aux[npos] = o.nImp;
-        if (out.time) out.time[npos] = o.time;
-        storeAlpha<NC>(out, npos, o.alpha);
+        for (int c = 0; c < NC / 4; ++c)
+            sq.contrib[(size_t)c * sq.capacity + spos] =
+                make_float4(o.sContrib.v[4 * c], o.sContrib.v[(4 * c + 1) % NC], o.sContrib.v[(4 * c + 2) % NC], o.sContrib.v[(4 * c + 3) % NC]);
     }
 }
+// ... the continued path to position npos of the next path queue
+template <int NC>
+__device__ __forceinline__ void materialWriteNext(const PathQueue& out, uint32_t npos, const MaterialResult<NC>& o) {
+    out.org[npos] = make_float4(o.nOrg.x, o.nOrg.y, o.nOrg.z, 0.0001f);      // Ray::Epsilon
+    out.dir[npos] = make_float4(o.nDir.x, o.nDir.y, o.nDir.z, o.nPdf);
+    out.meta[npos] = o.meta;
+    out.weight[npos] = o.weight;
+    out.aux[npos] = o.nImp;
+    if (out.time) out.time[npos] = o.time;
+    storeAlpha<NC>(out, npos, o.alpha);
+}
 
+// (Measured and dropped, round 2: storing the shadow entry where the light sample is complete -- its 23 values are then
+// dead while the BSDF is sampled -- through an atomic of the lanes executing together: material 6.69 vs 6.72 ms per C1
+// frame at 3 resident blocks, 7.2 ms at 4 (128 registers, 40 bytes of spills), C2 1.5 % slower.)
 template <int NC, int CLASS>
 __device__ __forceinline__ void materialStage(const DeviceScene& s, const RenderConstants& rc, const PathQueue& in, const HitBuffer& hits,
                                               const ClassQueue& cq, const PathQueue& out, const ShadowQueue& sq, WavefrontCounters* counters, uint32_t n) {
@@ -489,7 +479,8 @@ __device__ __forceinline__ void materialStage(const DeviceScene& s, const Render
         }
         uint32_t npos, spos;
         warpAppendPair(o.alive, o.shadow, counters, &npos, &spos);
-        materialWrite<NC>(out, sq, npos, spos, o);
+        if (o.shadow) materialWriteShadow<NC>(sq, spos, o);
+        if (o.alive) materialWriteNext<NC>(out, npos, o);
     }
 #else
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
@@ -502,7 +493,8 @@ __device__ __forceinline__ void materialStage(const DeviceScene& s, const Render
         }
         uint32_t npos, spos;
         warpAppendPair(o.alive, o.shadow, counters, &npos, &spos);
-        materialWrite<NC>(out, sq, npos, spos, o);
+        if (o.shadow) materialWriteShadow<NC>(sq, spos, o);
+        if (o.alive) materialWriteNext<NC>(out, npos, o);
     }
 #endif
 }

@@ -59,7 +59,8 @@ __device__ __noinline__ void tailMaterial(const DeviceScene& s, const RenderCons
     MaterialResult<NC> o;
     o.clear();
     materialItem<NC, CLASS>(s, rc, in, hits, slot, leaf, o);
-    materialWrite<NC>(out, sq, slot, slot, o);
+    if (o.shadow) materialWriteShadow<NC>(sq, slot, o);
+    if (o.alive) materialWriteNext<NC>(out, slot, o);
     *alive = o.alive; *shadow = o.shadow;
 }
 

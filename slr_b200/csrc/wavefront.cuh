@@ -54,6 +54,12 @@ enum ShadeClass : uint32_t {
     SC_LAMBERT = 0, SC_OREN_NAYAR = 1, SC_SPECULAR_BRDF = 2, SC_SPECULAR_BSDF = 3, SC_WARD = 4, SC_ASHIKHMIN = 5,
     SC_MF_BRDF = 6, SC_MF_BSDF = 7, SC_GENERIC = 8, SC_COUNT = 9, SC_NONE = 0xFFu
 };
+// Row SC_COUNT of the class queues is not a material class: the `surface` stage of a wave queues there the entries whose
+// arriving ray SEES EMISSION (it hit an emitter, or left the scene into the environment), as (queue position, isEnv);
+// emissionKernel adds them to the sensor with full warps. Inline, that path ran for 30 % of the warps of a later wave at
+// 1.2 of 32 lanes and was half of the stage's instructions (ncu, wave 2 of C1, profiles/r02_ncu_c1_final.md).
+constexpr uint32_t kEmissionRow = SC_COUNT;
+constexpr uint32_t kClassQueueRows = SC_COUNT + 1;
 
 // Device-resident loop state: every kernel of a wave reads its work size from here, so the host
 // never has to wait for a count (it only polls, two waves behind, for termination).
@@ -76,7 +82,7 @@ struct WavefrontCounters {
 
 // One entry of a material-class queue: position in the current path queue + the leaf material id.
 struct ClassQueue {
-    uint2* entries;        // [SC_COUNT][capacity]
+    uint2* entries;        // [kClassQueueRows][capacity]
     uint32_t capacity;
 };
 
