@@ -185,7 +185,12 @@ __device__ __forceinline__ void mulVector(const float* __restrict__ m, float x, 
 // the leaf-phase coherence returns. So was a warp-cooperative leaf phase -- the records waiting in all
 // lanes numbered by a prefix sum, one record per lane, owners' rays fetched by shuffles, hits taken in
 // record order from a shared-memory window: bit-exact, but 2695 -> 2289 Mrays/s on the intersect bench and
-// extend 10.9 -> 12.6 ms per C1 frame, profiles/r01_rejected_experiments.md.)
+// extend 10.9 -> 12.6 ms per C1 frame, profiles/r01_rejected_experiments.md. Round 2 tried it again on the leaner walk,
+// adaptively -- only in steps where some lane holds >= 3 (or >= 6) records, the winner per owner through a 64-bit
+// shared-memory minimum of (t, ~record number), because ncu showed the per-lane leaf loop of an incoherent wave at 3.8
+// iterations per node visit and 4.3 of 32 lanes: bit-exact again, and slower again -- C1 707 / 686 vs 730 Mpaths/s, C5 3189 vs
+// 3874 Mrays/s: 72-80 registers instead of 64, and the step's dependent chain grows by the scan, the shuffles and the
+// shared-memory round trip, while the leaf loop's time is load latency, not issue slots. profiles/r02_rejected_experiments.md.)
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kMaxChunk = 256;
 #ifndef SLR_WALK_STEPS_PER_ROUND
@@ -448,116 +453,6 @@ __device__ __forceinline__ bool walkStep(const DeviceScene& s, WalkState& w, Ins
     return w.sp == 0 && leaves.count == 0;
 }
 
-// ---------------------------------------------------------------------------------------------
-// The leaf records of a step, tested by the WHOLE warp (flat scenes; SLR_WALK_COOP_LEAVES).
-// In a wave of incoherent rays the lanes of a warp find very different numbers of leaf records at a node visit: the
-// per-lane loop of walkStep then runs as long as the longest list -- ncu, wave 2 of C1: 3.8 iterations per node visit at
-// 4.3 of 32 lanes, 53 % of the extend kernel's stall samples. Here the records waiting in all lanes are numbered by a
-// prefix sum and dealt out one per lane: a lane fetches the owner's ray by shuffles, tests the record, and the owner takes
-// the winner of its records. Per ray the outcome is what the in-order loop gives: every test is the same arithmetic on
-// the same operands; the in-order loop ends with the smallest t, the LATER record on a tie (`t > tmax` rejects, an equal t
-// replaces), which is what the 64-bit minimum of (t, ~record number) selects; a round uses the owner's tmax after the
-// rounds before it, whose records all come earlier in its order. Taken when the longest list holds at least
-// kCoopMinRecords records, else the per-lane loop runs (coherent waves: 1.25 iterations at 9.5 lanes).
-// ---------------------------------------------------------------------------------------------
-#ifndef SLR_WALK_COOP_LEAVES
-#define SLR_WALK_COOP_LEAVES 1
-#endif
-#ifndef SLR_WALK_COOP_MIN
-#define SLR_WALK_COOP_MIN 3
-#endif
-constexpr uint32_t kCoopMinRecords = SLR_WALK_COOP_MIN;
-
-__device__ __forceinline__ uint32_t sortableBits(float t) {      // monotone float -> uint32 (negative zero below zero)
-    const uint32_t b = __float_as_uint(t);
-    return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u);
-}
-__device__ __forceinline__ uint32_t leafChildCount(uint32_t c) { return c == kEmptyChild ? 0u : (c >> 27) & 0xFu; }
-
-// `best` = 32 words of shared memory pairs owned by the warp (one 64-bit slot per lane). Must be called by all lanes.
-// Returns with every lane's queue empty and the owners' hits / tmax updated (an any-hit owner: w.found).
-__device__ __forceinline__ void leafPhaseCoop(const DeviceScene& s, WalkState& w, LeafQueue& leaves, bool active,
-                                              unsigned long long* best, uint32_t total, uint32_t myCount) {
-    const uint32_t lane = threadIdx.x & 31;
-    // the lane's up to four leaf children as (first record, count) -- count 0 = none -- and the running sums of the counts
-    const uint32_t f0 = leaves.first, c0 = active ? leaves.count : 0u;
-    const uint32_t p0 = leaves.pending0, p1 = leaves.pending1, p2 = leaves.pending2;
-    const uint32_t c1 = active ? leafChildCount(p0) : 0u, c2 = active ? leafChildCount(p1) : 0u;
-    const uint32_t f1 = p0 & 0x07FFFFFFu, f2 = p1 & 0x07FFFFFFu, f3 = p2 & 0x07FFFFFFu;
-    const uint32_t sums = c0 | ((c0 + c1) << 8) | ((c0 + c1 + c2) << 16);      // exclusive ends of children 0, 1, 2 (each < 64)
-    // inclusive prefix sum of the counts over the lanes
-    uint32_t incl = myCount;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += v; }
-    const uint32_t excl = incl - myCount;
-    for (uint32_t base = 0; base < total; base += 32) {
-        best[lane] = 0xFFFFFFFFFFFFFFFFull;
-        __syncwarp();
-        const uint32_t g = base + lane;
-        const bool valid = g < total;
-        // owner of record g: the first lane whose inclusive sum exceeds g
-        uint32_t o = 0;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) { const uint32_t v = __shfl_sync(0xFFFFFFFFu, incl, (o + d - 1) & 31); if (v <= g) o += d; }
-        o &= 31;
-        const uint32_t k = g - __shfl_sync(0xFFFFFFFFu, excl, o);           // position in the owner's list
-        const uint32_t os = __shfl_sync(0xFFFFFFFFu, sums, o);
-        const uint32_t of0 = __shfl_sync(0xFFFFFFFFu, f0, o), of1 = __shfl_sync(0xFFFFFFFFu, f1, o);
-        const uint32_t of2 = __shfl_sync(0xFFFFFFFFu, f2, o), of3 = __shfl_sync(0xFFFFFFFFu, f3, o);
-        const uint32_t e0 = os & 0xFFu, e1 = (os >> 8) & 0xFFu, e2 = (os >> 16) & 0xFFu;
-        const uint32_t rec = k < e0 ? of0 + k : k < e1 ? of1 + (k - e0) : k < e2 ? of2 + (k - e1) : of3 + (k - e2);
-        Ray r;
-        r.ox = __shfl_sync(0xFFFFFFFFu, w.r.ox, o); r.oy = __shfl_sync(0xFFFFFFFFu, w.r.oy, o); r.oz = __shfl_sync(0xFFFFFFFFu, w.r.oz, o);
-        r.dx = __shfl_sync(0xFFFFFFFFu, w.r.dx, o); r.dy = __shfl_sync(0xFFFFFFFFu, w.r.dy, o); r.dz = __shfl_sync(0xFFFFFFFFu, w.r.dz, o);
-        r.tmin = __shfl_sync(0xFFFFFFFFu, w.r.tmin, o); r.tmax = __shfl_sync(0xFFFFFFFFu, w.r.tmax, o);
-        float t = 0.0f, b0 = 0.0f, b1 = 0.0f, b2;
-        uint32_t id = 0, info = 0;
-        if (valid) {
-            const float4* p = s.leaves + (size_t)rec * 3;
-            const float4 a = ldg4(p), b = ldg4(p + 1), cc = ldg4(p + 2);
-            if (triangleTest(a, b, cc, r, &t, &b0, &b1, &b2)) {
-                id = __float_as_uint(a.w); info = __float_as_uint(cc.w);
-                atomicMin(&best[o], ((unsigned long long)sortableBits(t) << 32) | (unsigned long long)(~g));
-            }
-        }
-        __syncwarp();
-        const unsigned long long mine = best[lane];
-        const bool won = mine != 0xFFFFFFFFFFFFFFFFull;
-        const uint32_t from = won ? (~(uint32_t)mine) - base : 0u;           // the lane that tested the winning record
-        const float wt = __shfl_sync(0xFFFFFFFFu, t, from), wb0 = __shfl_sync(0xFFFFFFFFu, b0, from), wb1 = __shfl_sync(0xFFFFFFFFu, b1, from);
-        const uint32_t wid = __shfl_sync(0xFFFFFFFFu, id, from), winfo = __shfl_sync(0xFFFFFFFFu, info, from);
-        if (won) {
-            w.r.tmax = wt;
-            w.hit.prim = wid; w.hit.inst = SLRGPU_INVALID_ID;
-            w.hit.t = wt; w.hit.u = wb0; w.hit.v = wb1; w.hit.info = winfo;
-            w.found = true;
-        }
-        __syncwarp();
-    }
-    leaves.count = 0; leaves.pending0 = leaves.pending1 = leaves.pending2 = kEmptyChild;
-}
-
-// the per-lane loop of walkStep for a flat scene (triangle records only): all waiting records, or one (`onlyOne`)
-template <bool ANY_HIT>
-__device__ __forceinline__ bool leafLoopFlat(const DeviceScene& s, WalkState& w, LeafQueue& leaves, bool onlyOne) {
-    while (leaves.count != 0) {
-        const float4* rec = s.leaves + (size_t)leaves.first * 3;
-        const float4 a = ldg4(rec), b = ldg4(rec + 1), cc = ldg4(rec + 2);
-        ++leaves.first;
-        if (--leaves.count == 0) leaves.next();
-        float t, b0, b1, b2;
-        if (triangleTest(a, b, cc, w.r, &t, &b0, &b1, &b2)) {
-            w.r.tmax = t;
-            w.hit.prim = __float_as_uint(a.w); w.hit.inst = SLRGPU_INVALID_ID;
-            w.hit.t = t; w.hit.u = b0; w.hit.v = b1; w.hit.info = __float_as_uint(cc.w);
-            w.found = true;
-            if (ANY_HIT) return true;
-        }
-        if (onlyOne) break;
-    }
-    return false;
-}
-
 // Runs `n` rays through the scene with one warp-cooperative loop. Source::load(i, Ray&) fetches ray i,
 // Sink::done(i, state) consumes its result. *cursor must be 0 at launch.
 template <bool INSTANCES, bool ANY_HIT, bool COUNT, bool ALPHA, typename Source, typename Sink>
@@ -617,35 +512,13 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
             if (exhausted) break;
             continue;
         }
-        if constexpr (SLR_WALK_COOP_LEAVES && !INSTANCES && !COUNT && !ALPHA) {
-            // a node visit for the lanes without waiting records, then the records of all lanes: by the whole warp when
-            // some lane holds a long list, else lane by lane
-            __shared__ unsigned long long coopBest[8][32];       // one slot per lane of up to eight warps
-            LeafQueue& leaves = iw.leaves;
-            if (active && leaves.count == 0) walkNode<false, false>(s, w, iw, leaves, stack, cnt, overflow);
-            const uint32_t myCount = active ? leaves.count + leafChildCount(leaves.pending0) + leafChildCount(leaves.pending1) + leafChildCount(leaves.pending2) : 0u;
-            const uint32_t longest = __reduce_max_sync(0xFFFFFFFFu, myCount);
-            bool hitDone = false;
-            if (longest >= kCoopMinRecords) {
-                leafPhaseCoop(s, w, leaves, active, coopBest[(threadIdx.x >> 5) & 7], __reduce_add_sync(0xFFFFFFFFu, myCount), myCount);
-                hitDone = ANY_HIT && active && w.found;
-            } else if (myCount != 0) {
-                hitDone = leafLoopFlat<ANY_HIT>(s, w, leaves, SLR_WALK_ONE_RECORD_PER_STEP != 0);
-            }
-            if (active && (hitDone || (w.sp == 0 && leaves.count == 0))) {
-                if (kDefer) finished = true;
-                else sink.done(idx, w, cnt);
-                active = false;
-            }
-        } else {
 #pragma unroll 1
-            for (int it = 0; it < kStepsPerRound; ++it) {
-                if (active) {
-                    if (walkStep<INSTANCES, ANY_HIT, COUNT, ALPHA>(s, w, iw, stack, cnt, overflow)) {
-                        if (kDefer) finished = true;
-                        else sink.done(idx, w, cnt);
-                        active = false;
-                    }
+        for (int it = 0; it < kStepsPerRound; ++it) {
+            if (active) {
+                if (walkStep<INSTANCES, ANY_HIT, COUNT, ALPHA>(s, w, iw, stack, cnt, overflow)) {
+                    if (kDefer) finished = true;
+                    else sink.done(idx, w, cnt);
+                    active = false;
                 }
             }
         }
