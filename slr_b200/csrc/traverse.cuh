@@ -196,8 +196,15 @@ constexpr uint32_t kMaxChunk = 256;
 #ifndef SLR_WALK_STEPS_PER_ROUND
 #define SLR_WALK_STEPS_PER_ROUND 1
 #endif
+// Idle lanes that trigger a refill. A refill stalls the whole warp for the DRAM round trip of the new rays' loads, so it
+// pays to refill rarely and many lanes at once: re-swept on the leaner node step (profiles/r02_variant_sweep.md) -- C1 699 /
+// 729 / 744 / 750 / 750 / 748 Mpaths/s at 4 / 8 / 12 / 16 / 20 / 24, C4 371 / 386 / 396 / 393 / 395 / 401 (round 1 chose 8
+// when a node step cost 420 instructions).
 #ifndef SLR_WALK_REFILL_IDLE
-#define SLR_WALK_REFILL_IDLE 8
+#define SLR_WALK_REFILL_IDLE 16
+#endif
+#ifndef SLR_WALK_REFILL_IDLE_INSTANCED
+#define SLR_WALK_REFILL_IDLE_INSTANCED 24
 #endif
 // (Measured and dropped, round 2: an L2 prefetch -- prefetch.global.L2 -- of every pushed inner child and of the first record
 // of every queued leaf child at push time: C5 (10 M triangles, scene larger than L2) 2581 -> 1797 Mrays/s, C4 299 -> 288
@@ -210,7 +217,7 @@ constexpr uint32_t kMaxChunk = 256;
 #define SLR_WALK_DEFER_SINK 1
 #endif
 constexpr int kStepsPerRound = SLR_WALK_STEPS_PER_ROUND;     // node visits between two refill checks (sweep: profiles/r01_variant_sweep.md)
-constexpr int kRefillIdle = SLR_WALK_REFILL_IDLE;            // idle lanes that trigger a refill
+constexpr int kRefillIdleFlat = SLR_WALK_REFILL_IDLE, kRefillIdleInstanced = SLR_WALK_REFILL_IDLE_INSTANCED;
 
 struct WalkState {
     Ray r;
@@ -477,6 +484,7 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
     // contribution loads + four 16-byte reductions of `shadow` -- runs once for all lanes that finished since, instead of
     // once per finishing lane at 1-3 active lanes.
     bool finished = false;
+    constexpr int kRefillIdle = INSTANCES ? kRefillIdleInstanced : kRefillIdleFlat;
     while (true) {
         const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
         const int numIdle = __popc(idle);
