@@ -357,7 +357,7 @@ def main():
                                  "launch / its device time; traffic = ncu dram__bytes of one launch of this mesh size (profiles/traffic.json), "
                                  "bytes per launch -- below the algorithmic figure because the upper tree levels are served by L2. The kernel is "
                                  "bound by the LATENCY of its dependent node fetches (ncu: long-scoreboard stalls dominate, DRAM throughput "
-                                 "14 %), see profiles/r02_ncu_c4_c5.md"},
+                                 "14 %), see profiles/r02_ncu_c4_c5_final.md"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e * world / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
             "gpu_launches": args.steps, "clocks": r["clocks"]}

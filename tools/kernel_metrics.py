@@ -21,7 +21,11 @@ KEYS = {"lanes_active": "smsp__thread_inst_executed_per_inst_executed.ratio",
 
 
 def read(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv.gz"):       # the raw page exported on the GPU box (reports larger than a call may bring back)
+        import gzip
+        out = gzip.open(rep, "rt").read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     res = {}

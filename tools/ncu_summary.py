@@ -95,7 +95,11 @@ def traffic(path, workload):
 
 
 def report(path, title):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv.gz"):      # the raw page exported on the GPU box
+        import gzip
+        out = gzip.open(path, "rt").read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     print(f"## {title}\n\n`{path}` (`ncu --set full --clock-control none`), one column per captured launch\n")
