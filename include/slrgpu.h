@@ -64,7 +64,10 @@ typedef enum SlrGpuStatus {
  * lanes' min x/y/z, max x/y/z, four packed children, three split axes. Empty lanes hold
  * (+inf, -inf) boxes and child 0xFFFFFFFF. Child word: idx:27 | numLeaves:4 | isLeaf:1 (QBVH.h:27-35).
  * For an inner child idx is a node index, for a leaf child idx is the first leaf record; both are
- * GLOBAL indices into the scene-wide arrays below (all BVH levels are concatenated). */
+ * GLOBAL indices into the scene-wide arrays below (all BVH levels are concatenated).
+ * The caller's table is read once: slrgpu_scene_create rewrites the three axis bytes of ITS device copy into bit masks
+ * (1 << axis) for the traversal's ordering test, and copies each triangle's shading class into the spare word of the
+ * device copy of the leaf records -- neither is visible through this interface. */
 typedef struct SlrGpuBvhNode {
     float lo_x[4], lo_y[4], lo_z[4];
     float hi_x[4], hi_y[4], hi_z[4];

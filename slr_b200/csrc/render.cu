@@ -467,7 +467,10 @@ static int renderImpl(SlrGpuScene* sc, const SlrGpuRenderParams* p, RenderWorksp
     constexpr int kLag = 2;
     // the tail kernel (tail.cu) takes over when only a few paths per thread of it are left; SLRGPU_TAIL_PATHS overrides
     // the limit (0 = no tail kernel: every bounce is a wave) -- a tuning / test knob, the image does not depend on it
-    uint32_t tailCap = tailCapacity(numSMs);
+    // Two paths per thread when the scene has at most three material classes: a round of a tail warp runs the classes of its
+    // lanes one after the other, so a warp that holds more paths pays per class -- C1 (3 classes) 748 -> 757 Mpaths/s and C4 (2)
+    // 400 -> 404 at 75 776 paths, C2 (8 classes) 795 -> 768 (profiles/r02_variant_sweep.md)
+    uint32_t tailCap = tailCapacity(numSMs) * (__builtin_popcount(sc->classMask) <= 3 ? 2u : 1u);
     if (const char* e = getenv("SLRGPU_TAIL_PATHS")) tailCap = (uint32_t)strtoul(e, nullptr, 10);
     const char* waveLogPath = getenv("SLRGPU_WAVE_LOG");
     ulonglong2* waveLog = waveLogPath ? w.dWaveLog : nullptr;
