@@ -4,7 +4,9 @@
 //   Scene::testVisibility   libSLR/Core/SurfaceObject.cpp:418-430  (the reference runs a full closest-hit
 //                           query and keeps only the boolean; any-hit with early exit gives the same boolean)
 // MUST be compiled with -fmad=false like intersect.cu: the renderer's rays use the bit-exact traversal.
+#ifndef SLR_WALK_DEFER_SINK
 #define SLR_WALK_DEFER_SINK 2      // results handed to the sink at the refill point: instanced instantiations only (traverse.cuh)
+#endif
 #include "ray_io.cuh"
 
 #ifndef SLR_TRACE_MIN_BLOCKS
