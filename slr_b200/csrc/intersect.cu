@@ -2,6 +2,9 @@
 // QBVH::intersect, QBVH.h:295-337) and occlusion (Scene::testVisibility, SurfaceObject.cpp:418-430).
 // MUST be compiled with -fmad=false (see traverse.cuh).
 #define SLR_WALK_ONE_RECORD_PER_STEP 1      // measured faster for ray batches (traverse.cuh walkStep)
+#ifndef SLR_WALK_STEPS_PER_ROUND
+#define SLR_WALK_STEPS_PER_ROUND 2         // two steps between refill checks: +0.8 % on the batch bench (a step here is a node OR a record)
+#endif
 #include "traverse.cuh"
 #include <algorithm>
 #include <cstring>

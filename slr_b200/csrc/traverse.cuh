@@ -216,6 +216,13 @@ constexpr uint32_t kMaxChunk = 256;
 #ifndef SLR_WALK_DEFER_SINK
 #define SLR_WALK_DEFER_SINK 1
 #endif
+// Long walks amortise the refill check over several steps: the instanced kernels (C4: 23 node visits per ray through two BVH
+// levels) 401 -> 413 Mpaths/s at two steps, 418 at three; the batch kernels +0.8 % at two (intersect.cu); the flat renderer kernels' short rays lose
+// 4 % (C1 762 -> 729) and keep one step per check.
+#ifndef SLR_WALK_STEPS_PER_ROUND_INSTANCED
+#define SLR_WALK_STEPS_PER_ROUND_INSTANCED 3
+#endif
+constexpr int kStepsPerRoundInstanced = SLR_WALK_STEPS_PER_ROUND_INSTANCED;
 constexpr int kStepsPerRound = SLR_WALK_STEPS_PER_ROUND;     // node visits between two refill checks (sweep: profiles/r01_variant_sweep.md)
 constexpr int kRefillIdleFlat = SLR_WALK_REFILL_IDLE, kRefillIdleInstanced = SLR_WALK_REFILL_IDLE_INSTANCED;
 
@@ -522,7 +529,7 @@ __device__ __forceinline__ void walkQueue(const DeviceScene& s, uint32_t n, uint
             continue;
         }
 #pragma unroll 1
-        for (int it = 0; it < kStepsPerRound; ++it) {
+        for (int it = 0; it < (INSTANCES ? kStepsPerRoundInstanced : kStepsPerRound); ++it) {
             if (active) {
                 if (walkStep<INSTANCES, ANY_HIT, COUNT, ALPHA>(s, w, iw, stack, cnt, overflow)) {
                     if (kDefer) finished = true;
