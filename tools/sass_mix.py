@@ -1,5 +1,5 @@
 """SASS instruction mix of every kernel in the built library (no GPU needed):
-    python tools/sass_mix.py > profiles/r01_sass_mix.md        # also rewrites profiles/sass/r01_<kernel>.sass for the ray kernels
+    python tools/sass_mix.py r02 > profiles/r02_sass_mix.md    # also rewrites profiles/sass/r02_<kernel>.sass for the ray kernels
 """
 import os
 import re
@@ -9,7 +9,9 @@ from collections import Counter
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "slr_b200", "lib", "libslrgpu.so")
-LISTED = ("extendKernel<false, false>", "shadowKernel<false, 16, false>", "intersectBatchKernel<false, false>", "raygenKernel<16>")
+LISTED = ("extendKernel<false, false, false>", "extendKernel<true, false, false>", "shadowKernel<false, 16, false, false>",
+          "intersectBatchKernel<false, false, false>", "surfaceKernel<16>", "raygenKernel<16>")
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 
 
 def demangle(name):
@@ -33,8 +35,8 @@ def main():
             continue
         if cur is not None and re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+\S", line):
             funcs[cur].append(line)
-    print("# r01 -- SASS instruction mix of the kernels (final round-1 pipeline; `cuobjdump -sass slr_b200/lib/libslrgpu.so`, sm_100a; `tools/sass_mix.py`)\n")
-    print("Full listings of the ray kernels: `profiles/sass/r01_*.sass`. The shade kernels and the tail kernel are 10-60 k instructions each "
+    print(f"# {TAG} -- SASS instruction mix of the kernels (final pipeline of the round; `cuobjdump -sass slr_b200/lib/libslrgpu.so`, sm_100a; `tools/sass_mix.py`)\n")
+    print(f"Full listings of the ray kernels: `profiles/sass/{TAG}_*.sass`. The shade kernels and the tail kernel are 10-60 k instructions each "
           "including their out-of-line device functions (16-wavelength code, all texture kinds reachable), so only their mix is listed.\n")
     print("| kernel | instructions | top opcodes |\n|---|---|---|")
     tc = 0
@@ -56,8 +58,9 @@ def main():
     os.makedirs(out, exist_ok=True)
     for name in LISTED:
         if name in funcs:
-            with open(os.path.join(out, "r01_" + re.sub(r"<.*", "", name) + ".sass"), "w") as f:
-                f.write(f"// {name}, sm_100a, final round-1 pipeline\n" + "\n".join(funcs[name]) + "\n")
+            stem = re.sub(r"<.*", "", name) + ("_instanced" if name.startswith("extendKernel<true") else "")
+            with open(os.path.join(out, f"{TAG}_{stem}.sass"), "w") as f:
+                f.write(f"// {name}, sm_100a, final pipeline of {TAG}\n" + "\n".join(funcs[name]) + "\n")
 
 
 if __name__ == "__main__":
