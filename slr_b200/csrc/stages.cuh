@@ -16,18 +16,6 @@
 
 namespace slrgpu {
 
-// position of `alive` lanes in an output queue: one atomic per warp
-__device__ __forceinline__ uint32_t warpAppend(bool alive, uint32_t* counter) {
-    const unsigned mask = __ballot_sync(0xFFFFFFFFu, alive);
-    if (mask == 0) return 0;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    return base + __popc(mask & ((1u << lane) - 1u));
-}
-
 // positions of the `alive` lanes in the next path queue and of the `shadow` lanes in the shadow queue: both counters
 // sit in one 64-bit word (WavefrontCounters::numNext / numShadow), so one atomic per warp reserves both ranges
 __device__ __forceinline__ void warpAppendPair(bool alive, bool shadow, WavefrontCounters* counters, uint32_t* npos, uint32_t* spos) {

@@ -47,33 +47,12 @@ struct TraversalCounters {
 };
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
-// 4-lane slab test; returns the 4-bit mask of lanes whose [tNear, tFar] is non-empty. The near / far planes
-// are already selected by the caller (the selection depends only on the sign of the ray direction, so the
-// walk fetches lo or hi per axis by ADDRESS instead of fetching both and selecting per lane).
+// 4-lane slab test with the outcome applied to the child words: lane l's child if its [tNear, tFar] is non-empty, else
+// kEmptyChild. The near / far planes are already selected by the caller (the selection depends only on the sign of the
+// ray direction, so the walk fetches lo or hi per axis by ADDRESS instead of fetching both and selecting per lane).
 // fmaxf/fminf return the non-NaN operand, which coincides with _mm_max_ps/_mm_min_ps here because a
 // NaN can only appear in the freshly computed first operand (0 * inf), never in the running bound.
-__device__ __forceinline__ uint32_t slab4NearFar(const float4 nx, const float4 ny, const float4 nz,
-                                                 const float4 fx, const float4 fy, const float4 fz,
-                                                 const Ray& r, float ix, float iy, float iz) {
-    uint32_t mask = 0;
-#define SLAB_LANE(L, bit)                                                   \
-    {                                                                       \
-        float tn = r.tmin, tf = r.tmax;                                     \
-        tn = fmaxf(__fmul_rn(__fsub_rn(nx.L, r.ox), ix), tn);                                 \
-        tn = fmaxf(__fmul_rn(__fsub_rn(ny.L, r.oy), iy), tn);                                 \
-        tn = fmaxf(__fmul_rn(__fsub_rn(nz.L, r.oz), iz), tn);                                 \
-        tf = fminf(__fmul_rn(__fsub_rn(fx.L, r.ox), ix), tf);                                 \
-        tf = fminf(__fmul_rn(__fsub_rn(fy.L, r.oy), iy), tf);                                 \
-        tf = fminf(__fmul_rn(__fsub_rn(fz.L, r.oz), iz), tf);                                 \
-        if (tn <= tf) mask |= bit;                                          \
-    }
-    SLAB_LANE(x, 1u) SLAB_LANE(y, 2u) SLAB_LANE(z, 4u) SLAB_LANE(w, 8u)
-#undef SLAB_LANE
-    return mask;
-}
-
-// The same test with the outcome applied to the child words: lane l's child if its box is hit, else kEmptyChild
-// (the predicates feed four selects directly; building a mask first and testing its bits again cost ~12 instructions).
+// (The predicates feed four selects directly; building a 4-bit mask first and testing its bits again cost ~12 instructions.)
 __device__ __forceinline__ uint4 slab4Children(const float4 nx, const float4 ny, const float4 nz,
                                                const float4 fx, const float4 fy, const float4 fz,
                                                const Ray& r, float ix, float iy, float iz, const uint4 kids) {
