@@ -40,6 +40,7 @@
 #include <memory>
 #include <set>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -584,6 +585,19 @@ void GPUPathTracingRenderer::render(const Scene &scene, const RenderSettings &se
     sensor->init(W, H);
 
     GpuSceneExporter exporter(scene);
+    // SLRGPU_DROPIN_DUMP=<file>: the geometry tables as they go to slrgpu_scene_create (a debugging aid; tests/test_dropin.py
+    // walks them on the CPU and compares the hits with the reference's own Scene::intersect on the same file)
+    if (const char* dumpPath = getenv("SLRGPU_DROPIN_DUMP")) {
+        if (FILE* f = fopen(dumpPath, "wb")) {
+            const SlrGpuSceneDesc &d = exporter.desc;
+            const uint32_t head[4] = {0x44524F50u, d.num_bvh_nodes, d.num_leaf_records, d.num_instances};
+            fwrite(head, 4, 4, f);
+            fwrite(d.bvh_nodes, sizeof(SlrGpuBvhNode), d.num_bvh_nodes, f);
+            fwrite(d.leaf_records, sizeof(SlrGpuLeafRecord), d.num_leaf_records, f);
+            fwrite(d.instances, sizeof(SlrGpuInstance), d.num_instances, f);
+            fclose(f);
+        }
+    }
     // without a CUDA device slrgpu_scene_create fails below with SLRGPU_ERR_NO_DEVICE (after validating the tables): there is
     // no CPU fallback behind this renderer -- a host without a GPU keeps PathTracingRenderer
     const int visible = slrgpu_device_count();

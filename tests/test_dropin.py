@@ -125,3 +125,68 @@ def test_dropin_bidirectional_renderer(tmp_path):
     floor = ru.rel_rmse(ref2, ref1, trim=0.005)
     got = ru.rel_rmse(gpu, ref1, trim=0.005)
     assert got <= 1.25 * floor, f"relRMSE {got:.4f} vs noise floor {floor:.4f}"
+
+
+def _load_table_dump(path):
+    """The file SLRGPU_DROPIN_DUMP writes: u32 magic, nodes, leaf records, instances, then the three tables."""
+    import ctypes as C
+    raw = open(path, "rb").read()
+    magic, nn, nl, ni = np.frombuffer(raw[:16], np.uint32)
+    assert magic == 0x44524F50
+    off = 16
+    tables = []
+    for cls, n in ((capi.BvhNode, int(nn)), (capi.LeafRecord, int(nl)), (capi.Instance, int(ni))):
+        size = C.sizeof(cls) * n
+        arr = (cls * max(n, 1))()
+        C.memmove(arr, raw[off:off + size], size)
+        off += size
+        tables.append(arr)
+    assert off == len(raw)
+    d = capi.SceneDesc()
+    d.struct_size = C.sizeof(capi.SceneDesc)
+    d.bvh_nodes, d.num_bvh_nodes = C.cast(tables[0], C.POINTER(capi.BvhNode)), int(nn)
+    d.leaf_records, d.num_leaf_records = C.cast(tables[1], C.POINTER(capi.LeafRecord)), int(nl)
+    d.instances, d.num_instances = C.cast(tables[2], C.POINTER(capi.Instance)), int(ni)
+    return d, tables
+
+
+@needs_binary
+@pytest.mark.parametrize("name", ["instanced", "lamps", "nested", "motion"])
+def test_exported_tables_give_the_reference_hits(name, tmp_path, monkeypatch):
+    """CPU: the geometry tables the exporter hands to slrgpu_scene_create -- for `nested` the scene it expanded to one level,
+    for `motion` the begin key frames -- walked by the CPU restatement of the traversal, against the reference's own
+    Scene::intersect on the same file and rays (oracle/_ref/ref_probe, shutter closed at time 0): the same rays hit, at
+    the same distance up to the rounding of the composed transforms."""
+    import ctypes as C
+    import oracle_util as ou
+    if not ru.have_ref_probe():
+        pytest.skip("oracle/_ref/ref_probe not built")
+    path = ru.scene_file(name, str(tmp_path), 24, 24, 2)
+    dump = str(tmp_path / "tables.bin")
+    monkeypatch.setenv("SLRGPU_DROPIN_DUMP", dump)
+    run_slr_gpu(path)
+    monkeypatch.delenv("SLRGPU_DROPIN_DUMP")
+    desc, keep = _load_table_dump(dump)
+    with capi.stdout_to_stderr():
+        hs = capi.read_scene(path)          # only for the scene's bounding sphere
+    center = [hs.desc.world_center[i] for i in range(3)]
+    radius = hs.desc.world_radius
+    probes = ru.make_probes(center, radius, 6000, 5)
+    want = ru.run_ref_probe(path, probes)
+    n = probes.shape[0]
+    comps = [np.ascontiguousarray(probes[:, k], np.float32) for k in range(6)] + [np.zeros(n, np.float32), np.full(n, np.inf, np.float32)]
+    rb = capi.RayBatch(*[c.ctypes.data_as(capi.PF) for c in comps])
+    prim, inst, t = np.empty(n, np.uint32), np.empty(n, np.uint32), np.empty(n, np.float32)
+    u, v = np.empty(n, np.float32), np.empty(n, np.float32)
+    hb = capi.HitBatch(prim.ctypes.data_as(capi.PU32), inst.ctypes.data_as(capi.PU32), t.ctypes.data_as(capi.PF),
+                       u.ctypes.data_as(capi.PF), v.ctypes.data_as(capi.PF), None, None)
+    tn, tl = C.c_uint64(0), C.c_uint64(0)
+    rc = ou.restate_lib().slr_restate_intersect(C.byref(desc), C.byref(rb), n, C.byref(hb), C.byref(tn), C.byref(tl))
+    assert rc == 0
+    hit_ref, hit_got = want[:, 0] == 1, prim != 0xFFFFFFFF
+    assert float(np.mean(hit_ref != hit_got)) <= 0.001
+    both = hit_ref & hit_got
+    excess = np.abs(t[both] - want[both, 1]) - (2e-5 * np.abs(want[both, 1]) + 1e-6 * radius)
+    assert both.sum() >= 500 and float(excess.max()) <= 0.0, float(excess.max())
+    if name == "nested":
+        assert desc.num_instances > 0
