@@ -585,16 +585,17 @@ void GPUPathTracingRenderer::render(const Scene &scene, const RenderSettings &se
     sensor->init(W, H);
 
     GpuSceneExporter exporter(scene);
-    // SLRGPU_DROPIN_DUMP=<file>: the geometry tables as they go to slrgpu_scene_create (a debugging aid; tests/test_dropin.py
+    // SLRGPU_DROPIN_DUMP=<file>: the geometry and light tables as they go to slrgpu_scene_create (a debugging aid; tests/test_dropin.py
     // walks them on the CPU and compares the hits with the reference's own Scene::intersect on the same file)
     if (const char* dumpPath = getenv("SLRGPU_DROPIN_DUMP")) {
         if (FILE* f = fopen(dumpPath, "wb")) {
             const SlrGpuSceneDesc &d = exporter.desc;
-            const uint32_t head[4] = {0x44524F50u, d.num_bvh_nodes, d.num_leaf_records, d.num_instances};
-            fwrite(head, 4, 4, f);
+            const uint32_t head[6] = {0x44524F50u, d.num_bvh_nodes, d.num_leaf_records, d.num_instances, d.num_lights, d.num_top_lights};
+            fwrite(head, 4, 6, f);
             fwrite(d.bvh_nodes, sizeof(SlrGpuBvhNode), d.num_bvh_nodes, f);
             fwrite(d.leaf_records, sizeof(SlrGpuLeafRecord), d.num_leaf_records, f);
             fwrite(d.instances, sizeof(SlrGpuInstance), d.num_instances, f);
+            fwrite(d.lights, sizeof(SlrGpuLight), d.num_lights, f);
             fclose(f);
         }
     }

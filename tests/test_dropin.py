@@ -128,14 +128,14 @@ def test_dropin_bidirectional_renderer(tmp_path):
 
 
 def _load_table_dump(path):
-    """The file SLRGPU_DROPIN_DUMP writes: u32 magic, nodes, leaf records, instances, then the three tables."""
+    """The file SLRGPU_DROPIN_DUMP writes: u32 magic, nodes, leaf records, instances, lights, top-level lights, then the four tables."""
     import ctypes as C
     raw = open(path, "rb").read()
-    magic, nn, nl, ni = np.frombuffer(raw[:16], np.uint32)
+    magic, nn, nl, ni, nlt, ntop = np.frombuffer(raw[:24], np.uint32)
     assert magic == 0x44524F50
-    off = 16
+    off = 24
     tables = []
-    for cls, n in ((capi.BvhNode, int(nn)), (capi.LeafRecord, int(nl)), (capi.Instance, int(ni))):
+    for cls, n in ((capi.BvhNode, int(nn)), (capi.LeafRecord, int(nl)), (capi.Instance, int(ni)), (capi.Light, int(nlt))):
         size = C.sizeof(cls) * n
         arr = (cls * max(n, 1))()
         C.memmove(arr, raw[off:off + size], size)
@@ -147,6 +147,7 @@ def _load_table_dump(path):
     d.bvh_nodes, d.num_bvh_nodes = C.cast(tables[0], C.POINTER(capi.BvhNode)), int(nn)
     d.leaf_records, d.num_leaf_records = C.cast(tables[1], C.POINTER(capi.LeafRecord)), int(nl)
     d.instances, d.num_instances = C.cast(tables[2], C.POINTER(capi.Instance)), int(ni)
+    d.lights, d.num_lights, d.num_top_lights = C.cast(tables[3], C.POINTER(capi.Light)), int(nlt), int(ntop)
     return d, tables
 
 
@@ -188,5 +189,21 @@ def test_exported_tables_give_the_reference_hits(name, tmp_path, monkeypatch):
     both = hit_ref & hit_got
     excess = np.abs(t[both] - want[both, 1]) - (2e-5 * np.abs(want[both, 1]) + 1e-6 * radius)
     assert both.sum() >= 500 and float(excess.max()) <= 0.0, float(excess.max())
+    # light selection: every emitting triangle has importance 1 and an aggregate's importance is the sum of its entries'
+    # (SurfaceObject.cpp:232-252), so whatever the nesting, each emitting triangle placement must be chosen with the same
+    # probability: the product of the pmfs along its chain
+    probs = []
+    for k in range(desc.num_top_lights):
+        l = desc.lights[k]
+        if l.object >> 31:
+            ins = desc.instances[l.object & 0x7FFFFFFF]
+            assert ins.light_index == k and ins.num_lights > 0
+            for j in range(ins.num_lights):
+                lj = desc.lights[ins.light_base + j]
+                assert not (lj.object >> 31), "one level on the device: a nested light list holds triangles only"
+                probs.append(l.pmf * lj.pmf)
+        else:
+            probs.append(l.pmf)
+    assert probs and abs(sum(probs) - 1.0) < 1e-5 and np.allclose(probs, 1.0 / len(probs), rtol=1e-5)
     if name == "nested":
-        assert desc.num_instances > 0
+        assert desc.num_instances > 0 and len(probs) == 8          # 2 + 3 x 2 emitting triangle placements, as tests/test_nested_instancing.py
